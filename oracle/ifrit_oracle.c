@@ -1,0 +1,786 @@
+/* ifrit_oracle.c — TEST INFRASTRUCTURE ONLY.  See ifrit_oracle.h for the rules.
+ *
+ * A scalar CPU restatement of the softgraphics tile-raster path, written for
+ * clarity, not speed: every triangle is rasterised by brute force over its
+ * bounding box with exact 64-bit integer edge functions.  The product (the
+ * CUDA library) must reproduce its coverage, primitive-id and depth outputs
+ * bit-for-bit and its colour within 1/255.
+ *
+ * Build: see oracle/Makefile (-ffp-contract=off: every fused multiply-add in
+ * this file is an explicit fmaf(), so the float op sequence is the spec).
+ */
+#include "ifrit_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define SUBPIX 256              /* 24.8 fixed point */
+#define SNAP_LIMIT 268435456.0f /* 2^28 sub-pixel units: guard band of the snapping grid */
+
+/* ------------------------------------------------------------------------- */
+/* MSAA sample positions, in 1/16 pixel.  Restates cMsaaSampleSequenceAgg
+ * (CU:223-234) and its indexing `S-1+k` (CU:932-933): note that for 8x the
+ * table yields the FIRST EIGHT ENTRIES OF THE 16x PATTERN, and 16x reads eight
+ * zero-initialised entries past the initialiser list; both are replicated. */
+static const int8_t k_sample_agg[31][2] = {
+    {8, 8},
+    {4, 4}, {12, 12},
+    {6, 2}, {14, 6}, {2, 10}, {10, 14},
+    {9, 9}, {7, 5}, {5, 10}, {12, 7}, {3, 6}, {10, 13}, {13, 11}, {11, 3},
+    {6, 14}, {8, 1}, {4, 2}, {2, 12}, {0, 8}, {15, 4}, {14, 15}, {1, 0},
+    {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}};
+
+static void sample_offset16(const orc_state* st, int k, int* ox, int* oy) {
+    if (st->convention == ORC_CONV_CPU) { /* WK:1043-1055: the pixel's integer corner */
+        *ox = 0; *oy = 0; return;
+    }
+    *ox = k_sample_agg[st->msaa - 1 + k][0];
+    *oy = k_sample_agg[st->msaa - 1 + k][1];
+}
+
+/* ------------------------------------------------------------------------- */
+/* Vertex stage: vertexProcessingKernel CU:330 / vertexProcessing WK:432.      */
+int orc_vertex_stage(int vs_id, const void* uniforms, const uint8_t* vb, int stride,
+                     const int32_t* attr_offsets, int nattr, int nvary, int nverts,
+                     orc_f4* pos, orc_f4* vary) {
+    const float* m = (const float*)uniforms;
+    if (nvary > nattr - 1) return -1;
+    for (int v = 0; v < nverts; v++) {
+        const uint8_t* base = vb + (size_t)v * stride;
+        orc_f4 a0;
+        memcpy(&a0, base + attr_offsets[0], sizeof a0);
+        if (vs_id == ORC_VS_MVP) {
+            orc_f4 p;
+            p.x = fmaf(m[3], a0.w, fmaf(m[2], a0.z, fmaf(m[1], a0.y, m[0] * a0.x)));
+            p.y = fmaf(m[7], a0.w, fmaf(m[6], a0.z, fmaf(m[5], a0.y, m[4] * a0.x)));
+            p.z = fmaf(m[11], a0.w, fmaf(m[10], a0.z, fmaf(m[9], a0.y, m[8] * a0.x)));
+            p.w = fmaf(m[15], a0.w, fmaf(m[14], a0.z, fmaf(m[13], a0.y, m[12] * a0.x)));
+            pos[v] = p;
+        } else if (vs_id == ORC_VS_PASSTHROUGH) {
+            pos[v] = a0;
+        } else
+            return -2;
+        for (int k = 0; k < nvary; k++)
+            memcpy(&vary[(size_t)v * nvary + k], base + attr_offsets[k + 1], sizeof(orc_f4));
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------- */
+/* Clip + viewport + snap + cull: devGeometryCullClip CU:1343-1491,
+ * geometryClippingKernel CU:1493-1524; CPU convention: triangleHomogeneousClip
+ * WK:136-276, geometryProcessing WK:738-770, directTriangleSetup WK:503-727.  */
+typedef struct { orc_f4 p; float bx, by; } clipv;
+
+static clipv clip_lerp(const clipv* a, const clipv* b, float t) {
+    clipv r;
+    r.p.x = fmaf(b->p.x - a->p.x, t, a->p.x);
+    r.p.y = fmaf(b->p.y - a->p.y, t, a->p.y);
+    r.p.z = fmaf(b->p.z - a->p.z, t, a->p.z);
+    r.p.w = fmaf(b->p.w - a->p.w, t, a->p.w);
+    r.bx = fmaf(b->bx - a->bx, t, a->bx);
+    r.by = fmaf(b->by - a->by, t, a->by);
+    return r;
+}
+
+static int32_t snap(float ndc, float half_extent_subpix) {
+    float f = fmaf(ndc, half_extent_subpix, half_extent_subpix); /* (ndc*0.5+0.5)*extent*256 */
+    f = fminf(fmaxf(f, -SNAP_LIMIT), SNAP_LIMIT);
+    return (int32_t)rintf(f); /* round half to even */
+}
+
+int orc_assemble(const orc_state* st, const orc_f4* pos, const int32_t* idx, int ntri, orc_tri* out) {
+    const int cpu = st->convention == ORC_CONV_CPU;
+    const float hw = 128.0f * (float)st->width, hh = 128.0f * (float)st->height;
+    const int64_t wmax = (int64_t)st->width * SUBPIX, hmax = (int64_t)st->height * SUBPIX;
+    int n = 0;
+    for (int t = 0; t < ntri; t++) {
+        clipv src[3];
+        for (int j = 0; j < 3; j++) {
+            src[j].p = pos[idx[3 * t + j]];
+            src[j].bx = (j == 0) ? 1.0f : 0.0f;
+            src[j].by = (j == 1) ? 1.0f : 0.0f;
+        }
+        const float w0 = src[0].p.w, w1 = src[1].p.w, w2 = src[2].p.w;
+        clipv poly[6];
+        int np = 0, clipped = 0;
+        if (!cpu) {
+            if (w0 < 0 && w1 < 0 && w2 < 0) continue; /* CU:1521 */
+        } else {
+            const float mx = fmaxf(w0, fmaxf(w1, w2)), mn = fminf(w0, fminf(w1, w2));
+            if (!(mx * mn < 0) && !(mn > 0)) continue; /* WK:752-767 */
+        }
+        /* Sutherland–Hodgman against the single w plane, walking v1->v2->v3->v1 and
+         * emitting into the list in the order (…, next) — CU:1361-1396 / WK:153-176 */
+        {
+            clipv pc = src[0];
+            for (int j = 0; j < 3; j++) {
+                const clipv* pn = &src[(j + 1) % 3];
+                const float npc = -pc.p.w, npn = -pn->p.w;
+                if (npc * npn < 0) {
+                    const float plane = cpu ? 1.0f : 1e-3f;
+                    const float t_ = (pc.p.w - plane) / (pc.p.w - pn->p.w);
+                    poly[np++] = clip_lerp(&pc, pn, t_);
+                    clipped = 1;
+                }
+                if (cpu ? (npn < 1e-8f) : (npn < 0)) poly[np++] = *pn;
+                pc = *pn;
+            }
+        }
+        if (np < 3) continue;
+        for (int f = 0; f < np - 2; f++) {
+            const clipv* v[3] = {&poly[0], &poly[f + 1], &poly[f + 2]};
+            orc_tri r;
+            r.prim = t; r.fan = f; r.clipped = clipped;
+            float zmin = INFINITY, zmax = -INFINITY;
+            for (int j = 0; j < 3; j++) {
+                const float iw = 1.0f / v[j]->p.w; /* CU:1403 */
+                r.IW[j] = iw;
+                r.Z[j] = v[j]->p.z * iw;
+                r.X[j] = snap(v[j]->p.x * iw, hw);
+                r.Y[j] = snap(v[j]->p.y * iw, hh);
+                r.bary[j][0] = v[j]->bx;
+                r.bary[j][1] = v[j]->by;
+                zmin = fminf(zmin, r.Z[j]);
+                zmax = fmaxf(zmax, r.Z[j]);
+            }
+            /* screen-bbox reject: devViewSpaceClip CU:278-285 / triangleFrustumClip WK:277-299 */
+            int64_t minx = r.X[0], maxx = r.X[0], miny = r.Y[0], maxy = r.Y[0];
+            for (int j = 1; j < 3; j++) {
+                if (r.X[j] < minx) minx = r.X[j];
+                if (r.X[j] > maxx) maxx = r.X[j];
+                if (r.Y[j] < miny) miny = r.Y[j];
+                if (r.Y[j] > maxy) maxy = r.Y[j];
+            }
+            if (maxx < 0 || maxy < 0 || minx > wmax || miny > hmax) continue;
+            if (cpu && (zmax < 0.0f || zmin > 1.0f)) continue; /* WK:283-286 */
+            /* facing: devTriangleCull CU:271-276; d = X1(Y2-Y3)+X2(Y3-Y1)+X3(Y1-Y2), exact */
+            const int64_t d = (int64_t)(r.X[1] - r.X[0]) * (r.Y[2] - r.Y[0]) -
+                              (int64_t)(r.X[2] - r.X[0]) * (r.Y[1] - r.Y[0]);
+            if (d == 0) continue; /* zero area covers no sample under the strict rule */
+            int swap = 0;
+            switch (st->cull_mode) { /* CU:1433-1462 */
+                case ORC_CULL_BACK: if (d < 0) continue; break;
+                case ORC_CULL_FRONT: if (d > 0) continue; swap = 1; break;
+                case ORC_CULL_NONE: swap = d < 0; break;
+                default: continue;
+            }
+            if (swap) {
+#define SWP(T, a, b) do { T _t = a; a = b; b = _t; } while (0)
+                SWP(int32_t, r.X[0], r.X[2]); SWP(int32_t, r.Y[0], r.Y[2]);
+                SWP(float, r.Z[0], r.Z[2]); SWP(float, r.IW[0], r.IW[2]);
+                SWP(float, r.bary[0][0], r.bary[2][0]); SWP(float, r.bary[0][1], r.bary[2][1]);
+#undef SWP
+            }
+            /* contribution cull (CU:1464-1475, WK:258-262, WK:623-636): restated exactly as
+             * "no sample row or column lies strictly inside the bounding box", which is
+             * what the reference's rounding rules approximate.  It never changes the
+             * image (a sample on the bbox boundary cannot be strictly inside). */
+            r.slot = (f == 0) ? t : ntri + t;
+            out[n++] = r;
+        }
+    }
+    return n;
+}
+
+/* ------------------------------------------------------------------------- */
+/* Texture sampling: SB:97-295.                                               */
+static void level_info(const orc_texture* t, int layer, int lod, int* w, int* h, int64_t* off) {
+    int64_t o = 0;
+    int lw = t->width, lh = t->height;
+    for (int i = 0; i < lod; i++) { /* textureLodPtroffImpl SB:97-105 */
+        o += (int64_t)lw * lh * t->layers;
+        lw = (lw + 1) >> 1;
+        lh = (lh + 1) >> 1;
+    }
+    *w = lw; *h = lh; *off = o + (int64_t)lw * lh * layer;
+}
+
+static float addr_mode(int mode, float c, int size, int* border) {
+    const float s = (float)size;
+    switch (mode) { /* SB:116-160 */
+        case ORC_ADDR_REPEAT:
+            if (c < 0) c += s;
+            c = fmodf(c, s);
+            if (c < 0) c += s; /* safety for uv < -1 (reference would index out of bounds) */
+            break;
+        case ORC_ADDR_MIRRORED_REPEAT:
+            if (c < 0) c += 2 * s;
+            c = fmodf(c, 2 * s);
+            if (c < 0) c += 2 * s;
+            c = fminf(c, 2 * s - c);
+            break;
+        case ORC_ADDR_CLAMP_TO_EDGE:
+            c = (c >= s - 1.0f) ? s - 1.0f : ((c <= 0.0f) ? 0.0f : c);
+            break;
+        case ORC_ADDR_CLAMP_TO_BORDER:
+            if (c >= s || c < 0.0f) *border = 1;
+            break;
+        case ORC_ADDR_MIRROR_CLAMP_TO_EDGE: /* mirrorclamp (sic) ShaderOpsCuda.cuh:36-39 */
+            c = (c >= s - 1.0f) ? 0.0f : ((c <= 0.0f) ? s - 1.0f : c);
+            break;
+    }
+    return c;
+}
+
+static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+static void texel(const orc_texture* t, int64_t off, int w, int x, int y, float o[4]) {
+    memcpy(o, t->data + 4 * (off + (int64_t)y * w + x), 16);
+}
+
+/* textureImplLegacy SB:106-182 (lod clamped to the allocated chain: the reference reads
+ * past the allocation for lod > mipLevels) */
+static void sample_level(const orc_texture* t, const orc_sampler* s, int layer, float u, float v,
+                         int offx, int offy, int lod, float out[4]) {
+    int w, h;
+    int64_t off;
+    lod = clampi(lod, 0, t->mip_levels);
+    level_info(t, layer, lod, &w, &h, &off);
+    float cx = fmaf(u, (float)(w - 1), (float)offx);
+    float cy = fmaf(v, (float)(h - 1), (float)offy);
+    int border = 0;
+    cx = addr_mode(s->addr_u, cx, w, &border);
+    if (!border) cy = addr_mode(s->addr_v, cy, h, &border);
+    if (border) {
+        const float b = s->border == 0 ? 0.0f : 1.0f;
+        out[0] = b; out[1] = b; out[2] = b; out[3] = 1.0f;
+        return;
+    }
+    if (s->filter == ORC_FILTER_NEAREST) {
+        int px = (int)roundf(cx), py = (int)roundf(cy);
+        px = clampi(px % w, 0, w - 1);
+        py = clampi(py % h, 0, h - 1);
+        texel(t, off, w, px, py, out);
+    } else {
+        int px = clampi((int)cx, 0, w - 1), py = clampi((int)cy, 0, h - 1);
+        const float fx = cx - (float)px, fy = cy - (float)py;
+        const int px1 = px + 1 < w - 1 ? px + 1 : w - 1, py1 = py + 1 < h - 1 ? py + 1 : h - 1;
+        float c00[4], c01[4], c10[4], c11[4];
+        texel(t, off, w, px, py, c00);
+        texel(t, off, w, px1, py, c01);
+        texel(t, off, w, px, py1, c10);
+        texel(t, off, w, px1, py1, c11);
+        for (int c = 0; c < 4; c++) {
+            const float a = fmaf(c01[c] - c00[c], fx, c00[c]);
+            const float b = fmaf(c11[c] - c10[c], fx, c10[c]);
+            out[c] = fmaf(b - a, fy, a);
+        }
+    }
+}
+
+/* textureImplLod SB:210-218 */
+static void sample_trilinear(const orc_texture* t, const orc_sampler* s, int layer, float u, float v,
+                             int offx, int offy, float lod, float out[4]) {
+    const int lo = (int)floorf(lod);
+    const float d = lod - (float)lo;
+    float a[4], b[4];
+    sample_level(t, s, layer, u, v, offx, offy, lo, a);
+    sample_level(t, s, layer, u, v, offx, offy, lo + 1, b);
+    for (int c = 0; c < 4; c++) out[c] = fmaf(b[c] - a[c], d, a[c]);
+}
+
+/* textureImplAdaptiveLod SB:233-243 — `dyI.y` uses dx.y (sic, SB:237), replicated */
+static void sample_adaptive(const orc_texture* t, const orc_sampler* s, float u, float v,
+                            const float dx[2], const float dy[2], float bias, float out[4]) {
+    const float W = (float)t->width, H = (float)t->height;
+    const float ax = dx[0] * W, ay = dx[1] * H;
+    const float bx = dy[0] * W, by = dx[1] * H;
+    const float a2 = fmaf(ay, ay, ax * ax), b2 = fmaf(by, by, bx * bx);
+    const float d = fmaxf(a2, b2);
+    const float lod = fmaxf(0.0f, fmaf(0.5f, log2f(d), bias));
+    sample_trilinear(t, s, 0, u, v, 0, 0, lod, out);
+}
+
+/* textureImplAnisotropicFilter SB:244-272, called as (du = ddx(uv), dv = ddy(uv)) SB:285-293 */
+static void sample_aniso(const orc_texture* t, const orc_sampler* s, float u, float v,
+                         const float du[2], const float dv[2], float bias, float out[4]) {
+    const float dudx = du[0], dudy = du[1], dvdx = dv[0], dvdy = dv[1];
+    const float px = sqrtf(fmaf(dvdx, dvdx, dudx * dudx)) * (float)t->width;
+    const float py = sqrtf(fmaf(dvdy, dvdy, dudy * dudy)) * (float)t->height;
+    const float pmax = fmaxf(px, py), pmin = fminf(px, py);
+    const int max_aniso = (int)s->max_aniso;
+    const int n = (int)fmax(1.0, fmin((double)ceilf(pmax / pmin) + 1e-3, (double)max_aniso + 1e-3));
+    const float lambda = fmaxf(0.0f, log2f(pmax / (float)n));
+    const float ddu = (px > py) ? dudx : dudy, ddv = (px > py) ? dvdx : dvdy;
+    float sum[4] = {0, 0, 0, 0};
+    for (int i = 0; i < n; i++) {
+        const float tt = (float)i / (float)(n + 1) - 0.5f;
+        float r[4];
+        sample_trilinear(t, s, 0, fmaf(ddu, tt, u), fmaf(ddv, tt, v), 0, 0, lambda + bias, r);
+        for (int c = 0; c < 4; c++) sum[c] += r[c];
+    }
+    for (int c = 0; c < 4; c++) out[c] = sum[c] / (float)n;
+}
+
+/* textureCubeCoordConversion SB:184-208, textureCubeImplLod SB:220-231 */
+static void sample_cube(const orc_texture* t, const orc_sampler* s, float x, float y, float z,
+                        float lod, float out[4]) {
+    const float ax = fabsf(x), ay = fabsf(y), az = fabsf(z);
+    float u, v, norm;
+    int face;
+    if (az >= ax && az >= ay) {
+        face = z < 0.0f ? 5 : 4; norm = 0.5f / az; u = z < 0.0f ? -x : x; v = -y;
+    } else if (ay >= ax) {
+        face = y < 0.0f ? 3 : 2; norm = 0.5f / ay; u = x; v = y < 0.0f ? -z : z;
+    } else {
+        face = x < 0.0f ? 1 : 0; norm = 0.5f / ax; u = x < 0.0f ? z : -z; v = -y;
+    }
+    u = fmaf(u, norm, 0.5f);
+    v = fmaf(v, norm, 0.5f);
+    sample_trilinear(t, s, face, u, v, 0, 0, lod, out);
+}
+
+void orc_texture_lod(const orc_texture* t, const orc_sampler* s, float u, float v, float lod, float out[4]) {
+    sample_trilinear(t, s, 0, u, v, 0, 0, lod, out);
+}
+void orc_texture_grad(const orc_texture* t, const orc_sampler* s, float u, float v,
+                      const float ddx[2], const float ddy[2], float bias, float out[4]) {
+    if (s->aniso_enable) sample_aniso(t, s, u, v, ddx, ddy, bias, out);
+    else sample_adaptive(t, s, u, v, ddx, ddy, bias, out);
+}
+void orc_texture_cube_lod(const orc_texture* t, const orc_sampler* s, float x, float y, float z,
+                          float lod, float out[4]) {
+    sample_cube(t, s, x, y, z, lod, out);
+}
+
+int64_t orc_texture_total_texels(int w, int h, int mip_levels, int layers) {
+    int64_t n = 0;
+    for (int i = 0; i <= mip_levels; i++) {
+        n += (int64_t)w * h * layers;
+        w = (w + 1) >> 1;
+        h = (h + 1) >> 1;
+    }
+    return n;
+}
+
+/* invokeMipmapGeneration CUIMG:132-155 + blitImage{Bilinear,Nearest}Kernel CUIMG:36-86 */
+void orc_generate_mipmap(float* data, int w, int h, int mip_levels, int layers, int filter) {
+    orc_texture t = {data, w, h, mip_levels, layers};
+    int sw = w, sh = h;
+    for (int l = 0; l < mip_levels; l++) {
+        const int dw = (sw + 1) >> 1, dh = (sh + 1) >> 1;
+        for (int layer = 0; layer < layers; layer++) {
+            int a, b;
+            int64_t soff, doff;
+            level_info(&t, layer, l, &a, &b, &soff);
+            level_info(&t, layer, l + 1, &a, &b, &doff);
+            for (int y = 0; y < dh; y++)
+                for (int x = 0; x < dw; x++) {
+                    const float px = (float)x / (float)dw, py = (float)y / (float)dh;
+                    const float sx = px * (float)sw, sy = py * (float)sh;
+                    float* dst = data + 4 * (doff + (int64_t)y * dw + x);
+                    if (filter == ORC_FILTER_LINEAR) {
+                        const int ix = (int)sx, iy = (int)sy;
+                        const float fx = sx - (float)ix, fy = sy - (float)iy;
+                        const int ix1 = ix + 1 < sw - 1 ? ix + 1 : sw - 1, iy1 = iy + 1 < sh - 1 ? iy + 1 : sh - 1;
+                        const float* c00 = data + 4 * (soff + (int64_t)iy * sw + ix);
+                        const float* c01 = data + 4 * (soff + (int64_t)iy * sw + ix1);
+                        const float* c10 = data + 4 * (soff + (int64_t)iy1 * sw + ix);
+                        const float* c11 = data + 4 * (soff + (int64_t)iy1 * sw + ix1);
+                        for (int c = 0; c < 4; c++) {
+                            const float p = fmaf(c01[c] - c00[c], fx, c00[c]);
+                            const float q = fmaf(c11[c] - c10[c], fx, c10[c]);
+                            dst[c] = fmaf(q - p, fy, p);
+                        }
+                    } else {
+                        int ix = (int)roundf(sx), iy = (int)roundf(sy);
+                        if (ix > sw - 1) ix = sw - 1;
+                        if (iy > sh - 1) iy = sh - 1;
+                        memcpy(dst, data + 4 * (soff + (int64_t)iy * sw + ix), 16);
+                    }
+                }
+        }
+        sw = dw; sh = dh;
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* Fragment shaders of the registry (ids shared with include/ifrit_b200.h).   */
+typedef struct {
+    const float* u;            /* uniform block (buffer slot 0) */
+    const orc_texture* tex;
+    const orc_sampler* samp;
+} fs_env;
+
+static void run_fs(int fs_id, const fs_env* e, const orc_f4* v, const orc_f4* ddx, const orc_f4* ddy,
+                   int prim, int fan, float out[4]) {
+    switch (fs_id) {
+        case ORC_FS_VARYING0:
+            out[0] = v[0].x; out[1] = v[0].y; out[2] = v[0].z; out[3] = v[0].w; break;
+        case ORC_FS_NORMAL_COLOR: /* DemoFragmentShaderCuda, SG/demo/shader/DefaultDemoShaders.cu */
+            out[0] = fmaf(v[0].x, 0.5f, 0.5f); out[1] = fmaf(v[0].y, 0.5f, 0.5f);
+            out[2] = fmaf(v[0].z, 0.5f, 0.5f); out[3] = 0.5f; break;
+        case ORC_FS_PRIM_ID:
+            out[0] = (float)prim; out[1] = (float)fan; out[2] = 0.0f; out[3] = 1.0f; break;
+        case ORC_FS_TEXTURED:
+        case ORC_FS_TEXTURED_LOD0: {
+            float c[4];
+            if (fs_id == ORC_FS_TEXTURED) {
+                const float dx[2] = {ddx[1].x, ddx[1].y}, dy[2] = {ddy[1].x, ddy[1].y};
+                orc_texture_grad(&e->tex[0], &e->samp[0], v[1].x, v[1].y, dx, dy, e->u[20], c);
+            } else
+                orc_texture_lod(&e->tex[0], &e->samp[0], v[1].x, v[1].y, 0.0f, c);
+            const float nx = v[0].x, ny = v[0].y, nz = v[0].z;
+            const float len = sqrtf(fmaf(nz, nz, fmaf(ny, ny, nx * nx)));
+            float ndl = fmaf(nz, e->u[18], fmaf(ny, e->u[17], nx * e->u[16])) / len;
+            ndl = fmaxf(ndl, 0.2f);
+            out[0] = c[0] * ndl; out[1] = c[1] * ndl; out[2] = c[2] * ndl; out[3] = 1.0f;
+            break;
+        }
+        case ORC_FS_SKYBOX:
+            orc_texture_cube_lod(&e->tex[0], &e->samp[0], v[0].x, v[0].y, v[0].z, e->u[20], out); break;
+        case ORC_FS_DERIV_VIS:
+            out[0] = ddx[1].x * e->u[21]; out[1] = ddx[1].y * e->u[21];
+            out[2] = ddy[1].x * e->u[21]; out[3] = ddy[1].y * e->u[21]; break;
+        default: out[0] = out[1] = out[2] = out[3] = 0.0f;
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* Visibility keys.  Depth-test outcome per sample is the minimum of a 64-bit
+ * key over all covering triangles, which makes the result independent of the
+ * order triangles are processed in (pixelTaggingExecKernel CU:1901-2004 is
+ * order dependent; its `ALWAYS keeps the lowest primitive id` rule, CU:1985-1992,
+ * is kept and extended to break every tie deterministically).                */
+static uint32_t mono(float d) {
+    d = d + 0.0f; /* -0 -> +0 */
+    uint32_t b;
+    memcpy(&b, &d, 4);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+static float unmono(uint32_t m) {
+    uint32_t b = (m & 0x80000000u) ? (m & 0x7fffffffu) : ~m;
+    float d;
+    memcpy(&d, &b, 4);
+    return d;
+}
+static uint32_t fbits(float d) { uint32_t b; memcpy(&b, &d, 4); return b; }
+
+static uint64_t key_init(int func, float d0) {
+    switch (func) {
+        case ORC_CMP_LESS: return ((uint64_t)mono(d0) << 32) | 0u;
+        case ORC_CMP_LESS_OR_EQUAL: return ((uint64_t)mono(d0) << 32) | 0xffffffffu;
+        case ORC_CMP_GREATER: return ((uint64_t)(~mono(d0)) << 32) | 0u;
+        case ORC_CMP_GREATER_OR_EQUAL: return ((uint64_t)(~mono(d0)) << 32) | 0xffffffffu;
+        default: return ((uint64_t)0xffffffffu << 32) | fbits(d0 + 0.0f); /* ALWAYS / EQUAL */
+    }
+}
+/* returns 0 when the fragment cannot pass at all */
+static int key_make(int func, float d, float d0, uint32_t slot, uint64_t* k) {
+    switch (func) {
+        case ORC_CMP_LESS: *k = ((uint64_t)mono(d) << 32) | (slot + 1u); return 1;
+        case ORC_CMP_LESS_OR_EQUAL: *k = ((uint64_t)mono(d) << 32) | ~(slot + 1u); return 1;
+        case ORC_CMP_GREATER: *k = ((uint64_t)(~mono(d)) << 32) | (slot + 1u); return 1;
+        case ORC_CMP_GREATER_OR_EQUAL: *k = ((uint64_t)(~mono(d)) << 32) | ~(slot + 1u); return 1;
+        case ORC_CMP_ALWAYS: *k = ((uint64_t)(slot + 1u) << 32) | fbits(d + 0.0f); return 1;
+        case ORC_CMP_EQUAL:
+            if (!(d == d0)) return 0;
+            *k = ((uint64_t)(slot + 1u) << 32) | fbits(d + 0.0f); return 1;
+        default: return 0; /* NEVER; NOT_EQUAL is order dependent and unsupported */
+    }
+}
+static int key_slot(int func, uint64_t k, uint32_t* slot) {
+    uint32_t s;
+    switch (func) {
+        case ORC_CMP_LESS: case ORC_CMP_GREATER: s = (uint32_t)k; if (s == 0) return 0; *slot = s - 1; return 1;
+        case ORC_CMP_LESS_OR_EQUAL: case ORC_CMP_GREATER_OR_EQUAL:
+            s = ~(uint32_t)k; if (s == 0) return 0; *slot = s - 1; return 1;
+        default: s = (uint32_t)(k >> 32); if (s == 0xffffffffu) return 0; *slot = s - 1; return 1;
+    }
+}
+static float key_depth(int func, uint64_t k) {
+    switch (func) {
+        case ORC_CMP_LESS: case ORC_CMP_LESS_OR_EQUAL: return unmono((uint32_t)(k >> 32));
+        case ORC_CMP_GREATER: case ORC_CMP_GREATER_OR_EQUAL: return unmono(~(uint32_t)(k >> 32));
+        default: { uint32_t b = (uint32_t)k; float d; memcpy(&d, &b, 4); return d; }
+    }
+}
+
+static int scissor_pass(const orc_state* st, int x, int y) { /* CU:1946-1957, CU:3345-3357 */
+    if (!st->scissor_enable || st->nscissor == 0) return 1;
+    for (int i = 0; i < st->nscissor; i++) {
+        const float* s = st->scissor[i];
+        if ((float)x >= s[0] && (float)x <= s[0] + s[2] && (float)y >= s[1] && (float)y <= s[1] + s[3]) return 1;
+    }
+    return 0;
+}
+
+void orc_clear(const orc_state* st, float* color, float* depth) { /* CU:3337-3391 */
+    for (int y = 0; y < st->height; y++)
+        for (int x = 0; x < st->width; x++) {
+            if (!scissor_pass(st, x, y)) continue;
+            const size_t i = (size_t)y * st->width + x;
+            memcpy(color + 4 * i, st->clear_color, 16);
+            depth[i] = st->clear_depth;
+        }
+}
+
+/* exact edge functions at a point given in sub-pixel units; E_i > 0 for all i <=> inside
+ * (strict `<` of CU:951-953, no top-left rule) */
+static void edges_at(const orc_tri* r, int64_t sx, int64_t sy, int64_t e[3]) {
+    /* e[0] is opposite vertex 0 (edge v1->v2), e[1] opposite vertex 1, e[2] opposite vertex 2 */
+    e[0] = (int64_t)(r->X[2] - r->X[1]) * (sy - r->Y[1]) - (int64_t)(r->Y[2] - r->Y[1]) * (sx - r->X[1]);
+    e[1] = (int64_t)(r->X[0] - r->X[2]) * (sy - r->Y[2]) - (int64_t)(r->Y[0] - r->Y[2]) * (sx - r->X[2]);
+    e[2] = (int64_t)(r->X[1] - r->X[0]) * (sy - r->Y[0]) - (int64_t)(r->Y[1] - r->Y[0]) * (sx - r->X[0]);
+}
+
+/* screen-space barycentrics at the INTEGER pixel (px,py): the reference evaluates depth and
+ * attributes at the pixel corner while coverage is taken at the sample (CU:1948 vs CU:934);
+ * replicated.  beta_i = E_i(p) / d, from the exact integer edge functions. */
+static void bary_at(const orc_tri* r, int px, int py, float beta[3]) {
+    int64_t e[3];
+    edges_at(r, (int64_t)px * SUBPIX, (int64_t)py * SUBPIX, e);
+    const int64_t d = (int64_t)(r->X[1] - r->X[0]) * (r->Y[2] - r->Y[0]) -
+                      (int64_t)(r->X[2] - r->X[0]) * (r->Y[1] - r->Y[0]);
+    const float ar = 1.0f / (float)d;
+    beta[0] = (float)e[0] * ar;
+    beta[1] = (float)e[1] * ar;
+    beta[2] = (float)e[2] * ar;
+}
+static float depth_at(const orc_tri* r, const float beta[3]) { /* CU:1974-1980 */
+    return fmaf(r->Z[2], beta[2], fmaf(r->Z[1], beta[1], r->Z[0] * beta[0]));
+}
+
+/* perspective-correct attribute weights, pixelShadingExecKernel CU:2185-2196 */
+static void weights_at(const orc_tri* r, const float beta[3], float wgt[3]) {
+    float b0 = beta[0] * r->IW[0], b1 = beta[1] * r->IW[1], b2 = beta[2] * r->IW[2];
+    const float inv = 1.0f / ((b0 + b1) + b2);
+    b0 *= inv; b1 *= inv; b2 *= inv;
+    const float u = fmaf(b2, r->bary[2][0], fmaf(b1, r->bary[1][0], b0 * r->bary[0][0]));
+    const float v = fmaf(b2, r->bary[2][1], fmaf(b1, r->bary[1][1], b0 * r->bary[0][1]));
+    wgt[0] = u; wgt[1] = v; wgt[2] = 1.0f - (u + v);
+}
+
+static void interp(const orc_tri* r, int px, int py, const orc_f4* vary, int nvary, const int32_t* idx,
+                   orc_f4* out) {
+    float beta[3], w[3];
+    bary_at(r, px, py, beta);
+    weights_at(r, beta, w);
+    const int32_t* a = idx + 3 * (size_t)r->prim;
+    for (int k = 0; k < nvary; k++) { /* CU:2197-2215 */
+        const orc_f4 v0 = vary[(size_t)a[0] * nvary + k], v1 = vary[(size_t)a[1] * nvary + k],
+                     v2 = vary[(size_t)a[2] * nvary + k];
+        out[k].x = fmaf(v2.x, w[2], fmaf(v1.x, w[1], v0.x * w[0]));
+        out[k].y = fmaf(v2.y, w[2], fmaf(v1.y, w[1], v0.y * w[0]));
+        out[k].z = fmaf(v2.z, w[2], fmaf(v1.z, w[1], v0.z * w[0]));
+        out[k].w = fmaf(v2.w, w[2], fmaf(v1.w, w[1], v0.w * w[0]));
+    }
+}
+
+#define MAXV 4
+#define MAXS 16
+
+int orc_render(const orc_state* st, const orc_f4* pos, const orc_f4* vary, int nvary,
+               const int32_t* idx, int ntri, int fs_id, const void* uniforms,
+               const orc_texture* textures, const orc_sampler* samplers,
+               float* color, float* depth, int32_t* prim_id, int64_t* stats) {
+    const int W = st->width, H = st->height, S = st->msaa, func = st->depth_func;
+    if (nvary > MAXV || S > MAXS) return -1;
+    if (func == ORC_CMP_NOT_EQUAL) return -2;
+    orc_tri* tris = (orc_tri*)malloc(sizeof(orc_tri) * 2 * (size_t)(ntri > 0 ? ntri : 1));
+    const int ntris = orc_assemble(st, pos, idx, ntri, tris);
+    /* slot -> assembled triangle */
+    int32_t* by_slot = (int32_t*)malloc(sizeof(int32_t) * 2 * (size_t)(ntri > 0 ? ntri : 1));
+    for (int i = 0; i < 2 * ntri; i++) by_slot[i] = -1;
+    for (int i = 0; i < ntris; i++) by_slot[tris[i].slot] = i;
+
+    if (st->do_clear) orc_clear(st, color, depth);
+
+    uint64_t* keys = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)W * H * S);
+    for (size_t p = 0; p < (size_t)W * H; p++)
+        for (int s = 0; s < S; s++) keys[p * S + s] = key_init(func, depth[p]);
+
+    int64_t covered = 0, frags = 0;
+    for (int i = 0; i < ntris; i++) {
+        const orc_tri* r = &tris[i];
+        int64_t minx = r->X[0], maxx = r->X[0], miny = r->Y[0], maxy = r->Y[0];
+        for (int j = 1; j < 3; j++) {
+            if (r->X[j] < minx) minx = r->X[j];
+            if (r->X[j] > maxx) maxx = r->X[j];
+            if (r->Y[j] < miny) miny = r->Y[j];
+            if (r->Y[j] > maxy) maxy = r->Y[j];
+        }
+        int x0 = (int)(minx >> 8) - 1, x1 = (int)(maxx >> 8) + 1;
+        int y0 = (int)(miny >> 8) - 1, y1 = (int)(maxy >> 8) + 1;
+        if (x0 < 0) x0 = 0;
+        if (y0 < 0) y0 = 0;
+        if (x1 > W - 1) x1 = W - 1;
+        if (y1 > H - 1) y1 = H - 1;
+        for (int y = y0; y <= y1; y++)
+            for (int x = x0; x <= x1; x++) {
+                int mask = 0;
+                for (int s = 0; s < S; s++) {
+                    int ox, oy;
+                    sample_offset16(st, s, &ox, &oy);
+                    int64_t e[3];
+                    edges_at(r, (int64_t)x * SUBPIX + ox * 16, (int64_t)y * SUBPIX + oy * 16, e);
+                    if (e[0] > 0 && e[1] > 0 && e[2] > 0) mask |= 1 << s;
+                }
+                if (!mask) continue;
+                if (!scissor_pass(st, x, y)) continue;
+                float beta[3];
+                bary_at(r, x, y, beta);
+                const float d = depth_at(r, beta);
+                const size_t p = (size_t)y * W + x;
+                uint64_t k;
+                if (!key_make(func, d, depth[p], (uint32_t)r->slot, &k)) continue;
+                for (int s = 0; s < S; s++)
+                    if ((mask >> s) & 1) {
+                        covered++;
+                        if (k < keys[p * S + s]) keys[p * S + s] = k;
+                    }
+            }
+    }
+
+    /* shading: 2x2 quads, one FS invocation per (pixel, distinct visible triangle);
+     * every lane of the quad interpolates so that ddx/ddy exist (CU:2264-2310, SB:36-76) */
+    fs_env env = {(const float*)uniforms, textures, samplers};
+    for (int qy = 0; qy < H; qy += 2)
+        for (int qx = 0; qx < W; qx += 2) {
+            uint32_t slots[4 * MAXS];
+            int nslots = 0;
+            for (int l = 0; l < 4; l++) {
+                const int x = qx + (l & 1), y = qy + (l >> 1);
+                if (x >= W || y >= H) continue;
+                for (int s = 0; s < S; s++) {
+                    uint32_t sl;
+                    if (!key_slot(func, keys[((size_t)y * W + x) * S + s], &sl)) continue;
+                    int j = 0;
+                    while (j < nslots && slots[j] != sl) j++;
+                    if (j == nslots) slots[nslots++] = sl;
+                }
+            }
+            if (!nslots) {
+                for (int l = 0; l < 4; l++) {
+                    const int x = qx + (l & 1), y = qy + (l >> 1);
+                    if (x >= W || y >= H) continue;
+                    for (int s = 0; s < S; s++) prim_id[((size_t)y * W + x) * S + s] = -1;
+                }
+                continue;
+            }
+            /* ascending slot order */
+            for (int a = 1; a < nslots; a++) {
+                uint32_t v = slots[a];
+                int b = a - 1;
+                while (b >= 0 && slots[b] > v) { slots[b + 1] = slots[b]; b--; }
+                slots[b + 1] = v;
+            }
+            float acc[4][4], dacc[4];
+            int cnt_bg[4];
+            memset(acc, 0, sizeof acc);
+            memset(dacc, 0, sizeof dacc);
+            for (int l = 0; l < 4; l++) cnt_bg[l] = S;
+            for (int j = 0; j < nslots; j++) {
+                const orc_tri* r = &tris[by_slot[slots[j]]];
+                orc_f4 v[4][MAXV];
+                for (int l = 0; l < 4; l++) interp(r, qx + (l & 1), qy + (l >> 1), vary, nvary, idx, v[l]);
+                for (int l = 0; l < 4; l++) {
+                    const int x = qx + (l & 1), y = qy + (l >> 1);
+                    if (x >= W || y >= H) continue;
+                    int cnt = 0;
+                    for (int s = 0; s < S; s++) {
+                        uint32_t sl;
+                        const size_t si = ((size_t)y * W + x) * S + s;
+                        if (key_slot(func, keys[si], &sl) && sl == slots[j]) { cnt++; prim_id[si] = r->prim; }
+                    }
+                    if (!cnt) continue; /* helper lane */
+                    orc_f4 ddx[MAXV], ddy[MAXV];
+                    const int row = l >> 1, col = l & 1;
+                    for (int k = 0; k < nvary; k++) {
+                        const orc_f4 *xl = &v[row * 2][k], *xr = &v[row * 2 + 1][k];
+                        const orc_f4 *yt = &v[col][k], *yb = &v[2 + col][k];
+                        ddx[k].x = xr->x - xl->x; ddx[k].y = xr->y - xl->y; ddx[k].z = xr->z - xl->z; ddx[k].w = xr->w - xl->w;
+                        ddy[k].x = yb->x - yt->x; ddy[k].y = yb->y - yt->y; ddy[k].z = yb->z - yt->z; ddy[k].w = yb->w - yt->w;
+                    }
+                    float c[4];
+                    run_fs(fs_id, &env, v[l], ddx, ddy, r->prim, r->fan, c);
+                    frags++;
+                    float beta[3];
+                    bary_at(r, x, y, beta);
+                    const float d = depth_at(r, beta);
+                    for (int ch = 0; ch < 4; ch++) acc[l][ch] = fmaf((float)cnt, c[ch], acc[l][ch]);
+                    dacc[l] = fmaf((float)cnt, d, dacc[l]);
+                    cnt_bg[l] -= cnt;
+                }
+            }
+            /* resolve: pixelMultisampleCoverageModulationKernel CU:2319-2361 (box average;
+             * uncovered samples keep the previous colour / depth) */
+            for (int l = 0; l < 4; l++) {
+                const int x = qx + (l & 1), y = qy + (l >> 1);
+                if (x >= W || y >= H) continue;
+                const size_t p = (size_t)y * W + x;
+                for (int s = 0; s < S; s++) {
+                    uint32_t sl;
+                    if (!key_slot(func, keys[p * S + s], &sl)) prim_id[p * S + s] = -1;
+                }
+                if (cnt_bg[l] == S) continue;
+                for (int ch = 0; ch < 4; ch++) {
+                    float a = acc[l][ch];
+                    if (cnt_bg[l] > 0) a = fmaf((float)cnt_bg[l], color[4 * p + ch], a);
+                    color[4 * p + ch] = a / (float)S;
+                }
+                float da = dacc[l];
+                if (cnt_bg[l] > 0) da = fmaf((float)cnt_bg[l], depth[p], da);
+                depth[p] = da / (float)S;
+            }
+        }
+    if (stats) { stats[0] = frags; stats[1] = covered; stats[2] = ntris; }
+    free(keys); free(by_slot); free(tris);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------- */
+/* Shader callbacks for the UNMODIFIED reference CPU renderer (see header).    */
+static float g_uniforms[64];
+static orc_texture g_ref_tex;
+static const orc_sampler g_ref_samp = {ORC_FILTER_LINEAR, ORC_ADDR_REPEAT, ORC_ADDR_REPEAT, ORC_ADDR_REPEAT, 0, 0, 1.0f};
+
+void orc_ref_set_uniforms(const void* data, int nbytes) {
+    memcpy(g_uniforms, data, nbytes < (int)sizeof g_uniforms ? (size_t)nbytes : sizeof g_uniforms);
+}
+void orc_ref_set_texture(const float* data, int w, int h) {
+    g_ref_tex.data = data; g_ref_tex.width = w; g_ref_tex.height = h;
+    g_ref_tex.mip_levels = 0; g_ref_tex.layers = 1;
+}
+static orc_f4 ref_mvp(const orc_f4 a0) {
+    const float* m = g_uniforms;
+    orc_f4 p;
+    p.x = fmaf(m[3], a0.w, fmaf(m[2], a0.z, fmaf(m[1], a0.y, m[0] * a0.x)));
+    p.y = fmaf(m[7], a0.w, fmaf(m[6], a0.z, fmaf(m[5], a0.y, m[4] * a0.x)));
+    p.z = fmaf(m[11], a0.w, fmaf(m[10], a0.z, fmaf(m[9], a0.y, m[8] * a0.x)));
+    p.w = fmaf(m[15], a0.w, fmaf(m[14], a0.z, fmaf(m[13], a0.y, m[12] * a0.x)));
+    return p;
+}
+void orc_ref_vs_passthrough1(const void* const* in, orc_f4* out_pos, orc_f4* const* out_vary) {
+    *out_pos = *(const orc_f4*)in[0];
+    *out_vary[0] = *(const orc_f4*)in[1];
+}
+void orc_ref_vs_passthrough2(const void* const* in, orc_f4* out_pos, orc_f4* const* out_vary) {
+    *out_pos = *(const orc_f4*)in[0];
+    *out_vary[0] = *(const orc_f4*)in[1];
+    *out_vary[1] = *(const orc_f4*)in[2];
+}
+void orc_ref_vs_mvp1(const void* const* in, orc_f4* out_pos, orc_f4* const* out_vary) {
+    *out_pos = ref_mvp(*(const orc_f4*)in[0]);
+    *out_vary[0] = *(const orc_f4*)in[1];
+}
+void orc_ref_vs_mvp2(const void* const* in, orc_f4* out_pos, orc_f4* const* out_vary) {
+    *out_pos = ref_mvp(*(const orc_f4*)in[0]);
+    *out_vary[0] = *(const orc_f4*)in[1];
+    *out_vary[1] = *(const orc_f4*)in[2];
+}
+void orc_ref_fs_varying0(const void* vary, void* color, float* depth) {
+    (void)depth;
+    memcpy(color, vary, 16);
+}
+void orc_ref_fs_normal_color(const void* vary, void* color, float* depth) {
+    (void)depth;
+    fs_env e = {g_uniforms, &g_ref_tex, &g_ref_samp};
+    run_fs(ORC_FS_NORMAL_COLOR, &e, (const orc_f4*)vary, NULL, NULL, 0, 0, (float*)color);
+}
+void orc_ref_fs_textured_lod0(const void* vary, void* color, float* depth) {
+    (void)depth;
+    fs_env e = {g_uniforms, &g_ref_tex, &g_ref_samp};
+    run_fs(ORC_FS_TEXTURED_LOD0, &e, (const orc_f4*)vary, NULL, NULL, 0, 0, (float*)color);
+}
