@@ -1,0 +1,671 @@
+// capi.cu — the C-ABI (include/ifrit_b200.h) and the host-side renderer state behind it.
+//
+// Host-side counterpart of TileRasterRendererCuda.cpp (CUHOST:1-379) and of the host half of
+// TileRasterCoreInvocationCuda.cu (CU:3549-3916), redesigned: instance-scoped state (no process-wide
+// __constant__ tables), grow-only device scratch sized from the draw instead of ~8 GB of static
+// arrays (CU:79-189, CU:248-254), a host-launched 5-kernel chain per draw instead of CDP
+// orchestrators, and status codes instead of abort().
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "common.cuh"
+#include "../../include/ifrit_b200.h"
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// cMsaaSampleSequenceAgg (CU:223-234) in 1/16 pixel; indexed S-1+k (CU:932-933)
+const int8_t kSampleAgg[31][2] = {
+    {8, 8}, {4, 4}, {12, 12}, {6, 2}, {14, 6}, {2, 10}, {10, 14},
+    {9, 9}, {7, 5}, {5, 10}, {12, 7}, {3, 6}, {10, 13}, {13, 11}, {11, 3},
+    {6, 14}, {8, 1}, {4, 2}, {2, 12}, {0, 8}, {15, 4}, {14, 15}, {1, 0},
+    {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}};
+
+}  // namespace
+
+struct iftrcuRenderer {
+    int device = 0;
+    cudaStream_t stream = nullptr, ownStream = nullptr;
+    std::string lastError;
+    bool inited = false;
+
+    // framebuffer
+    int W = 0, H = 0;
+    float4* dColor = nullptr; float* dDepth = nullptr;
+    DevBuf ownColor, ownDepth, primIds;
+    bool externalFB = false;
+    float* hColor = nullptr; float* hDepth = nullptr;
+    void* registeredHost = nullptr;
+    bool debugIds = false;
+
+    // geometry
+    const uint8_t* dVB = nullptr; DevBuf ownVB; int nverts = 0, stride = 0, nattr = 0; int attrOff[IFR_MAX_VARY + 1] = {0};
+    const int32_t* dIB = nullptr; DevBuf ownIB; int icount = 0;
+    int vsId = -1, fsId = -1, nvary = 0;
+
+    // state (defaults: TileRasterRendererCuda.h:42-47, CU:186-189)
+    int msaa = 1, depthFunc = IF_COMPARE_OP_LESS, depthTest = 1, cullMode = IF_CULL_MODE_NONE;
+    int convention = IFRIT_CONVENTION_CUDA;
+    float clearColor[4] = {0, 0, 0, 0}; float clearDepth = 1.0f;
+    int scissorEnable = 0, nScissor = 0; float scissor[IFR_MAX_SCISSOR][4];
+    int rank = 0, world = 1;
+    bool pendingClear = false, lastDrawCleared = false;
+
+    // resources
+    TexDesc tex[IFR_MAX_TEX]; DevBuf texMem[IFR_MAX_TEX]; size_t texTexels[IFR_MAX_TEX] = {0};
+    SampDesc samp[IFR_MAX_TEX];
+    DevBuf bufMem[IFR_MAX_BUF]; int bufSize[IFR_MAX_BUF] = {0};
+
+    // scratch
+    DevBuf pos, vary, rec, clipBary, tileBox, fan1List, tileCount, tileStart, tileCursor, queue, counters;
+    bool queueChecked = false;   // queue capacity verified for the current geometry / state
+    unsigned long long* hCounters = nullptr;   // pinned, 8 entries
+    bool haveDraw = false;
+    iftrcuStats stats;
+
+    int fail(int code, const char* what, const char* detail) {
+        lastError = std::string(what) + ": " + (detail ? detail : "");
+        return code;
+    }
+};
+
+#define R_CHECK(h) if (!(h)) return IFRIT_ERR_INVALID; iftrcuRenderer* r = (h); cudaSetDevice(r->device)
+
+static void build_params(iftrcuRenderer* r, DrawParams& p) {
+    memset(&p, 0, sizeof p);
+    p.color = r->dColor; p.depth = r->dDepth; p.primIds = r->debugIds ? (int32_t*)r->primIds.p : nullptr;
+    p.W = r->W; p.H = r->H;
+    p.tilesX = (r->W + IFR_TILE - 1) / IFR_TILE; p.tilesY = (r->H + IFR_TILE - 1) / IFR_TILE;
+    p.msaa = r->msaa; p.depthFunc = r->depthTest ? r->depthFunc : IF_COMPARE_OP_ALWAYS;   // CUHOST:207-218
+    p.cullMode = r->cullMode; p.convention = r->convention;
+    p.doClear = r->pendingClear ? 1 : 0;
+    memcpy(p.clearColor, r->clearColor, sizeof p.clearColor);
+    p.clearDepth = r->clearDepth;
+    p.scissorEnable = r->scissorEnable; p.nScissor = r->nScissor;
+    memcpy(p.scissor, r->scissor, sizeof p.scissor);
+    p.rank = r->rank; p.world = r->world;
+    int mnx = 255, mxx = 0, mny = 255, mxy = 0;
+    const int ns = r->convention == IFRIT_CONVENTION_CPU ? 1 : r->msaa;
+    for (int k = 0; k < r->msaa; k++) {
+        int ox = kSampleAgg[r->msaa - 1 + k][0], oy = kSampleAgg[r->msaa - 1 + k][1];
+        if (r->convention == IFRIT_CONVENTION_CPU) { ox = 0; oy = 0; }   // WK:1043-1055: pixel corner
+        p.sampX[k] = (int8_t)ox; p.sampY[k] = (int8_t)oy;
+        if (k < ns) {
+            mnx = std::min(mnx, ox * 16); mxx = std::max(mxx, ox * 16);
+            mny = std::min(mny, oy * 16); mxy = std::max(mxy, oy * 16);
+        }
+    }
+    p.sampMinX = mnx; p.sampMaxX = mxx; p.sampMinY = mny; p.sampMaxY = mxy;
+    p.vb = r->dVB; p.stride = r->stride; p.nattr = r->nattr; p.nvary = r->nvary; p.nverts = r->nverts;
+    memcpy(p.attrOff, r->attrOff, sizeof p.attrOff);
+    p.ib = r->dIB; p.ntri = r->icount / 3;
+    p.pos = (float4*)r->pos.p; p.vary = (float4*)r->vary.p;
+    p.rec = (TriVert*)r->rec.p; p.clipBary = (float*)r->clipBary.p; p.tileBox = (uint2*)r->tileBox.p;
+    p.fan1List = (uint32_t*)r->fan1List.p;
+    p.tileCount = (uint32_t*)r->tileCount.p; p.tileStart = (uint32_t*)r->tileStart.p;
+    p.tileCursor = (uint32_t*)r->tileCursor.p; p.queue = (uint32_t*)r->queue.p;
+    p.queueCap = (uint32_t)std::min<size_t>(r->queue.cap / 4, 0xffffffffu);
+    p.counters = (unsigned long long*)r->counters.p;
+    for (int i = 0; i < IFR_MAX_TEX; i++) { p.tex[i] = r->tex[i]; p.samp[i] = r->samp[i]; }
+    for (int i = 0; i < IFR_MAX_BUF; i++) p.buf[i] = (const float*)r->bufMem[i].p;
+}
+
+static int ensure_scratch(iftrcuRenderer* r) {
+    const size_t ntri = (size_t)r->icount / 3, ntiles = (size_t)((r->W + 15) / 16) * ((r->H + 15) / 16);
+    CUDA_TRY(r->pos.ensure(std::max<size_t>(1, r->nverts) * sizeof(float4)));
+    CUDA_TRY(r->vary.ensure(std::max<size_t>(1, (size_t)r->nverts * std::max(1, r->nvary)) * sizeof(float4)));
+    CUDA_TRY(r->rec.ensure(std::max<size_t>(1, 2 * ntri) * 3 * sizeof(TriVert)));
+    CUDA_TRY(r->clipBary.ensure(std::max<size_t>(1, 2 * ntri) * 6 * sizeof(float)));
+    CUDA_TRY(r->tileBox.ensure(std::max<size_t>(1, 2 * ntri) * sizeof(uint2)));
+    CUDA_TRY(r->fan1List.ensure(std::max<size_t>(1, ntri) * sizeof(uint32_t)));
+    CUDA_TRY(r->tileCount.ensure(ntiles * 4));
+    CUDA_TRY(r->tileStart.ensure((ntiles + 1) * 4));
+    CUDA_TRY(r->tileCursor.ensure(ntiles * 4));
+    CUDA_TRY(r->counters.ensure(8 * 8));
+    if (!r->queue.p) CUDA_TRY(r->queue.ensure(std::max<size_t>(ntri * 2 + ntiles, 1024) * 4));
+    if (r->debugIds) CUDA_TRY(r->primIds.ensure((size_t)r->W * r->H * r->msaa * 4));
+    return IFRIT_OK;
+}
+
+static int issue_draw(iftrcuRenderer* r, bool forceCheck) {
+    int rc = ensure_scratch(r);
+    if (rc) return rc;
+    DrawParams p;
+    build_params(r, p);
+    const size_t ntiles = (size_t)p.tilesX * p.tilesY;
+    cudaStream_t s = r->stream;
+    CUDA_TRY(cudaMemsetAsync(r->tileCount.p, 0, ntiles * 4, s));
+    CUDA_TRY(cudaMemsetAsync(r->counters.p, 0, 64, s));
+    CUDA_TRY(ifr_launch_vertex(p, r->vsId, s));
+    CUDA_TRY(ifr_launch_setup_count(p, s));
+    CUDA_TRY(ifr_launch_scan(p, s));
+    r->stats.kernel_launches += 3;
+    if (forceCheck || !r->queueChecked) {
+        // first draw with this geometry / state: size the (triangle, tile) queue exactly (one sync)
+        unsigned long long c[8];
+        CUDA_TRY(cudaMemcpyAsync(c, r->counters.p, 64, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (c[3]) {
+            CUDA_TRY(r->queue.ensure((size_t)(c[1] + c[1] / 4 + 1024) * 4));
+            CUDA_TRY(cudaMemsetAsync((char*)r->counters.p + 24, 0, 8, s));
+            build_params(r, p);
+        }
+        r->queueChecked = true;
+    }
+    CUDA_TRY(ifr_launch_fill(p, s));
+    CUDA_TRY(ifr_launch_tiles(p, r->fsId, s));
+    r->stats.kernel_launches += 2;
+    CUDA_TRY(cudaMemcpyAsync(r->hCounters, r->counters.p, 64, cudaMemcpyDeviceToHost, s));
+    r->lastDrawCleared = r->pendingClear;
+    r->pendingClear = false;
+    r->haveDraw = true;
+    r->stats.triangles_submitted = (uint64_t)p.ntri;
+    if (r->hColor && !r->externalFB)   // copy-back of the colour image, CU:3899-3909
+        CUDA_TRY(cudaMemcpyAsync(r->hColor, r->dColor, (size_t)r->W * r->H * 16, cudaMemcpyDeviceToHost, s));
+    return IFRIT_OK;
+}
+
+static int flush_clear(iftrcuRenderer* r) {
+    if (!r->pendingClear || !r->dColor) return IFRIT_OK;
+    DrawParams p;
+    build_params(r, p);
+    CUDA_TRY(ifr_launch_clear(p, r->stream));
+    r->stats.kernel_launches += 1;
+    r->pendingClear = false;
+    return IFRIT_OK;
+}
+
+static int sync_and_check(iftrcuRenderer* r) {
+    CUDA_TRY(cudaStreamSynchronize(r->stream));
+    if (r->haveDraw && r->hCounters[3]) {
+        // the queue sized from an earlier frame was too small: grow it and re-issue the draw
+        r->stats.queue_overflow = 1;
+        r->pendingClear = r->lastDrawCleared;
+        int rc = issue_draw(r, true);
+        if (rc) return rc;
+        CUDA_TRY(cudaStreamSynchronize(r->stream));
+    }
+    if (r->haveDraw) {
+        r->stats.triangles_assembled = r->hCounters[0];
+        r->stats.tile_pairs = r->hCounters[1];
+        r->stats.fragments_shaded = r->hCounters[2];
+    }
+    return IFRIT_OK;
+}
+
+static int check_types(iftrcuRenderer* r, const int* descs, int n, int maxN) {
+    if (n < 0 || n > maxN) return r->fail(IFRIT_ERR_INVALID, "attribute count", "out of range");
+    for (int i = 0; i < n; i++)
+        if (descs && descs[i] != IFTP_FLOAT4 && descs[i] != IFTP_UNDEFINED)
+            return r->fail(IFRIT_ERR_UNSUPPORTED, "attribute type", "only IFTP_FLOAT4 is supported");
+    return IFRIT_OK;
+}
+
+extern "C" {
+
+int iftrcuCreateInstance(int cudaDevice, iftrcuRenderer** out) {
+    if (!out) return IFRIT_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || cudaDevice < 0 || cudaDevice >= n) return IFRIT_ERR_CUDA;   // no CPU fallback
+    iftrcuRenderer* r = new iftrcuRenderer();
+    r->device = cudaDevice;
+    memset(r->tex, 0, sizeof r->tex); memset(r->samp, 0, sizeof r->samp); memset(&r->stats, 0, sizeof r->stats);
+    memset(r->scissor, 0, sizeof r->scissor);
+    if (cudaSetDevice(cudaDevice) != cudaSuccess || cudaStreamCreateWithFlags(&r->ownStream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMallocHost((void**)&r->hCounters, 64) != cudaSuccess) {
+        delete r;
+        return IFRIT_ERR_CUDA;
+    }
+    memset(r->hCounters, 0, 64);
+    r->stream = r->ownStream;
+    *out = r;
+    return IFRIT_OK;
+}
+
+int iftrcuDestroyInstance(iftrcuRenderer* h) {
+    R_CHECK(h);
+    cudaStreamSynchronize(r->stream);
+    if (r->registeredHost) cudaHostUnregister(r->registeredHost);
+    DevBuf* bufs[] = {&r->ownColor, &r->ownDepth, &r->primIds, &r->ownVB, &r->ownIB, &r->pos, &r->vary, &r->rec, &r->clipBary,
+                      &r->tileBox, &r->fan1List, &r->tileCount, &r->tileStart, &r->tileCursor, &r->queue, &r->counters};
+    for (DevBuf* b : bufs) b->release();
+    for (int i = 0; i < IFR_MAX_TEX; i++) r->texMem[i].release();
+    for (int i = 0; i < IFR_MAX_BUF; i++) r->bufMem[i].release();
+    if (r->hCounters) cudaFreeHost(r->hCounters);
+    if (r->ownStream) cudaStreamDestroy(r->ownStream);
+    delete r;
+    return IFRIT_OK;
+}
+
+int iftrcuInit(iftrcuRenderer* h) { R_CHECK(h); r->inited = true; return IFRIT_OK; }
+
+const char* iftrcuGetLastError(iftrcuRenderer* h) { return h ? h->lastError.c_str() : "invalid handle"; }
+
+int iftrcuSetStream(iftrcuRenderer* h, void* cudaStream) {
+    R_CHECK(h);
+    cudaStreamSynchronize(r->stream);
+    r->stream = cudaStream ? (cudaStream_t)cudaStream : r->ownStream;
+    return IFRIT_OK;
+}
+
+int iftrcuBindFrameBuffer(iftrcuRenderer* h, float* hostColor, float* hostDepth, int width, int height, int) {
+    R_CHECK(h);
+    if (width <= 0 || height <= 0 || width > 65535 * 16 || height > 65535 * 16) return r->fail(IFRIT_ERR_INVALID, "bindFrameBuffer", "bad size");
+    CUDA_TRY(cudaStreamSynchronize(r->stream));
+    CUDA_TRY(r->ownColor.ensure((size_t)width * height * 16));
+    CUDA_TRY(r->ownDepth.ensure((size_t)width * height * 4));
+    r->dColor = (float4*)r->ownColor.p; r->dDepth = (float*)r->ownDepth.p;
+    r->externalFB = false;
+    if (r->registeredHost) { cudaHostUnregister(r->registeredHost); r->registeredHost = nullptr; }
+    r->hColor = hostColor; r->hDepth = hostDepth;
+    if (hostColor) {
+        // pin the caller's image in place so the copy-back is a true async DMA; failure is harmless
+        if (cudaHostRegister(hostColor, (size_t)width * height * 16, cudaHostRegisterDefault) == cudaSuccess) r->registeredHost = hostColor;
+        else cudaGetLastError();
+        CUDA_TRY(cudaMemcpyAsync(r->dColor, hostColor, (size_t)width * height * 16, cudaMemcpyHostToDevice, r->stream));
+    }
+    if (hostDepth) CUDA_TRY(cudaMemcpyAsync(r->dDepth, hostDepth, (size_t)width * height * 4, cudaMemcpyHostToDevice, r->stream));
+    if (r->W != width || r->H != height) r->queueChecked = false;
+    r->W = width; r->H = height;
+    return IFRIT_OK;
+}
+
+int iftrcuBindFrameBufferDevice(iftrcuRenderer* h, float* devColor, float* devDepth, int width, int height) {
+    R_CHECK(h);
+    if (!devColor || !devDepth || width <= 0 || height <= 0) return r->fail(IFRIT_ERR_INVALID, "bindFrameBufferDevice", "bad argument");
+    CUDA_TRY(cudaStreamSynchronize(r->stream));
+    if (r->registeredHost) { cudaHostUnregister(r->registeredHost); r->registeredHost = nullptr; }
+    r->dColor = (float4*)devColor; r->dDepth = devDepth; r->externalFB = true; r->hColor = nullptr; r->hDepth = nullptr;
+    if (r->W != width || r->H != height) r->queueChecked = false;
+    r->W = width; r->H = height;
+    return IFRIT_OK;
+}
+
+static int bind_vb(iftrcuRenderer* r, const void* data, int vertexCount, const int* descs, int nattr, bool device) {
+    int rc = check_types(r, descs, nattr, IFR_MAX_VARY + 1);
+    if (rc) return rc;
+    if (!data || vertexCount < 0 || nattr < 1) return r->fail(IFRIT_ERR_INVALID, "bindVertexBuffer", "bad argument");
+    r->nverts = vertexCount; r->nattr = nattr; r->stride = nattr * 16;
+    for (int i = 0; i < nattr; i++) r->attrOff[i] = i * 16;
+    if (device) {
+        r->dVB = (const uint8_t*)data;
+    } else {
+        CUDA_TRY(r->ownVB.ensure(std::max<size_t>(16, (size_t)vertexCount * r->stride)));
+        CUDA_TRY(cudaMemcpyAsync(r->ownVB.p, data, (size_t)vertexCount * r->stride, cudaMemcpyHostToDevice, r->stream));
+        r->dVB = (const uint8_t*)r->ownVB.p;
+    }
+    return IFRIT_OK;
+}
+int iftrcuBindVertexBuffer(iftrcuRenderer* h, const void* hostData, int vertexCount, const int* typeDescs, int n) {
+    R_CHECK(h); return bind_vb(r, hostData, vertexCount, typeDescs, n, false);
+}
+int iftrcuBindVertexBufferDevice(iftrcuRenderer* h, const void* devData, int vertexCount, const int* typeDescs, int n) {
+    R_CHECK(h); return bind_vb(r, devData, vertexCount, typeDescs, n, true);
+}
+
+static int bind_ib(iftrcuRenderer* r, const int* idx, int count, bool device) {
+    if (!idx || count < 0 || count % 3) return r->fail(IFRIT_ERR_INVALID, "bindIndexBuffer", "count must be a multiple of 3");
+    if (count != r->icount) r->queueChecked = false;
+    r->icount = count;
+    if (device) {
+        r->dIB = idx;
+    } else {
+        CUDA_TRY(r->ownIB.ensure(std::max<size_t>(16, (size_t)count * 4)));
+        CUDA_TRY(cudaMemcpyAsync(r->ownIB.p, idx, (size_t)count * 4, cudaMemcpyHostToDevice, r->stream));
+        r->dIB = (const int32_t*)r->ownIB.p;
+    }
+    return IFRIT_OK;
+}
+int iftrcuBindIndexBuffer(iftrcuRenderer* h, const int* hostIndices, int indexCount) { R_CHECK(h); return bind_ib(r, hostIndices, indexCount, false); }
+int iftrcuBindIndexBufferDevice(iftrcuRenderer* h, const int* devIndices, int indexCount) { R_CHECK(h); return bind_ib(r, devIndices, indexCount, true); }
+
+int iftrcuBindVertexShader(iftrcuRenderer* h, int id, const int* varyingDescs, int nvary) {
+    R_CHECK(h);
+    if (id != IFRIT_VS_PASSTHROUGH && id != IFRIT_VS_MVP) return r->fail(IFRIT_ERR_INVALID, "bindVertexShader", "unknown shader id");
+    int rc = check_types(r, varyingDescs, nvary, IFR_MAX_VARY);
+    if (rc) return rc;
+    r->vsId = id; r->nvary = nvary;
+    return IFRIT_OK;
+}
+int iftrcuBindFragmentShader(iftrcuRenderer* h, int id) {
+    R_CHECK(h);
+    if (id < IFRIT_FS_VARYING0 || id > IFRIT_FS_DERIV_VIS) return r->fail(IFRIT_ERR_INVALID, "bindFragmentShader", "unknown shader id");
+    r->fsId = id;
+    return IFRIT_OK;
+}
+int iftrcuLookupVertexShader(const char* name) {
+    if (!name) return -1;
+    if (!strcmp(name, "passthrough")) return IFRIT_VS_PASSTHROUGH;
+    if (!strcmp(name, "mvp")) return IFRIT_VS_MVP;
+    return -1;
+}
+int iftrcuLookupFragmentShader(const char* name) {
+    static const char* names[] = {"varying0", "normal_color", "prim_id", "textured", "textured_lod0", "skybox", "deriv_vis"};
+    if (!name) return -1;
+    for (int i = 0; i < 7; i++) if (!strcmp(name, names[i])) return i;
+    return -1;
+}
+int iftrcuBindGeometryShader(iftrcuRenderer* h, int) { R_CHECK(h); return r->fail(IFRIT_ERR_UNSUPPORTED, "bindGeometryShader", "out of scope"); }
+int iftrcuBindMeshShader(iftrcuRenderer* h, int, const int*, int, int, int, int) { R_CHECK(h); return r->fail(IFRIT_ERR_UNSUPPORTED, "bindMeshShader", "out of scope"); }
+int iftrcuBindTaskShader(iftrcuRenderer* h, int, const int*, int) { R_CHECK(h); return r->fail(IFRIT_ERR_UNSUPPORTED, "bindTaskShader", "out of scope"); }
+
+static size_t chain_texels(int w, int h, int mips, int layers) {
+    size_t n = 0;
+    for (int i = 0; i <= mips; i++) { n += (size_t)w * h * layers; w = (w + 1) >> 1; h = (h + 1) >> 1; }
+    return n;
+}
+
+int iftrcuCreateTexture(iftrcuRenderer* h, int slot, const IfritImageCreateInfo* ci) {
+    R_CHECK(h);
+    if (slot < 0 || slot >= IFR_MAX_TEX || !ci || ci->extent.width == 0 || ci->extent.height == 0 || ci->arrayLayers == 0)
+        return r->fail(IFRIT_ERR_INVALID, "CreateTexture", "bad argument");
+    if (ci->format != IF_FORMAT_R32G32B32A32_SFLOAT) return r->fail(IFRIT_ERR_UNSUPPORTED, "CreateTexture", "only RGBA32F");
+    CUDA_TRY(cudaStreamSynchronize(r->stream));
+    const size_t n = chain_texels(ci->extent.width, ci->extent.height, ci->mipLevels, ci->arrayLayers);
+    CUDA_TRY(r->texMem[slot].ensure(n * 16));
+    CUDA_TRY(cudaMemsetAsync(r->texMem[slot].p, 0, n * 16, r->stream));
+    r->tex[slot].data = (const float4*)r->texMem[slot].p;
+    r->tex[slot].w = ci->extent.width; r->tex[slot].h = ci->extent.height;
+    r->tex[slot].mips = ci->mipLevels; r->tex[slot].layers = ci->arrayLayers;
+    r->texTexels[slot] = n;
+    return IFRIT_OK;
+}
+
+int iftrcuCreateSampler(iftrcuRenderer* h, int slot, const IfritSamplerT* s) {
+    R_CHECK(h);
+    if (slot < 0 || slot >= IFR_MAX_TEX || !s) return r->fail(IFRIT_ERR_INVALID, "CreateSampler", "bad argument");
+    SampDesc& d = r->samp[slot];
+    d.filter = s->filterMode; d.addrU = s->addressModeU; d.addrV = s->addressModeV; d.addrW = s->addressModeW;
+    d.border = s->borderColor; d.aniso = s->anisotropyEnable ? 1 : 0; d.maxAniso = s->maxAnisotropy;
+    return IFRIT_OK;
+}
+
+int iftrcuBlitImage(iftrcuRenderer* h, int srcSlot, int dstSlot, const IfritImageBlit* b, IfritFilter filter) {
+    R_CHECK(h);
+    if (srcSlot < 0 || srcSlot >= IFR_MAX_TEX || dstSlot < 0 || dstSlot >= IFR_MAX_TEX || !b || !r->tex[srcSlot].data || !r->tex[dstSlot].data)
+        return r->fail(IFRIT_ERR_INVALID, "blitImage", "bad argument");
+    if ((int)b->srcSubresource.mipLevel > r->tex[srcSlot].mips || (int)b->dstSubresource.mipLevel > r->tex[dstSlot].mips)
+        return r->fail(IFRIT_ERR_INVALID, "blitImage", "mip level out of range");
+    const uint32_t sr[4] = {b->srcExtentSt.width, b->srcExtentSt.height, b->srcExtentEd.width, b->srcExtentEd.height};
+    const uint32_t dr[4] = {b->dstExtentSt.width, b->dstExtentSt.height, b->dstExtentEd.width, b->dstExtentEd.height};
+    CUDA_TRY(ifr_launch_blit(r->tex[srcSlot], b->srcSubresource.mipLevel, b->srcSubresource.baseArrayLayer, r->tex[dstSlot],
+                             b->dstSubresource.mipLevel, b->dstSubresource.baseArrayLayer, sr, dr, filter, r->stream));
+    r->stats.kernel_launches += 1;
+    return IFRIT_OK;
+}
+
+int iftrcuGenerateMipmap(iftrcuRenderer* h, int slot, IfritFilter filter) {   // invokeMipmapGeneration CUIMG:132-155
+    R_CHECK(h);
+    if (slot < 0 || slot >= IFR_MAX_TEX || !r->tex[slot].data) return r->fail(IFRIT_ERR_INVALID, "generateMipmap", "bad slot");
+    uint32_t w = r->tex[slot].w, hh = r->tex[slot].h;
+    for (int i = 0; i < r->tex[slot].mips; i++) {
+        const uint32_t nw = (w + 1) >> 1, nh = (hh + 1) >> 1;
+        for (int l = 0; l < r->tex[slot].layers; l++) {
+            const uint32_t sr[4] = {0, 0, w, hh}, dr[4] = {0, 0, nw, nh};
+            CUDA_TRY(ifr_launch_blit(r->tex[slot], i, l, r->tex[slot], i + 1, l, sr, dr, filter, r->stream));
+            r->stats.kernel_launches += 1;
+        }
+        w = nw; hh = nh;
+    }
+    return IFRIT_OK;
+}
+
+int iftrcuCopyHostBufferToImage(iftrcuRenderer* h, const void* src, int dstSlot, const IfritBufferImageCopy* regions, int n) {
+    R_CHECK(h);
+    if (dstSlot < 0 || dstSlot >= IFR_MAX_TEX || !r->tex[dstSlot].data || !src || (!regions && n)) return r->fail(IFRIT_ERR_INVALID, "copyHostBufferToImage", "bad argument");
+    const TexDesc& t = r->tex[dstSlot];
+    for (int i = 0; i < n; i++) {   // same restrictions as invokeCopyBufferToImage CUIMG:157-181
+        const IfritBufferImageCopy& g = regions[i];
+        if (g.imageOffset.x || g.imageOffset.y || g.imageOffset.z || (int)g.imageExtent.width != t.w || (int)g.imageExtent.height != t.h ||
+            g.imageSubresource.mipLevel != 0 || (int)g.imageSubresource.baseArrayLayer >= t.layers)
+            return r->fail(IFRIT_ERR_UNSUPPORTED, "copyHostBufferToImage", "only whole level-0 layers can be uploaded");
+        const size_t bytes = (size_t)t.w * t.h * 16;
+        CUDA_TRY(cudaMemcpyAsync((char*)r->texMem[dstSlot].p + bytes * g.imageSubresource.baseArrayLayer, (const char*)src + g.bufferOffset,
+                                 bytes, cudaMemcpyHostToDevice, r->stream));
+    }
+    return IFRIT_OK;
+}
+
+int iftrcuCopyImageToHostBuffer(iftrcuRenderer* h, int srcSlot, void* dst, size_t nbytes) {
+    R_CHECK(h);
+    if (srcSlot < 0 || srcSlot >= IFR_MAX_TEX || !r->tex[srcSlot].data || !dst) return r->fail(IFRIT_ERR_INVALID, "copyImageToHostBuffer", "bad argument");
+    const size_t n = std::min(nbytes, r->texTexels[srcSlot] * 16);
+    CUDA_TRY(cudaMemcpyAsync(dst, r->texMem[srcSlot].p, n, cudaMemcpyDeviceToHost, r->stream));
+    CUDA_TRY(cudaStreamSynchronize(r->stream));
+    return IFRIT_OK;
+}
+
+int iftrcuCreateBuffer(iftrcuRenderer* h, int slot, int bufSize) {
+    R_CHECK(h);
+    if (slot < 0 || slot >= IFR_MAX_BUF || bufSize <= 0) return r->fail(IFRIT_ERR_INVALID, "CreateBuffer", "bad argument");
+    CUDA_TRY(cudaStreamSynchronize(r->stream));
+    CUDA_TRY(r->bufMem[slot].ensure((size_t)bufSize));
+    r->bufSize[slot] = bufSize;
+    return IFRIT_OK;
+}
+int iftrcuCopyHostBufferToBuffer(iftrcuRenderer* h, const void* src, int dstSlot, int size) {
+    R_CHECK(h);
+    if (dstSlot < 0 || dstSlot >= IFR_MAX_BUF || !src || size < 0 || size > r->bufSize[dstSlot]) return r->fail(IFRIT_ERR_INVALID, "copyHostBufferToBuffer", "bad argument");
+    CUDA_TRY(cudaMemcpyAsync(r->bufMem[dstSlot].p, src, (size_t)size, cudaMemcpyHostToDevice, r->stream));
+    return IFRIT_OK;
+}
+
+int iftrcuSetScissors(iftrcuRenderer* h, const float* xywh, int count) {
+    R_CHECK(h);
+    if (count < 0 || count > IFR_MAX_SCISSOR || (count && !xywh)) return r->fail(IFRIT_ERR_INVALID, "SetScissors", "at most 16 rectangles");
+    r->nScissor = count;
+    if (count) memcpy(r->scissor, xywh, (size_t)count * 16);
+    return IFRIT_OK;
+}
+int iftrcuSetScissorTestEnable(iftrcuRenderer* h, int enable) { R_CHECK(h); r->scissorEnable = enable ? 1 : 0; return IFRIT_OK; }
+int iftrcuSetMsaaSamples(iftrcuRenderer* h, IfritSampleCountFlagBits s) {
+    R_CHECK(h);
+    if (s != 1 && s != 2 && s != 4 && s != 8 && s != 16) return r->fail(IFRIT_ERR_INVALID, "setMsaaSamples", "1, 2, 4, 8 or 16");
+    if (r->msaa != (int)s) r->queueChecked = false;
+    r->msaa = (int)s;
+    return IFRIT_OK;
+}
+int iftrcuSetRasterizerPolygonMode(iftrcuRenderer* h, IfritPolygonMode mode) {
+    R_CHECK(h);
+    if (mode != IF_POLYGON_MODE_FILL) return r->fail(IFRIT_ERR_UNSUPPORTED, "setRasterizerPolygonMode", "line / point modes are out of scope");
+    return IFRIT_OK;
+}
+int iftrcuSetBlendFunc(iftrcuRenderer* h, const IfritColorAttachmentBlendState* s) {
+    R_CHECK(h);
+    if (!s) return IFRIT_ERR_INVALID;
+    if (s->blendEnable) return r->fail(IFRIT_ERR_UNSUPPORTED, "setBlendFunc", "ordered alpha blending is out of scope (SURVEY 8f rank 1)");
+    return IFRIT_OK;
+}
+int iftrcuSetDepthFunc(iftrcuRenderer* h, IfritCompareOp op) {
+    R_CHECK(h);
+    if ((int)op < 0 || (int)op > 7) return IFRIT_ERR_INVALID;
+    if (op == IF_COMPARE_OP_NOT_EQUAL) return r->fail(IFRIT_ERR_UNSUPPORTED, "SetDepthFunc", "NOT_EQUAL is order dependent");
+    r->depthFunc = op;
+    return IFRIT_OK;
+}
+int iftrcuSetDepthTestEnable(iftrcuRenderer* h, int enable) { R_CHECK(h); r->depthTest = enable ? 1 : 0; return IFRIT_OK; }
+int iftrcuSetCullMode(iftrcuRenderer* h, IfritCullMode mode) {
+    R_CHECK(h);
+    if ((int)mode < 0 || (int)mode > 3) return IFRIT_ERR_INVALID;
+    if (r->cullMode != (int)mode) r->queueChecked = false;
+    r->cullMode = mode;
+    return IFRIT_OK;
+}
+int iftrcuSetClearValues(iftrcuRenderer* h, const float* rgba, int numColors, float clearDepth) {
+    R_CHECK(h);
+    if (numColors > 0 && rgba) memcpy(r->clearColor, rgba, 16);
+    r->clearDepth = clearDepth;
+    return IFRIT_OK;
+}
+int iftrcuSetSampleConvention(iftrcuRenderer* h, int convention) {
+    R_CHECK(h);
+    if (convention != IFRIT_CONVENTION_CUDA && convention != IFRIT_CONVENTION_CPU) return IFRIT_ERR_INVALID;
+    r->convention = convention; r->queueChecked = false;
+    return IFRIT_OK;
+}
+int iftrcuSetTilePartition(iftrcuRenderer* h, int rank, int worldSize) {
+    R_CHECK(h);
+    if (worldSize < 1 || rank < 0 || rank >= worldSize) return r->fail(IFRIT_ERR_INVALID, "SetTilePartition", "bad rank / world size");
+    r->rank = rank; r->world = worldSize; r->queueChecked = false;
+    return IFRIT_OK;
+}
+int iftrcuSetDebugPrimitiveIds(iftrcuRenderer* h, int enable) { R_CHECK(h); r->debugIds = enable != 0; return IFRIT_OK; }
+
+int iftrcuClear(iftrcuRenderer* h) {
+    R_CHECK(h);
+    if (!r->dColor) return r->fail(IFRIT_ERR_STATE, "clear", "no framebuffer bound");
+    r->pendingClear = true;   // fused into the next draw's tile kernel; flushed on read-back otherwise
+    return IFRIT_OK;
+}
+
+int iftrcuDrawElements(iftrcuRenderer* h) {
+    R_CHECK(h);
+    if (!r->dColor || !r->dVB || !r->dIB || r->vsId < 0 || r->fsId < 0) return r->fail(IFRIT_ERR_STATE, "drawElements", "framebuffer, vertex/index buffers and shaders must be bound");
+    if (r->nvary > r->nattr - 1) return r->fail(IFRIT_ERR_STATE, "drawElements", "vertex shader outputs more varyings than the buffer has attributes");
+    if (r->vsId == IFRIT_VS_MVP && !r->bufMem[0].p) return r->fail(IFRIT_ERR_STATE, "drawElements", "buffer slot 0 (uniform block) not created");
+    if ((r->fsId == IFRIT_FS_TEXTURED || r->fsId == IFRIT_FS_TEXTURED_LOD0 || r->fsId == IFRIT_FS_SKYBOX) && (!r->tex[0].data || !r->bufMem[0].p))
+        return r->fail(IFRIT_ERR_STATE, "drawElements", "texture slot 0 / buffer slot 0 not created");
+    {
+        const int need = (r->fsId == IFRIT_FS_PRIM_ID) ? 0
+                         : (r->fsId == IFRIT_FS_TEXTURED || r->fsId == IFRIT_FS_TEXTURED_LOD0 || r->fsId == IFRIT_FS_DERIV_VIS) ? 2 : 1;
+        if (r->nvary < need) return r->fail(IFRIT_ERR_STATE, "drawElements", "fragment shader needs more varyings than the vertex shader outputs");
+    }
+    if (r->fsId == IFRIT_FS_DERIV_VIS && !r->bufMem[0].p) return r->fail(IFRIT_ERR_STATE, "drawElements", "buffer slot 0 (uniform block) not created");
+    if (r->haveDraw && !r->queueChecked) { int rc = sync_and_check(r); if (rc) return rc; }
+    return issue_draw(r, false);
+}
+
+int iftrcuDrawMeshTasks(iftrcuRenderer* h, int, int) { R_CHECK(h); return r->fail(IFRIT_ERR_UNSUPPORTED, "DrawMeshTasks", "out of scope"); }
+
+int iftrcuSynchronize(iftrcuRenderer* h) { R_CHECK(h); return sync_and_check(r); }
+
+int iftrcuReadColor(iftrcuRenderer* h, float* dst) {
+    R_CHECK(h);
+    if (!dst || !r->dColor) return r->fail(IFRIT_ERR_INVALID, "ReadColor", "bad argument");
+    int rc = flush_clear(r); if (rc) return rc;
+    rc = sync_and_check(r); if (rc) return rc;
+    CUDA_TRY(cudaMemcpy(dst, r->dColor, (size_t)r->W * r->H * 16, cudaMemcpyDeviceToHost));
+    return IFRIT_OK;
+}
+int iftrcuReadDepth(iftrcuRenderer* h, float* dst) {
+    R_CHECK(h);
+    if (!dst || !r->dDepth) return r->fail(IFRIT_ERR_INVALID, "ReadDepth", "bad argument");
+    int rc = flush_clear(r); if (rc) return rc;
+    rc = sync_and_check(r); if (rc) return rc;
+    CUDA_TRY(cudaMemcpy(dst, r->dDepth, (size_t)r->W * r->H * 4, cudaMemcpyDeviceToHost));
+    return IFRIT_OK;
+}
+int iftrcuReadPrimitiveIds(iftrcuRenderer* h, int32_t* dst) {
+    R_CHECK(h);
+    if (!dst || !r->debugIds || !r->primIds.p) return r->fail(IFRIT_ERR_STATE, "ReadPrimitiveIds", "enable with SetDebugPrimitiveIds before drawing");
+    int rc = sync_and_check(r); if (rc) return rc;
+    CUDA_TRY(cudaMemcpy(dst, r->primIds.p, (size_t)r->W * r->H * r->msaa * 4, cudaMemcpyDeviceToHost));
+    return IFRIT_OK;
+}
+int iftrcuGetDeviceColorPtr(iftrcuRenderer* h, void** out) { R_CHECK(h); if (!out) return IFRIT_ERR_INVALID; *out = r->dColor; return IFRIT_OK; }
+int iftrcuGetDeviceDepthPtr(iftrcuRenderer* h, void** out) { R_CHECK(h); if (!out) return IFRIT_ERR_INVALID; *out = r->dDepth; return IFRIT_OK; }
+int iftrcuGetStats(iftrcuRenderer* h, iftrcuStats* out) {
+    R_CHECK(h);
+    if (!out) return IFRIT_ERR_INVALID;
+    int rc = sync_and_check(r); if (rc) return rc;
+    *out = r->stats;
+    return IFRIT_OK;
+}
+
+int iftrcuReadAssembled(iftrcuRenderer* h, iftrcuAssembledTriangle* dst, int cap, int* n) {
+    R_CHECK(h);
+    if (!n || !r->haveDraw) return r->fail(IFRIT_ERR_STATE, "ReadAssembled", "no draw issued");
+    int rc = sync_and_check(r); if (rc) return rc;
+    const size_t ntri = (size_t)r->icount / 3;
+    std::vector<TriVert> rec(2 * ntri * 3);
+    std::vector<uint2> box(2 * ntri);
+    std::vector<float> cb(2 * ntri * 6);
+    const size_t nfan1 = (size_t)r->hCounters[4];
+    std::vector<uint32_t> fan1(std::max<size_t>(1, nfan1));
+    if (ntri) {
+        CUDA_TRY(cudaMemcpy(rec.data(), r->rec.p, rec.size() * sizeof(TriVert), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(box.data(), r->tileBox.p, box.size() * sizeof(uint2), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(cb.data(), r->clipBary.p, cb.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        if (nfan1) CUDA_TRY(cudaMemcpy(fan1.data(), r->fan1List.p, nfan1 * 4, cudaMemcpyDeviceToHost));
+    }
+    std::vector<uint32_t> slots;
+    for (size_t t = 0; t < ntri; t++) if ((box[t].x & 0xffff) <= (box[t].x >> 16)) slots.push_back((uint32_t)t);
+    for (size_t i = 0; i < nfan1; i++) slots.push_back(fan1[i]);
+    std::sort(slots.begin(), slots.end());
+    int k = 0;
+    for (uint32_t s : slots) {
+        if (dst && k < cap) {
+            iftrcuAssembledTriangle& a = dst[k];
+            a.fan = s >= ntri; a.prim = a.fan ? (int)(s - ntri) : (int)s; a.slot = (int)s;
+            const int flags = rec[3 * (size_t)s].x & 3;
+            a.clipped = (flags & IFR_FLAG_CLIPPED) ? 1 : 0;
+            for (int j = 0; j < 3; j++) {
+                const TriVert& v = rec[3 * (size_t)s + j];
+                a.X[j] = v.x >> 2; a.Y[j] = v.y; a.Z[j] = v.z; a.IW[j] = v.iw;
+            }
+            if (a.clipped) {
+                for (int j = 0; j < 3; j++) { a.bary[j][0] = cb[6 * (size_t)s + 2 * j]; a.bary[j][1] = cb[6 * (size_t)s + 2 * j + 1]; }
+            } else {
+                const bool sw = flags & IFR_FLAG_SWAPPED;
+                a.bary[0][0] = sw ? 1.f : 0.f; a.bary[0][1] = sw ? 0.f : 1.f;
+                a.bary[1][0] = 0.f; a.bary[1][1] = 0.f;
+                a.bary[2][0] = sw ? 0.f : 1.f; a.bary[2][1] = sw ? 1.f : 0.f;
+            }
+        }
+        k++;
+    }
+    *n = k;
+    return IFRIT_OK;
+}
+
+size_t iftrcuOwnedTileBytes(int width, int height, int rank, int worldSize) {
+    if (worldSize < 1) return 0;
+    const int sx = (width + IFR_SUPER - 1) / IFR_SUPER, sy = (height + IFR_SUPER - 1) / IFR_SUPER;
+    size_t n = 0;
+    for (int y = 0; y < sy; y++)
+        for (int x = 0; x < sx; x++) n += ((x + 3 * y) % worldSize) == rank;
+    return n * IFR_SUPER * IFR_SUPER * 16;
+}
+
+int iftrcuPackOwnedTiles(iftrcuRenderer* h, void* devDst, size_t dstBytes, size_t* usedBytes) {
+    R_CHECK(h);
+    if (!devDst || !r->dColor) return r->fail(IFRIT_ERR_INVALID, "PackOwnedTiles", "bad argument");
+    const size_t need = iftrcuOwnedTileBytes(r->W, r->H, r->rank, r->world);
+    if (usedBytes) *usedBytes = need;
+    if (dstBytes < need) return r->fail(IFRIT_ERR_INVALID, "PackOwnedTiles", "destination too small");
+    int rc = flush_clear(r); if (rc) return rc;
+    DrawParams p;
+    build_params(r, p);
+    CUDA_TRY(ifr_launch_pack(p, (float*)devDst, r->rank, r->world, 0, r->stream));
+    r->stats.kernel_launches += 1;
+    return IFRIT_OK;
+}
+
+int iftrcuUnpackOwnedTiles(iftrcuRenderer* h, const void* devSrc, int rank, int worldSize) {
+    R_CHECK(h);
+    if (!devSrc || !r->dColor || worldSize < 1 || rank < 0 || rank >= worldSize) return r->fail(IFRIT_ERR_INVALID, "UnpackOwnedTiles", "bad argument");
+    DrawParams p;
+    build_params(r, p);
+    CUDA_TRY(ifr_launch_pack(p, (float*)const_cast<void*>(devSrc), rank, worldSize, 1, r->stream));
+    r->stats.kernel_launches += 1;
+    return IFRIT_OK;
+}
+
+}  // extern "C"

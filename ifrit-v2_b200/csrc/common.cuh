@@ -1,0 +1,77 @@
+// common.cuh — internal types shared by the kernels and the C-ABI host code.
+// B200 (sm_100a) only.  See DESIGN.md §3 for the arithmetic specification these kernels
+// implement bit-for-bit (integer coverage / ids / depth) against oracle/ifrit_oracle.c.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define IFR_TILE 16          // tile edge in pixels (reference: CU_TILE_WIDTH, KC:36-42)
+#define IFR_TILE_PIX 256
+#define IFR_SUPER 64         // sort-first ownership granularity in pixels
+#define IFR_SUBPIX 256       // 24.8 fixed point
+#define IFR_MAX_TEX 8
+#define IFR_MAX_BUF 8
+#define IFR_MAX_VARY 4
+#define IFR_MAX_SCISSOR 16
+#define IFR_SLOT_NONE 0xffffffffu
+
+// One assembled triangle = three 16-byte vertices (48 B).  x carries two flag bits in its
+// low bits: X = x >> 2.  Vertex 0: bit0 = clipped, bit1 = swapped (cull-mode winding swap).
+struct TriVert { int32_t x, y; float z, iw; };
+#define IFR_FLAG_CLIPPED 1
+#define IFR_FLAG_SWAPPED 2
+
+struct TexDesc { const float4* data; int w, h, mips, layers; };
+struct SampDesc { int filter, addrU, addrV, addrW, border, aniso; float maxAniso; };
+
+struct DrawParams {
+    // framebuffer
+    float4* color; float* depth; int32_t* primIds;
+    int W, H, tilesX, tilesY;
+    int msaa, depthFunc, cullMode, convention;
+    int doClear; float clearColor[4]; float clearDepth;
+    int scissorEnable, nScissor; float scissor[IFR_MAX_SCISSOR][4];
+    int rank, world;
+    // coverage sample pattern of this draw, in 1/16 pixel (from cMsaaSampleSequenceAgg, CU:223-234)
+    int8_t sampX[16], sampY[16];
+    int sampMinX, sampMaxX, sampMinY, sampMaxY;   // extents in sub-pixel (1/256) units
+    // geometry
+    const uint8_t* vb; int stride, nattr, nvary, nverts; int attrOff[IFR_MAX_VARY + 1];
+    const int32_t* ib; int ntri;
+    float4* pos; float4* vary;
+    // assembled triangles: rec[slot*3+v]; slot = prim (fan 0) or ntri + prim (fan 1)
+    TriVert* rec; float* clipBary;   // clipBary[slot*6]
+    uint2* tileBox;                  // per slot: packed tile bbox, x = x0 | x1<<16, y = y0 | y1<<16; x0>x1 = none
+    uint32_t* fan1List;              // slots of second fan triangles (clipped primitives only)
+    // binning
+    uint32_t* tileCount; uint32_t* tileStart; uint32_t* tileCursor; uint32_t* queue; uint32_t queueCap;
+    unsigned long long* counters;    // [0] assembled, [1] pairs, [2] frags, [3] overflow flag, [4] fan1 count
+    // resources
+    TexDesc tex[IFR_MAX_TEX]; SampDesc samp[IFR_MAX_TEX]; const float* buf[IFR_MAX_BUF];
+};
+
+// sort-first ownership of a tile: 64-px super-tiles interleaved over ranks
+__host__ __device__ inline int ifr_tile_owner(int tx, int ty, int world) {
+    const int sx = tx / (IFR_SUPER / IFR_TILE), sy = ty / (IFR_SUPER / IFR_TILE);
+    return (sx + 3 * sy) % world;
+}
+
+#define CUDA_TRY(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) return r->fail(IFRIT_ERR_CUDA, #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+// kernel launchers (defined in the .cu files)
+struct Launch { cudaStream_t stream; };
+cudaError_t ifr_launch_vertex(const DrawParams& p, int vsId, cudaStream_t s);
+cudaError_t ifr_launch_setup_count(const DrawParams& p, cudaStream_t s);
+cudaError_t ifr_launch_scan(const DrawParams& p, cudaStream_t s);
+cudaError_t ifr_launch_fill(const DrawParams& p, cudaStream_t s);
+cudaError_t ifr_launch_tiles(const DrawParams& p, int fsId, cudaStream_t s);
+cudaError_t ifr_launch_clear(const DrawParams& p, cudaStream_t s);
+cudaError_t ifr_launch_blit(const TexDesc& src, int srcLevel, int srcLayer, const TexDesc& dst, int dstLevel,
+                            int dstLayer, const uint32_t srcRect[4], const uint32_t dstRect[4], int filter,
+                            cudaStream_t s);
+cudaError_t ifr_launch_pack(const DrawParams& p, float* dst, int rank, int world, int unpack, cudaStream_t s);
+int ifr_kernels_per_draw();

@@ -1,0 +1,403 @@
+// kernels_geometry.cu — vertex shading, clip/cull/snap triangle setup, sort-middle binning.
+//
+// Replaces, B200-first (host-launched, count -> scan -> fill, exactly-sized queues):
+//   vertexProcessingKernel            CU:330        -> vs_kernel
+//   geometryClippingKernel            CU:1493/1343  -> setup_bin_kernel<false> (clip, viewport, snap, cull)
+//   geometryParamPostprocKernel       CU:1549       -> folded into the tile kernel (48-byte snapped records
+//                                                      are cheaper to stream than 112-byte setup records)
+//   firstBinner* / *Alloc / *Gather   CU:721-1222   -> setup_bin_kernel<false> (count), scan_kernel,
+//                                                      setup_bin_kernel<true> (fill)
+// All arithmetic that decides coverage / visibility is integer (24.8 fixed point, 64-bit products) and
+// follows oracle/ifrit_oracle.c op for op; float ops use explicit fmaf / rn intrinsics (-fmad=false).
+#include "common.cuh"
+#include "../../include/ifrit_b200.h"
+
+#define SNAP_LIMIT 268435456.0f
+
+// ------------------------------------------------------------------------------------------------
+// Vertex stage: one thread per vertex, 128-bit loads of the interleaved attributes, 128-bit stores.
+template <int VS>
+__global__ void __launch_bounds__(256) vs_kernel(const __grid_constant__ DrawParams p) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= p.nverts) return;
+    const uint8_t* base = p.vb + (size_t)v * p.stride;
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(base + p.attrOff[0]));
+    float4 o;
+    if (VS == IFRIT_VS_MVP) {
+        const float4* m = reinterpret_cast<const float4*>(p.buf[0]);
+        const float4 r0 = __ldg(m), r1 = __ldg(m + 1), r2 = __ldg(m + 2), r3 = __ldg(m + 3);
+        o.x = fmaf(r0.w, a0.w, fmaf(r0.z, a0.z, fmaf(r0.y, a0.y, __fmul_rn(r0.x, a0.x))));
+        o.y = fmaf(r1.w, a0.w, fmaf(r1.z, a0.z, fmaf(r1.y, a0.y, __fmul_rn(r1.x, a0.x))));
+        o.z = fmaf(r2.w, a0.w, fmaf(r2.z, a0.z, fmaf(r2.y, a0.y, __fmul_rn(r2.x, a0.x))));
+        o.w = fmaf(r3.w, a0.w, fmaf(r3.z, a0.z, fmaf(r3.y, a0.y, __fmul_rn(r3.x, a0.x))));
+    } else {
+        o = a0;
+    }
+    p.pos[v] = o;
+    for (int k = 0; k < p.nvary; k++)
+        p.vary[(size_t)v * p.nvary + k] = __ldg(reinterpret_cast<const float4*>(base + p.attrOff[k + 1]));
+}
+
+cudaError_t ifr_launch_vertex(const DrawParams& p, int vsId, cudaStream_t s) {
+    if (p.nverts <= 0) return cudaSuccess;
+    const int blocks = (p.nverts + 255) / 256;
+    if (vsId == IFRIT_VS_MVP) vs_kernel<IFRIT_VS_MVP><<<blocks, 256, 0, s>>>(p);
+    else vs_kernel<IFRIT_VS_PASSTHROUGH><<<blocks, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+struct ClipV { float4 p; float bx, by; };
+
+__device__ __forceinline__ ClipV clip_lerp(const ClipV& a, const ClipV& b, float t) {
+    ClipV r;
+    r.p.x = fmaf(__fsub_rn(b.p.x, a.p.x), t, a.p.x);
+    r.p.y = fmaf(__fsub_rn(b.p.y, a.p.y), t, a.p.y);
+    r.p.z = fmaf(__fsub_rn(b.p.z, a.p.z), t, a.p.z);
+    r.p.w = fmaf(__fsub_rn(b.p.w, a.p.w), t, a.p.w);
+    r.bx = fmaf(__fsub_rn(b.bx, a.bx), t, a.bx);
+    r.by = fmaf(__fsub_rn(b.by, a.by), t, a.by);
+    return r;
+}
+
+__device__ __forceinline__ int snap(float ndc, float halfExtentSubpix) {
+    float f = fmaf(ndc, halfExtentSubpix, halfExtentSubpix);
+    f = fminf(fmaxf(f, -SNAP_LIMIT), SNAP_LIMIT);
+    return __float2int_rn(f);
+}
+
+struct Assembled {
+    int X[3], Y[3];
+    float Z[3], IW[3];
+    float bary[3][2];
+    int flags;
+    int tx0, tx1, ty0, ty1;   // tile bbox (inclusive), valid when ok
+    bool ok;
+};
+
+// viewport + snap + rejects + cull for one fan triangle (devGeometryCullClip CU:1399-1483)
+__device__ __forceinline__ void finish_triangle(const DrawParams& p, const ClipV& v0, const ClipV& v1,
+                                                const ClipV& v2, bool clipped, Assembled& a) {
+    a.ok = false;
+    const bool cpu = p.convention == IFRIT_CONVENTION_CPU;
+    const float hw = 128.0f * (float)p.W, hh = 128.0f * (float)p.H;
+    const ClipV* v[3] = {&v0, &v1, &v2};
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const float iw = __frcp_rn(v[j]->p.w);
+        a.IW[j] = iw;
+        a.Z[j] = __fmul_rn(v[j]->p.z, iw);
+        a.X[j] = snap(__fmul_rn(v[j]->p.x, iw), hw);
+        a.Y[j] = snap(__fmul_rn(v[j]->p.y, iw), hh);
+        a.bary[j][0] = v[j]->bx;
+        a.bary[j][1] = v[j]->by;
+    }
+    const int minx = min(a.X[0], min(a.X[1], a.X[2])), maxx = max(a.X[0], max(a.X[1], a.X[2]));
+    const int miny = min(a.Y[0], min(a.Y[1], a.Y[2])), maxy = max(a.Y[0], max(a.Y[1], a.Y[2]));
+    if (maxx < 0 || maxy < 0 || minx > p.W * IFR_SUBPIX || miny > p.H * IFR_SUBPIX) return;
+    if (cpu) {
+        const float zmin = fminf(a.Z[0], fminf(a.Z[1], a.Z[2])), zmax = fmaxf(a.Z[0], fmaxf(a.Z[1], a.Z[2]));
+        if (zmax < 0.0f || zmin > 1.0f) return;
+    }
+    const long long d = (long long)(a.X[1] - a.X[0]) * (a.Y[2] - a.Y[0]) -
+                        (long long)(a.X[2] - a.X[0]) * (a.Y[1] - a.Y[0]);
+    if (d == 0) return;
+    bool swp = false;
+    switch (p.cullMode) {
+        case IF_CULL_MODE_BACK: if (d < 0) return; break;
+        case IF_CULL_MODE_FRONT: if (d > 0) return; swp = true; break;
+        case IF_CULL_MODE_NONE: swp = d < 0; break;
+        default: return;
+    }
+    a.flags = (clipped ? IFR_FLAG_CLIPPED : 0) | (swp ? IFR_FLAG_SWAPPED : 0);
+    if (swp) {
+        int t;
+        float f;
+        t = a.X[0]; a.X[0] = a.X[2]; a.X[2] = t;
+        t = a.Y[0]; a.Y[0] = a.Y[2]; a.Y[2] = t;
+        f = a.Z[0]; a.Z[0] = a.Z[2]; a.Z[2] = f;
+        f = a.IW[0]; a.IW[0] = a.IW[2]; a.IW[2] = f;
+        f = a.bary[0][0]; a.bary[0][0] = a.bary[2][0]; a.bary[2][0] = f;
+        f = a.bary[0][1]; a.bary[0][1] = a.bary[2][1]; a.bary[2][1] = f;
+    }
+    // exact contribution cull: pixel range that can contain a strictly-inside sample
+    int px0 = ((minx - p.sampMaxX) >> 8) + 1, px1 = (maxx - p.sampMinX - 1) >> 8;
+    int py0 = ((miny - p.sampMaxY) >> 8) + 1, py1 = (maxy - p.sampMinY - 1) >> 8;
+    px0 = max(px0, 0); py0 = max(py0, 0);
+    px1 = min(px1, p.W - 1); py1 = min(py1, p.H - 1);
+    if (px0 > px1 || py0 > py1) return;
+    a.tx0 = px0 >> 4; a.tx1 = px1 >> 4; a.ty0 = py0 >> 4; a.ty1 = py1 >> 4;
+    a.ok = true;
+}
+
+// clip one input triangle against the w plane; returns the number of fan triangles (0..2+)
+__device__ int assemble(const DrawParams& p, int t, Assembled out[2]) {
+    const bool cpu = p.convention == IFRIT_CONVENTION_CPU;
+    const int i0 = __ldg(p.ib + 3 * (size_t)t), i1 = __ldg(p.ib + 3 * (size_t)t + 1), i2 = __ldg(p.ib + 3 * (size_t)t + 2);
+    ClipV src[3];
+    src[0].p = __ldg(p.pos + i0); src[0].bx = 1.0f; src[0].by = 0.0f;
+    src[1].p = __ldg(p.pos + i1); src[1].bx = 0.0f; src[1].by = 1.0f;
+    src[2].p = __ldg(p.pos + i2); src[2].bx = 0.0f; src[2].by = 0.0f;
+    const float w0 = src[0].p.w, w1 = src[1].p.w, w2 = src[2].p.w;
+    out[0].ok = false; out[1].ok = false;
+    if (!cpu) {
+        if (w0 < 0 && w1 < 0 && w2 < 0) return 0;
+    } else {
+        const float mx = fmaxf(w0, fmaxf(w1, w2)), mn = fminf(w0, fminf(w1, w2));
+        if (!(__fmul_rn(mx, mn) < 0) && !(mn > 0)) return 0;
+    }
+    if (w0 > 0 && w1 > 0 && w2 > 0) {
+        // no sign change: Sutherland–Hodgman emits (v2, v3, v1) — CU:1361-1396
+        finish_triangle(p, src[1], src[2], src[0], false, out[0]);
+        return 1;
+    }
+    ClipV poly[6];
+    int np = 0;
+    bool clipped = false;
+    ClipV pc = src[0];
+    for (int j = 0; j < 3; j++) {
+        const ClipV& pn = src[(j + 1) % 3];
+        const float npc = -pc.p.w, npn = -pn.p.w;
+        if (__fmul_rn(npc, npn) < 0) {
+            const float plane = cpu ? 1.0f : 1e-3f;
+            const float tt = __fdiv_rn(__fsub_rn(pc.p.w, plane), __fsub_rn(pc.p.w, pn.p.w));
+            poly[np++] = clip_lerp(pc, pn, tt);
+            clipped = true;
+        }
+        if (cpu ? (npn < 1e-8f) : (npn < 0)) poly[np++] = pn;
+        pc = pn;
+    }
+    if (np < 3) return 0;
+    int nf = 0;
+    for (int f = 0; f < np - 2 && f < 2; f++) {
+        finish_triangle(p, poly[0], poly[f + 1], poly[f + 2], clipped, out[f]);
+        nf = f + 1;
+    }
+    return nf;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Binning.  A tile is kept for a triangle unless one edge function is <= 0 at every sample position
+// of the tile (exact, 64-bit) — same predicate in the count and the fill pass.
+struct EdgeSet { int dX[3], dY[3], Xa[3], Ya[3]; };
+
+__device__ __forceinline__ void make_edges(const int X[3], const int Y[3], EdgeSet& e) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const int a = (i + 1) % 3, b = (i + 2) % 3;
+        e.dX[i] = X[b] - X[a]; e.dY[i] = Y[b] - Y[a]; e.Xa[i] = X[a]; e.Ya[i] = Y[a];
+    }
+}
+
+__device__ __forceinline__ bool tile_may_cover(const EdgeSet& e, int tx, int ty) {
+    const long long sx0 = (long long)tx * (IFR_TILE * IFR_SUBPIX), sy0 = (long long)ty * (IFR_TILE * IFR_SUBPIX);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const long long E0 = (long long)e.dX[i] * (sy0 - e.Ya[i]) - (long long)e.dY[i] * (sx0 - e.Xa[i]);
+        const long long add = 4080LL * ((e.dX[i] > 0 ? (long long)e.dX[i] : 0) + (e.dY[i] < 0 ? -(long long)e.dY[i] : 0));
+        if (E0 + add <= 0) return false;
+    }
+    return true;
+}
+
+template <bool FILL>
+__device__ __forceinline__ void bin_one(const DrawParams& p, uint32_t slot, int tx, int ty) {
+    if (p.world > 1 && ifr_tile_owner(tx, ty, p.world) != p.rank) return;
+    const int tile = ty * p.tilesX + tx;
+    if (FILL) {
+        const uint32_t pos = p.tileStart[tile] + atomicAdd(&p.tileCursor[tile], 1u);
+        p.queue[pos] = slot;
+    } else {
+        atomicAdd(&p.tileCount[tile], 1u);
+    }
+}
+
+#define IFR_BIG_TILES 16
+
+// per-thread binning of small boxes + warp-cooperative binning of large ones
+template <bool FILL>
+__device__ __forceinline__ void bin_triangle(const DrawParams& p, bool has, uint32_t slot, int tx0, int tx1,
+                                             int ty0, int ty1, const EdgeSet& e) {
+    const int nx = tx1 - tx0 + 1, ny = ty1 - ty0 + 1;
+    const int nt = has ? nx * ny : 0;
+    if (nt == 1) {
+        bin_one<FILL>(p, slot, tx0, ty0);
+    } else if (nt > 1 && nt <= IFR_BIG_TILES) {
+        const bool test = nx > 1 && ny > 1;
+        for (int ty = ty0; ty <= ty1; ty++)
+            for (int tx = tx0; tx <= tx1; tx++)
+                if (!test || tile_may_cover(e, tx, ty)) bin_one<FILL>(p, slot, tx, ty);
+    }
+    unsigned big = __ballot_sync(0xffffffffu, nt > IFR_BIG_TILES);
+    const int lane = threadIdx.x & 31;
+    while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const uint32_t s = __shfl_sync(0xffffffffu, slot, src);
+        const int bx0 = __shfl_sync(0xffffffffu, tx0, src), bx1 = __shfl_sync(0xffffffffu, tx1, src);
+        const int by0 = __shfl_sync(0xffffffffu, ty0, src), by1 = __shfl_sync(0xffffffffu, ty1, src);
+        EdgeSet be;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            be.dX[i] = __shfl_sync(0xffffffffu, e.dX[i], src); be.dY[i] = __shfl_sync(0xffffffffu, e.dY[i], src);
+            be.Xa[i] = __shfl_sync(0xffffffffu, e.Xa[i], src); be.Ya[i] = __shfl_sync(0xffffffffu, e.Ya[i], src);
+        }
+        const int bnx = bx1 - bx0 + 1, total = bnx * (by1 - by0 + 1);
+        for (int i = lane; i < total; i += 32) {
+            const int tx = bx0 + i % bnx, ty = by0 + i / bnx;
+            if (tile_may_cover(be, tx, ty)) bin_one<FILL>(p, s, tx, ty);
+        }
+    }
+}
+
+__device__ __forceinline__ void store_record(const DrawParams& p, uint32_t slot, const Assembled& a) {
+    int4* r = reinterpret_cast<int4*>(p.rec + (size_t)slot * 3);
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        int4 v;
+        v.x = (a.X[j] << 2) | (j == 0 ? a.flags : 0);
+        v.y = a.Y[j];
+        v.z = __float_as_int(a.Z[j]);
+        v.w = __float_as_int(a.IW[j]);
+        r[j] = v;
+    }
+    if (a.flags & IFR_FLAG_CLIPPED) {
+        float* b = p.clipBary + (size_t)slot * 6;
+#pragma unroll
+        for (int j = 0; j < 3; j++) { b[2 * j] = a.bary[j][0]; b[2 * j + 1] = a.bary[j][1]; }
+    }
+}
+
+// pass 1: one thread per input triangle — clip, snap, cull, store the 48-byte record, count tiles
+__global__ void __launch_bounds__(256) setup_count_kernel(const __grid_constant__ DrawParams p) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    Assembled a[2];
+    a[0].ok = a[1].ok = false;
+    if (t < p.ntri) assemble(p, t, a);
+    unsigned long long nasm = 0;
+#pragma unroll
+    for (int f = 0; f < 2; f++) {
+        const bool has = a[f].ok;
+        const uint32_t slot = f == 0 ? (uint32_t)t : (uint32_t)(p.ntri + t);
+        EdgeSet e;
+        if (has) {
+            store_record(p, slot, a[f]);
+            make_edges(a[f].X, a[f].Y, e);
+            nasm++;
+            if (f == 1) {
+                const unsigned long long k = atomicAdd(&p.counters[4], 1ull);
+                p.fan1List[k] = slot;
+            }
+        }
+        if (t < p.ntri && (f == 0 || has)) {
+            uint2 box;
+            if (has) { box.x = (uint32_t)a[f].tx0 | ((uint32_t)a[f].tx1 << 16); box.y = (uint32_t)a[f].ty0 | ((uint32_t)a[f].ty1 << 16); }
+            else { box.x = 1u; box.y = 0u; }   // x0 = 1 > x1 = 0: empty
+            p.tileBox[slot] = box;
+        }
+        if (f == 1 && __ballot_sync(0xffffffffu, has) == 0) continue;   // warp-uniform skip
+        bin_triangle<false>(p, has, slot, a[f].tx0, a[f].tx1, a[f].ty0, a[f].ty1, e);
+    }
+    // block-aggregated statistics
+    nasm = __reduce_add_sync(0xffffffffu, (unsigned)nasm);
+    if ((threadIdx.x & 31) == 0 && nasm) atomicAdd(&p.counters[0], nasm);
+}
+
+// pass 3: one thread per slot of pass 1 (fan-0 slots densely, fan-1 slots through fan1List)
+__global__ void __launch_bounds__(256) fill_kernel(const __grid_constant__ DrawParams p) {
+    if (p.counters[3]) return;   // queue too small: host re-issues the draw with a larger one
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long nfan1 = p.counters[4];
+#pragma unroll
+    for (int f = 0; f < 2; f++) {
+        bool has = false;
+        uint32_t slot = 0;
+        if (f == 0) { has = t < p.ntri; slot = (uint32_t)t; }
+        else if ((unsigned long long)t < nfan1) { has = true; slot = p.fan1List[t]; }
+        if (f == 1 && __ballot_sync(0xffffffffu, has) == 0) continue;
+        int tx0 = 0, tx1 = 0, ty0 = 0, ty1 = 0;
+        EdgeSet e;
+        if (has) {
+            const uint2 box = p.tileBox[slot];
+            tx0 = box.x & 0xffff; tx1 = box.x >> 16; ty0 = box.y & 0xffff; ty1 = box.y >> 16;
+            has = tx0 <= tx1;
+            if (has && (tx1 > tx0 || ty1 > ty0)) {
+                const int4* r = reinterpret_cast<const int4*>(p.rec + (size_t)slot * 3);
+                int X[3], Y[3];
+#pragma unroll
+                for (int j = 0; j < 3; j++) { const int4 v = r[j]; X[j] = v.x >> 2; Y[j] = v.y; }
+                make_edges(X, Y, e);
+            }
+        }
+        bin_triangle<true>(p, has, slot, tx0, tx1, ty0, ty1, e);
+    }
+}
+
+// pass 2: exclusive scan of the per-tile counts (single CTA; <= 130k tiles at 8K), cursor reset,
+// total -> counters[1], overflow flag -> counters[3]
+__global__ void __launch_bounds__(1024) scan_kernel(const __grid_constant__ DrawParams p) {
+    __shared__ uint32_t warpSums[32];
+    __shared__ uint32_t carry;
+    const int n = p.tilesX * p.tilesY;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024 * 4) {
+        uint32_t v[4];
+        uint32_t sum = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int i = base + tid * 4 + k;
+            v[k] = i < n ? p.tileCount[i] : 0u;
+            sum += v[k];
+        }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) warpSums[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t w = warpSums[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += y;
+            }
+            warpSums[lane] = wi - w;
+        }
+        __syncthreads();
+        uint32_t run = carry + warpSums[wid] + (incl - sum);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int i = base + tid * 4 + k;
+            if (i < n) { p.tileStart[i] = run; p.tileCursor[i] = 0u; }
+            run += v[k];
+        }
+        __syncthreads();
+        if (tid == 1023) carry = run;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        p.tileStart[n] = carry;
+        p.counters[1] = carry;
+        if (carry > p.queueCap) p.counters[3] = 1ull;
+    }
+}
+
+cudaError_t ifr_launch_setup_count(const DrawParams& p, cudaStream_t s) {
+    if (p.ntri <= 0) return cudaSuccess;
+    setup_count_kernel<<<(p.ntri + 255) / 256, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+cudaError_t ifr_launch_scan(const DrawParams& p, cudaStream_t s) {
+    scan_kernel<<<1, 1024, 0, s>>>(p);
+    return cudaGetLastError();
+}
+cudaError_t ifr_launch_fill(const DrawParams& p, cudaStream_t s) {
+    if (p.ntri <= 0) return cudaSuccess;
+    fill_kernel<<<(p.ntri + 255) / 256, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}

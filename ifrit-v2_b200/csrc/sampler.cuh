@@ -1,0 +1,186 @@
+// sampler.cuh — device texture sampling library + fragment-shader registry.
+//
+// Behaviour restated from include/ifrit/softgraphics/engine/math/ShaderBuiltinCuda.cuh ("SB"):
+//   textureImplLegacy SB:106-182 (address modes, nearest / bilinear), textureImplLod SB:210-218
+//   (trilinear), textureImplAdaptiveLod SB:233-243 (incl. the dx.y-for-dy.y slip at SB:237),
+//   textureImplAnisotropicFilter SB:244-272, textureCubeCoordConversion SB:184-208,
+//   textureCubeImplLod SB:220-231.  Texture memory layout SB:97-105: RGBA32F, level-major, layers
+//   inside each level, row-major.  Deviations (documented in DESIGN.md §3.6): the sampled level is
+//   clamped to the allocated chain and linear-filter texel indices are clamped (the reference reads
+//   out of bounds there).  Op order matches oracle/ifrit_oracle.c; log2f is the only libm call whose
+//   device / host results may differ in the last ulp.
+#pragma once
+#include "common.cuh"
+#include "../../include/ifrit_b200.h"
+
+__device__ __forceinline__ void level_info(const TexDesc& t, int layer, int lod, int& w, int& h, long long& off) {
+    long long o = 0;
+    int lw = t.w, lh = t.h;
+    for (int i = 0; i < lod; i++) {
+        o += (long long)lw * lh * t.layers;
+        lw = (lw + 1) >> 1;
+        lh = (lh + 1) >> 1;
+    }
+    w = lw; h = lh; off = o + (long long)lw * lh * layer;
+}
+
+__device__ __forceinline__ float addr_mode(int mode, float c, int size, bool& border) {
+    const float s = (float)size;
+    switch (mode) {
+        case IF_SAMPLER_ADDRESS_MODE_REPEAT:
+            if (c < 0) c += s;
+            c = fmodf(c, s);
+            if (c < 0) c += s;
+            break;
+        case IF_SAMPLER_ADDRESS_MODE_MIRRORED_REPEAT:
+            if (c < 0) c += 2 * s;
+            c = fmodf(c, 2 * s);
+            if (c < 0) c += 2 * s;
+            c = fminf(c, 2 * s - c);
+            break;
+        case IF_SAMPLER_ADDRESS_MODE_CLAMP_TO_EDGE:
+            c = (c >= s - 1.0f) ? s - 1.0f : ((c <= 0.0f) ? 0.0f : c);
+            break;
+        case IF_SAMPLER_ADDRESS_MODE_CLAMP_TO_BORDER:
+            if (c >= s || c < 0.0f) border = true;
+            break;
+        case IF_SAMPLER_ADDRESS_MODE_MIRROR_CLAMP_TO_EDGE:
+            c = (c >= s - 1.0f) ? 0.0f : ((c <= 0.0f) ? s - 1.0f : c);
+            break;
+    }
+    return c;
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+__device__ __forceinline__ float4 lerp4(const float4& a, const float4& b, float t) {
+    return make_float4(fmaf(b.x - a.x, t, a.x), fmaf(b.y - a.y, t, a.y), fmaf(b.z - a.z, t, a.z),
+                       fmaf(b.w - a.w, t, a.w));
+}
+
+__device__ float4 sample_level(const TexDesc& t, const SampDesc& s, int layer, float u, float v, int offx,
+                               int offy, int lod) {
+    int w, h;
+    long long off;
+    lod = clampi(lod, 0, t.mips);
+    level_info(t, layer, lod, w, h, off);
+    float cx = fmaf(u, (float)(w - 1), (float)offx);
+    float cy = fmaf(v, (float)(h - 1), (float)offy);
+    bool border = false;
+    cx = addr_mode(s.addrU, cx, w, border);
+    if (!border) cy = addr_mode(s.addrV, cy, h, border);
+    if (border) {
+        const float b = s.border == 0 ? 0.0f : 1.0f;
+        return make_float4(b, b, b, 1.0f);
+    }
+    const float4* base = t.data + off;
+    if (s.filter == IF_FILTER_NEAREST) {
+        int px = (int)roundf(cx), py = (int)roundf(cy);
+        px = clampi(px % w, 0, w - 1);
+        py = clampi(py % h, 0, h - 1);
+        return __ldg(base + (long long)py * w + px);
+    }
+    const int px = clampi((int)cx, 0, w - 1), py = clampi((int)cy, 0, h - 1);
+    const float fx = cx - (float)px, fy = cy - (float)py;
+    const int px1 = min(px + 1, w - 1), py1 = min(py + 1, h - 1);
+    const float4 c00 = __ldg(base + (long long)py * w + px), c01 = __ldg(base + (long long)py * w + px1);
+    const float4 c10 = __ldg(base + (long long)py1 * w + px), c11 = __ldg(base + (long long)py1 * w + px1);
+    const float4 a = lerp4(c00, c01, fx), b = lerp4(c10, c11, fx);
+    return lerp4(a, b, fy);
+}
+
+__device__ float4 sample_trilinear(const TexDesc& t, const SampDesc& s, int layer, float u, float v, int offx,
+                                   int offy, float lod) {
+    const int lo = (int)floorf(lod);
+    const float d = lod - (float)lo;
+    const float4 a = sample_level(t, s, layer, u, v, offx, offy, lo);
+    const float4 b = sample_level(t, s, layer, u, v, offx, offy, lo + 1);
+    return lerp4(a, b, d);
+}
+
+__device__ float4 sample_adaptive(const TexDesc& t, const SampDesc& s, float u, float v, float2 dx, float2 dy,
+                                  float bias) {
+    const float W = (float)t.w, H = (float)t.h;
+    const float ax = dx.x * W, ay = dx.y * H;
+    const float bx = dy.x * W, by = dx.y * H;   // (sic) SB:237
+    const float a2 = fmaf(ay, ay, ax * ax), b2 = fmaf(by, by, bx * bx);
+    const float d = fmaxf(a2, b2);
+    const float lod = fmaxf(0.0f, fmaf(0.5f, log2f(d), bias));
+    return sample_trilinear(t, s, 0, u, v, 0, 0, lod);
+}
+
+__device__ float4 sample_aniso(const TexDesc& t, const SampDesc& s, float u, float v, float2 du, float2 dv,
+                               float bias) {
+    const float dudx = du.x, dudy = du.y, dvdx = dv.x, dvdy = dv.y;
+    const float px = sqrtf(fmaf(dvdx, dvdx, dudx * dudx)) * (float)t.w;
+    const float py = sqrtf(fmaf(dvdy, dvdy, dudy * dudy)) * (float)t.h;
+    const float pmax = fmaxf(px, py), pmin = fminf(px, py);
+    const int maxAniso = (int)s.maxAniso;
+    const int n = (int)fmax(1.0, fmin((double)ceilf(pmax / pmin) + 1e-3, (double)maxAniso + 1e-3));
+    const float lambda = fmaxf(0.0f, log2f(pmax / (float)n));
+    const float ddu = (px > py) ? dudx : dudy, ddv = (px > py) ? dvdx : dvdy;
+    float4 sum = make_float4(0, 0, 0, 0);
+    for (int i = 0; i < n; i++) {
+        const float tt = (float)i / (float)(n + 1) - 0.5f;
+        const float4 r = sample_trilinear(t, s, 0, fmaf(ddu, tt, u), fmaf(ddv, tt, v), 0, 0, lambda + bias);
+        sum.x += r.x; sum.y += r.y; sum.z += r.z; sum.w += r.w;
+    }
+    const float fn = (float)n;
+    return make_float4(sum.x / fn, sum.y / fn, sum.z / fn, sum.w / fn);
+}
+
+__device__ float4 sample_cube(const TexDesc& t, const SampDesc& s, float x, float y, float z, float lod) {
+    const float ax = fabsf(x), ay = fabsf(y), az = fabsf(z);
+    float u, v, norm;
+    int face;
+    if (az >= ax && az >= ay) {
+        face = z < 0.0f ? 5 : 4; norm = 0.5f / az; u = z < 0.0f ? -x : x; v = -y;
+    } else if (ay >= ax) {
+        face = y < 0.0f ? 3 : 2; norm = 0.5f / ay; u = x; v = y < 0.0f ? -z : z;
+    } else {
+        face = x < 0.0f ? 1 : 0; norm = 0.5f / ax; u = x < 0.0f ? z : -z; v = -y;
+    }
+    u = fmaf(u, norm, 0.5f);
+    v = fmaf(v, norm, 0.5f);
+    return sample_trilinear(t, s, face, u, v, 0, 0, lod);
+}
+
+// texture(tex, samp, varyings, uvVaryId, bias) — SB:357-372
+__device__ __forceinline__ float4 tex_grad(const TexDesc& t, const SampDesc& s, float u, float v, float2 ddx,
+                                           float2 ddy, float bias) {
+    return s.aniso ? sample_aniso(t, s, u, v, ddx, ddy, bias) : sample_adaptive(t, s, u, v, ddx, ddy, bias);
+}
+
+// ---- fragment shader registry (static functors inlined into the tile kernel) -----------------
+template <int FS> struct FsTraits { static constexpr bool needsDerivs = false; };
+template <> struct FsTraits<IFRIT_FS_TEXTURED> { static constexpr bool needsDerivs = true; };
+template <> struct FsTraits<IFRIT_FS_DERIV_VIS> { static constexpr bool needsDerivs = true; };
+
+template <int FS>
+__device__ __forceinline__ float4 run_fs(const DrawParams& p, const float4* v, const float4* ddx,
+                                         const float4* ddy, int prim, int fan) {
+    const float* u = p.buf[0];
+    if (FS == IFRIT_FS_VARYING0) return v[0];
+    if (FS == IFRIT_FS_NORMAL_COLOR)
+        return make_float4(fmaf(v[0].x, 0.5f, 0.5f), fmaf(v[0].y, 0.5f, 0.5f), fmaf(v[0].z, 0.5f, 0.5f), 0.5f);
+    if (FS == IFRIT_FS_PRIM_ID) return make_float4((float)prim, (float)fan, 0.0f, 1.0f);
+    if (FS == IFRIT_FS_TEXTURED || FS == IFRIT_FS_TEXTURED_LOD0) {
+        float4 c;
+        if (FS == IFRIT_FS_TEXTURED)
+            c = tex_grad(p.tex[0], p.samp[0], v[1].x, v[1].y, make_float2(ddx[1].x, ddx[1].y),
+                         make_float2(ddy[1].x, ddy[1].y), __ldg(u + 20));
+        else
+            c = sample_trilinear(p.tex[0], p.samp[0], 0, v[1].x, v[1].y, 0, 0, 0.0f);
+        const float nx = v[0].x, ny = v[0].y, nz = v[0].z;
+        const float len = sqrtf(fmaf(nz, nz, fmaf(ny, ny, nx * nx)));
+        float ndl = fmaf(nz, __ldg(u + 18), fmaf(ny, __ldg(u + 17), nx * __ldg(u + 16))) / len;
+        ndl = fmaxf(ndl, 0.2f);
+        return make_float4(c.x * ndl, c.y * ndl, c.z * ndl, 1.0f);
+    }
+    if (FS == IFRIT_FS_SKYBOX) return sample_cube(p.tex[0], p.samp[0], v[0].x, v[0].y, v[0].z, __ldg(u + 20));
+    if (FS == IFRIT_FS_DERIV_VIS) {
+        const float sc = __ldg(u + 21);
+        return make_float4(ddx[1].x * sc, ddx[1].y * sc, ddy[1].x * sc, ddy[1].y * sc);
+    }
+    return make_float4(0, 0, 0, 0);
+}

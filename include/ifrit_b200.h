@@ -1,0 +1,233 @@
+/* ifrit_b200.h — C-ABI of the B200-native tile rasterizer (drop-in boundary).
+ *
+ * The reference's CUDA renderer has NO C ABI of its own (only the CPU renderer is exported:
+ * include/ifrit/softgraphics/engine/export/TileRasterRendererExport.h:33-76).  The interface
+ * being replaced is the C++ class TileRasterRendererCuda
+ * (include/ifrit/softgraphics/engine/tilerastercuda/TileRasterRendererCuda.h:81-115, "RC" below);
+ * this header exports one `iftrcu*` function per public verb of that class, following the
+ * naming / ownership conventions of the reference's `iftr*` exports:
+ *   - opaque instance handle, create/destroy pair (TileRasterRendererExport.h:33-36);
+ *   - bindings are NON-OWNING: the caller keeps host buffers alive
+ *     (TileRasterContextCuda.h:42-49); device mirrors are owned by the instance;
+ *   - POD structs / enums are bit-identical to engine/base/Structures.h:52-97 and
+ *     engine/base/Constants.h:23-96.
+ * Differences, all deliberate: every call returns a status code (the reference
+ * aborts / ignores CUDA errors), state is per instance (the reference keeps it in process-wide
+ * __constant__/__device__ globals, CU:39-58, one renderer per process), and shader objects are
+ * selected from a compiled-in registry of device functors because host virtual objects /
+ * host function pointers (Shaders.h:46-78, :117-120) cannot run on the device.
+ *
+ * No torch / C++ types appear in any signature: plain pointers, ints, floats, POD structs.
+ * The library has NO CPU fallback: every entry point that needs the GPU fails with
+ * IFRIT_ERR_CUDA when no CUDA device is usable.
+ */
+#ifndef IFRIT_B200_H
+#define IFRIT_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IFRIT_B200_API __attribute__((visibility("default")))
+
+/* ---- status codes ------------------------------------------------------------------- */
+enum {
+    IFRIT_OK = 0,
+    IFRIT_ERR_INVALID = 1,     /* bad argument / handle */
+    IFRIT_ERR_UNSUPPORTED = 2, /* verb of the reference API that is out of scope */
+    IFRIT_ERR_CUDA = 3,        /* CUDA runtime failure; see iftrcuGetLastError */
+    IFRIT_ERR_STATE = 4        /* draw issued with incomplete bindings */
+};
+
+/* ---- enums: engine/base/Constants.h:23-96 ------------------------------------------- */
+typedef enum { IF_POLYGON_MODE_FILL = 0, IF_POLYGON_MODE_LINE = 1, IF_POLYGON_MODE_POINT = 2 } IfritPolygonMode;
+typedef enum { IF_CULL_MODE_NONE = 0, IF_CULL_MODE_FRONT = 1, IF_CULL_MODE_BACK = 2,
+               IF_CULL_MODE_FRONT_AND_BACK = 3 } IfritCullMode;
+typedef enum { IF_SAMPLER_ADDRESS_MODE_REPEAT = 0, IF_SAMPLER_ADDRESS_MODE_MIRRORED_REPEAT = 1,
+               IF_SAMPLER_ADDRESS_MODE_CLAMP_TO_EDGE = 2, IF_SAMPLER_ADDRESS_MODE_CLAMP_TO_BORDER = 3,
+               IF_SAMPLER_ADDRESS_MODE_MIRROR_CLAMP_TO_EDGE = 4 } IfritSamplerAddressMode;
+typedef enum { IF_FILTER_NEAREST = 0, IF_FILTER_LINEAR = 1 } IfritFilter;
+typedef enum { IF_BORDER_COLOR_BLACK = 0, IF_BORDER_COLOR_WHITE = 1 } IfritBorderColor;
+typedef enum { IF_IMAGE_TILING_LINEAR = 1, IF_IMAGE_TILING_OPTIMAL = 2 } IfritImageTiling;
+typedef enum { IF_FORMAT_R8G8B8A8_UINT = 0, IF_FORMAT_R32G32B32A32_SFLOAT = 1 } IfritFormat;
+typedef enum { IF_BLEND_FACTOR_ZERO = 0, IF_BLEND_FACTOR_ONE = 1, IF_BLEND_FACTOR_SRC_COLOR = 2,
+               IF_BLEND_FACTOR_ONE_MINUS_SRC_COLOR = 3, IF_BLEND_FACTOR_DST_COLOR = 4,
+               IF_BLEND_FACTOR_ONE_MINUS_DST_COLOR = 5, IF_BLEND_FACTOR_SRC_ALPHA = 6,
+               IF_BLEND_FACTOR_ONE_MINUS_SRC_ALPHA = 7, IF_BLEND_FACTOR_DST_ALPHA = 8,
+               IF_BLEND_FACTOR_ONE_MINUS_DST_ALPHA = 9 } IfritBlendFactor;
+typedef enum { IF_COMPARE_OP_NEVER = 0, IF_COMPARE_OP_LESS = 1, IF_COMPARE_OP_EQUAL = 2,
+               IF_COMPARE_OP_LESS_OR_EQUAL = 3, IF_COMPARE_OP_GREATER = 4, IF_COMPARE_OP_NOT_EQUAL = 5,
+               IF_COMPARE_OP_GREATER_OR_EQUAL = 6, IF_COMPARE_OP_ALWAYS = 7 } IfritCompareOp;
+typedef enum { IF_SAMPLE_COUNT_1_BIT = 1, IF_SAMPLE_COUNT_2_BIT = 2, IF_SAMPLE_COUNT_4_BIT = 4,
+               IF_SAMPLE_COUNT_8_BIT = 8, IF_SAMPLE_COUNT_16_BIT = 16 } IfritSampleCountFlagBits;
+/* engine/base/TypeDescriptor.h:26-41 */
+typedef enum { IFTP_UNDEFINED = 0, IFTP_FLOAT1, IFTP_FLOAT2, IFTP_FLOAT3, IFTP_FLOAT4, IFTP_INT1, IFTP_INT2,
+               IFTP_INT3, IFTP_INT4, IFTP_UINT1, IFTP_UINT2, IFTP_UINT3, IFTP_UINT4 } IfritTypeDescriptorEnum;
+
+/* ---- POD structs: engine/base/Structures.h:39-97 ------------------------------------ */
+typedef struct { uint32_t width, height, depth; } IfritExtent3D;
+typedef struct { int32_t x, y, z; } IfritOffset3D;
+typedef struct {
+    IfritFilter filterMode;
+    IfritSamplerAddressMode addressModeU, addressModeV, addressModeW;
+    IfritBorderColor borderColor;
+    uint8_t anisotropyEnable; /* C++ `bool` */
+    float maxAnisotropy;
+} IfritSamplerT;
+typedef struct {
+    IfritExtent3D extent;
+    IfritImageTiling tilingMode;
+    uint32_t mipLevels;   /* levels BEYOND level 0 (CU:3561-3577) */
+    uint32_t arrayLayers;
+    IfritFormat format;
+} IfritImageCreateInfo;
+typedef struct { uint32_t mipLevel, baseArrayLayer; } IfritImageSubresourceLayers;
+typedef struct {
+    IfritImageSubresourceLayers srcSubresource;
+    IfritExtent3D srcExtentSt, srcExtentEd;
+    IfritImageSubresourceLayers dstSubresource;
+    IfritExtent3D dstExtentSt, dstExtentEd;
+} IfritImageBlit;
+typedef struct {
+    uint32_t bufferOffset;
+    IfritImageSubresourceLayers imageSubresource;
+    IfritOffset3D imageOffset;
+    IfritExtent3D imageExtent;
+} IfritBufferImageCopy;
+typedef struct {
+    uint8_t blendEnable; /* C++ `bool` */
+    IfritBlendFactor srcColorBlendFactor, dstColorBlendFactor, srcAlphaBlendFactor, dstAlphaBlendFactor;
+} IfritColorAttachmentBlendState;
+
+/* ---- shader registry (replaces the VertexShader / FragmentShader objects of Shaders.h:46-78) --
+ * Uniform block = buffer slot 0 (reference: GetBufferPtr(slot), ShaderBuiltinCuda.cuh:394):
+ *   float[0..15] MVP row-major, [16..18] light direction, [20] lod bias / cube lod,
+ *   [21] derivative-visualisation scale. */
+enum { IFRIT_VS_PASSTHROUGH = 0, /* pos = attr0, varying k = attr k+1 */
+       IFRIT_VS_MVP = 1          /* pos = MVP * attr0, varying k = attr k+1 (DemoVertexShaderCuda) */ };
+enum { IFRIT_FS_VARYING0 = 0,     /* colour = varying 0 */
+       IFRIT_FS_NORMAL_COLOR = 1, /* varying0 * 0.5 + 0.5, a = 0.5 (DemoFragmentShaderCuda) */
+       IFRIT_FS_PRIM_ID = 2,      /* (primitive id, fan index, 0, 1) */
+       IFRIT_FS_TEXTURED = 3,     /* texture(0,0,vary,1,bias) * max(N.L, 0.2): adaptive-LOD or anisotropic */
+       IFRIT_FS_TEXTURED_LOD0 = 4,/* textureLod(0,0,uv,0) * max(N.L, 0.2) */
+       IFRIT_FS_SKYBOX = 5,       /* textureCubeLod(0,0,varying0.xyz,lod) */
+       IFRIT_FS_DERIV_VIS = 6     /* (ddx(v1).xy, ddy(v1).xy) * scale */ };
+
+/* coverage-sample convention: which of the reference's two renderers is reproduced */
+enum { IFRIT_CONVENTION_CUDA = 0, /* TileRasterRendererCuda: pixel centre / MSAA table, clip at w=1e-3 */
+       IFRIT_CONVENTION_CPU = 1   /* TileRasterRenderer (AVX2): pixel corner, clip at w=1, z reject */ };
+
+typedef struct iftrcuRenderer iftrcuRenderer; /* opaque; = std::shared_ptr<TileRasterRendererCuda> in RC */
+
+typedef struct {
+    uint64_t triangles_submitted; /* input triangles of the last draw */
+    uint64_t triangles_assembled; /* after clip / cull */
+    uint64_t tile_pairs;          /* (triangle, tile) queue entries */
+    uint64_t fragments_shaded;    /* FS invocations that wrote >= 1 sample */
+    uint64_t kernel_launches;     /* kernels launched by this instance since creation */
+    uint32_t queue_overflow;      /* 1 if the last draw had to be re-issued with a larger queue */
+    uint32_t reserved;
+} iftrcuStats;
+
+/* one assembled triangle, for stage-level parity tests (debug read-back) */
+typedef struct {
+    int32_t prim, fan, clipped, slot;
+    int32_t X[3], Y[3];
+    float Z[3], IW[3];
+    float bary[3][2];
+} iftrcuAssembledTriangle;
+
+/* ---- lifetime (iftrCreateInstance / iftrDestroyInstance / iftrInit) ------------------ */
+IFRIT_B200_API int iftrcuCreateInstance(int cudaDevice, iftrcuRenderer** out);
+IFRIT_B200_API int iftrcuDestroyInstance(iftrcuRenderer* h);
+IFRIT_B200_API int iftrcuInit(iftrcuRenderer* h);                                  /* RC::Init */
+IFRIT_B200_API const char* iftrcuGetLastError(iftrcuRenderer* h);
+/* run on a caller-provided cudaStream_t (e.g. torch's current stream); NULL = own stream */
+IFRIT_B200_API int iftrcuSetStream(iftrcuRenderer* h, void* cudaStream);
+
+/* ---- bindings ------------------------------------------------------------------------- */
+/* RC::bindFrameBuffer(FrameBuffer&, bool): colour = ImageF32 RGBA32F [(y*W+x)*4+c]
+ * (core/data/Image.h:224), depth = ImageF32 F32; host pointers, non-owning; either may be NULL
+ * (device-only rendering).  The colour image is copied back by iftrcuDrawElements (CU:3899-3909). */
+IFRIT_B200_API int iftrcuBindFrameBuffer(iftrcuRenderer* h, float* hostColorRGBA32F, float* hostDepthF32,
+                                         int width, int height, int useDoubleBuffer);
+/* zero-copy variant: render straight into caller-owned DEVICE memory (no host copy-back) */
+IFRIT_B200_API int iftrcuBindFrameBufferDevice(iftrcuRenderer* h, float* devColorRGBA32F, float* devDepthF32,
+                                               int width, int height);
+/* RC::bindVertexBuffer(const VertexBuffer&): interleaved attributes (VertexBuffer.h:28-90);
+ * only IFTP_FLOAT4 attributes are supported (what every reference demo uses). */
+IFRIT_B200_API int iftrcuBindVertexBuffer(iftrcuRenderer* h, const void* hostData, int vertexCount,
+                                          const int* typeDescs, int numAttributes);
+IFRIT_B200_API int iftrcuBindVertexBufferDevice(iftrcuRenderer* h, const void* devData, int vertexCount,
+                                                const int* typeDescs, int numAttributes);
+/* RC::bindIndexBuffer(const std::vector<int>&) */
+IFRIT_B200_API int iftrcuBindIndexBuffer(iftrcuRenderer* h, const int* hostIndices, int indexCount);
+IFRIT_B200_API int iftrcuBindIndexBufferDevice(iftrcuRenderer* h, const int* devIndices, int indexCount);
+/* RC::bindVertexShader(VertexShader*, VaryingDescriptor&) / RC::bindFragmentShader(FragmentShader*) */
+IFRIT_B200_API int iftrcuBindVertexShader(iftrcuRenderer* h, int vertexShaderId, const int* varyingTypeDescs,
+                                          int numVaryings);
+IFRIT_B200_API int iftrcuBindFragmentShader(iftrcuRenderer* h, int fragmentShaderId);
+IFRIT_B200_API int iftrcuLookupVertexShader(const char* name);   /* -1 if unknown */
+IFRIT_B200_API int iftrcuLookupFragmentShader(const char* name); /* -1 if unknown */
+/* out of scope: always IFRIT_ERR_UNSUPPORTED */
+IFRIT_B200_API int iftrcuBindGeometryShader(iftrcuRenderer* h, int shaderId);
+IFRIT_B200_API int iftrcuBindMeshShader(iftrcuRenderer* h, int shaderId, const int* varyingTypeDescs, int n,
+                                        int lx, int ly, int lz);
+IFRIT_B200_API int iftrcuBindTaskShader(iftrcuRenderer* h, int shaderId, const int* varyingTypeDescs, int n);
+
+/* ---- resources ------------------------------------------------------------------------ */
+IFRIT_B200_API int iftrcuCreateTexture(iftrcuRenderer* h, int slot, const IfritImageCreateInfo* ci); /* RC::CreateTexture */
+IFRIT_B200_API int iftrcuCreateSampler(iftrcuRenderer* h, int slot, const IfritSamplerT* s);         /* RC::CreateSampler */
+IFRIT_B200_API int iftrcuGenerateMipmap(iftrcuRenderer* h, int slot, IfritFilter filter);            /* RC::generateMipmap */
+IFRIT_B200_API int iftrcuBlitImage(iftrcuRenderer* h, int srcSlot, int dstSlot, const IfritImageBlit* region,
+                                   IfritFilter filter);                                               /* RC::blitImage */
+IFRIT_B200_API int iftrcuCopyHostBufferToImage(iftrcuRenderer* h, const void* src, int dstSlot,
+                                               const IfritBufferImageCopy* regions, int regionCount); /* RC::copyHostBufferToImage */
+IFRIT_B200_API int iftrcuCopyImageToHostBuffer(iftrcuRenderer* h, int srcSlot, void* dst, size_t nbytes); /* test read-back of the whole chain */
+IFRIT_B200_API int iftrcuCreateBuffer(iftrcuRenderer* h, int slot, int bufSize);                     /* RC::CreateBuffer */
+IFRIT_B200_API int iftrcuCopyHostBufferToBuffer(iftrcuRenderer* h, const void* src, int dstSlot, int size); /* RC::copyHostBufferToBuffer */
+
+/* ---- pipeline state ------------------------------------------------------------------- */
+IFRIT_B200_API int iftrcuSetScissors(iftrcuRenderer* h, const float* xywh, int count); /* RC::SetScissors (Vector4f each) */
+IFRIT_B200_API int iftrcuSetScissorTestEnable(iftrcuRenderer* h, int enable);
+IFRIT_B200_API int iftrcuSetMsaaSamples(iftrcuRenderer* h, IfritSampleCountFlagBits samples);
+IFRIT_B200_API int iftrcuSetRasterizerPolygonMode(iftrcuRenderer* h, IfritPolygonMode mode); /* FILL only */
+IFRIT_B200_API int iftrcuSetBlendFunc(iftrcuRenderer* h, const IfritColorAttachmentBlendState* s); /* blendEnable must be 0 */
+IFRIT_B200_API int iftrcuSetDepthFunc(iftrcuRenderer* h, IfritCompareOp op);
+IFRIT_B200_API int iftrcuSetDepthTestEnable(iftrcuRenderer* h, int enable);
+IFRIT_B200_API int iftrcuSetCullMode(iftrcuRenderer* h, IfritCullMode mode);
+IFRIT_B200_API int iftrcuSetClearValues(iftrcuRenderer* h, const float* clearColorsRGBA, int numColors,
+                                        float clearDepth);
+/* extensions with no reference counterpart */
+IFRIT_B200_API int iftrcuSetSampleConvention(iftrcuRenderer* h, int convention);
+/* sort-first partition: this instance renders only the 64-px super-tiles it owns */
+IFRIT_B200_API int iftrcuSetTilePartition(iftrcuRenderer* h, int rank, int worldSize);
+IFRIT_B200_API int iftrcuSetDebugPrimitiveIds(iftrcuRenderer* h, int enable);
+
+/* ---- draw ----------------------------------------------------------------------------- */
+IFRIT_B200_API int iftrcuClear(iftrcuRenderer* h);        /* RC::clear — fused into the next draw */
+IFRIT_B200_API int iftrcuDrawElements(iftrcuRenderer* h); /* RC::drawElements — asynchronous */
+IFRIT_B200_API int iftrcuDrawMeshTasks(iftrcuRenderer* h, int numWorkGroups, int firstWorkGroup); /* unsupported */
+/* wait for everything issued so far (incl. the host copy-back of the colour image) */
+IFRIT_B200_API int iftrcuSynchronize(iftrcuRenderer* h);
+
+/* ---- read-back / introspection --------------------------------------------------------- */
+IFRIT_B200_API int iftrcuReadColor(iftrcuRenderer* h, float* hostDst);  /* W*H*4 floats, synchronous */
+IFRIT_B200_API int iftrcuReadDepth(iftrcuRenderer* h, float* hostDst);  /* W*H floats */
+IFRIT_B200_API int iftrcuReadPrimitiveIds(iftrcuRenderer* h, int32_t* hostDst); /* W*H*S, needs SetDebugPrimitiveIds */
+IFRIT_B200_API int iftrcuGetDeviceColorPtr(iftrcuRenderer* h, void** out);
+IFRIT_B200_API int iftrcuGetDeviceDepthPtr(iftrcuRenderer* h, void** out);
+IFRIT_B200_API int iftrcuGetStats(iftrcuRenderer* h, iftrcuStats* out);
+/* assembled triangles of the last draw, sorted by slot; returns count via *n (cap = capacity of dst) */
+IFRIT_B200_API int iftrcuReadAssembled(iftrcuRenderer* h, iftrcuAssembledTriangle* dst, int cap, int* n);
+/* pack / unpack the super-tiles owned by `rank` (sort-first gather plumbing, device pointers) */
+IFRIT_B200_API int iftrcuPackOwnedTiles(iftrcuRenderer* h, void* devDst, size_t dstBytes, size_t* usedBytes);
+IFRIT_B200_API int iftrcuUnpackOwnedTiles(iftrcuRenderer* h, const void* devSrc, int rank, int worldSize);
+IFRIT_B200_API size_t iftrcuOwnedTileBytes(int width, int height, int rank, int worldSize);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IFRIT_B200_H */

@@ -176,6 +176,26 @@ int orc_assemble(const orc_state* st, const orc_f4* pos, const int32_t* idx, int
              * "no sample row or column lies strictly inside the bounding box", which is
              * what the reference's rounding rules approximate.  It never changes the
              * image (a sample on the bbox boundary cannot be strictly inside). */
+            {
+                int omin_x = 255, omax_x = 0, omin_y = 255, omax_y = 0;
+                const int ns = cpu ? 1 : st->msaa;
+                for (int k = 0; k < ns; k++) {
+                    int ox, oy;
+                    sample_offset16(st, k, &ox, &oy);
+                    ox *= 16; oy *= 16;
+                    if (ox < omin_x) omin_x = ox;
+                    if (ox > omax_x) omax_x = ox;
+                    if (oy < omin_y) omin_y = oy;
+                    if (oy > omax_y) omax_y = oy;
+                }
+                int64_t px0 = ((minx - omax_x) >> 8) + 1, px1 = (maxx - omin_x - 1) >> 8;
+                int64_t py0 = ((miny - omax_y) >> 8) + 1, py1 = (maxy - omin_y - 1) >> 8;
+                if (px0 < 0) px0 = 0;
+                if (py0 < 0) py0 = 0;
+                if (px1 > st->width - 1) px1 = st->width - 1;
+                if (py1 > st->height - 1) py1 = st->height - 1;
+                if (px0 > px1 || py0 > py1) continue;
+            }
             r.slot = (f == 0) ? t : ntri + t;
             out[n++] = r;
         }

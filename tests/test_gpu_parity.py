@@ -1,0 +1,282 @@
+"""GPU parity tests proper (-m gpu): the CUDA path, called through the C-ABI, against the oracle on the
+same seeded inputs.  Bar: coverage, primitive id and depth bit-exact; colour within 1/255 on >= 99.9 % of
+pixels (BASELINE.json north_star); where no libm call is involved colour is checked bit-exact too."""
+import numpy as np
+import pytest
+import ifrit_v2_b200  # noqa: F401
+from ifrit_v2_b200 import scenes
+from oracle import oracle as O
+from util import oracle_draw, gpu_draw, compare
+
+pytestmark = pytest.mark.gpu
+IDENT = scenes.uniform_block(np.eye(4))
+
+
+@pytest.fixture(scope="module")
+def r(gpu_renderer_factory):
+    return gpu_renderer_factory()
+
+
+@pytest.mark.parametrize("conv", [0, 1])
+def test_kat1_kat2(r, conv):
+    for vb, idx in (scenes.kat1(), scenes.kat2()):
+        kw = dict(cull=2, convention=conv)
+        o = oracle_draw(64, 64, vb, idx, 0, O.FS_VARYING0, 1, IDENT, **kw)
+        g = gpu_draw(r, 64, 64, vb, idx, 0, O.FS_VARYING0, 1, IDENT, **kw)
+        compare(o, g, exact_color=True)
+        assert g["fragments_shaded"] == o["frags"]
+    # pinned counts of SURVEY.md §8c (corner sampling): KAT-1 oracle = reference minus the 31 exact-tie pixels
+    o = oracle_draw(64, 64, *scenes.kat1(), 0, O.FS_VARYING0, 1, IDENT, cull=2, convention=1)
+    assert (o["prim_id"] >= 0).sum() == 961 - 31
+
+
+@pytest.mark.parametrize("msaa", [1, 2, 4, 8, 16])
+@pytest.mark.parametrize("cull", [0, 1, 2])
+def test_random_triangles(r, msaa, cull):
+    W, H = 200, 120   # ragged: not a multiple of the 16-px tile
+    for seed, neg, size, n in [(11, 0.0, 0.25, 200), (12, 0.2, 0.4, 150), (13, 0.0, 0.02, 2500)]:
+        vb, idx = scenes.random_tris(n, seed, neg_w_frac=neg, size=size)
+        kw = dict(msaa=msaa, cull=cull, clear_color=(0.1, 0.2, 0.3, 1.0), clear_depth=1.0)
+        o = oracle_draw(W, H, vb, idx, 0, O.FS_VARYING0, 1, IDENT, **kw)
+        g = gpu_draw(r, W, H, vb, idx, 0, O.FS_VARYING0, 1, IDENT, **kw)
+        compare(o, g, exact_color=True)
+        assert g["triangles_assembled"] == o["assembled"]
+        assert g["fragments_shaded"] == o["frags"]
+
+
+@pytest.mark.parametrize("func", [O.CMP_NEVER, O.CMP_LESS, O.CMP_EQUAL, O.CMP_LEQUAL, O.CMP_GREATER, O.CMP_GEQUAL,
+                                  O.CMP_ALWAYS])
+def test_depth_funcs(r, func):
+    vb, idx = scenes.random_tris(300, 21, size=0.3)
+    vb[:, 2] = np.round(vb[:, 2] / vb[:, 3] * 4) / 4 * vb[:, 3]   # quantised z: many exact depth ties
+    kw = dict(msaa=4, depth_func=func, clear_depth=0.5)
+    o = oracle_draw(160, 96, vb, idx, 0, O.FS_VARYING0, 1, IDENT, **kw)
+    g = gpu_draw(r, 160, 96, vb, idx, 0, O.FS_VARYING0, 1, IDENT, **kw)
+    compare(o, g, exact_color=True)
+
+
+def test_depth_test_disabled_is_always(r):
+    vb, idx = scenes.random_tris(100, 22, size=0.3)
+    o = oracle_draw(96, 96, vb, idx, 0, O.FS_VARYING0, 1, IDENT, depth_func=O.CMP_ALWAYS)
+    g = gpu_draw(r, 96, 96, vb, idx, 0, O.FS_VARYING0, 1, IDENT, depth_func=O.CMP_LESS, depth_test=False)
+    compare(o, g, exact_color=True)
+
+
+def test_assembled_records_bit_exact(r):
+    """Stage-level parity: clip / viewport / snap / cull records (CU:1343-1491) field by field."""
+    W, H = 320, 200
+    vb, idx = scenes.random_tris(4000, 31, neg_w_frac=0.25, size=0.5, extent=1.6)
+    for conv in (0, 1):
+        for cull in (0, 1, 2):
+            gpu_draw(r, W, H, vb, idx, 0, O.FS_PRIM_ID, 0, IDENT, cull=cull, convention=conv)
+            got, n = r.readAssembled(2 * len(idx) // 3)
+            st = O.make_state(W, H, cull=cull, convention=conv)
+            pos, _ = O.vertex_stage(0, IDENT, vb, 0)
+            exp = O.assemble(st, pos, idx)
+            exp = exp[np.argsort(exp["slot"], kind="stable")]
+            assert n == len(exp) and n > 0
+            for f in ("prim", "fan", "clipped", "slot", "X", "Y"):
+                assert np.array_equal(got[f], exp[f]), f
+            for f in ("Z", "IW", "bary"):
+                assert np.array_equal(got[f].view(np.uint32), exp[f].view(np.uint32)), f
+
+
+def test_empty_and_degenerate_inputs(r):
+    W, H = 64, 48
+    vb = np.zeros((3, 8), np.float32)
+    vb[:, 3] = 1.0
+    idx = np.arange(3, dtype=np.int32)   # zero-area triangle
+    o = oracle_draw(W, H, vb, idx, 0, O.FS_VARYING0, 1, IDENT, clear_color=(1, 0, 1, 0), clear_depth=7.0)
+    g = gpu_draw(r, W, H, vb, idx, 0, O.FS_VARYING0, 1, IDENT, clear_color=(1, 0, 1, 0), clear_depth=7.0)
+    compare(o, g, exact_color=True)
+    assert (g["prim_id"] == -1).all() and (g["depth"] == 7.0).all()
+    # no indices at all: the draw degenerates to the (fused) clear
+    g = gpu_draw(r, W, H, vb, idx[:0], 0, O.FS_VARYING0, 1, IDENT, clear_color=(0, 1, 0, 1), clear_depth=3.0)
+    assert (g["color"] == np.array([0, 1, 0, 1], np.float32)).all() and (g["depth"] == 3.0).all()
+    # vertices at w == 0 and behind the eye
+    vb2, idx2 = scenes.random_tris(50, 5, neg_w_frac=0.5)
+    vb2[::7, 3] = 0.0
+    o = oracle_draw(W, H, vb2, idx2, 0, O.FS_VARYING0, 1, IDENT)
+    g = gpu_draw(r, W, H, vb2, idx2, 0, O.FS_VARYING0, 1, IDENT)
+    compare(o, g, exact_color=True)
+
+
+def test_huge_triangles_guard_band(r):
+    """Triangles far larger than the screen: warp-cooperative binning + the 64-bit edge path."""
+    W, H = 256, 160
+    vb, idx = scenes.random_tris(12, 41, size=900.0, extent=3.0)
+    vb2, idx2 = scenes.random_tris(40, 42, size=2.5, extent=1.0)
+    vb = np.concatenate([vb, vb2]); idx = np.arange(len(vb), dtype=np.int32)
+    for msaa in (1, 8):
+        o = oracle_draw(W, H, vb, idx, 0, O.FS_VARYING0, 1, IDENT, msaa=msaa)
+        g = gpu_draw(r, W, H, vb, idx, 0, O.FS_VARYING0, 1, IDENT, msaa=msaa)
+        compare(o, g)
+
+
+def test_scissor_and_no_clear_second_draw(r):
+    W, H = 128, 96
+    vb, idx = scenes.random_tris(120, 51, size=0.4)
+    sc = [(10, 8, 50, 40), (70, 50, 30, 30)]
+    o = oracle_draw(W, H, vb, idx, 0, O.FS_VARYING0, 1, IDENT, msaa=4, scissors=sc, clear_color=(.5, .5, .5, 1))
+    g = gpu_draw(r, W, H, vb, idx, 0, O.FS_VARYING0, 1, IDENT, msaa=4, scissors=sc, clear_color=(.5, .5, .5, 1))
+    compare(o, g, exact_color=True)
+    # second draw on top of the first, load-op LOAD (no clear): depth test against the stored depth
+    vb2, idx2 = scenes.random_tris(120, 52, size=0.4)
+    o2 = oracle_draw(W, H, vb2, idx2, 0, O.FS_VARYING0, 1, IDENT, clear=False, color=o["color"], depth=o["depth"])
+    g2 = gpu_draw(r, W, H, vb2, idx2, 0, O.FS_VARYING0, 1, IDENT, clear=False, color=g["color"], depth=g["depth"])
+    compare(o2, g2, exact_color=True)
+
+
+def _mesh_case(W, H, n=40):
+    vb, idx = scenes.mesh_sphere(n=n)
+    u = scenes.uniform_block(scenes.default_mvp(W, H))
+    return vb, idx, u
+
+
+def test_mesh_normal_color_mvp(r):
+    W, H = 320, 180
+    vb, idx, u = _mesh_case(W, H)
+    for cull, msaa in ((0, 1), (2, 8)):
+        o = oracle_draw(W, H, vb, idx, 1, O.FS_NORMAL_COLOR, 2, u, cull=cull, msaa=msaa)
+        g = gpu_draw(r, W, H, vb, idx, 1, O.FS_NORMAL_COLOR, 2, u, cull=cull, msaa=msaa)
+        compare(o, g, exact_color=True)
+        assert (g["prim_id"] >= 0).mean() > 0.3
+
+
+def test_derivatives_quad(r):
+    """ddx / ddy of the uv varying (ShaderBuiltinCuda.cuh:36-76) incl. helper lanes at triangle edges."""
+    W, H = 320, 180
+    vb, idx, _ = _mesh_case(W, H)
+    u = scenes.uniform_block(scenes.default_mvp(W, H), deriv_scale=64.0)
+    for msaa in (1, 4):
+        o = oracle_draw(W, H, vb, idx, 1, O.FS_DERIV_VIS, 2, u, msaa=msaa, cull=2)
+        g = gpu_draw(r, W, H, vb, idx, 1, O.FS_DERIV_VIS, 2, u, msaa=msaa, cull=2)
+        compare(o, g, exact_color=True)
+
+
+@pytest.mark.parametrize("aniso", [False, True])
+@pytest.mark.parametrize("addr", [0, 1, 2, 3, 4])
+def test_textured_mesh(r, aniso, addr):
+    W, H = 384, 216
+    vb, idx, u = _mesh_case(W, H)
+    vb = vb.copy(); vb[:, 8:10] = vb[:, 8:10] * 1.5 - 0.25   # exercise the address modes outside [0,1]
+    tex = scenes.texture_checker(size=256, seed=7)
+    samp = dict(filterMode=1, addressModeU=addr, addressModeV=addr, borderColor=1, anisotropyEnable=aniso, maxAnisotropy=16.0)
+    chain = O.texture_chain(tex, 8)
+    o = oracle_draw(W, H, vb, idx, 1, O.FS_TEXTURED, 2, u, cull=2, texture_chain=chain, tex_dims=(256, 256), mip_levels=8, sampler=samp)
+    g = gpu_draw(r, W, H, vb, idx, 1, O.FS_TEXTURED, 2, u, cull=2, texture=tex, mip_levels=8, sampler=samp)
+    mx = compare(o, g)   # log2f may differ in the last ulp between libm and the device: tolerance 1/255
+    assert mx < 0.05
+
+
+def test_textured_msaa8_nearest_and_lod0(r):
+    W, H = 256, 144
+    vb, idx, u = _mesh_case(W, H)
+    tex = scenes.texture_checker(size=128, seed=9)
+    chain = O.texture_chain(tex, 7)
+    for fs, samp in ((O.FS_TEXTURED_LOD0, dict(filterMode=1)), (O.FS_TEXTURED, dict(filterMode=0))):
+        o = oracle_draw(W, H, vb, idx, 1, fs, 2, u, cull=2, msaa=8, texture_chain=chain, tex_dims=(128, 128), mip_levels=7, sampler=samp)
+        g = gpu_draw(r, W, H, vb, idx, 1, fs, 2, u, cull=2, msaa=8, texture=tex, mip_levels=7, sampler=samp)
+        compare(o, g)
+
+
+def test_mipmap_generation_bit_exact(r):
+    """invokeMipmapGeneration (CUIMG:132-155): repeated bilinear 2:1 blits, odd sizes, 2 layers."""
+    rng = np.random.default_rng(3)
+    for (w, h, mips, layers, filt) in ((64, 64, 6, 1, 1), (100, 37, 5, 2, 1), (33, 17, 3, 1, 0)):
+        lvl0 = rng.random((layers, h, w, 4), dtype=np.float32)
+        exp = O.texture_chain(lvl0, mips, layers=layers, filter=filt)
+        r.CreateTexture(1, w, h, mips, layers)
+        r.copyHostBufferToImage(lvl0, 1, w, h, layers=tuple(range(layers)))
+        r.generateMipmap(1, filt)
+        got = r.copyImageToHost(1, exp.size // 4)
+        assert np.array_equal(got.view(np.uint32), exp.view(np.uint32))
+
+
+def test_cube_map_skybox(r):
+    W, H = 160, 120
+    rng = np.random.default_rng(8)
+    faces = rng.random((6, 32, 32, 4), dtype=np.float32)
+    chain = O.texture_chain(faces, 3, layers=6)
+    # a full-screen quad whose varying is the view direction
+    vb = np.zeros((4, 8), np.float32)
+    vb[:, :4] = [[-1, -1, .5, 1], [1, -1, .5, 1], [1, 1, .5, 1], [-1, 1, .5, 1]]
+    vb[:, 4:7] = [[-1, -1, 1], [1.3, -1, -0.2], [1, 1, -1], [-1, 0.7, 0.4]]
+    idx = np.array([0, 1, 2, 0, 2, 3], np.int32)
+    u = scenes.uniform_block(np.eye(4), lod_bias=1.25)
+    samp = dict(filterMode=1, addressModeU=2, addressModeV=2)
+    o = oracle_draw(W, H, vb, idx, 0, O.FS_SKYBOX, 1, u, texture_chain=chain, tex_dims=(32, 32), mip_levels=3, layers=6, sampler=samp)
+    g = gpu_draw(r, W, H, vb, idx, 0, O.FS_SKYBOX, 1, u, texture=faces, mip_levels=3, layers=6, sampler=samp)
+    compare(o, g, exact_color=True)
+
+
+def test_small_triangle_soup_binning_stress(r):
+    """S2-style soup at reduced size: queue sizing, shared-memory atomics, ties."""
+    W, H = 480, 270
+    vb, idx = scenes.soup(ntri=60000, width=W, height=H, seed=42)
+    for msaa in (1, 8):
+        o = oracle_draw(W, H, vb, idx, 0, O.FS_VARYING0, 1, IDENT, msaa=msaa, cull=2)
+        g = gpu_draw(r, W, H, vb, idx, 0, O.FS_VARYING0, 1, IDENT, msaa=msaa, cull=2)
+        compare(o, g, exact_color=True)
+        assert g["tile_pairs"] >= g["triangles_assembled"] > 10000
+
+
+def test_unsupported_verbs_return_status(r):
+    from ifrit_v2_b200 import renderer as R
+    for fn, args in ((r.bindGeometryShader, ()), (r.DrawMeshTasks, (1, 0)), (r.setRasterizerPolygonMode, (1,)),
+                     (r.SetDepthFunc, (R.IF_COMPARE_OP_NOT_EQUAL,))):
+        with pytest.raises(R.IfritError) as e:
+            fn(*args)
+        assert e.value.code == R.IFRIT_ERR_UNSUPPORTED
+    with pytest.raises(R.IfritError) as e:
+        r.setBlendFunc(blendEnable=True)
+    assert e.value.code == R.IFRIT_ERR_UNSUPPORTED
+    r.setBlendFunc(blendEnable=False)
+
+
+def test_sort_first_partition_is_bit_identical(r, gpu_renderer_factory):
+    """N tile-interleaved instances + pack / unpack == the single-instance frame."""
+    import torch
+    W, H = 400, 230
+    vb, idx, u = _mesh_case(W, H)
+    full = gpu_draw(r, W, H, vb, idx, 1, O.FS_NORMAL_COLOR, 2, u, msaa=4, cull=2, clear_color=(.2, .3, .4, 1))
+    from ifrit_v2_b200 import renderer as R
+    for world in (2, 3, 8):
+        root = gpu_renderer_factory()
+        root.bindFrameBuffer(np.zeros((H, W, 4), np.float32), np.zeros((H, W), np.float32))
+        for rank in range(world):
+            part = gpu_renderer_factory()
+            gpu_draw(part, W, H, vb, idx, 1, O.FS_NORMAL_COLOR, 2, u, msaa=4, cull=2, clear_color=(.2, .3, .4, 1),
+                     partition=(rank, world))
+            nbytes = R.owned_tile_bytes(W, H, rank, world)
+            buf = torch.empty(nbytes // 4, dtype=torch.float32, device="cuda")
+            part.packOwnedTiles(buf.data_ptr(), nbytes)
+            part.synchronize()
+            torch.cuda.synchronize()
+            root.unpackOwnedTiles(buf.data_ptr(), rank, world)
+            root.synchronize()
+            part.close()
+        assert np.array_equal(root.readColor().view(np.uint32), full["color"].view(np.uint32))
+        root.close()
+
+
+def test_full_size_properties_4k(r):
+    """BASELINE.json full size (4K, mesh50k): size-independent properties — idempotence of a re-draw,
+    8x MSAA coverage is a superset relation with 1x centres, and culled + unculled agree on front faces."""
+    W, H = 3840, 2160
+    vb, idx = scenes.mesh_sphere(n=160)
+    u = scenes.uniform_block(scenes.default_mvp(W, H))
+    a = gpu_draw(r, W, H, vb, idx, 1, O.FS_NORMAL_COLOR, 2, u, cull=2)
+    b = gpu_draw(r, W, H, vb, idx, 1, O.FS_NORMAL_COLOR, 2, u, cull=2)
+    assert np.array_equal(a["color"].view(np.uint32), b["color"].view(np.uint32))
+    assert np.array_equal(a["depth"].view(np.uint32), b["depth"].view(np.uint32))
+    cov = (a["prim_id"][..., 0] >= 0)
+    assert 0.3 < cov.mean() < 0.9
+    c = gpu_draw(r, W, H, vb, idx, 1, O.FS_NORMAL_COLOR, 2, u, cull=0)
+    # the sphere is closed: with depth LESS the nearest surface is a front face, so NONE == BACK
+    same = (a["prim_id"][..., 0] == c["prim_id"][..., 0]).mean()
+    assert same > 0.995
+    # re-drawing the same geometry without clearing changes nothing under LESS (idempotence)
+    d = gpu_draw(r, W, H, vb, idx, 1, O.FS_NORMAL_COLOR, 2, u, cull=2, clear=False, color=a["color"], depth=a["depth"])
+    assert np.array_equal(d["color"].view(np.uint32), a["color"].view(np.uint32))
+    assert (d["prim_id"] == -1).all()
