@@ -1,0 +1,108 @@
+"""Sort-first multi-GPU plumbing (SURVEY.md §8e — no reference counterpart: the reference is single-GPU).
+
+One process per GPU (torchrun).  Geometry is replicated (broadcast once from rank 0), screen ownership is
+interleaved in 64-px super-tiles, ``owner(sx, sy) = (sx + 3*sy) % world`` (ifr_tile_owner in
+csrc/common.cuh); each rank bins / rasterises / shades only the tiles it owns, packs its super-tiles
+contiguously (pack_kernel) and rank 0 gathers them over NCCL (NVLink) and scatters them into the final
+frame (unpack).  There is exactly one exchange step; nothing on the data path before it communicates.
+
+The pure-numpy ``pack_host`` / ``unpack_host`` restate the device layout and are what the gloo CPU tests
+exercise (world_size 2) together with ``gather_frame``."""
+import numpy as np
+
+SUPER = 64
+
+
+def owned_supertiles(width, height, rank, world):
+    sx_n, sy_n = (width + SUPER - 1) // SUPER, (height + SUPER - 1) // SUPER
+    return [(sx, sy) for sy in range(sy_n) for sx in range(sx_n) if (sx + 3 * sy) % world == rank]
+
+
+def owned_mask(width, height, rank, world):
+    ys, xs = np.mgrid[0:height, 0:width]
+    return ((xs // SUPER) + 3 * (ys // SUPER)) % world == rank
+
+
+def pack_host(color, rank, world):
+    """color [H, W, 4] float32 -> [n_owned, 64, 64, 4] (edge super-tiles zero padded)."""
+    h, w = color.shape[:2]
+    tiles = owned_supertiles(w, h, rank, world)
+    out = np.zeros((len(tiles), SUPER, SUPER, 4), dtype=np.float32)
+    for i, (sx, sy) in enumerate(tiles):
+        blk = color[sy * SUPER:(sy + 1) * SUPER, sx * SUPER:(sx + 1) * SUPER]
+        out[i, :blk.shape[0], :blk.shape[1]] = blk
+    return out
+
+
+def unpack_host(dst, packed, rank, world):
+    h, w = dst.shape[:2]
+    packed = np.asarray(packed).reshape(-1, SUPER, SUPER, 4)
+    for i, (sx, sy) in enumerate(owned_supertiles(w, h, rank, world)):
+        blk = dst[sy * SUPER:(sy + 1) * SUPER, sx * SUPER:(sx + 1) * SUPER]
+        blk[...] = packed[i, :blk.shape[0], :blk.shape[1]]
+    return dst
+
+
+def max_owned_floats(width, height, world):
+    return max(len(owned_supertiles(width, height, r, world)) for r in range(world)) * SUPER * SUPER * 4
+
+
+def broadcast_geometry(vb, idx, dist, device):
+    """rank 0 holds numpy (vb, idx); every rank returns torch tensors on `device` (ncclBroadcast)."""
+    import torch
+    rank = dist.get_rank()
+    meta = torch.zeros(3, dtype=torch.int64, device=device)
+    if rank == 0:
+        meta = torch.tensor([vb.shape[0], vb.shape[1], idx.shape[0]], dtype=torch.int64, device=device)
+    dist.broadcast(meta, 0)
+    nv, nf, ni = (int(x) for x in meta.tolist())
+    tvb = torch.from_numpy(np.ascontiguousarray(vb, np.float32)).to(device) if rank == 0 else \
+        torch.empty((nv, nf), dtype=torch.float32, device=device)
+    tib = torch.from_numpy(np.ascontiguousarray(idx, np.int32)).to(device) if rank == 0 else \
+        torch.empty(ni, dtype=torch.int32, device=device)
+    dist.broadcast(tvb, 0)
+    dist.broadcast(tib, 0)
+    return tvb, tib
+
+
+def gather_frame(packed_local, width, height, dist, dst=0):
+    """Gather every rank's packed super-tiles on rank `dst`.
+
+    packed_local: 1-D float32 torch tensor (CPU for gloo, CUDA for NCCL) padded to
+    max_owned_floats().  Returns the list of per-rank tensors on `dst`, None elsewhere."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if world == 1:
+        return [packed_local]
+    outs = [torch.empty_like(packed_local) for _ in range(world)] if rank == dst else None
+    dist.gather(packed_local, outs, dst=dst)
+    return outs
+
+
+class SortFirstRenderer:
+    """Wraps one TileRasterRendererCuda per rank: partition state + pack / NCCL gather / unpack."""
+
+    def __init__(self, renderer, dist, device):
+        import torch
+        self.r, self.dist, self.device = renderer, dist, device
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        renderer.setTilePartition(self.rank, self.world)
+        self.torch = torch
+        self.packed = None
+
+    def gather(self):
+        """After drawElements(): rank 0's device framebuffer becomes the complete frame."""
+        torch, r = self.torch, self.r
+        if self.world == 1:
+            return
+        n = max_owned_floats(r.width, r.height, self.world)
+        if self.packed is None or self.packed.numel() != n:
+            self.packed = torch.zeros(n, dtype=torch.float32, device=self.device)
+        r.packOwnedTiles(self.packed.data_ptr(), n * 4)
+        r.synchronize()   # pack ran on the renderer's stream; NCCL runs on torch's
+        outs = gather_frame(self.packed, r.width, r.height, self.dist)
+        if self.rank == 0:
+            torch.cuda.current_stream().synchronize()
+            for src in range(1, self.world):
+                r.unpackOwnedTiles(outs[src].data_ptr(), src, self.world)
+            r.synchronize()

@@ -36,7 +36,7 @@ def look_at(eye, center, up):
     return (rot @ tr).astype(F)
 
 
-def default_mvp(width, height, eye=(0.0, 0.0, 2.6)):
+def default_mvp(width, height, eye=(0.013, 0.021, 1.8)):
     p = perspective(60.0 * math.pi / 180.0, width / height, 0.1, 100.0)
     v = look_at(eye, (0, 0, 0), (0, 1, 0))
     return (p.astype(np.float64) @ v.astype(np.float64)).astype(F)
@@ -58,7 +58,7 @@ def uniform_block(mvp, light=(0.3, 0.5, -0.8), lod_bias=0.0, deriv_scale=1.0):
 
 def _hash01(ix, iy, seed):
     h = (ix.astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15) + iy.astype(np.uint64) * np.uint64(0xC2B2AE3D27D4EB4F)
-         + np.uint64(seed) * np.uint64(0x165667B19E3779F9))
+         + np.uint64((int(seed) * 0x165667B19E3779F9) & 0xFFFFFFFFFFFFFFFF))
     h ^= h >> np.uint64(29)
     h *= np.uint64(0xBF58476D1CE4E5B9)
     h ^= h >> np.uint64(32)
@@ -95,7 +95,7 @@ def mesh_sphere(n=160, seed=1234):
     Returns (vertex_buffer [V,12] float32 = pos4|normal4|uv4, indices int32 [T*3])."""
     i = np.arange(n + 1)
     u, v = np.meshgrid(i / n, i / n, indexing="xy")
-    theta = u * 2 * np.pi
+    theta = u * 2 * np.pi + 0.1   # keep the seam off the exact screen centre line (exact edge ties)
     phi = (v * 0.98 + 0.01) * np.pi
     r = 1.0 + 0.15 * (fbm(u * 6, v * 6, seed) - 0.5) * 2
     x = r * np.sin(phi) * np.cos(theta)

@@ -1,0 +1,62 @@
+"""CPU test of the N>1 path (world_size 2, gloo): sort-first partition + gather plumbing.
+
+Each rank "renders" only the super-tiles it owns (here: the oracle's frame masked to the rank's tiles,
+because the CUDA path cannot run without a GPU), packs them, rank 0 gathers with torch.distributed and
+unpacks; the result must be bit-identical to the single-rank frame."""
+import os
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, W, H, q):
+    import sys
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ifrit_v2_b200  # noqa: F401
+    from ifrit_v2_b200 import scenes, multigpu as MG
+    from oracle import oracle as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # geometry lives on rank 0 and is broadcast (replicated geometry, sort-first)
+    vb = idx = None
+    if rank == 0:
+        vb, idx = scenes.mesh_sphere(n=24)
+    tvb, tib = MG.broadcast_geometry(vb, idx, dist, "cpu")
+    vb, idx = tvb.numpy(), tib.numpy()
+    u = scenes.uniform_block(scenes.default_mvp(W, H))
+    st = O.make_state(W, H, msaa=4, cull=O.CULL_BACK, clear_color=(.2, .3, .4, 1))
+    full = O.draw(st, vb, idx, O.VS_MVP, O.FS_NORMAL_COLOR, 2, u)["color"]
+    mine = np.where(MG.owned_mask(W, H, rank, world)[..., None], full, np.float32(-1))   # only owned tiles are valid
+    n = MG.max_owned_floats(W, H, world)
+    packed = torch.zeros(n, dtype=torch.float32)
+    p = MG.pack_host(mine, rank, world).reshape(-1)
+    packed[: p.size] = torch.from_numpy(p)
+    outs = MG.gather_frame(packed, W, H, dist)
+    if rank == 0:
+        frame = np.full_like(full, -2)
+        for src in range(world):
+            MG.unpack_host(frame, outs[src].numpy()[: len(MG.owned_supertiles(W, H, src, world)) * 64 * 64 * 4], src, world)
+        q.put(bool(np.array_equal(frame, full)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_sort_first_gather_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 400, 230, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok
