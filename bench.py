@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py — the measurement contract.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--config c2|c3|c4|c5]
+
+One "step" = one frame of the hot path: clear + drawElements (+ the sort-first gather when N > 1) of the
+named BASELINE.json configuration on synthetic, seeded geometry (ifrit-v2_b200/scenes.py).  Prints ONE
+JSON line (rank 0).  See DESIGN.md §6 for the definition of every field.
+
+  value         whole-job Mtris/s (triangles submitted to drawElements / frame time), inputs resident
+                in HBM, CUDA-event timed on the launching stream, max over ranks.
+  e2e           same metric through the C-ABI with HOST buffers: per step the vertex + index buffers are
+                bound from pinned host memory (H2D), the frame is drawn and the colour image is copied
+                back to the host image (D2H), all inside the timed region.
+  roofline      dominant kernel (tile kernel): algorithmic bytes per launch / its CUDA-event duration
+                against MEASURED_PEAKS.json's HBM copy bandwidth.
+  cpu_baseline  the UNMODIFIED reference CPU renderer (oracle/_ref/libifrit_ref.so, 17 threads) timed on
+                this box's host cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # BASELINE.json configs[1..4]; scene definitions in SURVEY.md §8(d)
+    "c2": dict(workload="mesh50k 3840x2160 textured (2048^2 RGBA32F, 11 mips, aniso16) + depth test, 1x",
+               W=3840, H=2160, scene="mesh", msaa=1, cull=0, fs="textured"),
+    "c3": dict(workload="mesh50k 3840x2160 8xMSAA textured aniso16, back-face + contribution cull, ddx/ddy",
+               W=3840, H=2160, scene="mesh", msaa=8, cull=2, fs="textured"),
+    "c4": dict(workload="soup10M 3840x2160 small-triangle soup (binning/atomic stress), 1x",
+               W=3840, H=2160, scene="soup", ntri=10_000_000, msaa=1, cull=2, fs="varying0"),
+    "c5": dict(workload="scene50M 7680x4320 8xMSAA, sort-first over N GPUs",
+               W=7680, H=4320, scene="mix", ntri=50_000_000, msaa=8, cull=2, fs="varying0"),
+}
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.samples, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        mhz, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                mhz.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        mhz.sort()
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(mhz)}
+
+
+def build_scene(cfg, small=False):
+    import ifrit_v2_b200  # noqa: F401
+    from ifrit_v2_b200 import scenes
+    W, H = cfg["W"], cfg["H"]
+    if cfg["scene"] == "mesh":
+        vb, idx = scenes.mesh_sphere(n=160, seed=1234)
+        u = scenes.uniform_block(scenes.default_mvp(W, H))
+        tex = scenes.texture_checker(size=2048 if not small else 256, seed=7)
+        return dict(vb=vb, idx=idx, u=u, tex=tex, vs=1, nvary=2, mips=11 if not small else 8)
+    import numpy as np
+    gen = scenes.soup if cfg["scene"] == "soup" else scenes.scene_mix
+    vb, idx = gen(ntri=cfg["ntri"], width=W, height=H)
+    return dict(vb=vb, idx=idx, u=scenes.uniform_block(np.eye(4)), tex=None, vs=0, nvary=1, mips=0)
+
+
+def algorithmic_bytes(cfg, sc, covered_pixels):
+    """B = V*Sv + I*4 + P*(16+4) + Tex, Tex = min(1.33*covered, texels in chain)*16."""
+    V, Sv = sc["vb"].shape[0], sc["vb"].shape[1] * 4
+    I = sc["idx"].shape[0]
+    P = cfg["W"] * cfg["H"]
+    tex = 0
+    if sc["tex"] is not None:
+        n, w = 0, sc["tex"].shape[0]
+        for _ in range(sc["mips"] + 1):
+            n += w * w
+            w = (w + 1) >> 1
+        tex = int(min(1.33 * covered_pixels, n)) * 16
+    geometry = V * Sv + I * 4
+    tile = P * 20 + tex
+    return dict(frame=geometry + tile, geometry=geometry, tile=tile, tex=tex)
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args, cfg_name):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import ifrit_v2_b200  # noqa: F401
+    from ifrit_v2_b200 import renderer as R, multigpu as MG
+
+    cfg = CONFIGS[cfg_name]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W, H = cfg["W"], cfg["H"]
+
+    sc = build_scene(cfg) if rank == 0 or world == 1 else None
+    if world > 1:
+        # geometry is replicated: broadcast once from rank 0 (static scene)
+        import numpy as _np
+        meta = [None]
+        if rank == 0:
+            meta = [dict(u=sc["u"], tex=sc["tex"], vs=sc["vs"], nvary=sc["nvary"], mips=sc["mips"])]
+        dist.broadcast_object_list(meta, 0)
+        tvb, tib = MG.broadcast_geometry(sc["vb"] if rank == 0 else None, sc["idx"] if rank == 0 else None, dist, dev)
+        if rank != 0:
+            sc = dict(meta[0])
+            sc["vb"], sc["idx"] = _np.empty((tvb.shape[0], tvb.shape[1]), _np.float32), _np.empty(tib.shape[0], _np.int32)
+    else:
+        tvb = torch.from_numpy(sc["vb"]).to(dev)
+        tib = torch.from_numpy(sc["idx"]).to(dev)
+    ntri = tib.shape[0] // 3
+
+    r = R.TileRasterRendererCuda(local)
+    r.Init()
+    stream = torch.cuda.current_stream()
+    r.setStream(stream.cuda_stream)
+    color = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
+    depth = torch.zeros((H, W), dtype=torch.float32, device=dev)
+    r.bindFrameBufferDevice(color, depth, W, H)
+    r.bindVertexBuffer(tvb, tvb.shape[0], tvb.shape[1] // 4, device=True)
+    r.bindIndexBuffer(tib, tib.shape[0], device=True)
+    r.bindVertexShader(sc["vs"], sc["nvary"])
+    r.bindFragmentShader(cfg["fs"])
+    r.CreateBuffer(0, sc["u"].nbytes)
+    r.copyHostBufferToBuffer(sc["u"], 0)
+    if sc["tex"] is not None:
+        s = sc["tex"].shape[0]
+        r.CreateTexture(0, s, s, sc["mips"], 1)
+        r.copyHostBufferToImage(np.ascontiguousarray(sc["tex"][None]), 0, s, s)
+        r.generateMipmap(0, R.IF_FILTER_LINEAR)
+        r.CreateSampler(0, filterMode=R.IF_FILTER_LINEAR, anisotropyEnable=True, maxAnisotropy=16.0)
+    r.setMsaaSamples(cfg["msaa"])
+    r.SetCullMode(cfg["cull"])
+    r.SetDepthFunc(R.IF_COMPARE_OP_LESS)
+    r.SetDepthTestEnable(True)
+    r.setClearValues([(0, 0, 0, 0)], 255.0)   # reference demo clear depth, SG/demo/DefaultDemo.cpp:355
+    sf = MG.SortFirstRenderer(r, dist, dev) if world > 1 else None
+
+    def step():
+        r.clear()
+        r.drawElements()
+        if sf:
+            sf.gather()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    r.synchronize()
+    st0 = r.stats()
+    r.setProfiling(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    ktimes, ndraws = r.kernelTimes()
+    r.setProfiling(False)
+    st1 = r.stats()
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        frags_t = torch.tensor([st1["fragments_shaded"]], dtype=torch.float64, device=dev)
+        dist.all_reduce(frags_t)
+        frags = float(frags_t.item())
+    else:
+        frags = float(st1["fragments_shaded"])
+    ms_step = ms / args.steps
+    launches = st1["kernel_launches"] - st0["kernel_launches"]
+
+    # ---- e2e: host buffers through the C-ABI, H2D + D2H inside the timed region -----------------------
+    hvb = torch.from_numpy(sc["vb"]).pin_memory() if rank == 0 or world == 1 else torch.empty(tvb.shape, dtype=torch.float32).pin_memory()
+    hib = torch.from_numpy(sc["idx"]).pin_memory() if rank == 0 or world == 1 else torch.empty(tib.shape, dtype=torch.int32).pin_memory()
+    if world > 1 and rank != 0:
+        hvb.copy_(tvb.cpu()); hib.copy_(tib.cpu())
+    hcol = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
+    e2e_steps = max(3, min(args.steps, 20))
+
+    def e2e_step():
+        r.bindVertexBuffer(hvb, hvb.shape[0], hvb.shape[1] // 4)        # H2D (pinned, async)
+        r.bindIndexBuffer(hib, hib.shape[0])                           # H2D
+        r.clear()
+        r.drawElements()
+        if sf:
+            sf.gather()
+        if rank == 0:
+            hcol.copy_(color, non_blocking=True)                       # D2H of the step's result
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0.record(stream)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record(stream)
+    barrier()
+    wall = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max(e0.elapsed_time(e1), wall)
+    if world > 1:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_ms /= e2e_steps
+
+    out = None
+    if rank == 0:
+        peak, peak_src = peak_hbm()
+        covered = frags   # FS invocations of one frame (= covered pixels at 1x, >= covered pixels under MSAA)
+        ab = algorithmic_bytes(cfg, sc, covered_pixels=min(covered, W * H))
+        tile_ms = ktimes["tile"]
+        achieved = ab["tile"] / world / (tile_ms * 1e-3) / 1e9 if tile_ms > 0 else 0.0
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(cfg_name)
+            except Exception:
+                traffic = None
+        out = {
+            "metric": "Mtris/s", "value": ntri / (ms_step * 1e-3) / 1e6, "unit": "Mtris/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+            "dtype": "int64 edge functions (24.8 fixed point) + f32 shading", "data": "synthetic",
+            "config": {"workload": cfg["workload"], "name": cfg_name, "triangles": ntri, "resolution": [W, H],
+                       "msaa": cfg["msaa"], "l2": "no explicit flush: per-step working set (framebuffer "
+                       f"{W * H * 20 / 1e6:.0f} MB + texture) exceeds the 126 MB L2",
+                       "parallelism": f"sort-first x{world}" if world > 1 else "1 GPU"},
+            "fps": 1e3 / ms_step, "gfrags_per_s": frags / (ms_step * 1e-3) / 1e9,
+            "fragments_per_frame": frags,
+            "gpu_launches": int(launches),
+            "kernel_ms": ktimes, "kernel_ms_draws": ndraws,
+            "roofline": {"bound": "hbm", "kernel": "tile_kernel", "achieved": achieved, "peak": peak,
+                         "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                         "algorithmic_bytes_per_launch": ab["tile"] / world, "traffic": traffic},
+            "frame_roofline": {"algorithmic_bytes": ab["frame"], "achieved": ab["frame"] / (ms_step * 1e-3) / 1e9,
+                               "frac": ab["frame"] / (ms_step * 1e-3) / 1e9 / peak},
+            "e2e": {"value": ntri / (e2e_ms * 1e-3) / 1e6, "unit": "Mtris/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(hvb.numel() * 4 + hib.numel() * 4),
+                    "d2h_bytes_per_step": int(W * H * 16), "steps": e2e_steps},
+            "clocks": clocks,
+        }
+    r.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_reference(args, cfg_name, steps, warmup):
+    """The reference's own CPU renderer on this box's host cores, same scene / resolution.  The CPU
+    renderer has no sampler library, MSAA or cull-mode state: textured configs use the
+    bilinear LOD-0 C fragment shader, BACK culling is what it always does."""
+    import numpy as np
+    import ifrit_v2_b200  # noqa: F401
+    from oracle import oracle as O, ref_driver as RD
+    cfg = dict(CONFIGS[cfg_name])
+    if not RD.available():
+        return None
+    sc = build_scene(cfg)
+    note = ""
+    if cfg["scene"] != "mesh":
+        # bounded sample: the vertex upload of the reference C ABI is one call per attribute value
+        n = 200_000
+        sc["vb"], sc["idx"] = sc["vb"][: 3 * n], sc["idx"][: 3 * n]
+        note = f" (first {n} triangles)"
+    fs = O.FS_TEXTURED_LOD0 if sc["tex"] is not None else O.FS_VARYING0
+    ref = RD.RefRenderer(cfg["W"], cfg["H"], sc["vb"], sc["idx"], sc["vs"], fs, sc["nvary"], sc["u"], texture=sc["tex"])
+    for _ in range(warmup):
+        ref.draw()
+    ts = ref.timed_draws(steps)
+    ntri = len(sc["idx"]) // 3
+    covered = int((ref.depth() < 1e38).sum())
+    med = sorted(ts)[len(ts) // 2]
+    mean = sum(ts) / len(ts)
+    return dict(ms_per_step=mean * 1e3, median_ms=med * 1e3, min_ms=min(ts) * 1e3, ntri=ntri, covered=covered,
+                value=ntri / mean / 1e6, threads=RD.REF_THREADS, cores=os.cpu_count(),
+                sample=f"{steps} frames of {cfg['workload']}{note}; CPU path: bilinear LOD-0 FS, no MSAA, BACK cull",
+                W=cfg["W"], H=cfg["H"])
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default=None, choices=sorted(CONFIGS))
+    ap.add_argument("--extra-configs", default="c3", help="comma list of further configs measured at N=1 (short runs)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    cfg_name = args.config or "c2"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        res = run_reference(args, cfg_name, steps=min(args.steps, 20), warmup=min(max(args.warmup, 1), 3))
+        if res is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libifrit_ref.so missing (build needs /root/reference)"}))
+            return
+        cfg = CONFIGS[cfg_name]
+        print(json.dumps({
+            "impl": "reference", "metric": "Mtris/s", "value": res["value"], "unit": "Mtris/s", "n_gpus": args.gpus,
+            "steps": min(args.steps, 20), "warmup": min(max(args.warmup, 1), 3), "ms_per_step": res["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (AVX2, rcpps)",
+            "data": "synthetic",
+            "config": {"workload": cfg["workload"], "name": cfg_name, "triangles": res["ntri"], "resolution": [res["W"], res["H"]]},
+            "fps": 1e3 / res["ms_per_step"],
+            "cpu_baseline": {"value": res["value"], "unit": "Mtris/s", "cores": res["cores"], "threads": res["threads"],
+                             "kind": "reference", "sample": res["sample"]},
+            "e2e": {"value": res["value"], "unit": "Mtris/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}))
+        return
+
+    out = run_ours(args, cfg_name)
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1:
+        extras = {}
+        for name in [c for c in args.extra_configs.split(",") if c and c != cfg_name]:
+            sub = argparse.Namespace(**vars(args))
+            sub.steps, sub.warmup = max(5, min(args.steps, 20)), 3
+            try:
+                o = run_ours(sub, name)
+                extras[name] = {k: o[k] for k in ("value", "ms_per_step", "fps", "gfrags_per_s", "kernel_ms", "roofline",
+                                                  "frame_roofline", "e2e", "gpu_launches")}
+                extras[name]["workload"] = o["config"]["workload"]
+            except Exception as ex:   # an extra config must never take the headline down
+                extras[name] = {"error": repr(ex)}
+        out["extra_configs"] = extras
+        if not args.no_cpu_baseline:
+            try:
+                res = run_reference(args, cfg_name, steps=10, warmup=2)
+                if res:
+                    out["cpu_baseline"] = {"value": res["value"], "unit": "Mtris/s", "cores": res["cores"],
+                                           "threads": res["threads"], "kind": "reference", "ms_per_frame": res["ms_per_step"],
+                                           "sample": res["sample"]}
+            except Exception as ex:
+                out["cpu_baseline"] = {"error": repr(ex)}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -13,6 +13,9 @@
 #include "common.cuh"
 #include "../../include/ifrit_b200.h"
 
+#define IFR_PROF_RING 256
+#define IFR_PROF_EVENTS 6   // before vs | setup | scan | fill | tile | after tile
+
 namespace {
 
 struct DevBuf {
@@ -78,6 +81,11 @@ struct iftrcuRenderer {
     unsigned long long* hCounters = nullptr;   // pinned, 8 entries
     bool haveDraw = false;
     iftrcuStats stats;
+
+    // per-kernel timing (CUDA events on the launching stream), ring of the last IFR_PROF_RING draws
+    bool profiling = false;
+    std::vector<cudaEvent_t> profEvents;   // IFR_PROF_RING * IFR_PROF_EVENTS
+    uint64_t profDraws = 0;
 
     int fail(int code, const char* what, const char* detail) {
         lastError = std::string(what) + ": " + (detail ? detail : "");
@@ -152,9 +160,15 @@ static int issue_draw(iftrcuRenderer* r, bool forceCheck) {
     cudaStream_t s = r->stream;
     CUDA_TRY(cudaMemsetAsync(r->tileCount.p, 0, ntiles * 4, s));
     CUDA_TRY(cudaMemsetAsync(r->counters.p, 0, 64, s));
+    cudaEvent_t* ev = nullptr;
+    if (r->profiling && !forceCheck && r->queueChecked) ev = &r->profEvents[(r->profDraws % IFR_PROF_RING) * IFR_PROF_EVENTS];
+    if (ev) CUDA_TRY(cudaEventRecord(ev[0], s));
     CUDA_TRY(ifr_launch_vertex(p, r->vsId, s));
+    if (ev) CUDA_TRY(cudaEventRecord(ev[1], s));
     CUDA_TRY(ifr_launch_setup_count(p, s));
+    if (ev) CUDA_TRY(cudaEventRecord(ev[2], s));
     CUDA_TRY(ifr_launch_scan(p, s));
+    if (ev) CUDA_TRY(cudaEventRecord(ev[3], s));
     r->stats.kernel_launches += 3;
     if (forceCheck || !r->queueChecked) {
         // first draw with this geometry / state: size the (triangle, tile) queue exactly (one sync)
@@ -169,7 +183,9 @@ static int issue_draw(iftrcuRenderer* r, bool forceCheck) {
         r->queueChecked = true;
     }
     CUDA_TRY(ifr_launch_fill(p, s));
+    if (ev) CUDA_TRY(cudaEventRecord(ev[4], s));
     CUDA_TRY(ifr_launch_tiles(p, r->fsId, s));
+    if (ev) { CUDA_TRY(cudaEventRecord(ev[5], s)); r->profDraws++; }
     r->stats.kernel_launches += 2;
     CUDA_TRY(cudaMemcpyAsync(r->hCounters, r->counters.p, 64, cudaMemcpyDeviceToHost, s));
     r->lastDrawCleared = r->pendingClear;
@@ -248,6 +264,7 @@ int iftrcuDestroyInstance(iftrcuRenderer* h) {
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < IFR_MAX_TEX; i++) r->texMem[i].release();
     for (int i = 0; i < IFR_MAX_BUF; i++) r->bufMem[i].release();
+    for (auto& e : r->profEvents) cudaEventDestroy(e);
     if (r->hCounters) cudaFreeHost(r->hCounters);
     if (r->ownStream) cudaStreamDestroy(r->ownStream);
     delete r;
@@ -632,6 +649,36 @@ int iftrcuReadAssembled(iftrcuRenderer* h, iftrcuAssembledTriangle* dst, int cap
         k++;
     }
     *n = k;
+    return IFRIT_OK;
+}
+
+int iftrcuSetProfiling(iftrcuRenderer* h, int enable) {
+    R_CHECK(h);
+    if (enable && r->profEvents.empty()) {
+        r->profEvents.resize(IFR_PROF_RING * IFR_PROF_EVENTS);
+        for (auto& e : r->profEvents) CUDA_TRY(cudaEventCreate(&e));
+    }
+    r->profiling = enable != 0;
+    r->profDraws = 0;
+    return IFRIT_OK;
+}
+
+int iftrcuGetKernelTimes(iftrcuRenderer* h, float* msOut5, int* numDraws) {
+    R_CHECK(h);
+    if (!msOut5 || !numDraws) return IFRIT_ERR_INVALID;
+    int rc = sync_and_check(r); if (rc) return rc;
+    const uint64_t n = std::min<uint64_t>(r->profDraws, IFR_PROF_RING);
+    double acc[5] = {0, 0, 0, 0, 0};
+    for (uint64_t d = 0; d < n; d++) {
+        cudaEvent_t* ev = &r->profEvents[d * IFR_PROF_EVENTS];
+        for (int k = 0; k < 5; k++) {
+            float ms = 0.f;
+            CUDA_TRY(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
+            acc[k] += ms;
+        }
+    }
+    for (int k = 0; k < 5; k++) msOut5[k] = n ? (float)(acc[k] / (double)n) : 0.f;
+    *numDraws = (int)n;
     return IFRIT_OK;
 }
 

@@ -82,9 +82,11 @@ def gather_frame(packed_local, width, height, dist, dst=0):
 class SortFirstRenderer:
     """Wraps one TileRasterRendererCuda per rank: partition state + pack / NCCL gather / unpack."""
 
-    def __init__(self, renderer, dist, device):
+    def __init__(self, renderer, dist, device, same_stream=True):
+        """same_stream: the renderer was given torch's current stream (setStream), so pack -> NCCL ->
+        unpack are ordered on the device and need no host synchronisation."""
         import torch
-        self.r, self.dist, self.device = renderer, dist, device
+        self.r, self.dist, self.device, self.same_stream = renderer, dist, device, same_stream
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         renderer.setTilePartition(self.rank, self.world)
         self.torch = torch
@@ -99,10 +101,14 @@ class SortFirstRenderer:
         if self.packed is None or self.packed.numel() != n:
             self.packed = torch.zeros(n, dtype=torch.float32, device=self.device)
         r.packOwnedTiles(self.packed.data_ptr(), n * 4)
-        r.synchronize()   # pack ran on the renderer's stream; NCCL runs on torch's
+        if not self.same_stream:
+            r.synchronize()   # pack ran on the renderer's own stream; NCCL is ordered after torch's
         outs = gather_frame(self.packed, r.width, r.height, self.dist)
         if self.rank == 0:
-            torch.cuda.current_stream().synchronize()
+            if not self.same_stream:
+                torch.cuda.current_stream().synchronize()
             for src in range(1, self.world):
                 r.unpackOwnedTiles(outs[src].data_ptr(), src, self.world)
-            r.synchronize()
+            if not self.same_stream:
+                r.synchronize()
+            self._keep = outs   # keep the receive buffers alive until the unpack kernels have run

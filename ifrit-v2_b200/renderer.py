@@ -131,6 +131,8 @@ def load_library():
                      "iftrcuSetDebugPrimitiveIds"):
             getattr(L, name).argtypes = [C.c_void_p, C.c_int]
         L.iftrcuSetTilePartition.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.iftrcuSetProfiling.argtypes = [C.c_void_p, C.c_int]
+        L.iftrcuGetKernelTimes.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
         L.iftrcuGenerateMipmap.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.iftrcuCreateBuffer.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.iftrcuDrawMeshTasks.argtypes = [C.c_void_p, C.c_int, C.c_int]
@@ -352,6 +354,18 @@ class TileRasterRendererCuda:
         s = Stats()
         self._ck(self._lib.iftrcuGetStats(self._h, C.byref(s)))
         return {k: getattr(s, k) for k, _ in Stats._fields_ if k != "reserved"}
+
+    KERNEL_NAMES = ("vertex", "setup_count", "scan", "fill", "tile")
+
+    def setProfiling(self, enable=True):
+        self._ck(self._lib.iftrcuSetProfiling(self._h, int(enable)))
+
+    def kernelTimes(self):
+        """Average per-kernel device time in ms over the profiled draws: (dict, number of draws)."""
+        ms = np.zeros(5, dtype=np.float32)
+        n = C.c_int()
+        self._ck(self._lib.iftrcuGetKernelTimes(self._h, _ptr(ms), C.byref(n)))
+        return dict(zip(self.KERNEL_NAMES, (float(x) for x in ms))), n.value
 
     def readAssembled(self, cap):
         out = np.zeros(max(cap, 1), dtype=ASSEMBLED_DTYPE)

@@ -220,6 +220,11 @@ IFRIT_B200_API int iftrcuReadPrimitiveIds(iftrcuRenderer* h, int32_t* hostDst); 
 IFRIT_B200_API int iftrcuGetDeviceColorPtr(iftrcuRenderer* h, void** out);
 IFRIT_B200_API int iftrcuGetDeviceDepthPtr(iftrcuRenderer* h, void** out);
 IFRIT_B200_API int iftrcuGetStats(iftrcuRenderer* h, iftrcuStats* out);
+/* per-kernel device time: CUDA events recorded on the launching stream around each kernel of the draw
+ * chain (vertex, setup+count, scan, fill, tile); averages over the draws issued since SetProfiling(1)
+ * (ring of 256).  Reference analogue: the CU_PROFILER_* switches, KC:128-135. */
+IFRIT_B200_API int iftrcuSetProfiling(iftrcuRenderer* h, int enable);
+IFRIT_B200_API int iftrcuGetKernelTimes(iftrcuRenderer* h, float* msOut5, int* numDraws);
 /* assembled triangles of the last draw, sorted by slot; returns count via *n (cap = capacity of dst) */
 IFRIT_B200_API int iftrcuReadAssembled(iftrcuRenderer* h, iftrcuAssembledTriangle* dst, int cap, int* n);
 /* pack / unpack the super-tiles owned by `rank` (sort-first gather plumbing, device pointers) */
