@@ -170,7 +170,8 @@ def run_ours(args, cfg_name):
 
     r = R.TileRasterRendererCuda(local)
     r.Init()
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)   # one explicit stream for kernels, NCCL ordering and the timing events
+    torch.cuda.set_stream(stream)
     r.setStream(stream.cuda_stream)
     color = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
     depth = torch.zeros((H, W), dtype=torch.float32, device=dev)

@@ -278,7 +278,7 @@ const char* iftrcuGetLastError(iftrcuRenderer* h) { return h ? h->lastError.c_st
 int iftrcuSetStream(iftrcuRenderer* h, void* cudaStream) {
     R_CHECK(h);
     cudaStreamSynchronize(r->stream);
-    r->stream = cudaStream ? (cudaStream_t)cudaStream : r->ownStream;
+    r->stream = (cudaStream == (void*)-1) ? r->ownStream : (cudaStream_t)cudaStream;   // NULL = legacy default stream
     return IFRIT_OK;
 }
 

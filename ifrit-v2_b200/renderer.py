@@ -188,7 +188,9 @@ class TileRasterRendererCuda:
         self._ck(self._lib.iftrcuInit(self._h))
 
     def setStream(self, cuda_stream_ptr):
-        self._ck(self._lib.iftrcuSetStream(self._h, C.c_void_p(cuda_stream_ptr)))
+        """cuda_stream_ptr: cudaStream_t as int (0 = legacy default stream); None = the instance's own stream."""
+        v = C.c_void_p(-1) if cuda_stream_ptr is None else C.c_void_p(cuda_stream_ptr)
+        self._ck(self._lib.iftrcuSetStream(self._h, v))
 
     def bindFrameBuffer(self, color, depth, width=None, height=None, useDoubleBuffer=True):
         """color: host float32 [H,W,4] (ImageF32 RGBA) or None; depth: host float32 [H,W] or None."""

@@ -144,7 +144,8 @@ IFRIT_B200_API int iftrcuCreateInstance(int cudaDevice, iftrcuRenderer** out);
 IFRIT_B200_API int iftrcuDestroyInstance(iftrcuRenderer* h);
 IFRIT_B200_API int iftrcuInit(iftrcuRenderer* h);                                  /* RC::Init */
 IFRIT_B200_API const char* iftrcuGetLastError(iftrcuRenderer* h);
-/* run on a caller-provided cudaStream_t (e.g. torch's current stream); NULL = own stream */
+/* run on a caller-provided cudaStream_t (e.g. torch's current stream).  NULL is the legacy default
+ * stream; (void*)-1 returns to the instance's own non-blocking stream (the initial state). */
 IFRIT_B200_API int iftrcuSetStream(iftrcuRenderer* h, void* cudaStream);
 
 /* ---- bindings ------------------------------------------------------------------------- */

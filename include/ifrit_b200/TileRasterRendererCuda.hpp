@@ -1,0 +1,110 @@
+// TileRasterRendererCuda.hpp — header-only C++ mirror of the reference's
+//   Ifrit::Graphics::SoftGraphics::TileRaster::CUDA::TileRasterRendererCuda
+//   (include/ifrit/softgraphics/engine/tilerastercuda/TileRasterRendererCuda.h:81-115)
+// over the C-ABI of ifrit_b200.h: same verb names, same argument meaning, same non-owning binding
+// contract.  The bind* templates accept the reference's own FrameBuffer / VertexBuffer /
+// VaryingDescriptor types (they only use GetColorAttachment / GetDepthAttachment / getData /
+// GetBufferUnsafe / getVertexCount / getAttributeCount / getVaryingCounts — FrameBuffer.h:48-51,
+// Image.h:141, VertexBuffer.h:42-86, VaryingDescriptor.h:47-52), so a reference caller switches
+// renderers by changing one include and the shader-object arguments (registry ids instead of host
+// virtual objects).  Errors throw std::runtime_error (the reference aborts).
+#pragma once
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "../ifrit_b200.h"
+
+namespace ifrit_b200 {
+
+struct Vector4f { float x, y, z, w; };
+
+class TileRasterRendererCuda {
+public:
+    explicit TileRasterRendererCuda(int cudaDevice = 0) { ck(iftrcuCreateInstance(cudaDevice, &h_), "iftrcuCreateInstance"); }
+    ~TileRasterRendererCuda() { if (h_) iftrcuDestroyInstance(h_); }
+    TileRasterRendererCuda(const TileRasterRendererCuda&) = delete;
+    TileRasterRendererCuda& operator=(const TileRasterRendererCuda&) = delete;
+
+    void Init() { ck(iftrcuInit(h_)); }
+
+    // raw-pointer forms (what the templates below reduce to)
+    void bindFrameBuffer(float* colorRGBA32F, float* depthF32, int width, int height, bool useDoubleBuffer = true) {
+        ck(iftrcuBindFrameBuffer(h_, colorRGBA32F, depthF32, width, height, useDoubleBuffer));
+    }
+    void bindVertexBuffer(const void* data, int vertexCount, int numFloat4Attributes) {
+        std::vector<int> layout(numFloat4Attributes, IFTP_FLOAT4);
+        ck(iftrcuBindVertexBuffer(h_, data, vertexCount, layout.data(), numFloat4Attributes));
+    }
+    void bindIndexBuffer(const std::vector<int>& indexBuffer) {
+        ck(iftrcuBindIndexBuffer(h_, indexBuffer.data(), (int)indexBuffer.size()));
+    }
+    // reference-typed forms
+    template <class FrameBufferT>
+    void bindFrameBuffer(FrameBufferT& fb, bool useDoubleBuffer = true) {
+        auto* c = fb.GetColorAttachment(0);
+        auto* d = fb.GetDepthAttachment();
+        bindFrameBuffer(c->getData(), d ? d->getData() : nullptr, (int)c->GetWidth(), (int)c->GetHeight(), useDoubleBuffer);
+    }
+    template <class VertexBufferT>
+    void bindVertexBuffer(const VertexBufferT& vb) {
+        bindVertexBuffer(vb.GetBufferUnsafe(), vb.getVertexCount(), vb.getAttributeCount());
+    }
+    // shaders: registry id (IFRIT_VS_* / IFRIT_FS_*) or name instead of VertexShader* / FragmentShader*
+    void bindVertexShader(int vertexShaderId, int numVaryings) {
+        std::vector<int> layout(numVaryings > 0 ? numVaryings : 1, IFTP_FLOAT4);
+        ck(iftrcuBindVertexShader(h_, vertexShaderId, layout.data(), numVaryings));
+    }
+    template <class VaryingDescriptorT>
+    void bindVertexShader(int vertexShaderId, VaryingDescriptorT& varyingDescriptor) {
+        bindVertexShader(vertexShaderId, (int)varyingDescriptor.getVaryingCounts());
+    }
+    void bindVertexShader(const char* name, int numVaryings) { bindVertexShader(iftrcuLookupVertexShader(name), numVaryings); }
+    void bindFragmentShader(int fragmentShaderId) { ck(iftrcuBindFragmentShader(h_, fragmentShaderId)); }
+    void bindFragmentShader(const char* name) { bindFragmentShader(iftrcuLookupFragmentShader(name)); }
+    void bindGeometryShader(int id) { ck(iftrcuBindGeometryShader(h_, id)); }
+
+    void CreateTexture(int slotId, const IfritImageCreateInfo& createInfo) { ck(iftrcuCreateTexture(h_, slotId, &createInfo)); }
+    void CreateSampler(int slotId, const IfritSamplerT& samplerState) { ck(iftrcuCreateSampler(h_, slotId, &samplerState)); }
+    void generateMipmap(int slotId, IfritFilter filter) { ck(iftrcuGenerateMipmap(h_, slotId, filter)); }
+    void blitImage(int srcSlotId, int dstSlotId, const IfritImageBlit& region, IfritFilter filter) {
+        ck(iftrcuBlitImage(h_, srcSlotId, dstSlotId, &region, filter));
+    }
+    void copyHostBufferToImage(void* srcBuffer, int dstSlot, const std::vector<IfritBufferImageCopy>& regions) {
+        ck(iftrcuCopyHostBufferToImage(h_, srcBuffer, dstSlot, regions.data(), (int)regions.size()));
+    }
+    void CreateBuffer(int slotId, int bufSize) { ck(iftrcuCreateBuffer(h_, slotId, bufSize)); }
+    void copyHostBufferToBuffer(const void* srcBuffer, int dstSlot, int size) { ck(iftrcuCopyHostBufferToBuffer(h_, srcBuffer, dstSlot, size)); }
+
+    void SetScissors(const std::vector<Vector4f>& scissors) { ck(iftrcuSetScissors(h_, scissors.empty() ? nullptr : &scissors[0].x, (int)scissors.size())); }
+    void setScissorTestEnable(bool option) { ck(iftrcuSetScissorTestEnable(h_, option)); }
+    void setMsaaSamples(IfritSampleCountFlagBits msaaSamples) { ck(iftrcuSetMsaaSamples(h_, msaaSamples)); }
+    void setRasterizerPolygonMode(IfritPolygonMode mode) { ck(iftrcuSetRasterizerPolygonMode(h_, mode)); }
+    void setBlendFunc(IfritColorAttachmentBlendState state) { ck(iftrcuSetBlendFunc(h_, &state)); }
+    void SetDepthFunc(IfritCompareOp depthFunc) { ck(iftrcuSetDepthFunc(h_, depthFunc)); }
+    void SetDepthTestEnable(bool option) { ck(iftrcuSetDepthTestEnable(h_, option)); }
+    void SetCullMode(IfritCullMode cullMode) { ck(iftrcuSetCullMode(h_, cullMode)); }
+    void setClearValues(const std::vector<Vector4f>& clearColors, float clearDepth) {
+        ck(iftrcuSetClearValues(h_, clearColors.empty() ? nullptr : &clearColors[0].x, (int)clearColors.size(), clearDepth));
+    }
+
+    void clear() { ck(iftrcuClear(h_)); }
+    void drawElements() { ck(iftrcuDrawElements(h_)); }
+    void DrawMeshTasks(int numWorkGroups, int firstWorkGroup) { ck(iftrcuDrawMeshTasks(h_, numWorkGroups, firstWorkGroup)); }
+
+    // extensions
+    void synchronize() { ck(iftrcuSynchronize(h_)); }
+    void setTilePartition(int rank, int world) { ck(iftrcuSetTilePartition(h_, rank, world)); }
+    void setSampleConvention(int c) { ck(iftrcuSetSampleConvention(h_, c)); }
+    iftrcuStats stats() { iftrcuStats s; ck(iftrcuGetStats(h_, &s)); return s; }
+    iftrcuRenderer* handle() { return h_; }
+
+private:
+    void ck(int rc, const char* what = nullptr) {
+        if (rc != IFRIT_OK)
+            throw std::runtime_error(std::string("ifrit_b200 error ") + std::to_string(rc) + ": " +
+                                     (h_ ? iftrcuGetLastError(h_) : (what ? what : "no CUDA device (no CPU fallback)")));
+    }
+    iftrcuRenderer* h_ = nullptr;
+};
+
+}  // namespace ifrit_b200
