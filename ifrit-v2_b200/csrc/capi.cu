@@ -394,6 +394,8 @@ int iftrcuCreateTexture(iftrcuRenderer* h, int slot, const IfritImageCreateInfo*
     if (slot < 0 || slot >= IFR_MAX_TEX || !ci || ci->extent.width == 0 || ci->extent.height == 0 || ci->arrayLayers == 0)
         return r->fail(IFRIT_ERR_INVALID, "CreateTexture", "bad argument");
     if (ci->format != IF_FORMAT_R32G32B32A32_SFLOAT) return r->fail(IFRIT_ERR_UNSUPPORTED, "CreateTexture", "only RGBA32F");
+    if (ci->mipLevels >= IFR_MAX_MIPS) return r->fail(IFRIT_ERR_INVALID, "CreateTexture", "at most 15 mip levels beyond level 0");
+    if (chain_texels(ci->extent.width, ci->extent.height, ci->mipLevels, ci->arrayLayers) > 0x7fffffffull) return r->fail(IFRIT_ERR_INVALID, "CreateTexture", "texture chain too large");
     CUDA_TRY(cudaStreamSynchronize(r->stream));
     const size_t n = chain_texels(ci->extent.width, ci->extent.height, ci->mipLevels, ci->arrayLayers);
     CUDA_TRY(r->texMem[slot].ensure(n * 16));
@@ -401,6 +403,18 @@ int iftrcuCreateTexture(iftrcuRenderer* h, int slot, const IfritImageCreateInfo*
     r->tex[slot].data = (const float4*)r->texMem[slot].p;
     r->tex[slot].w = ci->extent.width; r->tex[slot].h = ci->extent.height;
     r->tex[slot].mips = ci->mipLevels; r->tex[slot].layers = ci->arrayLayers;
+    {
+        uint64_t off = 0;
+        int lw = ci->extent.width, lh = ci->extent.height;
+        for (uint32_t l = 0; l <= ci->mipLevels; l++) {
+            TexLevel& L = r->tex[slot].lvl[l];
+            L.w = lw; L.h = lh; L.off = (uint32_t)off; L.layerStride = (uint32_t)((uint64_t)lw * lh);
+            L.invW = 1.0f / (float)lw; L.invH = 1.0f / (float)lh;
+            L.inv2W = 1.0f / (2.0f * (float)lw); L.inv2H = 1.0f / (2.0f * (float)lh);
+            off += (uint64_t)lw * lh * ci->arrayLayers;
+            lw = (lw + 1) >> 1; lh = (lh + 1) >> 1;
+        }
+    }
     r->texTexels[slot] = n;
     return IFRIT_OK;
 }

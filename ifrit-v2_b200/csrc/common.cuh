@@ -21,7 +21,10 @@ struct TriVert { int32_t x, y; float z, iw; };
 #define IFR_FLAG_CLIPPED 1
 #define IFR_FLAG_SWAPPED 2
 
-struct TexDesc { const float4* data; int w, h, mips, layers; };
+#define IFR_MAX_MIPS 16
+// one mip level: dimensions, texel offset of layer 0, texels per layer, reciprocals for address wrapping
+struct TexLevel { int w, h; uint32_t off, layerStride; float invW, invH, inv2W, inv2H; };
+struct TexDesc { const float4* data; int w, h, mips, layers; TexLevel lvl[IFR_MAX_MIPS]; };
 struct SampDesc { int filter, addrU, addrV, addrW, border, aniso; float maxAniso; };
 
 struct DrawParams {

@@ -83,13 +83,14 @@ __device__ __forceinline__ bool setup_tri(const DrawParams& p, uint32_t slot, in
         X[j] = v.x >> 2; Y[j] = v.y; s.Z[j] = __int_as_float(v.z);
     }
     s.slot = slot;
-    const long long sx0 = (long long)tileX * (IFR_TILE * IFR_SUBPIX), sy0 = (long long)tileY * (IFR_TILE * IFR_SUBPIX);
+    // tile origin <= 2^21 and |X|,|Y| <= 2^28: the differences fit int32, products are IMAD.WIDE
+    const int sx0 = tileX * (IFR_TILE * IFR_SUBPIX), sy0 = tileY * (IFR_TILE * IFR_SUBPIX);
     int wide = 0;
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         const int a = (i + 1) % 3, b = (i + 2) % 3;
         s.dX[i] = X[b] - X[a]; s.dY[i] = Y[b] - Y[a];
-        s.E0[i] = (long long)s.dX[i] * (sy0 - Y[a]) - (long long)s.dY[i] * (sx0 - X[a]);
+        s.E0[i] = (long long)s.dX[i] * (long long)(sy0 - Y[a]) - (long long)s.dY[i] * (long long)(sx0 - X[a]);
         wide |= (abs(s.dX[i]) > (1 << 22)) | (abs(s.dY[i]) > (1 << 22));
         long long T = ((-s.E0[i]) >> 4) + 1;
         T = T > 2147483647LL ? 2147483647LL : (T < -2147483648LL ? -2147483648LL : T);
@@ -168,14 +169,14 @@ __device__ __forceinline__ void interp(const DrawParams& p, uint32_t slot, int p
         if (j == 0) flags = v.x & 3;
         X[j] = v.x >> 2; Y[j] = v.y; Z[j] = __int_as_float(v.z); IW[j] = __int_as_float(v.w);
     }
-    const long long sx = (long long)px * IFR_SUBPIX, sy = (long long)py * IFR_SUBPIX;
-    const long long d = (long long)(X[1] - X[0]) * (Y[2] - Y[0]) - (long long)(X[2] - X[0]) * (Y[1] - Y[0]);
+    const int sx = px * IFR_SUBPIX, sy = py * IFR_SUBPIX;
+    const long long d = (long long)(X[1] - X[0]) * (long long)(Y[2] - Y[0]) - (long long)(X[2] - X[0]) * (long long)(Y[1] - Y[0]);
     const float ar = __frcp_rn((float)d);
     float beta[3];
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         const int a = (i + 1) % 3, b = (i + 2) % 3;
-        const long long E = (long long)(X[b] - X[a]) * (sy - Y[a]) - (long long)(Y[b] - Y[a]) * (sx - X[a]);
+        const long long E = (long long)(X[b] - X[a]) * (long long)(sy - Y[a]) - (long long)(Y[b] - Y[a]) * (long long)(sx - X[a]);
         beta[i] = __fmul_rn((float)E, ar);
     }
     depth = fmaf(Z[2], beta[2], fmaf(Z[1], beta[1], __fmul_rn(Z[0], beta[0])));
@@ -215,7 +216,6 @@ __global__ void __launch_bounds__(256) tile_kernel(const __grid_constant__ DrawP
     extern __shared__ unsigned long long keys[];        // [S][256], index = owning thread
     __shared__ TriSetup big[IFR_CHUNK];
     __shared__ int nbig;
-    __shared__ unsigned int fragCount;
 
     const int tileX = blockIdx.x, tileY = blockIdx.y;
     if (p.world > 1 && ifr_tile_owner(tileX, tileY, p.world) != p.rank) return;
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(256) tile_kernel(const __grid_constant__ DrawP
 #pragma unroll
         for (int s = 0; s < S; s++) keys[s * IFR_TILE_PIX + tid] = k0;
     }
-    if (tid == 0) { nbig = 0; fragCount = 0; }
+    if (tid == 0) nbig = 0;
     __syncthreads();
 
     // ---- coverage + early-Z ---------------------------------------------------------------------
@@ -395,9 +395,7 @@ __global__ void __launch_bounds__(256) tile_kernel(const __grid_constant__ DrawP
         }
     }
     myFrags = __reduce_add_sync(0xffffffffu, myFrags);
-    if ((tid & 31) == 0 && myFrags) atomicAdd(&fragCount, myFrags);
-    __syncthreads();
-    if (tid == 0 && fragCount) atomicAdd(&p.counters[2], (unsigned long long)fragCount);
+    if ((tid & 31) == 0 && myFrags) atomicAdd(&p.counters[2], (unsigned long long)myFrags);   // no CTA barrier: warps retire independently
 }
 
 template <int FS>

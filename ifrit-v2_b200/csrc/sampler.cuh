@@ -13,29 +13,21 @@
 #include "common.cuh"
 #include "../../include/ifrit_b200.h"
 
-__device__ __forceinline__ void level_info(const TexDesc& t, int layer, int lod, int& w, int& h, long long& off) {
-    long long o = 0;
-    int lw = t.w, lh = t.h;
-    for (int i = 0; i < lod; i++) {
-        o += (long long)lw * lh * t.layers;
-        lw = (lw + 1) >> 1;
-        lh = (lh + 1) >> 1;
-    }
-    w = lw; h = lh; off = o + (long long)lw * lh * layer;
+__device__ __forceinline__ float wrapf(float c, float s, float invS) {
+    const float q = floorf(c * invS);
+    float r = fmaf(-q, s, c);
+    if (r < 0.0f) r += s;
+    if (r >= s) r -= s;
+    return r;
 }
 
-__device__ __forceinline__ float addr_mode(int mode, float c, int size, bool& border) {
-    const float s = (float)size;
+__device__ __forceinline__ float addr_mode(int mode, float c, float s, float invS, float inv2S, bool& border) {
     switch (mode) {
         case IF_SAMPLER_ADDRESS_MODE_REPEAT:
-            if (c < 0) c += s;
-            c = fmodf(c, s);
-            if (c < 0) c += s;
+            c = wrapf(c, s, invS);
             break;
         case IF_SAMPLER_ADDRESS_MODE_MIRRORED_REPEAT:
-            if (c < 0) c += 2 * s;
-            c = fmodf(c, 2 * s);
-            if (c < 0) c += 2 * s;
+            c = wrapf(c, 2 * s, inv2S);
             c = fminf(c, 2 * s - c);
             break;
         case IF_SAMPLER_ADDRESS_MODE_CLAMP_TO_EDGE:
@@ -58,33 +50,33 @@ __device__ __forceinline__ float4 lerp4(const float4& a, const float4& b, float 
                        fmaf(b.w - a.w, t, a.w));
 }
 
-__device__ float4 sample_level(const TexDesc& t, const SampDesc& s, int layer, float u, float v, int offx,
-                               int offy, int lod) {
-    int w, h;
-    long long off;
+__device__ __forceinline__ float4 sample_level(const TexDesc& t, const SampDesc& s, int layer, float u, float v, int offx,
+                                               int offy, int lod) {
     lod = clampi(lod, 0, t.mips);
-    level_info(t, layer, lod, w, h, off);
+    const TexLevel L = t.lvl[lod];   // precomputed on the host: no per-fetch level walk (SB:97-105)
+    const int w = L.w, h = L.h;
+    const float fw = (float)w, fh = (float)h;
     float cx = fmaf(u, (float)(w - 1), (float)offx);
     float cy = fmaf(v, (float)(h - 1), (float)offy);
     bool border = false;
-    cx = addr_mode(s.addrU, cx, w, border);
-    if (!border) cy = addr_mode(s.addrV, cy, h, border);
+    cx = addr_mode(s.addrU, cx, fw, L.invW, L.inv2W, border);
+    if (!border) cy = addr_mode(s.addrV, cy, fh, L.invH, L.inv2H, border);
     if (border) {
         const float b = s.border == 0 ? 0.0f : 1.0f;
         return make_float4(b, b, b, 1.0f);
     }
-    const float4* base = t.data + off;
+    const float4* base = t.data + L.off + (size_t)L.layerStride * layer;
     if (s.filter == IF_FILTER_NEAREST) {
         int px = (int)roundf(cx), py = (int)roundf(cy);
         px = clampi(px % w, 0, w - 1);
         py = clampi(py % h, 0, h - 1);
-        return __ldg(base + (long long)py * w + px);
+        return __ldg(base + py * w + px);
     }
     const int px = clampi((int)cx, 0, w - 1), py = clampi((int)cy, 0, h - 1);
     const float fx = cx - (float)px, fy = cy - (float)py;
     const int px1 = min(px + 1, w - 1), py1 = min(py + 1, h - 1);
-    const float4 c00 = __ldg(base + (long long)py * w + px), c01 = __ldg(base + (long long)py * w + px1);
-    const float4 c10 = __ldg(base + (long long)py1 * w + px), c11 = __ldg(base + (long long)py1 * w + px1);
+    const float4 c00 = __ldg(base + py * w + px), c01 = __ldg(base + py * w + px1);
+    const float4 c10 = __ldg(base + py1 * w + px), c11 = __ldg(base + py1 * w + px1);
     const float4 a = lerp4(c00, c01, fx), b = lerp4(c10, c11, fx);
     return lerp4(a, b, fy);
 }
@@ -94,6 +86,7 @@ __device__ float4 sample_trilinear(const TexDesc& t, const SampDesc& s, int laye
     const int lo = (int)floorf(lod);
     const float d = lod - (float)lo;
     const float4 a = sample_level(t, s, layer, u, v, offx, offy, lo);
+    if (d == 0.0f) return a;   // lerp(a, b, 0) == a: skip the second level (bit-identical for finite texels)
     const float4 b = sample_level(t, s, layer, u, v, offx, offy, lo + 1);
     return lerp4(a, b, d);
 }
@@ -120,13 +113,13 @@ __device__ float4 sample_aniso(const TexDesc& t, const SampDesc& s, float u, flo
     const float lambda = fmaxf(0.0f, log2f(pmax / (float)n));
     const float ddu = (px > py) ? dudx : dudy, ddv = (px > py) ? dvdx : dvdy;
     float4 sum = make_float4(0, 0, 0, 0);
+    const float step = 1.0f / (float)(n + 1), invN = 1.0f / (float)n;
     for (int i = 0; i < n; i++) {
-        const float tt = (float)i / (float)(n + 1) - 0.5f;
+        const float tt = (float)i * step - 0.5f;
         const float4 r = sample_trilinear(t, s, 0, fmaf(ddu, tt, u), fmaf(ddv, tt, v), 0, 0, lambda + bias);
         sum.x += r.x; sum.y += r.y; sum.z += r.z; sum.w += r.w;
     }
-    const float fn = (float)n;
-    return make_float4(sum.x / fn, sum.y / fn, sum.z / fn, sum.w / fn);
+    return make_float4(sum.x * invN, sum.y * invN, sum.z * invN, sum.w * invN);
 }
 
 __device__ float4 sample_cube(const TexDesc& t, const SampDesc& s, float x, float y, float z, float lod) {

@@ -216,18 +216,25 @@ static void level_info(const orc_texture* t, int layer, int lod, int* w, int* h,
     *w = lw; *h = lh; *off = o + (int64_t)lw * lh * layer;
 }
 
+/* exact float remainder of c by the positive size s (== fmodf for c >= 0, and == fmodf(c + s, s)
+ * for -s <= c < 0, which is what SB:116-124 computes), written with a reciprocal multiply + one
+ * fused multiply-add so that the device does not need the slow exact fmodf loop */
+static float wrapf(float c, float s) {
+    const float q = floorf(c * (1.0f / s));
+    float r = fmaf(-q, s, c);
+    if (r < 0.0f) r += s;
+    if (r >= s) r -= s;
+    return r;
+}
+
 static float addr_mode(int mode, float c, int size, int* border) {
     const float s = (float)size;
     switch (mode) { /* SB:116-160 */
         case ORC_ADDR_REPEAT:
-            if (c < 0) c += s;
-            c = fmodf(c, s);
-            if (c < 0) c += s; /* safety for uv < -1 (reference would index out of bounds) */
+            c = wrapf(c, s);
             break;
         case ORC_ADDR_MIRRORED_REPEAT:
-            if (c < 0) c += 2 * s;
-            c = fmodf(c, 2 * s);
-            if (c < 0) c += 2 * s;
+            c = wrapf(c, 2 * s);
             c = fminf(c, 2 * s - c);
             break;
         case ORC_ADDR_CLAMP_TO_EDGE:
@@ -296,6 +303,10 @@ static void sample_trilinear(const orc_texture* t, const orc_sampler* s, int lay
     const float d = lod - (float)lo;
     float a[4], b[4];
     sample_level(t, s, layer, u, v, offx, offy, lo, a);
+    if (d == 0.0f) { /* lerp(a, b, 0) == a for finite texels: the second level is not fetched */
+        for (int c = 0; c < 4; c++) out[c] = a[c];
+        return;
+    }
     sample_level(t, s, layer, u, v, offx, offy, lo + 1, b);
     for (int c = 0; c < 4; c++) out[c] = fmaf(b[c] - a[c], d, a[c]);
 }
@@ -324,13 +335,14 @@ static void sample_aniso(const orc_texture* t, const orc_sampler* s, float u, fl
     const float lambda = fmaxf(0.0f, log2f(pmax / (float)n));
     const float ddu = (px > py) ? dudx : dudy, ddv = (px > py) ? dvdx : dvdy;
     float sum[4] = {0, 0, 0, 0};
+    const float step = 1.0f / (float)(n + 1), inv_n = 1.0f / (float)n;
     for (int i = 0; i < n; i++) {
-        const float tt = (float)i / (float)(n + 1) - 0.5f;
+        const float tt = (float)i * step - 0.5f;
         float r[4];
         sample_trilinear(t, s, 0, fmaf(ddu, tt, u), fmaf(ddv, tt, v), 0, 0, lambda + bias, r);
         for (int c = 0; c < 4; c++) sum[c] += r[c];
     }
-    for (int c = 0; c < 4; c++) out[c] = sum[c] / (float)n;
+    for (int c = 0; c < 4; c++) out[c] = sum[c] * inv_n;
 }
 
 /* textureCubeCoordConversion SB:184-208, textureCubeImplLod SB:220-231 */
