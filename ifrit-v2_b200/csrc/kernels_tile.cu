@@ -64,25 +64,29 @@ __device__ __forceinline__ bool scissor_pass(const DrawParams& p, int x, int y) 
 }
 
 // ---- per (triangle, tile) setup ---------------------------------------------------------------
-struct TriSetup {
-    int dX[3], dY[3];
-    long long E0[3];      // edge functions at the tile origin
-    int T[3];             // int32 thresholds: inside <=> dX*j - dY*i >= T  (i, j in 1/16 px, tile local)
-    float Z[3], ar;
-    int bx0, bx1, by0, by1;   // tile-local pixel bbox that can contain covered samples
-    uint32_t slot;
-    int wide;             // edge deltas too large for the int32 path
+// 96 bytes = six 16-byte words, read with broadcast LDS.128 by every pixel thread of the tile.
+struct __align__(16) TriS {
+    int dX[3]; uint32_t box;     // box = x0 | x1<<8 | y0<<16 | y1<<24: tile-local pixel bbox that can hold covered samples
+    int dY[3]; uint32_t slot;
+    int T[3]; int wide;          // int32 thresholds: inside <=> dX*j - dY*i >= T (i, j in 1/16 px, tile local); wide: int64 path
+    long long E0[3];             // edge functions at the tile origin
+    float ar, z0, z1, z2;
+    int pad[2];
 };
+static_assert(sizeof(TriS) == 96, "TriS layout");
 
-__device__ __forceinline__ bool setup_tri(const DrawParams& p, uint32_t slot, int tileX, int tileY, TriSetup& s) {
+__device__ __forceinline__ bool setup_tri(const DrawParams& p, uint32_t slot, int tileX, int tileY, TriS& s,
+                                          int& bx0, int& bx1, int& by0, int& by1) {
     const int4* r = reinterpret_cast<const int4*>(p.rec + (size_t)slot * 3);
     int X[3], Y[3];
+    float Z[3];
 #pragma unroll
     for (int j = 0; j < 3; j++) {
         const int4 v = __ldg(r + j);
-        X[j] = v.x >> 2; Y[j] = v.y; s.Z[j] = __int_as_float(v.z);
+        X[j] = v.x >> 2; Y[j] = v.y; Z[j] = __int_as_float(v.z);
     }
     s.slot = slot;
+    s.z0 = Z[0]; s.z1 = Z[1]; s.z2 = Z[2];
     // tile origin <= 2^21 and |X|,|Y| <= 2^28: the differences fit int32, products are IMAD.WIDE
     const int sx0 = tileX * (IFR_TILE * IFR_SUBPIX), sy0 = tileY * (IFR_TILE * IFR_SUBPIX);
     int wide = 0;
@@ -104,29 +108,31 @@ __device__ __forceinline__ bool setup_tri(const DrawParams& p, uint32_t slot, in
     const int px0 = ((minx - p.sampMaxX) >> 8) + 1, px1 = (maxx - p.sampMinX - 1) >> 8;
     const int py0 = ((miny - p.sampMaxY) >> 8) + 1, py1 = (maxy - p.sampMinY - 1) >> 8;
     const int ox = tileX * IFR_TILE, oy = tileY * IFR_TILE;
-    s.bx0 = max(px0 - ox, 0); s.by0 = max(py0 - oy, 0);
-    s.bx1 = min(min(px1, p.W - 1) - ox, IFR_TILE - 1); s.by1 = min(min(py1, p.H - 1) - oy, IFR_TILE - 1);
-    return s.bx0 <= s.bx1 && s.by0 <= s.by1;
+    bx0 = max(px0 - ox, 0); by0 = max(py0 - oy, 0);
+    bx1 = min(min(px1, p.W - 1) - ox, IFR_TILE - 1); by1 = min(min(py1, p.H - 1) - oy, IFR_TILE - 1);
+    s.box = (uint32_t)bx0 | ((uint32_t)bx1 << 8) | ((uint32_t)by0 << 16) | ((uint32_t)by1 << 24);
+    return bx0 <= bx1 && by0 <= by1;
 }
 
-// coverage mask of pixel (lx, ly) of the tile over the S samples
+// coverage mask of the pixel whose origin is (ci, cj) = (16 lx, 16 ly) in 1/16 px, over the S samples
 template <int S>
-__device__ __forceinline__ uint32_t coverage(const DrawParams& p, const TriSetup& s, int lx, int ly) {
+__device__ __forceinline__ uint32_t coverage(const DrawParams& p, const int dX[3], const int dY[3], const int T[3],
+                                             const long long E0[3], int wide, int ci, int cj) {
     uint32_t mask = 0;
-    if (!s.wide) {
+    if (!wide) {
 #pragma unroll
         for (int k = 0; k < S; k++) {
-            const int i = 16 * lx + p.sampX[k], j = 16 * ly + p.sampY[k];
-            const bool in = (s.dX[0] * j - s.dY[0] * i >= s.T[0]) && (s.dX[1] * j - s.dY[1] * i >= s.T[1]) &&
-                            (s.dX[2] * j - s.dY[2] * i >= s.T[2]);
+            const int i = ci + p.sampX[k], j = cj + p.sampY[k];
+            const bool in = (dX[0] * j - dY[0] * i >= T[0]) && (dX[1] * j - dY[1] * i >= T[1]) &&
+                            (dX[2] * j - dY[2] * i >= T[2]);
             mask |= (uint32_t)in << k;
         }
     } else {
         for (int k = 0; k < S; k++) {
-            const long long i = 16 * lx + p.sampX[k], j = 16 * ly + p.sampY[k];
+            const long long i = ci + p.sampX[k], j = cj + p.sampY[k];
             bool in = true;
 #pragma unroll
-            for (int e = 0; e < 3; e++) in = in && (s.E0[e] + 16 * (s.dX[e] * j - s.dY[e] * i) > 0);
+            for (int e = 0; e < 3; e++) in = in && (E0[e] + 16 * (dX[e] * j - dY[e] * i) > 0);
             mask |= (uint32_t)in << k;
         }
     }
@@ -134,14 +140,17 @@ __device__ __forceinline__ uint32_t coverage(const DrawParams& p, const TriSetup
 }
 
 // depth at the integer pixel (lx, ly): beta_i = E_i(corner) / d, from exact integer edge values
-__device__ __forceinline__ float depth_at(const TriSetup& s, int lx, int ly) {
+__device__ __forceinline__ float depth_at(const int dX[3], const int dY[3], const long long E0[3], int wide, float ar,
+                                          float z0, float z1, float z2, int lx, int ly) {
     float beta[3];
 #pragma unroll
     for (int e = 0; e < 3; e++) {
-        const long long Ec = s.E0[e] + 256 * ((long long)s.dX[e] * ly - (long long)s.dY[e] * lx);
-        beta[e] = __fmul_rn((float)Ec, s.ar);
+        long long Ec;
+        if (!wide) Ec = E0[e] + (long long)(dX[e] * ly - dY[e] * lx) * 256;   // |dX|,|dY| <= 2^22: int32 is exact
+        else Ec = E0[e] + 256 * ((long long)dX[e] * ly - (long long)dY[e] * lx);
+        beta[e] = __fmul_rn((float)Ec, ar);
     }
-    return fmaf(s.Z[2], beta[2], fmaf(s.Z[1], beta[1], __fmul_rn(s.Z[0], beta[0])));
+    return fmaf(z2, beta[2], fmaf(z1, beta[1], __fmul_rn(z0, beta[0])));
 }
 
 // tile-local pixel -> key index = index of the owning thread (quad order: 4 consecutive lanes = 2x2)
@@ -157,6 +166,7 @@ __device__ __forceinline__ void key_min_shared(unsigned long long* addr, unsigne
 #define IFR_CHUNK 256
 
 // ---- attribute interpolation at an integer pixel (pixelShadingExecKernel CU:2168-2215) ---------
+template <int NV>
 __device__ __forceinline__ void interp(const DrawParams& p, uint32_t slot, int px, int py, float4* out, float& depth,
                                        int& prim, int& fan) {
     const int4* r = reinterpret_cast<const int4*>(p.rec + (size_t)slot * 3);
@@ -169,6 +179,13 @@ __device__ __forceinline__ void interp(const DrawParams& p, uint32_t slot, int p
         if (j == 0) flags = v.x & 3;
         X[j] = v.x >> 2; Y[j] = v.y; Z[j] = __int_as_float(v.z); IW[j] = __int_as_float(v.w);
     }
+    fan = slot >= (uint32_t)p.ntri;
+    prim = fan ? (int)(slot - (uint32_t)p.ntri) : (int)slot;
+    int idx[3];
+    if (NV > 0) {
+#pragma unroll
+        for (int j = 0; j < 3; j++) idx[j] = __ldg(p.ib + 3 * (size_t)prim + j);
+    }
     const int sx = px * IFR_SUBPIX, sy = py * IFR_SUBPIX;
     const long long d = (long long)(X[1] - X[0]) * (long long)(Y[2] - Y[0]) - (long long)(X[2] - X[0]) * (long long)(Y[1] - Y[0]);
     const float ar = __frcp_rn((float)d);
@@ -180,29 +197,33 @@ __device__ __forceinline__ void interp(const DrawParams& p, uint32_t slot, int p
         beta[i] = __fmul_rn((float)E, ar);
     }
     depth = fmaf(Z[2], beta[2], fmaf(Z[1], beta[1], __fmul_rn(Z[0], beta[0])));
+    if (NV == 0) return;
     float b0 = __fmul_rn(beta[0], IW[0]), b1 = __fmul_rn(beta[1], IW[1]), b2 = __fmul_rn(beta[2], IW[2]);
     const float inv = __frcp_rn(__fadd_rn(__fadd_rn(b0, b1), b2));
     b0 = __fmul_rn(b0, inv); b1 = __fmul_rn(b1, inv); b2 = __fmul_rn(b2, inv);
-    float B[3][2];
+    float u, v;
     if (flags & IFR_FLAG_CLIPPED) {
         const float* cb = p.clipBary + (size_t)slot * 6;
+        float B[3][2];
 #pragma unroll
         for (int j = 0; j < 3; j++) { B[j][0] = __ldg(cb + 2 * j); B[j][1] = __ldg(cb + 2 * j + 1); }
-    } else {   // unclipped: (v2, v3, v1) of the input triangle, first and last exchanged by a cull swap
+        u = fmaf(b2, B[2][0], fmaf(b1, B[1][0], __fmul_rn(b0, B[0][0])));
+        v = fmaf(b2, B[2][1], fmaf(b1, B[1][1], __fmul_rn(b0, B[0][1])));
+    } else {
+        // unclipped: clip barycentrics are those of (v2, v3, v1) of the input triangle, first and last
+        // exchanged by a cull swap: B = {(0,1),(0,0),(1,0)} or {(1,0),(0,0),(0,1)}.  The fma chains with
+        // exact 0 / 1 factors reduce to (x * 1 + 0 * y + 0) = x up to the sign of zero, which + 0.0f fixes.
         const bool sw = flags & IFR_FLAG_SWAPPED;
-        B[0][0] = sw ? 1.0f : 0.0f; B[0][1] = sw ? 0.0f : 1.0f;
-        B[1][0] = 0.0f; B[1][1] = 0.0f;
-        B[2][0] = sw ? 0.0f : 1.0f; B[2][1] = sw ? 1.0f : 0.0f;
+        const float B00 = sw ? 1.0f : 0.0f, B01 = sw ? 0.0f : 1.0f;
+        u = fmaf(b2, B01, fmaf(b1, 0.0f, __fmul_rn(b0, B00)));
+        v = fmaf(b2, B00, fmaf(b1, 0.0f, __fmul_rn(b0, B01)));
     }
-    const float u = fmaf(b2, B[2][0], fmaf(b1, B[1][0], __fmul_rn(b0, B[0][0])));
-    const float v = fmaf(b2, B[2][1], fmaf(b1, B[1][1], __fmul_rn(b0, B[0][1])));
     const float w2 = __fsub_rn(1.0f, __fadd_rn(u, v));
-    fan = slot >= (uint32_t)p.ntri;
-    prim = fan ? (int)(slot - (uint32_t)p.ntri) : (int)slot;
-    const int i0 = __ldg(p.ib + 3 * (size_t)prim), i1 = __ldg(p.ib + 3 * (size_t)prim + 1), i2 = __ldg(p.ib + 3 * (size_t)prim + 2);
-    for (int k = 0; k < p.nvary; k++) {
-        const float4 v0 = __ldg(p.vary + (size_t)i0 * p.nvary + k), v1 = __ldg(p.vary + (size_t)i1 * p.nvary + k),
-                     v2 = __ldg(p.vary + (size_t)i2 * p.nvary + k);
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+        if (k >= p.nvary) { out[k] = make_float4(0, 0, 0, 0); continue; }
+        const float4 v0 = __ldg(p.vary + (size_t)idx[0] * p.nvary + k), v1 = __ldg(p.vary + (size_t)idx[1] * p.nvary + k),
+                     v2 = __ldg(p.vary + (size_t)idx[2] * p.nvary + k);
         out[k].x = fmaf(v2.x, w2, fmaf(v1.x, v, __fmul_rn(v0.x, u)));
         out[k].y = fmaf(v2.y, w2, fmaf(v1.y, v, __fmul_rn(v0.y, u)));
         out[k].z = fmaf(v2.z, w2, fmaf(v1.z, v, __fmul_rn(v0.z, u)));
@@ -212,10 +233,11 @@ __device__ __forceinline__ void interp(const DrawParams& p, uint32_t slot, int p
 
 // ------------------------------------------------------------------------------------------------
 template <int FS, int S>
-__global__ void __launch_bounds__(256) tile_kernel(const __grid_constant__ DrawParams p) {
+__global__ void __launch_bounds__(256, 4) tile_kernel(const __grid_constant__ DrawParams p) {
     extern __shared__ unsigned long long keys[];        // [S][256], index = owning thread
-    __shared__ TriSetup big[IFR_CHUNK];
+    __shared__ TriS big[IFR_CHUNK];
     __shared__ int nbig;
+    constexpr int NV = FsTraits<FS>::nv;
 
     const int tileX = blockIdx.x, tileY = blockIdx.y;
     if (p.world > 1 && ifr_tile_owner(tileX, tileY, p.world) != p.rank) return;
@@ -229,37 +251,51 @@ __global__ void __launch_bounds__(256) tile_kernel(const __grid_constant__ DrawP
     const uint32_t qStart = p.tileStart[tile], qEnd = p.tileStart[tile + 1];
     const bool overflow = p.counters[3] != 0;
     const uint32_t nq = overflow ? 0u : qEnd - qStart;
-    if (nq == 0 && !p.doClear) return;
+    const size_t pidx = (size_t)py * p.W + px;
+    if (nq == 0) {
+        // nothing binned here: the fused clear is all there is to do (imageResetFloat32* CU:3337/3363)
+        if (!p.doClear || !inFrame) return;
+        if (scis) {
+            p.color[pidx] = make_float4(p.clearColor[0], p.clearColor[1], p.clearColor[2], p.clearColor[3]);
+            p.depth[pidx] = p.clearDepth;
+        }
+        if (p.primIds) {
+#pragma unroll
+            for (int s = 0; s < S; s++) p.primIds[pidx * S + s] = -1;
+        }
+        return;
+    }
 
     const int func = p.depthFunc;
-    const size_t pidx = (size_t)py * p.W + px;
     float d0 = 0.0f;
     if (inFrame) d0 = (p.doClear && scis) ? p.clearDepth : p.depth[pidx];
-    {
-        const unsigned long long k0 = key_init(func, d0);
+    const unsigned long long k0 = key_init(func, d0);
 #pragma unroll
-        for (int s = 0; s < S; s++) keys[s * IFR_TILE_PIX + tid] = k0;
-    }
+    for (int s = 0; s < S; s++) keys[s * IFR_TILE_PIX + tid] = k0;
+    unsigned long long best = k0;     // S == 1: this pixel's key for the large-triangle path lives in a register
     if (tid == 0) nbig = 0;
     __syncthreads();
 
     // ---- coverage + early-Z ---------------------------------------------------------------------
+    const int ci = 16 * lx, cj = 16 * ly;
+    const int wy0 = (tid >> 5) * 2;       // a warp owns the 16x2 pixel strip [wy0, wy0+1]
     for (uint32_t base = 0; base < nq; base += IFR_CHUNK) {
         const uint32_t qi = base + tid;
         if (qi < nq) {
-            TriSetup s;
+            TriS s;
+            int bx0, bx1, by0, by1;
             const uint32_t slot = __ldg(p.queue + qStart + qi);
-            if (setup_tri(p, slot, tileX, tileY, s)) {
-                const int area = (s.bx1 - s.bx0 + 1) * (s.by1 - s.by0 + 1);
+            if (setup_tri(p, slot, tileX, tileY, s, bx0, bx1, by0, by1)) {
+                const int area = (bx1 - bx0 + 1) * (by1 - by0 + 1);
                 if (area <= IFR_SMALL_AREA) {
                     // small triangle: this thread walks its few pixels, shared-memory atomicMin
-                    for (int y = s.by0; y <= s.by1; y++)
-                        for (int x = s.bx0; x <= s.bx1; x++) {
-                            const uint32_t m = coverage<S>(p, s, x, y);
+                    for (int y = by0; y <= by1; y++)
+                        for (int x = bx0; x <= bx1; x++) {
+                            const uint32_t m = coverage<S>(p, s.dX, s.dY, s.T, s.E0, s.wide, 16 * x, 16 * y);
                             if (!m) continue;
                             const int gx = tileX * IFR_TILE + x, gy = tileY * IFR_TILE + y;
                             if (p.scissorEnable && !scissor_pass(p, gx, gy)) continue;
-                            const float d = depth_at(s, x, y);
+                            const float d = depth_at(s.dX, s.dY, s.E0, s.wide, s.ar, s.z0, s.z1, s.z2, x, y);
                             unsigned long long k;
                             float dd0 = 0.0f;
                             if (func == IF_COMPARE_OP_EQUAL)
@@ -276,38 +312,53 @@ __global__ void __launch_bounds__(256) tile_kernel(const __grid_constant__ DrawP
             }
         }
         __syncthreads();
-        // large triangles: every thread tests its own pixel, plain stores to its own keys
+        // large triangles: every thread tests its own pixel
         const int nb = nbig;
-        if (scis) {
+        if (nb) {
             for (int b = 0; b < nb; b++) {
-                const TriSetup& s = big[b];
-                if (lx < s.bx0 || lx > s.bx1 || ly < s.by0 || ly > s.by1) continue;
-                const uint32_t m = coverage<S>(p, s, lx, ly);
+                const int4* t4 = reinterpret_cast<const int4*>(&big[b]);
+                const int4 A = t4[0];
+                const int y0 = (A.w >> 16) & 0xff, y1 = (int)((uint32_t)A.w >> 24);
+                if (wy0 + 1 < y0 || wy0 > y1) continue;          // warp-uniform: strip outside the bbox rows
+                const int4 B = t4[1], C = t4[2];
+                const int4 D = t4[3], E = t4[4];
+                const int dX[3] = {A.x, A.y, A.z}, dY[3] = {B.x, B.y, B.z}, T[3] = {C.x, C.y, C.z};
+                const long long E0[3] = {(long long)(((unsigned long long)(uint32_t)D.y << 32) | (uint32_t)D.x),
+                                         (long long)(((unsigned long long)(uint32_t)D.w << 32) | (uint32_t)D.z),
+                                         (long long)(((unsigned long long)(uint32_t)E.y << 32) | (uint32_t)E.x)};
+                const uint32_t m = scis ? coverage<S>(p, dX, dY, T, E0, C.w, ci, cj) : 0u;
                 if (!m) continue;
-                const float d = depth_at(s, lx, ly);
+                const float2 Zr = *reinterpret_cast<const float2*>(t4 + 5);
+                const float d = depth_at(dX, dY, E0, C.w, __int_as_float(E.z), __int_as_float(E.w), Zr.x, Zr.y, lx, ly);
                 unsigned long long k;
-                if (!key_make(func, d, d0, s.slot, k)) continue;
+                if (!key_make(func, d, d0, (uint32_t)B.w, k)) continue;
+                if (S == 1) {
+                    if (k < best) best = k;
+                } else {
 #pragma unroll
-                for (int sm = 0; sm < S; sm++)
-                    if (((m >> sm) & 1) && k < keys[sm * IFR_TILE_PIX + tid]) keys[sm * IFR_TILE_PIX + tid] = k;
+                    for (int sm = 0; sm < S; sm++)
+                        if (((m >> sm) & 1) && k < keys[sm * IFR_TILE_PIX + tid]) keys[sm * IFR_TILE_PIX + tid] = k;
+                }
             }
+            __syncthreads();
+            if (tid == 0) nbig = 0;
         }
-        __syncthreads();
-        if (tid == 0) nbig = 0;
-        __syncthreads();
+        if (base + IFR_CHUNK < nq) __syncthreads();
     }
 
     // ---- quad shading + resolve -----------------------------------------------------------------
     uint32_t mySlots[S];
-    float sampDepth = 0.0f;   // unused for S > 1
-    (void)sampDepth;
 #pragma unroll
-    for (int s = 0; s < S; s++) mySlots[s] = key_slot(func, keys[s * IFR_TILE_PIX + tid]);
+    for (int s = 0; s < S; s++) {
+        unsigned long long k = keys[s * IFR_TILE_PIX + tid];
+        if (S == 1 && best < k) k = best;
+        mySlots[s] = key_slot(func, k);
+    }
 
     float4 acc = make_float4(0, 0, 0, 0);
     float dacc = 0.0f;
     int bg = S;
-    uint32_t last = IFR_SLOT_NONE;   // quad-uniform: last slot shaded (ascending order)
+    uint32_t last = IFR_SLOT_NONE;   // last slot shaded (ascending order); quad-uniform when derivatives are needed
     bool first = true;
     unsigned int myFrags = 0;
     while (true) {
@@ -317,17 +368,25 @@ __global__ void __launch_bounds__(256) tile_kernel(const __grid_constant__ DrawP
             const uint32_t v = mySlots[s];
             if (v != IFR_SLOT_NONE && (first || v > last) && v < mine) mine = v;
         }
-        uint32_t cur = min(mine, __shfl_xor_sync(0xffffffffu, mine, 1));
-        cur = min(cur, __shfl_xor_sync(0xffffffffu, cur, 2));
-        if (__ballot_sync(0xffffffffu, cur != IFR_SLOT_NONE) == 0) break;
+        uint32_t cur = mine;
+        if (FsTraits<FS>::needsDerivs) {
+            // helper lanes: the whole quad interpolates every slot visible anywhere in the quad
+            cur = min(cur, __shfl_xor_sync(0xffffffffu, cur, 1));
+            cur = min(cur, __shfl_xor_sync(0xffffffffu, cur, 2));
+            if (__ballot_sync(0xffffffffu, cur != IFR_SLOT_NONE) == 0) break;
+        } else {
+            // no derivatives: a lane shades exactly its own slots (helper invocations have no observable effect)
+            if (cur == IFR_SLOT_NONE) break;
+        }
         const bool active = cur != IFR_SLOT_NONE;
-        float4 v[IFR_MAX_VARY];
+        float4 v[NV > 0 ? NV : 1];
         float depth = 0.0f;
         int prim = 0, fan = 0;
-        if (active) interp(p, cur, px, py, v, depth, prim, fan);
-        float4 ddx[IFR_MAX_VARY], ddy[IFR_MAX_VARY];
+        if (active) interp<NV>(p, cur, px, py, v, depth, prim, fan);
+        float4 ddx[NV > 0 ? NV : 1], ddy[NV > 0 ? NV : 1];
         if (FsTraits<FS>::needsDerivs) {
-            for (int k = 0; k < p.nvary; k++) {
+#pragma unroll
+            for (int k = 0; k < NV; k++) {
                 // coarse derivatives: right - left of the row, bottom - top of the column (SB:36-76)
                 const float4 a = v[k];
                 float4 o1, o2;
@@ -385,7 +444,7 @@ __global__ void __launch_bounds__(256) tile_kernel(const __grid_constant__ DrawP
             if (bg == S) {   // nothing drawn here: plain clear
                 out = make_float4(p.clearColor[0], p.clearColor[1], p.clearColor[2], p.clearColor[3]);
                 dout = p.clearDepth;
-            } else {
+            } else if (S > 1) {
                 const float fs = (float)S;
                 out.x = out.x / fs; out.y = out.y / fs; out.z = out.z / fs; out.w = out.w / fs;
                 dout = dout / fs;

@@ -50,22 +50,34 @@ __device__ __forceinline__ float4 lerp4(const float4& a, const float4& b, float 
                        fmaf(b.w - a.w, t, a.w));
 }
 
-__device__ __forceinline__ float4 sample_level(const TexDesc& t, const SampDesc& s, int layer, float u, float v, int offx,
-                                               int offy, int lod) {
+// Per-level sampling context: everything that depends on the level only, prepared once per
+// texture() call so that the taps of an anisotropic footprint share it (SB:97-105 walks the level
+// table on every fetch).
+struct LevelCtx { const float4* base; int w, h; float fw, fh, fw1, fh1, invW, invH, inv2W, inv2H; };
+
+__device__ __forceinline__ LevelCtx level_ctx(const TexDesc& t, int layer, int lod) {
     lod = clampi(lod, 0, t.mips);
-    const TexLevel L = t.lvl[lod];   // precomputed on the host: no per-fetch level walk (SB:97-105)
+    const TexLevel& L = t.lvl[lod];
+    LevelCtx c;
+    c.w = L.w; c.h = L.h;
+    c.fw = (float)c.w; c.fh = (float)c.h; c.fw1 = (float)(c.w - 1); c.fh1 = (float)(c.h - 1);
+    c.invW = L.invW; c.invH = L.invH; c.inv2W = L.inv2W; c.inv2H = L.inv2H;
+    c.base = t.data + L.off + (size_t)L.layerStride * layer;
+    return c;
+}
+
+__device__ __forceinline__ float4 sample_level(const LevelCtx& L, const SampDesc& s, float u, float v, int offx, int offy) {
     const int w = L.w, h = L.h;
-    const float fw = (float)w, fh = (float)h;
-    float cx = fmaf(u, (float)(w - 1), (float)offx);
-    float cy = fmaf(v, (float)(h - 1), (float)offy);
+    float cx = fmaf(u, L.fw1, (float)offx);
+    float cy = fmaf(v, L.fh1, (float)offy);
     bool border = false;
-    cx = addr_mode(s.addrU, cx, fw, L.invW, L.inv2W, border);
-    if (!border) cy = addr_mode(s.addrV, cy, fh, L.invH, L.inv2H, border);
+    cx = addr_mode(s.addrU, cx, L.fw, L.invW, L.inv2W, border);
+    if (!border) cy = addr_mode(s.addrV, cy, L.fh, L.invH, L.inv2H, border);
     if (border) {
         const float b = s.border == 0 ? 0.0f : 1.0f;
         return make_float4(b, b, b, 1.0f);
     }
-    const float4* base = t.data + L.off + (size_t)L.layerStride * layer;
+    const float4* base = L.base;
     if (s.filter == IF_FILTER_NEAREST) {
         int px = (int)roundf(cx), py = (int)roundf(cy);
         px = clampi(px % w, 0, w - 1);
@@ -75,24 +87,40 @@ __device__ __forceinline__ float4 sample_level(const TexDesc& t, const SampDesc&
     const int px = clampi((int)cx, 0, w - 1), py = clampi((int)cy, 0, h - 1);
     const float fx = cx - (float)px, fy = cy - (float)py;
     const int px1 = min(px + 1, w - 1), py1 = min(py + 1, h - 1);
-    const float4 c00 = __ldg(base + py * w + px), c01 = __ldg(base + py * w + px1);
-    const float4 c10 = __ldg(base + py1 * w + px), c11 = __ldg(base + py1 * w + px1);
+    const float4* r0 = base + py * w;
+    const float4* r1 = base + py1 * w;
+    const float4 c00 = __ldg(r0 + px), c01 = __ldg(r0 + px1);
+    const float4 c10 = __ldg(r1 + px), c11 = __ldg(r1 + px1);
     const float4 a = lerp4(c00, c01, fx), b = lerp4(c10, c11, fx);
     return lerp4(a, b, fy);
 }
 
-__device__ float4 sample_trilinear(const TexDesc& t, const SampDesc& s, int layer, float u, float v, int offx,
-                                   int offy, float lod) {
+// trilinear footprint shared by n taps: levels floor(lod), floor(lod)+1 and the blend factor
+struct TriCtx { LevelCtx lo, hi; float d; };
+
+__device__ __forceinline__ TriCtx tri_ctx(const TexDesc& t, int layer, float lod) {
+    TriCtx c;
     const int lo = (int)floorf(lod);
-    const float d = lod - (float)lo;
-    const float4 a = sample_level(t, s, layer, u, v, offx, offy, lo);
-    if (d == 0.0f) return a;   // lerp(a, b, 0) == a: skip the second level (bit-identical for finite texels)
-    const float4 b = sample_level(t, s, layer, u, v, offx, offy, lo + 1);
-    return lerp4(a, b, d);
+    c.d = lod - (float)lo;
+    c.lo = level_ctx(t, layer, lo);
+    c.hi = level_ctx(t, layer, lo + 1);
+    return c;
 }
 
-__device__ float4 sample_adaptive(const TexDesc& t, const SampDesc& s, float u, float v, float2 dx, float2 dy,
-                                  float bias) {
+__device__ __forceinline__ float4 sample_trilinear(const TriCtx& c, const SampDesc& s, float u, float v, int offx, int offy) {
+    const float4 a = sample_level(c.lo, s, u, v, offx, offy);
+    if (c.d == 0.0f) return a;   // lerp(a, b, 0) == a: skip the second level (bit-identical for finite texels)
+    const float4 b = sample_level(c.hi, s, u, v, offx, offy);
+    return lerp4(a, b, c.d);
+}
+
+__device__ __forceinline__ float4 sample_trilinear(const TexDesc& t, const SampDesc& s, int layer, float u, float v,
+                                                   int offx, int offy, float lod) {
+    return sample_trilinear(tri_ctx(t, layer, lod), s, u, v, offx, offy);
+}
+
+__device__ __forceinline__ float4 sample_adaptive(const TexDesc& t, const SampDesc& s, float u, float v, float2 dx,
+                                                  float2 dy, float bias) {
     const float W = (float)t.w, H = (float)t.h;
     const float ax = dx.x * W, ay = dx.y * H;
     const float bx = dy.x * W, by = dx.y * H;   // (sic) SB:237
@@ -102,27 +130,40 @@ __device__ float4 sample_adaptive(const TexDesc& t, const SampDesc& s, float u, 
     return sample_trilinear(t, s, 0, u, v, 0, 0, lod);
 }
 
-__device__ float4 sample_aniso(const TexDesc& t, const SampDesc& s, float u, float v, float2 du, float2 dv,
-                               float bias) {
+// 1/k for k = 0..33 as correctly rounded floats (identical to the oracle's 1.0f / (float)k)
+__constant__ float kRcpTab[34] = {
+    0.0f, 1.0f / 1.0f, 1.0f / 2.0f, 1.0f / 3.0f, 1.0f / 4.0f, 1.0f / 5.0f, 1.0f / 6.0f, 1.0f / 7.0f, 1.0f / 8.0f,
+    1.0f / 9.0f, 1.0f / 10.0f, 1.0f / 11.0f, 1.0f / 12.0f, 1.0f / 13.0f, 1.0f / 14.0f, 1.0f / 15.0f, 1.0f / 16.0f,
+    1.0f / 17.0f, 1.0f / 18.0f, 1.0f / 19.0f, 1.0f / 20.0f, 1.0f / 21.0f, 1.0f / 22.0f, 1.0f / 23.0f, 1.0f / 24.0f,
+    1.0f / 25.0f, 1.0f / 26.0f, 1.0f / 27.0f, 1.0f / 28.0f, 1.0f / 29.0f, 1.0f / 30.0f, 1.0f / 31.0f, 1.0f / 32.0f,
+    1.0f / 33.0f};
+__device__ __forceinline__ float rcp_int(int k) { return k <= 33 ? kRcpTab[k] : __fdiv_rn(1.0f, (float)k); }
+
+__device__ __forceinline__ float4 sample_aniso(const TexDesc& t, const SampDesc& s, float u, float v, float2 du, float2 dv,
+                                               float bias) {
     const float dudx = du.x, dudy = du.y, dvdx = dv.x, dvdy = dv.y;
     const float px = sqrtf(fmaf(dvdx, dvdx, dudx * dudx)) * (float)t.w;
     const float py = sqrtf(fmaf(dvdy, dvdy, dudy * dudy)) * (float)t.h;
     const float pmax = fmaxf(px, py), pmin = fminf(px, py);
     const int maxAniso = (int)s.maxAniso;
-    const int n = (int)fmax(1.0, fmin((double)ceilf(pmax / pmin) + 1e-3, (double)maxAniso + 1e-3));
+    // n = (int)fmax(1.0, fmin((double)ceilf(pmax / pmin) + 1e-3, (double)maxAniso + 1e-3)) of SB:252,
+    // without the double-precision detour: ceilf() is integral, NaN / inf fall through to maxAniso
+    const float cr = ceilf(pmax / pmin);
+    const int n = max(1, (cr < (float)maxAniso) ? (int)cr : maxAniso);
     const float lambda = fmaxf(0.0f, log2f(pmax / (float)n));
     const float ddu = (px > py) ? dudx : dudy, ddv = (px > py) ? dvdx : dvdy;
     float4 sum = make_float4(0, 0, 0, 0);
-    const float step = 1.0f / (float)(n + 1), invN = 1.0f / (float)n;
+    const float step = rcp_int(n + 1), invN = rcp_int(n);
+    const TriCtx ctx = tri_ctx(t, 0, lambda + bias);
     for (int i = 0; i < n; i++) {
         const float tt = (float)i * step - 0.5f;
-        const float4 r = sample_trilinear(t, s, 0, fmaf(ddu, tt, u), fmaf(ddv, tt, v), 0, 0, lambda + bias);
+        const float4 r = sample_trilinear(ctx, s, fmaf(ddu, tt, u), fmaf(ddv, tt, v), 0, 0);
         sum.x += r.x; sum.y += r.y; sum.z += r.z; sum.w += r.w;
     }
     return make_float4(sum.x * invN, sum.y * invN, sum.z * invN, sum.w * invN);
 }
 
-__device__ float4 sample_cube(const TexDesc& t, const SampDesc& s, float x, float y, float z, float lod) {
+__device__ __forceinline__ float4 sample_cube(const TexDesc& t, const SampDesc& s, float x, float y, float z, float lod) {
     const float ax = fabsf(x), ay = fabsf(y), az = fabsf(z);
     float u, v, norm;
     int face;
@@ -145,9 +186,12 @@ __device__ __forceinline__ float4 tex_grad(const TexDesc& t, const SampDesc& s, 
 }
 
 // ---- fragment shader registry (static functors inlined into the tile kernel) -----------------
-template <int FS> struct FsTraits { static constexpr bool needsDerivs = false; };
-template <> struct FsTraits<IFRIT_FS_TEXTURED> { static constexpr bool needsDerivs = true; };
-template <> struct FsTraits<IFRIT_FS_DERIV_VIS> { static constexpr bool needsDerivs = true; };
+// nv = number of varyings the shader reads (interpolation of the others is skipped)
+template <int FS> struct FsTraits { static constexpr bool needsDerivs = false; static constexpr int nv = 1; };
+template <> struct FsTraits<IFRIT_FS_PRIM_ID> { static constexpr bool needsDerivs = false; static constexpr int nv = 0; };
+template <> struct FsTraits<IFRIT_FS_TEXTURED> { static constexpr bool needsDerivs = true; static constexpr int nv = 2; };
+template <> struct FsTraits<IFRIT_FS_TEXTURED_LOD0> { static constexpr bool needsDerivs = false; static constexpr int nv = 2; };
+template <> struct FsTraits<IFRIT_FS_DERIV_VIS> { static constexpr bool needsDerivs = true; static constexpr int nv = 2; };
 
 template <int FS>
 __device__ __forceinline__ float4 run_fs(const DrawParams& p, const float4* v, const float4* ddx,
