@@ -76,7 +76,7 @@ struct iftrcuRenderer {
     DevBuf bufMem[IFR_MAX_BUF]; int bufSize[IFR_MAX_BUF] = {0};
 
     // scratch
-    DevBuf pos, vary, rec, clipBary, tileBox, fan1List, tileCount, tileStart, tileCursor, queue, counters;
+    DevBuf pos, vary, rec, clipBary, tileBox, fan1List, tileCount, tileStart, tileCursor, queue, bigQueue, counters;
     bool queueChecked = false;   // queue capacity verified for the current geometry / state
     unsigned long long* hCounters = nullptr;   // pinned, 8 entries
     bool haveDraw = false;
@@ -124,11 +124,13 @@ static void build_params(iftrcuRenderer* r, DrawParams& p) {
     memcpy(p.attrOff, r->attrOff, sizeof p.attrOff);
     p.ib = r->dIB; p.ntri = r->icount / 3;
     p.pos = (float4*)r->pos.p; p.vary = (float4*)r->vary.p;
-    p.rec = (TriVert*)r->rec.p; p.clipBary = (float*)r->clipBary.p; p.tileBox = (uint2*)r->tileBox.p;
+    p.rec = (TriRec*)r->rec.p; p.clipBary = (float*)r->clipBary.p; p.tileBox = (uint2*)r->tileBox.p;
     p.fan1List = (uint32_t*)r->fan1List.p;
     p.tileCount = (uint32_t*)r->tileCount.p; p.tileStart = (uint32_t*)r->tileStart.p;
     p.tileCursor = (uint32_t*)r->tileCursor.p; p.queue = (uint32_t*)r->queue.p;
     p.queueCap = (uint32_t)std::min<size_t>(r->queue.cap / 4, 0xffffffffu);
+    p.bigQueue = (TriS*)r->bigQueue.p;
+    p.bigCap = (uint32_t)std::min<size_t>(r->bigQueue.cap / sizeof(TriS), 0xffffffffu);
     p.counters = (unsigned long long*)r->counters.p;
     for (int i = 0; i < IFR_MAX_TEX; i++) { p.tex[i] = r->tex[i]; p.samp[i] = r->samp[i]; }
     for (int i = 0; i < IFR_MAX_BUF; i++) p.buf[i] = (const float*)r->bufMem[i].p;
@@ -138,15 +140,16 @@ static int ensure_scratch(iftrcuRenderer* r) {
     const size_t ntri = (size_t)r->icount / 3, ntiles = (size_t)((r->W + 15) / 16) * ((r->H + 15) / 16);
     CUDA_TRY(r->pos.ensure(std::max<size_t>(1, r->nverts) * sizeof(float4)));
     CUDA_TRY(r->vary.ensure(std::max<size_t>(1, (size_t)r->nverts * std::max(1, r->nvary)) * sizeof(float4)));
-    CUDA_TRY(r->rec.ensure(std::max<size_t>(1, 2 * ntri) * 3 * sizeof(TriVert)));
+    CUDA_TRY(r->rec.ensure(std::max<size_t>(1, 2 * ntri) * sizeof(TriRec)));
     CUDA_TRY(r->clipBary.ensure(std::max<size_t>(1, 2 * ntri) * 6 * sizeof(float)));
     CUDA_TRY(r->tileBox.ensure(std::max<size_t>(1, 2 * ntri) * sizeof(uint2)));
     CUDA_TRY(r->fan1List.ensure(std::max<size_t>(1, ntri) * sizeof(uint32_t)));
-    CUDA_TRY(r->tileCount.ensure(ntiles * 4));
-    CUDA_TRY(r->tileStart.ensure((ntiles + 1) * 4));
-    CUDA_TRY(r->tileCursor.ensure(ntiles * 4));
+    CUDA_TRY(r->tileCount.ensure(2 * ntiles * 4));
+    CUDA_TRY(r->tileStart.ensure(2 * (ntiles + 1) * 4));
+    CUDA_TRY(r->tileCursor.ensure(2 * ntiles * 4));
     CUDA_TRY(r->counters.ensure(8 * 8));
     if (!r->queue.p) CUDA_TRY(r->queue.ensure(std::max<size_t>(ntri * 2 + ntiles, 1024) * 4));
+    if (!r->bigQueue.p) CUDA_TRY(r->bigQueue.ensure(std::max<size_t>(ntri / 4 + ntiles, 1024) * sizeof(TriS)));
     if (r->debugIds) CUDA_TRY(r->primIds.ensure((size_t)r->W * r->H * r->msaa * 4));
     return IFRIT_OK;
 }
@@ -158,7 +161,7 @@ static int issue_draw(iftrcuRenderer* r, bool forceCheck) {
     build_params(r, p);
     const size_t ntiles = (size_t)p.tilesX * p.tilesY;
     cudaStream_t s = r->stream;
-    CUDA_TRY(cudaMemsetAsync(r->tileCount.p, 0, ntiles * 4, s));
+    CUDA_TRY(cudaMemsetAsync(r->tileCount.p, 0, 2 * ntiles * 4, s));
     CUDA_TRY(cudaMemsetAsync(r->counters.p, 0, 64, s));
     cudaEvent_t* ev = nullptr;
     if (r->profiling && !forceCheck && r->queueChecked) ev = &r->profEvents[(r->profDraws % IFR_PROF_RING) * IFR_PROF_EVENTS];
@@ -177,6 +180,7 @@ static int issue_draw(iftrcuRenderer* r, bool forceCheck) {
         CUDA_TRY(cudaStreamSynchronize(s));
         if (c[3]) {
             CUDA_TRY(r->queue.ensure((size_t)(c[1] + c[1] / 4 + 1024) * 4));
+            CUDA_TRY(r->bigQueue.ensure((size_t)(c[5] + c[5] / 4 + 1024) * sizeof(TriS)));
             CUDA_TRY(cudaMemsetAsync((char*)r->counters.p + 24, 0, 8, s));
             build_params(r, p);
         }
@@ -219,7 +223,7 @@ static int sync_and_check(iftrcuRenderer* r) {
     }
     if (r->haveDraw) {
         r->stats.triangles_assembled = r->hCounters[0];
-        r->stats.tile_pairs = r->hCounters[1];
+        r->stats.tile_pairs = r->hCounters[1] + r->hCounters[5];
         r->stats.fragments_shaded = r->hCounters[2];
     }
     return IFRIT_OK;
@@ -260,7 +264,7 @@ int iftrcuDestroyInstance(iftrcuRenderer* h) {
     cudaStreamSynchronize(r->stream);
     if (r->registeredHost) cudaHostUnregister(r->registeredHost);
     DevBuf* bufs[] = {&r->ownColor, &r->ownDepth, &r->primIds, &r->ownVB, &r->ownIB, &r->pos, &r->vary, &r->rec, &r->clipBary,
-                      &r->tileBox, &r->fan1List, &r->tileCount, &r->tileStart, &r->tileCursor, &r->queue, &r->counters};
+                      &r->tileBox, &r->fan1List, &r->tileCount, &r->tileStart, &r->tileCursor, &r->queue, &r->bigQueue, &r->counters};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < IFR_MAX_TEX; i++) r->texMem[i].release();
     for (int i = 0; i < IFR_MAX_BUF; i++) r->bufMem[i].release();
@@ -625,13 +629,13 @@ int iftrcuReadAssembled(iftrcuRenderer* h, iftrcuAssembledTriangle* dst, int cap
     if (!n || !r->haveDraw) return r->fail(IFRIT_ERR_STATE, "ReadAssembled", "no draw issued");
     int rc = sync_and_check(r); if (rc) return rc;
     const size_t ntri = (size_t)r->icount / 3;
-    std::vector<TriVert> rec(2 * ntri * 3);
+    std::vector<TriRec> rec(2 * ntri);
     std::vector<uint2> box(2 * ntri);
     std::vector<float> cb(2 * ntri * 6);
     const size_t nfan1 = (size_t)r->hCounters[4];
     std::vector<uint32_t> fan1(std::max<size_t>(1, nfan1));
     if (ntri) {
-        CUDA_TRY(cudaMemcpy(rec.data(), r->rec.p, rec.size() * sizeof(TriVert), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(rec.data(), r->rec.p, rec.size() * sizeof(TriRec), cudaMemcpyDeviceToHost));
         CUDA_TRY(cudaMemcpy(box.data(), r->tileBox.p, box.size() * sizeof(uint2), cudaMemcpyDeviceToHost));
         CUDA_TRY(cudaMemcpy(cb.data(), r->clipBary.p, cb.size() * sizeof(float), cudaMemcpyDeviceToHost));
         if (nfan1) CUDA_TRY(cudaMemcpy(fan1.data(), r->fan1List.p, nfan1 * 4, cudaMemcpyDeviceToHost));
@@ -645,11 +649,11 @@ int iftrcuReadAssembled(iftrcuRenderer* h, iftrcuAssembledTriangle* dst, int cap
         if (dst && k < cap) {
             iftrcuAssembledTriangle& a = dst[k];
             a.fan = s >= ntri; a.prim = a.fan ? (int)(s - ntri) : (int)s; a.slot = (int)s;
-            const int flags = rec[3 * (size_t)s].x & 3;
+            const int flags = (int)rec[s].flags;
             a.clipped = (flags & IFR_FLAG_CLIPPED) ? 1 : 0;
             for (int j = 0; j < 3; j++) {
-                const TriVert& v = rec[3 * (size_t)s + j];
-                a.X[j] = v.x >> 2; a.Y[j] = v.y; a.Z[j] = v.z; a.IW[j] = v.iw;
+                const TriVert& v = rec[s].v[j];
+                a.X[j] = v.x; a.Y[j] = v.y; a.Z[j] = v.z; a.IW[j] = v.iw;
             }
             if (a.clipped) {
                 for (int j = 0; j < 3; j++) { a.bary[j][0] = cb[6 * (size_t)s + 2 * j]; a.bary[j][1] = cb[6 * (size_t)s + 2 * j + 1]; }

@@ -15,11 +15,32 @@
 #define IFR_MAX_SCISSOR 16
 #define IFR_SLOT_NONE 0xffffffffu
 
-// One assembled triangle = three 16-byte vertices (48 B).  x carries two flag bits in its
-// low bits: X = x >> 2.  Vertex 0: bit0 = clipped, bit1 = swapped (cull-mode winding swap).
+// One assembled triangle = 64 bytes: three 16-byte snapped vertices + one word of triangle-level
+// setup (geometryParamPostprocKernel CU:1549 keeps ~112 bytes per triangle).
 struct TriVert { int32_t x, y; float z, iw; };
-#define IFR_FLAG_CLIPPED 1
-#define IFR_FLAG_SWAPPED 2
+struct __align__(16) TriRec {
+    TriVert v[3];
+    float ar;            // 1 / float(d), d = twice the signed area in sub-pixel units (post-swap winding)
+    uint32_t flags;
+    uint32_t pad[2];
+};
+#define IFR_FLAG_CLIPPED 1   // clip barycentrics in clipBary[slot*6]
+#define IFR_FLAG_SWAPPED 2   // cull-mode winding swap (v1 <-> v3)
+#define IFR_FLAG_FITS32 4    // edge functions at every pixel corner that gets evaluated fit int32
+#define IFR_FLAG_SMALL 8     // pixel bbox area <= IFR_SMALL_AREA: thread-per-triangle path of the tile kernel
+#define IFR_FLAG_WIDE 16     // an edge delta exceeds 2^22 sub-pixels: int64 coverage path
+#define IFR_SMALL_AREA 16
+
+// Per (triangle, tile) raster setup, written by the fill pass into the tile's big-triangle queue and
+// read with uniform 128-bit loads by every pixel thread of the tile: six 16-byte words.
+struct __align__(16) TriS {
+    int dX[3]; uint32_t box;     // box = x0 | x1<<8 | y0<<16 | y1<<24: tile-local pixel bbox that can hold covered samples
+    int dY[3]; uint32_t slot;
+    int T[3]; uint32_t flags;    // int32 thresholds: inside <=> dX*j - dY*i >= T (i, j in 1/16 px, tile local)
+    long long E0[3];             // edge functions at the tile origin (sub-pixel units)
+    float ar, z0, z1, z2;
+    int pad[2];
+};
 
 #define IFR_MAX_MIPS 16
 // one mip level: dimensions, texel offset of layer 0, texels per layer, reciprocals for address wrapping
@@ -43,12 +64,14 @@ struct DrawParams {
     const int32_t* ib; int ntri;
     float4* pos; float4* vary;
     // assembled triangles: rec[slot*3+v]; slot = prim (fan 0) or ntri + prim (fan 1)
-    TriVert* rec; float* clipBary;   // clipBary[slot*6]
-    uint2* tileBox;                  // per slot: packed tile bbox, x = x0 | x1<<16, y = y0 | y1<<16; x0>x1 = none
+    TriRec* rec; float* clipBary;    // clipBary[slot*6]
+    uint2* tileBox;                  // per slot: packed tile bbox, x = x0 | x1<<16, y = y0 | y1<<16 | small<<31; x0>x1 = none
     uint32_t* fan1List;              // slots of second fan triangles (clipped primitives only)
-    // binning
-    uint32_t* tileCount; uint32_t* tileStart; uint32_t* tileCursor; uint32_t* queue; uint32_t queueCap;
-    unsigned long long* counters;    // [0] assembled, [1] pairs, [2] frags, [3] overflow flag, [4] fan1 count
+    // binning: two queues per tile.  Index 0 = small triangles (u32 slot per pair), 1 = big triangles
+    // (one TriS per pair).  tileCount / tileCursor: [2][ntiles]; tileStart: [2][ntiles + 1]
+    uint32_t* tileCount; uint32_t* tileStart; uint32_t* tileCursor;
+    uint32_t* queue; uint32_t queueCap; TriS* bigQueue; uint32_t bigCap;
+    unsigned long long* counters;    // [0] assembled, [1] small pairs, [2] frags, [3] overflow flag, [4] fan1 count, [5] big pairs
     // resources
     TexDesc tex[IFR_MAX_TEX]; SampDesc samp[IFR_MAX_TEX]; const float* buf[IFR_MAX_BUF];
 };
@@ -69,7 +92,7 @@ __host__ __device__ inline int ifr_tile_owner(int tx, int ty, int world) {
 struct Launch { cudaStream_t stream; };
 cudaError_t ifr_launch_vertex(const DrawParams& p, int vsId, cudaStream_t s);
 cudaError_t ifr_launch_setup_count(const DrawParams& p, cudaStream_t s);
-cudaError_t ifr_launch_scan(const DrawParams& p, cudaStream_t s);
+cudaError_t ifr_launch_scan(const DrawParams& p, cudaStream_t s);   // both queues
 cudaError_t ifr_launch_fill(const DrawParams& p, cudaStream_t s);
 cudaError_t ifr_launch_tiles(const DrawParams& p, int fsId, cudaStream_t s);
 cudaError_t ifr_launch_clear(const DrawParams& p, cudaStream_t s);

@@ -10,6 +10,7 @@
 // All arithmetic that decides coverage / visibility is integer (24.8 fixed point, 64-bit products) and
 // follows oracle/ifrit_oracle.c op for op; float ops use explicit fmaf / rn intrinsics (-fmad=false).
 #include "common.cuh"
+#include "tri_setup.cuh"
 #include "../../include/ifrit_b200.h"
 
 #define SNAP_LIMIT 268435456.0f
@@ -71,6 +72,7 @@ struct Assembled {
     float Z[3], IW[3];
     float bary[3][2];
     int flags;
+    float ar;                 // 1 / float(d) of the stored (post-swap) winding
     int tx0, tx1, ty0, ty1;   // tile bbox (inclusive), valid when ok
     bool ok;
 };
@@ -110,6 +112,24 @@ __device__ __forceinline__ void finish_triangle(const DrawParams& p, const ClipV
         default: return;
     }
     a.flags = (clipped ? IFR_FLAG_CLIPPED : 0) | (swp ? IFR_FLAG_SWAPPED : 0);
+    {
+        // triangle-level setup shared by every tile: 1/d (sign follows the stored winding) and the
+        // arithmetic class of the edge functions
+        const long long dpost = swp ? -d : d;
+        a.ar = __frcp_rn((float)dpost);
+        long long span = 0;
+        int wide = 0;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const int j = (i + 1) % 3;
+            const long long adx = llabs((long long)a.X[j] - a.X[i]), ady = llabs((long long)a.Y[j] - a.Y[i]);
+            span = max(span, adx + ady);
+            wide |= (adx > (1 << 22)) | (ady > (1 << 22));
+        }
+        // |E_i| at any pixel corner within two pixels of a covered sample is below |d| + 1024 (|dX| + |dY|)
+        if (llabs(d) + 1024 * span < 2147483647LL) a.flags |= IFR_FLAG_FITS32;
+        if (wide) a.flags |= IFR_FLAG_WIDE;
+    }
     if (swp) {
         int t;
         float f;
@@ -126,6 +146,7 @@ __device__ __forceinline__ void finish_triangle(const DrawParams& p, const ClipV
     px0 = max(px0, 0); py0 = max(py0, 0);
     px1 = min(px1, p.W - 1); py1 = min(py1, p.H - 1);
     if (px0 > px1 || py0 > py1) return;
+    if ((long long)(px1 - px0 + 1) * (py1 - py0 + 1) <= IFR_SMALL_AREA) a.flags |= IFR_FLAG_SMALL;
     a.tx0 = px0 >> 4; a.tx1 = px1 >> 4; a.ty0 = py0 >> 4; a.ty1 = py1 >> 4;
     a.ok = true;
 }
@@ -200,15 +221,29 @@ __device__ __forceinline__ bool tile_may_cover(const EdgeSet& e, int tx, int ty)
     return true;
 }
 
+// One (triangle, tile) pair.  Count pass: bump the tile's counter of the triangle's class.  Fill
+// pass: small class -> append the slot; big class -> compute the per-tile raster setup once, here,
+// and append it, so that the tile kernel has no setup phase (and no barrier) for big triangles.
 template <bool FILL>
-__device__ __forceinline__ void bin_one(const DrawParams& p, uint32_t slot, int tx, int ty) {
+__device__ __forceinline__ void bin_one(const DrawParams& p, uint32_t slot, int big, int tx, int ty) {
     if (p.world > 1 && ifr_tile_owner(tx, ty, p.world) != p.rank) return;
+    const int ntiles = p.tilesX * p.tilesY;
     const int tile = ty * p.tilesX + tx;
-    if (FILL) {
-        const uint32_t pos = p.tileStart[tile] + atomicAdd(&p.tileCursor[tile], 1u);
+    if (!FILL) {
+        atomicAdd(&p.tileCount[big * ntiles + tile], 1u);
+        return;
+    }
+    const uint32_t pos = p.tileStart[big * (ntiles + 1) + tile] + atomicAdd(&p.tileCursor[big * ntiles + tile], 1u);
+    if (!big) {
         p.queue[pos] = slot;
     } else {
-        atomicAdd(&p.tileCount[tile], 1u);
+        TriS s;
+        int bx0, bx1, by0, by1;
+        if (!setup_tri(p, slot, tx, ty, s, bx0, bx1, by0, by1)) s.box = 0x00ff00ffu;   // empty: rows 255..0
+        int4* dst = reinterpret_cast<int4*>(p.bigQueue + pos);
+        const int4* src = reinterpret_cast<const int4*>(&s);
+#pragma unroll
+        for (int k = 0; k < 6; k++) dst[k] = src[k];
     }
 }
 
@@ -216,24 +251,25 @@ __device__ __forceinline__ void bin_one(const DrawParams& p, uint32_t slot, int 
 
 // per-thread binning of small boxes + warp-cooperative binning of large ones
 template <bool FILL>
-__device__ __forceinline__ void bin_triangle(const DrawParams& p, bool has, uint32_t slot, int tx0, int tx1,
+__device__ __forceinline__ void bin_triangle(const DrawParams& p, bool has, uint32_t slot, int big, int tx0, int tx1,
                                              int ty0, int ty1, const EdgeSet& e) {
     const int nx = tx1 - tx0 + 1, ny = ty1 - ty0 + 1;
     const int nt = has ? nx * ny : 0;
     if (nt == 1) {
-        bin_one<FILL>(p, slot, tx0, ty0);
+        bin_one<FILL>(p, slot, big, tx0, ty0);
     } else if (nt > 1 && nt <= IFR_BIG_TILES) {
         const bool test = nx > 1 && ny > 1;
         for (int ty = ty0; ty <= ty1; ty++)
             for (int tx = tx0; tx <= tx1; tx++)
-                if (!test || tile_may_cover(e, tx, ty)) bin_one<FILL>(p, slot, tx, ty);
+                if (!test || tile_may_cover(e, tx, ty)) bin_one<FILL>(p, slot, big, tx, ty);
     }
-    unsigned big = __ballot_sync(0xffffffffu, nt > IFR_BIG_TILES);
+    unsigned wideBox = __ballot_sync(0xffffffffu, nt > IFR_BIG_TILES);
     const int lane = threadIdx.x & 31;
-    while (big) {
-        const int src = __ffs(big) - 1;
-        big &= big - 1;
+    while (wideBox) {
+        const int src = __ffs(wideBox) - 1;
+        wideBox &= wideBox - 1;
         const uint32_t s = __shfl_sync(0xffffffffu, slot, src);
+        const int sbig = __shfl_sync(0xffffffffu, big, src);
         const int bx0 = __shfl_sync(0xffffffffu, tx0, src), bx1 = __shfl_sync(0xffffffffu, tx1, src);
         const int by0 = __shfl_sync(0xffffffffu, ty0, src), by1 = __shfl_sync(0xffffffffu, ty1, src);
         EdgeSet be;
@@ -245,22 +281,23 @@ __device__ __forceinline__ void bin_triangle(const DrawParams& p, bool has, uint
         const int bnx = bx1 - bx0 + 1, total = bnx * (by1 - by0 + 1);
         for (int i = lane; i < total; i += 32) {
             const int tx = bx0 + i % bnx, ty = by0 + i / bnx;
-            if (tile_may_cover(be, tx, ty)) bin_one<FILL>(p, s, tx, ty);
+            if (tile_may_cover(be, tx, ty)) bin_one<FILL>(p, s, sbig, tx, ty);
         }
     }
 }
 
 __device__ __forceinline__ void store_record(const DrawParams& p, uint32_t slot, const Assembled& a) {
-    int4* r = reinterpret_cast<int4*>(p.rec + (size_t)slot * 3);
+    int4* r = reinterpret_cast<int4*>(p.rec + slot);
 #pragma unroll
     for (int j = 0; j < 3; j++) {
         int4 v;
-        v.x = (a.X[j] << 2) | (j == 0 ? a.flags : 0);
+        v.x = a.X[j];
         v.y = a.Y[j];
         v.z = __float_as_int(a.Z[j]);
         v.w = __float_as_int(a.IW[j]);
         r[j] = v;
     }
+    r[3] = make_int4(__float_as_int(a.ar), a.flags, 0, 0);
     if (a.flags & IFR_FLAG_CLIPPED) {
         float* b = p.clipBary + (size_t)slot * 6;
 #pragma unroll
@@ -268,7 +305,7 @@ __device__ __forceinline__ void store_record(const DrawParams& p, uint32_t slot,
     }
 }
 
-// pass 1: one thread per input triangle — clip, snap, cull, store the 48-byte record, count tiles
+// pass 1: one thread per input triangle — clip, snap, cull, store the 64-byte record, count tiles
 __global__ void __launch_bounds__(256) setup_count_kernel(const __grid_constant__ DrawParams p) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     Assembled a[2];
@@ -279,6 +316,7 @@ __global__ void __launch_bounds__(256) setup_count_kernel(const __grid_constant_
     for (int f = 0; f < 2; f++) {
         const bool has = a[f].ok;
         const uint32_t slot = f == 0 ? (uint32_t)t : (uint32_t)(p.ntri + t);
+        const int big = has && !(a[f].flags & IFR_FLAG_SMALL);
         EdgeSet e;
         if (has) {
             store_record(p, slot, a[f]);
@@ -291,12 +329,14 @@ __global__ void __launch_bounds__(256) setup_count_kernel(const __grid_constant_
         }
         if (t < p.ntri && (f == 0 || has)) {
             uint2 box;
-            if (has) { box.x = (uint32_t)a[f].tx0 | ((uint32_t)a[f].tx1 << 16); box.y = (uint32_t)a[f].ty0 | ((uint32_t)a[f].ty1 << 16); }
-            else { box.x = 1u; box.y = 0u; }   // x0 = 1 > x1 = 0: empty
+            if (has) {
+                box.x = (uint32_t)a[f].tx0 | ((uint32_t)a[f].tx1 << 16);
+                box.y = (uint32_t)a[f].ty0 | ((uint32_t)a[f].ty1 << 16) | (big ? 0u : 0x80000000u);
+            } else { box.x = 1u; box.y = 0u; }   // x0 = 1 > x1 = 0: empty
             p.tileBox[slot] = box;
         }
         if (f == 1 && __ballot_sync(0xffffffffu, has) == 0) continue;   // warp-uniform skip
-        bin_triangle<false>(p, has, slot, a[f].tx0, a[f].tx1, a[f].ty0, a[f].ty1, e);
+        bin_triangle<false>(p, has, slot, big, a[f].tx0, a[f].tx1, a[f].ty0, a[f].ty1, e);
     }
     // block-aggregated statistics
     nasm = __reduce_add_sync(0xffffffffu, (unsigned)nasm);
@@ -305,7 +345,7 @@ __global__ void __launch_bounds__(256) setup_count_kernel(const __grid_constant_
 
 // pass 3: one thread per slot of pass 1 (fan-0 slots densely, fan-1 slots through fan1List)
 __global__ void __launch_bounds__(256) fill_kernel(const __grid_constant__ DrawParams p) {
-    if (p.counters[3]) return;   // queue too small: host re-issues the draw with a larger one
+    if (p.counters[3]) return;   // a queue is too small: host re-issues the draw with larger ones
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned long long nfan1 = p.counters[4];
 #pragma unroll
@@ -315,30 +355,35 @@ __global__ void __launch_bounds__(256) fill_kernel(const __grid_constant__ DrawP
         if (f == 0) { has = t < p.ntri; slot = (uint32_t)t; }
         else if ((unsigned long long)t < nfan1) { has = true; slot = p.fan1List[t]; }
         if (f == 1 && __ballot_sync(0xffffffffu, has) == 0) continue;
-        int tx0 = 0, tx1 = 0, ty0 = 0, ty1 = 0;
+        int tx0 = 0, tx1 = 0, ty0 = 0, ty1 = 0, big = 0;
         EdgeSet e;
         if (has) {
             const uint2 box = p.tileBox[slot];
-            tx0 = box.x & 0xffff; tx1 = box.x >> 16; ty0 = box.y & 0xffff; ty1 = box.y >> 16;
+            tx0 = box.x & 0xffff; tx1 = box.x >> 16; ty0 = box.y & 0xffff; ty1 = (box.y >> 16) & 0x7fff;
+            big = !(box.y >> 31);
             has = tx0 <= tx1;
             if (has && (tx1 > tx0 || ty1 > ty0)) {
-                const int4* r = reinterpret_cast<const int4*>(p.rec + (size_t)slot * 3);
+                const int4* r = reinterpret_cast<const int4*>(p.rec + slot);
                 int X[3], Y[3];
 #pragma unroll
-                for (int j = 0; j < 3; j++) { const int4 v = r[j]; X[j] = v.x >> 2; Y[j] = v.y; }
+                for (int j = 0; j < 3; j++) { const int4 v = r[j]; X[j] = v.x; Y[j] = v.y; }
                 make_edges(X, Y, e);
             }
         }
-        bin_triangle<true>(p, has, slot, tx0, tx1, ty0, ty1, e);
+        bin_triangle<true>(p, has, slot, big, tx0, tx1, ty0, ty1, e);
     }
 }
 
-// pass 2: exclusive scan of the per-tile counts (single CTA; <= 130k tiles at 8K), cursor reset,
-// total -> counters[1], overflow flag -> counters[3]
+// pass 2: exclusive scan of the per-tile counts, one CTA per queue class (<= 130k tiles at 8K); cursor
+// reset, totals -> counters[1] (small pairs) / counters[5] (big pairs), overflow flag -> counters[3]
 __global__ void __launch_bounds__(1024) scan_kernel(const __grid_constant__ DrawParams p) {
     __shared__ uint32_t warpSums[32];
     __shared__ uint32_t carry;
     const int n = p.tilesX * p.tilesY;
+    const int cls = blockIdx.x;
+    const uint32_t* count = p.tileCount + (size_t)cls * n;
+    uint32_t* start = p.tileStart + (size_t)cls * (n + 1);
+    uint32_t* cursor = p.tileCursor + (size_t)cls * n;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) carry = 0;
     __syncthreads();
@@ -348,7 +393,7 @@ __global__ void __launch_bounds__(1024) scan_kernel(const __grid_constant__ Draw
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const int i = base + tid * 4 + k;
-            v[k] = i < n ? p.tileCount[i] : 0u;
+            v[k] = i < n ? count[i] : 0u;
             sum += v[k];
         }
         uint32_t incl = sum;
@@ -373,7 +418,7 @@ __global__ void __launch_bounds__(1024) scan_kernel(const __grid_constant__ Draw
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const int i = base + tid * 4 + k;
-            if (i < n) { p.tileStart[i] = run; p.tileCursor[i] = 0u; }
+            if (i < n) { start[i] = run; cursor[i] = 0u; }
             run += v[k];
         }
         __syncthreads();
@@ -381,9 +426,9 @@ __global__ void __launch_bounds__(1024) scan_kernel(const __grid_constant__ Draw
         __syncthreads();
     }
     if (tid == 0) {
-        p.tileStart[n] = carry;
-        p.counters[1] = carry;
-        if (carry > p.queueCap) p.counters[3] = 1ull;
+        start[n] = carry;
+        p.counters[cls ? 5 : 1] = carry;
+        if (carry > (cls ? p.bigCap : p.queueCap)) p.counters[3] = 1ull;
     }
 }
 
@@ -393,7 +438,7 @@ cudaError_t ifr_launch_setup_count(const DrawParams& p, cudaStream_t s) {
     return cudaGetLastError();
 }
 cudaError_t ifr_launch_scan(const DrawParams& p, cudaStream_t s) {
-    scan_kernel<<<1, 1024, 0, s>>>(p);
+    scan_kernel<<<2, 1024, 0, s>>>(p);
     return cudaGetLastError();
 }
 cudaError_t ifr_launch_fill(const DrawParams& p, cudaStream_t s) {

@@ -11,6 +11,7 @@
 //   pixelMultisampleCoverageModulationKernel CU:2319 -> resolve from the shared-memory keys
 //   imageResetFloat32{Mono,RGBA}Kernel CU:3337/3363 -> fused clear
 #include "common.cuh"
+#include "tri_setup.cuh"
 #include "sampler.cuh"
 
 // ---- visibility keys (identical to oracle/ifrit_oracle.c key_*) --------------------------------
@@ -63,57 +64,6 @@ __device__ __forceinline__ bool scissor_pass(const DrawParams& p, int x, int y) 
     return false;
 }
 
-// ---- per (triangle, tile) setup ---------------------------------------------------------------
-// 96 bytes = six 16-byte words, read with broadcast LDS.128 by every pixel thread of the tile.
-struct __align__(16) TriS {
-    int dX[3]; uint32_t box;     // box = x0 | x1<<8 | y0<<16 | y1<<24: tile-local pixel bbox that can hold covered samples
-    int dY[3]; uint32_t slot;
-    int T[3]; int wide;          // int32 thresholds: inside <=> dX*j - dY*i >= T (i, j in 1/16 px, tile local); wide: int64 path
-    long long E0[3];             // edge functions at the tile origin
-    float ar, z0, z1, z2;
-    int pad[2];
-};
-static_assert(sizeof(TriS) == 96, "TriS layout");
-
-__device__ __forceinline__ bool setup_tri(const DrawParams& p, uint32_t slot, int tileX, int tileY, TriS& s,
-                                          int& bx0, int& bx1, int& by0, int& by1) {
-    const int4* r = reinterpret_cast<const int4*>(p.rec + (size_t)slot * 3);
-    int X[3], Y[3];
-    float Z[3];
-#pragma unroll
-    for (int j = 0; j < 3; j++) {
-        const int4 v = __ldg(r + j);
-        X[j] = v.x >> 2; Y[j] = v.y; Z[j] = __int_as_float(v.z);
-    }
-    s.slot = slot;
-    s.z0 = Z[0]; s.z1 = Z[1]; s.z2 = Z[2];
-    // tile origin <= 2^21 and |X|,|Y| <= 2^28: the differences fit int32, products are IMAD.WIDE
-    const int sx0 = tileX * (IFR_TILE * IFR_SUBPIX), sy0 = tileY * (IFR_TILE * IFR_SUBPIX);
-    int wide = 0;
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        const int a = (i + 1) % 3, b = (i + 2) % 3;
-        s.dX[i] = X[b] - X[a]; s.dY[i] = Y[b] - Y[a];
-        s.E0[i] = (long long)s.dX[i] * (long long)(sy0 - Y[a]) - (long long)s.dY[i] * (long long)(sx0 - X[a]);
-        wide |= (abs(s.dX[i]) > (1 << 22)) | (abs(s.dY[i]) > (1 << 22));
-        long long T = ((-s.E0[i]) >> 4) + 1;
-        T = T > 2147483647LL ? 2147483647LL : (T < -2147483648LL ? -2147483648LL : T);
-        s.T[i] = (int)T;
-    }
-    s.wide = wide;
-    const long long d = (long long)s.dX[1] * s.dY[2] - (long long)s.dX[2] * s.dY[1];
-    s.ar = __frcp_rn((float)d);
-    const int minx = min(X[0], min(X[1], X[2])), maxx = max(X[0], max(X[1], X[2]));
-    const int miny = min(Y[0], min(Y[1], Y[2])), maxy = max(Y[0], max(Y[1], Y[2]));
-    const int px0 = ((minx - p.sampMaxX) >> 8) + 1, px1 = (maxx - p.sampMinX - 1) >> 8;
-    const int py0 = ((miny - p.sampMaxY) >> 8) + 1, py1 = (maxy - p.sampMinY - 1) >> 8;
-    const int ox = tileX * IFR_TILE, oy = tileY * IFR_TILE;
-    bx0 = max(px0 - ox, 0); by0 = max(py0 - oy, 0);
-    bx1 = min(min(px1, p.W - 1) - ox, IFR_TILE - 1); by1 = min(min(py1, p.H - 1) - oy, IFR_TILE - 1);
-    s.box = (uint32_t)bx0 | ((uint32_t)bx1 << 8) | ((uint32_t)by0 << 16) | ((uint32_t)by1 << 24);
-    return bx0 <= bx1 && by0 <= by1;
-}
-
 // coverage mask of the pixel whose origin is (ci, cj) = (16 lx, 16 ly) in 1/16 px, over the S samples
 template <int S>
 __device__ __forceinline__ uint32_t coverage(const DrawParams& p, const int dX[3], const int dY[3], const int T[3],
@@ -140,15 +90,22 @@ __device__ __forceinline__ uint32_t coverage(const DrawParams& p, const int dX[3
 }
 
 // depth at the integer pixel (lx, ly): beta_i = E_i(corner) / d, from exact integer edge values
-__device__ __forceinline__ float depth_at(const int dX[3], const int dY[3], const long long E0[3], int wide, float ar,
+__device__ __forceinline__ float depth_at(const int dX[3], const int dY[3], const long long E0[3], uint32_t flags, float ar,
                                           float z0, float z1, float z2, int lx, int ly) {
     float beta[3];
+    if (flags & IFR_FLAG_FITS32) {
+        // triangle-level bound: the edge values at this corner fit int32 -> wrapping 32-bit arithmetic, I2F.S32
 #pragma unroll
-    for (int e = 0; e < 3; e++) {
-        long long Ec;
-        if (!wide) Ec = E0[e] + (long long)(dX[e] * ly - dY[e] * lx) * 256;   // |dX|,|dY| <= 2^22: int32 is exact
-        else Ec = E0[e] + 256 * ((long long)dX[e] * ly - (long long)dY[e] * lx);
-        beta[e] = __fmul_rn((float)Ec, ar);
+        for (int e = 0; e < 3; e++) {
+            const uint32_t Ec = (uint32_t)E0[e] + (((uint32_t)dX[e] * (uint32_t)ly - (uint32_t)dY[e] * (uint32_t)lx) << 8);
+            beta[e] = __fmul_rn((float)(int)Ec, ar);
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 3; e++) {
+            const long long Ec = E0[e] + 256 * ((long long)dX[e] * ly - (long long)dY[e] * lx);
+            beta[e] = __fmul_rn((float)Ec, ar);
+        }
     }
     return fmaf(z2, beta[2], fmaf(z1, beta[1], __fmul_rn(z0, beta[0])));
 }
@@ -162,23 +119,22 @@ __device__ __forceinline__ void key_min_shared(unsigned long long* addr, unsigne
     if (k < *reinterpret_cast<volatile unsigned long long*>(addr)) atomicMin(addr, k);
 }
 
-#define IFR_SMALL_AREA 16
-#define IFR_CHUNK 256
 
 // ---- attribute interpolation at an integer pixel (pixelShadingExecKernel CU:2168-2215) ---------
 template <int NV>
 __device__ __forceinline__ void interp(const DrawParams& p, uint32_t slot, int px, int py, float4* out, float& depth,
                                        int& prim, int& fan) {
-    const int4* r = reinterpret_cast<const int4*>(p.rec + (size_t)slot * 3);
+    const int4* r = reinterpret_cast<const int4*>(p.rec + slot);
     int X[3], Y[3];
     float Z[3], IW[3];
-    int flags = 0;
 #pragma unroll
     for (int j = 0; j < 3; j++) {
         const int4 v = __ldg(r + j);
-        if (j == 0) flags = v.x & 3;
-        X[j] = v.x >> 2; Y[j] = v.y; Z[j] = __int_as_float(v.z); IW[j] = __int_as_float(v.w);
+        X[j] = v.x; Y[j] = v.y; Z[j] = __int_as_float(v.z); IW[j] = __int_as_float(v.w);
     }
+    const int4 w3 = __ldg(r + 3);
+    const float ar = __int_as_float(w3.x);
+    const int flags = w3.y;
     fan = slot >= (uint32_t)p.ntri;
     prim = fan ? (int)(slot - (uint32_t)p.ntri) : (int)slot;
     int idx[3];
@@ -187,14 +143,22 @@ __device__ __forceinline__ void interp(const DrawParams& p, uint32_t slot, int p
         for (int j = 0; j < 3; j++) idx[j] = __ldg(p.ib + 3 * (size_t)prim + j);
     }
     const int sx = px * IFR_SUBPIX, sy = py * IFR_SUBPIX;
-    const long long d = (long long)(X[1] - X[0]) * (long long)(Y[2] - Y[0]) - (long long)(X[2] - X[0]) * (long long)(Y[1] - Y[0]);
-    const float ar = __frcp_rn((float)d);
     float beta[3];
+    if (flags & IFR_FLAG_FITS32) {
+        // the edge values fit int32 (triangle-level bound): wrapping 32-bit arithmetic is exact
 #pragma unroll
-    for (int i = 0; i < 3; i++) {
-        const int a = (i + 1) % 3, b = (i + 2) % 3;
-        const long long E = (long long)(X[b] - X[a]) * (long long)(sy - Y[a]) - (long long)(Y[b] - Y[a]) * (long long)(sx - X[a]);
-        beta[i] = __fmul_rn((float)E, ar);
+        for (int i = 0; i < 3; i++) {
+            const int a = (i + 1) % 3, b = (i + 2) % 3;
+            const uint32_t E = (uint32_t)(X[b] - X[a]) * (uint32_t)(sy - Y[a]) - (uint32_t)(Y[b] - Y[a]) * (uint32_t)(sx - X[a]);
+            beta[i] = __fmul_rn((float)(int)E, ar);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const int a = (i + 1) % 3, b = (i + 2) % 3;
+            const long long E = (long long)(X[b] - X[a]) * (long long)(sy - Y[a]) - (long long)(Y[b] - Y[a]) * (long long)(sx - X[a]);
+            beta[i] = __fmul_rn((float)E, ar);
+        }
     }
     depth = fmaf(Z[2], beta[2], fmaf(Z[1], beta[1], __fmul_rn(Z[0], beta[0])));
     if (NV == 0) return;
@@ -232,15 +196,16 @@ __device__ __forceinline__ void interp(const DrawParams& p, uint32_t slot, int p
 }
 
 // ------------------------------------------------------------------------------------------------
+#define IFR_CHUNK 256
+
 template <int FS, int S>
 __global__ void __launch_bounds__(256, 4) tile_kernel(const __grid_constant__ DrawParams p) {
     extern __shared__ unsigned long long keys[];        // [S][256], index = owning thread
-    __shared__ TriS big[IFR_CHUNK];
-    __shared__ int nbig;
     constexpr int NV = FsTraits<FS>::nv;
 
     const int tileX = blockIdx.x, tileY = blockIdx.y;
     if (p.world > 1 && ifr_tile_owner(tileX, tileY, p.world) != p.rank) return;
+    const int ntiles = p.tilesX * p.tilesY;
     const int tile = tileY * p.tilesX + tileX;
     const int tid = threadIdx.x;
     const int q = tid >> 2, l = tid & 3;
@@ -248,11 +213,12 @@ __global__ void __launch_bounds__(256, 4) tile_kernel(const __grid_constant__ Dr
     const int px = tileX * IFR_TILE + lx, py = tileY * IFR_TILE + ly;
     const bool inFrame = px < p.W && py < p.H;
     const bool scis = inFrame && scissor_pass(p, px, py);
-    const uint32_t qStart = p.tileStart[tile], qEnd = p.tileStart[tile + 1];
     const bool overflow = p.counters[3] != 0;
-    const uint32_t nq = overflow ? 0u : qEnd - qStart;
+    const uint32_t sStart = p.tileStart[tile], bStart = p.tileStart[ntiles + 1 + tile];
+    const uint32_t nSmall = overflow ? 0u : p.tileStart[tile + 1] - sStart;
+    const uint32_t nBig = overflow ? 0u : p.tileStart[ntiles + 1 + tile + 1] - bStart;
     const size_t pidx = (size_t)py * p.W + px;
-    if (nq == 0) {
+    if (nSmall + nBig == 0) {
         // nothing binned here: the fused clear is all there is to do (imageResetFloat32* CU:3337/3363)
         if (!p.doClear || !inFrame) return;
         if (scis) {
@@ -270,88 +236,92 @@ __global__ void __launch_bounds__(256, 4) tile_kernel(const __grid_constant__ Dr
     float d0 = 0.0f;
     if (inFrame) d0 = (p.doClear && scis) ? p.clearDepth : p.depth[pidx];
     const unsigned long long k0 = key_init(func, d0);
+    // Per-sample visibility keys.  S == 1: the pixel's key lives in a register (`best`); shared memory
+    // is only the mailbox through which small triangles (processed by other threads) reach this pixel.
+    if (S > 1 || nSmall) {
 #pragma unroll
-    for (int s = 0; s < S; s++) keys[s * IFR_TILE_PIX + tid] = k0;
-    unsigned long long best = k0;     // S == 1: this pixel's key for the large-triangle path lives in a register
-    if (tid == 0) nbig = 0;
-    __syncthreads();
+        for (int s = 0; s < S; s++) keys[s * IFR_TILE_PIX + tid] = k0;
+    }
+    unsigned long long best = k0;
 
-    // ---- coverage + early-Z ---------------------------------------------------------------------
-    const int ci = 16 * lx, cj = 16 * ly;
-    const int wy0 = (tid >> 5) * 2;       // a warp owns the 16x2 pixel strip [wy0, wy0+1]
-    for (uint32_t base = 0; base < nq; base += IFR_CHUNK) {
-        const uint32_t qi = base + tid;
-        if (qi < nq) {
+    // ---- small triangles: one thread per (triangle, tile) pair, shared-memory atomicMin --------------
+    if (nSmall) {
+        __syncthreads();
+        for (uint32_t qi = tid; qi < nSmall; qi += IFR_CHUNK) {
             TriS s;
             int bx0, bx1, by0, by1;
-            const uint32_t slot = __ldg(p.queue + qStart + qi);
-            if (setup_tri(p, slot, tileX, tileY, s, bx0, bx1, by0, by1)) {
-                const int area = (bx1 - bx0 + 1) * (by1 - by0 + 1);
-                if (area <= IFR_SMALL_AREA) {
-                    // small triangle: this thread walks its few pixels, shared-memory atomicMin
-                    for (int y = by0; y <= by1; y++)
-                        for (int x = bx0; x <= bx1; x++) {
-                            const uint32_t m = coverage<S>(p, s.dX, s.dY, s.T, s.E0, s.wide, 16 * x, 16 * y);
-                            if (!m) continue;
-                            const int gx = tileX * IFR_TILE + x, gy = tileY * IFR_TILE + y;
-                            if (p.scissorEnable && !scissor_pass(p, gx, gy)) continue;
-                            const float d = depth_at(s.dX, s.dY, s.E0, s.wide, s.ar, s.z0, s.z1, s.z2, x, y);
-                            unsigned long long k;
-                            float dd0 = 0.0f;
-                            if (func == IF_COMPARE_OP_EQUAL)
-                                dd0 = p.doClear ? p.clearDepth : p.depth[(size_t)gy * p.W + gx];
-                            if (!key_make(func, d, dd0, slot, k)) continue;
-                            const int pi = pix_index(x, y);
-#pragma unroll
-                            for (int sm = 0; sm < S; sm++)
-                                if ((m >> sm) & 1) key_min_shared(&keys[sm * IFR_TILE_PIX + pi], k);
-                        }
-                } else {
-                    big[atomicAdd(&nbig, 1)] = s;
-                }
-            }
-        }
-        __syncthreads();
-        // large triangles: every thread tests its own pixel
-        const int nb = nbig;
-        if (nb) {
-            for (int b = 0; b < nb; b++) {
-                const int4* t4 = reinterpret_cast<const int4*>(&big[b]);
-                const int4 A = t4[0];
-                const int y0 = (A.w >> 16) & 0xff, y1 = (int)((uint32_t)A.w >> 24);
-                if (wy0 + 1 < y0 || wy0 > y1) continue;          // warp-uniform: strip outside the bbox rows
-                const int4 B = t4[1], C = t4[2];
-                const int4 D = t4[3], E = t4[4];
-                const int dX[3] = {A.x, A.y, A.z}, dY[3] = {B.x, B.y, B.z}, T[3] = {C.x, C.y, C.z};
-                const long long E0[3] = {(long long)(((unsigned long long)(uint32_t)D.y << 32) | (uint32_t)D.x),
-                                         (long long)(((unsigned long long)(uint32_t)D.w << 32) | (uint32_t)D.z),
-                                         (long long)(((unsigned long long)(uint32_t)E.y << 32) | (uint32_t)E.x)};
-                const uint32_t m = scis ? coverage<S>(p, dX, dY, T, E0, C.w, ci, cj) : 0u;
-                if (!m) continue;
-                const float2 Zr = *reinterpret_cast<const float2*>(t4 + 5);
-                const float d = depth_at(dX, dY, E0, C.w, __int_as_float(E.z), __int_as_float(E.w), Zr.x, Zr.y, lx, ly);
-                unsigned long long k;
-                if (!key_make(func, d, d0, (uint32_t)B.w, k)) continue;
-                if (S == 1) {
-                    if (k < best) best = k;
-                } else {
+            const uint32_t slot = __ldg(p.queue + sStart + qi);
+            if (!setup_tri(p, slot, tileX, tileY, s, bx0, bx1, by0, by1)) continue;
+            const int wide = s.flags & IFR_FLAG_WIDE;
+            for (int y = by0; y <= by1; y++)
+                for (int x = bx0; x <= bx1; x++) {
+                    const uint32_t m = coverage<S>(p, s.dX, s.dY, s.T, s.E0, wide, 16 * x, 16 * y);
+                    if (!m) continue;
+                    const int gx = tileX * IFR_TILE + x, gy = tileY * IFR_TILE + y;
+                    if (p.scissorEnable && !scissor_pass(p, gx, gy)) continue;
+                    const float d = depth_at(s.dX, s.dY, s.E0, s.flags, s.ar, s.z0, s.z1, s.z2, x, y);
+                    unsigned long long k;
+                    float dd0 = 0.0f;
+                    if (func == IF_COMPARE_OP_EQUAL)
+                        dd0 = p.doClear ? p.clearDepth : p.depth[(size_t)gy * p.W + gx];
+                    if (!key_make(func, d, dd0, slot, k)) continue;
+                    const int pi = pix_index(x, y);
 #pragma unroll
                     for (int sm = 0; sm < S; sm++)
-                        if (((m >> sm) & 1) && k < keys[sm * IFR_TILE_PIX + tid]) keys[sm * IFR_TILE_PIX + tid] = k;
+                        if ((m >> sm) & 1) key_min_shared(&keys[sm * IFR_TILE_PIX + pi], k);
                 }
-            }
-            __syncthreads();
-            if (tid == 0) nbig = 0;
         }
-        if (base + IFR_CHUNK < nq) __syncthreads();
+        __syncthreads();
+    }
+
+    // ---- big triangles: setups precomputed by the fill pass, every thread tests its own pixel; warps run
+    //      independently (no barrier), all lanes read the same 16-byte words ------------------------------
+    if (nBig) {
+        const int ci = 16 * lx, cj = 16 * ly;
+        const int wy0 = (tid >> 5) * 2;       // a warp owns the 16x2 pixel strip [wy0, wy0+1]
+        const int4* t4 = reinterpret_cast<const int4*>(p.bigQueue + bStart);
+        int4 A = __ldg(t4);
+        for (uint32_t b = 0; b < nBig; b++, t4 += 6) {
+            const int4 Acur = A;
+            if (b + 1 < nBig) A = __ldg(t4 + 6);               // prefetch the next entry's first word
+            const int y0 = (Acur.w >> 16) & 0xff, y1 = (int)((uint32_t)Acur.w >> 24);
+            if (wy0 + 1 < y0 || wy0 > y1) continue;            // warp-uniform: strip outside the bbox rows
+            const int4 B = __ldg(t4 + 1), C = __ldg(t4 + 2);
+            const int dX[3] = {Acur.x, Acur.y, Acur.z}, dY[3] = {B.x, B.y, B.z}, T[3] = {C.x, C.y, C.z};
+            const uint32_t flags = (uint32_t)C.w;
+            uint32_t m = 0;
+            if (!(flags & IFR_FLAG_WIDE)) {
+                if (scis) m = coverage<S>(p, dX, dY, T, nullptr, 0, ci, cj);
+                if (!m) continue;
+            }
+            const int4 D = __ldg(t4 + 3), E = __ldg(t4 + 4);
+            const long long E0[3] = {(long long)(((unsigned long long)(uint32_t)D.y << 32) | (uint32_t)D.x),
+                                     (long long)(((unsigned long long)(uint32_t)D.w << 32) | (uint32_t)D.z),
+                                     (long long)(((unsigned long long)(uint32_t)E.y << 32) | (uint32_t)E.x)};
+            if (flags & IFR_FLAG_WIDE) {
+                if (scis) m = coverage<S>(p, dX, dY, T, E0, 1, ci, cj);
+                if (!m) continue;
+            }
+            const float2 Zr = __ldg(reinterpret_cast<const float2*>(t4 + 5));
+            const float d = depth_at(dX, dY, E0, flags, __int_as_float(E.z), __int_as_float(E.w), Zr.x, Zr.y, lx, ly);
+            unsigned long long k;
+            if (!key_make(func, d, d0, (uint32_t)B.w, k)) continue;
+            if (S == 1) {
+                if (k < best) best = k;
+            } else {
+#pragma unroll
+                for (int sm = 0; sm < S; sm++)
+                    if (((m >> sm) & 1) && k < keys[sm * IFR_TILE_PIX + tid]) keys[sm * IFR_TILE_PIX + tid] = k;
+            }
+        }
     }
 
     // ---- quad shading + resolve -----------------------------------------------------------------
     uint32_t mySlots[S];
 #pragma unroll
     for (int s = 0; s < S; s++) {
-        unsigned long long k = keys[s * IFR_TILE_PIX + tid];
-        if (S == 1 && best < k) k = best;
+        unsigned long long k = best;
+        if (S > 1 || nSmall) { const unsigned long long ks = keys[s * IFR_TILE_PIX + tid]; if (S > 1 || ks < k) k = ks; }
         mySlots[s] = key_slot(func, k);
     }
 

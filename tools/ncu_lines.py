@@ -55,3 +55,6 @@ byfile = collections.defaultdict(lambda: [0, 0])
 for key, (s, e, st) in agg.items():
     byfile[key[0]][0] += s; byfile[key[0]][1] += e
 for f, (s, e) in byfile.items(): print(f"FILE {f}: samples {100*s/tot_s:.1f}% inst {100*e/tot_e:.1f}%")
+tot = collections.Counter()
+for key, (s, e, st) in agg.items(): tot.update(st)
+print("---- stall totals:", ", ".join(f"{n[6:]}={100*v/tot_s:.1f}%" for n, v in tot.most_common(12)))
