@@ -197,10 +197,31 @@ __device__ __forceinline__ void interp(const DrawParams& p, uint32_t slot, int p
 
 // ------------------------------------------------------------------------------------------------
 #define IFR_CHUNK 256
+#define IFR_BIG_CHUNK 64     // big-queue entries staged per bulk copy (6 KB), double buffered
+
+// ---- TMA bulk copy (global -> shared) completing on an mbarrier -----------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
 
 template <int FS, int S>
 __global__ void __launch_bounds__(256, 4) tile_kernel(const __grid_constant__ DrawParams p) {
     extern __shared__ unsigned long long keys[];        // [S][256], index = owning thread
+    __shared__ __align__(128) TriS bigBuf[2][IFR_BIG_CHUNK];
+    __shared__ __align__(8) uint64_t mbar[2];
     constexpr int NV = FsTraits<FS>::nv;
 
     const int tileX = blockIdx.x, tileY = blockIdx.y;
@@ -243,10 +264,17 @@ __global__ void __launch_bounds__(256, 4) tile_kernel(const __grid_constant__ Dr
         for (int s = 0; s < S; s++) keys[s * IFR_TILE_PIX + tid] = k0;
     }
     unsigned long long best = k0;
+    if (nBig && tid == 0) {
+        mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();      // keys + mbarriers initialised
+    const TriS* bigSrc = p.bigQueue + bStart;
+    if (nBig && tid == 0)  // stage the first chunk of precomputed setups while the small triangles are processed
+        bulk_load(bigBuf[0], bigSrc, min(nBig, (uint32_t)IFR_BIG_CHUNK) * (uint32_t)sizeof(TriS), &mbar[0]);
 
     // ---- small triangles: one thread per (triangle, tile) pair, shared-memory atomicMin --------------
     if (nSmall) {
-        __syncthreads();
         for (uint32_t qi = tid; qi < nSmall; qi += IFR_CHUNK) {
             TriS s;
             int bx0, bx1, by0, by1;
@@ -274,45 +302,54 @@ __global__ void __launch_bounds__(256, 4) tile_kernel(const __grid_constant__ Dr
         __syncthreads();
     }
 
-    // ---- big triangles: setups precomputed by the fill pass, every thread tests its own pixel; warps run
-    //      independently (no barrier), all lanes read the same 16-byte words ------------------------------
+    // ---- big triangles: setups precomputed by the fill pass arrive by TMA bulk copy (double buffered);
+    //      every thread tests its own pixel against broadcast LDS.128 words, warps run independently ------
     if (nBig) {
         const int ci = 16 * lx, cj = 16 * ly;
         const int wy0 = (tid >> 5) * 2;       // a warp owns the 16x2 pixel strip [wy0, wy0+1]
-        const int4* t4 = reinterpret_cast<const int4*>(p.bigQueue + bStart);
-        int4 A = __ldg(t4);
-        for (uint32_t b = 0; b < nBig; b++, t4 += 6) {
-            const int4 Acur = A;
-            if (b + 1 < nBig) A = __ldg(t4 + 6);               // prefetch the next entry's first word
-            const int y0 = (Acur.w >> 16) & 0xff, y1 = (int)((uint32_t)Acur.w >> 24);
-            if (wy0 + 1 < y0 || wy0 > y1) continue;            // warp-uniform: strip outside the bbox rows
-            const int4 B = __ldg(t4 + 1), C = __ldg(t4 + 2);
-            const int dX[3] = {Acur.x, Acur.y, Acur.z}, dY[3] = {B.x, B.y, B.z}, T[3] = {C.x, C.y, C.z};
-            const uint32_t flags = (uint32_t)C.w;
-            uint32_t m = 0;
-            if (!(flags & IFR_FLAG_WIDE)) {
-                if (scis) m = coverage<S>(p, dX, dY, T, nullptr, 0, ci, cj);
-                if (!m) continue;
+        const uint32_t nchunks = (nBig + IFR_BIG_CHUNK - 1) / IFR_BIG_CHUNK;
+        for (uint32_t c = 0; c < nchunks; c++) {
+            if (tid == 0 && c + 1 < nchunks) {
+                const uint32_t cnt1 = min(nBig - (c + 1) * IFR_BIG_CHUNK, (uint32_t)IFR_BIG_CHUNK);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                bulk_load(bigBuf[(c + 1) & 1], bigSrc + (size_t)(c + 1) * IFR_BIG_CHUNK, cnt1 * (uint32_t)sizeof(TriS), &mbar[(c + 1) & 1]);
             }
-            const int4 D = __ldg(t4 + 3), E = __ldg(t4 + 4);
-            const long long E0[3] = {(long long)(((unsigned long long)(uint32_t)D.y << 32) | (uint32_t)D.x),
-                                     (long long)(((unsigned long long)(uint32_t)D.w << 32) | (uint32_t)D.z),
-                                     (long long)(((unsigned long long)(uint32_t)E.y << 32) | (uint32_t)E.x)};
-            if (flags & IFR_FLAG_WIDE) {
-                if (scis) m = coverage<S>(p, dX, dY, T, E0, 1, ci, cj);
-                if (!m) continue;
-            }
-            const float2 Zr = __ldg(reinterpret_cast<const float2*>(t4 + 5));
-            const float d = depth_at(dX, dY, E0, flags, __int_as_float(E.z), __int_as_float(E.w), Zr.x, Zr.y, lx, ly);
-            unsigned long long k;
-            if (!key_make(func, d, d0, (uint32_t)B.w, k)) continue;
-            if (S == 1) {
-                if (k < best) best = k;
-            } else {
+            mbar_wait(&mbar[c & 1], (c >> 1) & 1);
+            const uint32_t cnt = min(nBig - c * IFR_BIG_CHUNK, (uint32_t)IFR_BIG_CHUNK);
+            const int4* t4 = reinterpret_cast<const int4*>(bigBuf[c & 1]);
+            for (uint32_t b = 0; b < cnt; b++, t4 += 6) {
+                const int4 A = t4[0];
+                const int y0 = (A.w >> 16) & 0xff, y1 = (int)((uint32_t)A.w >> 24);
+                if (wy0 + 1 < y0 || wy0 > y1) continue;            // warp-uniform: strip outside the bbox rows
+                const int4 B = t4[1], C = t4[2];
+                const int dX[3] = {A.x, A.y, A.z}, dY[3] = {B.x, B.y, B.z}, T[3] = {C.x, C.y, C.z};
+                const uint32_t flags = (uint32_t)C.w;
+                uint32_t m = 0;
+                if (!(flags & IFR_FLAG_WIDE)) {
+                    if (scis) m = coverage<S>(p, dX, dY, T, nullptr, 0, ci, cj);
+                    if (!m) continue;
+                }
+                const int4 D = t4[3], E = t4[4];
+                const long long E0[3] = {(long long)(((unsigned long long)(uint32_t)D.y << 32) | (uint32_t)D.x),
+                                         (long long)(((unsigned long long)(uint32_t)D.w << 32) | (uint32_t)D.z),
+                                         (long long)(((unsigned long long)(uint32_t)E.y << 32) | (uint32_t)E.x)};
+                if (flags & IFR_FLAG_WIDE) {
+                    if (scis) m = coverage<S>(p, dX, dY, T, E0, 1, ci, cj);
+                    if (!m) continue;
+                }
+                const float2 Zr = *reinterpret_cast<const float2*>(t4 + 5);
+                const float d = depth_at(dX, dY, E0, flags, __int_as_float(E.z), __int_as_float(E.w), Zr.x, Zr.y, lx, ly);
+                unsigned long long k;
+                if (!key_make(func, d, d0, (uint32_t)B.w, k)) continue;
+                if (S == 1) {
+                    if (k < best) best = k;
+                } else {
 #pragma unroll
-                for (int sm = 0; sm < S; sm++)
-                    if (((m >> sm) & 1) && k < keys[sm * IFR_TILE_PIX + tid]) keys[sm * IFR_TILE_PIX + tid] = k;
+                    for (int sm = 0; sm < S; sm++)
+                        if (((m >> sm) & 1) && k < keys[sm * IFR_TILE_PIX + tid]) keys[sm * IFR_TILE_PIX + tid] = k;
+                }
             }
+            if (c + 2 < nchunks) __syncthreads();   // buffer (c & 1) is refilled at the top of iteration c + 1
         }
     }
 
