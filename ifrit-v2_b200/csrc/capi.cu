@@ -76,7 +76,8 @@ struct iftrcuRenderer {
     DevBuf bufMem[IFR_MAX_BUF]; int bufSize[IFR_MAX_BUF] = {0};
 
     // scratch
-    DevBuf pos, vary, rec, clipBary, tileBox, fan1List, tileCount, tileStart, tileCursor, queue, bigQueue, counters;
+    DevBuf scanPartial; uint32_t epoch = 0;
+    DevBuf pos, vary, rec, clipBary, tileBox, fan1List, heavyBits, tileCount, tileStart, tileCursor, queue, bigQueue, counters;
     bool queueChecked = false;   // queue capacity verified for the current geometry / state
     unsigned long long* hCounters = nullptr;   // pinned, 8 entries
     bool haveDraw = false;
@@ -125,13 +126,14 @@ static void build_params(iftrcuRenderer* r, DrawParams& p) {
     p.ib = r->dIB; p.ntri = r->icount / 3;
     p.pos = (float4*)r->pos.p; p.vary = (float4*)r->vary.p;
     p.rec = (TriRec*)r->rec.p; p.clipBary = (float*)r->clipBary.p; p.tileBox = (uint2*)r->tileBox.p;
-    p.fan1List = (uint32_t*)r->fan1List.p;
+    p.fan1List = (uint32_t*)r->fan1List.p; p.heavyBits = (uint32_t*)r->heavyBits.p;
     p.tileCount = (uint32_t*)r->tileCount.p; p.tileStart = (uint32_t*)r->tileStart.p;
     p.tileCursor = (uint32_t*)r->tileCursor.p; p.queue = (uint32_t*)r->queue.p;
     p.queueCap = (uint32_t)std::min<size_t>(r->queue.cap / 4, 0xffffffffu);
     p.bigQueue = (TriS*)r->bigQueue.p;
     p.bigCap = (uint32_t)std::min<size_t>(r->bigQueue.cap / sizeof(TriS), 0xffffffffu);
     p.counters = (unsigned long long*)r->counters.p;
+    p.scanPartial = (unsigned long long*)r->scanPartial.p; p.epoch = r->epoch;
     for (int i = 0; i < IFR_MAX_TEX; i++) { p.tex[i] = r->tex[i]; p.samp[i] = r->samp[i]; }
     for (int i = 0; i < IFR_MAX_BUF; i++) p.buf[i] = (const float*)r->bufMem[i].p;
 }
@@ -144,10 +146,15 @@ static int ensure_scratch(iftrcuRenderer* r) {
     CUDA_TRY(r->clipBary.ensure(std::max<size_t>(1, 2 * ntri) * 6 * sizeof(float)));
     CUDA_TRY(r->tileBox.ensure(std::max<size_t>(1, 2 * ntri) * sizeof(uint2)));
     CUDA_TRY(r->fan1List.ensure(std::max<size_t>(1, ntri) * sizeof(uint32_t)));
+    CUDA_TRY(r->heavyBits.ensure((ntri / 32 + 2) * sizeof(uint32_t)));
     CUDA_TRY(r->tileCount.ensure(2 * ntiles * 4));
     CUDA_TRY(r->tileStart.ensure(2 * (ntiles + 1) * 4));
     CUDA_TRY(r->tileCursor.ensure(2 * ntiles * 4));
     CUDA_TRY(r->counters.ensure(8 * 8));
+    if (!r->scanPartial.p || r->scanPartial.cap < 2 * (ntiles / 4096 + 1) * 8) {
+        CUDA_TRY(r->scanPartial.ensure(2 * (ntiles / 4096 + 1) * 8));
+        CUDA_TRY(cudaMemsetAsync(r->scanPartial.p, 0, r->scanPartial.cap, r->stream));
+    }
     if (!r->queue.p) CUDA_TRY(r->queue.ensure(std::max<size_t>(ntri * 2 + ntiles, 1024) * 4));
     if (!r->bigQueue.p) CUDA_TRY(r->bigQueue.ensure(std::max<size_t>(ntri / 4 + ntiles, 1024) * sizeof(TriS)));
     if (r->debugIds) CUDA_TRY(r->primIds.ensure((size_t)r->W * r->H * r->msaa * 4));
@@ -158,6 +165,8 @@ static int issue_draw(iftrcuRenderer* r, bool forceCheck) {
     int rc = ensure_scratch(r);
     if (rc) return rc;
     DrawParams p;
+    r->epoch++;
+    if (r->epoch == 0) r->epoch = 1;
     build_params(r, p);
     const size_t ntiles = (size_t)p.tilesX * p.tilesY;
     cudaStream_t s = r->stream;
@@ -190,7 +199,7 @@ static int issue_draw(iftrcuRenderer* r, bool forceCheck) {
     if (ev) CUDA_TRY(cudaEventRecord(ev[4], s));
     CUDA_TRY(ifr_launch_tiles(p, r->fsId, s));
     if (ev) { CUDA_TRY(cudaEventRecord(ev[5], s)); r->profDraws++; }
-    r->stats.kernel_launches += 2;
+    r->stats.kernel_launches += 3;
     CUDA_TRY(cudaMemcpyAsync(r->hCounters, r->counters.p, 64, cudaMemcpyDeviceToHost, s));
     r->lastDrawCleared = r->pendingClear;
     r->pendingClear = false;
@@ -264,7 +273,7 @@ int iftrcuDestroyInstance(iftrcuRenderer* h) {
     cudaStreamSynchronize(r->stream);
     if (r->registeredHost) cudaHostUnregister(r->registeredHost);
     DevBuf* bufs[] = {&r->ownColor, &r->ownDepth, &r->primIds, &r->ownVB, &r->ownIB, &r->pos, &r->vary, &r->rec, &r->clipBary,
-                      &r->tileBox, &r->fan1List, &r->tileCount, &r->tileStart, &r->tileCursor, &r->queue, &r->bigQueue, &r->counters};
+                      &r->scanPartial, &r->tileBox, &r->fan1List, &r->heavyBits, &r->tileCount, &r->tileStart, &r->tileCursor, &r->queue, &r->bigQueue, &r->counters};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < IFR_MAX_TEX; i++) r->texMem[i].release();
     for (int i = 0; i < IFR_MAX_BUF; i++) r->bufMem[i].release();

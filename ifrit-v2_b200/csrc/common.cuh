@@ -67,10 +67,12 @@ struct DrawParams {
     TriRec* rec; float* clipBary;    // clipBary[slot*6]
     uint2* tileBox;                  // per slot: packed tile bbox, x = x0 | x1<<16, y = y0 | y1<<16 | small<<31; x0>x1 = none
     uint32_t* fan1List;              // slots of second fan triangles (clipped primitives only)
+    uint32_t* heavyBits;             // one bit per first-fan slot: left to the heavy fill pass (multi-tile or big)
     // binning: two queues per tile.  Index 0 = small triangles (u32 slot per pair), 1 = big triangles
     // (one TriS per pair).  tileCount / tileCursor: [2][ntiles]; tileStart: [2][ntiles + 1]
     uint32_t* tileCount; uint32_t* tileStart; uint32_t* tileCursor;
     uint32_t* queue; uint32_t queueCap; TriS* bigQueue; uint32_t bigCap;
+    uint32_t epoch; unsigned long long* scanPartial;   // chained scan: (epoch << 32 | block total) per scan CTA
     unsigned long long* counters;    // [0] assembled, [1] small pairs, [2] frags, [3] overflow flag, [4] fan1 count, [5] big pairs
     // resources
     TexDesc tex[IFR_MAX_TEX]; SampDesc samp[IFR_MAX_TEX]; const float* buf[IFR_MAX_BUF];

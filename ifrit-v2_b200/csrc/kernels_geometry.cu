@@ -9,6 +9,7 @@
 //                                                      setup_bin_kernel<true> (fill)
 // All arithmetic that decides coverage / visibility is integer (24.8 fixed point, 64-bit products) and
 // follows oracle/ifrit_oracle.c op for op; float ops use explicit fmaf / rn intrinsics (-fmad=false).
+#include <algorithm>
 #include "common.cuh"
 #include "tri_setup.cuh"
 #include "../../include/ifrit_b200.h"
@@ -211,11 +212,12 @@ __device__ __forceinline__ void make_edges(const int X[3], const int Y[3], EdgeS
 }
 
 __device__ __forceinline__ bool tile_may_cover(const EdgeSet& e, int tx, int ty) {
-    const long long sx0 = (long long)tx * (IFR_TILE * IFR_SUBPIX), sy0 = (long long)ty * (IFR_TILE * IFR_SUBPIX);
+    // tile origin <= 2^21, |Xa|,|Ya| <= 2^28: the differences fit int32 and the products are single IMAD.WIDE
+    const int sx0 = tx * (IFR_TILE * IFR_SUBPIX), sy0 = ty * (IFR_TILE * IFR_SUBPIX);
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-        const long long E0 = (long long)e.dX[i] * (sy0 - e.Ya[i]) - (long long)e.dY[i] * (sx0 - e.Xa[i]);
-        const long long add = 4080LL * ((e.dX[i] > 0 ? (long long)e.dX[i] : 0) + (e.dY[i] < 0 ? -(long long)e.dY[i] : 0));
+        const long long E0 = (long long)e.dX[i] * (long long)(sy0 - e.Ya[i]) - (long long)e.dY[i] * (long long)(sx0 - e.Xa[i]);
+        const long long add = 4080LL * ((long long)max(e.dX[i], 0) + (long long)max(-e.dY[i], 0));
         if (E0 + add <= 0) return false;
     }
     return true;
@@ -224,22 +226,27 @@ __device__ __forceinline__ bool tile_may_cover(const EdgeSet& e, int tx, int ty)
 // One (triangle, tile) pair.  Count pass: bump the tile's counter of the triangle's class.  Fill
 // pass: small class -> append the slot; big class -> compute the per-tile raster setup once, here,
 // and append it, so that the tile kernel has no setup phase (and no barrier) for big triangles.
-template <bool FILL>
-__device__ __forceinline__ void bin_one(const DrawParams& p, uint32_t slot, int big, int tx, int ty) {
-    if (p.world > 1 && ifr_tile_owner(tx, ty, p.world) != p.rank) return;
+__device__ __forceinline__ bool tile_owned(const DrawParams& p, int tx, int ty) {
+    return p.world <= 1 || ifr_tile_owner(tx, ty, p.world) == p.rank;
+}
+__device__ __forceinline__ void count_one(const DrawParams& p, int big, int tx, int ty) {
+    if (!tile_owned(p, tx, ty)) return;
+    atomicAdd(&p.tileCount[big * p.tilesX * p.tilesY + ty * p.tilesX + tx], 1u);
+}
+// reserve the queue position of a pair (the expensive part: an atomic round trip to L2)
+__device__ __forceinline__ uint32_t reserve_one(const DrawParams& p, int big, int tx, int ty) {
     const int ntiles = p.tilesX * p.tilesY;
     const int tile = ty * p.tilesX + tx;
-    if (!FILL) {
-        atomicAdd(&p.tileCount[big * ntiles + tile], 1u);
-        return;
-    }
-    const uint32_t pos = p.tileStart[big * (ntiles + 1) + tile] + atomicAdd(&p.tileCursor[big * ntiles + tile], 1u);
+    return p.tileStart[big * (ntiles + 1) + tile] + atomicAdd(&p.tileCursor[big * ntiles + tile], 1u);
+}
+__device__ __forceinline__ void emit_one(const DrawParams& p, const RecRegs& rr, uint32_t slot, int big, int tx, int ty,
+                                         uint32_t pos) {
     if (!big) {
         p.queue[pos] = slot;
     } else {
         TriS s;
         int bx0, bx1, by0, by1;
-        if (!setup_tri(p, slot, tx, ty, s, bx0, bx1, by0, by1)) s.box = 0x00ff00ffu;   // empty: rows 255..0
+        if (!setup_from_rec(p, rr, slot, tx, ty, s, bx0, bx1, by0, by1)) s.box = 0x00ff00ffu;   // empty: rows 255..0
         int4* dst = reinterpret_cast<int4*>(p.bigQueue + pos);
         const int4* src = reinterpret_cast<const int4*>(&s);
 #pragma unroll
@@ -249,19 +256,42 @@ __device__ __forceinline__ void bin_one(const DrawParams& p, uint32_t slot, int 
 
 #define IFR_BIG_TILES 16
 
-// per-thread binning of small boxes + warp-cooperative binning of large ones
+// per-thread binning of boxes of <= 16 tiles + warp-cooperative binning of larger ones
 template <bool FILL>
 __device__ __forceinline__ void bin_triangle(const DrawParams& p, bool has, uint32_t slot, int big, int tx0, int tx1,
                                              int ty0, int ty1, const EdgeSet& e) {
     const int nx = tx1 - tx0 + 1, ny = ty1 - ty0 + 1;
     const int nt = has ? nx * ny : 0;
+    RecRegs rr;
+    if (FILL && big && nt > 0 && nt <= IFR_BIG_TILES) load_rec(p, slot, rr);
     if (nt == 1) {
-        bin_one<FILL>(p, slot, big, tx0, ty0);
+        if (!FILL) count_one(p, big, tx0, ty0);
+        else if (tile_owned(p, tx0, ty0)) emit_one(p, rr, slot, big, tx0, ty0, reserve_one(p, big, tx0, ty0));
     } else if (nt > 1 && nt <= IFR_BIG_TILES) {
+        // which tiles of the box can hold a covered sample (exact), as a bit mask
         const bool test = nx > 1 && ny > 1;
-        for (int ty = ty0; ty <= ty1; ty++)
-            for (int tx = tx0; tx <= tx1; tx++)
-                if (!test || tile_may_cover(e, tx, ty)) bin_one<FILL>(p, slot, big, tx, ty);
+        uint32_t keep = 0;
+        {
+            int i = 0;
+            for (int ty = ty0; ty <= ty1; ty++)
+                for (int tx = tx0; tx <= tx1; tx++, i++)
+                    if ((!test || tile_may_cover(e, tx, ty)) && tile_owned(p, tx, ty)) keep |= 1u << i;
+        }
+        if (!FILL) {
+            for (uint32_t m = keep; m; m &= m - 1) {
+                const int i = __ffs(m) - 1;
+                atomicAdd(&p.tileCount[big * p.tilesX * p.tilesY + (ty0 + i / nx) * p.tilesX + tx0 + i % nx], 1u);
+            }
+        } else {
+            // all position reservations first (independent atomics overlap), then the stores
+            uint32_t pos[IFR_BIG_TILES];
+#pragma unroll
+            for (int i = 0; i < IFR_BIG_TILES; i++)
+                if ((keep >> i) & 1) pos[i] = reserve_one(p, big, tx0 + i % nx, ty0 + i / nx);
+#pragma unroll
+            for (int i = 0; i < IFR_BIG_TILES; i++)
+                if ((keep >> i) & 1) emit_one(p, rr, slot, big, tx0 + i % nx, ty0 + i / nx, pos[i]);
+        }
     }
     unsigned wideBox = __ballot_sync(0xffffffffu, nt > IFR_BIG_TILES);
     const int lane = threadIdx.x & 31;
@@ -278,10 +308,14 @@ __device__ __forceinline__ void bin_triangle(const DrawParams& p, bool has, uint
             be.dX[i] = __shfl_sync(0xffffffffu, e.dX[i], src); be.dY[i] = __shfl_sync(0xffffffffu, e.dY[i], src);
             be.Xa[i] = __shfl_sync(0xffffffffu, e.Xa[i], src); be.Ya[i] = __shfl_sync(0xffffffffu, e.Ya[i], src);
         }
+        RecRegs wr;
+        if (FILL && sbig) load_rec(p, s, wr);
         const int bnx = bx1 - bx0 + 1, total = bnx * (by1 - by0 + 1);
         for (int i = lane; i < total; i += 32) {
             const int tx = bx0 + i % bnx, ty = by0 + i / bnx;
-            if (tile_may_cover(be, tx, ty)) bin_one<FILL>(p, s, sbig, tx, ty);
+            if (!tile_may_cover(be, tx, ty) || !tile_owned(p, tx, ty)) continue;
+            if (!FILL) atomicAdd(&p.tileCount[sbig * p.tilesX * p.tilesY + ty * p.tilesX + tx], 1u);
+            else emit_one(p, wr, s, sbig, tx, ty, reserve_one(p, sbig, tx, ty));
         }
     }
 }
@@ -337,98 +371,165 @@ __global__ void __launch_bounds__(256) setup_count_kernel(const __grid_constant_
         }
         if (f == 1 && __ballot_sync(0xffffffffu, has) == 0) continue;   // warp-uniform skip
         bin_triangle<false>(p, has, slot, big, a[f].tx0, a[f].tx1, a[f].ty0, a[f].ty1, e);
+        // everything but single-tile small triangles of the first fan is left to the heavy fill pass:
+        // one bit per triangle, one plain 4-byte store per warp (no atomics); second-fan slots are
+        // already listed in fan1List
+        if (f == 0) {
+            const bool heavy = has && (big || a[f].tx1 > a[f].tx0 || a[f].ty1 > a[f].ty0);
+            const unsigned hm = __ballot_sync(0xffffffffu, heavy);
+            if ((threadIdx.x & 31) == 0) p.heavyBits[t >> 5] = hm;
+        }
     }
     // block-aggregated statistics
     nasm = __reduce_add_sync(0xffffffffu, (unsigned)nasm);
     if ((threadIdx.x & 31) == 0 && nasm) atomicAdd(&p.counters[0], nasm);
 }
 
-// pass 3: one thread per slot of pass 1 (fan-0 slots densely, fan-1 slots through fan1List)
-__global__ void __launch_bounds__(256) fill_kernel(const __grid_constant__ DrawParams p) {
+// pass 3a: single-tile small triangles of the first fan — one thread per input triangle, nothing but
+// tileBox -> {tileStart, cursor atomic} -> 4-byte store, so that it runs at full occupancy
+__global__ void __launch_bounds__(256) fill_light_kernel(const __grid_constant__ DrawParams p) {
     if (p.counters[3]) return;   // a queue is too small: host re-issues the draw with larger ones
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned long long nfan1 = p.counters[4];
+    if (t >= p.ntri) return;
+    const uint2 box = p.tileBox[t];
+    const int tx0 = box.x & 0xffff, tx1 = box.x >> 16, ty0 = box.y & 0xffff, ty1 = (box.y >> 16) & 0x7fff;
+    if (tx0 != tx1 || ty0 != ty1 || !(box.y >> 31)) return;     // empty, multi-tile or big: heavy list
+    if (!tile_owned(p, tx0, ty0)) return;
+    p.queue[reserve_one(p, 0, tx0, ty0)] = (uint32_t)t;
+}
+
+// pass 3b: the heavy slots (multi-tile or big triangles via the per-warp bit words, second-fan slots via
+// fan1List).  A warp takes 32 bit words (1024 triangles) at a time and compacts their set bits so
+// that every lane gets a slot: no atomics, no list.
+__device__ __forceinline__ void fill_heavy_slot(const DrawParams& p, bool has, uint32_t slot) {
+    int tx0 = 0, tx1 = 0, ty0 = 0, ty1 = 0, big = 0;
+    EdgeSet e;
+    if (has) {
+        const uint2 box = p.tileBox[slot];
+        tx0 = box.x & 0xffff; tx1 = box.x >> 16; ty0 = box.y & 0xffff; ty1 = (box.y >> 16) & 0x7fff;
+        big = !(box.y >> 31);
+        has = tx0 <= tx1;
+        if (has && (tx1 > tx0 || ty1 > ty0)) {
+            const int4* r = reinterpret_cast<const int4*>(p.rec + slot);
+            int X[3], Y[3];
 #pragma unroll
-    for (int f = 0; f < 2; f++) {
-        bool has = false;
-        uint32_t slot = 0;
-        if (f == 0) { has = t < p.ntri; slot = (uint32_t)t; }
-        else if ((unsigned long long)t < nfan1) { has = true; slot = p.fan1List[t]; }
-        if (f == 1 && __ballot_sync(0xffffffffu, has) == 0) continue;
-        int tx0 = 0, tx1 = 0, ty0 = 0, ty1 = 0, big = 0;
-        EdgeSet e;
-        if (has) {
-            const uint2 box = p.tileBox[slot];
-            tx0 = box.x & 0xffff; tx1 = box.x >> 16; ty0 = box.y & 0xffff; ty1 = (box.y >> 16) & 0x7fff;
-            big = !(box.y >> 31);
-            has = tx0 <= tx1;
-            if (has && (tx1 > tx0 || ty1 > ty0)) {
-                const int4* r = reinterpret_cast<const int4*>(p.rec + slot);
-                int X[3], Y[3];
-#pragma unroll
-                for (int j = 0; j < 3; j++) { const int4 v = r[j]; X[j] = v.x; Y[j] = v.y; }
-                make_edges(X, Y, e);
-            }
+            for (int j = 0; j < 3; j++) { const int4 v = __ldg(r + j); X[j] = v.x; Y[j] = v.y; }
+            make_edges(X, Y, e);
         }
-        bin_triangle<true>(p, has, slot, big, tx0, tx1, ty0, ty1, e);
+    }
+    bin_triangle<true>(p, has, slot, big, tx0, tx1, ty0, ty1, e);
+}
+
+__global__ void __launch_bounds__(128) fill_heavy_kernel(const __grid_constant__ DrawParams p, const int wordsPerWarp) {
+    if (p.counters[3]) return;
+    const unsigned long long nfan1 = p.counters[4];
+    const long long nwords = (p.ntri + 31) / 32;
+    const int lane = threadIdx.x & 31;
+    const long long warpId = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    // wordsPerWarp (1..32): small draws spread over many warps, large ones compact 1024 triangles per warp
+    for (long long wb = warpId * wordsPerWarp; wb < nwords; wb += nwarps * wordsPerWarp) {
+        const uint32_t bits = (lane < wordsPerWarp && wb + lane < nwords) ? p.heavyBits[wb + lane] : 0u;
+        const int cnt = __popc(bits);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        const int excl = incl - cnt, total = __shfl_sync(0xffffffffu, incl, 31);
+        for (int j = 0; j < total; j += 32) {
+            const int item = j + lane;
+            const bool has = item < total;
+            int k = 0;   // number of words whose inclusive count is <= item = index of the word holding the item
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const int v = __shfl_sync(0xffffffffu, incl, k + step - 1);
+                if (has && v <= item) k += step;
+            }
+            const uint32_t wbits = __shfl_sync(0xffffffffu, bits, k);
+            const int wexcl = __shfl_sync(0xffffffffu, excl, k);
+            const uint32_t slot = has ? (uint32_t)((wb + k) * 32 + __fns(wbits, 0, item - wexcl + 1)) : 0u;
+            fill_heavy_slot(p, has, slot);
+        }
+    }
+    for (unsigned long long i0 = (unsigned long long)warpId * 32; i0 < nfan1; i0 += (unsigned long long)nwarps * 32) {
+        const bool has = i0 + lane < nfan1;
+        fill_heavy_slot(p, has, has ? p.fan1List[i0 + lane] : 0u);
     }
 }
 
-// pass 2: exclusive scan of the per-tile counts, one CTA per queue class (<= 130k tiles at 8K); cursor
-// reset, totals -> counters[1] (small pairs) / counters[5] (big pairs), overflow flag -> counters[3]
+// pass 2: exclusive scan of the per-tile counts of both queue classes.  Chained multi-CTA scan: CTA b
+// scans 4096 counts locally, publishes (epoch, total) and sums the totals of its predecessors (all
+// resident: <= 64 CTAs at 8K).  Cursor reset, totals -> counters[1] (small pairs) / counters[5]
+// (big pairs), overflow flag -> counters[3].
+#define IFR_SCAN_ITEMS 4096
 __global__ void __launch_bounds__(1024) scan_kernel(const __grid_constant__ DrawParams p) {
     __shared__ uint32_t warpSums[32];
-    __shared__ uint32_t carry;
+    __shared__ uint32_t prefix;
     const int n = p.tilesX * p.tilesY;
-    const int cls = blockIdx.x;
+    const int cls = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
     const uint32_t* count = p.tileCount + (size_t)cls * n;
     uint32_t* start = p.tileStart + (size_t)cls * (n + 1);
     uint32_t* cursor = p.tileCursor + (size_t)cls * n;
+    volatile unsigned long long* partial = p.scanPartial + (size_t)cls * nblk;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) carry = 0;
-    __syncthreads();
-    for (int base = 0; base < n; base += 1024 * 4) {
-        uint32_t v[4];
-        uint32_t sum = 0;
+    const int i0 = blk * IFR_SCAN_ITEMS + tid * 4;
+    uint32_t v[4];
+    if (i0 + 3 < n && ((n & 3) == 0)) {
+        const uint4 q = *reinterpret_cast<const uint4*>(count + i0);
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int i = base + tid * 4 + k;
-            v[k] = i < n ? count[i] : 0u;
-            sum += v[k];
-        }
-        uint32_t incl = sum;
+        for (int k = 0; k < 4; k++) v[k] = i0 + k < n ? count[i0 + k] : 0u;
+    }
+    const uint32_t sum = v[0] + v[1] + v[2] + v[3];
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) warpSums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        const uint32_t w = warpSums[lane];
+        uint32_t wi = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += y;
+            const uint32_t y = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += y;
         }
-        if (lane == 31) warpSums[wid] = incl;
-        __syncthreads();
-        if (wid == 0) {
-            uint32_t w = warpSums[lane], wi = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, wi, o);
-                if (lane >= o) wi += y;
+        warpSums[lane] = wi - w;
+        const uint32_t total = __shfl_sync(0xffffffffu, wi, 31);
+        if (lane == 0) {
+            __threadfence();
+            partial[blk] = ((unsigned long long)p.epoch << 32) | total;
+        }
+        // totals of the predecessors (spin until each has published this draw's epoch)
+        uint32_t pre = 0;
+        for (int b0 = 0; b0 < blk; b0 += 32) {
+            uint32_t t = 0;
+            if (b0 + lane < blk) {
+                unsigned long long x;
+                do { x = partial[b0 + lane]; } while ((uint32_t)(x >> 32) != p.epoch);
+                t = (uint32_t)x;
             }
-            warpSums[lane] = wi - w;
+            pre += __reduce_add_sync(0xffffffffu, t);
         }
-        __syncthreads();
-        uint32_t run = carry + warpSums[wid] + (incl - sum);
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int i = base + tid * 4 + k;
-            if (i < n) { start[i] = run; cursor[i] = 0u; }
-            run += v[k];
+        if (lane == 0) prefix = pre;
+        if (blk == nblk - 1 && lane == 0) {
+            const uint32_t all = pre + total;
+            start[n] = all;
+            p.counters[cls ? 5 : 1] = all;
+            if (all > (cls ? p.bigCap : p.queueCap)) p.counters[3] = 1ull;
         }
-        __syncthreads();
-        if (tid == 1023) carry = run;
-        __syncthreads();
     }
-    if (tid == 0) {
-        start[n] = carry;
-        p.counters[cls ? 5 : 1] = carry;
-        if (carry > (cls ? p.bigCap : p.queueCap)) p.counters[3] = 1ull;
+    __syncthreads();
+    uint32_t run = prefix + warpSums[wid] + (incl - sum);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (i0 + k < n) { start[i0 + k] = run; cursor[i0 + k] = 0u; }
+        run += v[k];
     }
 }
 
@@ -438,11 +539,17 @@ cudaError_t ifr_launch_setup_count(const DrawParams& p, cudaStream_t s) {
     return cudaGetLastError();
 }
 cudaError_t ifr_launch_scan(const DrawParams& p, cudaStream_t s) {
-    scan_kernel<<<2, 1024, 0, s>>>(p);
+    const int n = p.tilesX * p.tilesY;
+    scan_kernel<<<dim3((n + IFR_SCAN_ITEMS - 1) / IFR_SCAN_ITEMS, 2), 1024, 0, s>>>(p);
     return cudaGetLastError();
 }
 cudaError_t ifr_launch_fill(const DrawParams& p, cudaStream_t s) {
     if (p.ntri <= 0) return cudaSuccess;
-    fill_kernel<<<(p.ntri + 255) / 256, 256, 0, s>>>(p);
+    fill_light_kernel<<<(p.ntri + 255) / 256, 256, 0, s>>>(p);
+    const long long nwords = ((long long)p.ntri + 31) / 32;
+    int wordsPerWarp = 1;
+    while (wordsPerWarp < 32 && nwords / (wordsPerWarp * 2) >= 148 * 16) wordsPerWarp *= 2;
+    const int heavyBlocks = (int)std::min<long long>((nwords / wordsPerWarp + 4) / 4 + 1, 148 * 16);
+    fill_heavy_kernel<<<heavyBlocks, 128, 0, s>>>(p, wordsPerWarp);
     return cudaGetLastError();
 }

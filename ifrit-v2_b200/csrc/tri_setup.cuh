@@ -5,21 +5,27 @@
 #pragma once
 #include "common.cuh"
 
-__device__ __forceinline__ bool setup_tri(const DrawParams& p, uint32_t slot, int tileX, int tileY, TriS& s,
-                                          int& bx0, int& bx1, int& by0, int& by1) {
+struct RecRegs { int X[3], Y[3]; float Z[3]; float ar; uint32_t flags; };
+
+__device__ __forceinline__ void load_rec(const DrawParams& p, uint32_t slot, RecRegs& rr) {
     const int4* r = reinterpret_cast<const int4*>(p.rec + slot);
-    int X[3], Y[3];
-    float Z[3];
 #pragma unroll
     for (int j = 0; j < 3; j++) {
         const int4 v = __ldg(r + j);
-        X[j] = v.x; Y[j] = v.y; Z[j] = __int_as_float(v.z);
+        rr.X[j] = v.x; rr.Y[j] = v.y; rr.Z[j] = __int_as_float(v.z);
     }
     const int4 w3 = __ldg(r + 3);
+    rr.ar = __int_as_float(w3.x);
+    rr.flags = (uint32_t)w3.y;
+}
+
+__device__ __forceinline__ bool setup_from_rec(const DrawParams& p, const RecRegs& rr, uint32_t slot, int tileX, int tileY,
+                                               TriS& s, int& bx0, int& bx1, int& by0, int& by1) {
+    const int* X = rr.X; const int* Y = rr.Y;
     s.slot = slot;
-    s.ar = __int_as_float(w3.x);
-    s.flags = (uint32_t)w3.y;
-    s.z0 = Z[0]; s.z1 = Z[1]; s.z2 = Z[2];
+    s.ar = rr.ar;
+    s.flags = rr.flags;
+    s.z0 = rr.Z[0]; s.z1 = rr.Z[1]; s.z2 = rr.Z[2];
     s.pad[0] = 0; s.pad[1] = 0;
     // tile origin <= 2^21 and |X|,|Y| <= 2^28: the differences fit int32, products are IMAD.WIDE
     const int sx0 = tileX * (IFR_TILE * IFR_SUBPIX), sy0 = tileY * (IFR_TILE * IFR_SUBPIX);
@@ -41,4 +47,11 @@ __device__ __forceinline__ bool setup_tri(const DrawParams& p, uint32_t slot, in
     bx1 = min(min(px1, p.W - 1) - ox, IFR_TILE - 1); by1 = min(min(py1, p.H - 1) - oy, IFR_TILE - 1);
     s.box = (uint32_t)(bx0 & 0xff) | ((uint32_t)(bx1 & 0xff) << 8) | ((uint32_t)(by0 & 0xff) << 16) | ((uint32_t)(by1 & 0xff) << 24);
     return bx0 <= bx1 && by0 <= by1;
+}
+
+__device__ __forceinline__ bool setup_tri(const DrawParams& p, uint32_t slot, int tileX, int tileY, TriS& s,
+                                          int& bx0, int& bx1, int& by0, int& by1) {
+    RecRegs rr;
+    load_rec(p, slot, rr);
+    return setup_from_rec(p, rr, slot, tileX, tileY, s, bx0, bx1, by0, by1);
 }
