@@ -256,44 +256,26 @@ __device__ __forceinline__ void emit_one(const DrawParams& p, const RecRegs& rr,
 
 #define IFR_BIG_TILES 16
 
-// per-thread binning of boxes of <= 16 tiles + warp-cooperative binning of larger ones
-template <bool FILL>
+// binning of boxes of <= 16 tiles by a group of G lanes that share the slot (lane `sub` of the group
+// takes tiles sub, sub + G, ...; G = 1 in the count pass) + warp-cooperative binning of larger boxes
+template <bool FILL, int G>
 __device__ __forceinline__ void bin_triangle(const DrawParams& p, bool has, uint32_t slot, int big, int tx0, int tx1,
-                                             int ty0, int ty1, const EdgeSet& e) {
+                                             int ty0, int ty1, const EdgeSet& e, int sub) {
     const int nx = tx1 - tx0 + 1, ny = ty1 - ty0 + 1;
     const int nt = has ? nx * ny : 0;
-    RecRegs rr;
-    if (FILL && big && nt > 0 && nt <= IFR_BIG_TILES) load_rec(p, slot, rr);
-    if (nt == 1) {
-        if (!FILL) count_one(p, big, tx0, ty0);
-        else if (tile_owned(p, tx0, ty0)) emit_one(p, rr, slot, big, tx0, ty0, reserve_one(p, big, tx0, ty0));
-    } else if (nt > 1 && nt <= IFR_BIG_TILES) {
-        // which tiles of the box can hold a covered sample (exact), as a bit mask
-        const bool test = nx > 1 && ny > 1;
-        uint32_t keep = 0;
-        {
-            int i = 0;
-            for (int ty = ty0; ty <= ty1; ty++)
-                for (int tx = tx0; tx <= tx1; tx++, i++)
-                    if ((!test || tile_may_cover(e, tx, ty)) && tile_owned(p, tx, ty)) keep |= 1u << i;
-        }
-        if (!FILL) {
-            for (uint32_t m = keep; m; m &= m - 1) {
-                const int i = __ffs(m) - 1;
-                atomicAdd(&p.tileCount[big * p.tilesX * p.tilesY + (ty0 + i / nx) * p.tilesX + tx0 + i % nx], 1u);
-            }
-        } else {
-            // all position reservations first (independent atomics overlap), then the stores
-            uint32_t pos[IFR_BIG_TILES];
-#pragma unroll
-            for (int i = 0; i < IFR_BIG_TILES; i++)
-                if ((keep >> i) & 1) pos[i] = reserve_one(p, big, tx0 + i % nx, ty0 + i / nx);
-#pragma unroll
-            for (int i = 0; i < IFR_BIG_TILES; i++)
-                if ((keep >> i) & 1) emit_one(p, rr, slot, big, tx0 + i % nx, ty0 + i / nx, pos[i]);
+    if (nt >= 1 && nt <= IFR_BIG_TILES && sub < nt) {
+        RecRegs rr;
+        if (FILL && big) load_rec(p, slot, rr);
+        const bool test = nx > 1 && ny > 1;     // a one-tile-wide box is covered in every tile of it
+        for (int i = sub; i < nt; i += G) {
+            const int tx = tx0 + i % nx, ty = ty0 + i / nx;
+            if (test && !tile_may_cover(e, tx, ty)) continue;
+            if (!tile_owned(p, tx, ty)) continue;
+            if (!FILL) atomicAdd(&p.tileCount[big * p.tilesX * p.tilesY + ty * p.tilesX + tx], 1u);
+            else emit_one(p, rr, slot, big, tx, ty, reserve_one(p, big, tx, ty));
         }
     }
-    unsigned wideBox = __ballot_sync(0xffffffffu, nt > IFR_BIG_TILES);
+    unsigned wideBox = __ballot_sync(0xffffffffu, nt > IFR_BIG_TILES && sub == 0);
     const int lane = threadIdx.x & 31;
     while (wideBox) {
         const int src = __ffs(wideBox) - 1;
@@ -370,7 +352,7 @@ __global__ void __launch_bounds__(256) setup_count_kernel(const __grid_constant_
             p.tileBox[slot] = box;
         }
         if (f == 1 && __ballot_sync(0xffffffffu, has) == 0) continue;   // warp-uniform skip
-        bin_triangle<false>(p, has, slot, big, a[f].tx0, a[f].tx1, a[f].ty0, a[f].ty1, e);
+        bin_triangle<false, 1>(p, has, slot, big, a[f].tx0, a[f].tx1, a[f].ty0, a[f].ty1, e, 0);
         // everything but single-tile small triangles of the first fan is left to the heavy fill pass:
         // one bit per triangle, one plain 4-byte store per warp (no atomics); second-fan slots are
         // already listed in fan1List
@@ -401,7 +383,8 @@ __global__ void __launch_bounds__(256) fill_light_kernel(const __grid_constant__
 // pass 3b: the heavy slots (multi-tile or big triangles via the per-warp bit words, second-fan slots via
 // fan1List).  A warp takes 32 bit words (1024 triangles) at a time and compacts their set bits so
 // that every lane gets a slot: no atomics, no list.
-__device__ __forceinline__ void fill_heavy_slot(const DrawParams& p, bool has, uint32_t slot) {
+#define IFR_FILL_GROUP 4      // lanes that share one heavy slot (each takes every 4th tile of its box)
+__device__ __forceinline__ void fill_heavy_slot(const DrawParams& p, bool has, uint32_t slot, int sub) {
     int tx0 = 0, tx1 = 0, ty0 = 0, ty1 = 0, big = 0;
     EdgeSet e;
     if (has) {
@@ -417,16 +400,20 @@ __device__ __forceinline__ void fill_heavy_slot(const DrawParams& p, bool has, u
             make_edges(X, Y, e);
         }
     }
-    bin_triangle<true>(p, has, slot, big, tx0, tx1, ty0, ty1, e);
+    bin_triangle<true, IFR_FILL_GROUP>(p, has, slot, big, tx0, tx1, ty0, ty1, e, sub);
 }
 
-__global__ void __launch_bounds__(128) fill_heavy_kernel(const __grid_constant__ DrawParams p, const int wordsPerWarp) {
+__global__ void __launch_bounds__(128) fill_heavy_kernel(const __grid_constant__ DrawParams p, const int wordsPerWarp, const int split) {
     if (p.counters[3]) return;
     const unsigned long long nfan1 = p.counters[4];
     const long long nwords = (p.ntri + 31) / 32;
-    const int lane = threadIdx.x & 31;
-    const long long warpId = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    // wordsPerWarp (1..32): small draws spread over many warps, large ones compact 1024 triangles per warp
+    const int lane = threadIdx.x & 31, grp = lane / IFR_FILL_GROUP, sub = lane % IFR_FILL_GROUP;
+    constexpr int PER = 32 / IFR_FILL_GROUP;    // slots per warp pass
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    // wordsPerWarp (1..32): small draws spread over many warps, large ones compact 1024 triangles per warp;
+    // split (1 or 4): for small draws, `split` warps share one batch and take every split-th pass of it
+    const long long warpId = gw / split, nwarps = (((long long)gridDim.x * blockDim.x) >> 5) / split;
+    const int part = (int)(gw % split);
     for (long long wb = warpId * wordsPerWarp; wb < nwords; wb += nwarps * wordsPerWarp) {
         const uint32_t bits = (lane < wordsPerWarp && wb + lane < nwords) ? p.heavyBits[wb + lane] : 0u;
         const int cnt = __popc(bits);
@@ -437,8 +424,8 @@ __global__ void __launch_bounds__(128) fill_heavy_kernel(const __grid_constant__
             if (lane >= o) incl += y;
         }
         const int excl = incl - cnt, total = __shfl_sync(0xffffffffu, incl, 31);
-        for (int j = 0; j < total; j += 32) {
-            const int item = j + lane;
+        for (int j = part * PER; j < total; j += PER * split) {
+            const int item = j + grp;
             const bool has = item < total;
             int k = 0;   // number of words whose inclusive count is <= item = index of the word holding the item
 #pragma unroll
@@ -449,12 +436,12 @@ __global__ void __launch_bounds__(128) fill_heavy_kernel(const __grid_constant__
             const uint32_t wbits = __shfl_sync(0xffffffffu, bits, k);
             const int wexcl = __shfl_sync(0xffffffffu, excl, k);
             const uint32_t slot = has ? (uint32_t)((wb + k) * 32 + __fns(wbits, 0, item - wexcl + 1)) : 0u;
-            fill_heavy_slot(p, has, slot);
+            fill_heavy_slot(p, has, slot, sub);
         }
     }
-    for (unsigned long long i0 = (unsigned long long)warpId * 32; i0 < nfan1; i0 += (unsigned long long)nwarps * 32) {
-        const bool has = i0 + lane < nfan1;
-        fill_heavy_slot(p, has, has ? p.fan1List[i0 + lane] : 0u);
+    for (unsigned long long i0 = (unsigned long long)gw * PER; i0 < nfan1; i0 += (unsigned long long)nwarps * split * PER) {
+        const bool has = i0 + grp < nfan1;
+        fill_heavy_slot(p, has, has ? p.fan1List[i0 + grp] : 0u, sub);
     }
 }
 
@@ -548,8 +535,9 @@ cudaError_t ifr_launch_fill(const DrawParams& p, cudaStream_t s) {
     fill_light_kernel<<<(p.ntri + 255) / 256, 256, 0, s>>>(p);
     const long long nwords = ((long long)p.ntri + 31) / 32;
     int wordsPerWarp = 1;
-    while (wordsPerWarp < 32 && nwords / (wordsPerWarp * 2) >= 148 * 16) wordsPerWarp *= 2;
-    const int heavyBlocks = (int)std::min<long long>((nwords / wordsPerWarp + 4) / 4 + 1, 148 * 16);
-    fill_heavy_kernel<<<heavyBlocks, 128, 0, s>>>(p, wordsPerWarp);
+    while (wordsPerWarp < 32 && nwords / (wordsPerWarp * 2) >= 148 * 16 * IFR_FILL_GROUP) wordsPerWarp *= 2;
+    const int split = wordsPerWarp == 1 ? 4 : 1;
+    const int heavyBlocks = (int)std::min<long long>((nwords / wordsPerWarp + 1) * split / 4 + 1, 148 * 16);
+    fill_heavy_kernel<<<heavyBlocks, 128, 0, s>>>(p, wordsPerWarp, split);
     return cudaGetLastError();
 }
