@@ -61,6 +61,7 @@ struct iftrcuRenderer {
     const uint8_t* dVB = nullptr; DevBuf ownVB; int nverts = 0, stride = 0, nattr = 0; int attrOff[IFR_MAX_VARY + 1] = {0};
     const int32_t* dIB = nullptr; DevBuf ownIB; int icount = 0;
     int vsId = -1, fsId = -1, nvary = 0;
+    bool fusedVS = true;   // vertex stage fused into triangle setup (default) or stand-alone vs_kernel
 
     // state (defaults: TileRasterRendererCuda.h:42-47, CU:186-189)
     int msaa = 1, depthFunc = IF_COMPARE_OP_LESS, depthTest = 1, cullMode = IF_CULL_MODE_NONE;
@@ -125,6 +126,13 @@ static void build_params(iftrcuRenderer* r, DrawParams& p) {
     memcpy(p.attrOff, r->attrOff, sizeof p.attrOff);
     p.ib = r->dIB; p.ntri = r->icount / 3;
     p.pos = (float4*)r->pos.p; p.vary = (float4*)r->vary.p;
+    if (r->fusedVS) {
+        p.varyBase = r->dVB; p.varyStride = r->stride;
+        for (int k = 0; k < IFR_MAX_VARY; k++) p.varyOff[k] = r->attrOff[k + 1];
+    } else {
+        p.varyBase = (const uint8_t*)r->vary.p; p.varyStride = r->nvary * 16;
+        for (int k = 0; k < IFR_MAX_VARY; k++) p.varyOff[k] = 16 * k;
+    }
     p.rec = (TriRec*)r->rec.p; p.clipBary = (float*)r->clipBary.p; p.tileBox = (uint2*)r->tileBox.p;
     p.fan1List = (uint32_t*)r->fan1List.p; p.heavyBits = (uint32_t*)r->heavyBits.p;
     p.tileCount = (uint32_t*)r->tileCount.p; p.tileStart = (uint32_t*)r->tileStart.p;
@@ -140,8 +148,10 @@ static void build_params(iftrcuRenderer* r, DrawParams& p) {
 
 static int ensure_scratch(iftrcuRenderer* r) {
     const size_t ntri = (size_t)r->icount / 3, ntiles = (size_t)((r->W + 15) / 16) * ((r->H + 15) / 16);
-    CUDA_TRY(r->pos.ensure(std::max<size_t>(1, r->nverts) * sizeof(float4)));
-    CUDA_TRY(r->vary.ensure(std::max<size_t>(1, (size_t)r->nverts * std::max(1, r->nvary)) * sizeof(float4)));
+    if (!r->fusedVS) {
+        CUDA_TRY(r->pos.ensure(std::max<size_t>(1, r->nverts) * sizeof(float4)));
+        CUDA_TRY(r->vary.ensure(std::max<size_t>(1, (size_t)r->nverts * std::max(1, r->nvary)) * sizeof(float4)));
+    }
     CUDA_TRY(r->rec.ensure(std::max<size_t>(1, 2 * ntri) * sizeof(TriRec)));
     CUDA_TRY(r->clipBary.ensure(std::max<size_t>(1, 2 * ntri) * 6 * sizeof(float)));
     CUDA_TRY(r->tileBox.ensure(std::max<size_t>(1, 2 * ntri) * sizeof(uint2)));
@@ -175,13 +185,13 @@ static int issue_draw(iftrcuRenderer* r, bool forceCheck) {
     cudaEvent_t* ev = nullptr;
     if (r->profiling && !forceCheck && r->queueChecked) ev = &r->profEvents[(r->profDraws % IFR_PROF_RING) * IFR_PROF_EVENTS];
     if (ev) CUDA_TRY(cudaEventRecord(ev[0], s));
-    CUDA_TRY(ifr_launch_vertex(p, r->vsId, s));
+    if (!r->fusedVS) { CUDA_TRY(ifr_launch_vertex(p, r->vsId, s)); r->stats.kernel_launches += 1; }
     if (ev) CUDA_TRY(cudaEventRecord(ev[1], s));
-    CUDA_TRY(ifr_launch_setup_count(p, s));
+    CUDA_TRY(ifr_launch_setup_count(p, r->fusedVS ? r->vsId : -1, s));
     if (ev) CUDA_TRY(cudaEventRecord(ev[2], s));
     CUDA_TRY(ifr_launch_scan(p, s));
     if (ev) CUDA_TRY(cudaEventRecord(ev[3], s));
-    r->stats.kernel_launches += 3;
+    r->stats.kernel_launches += 2;
     if (forceCheck || !r->queueChecked) {
         // first draw with this geometry / state: size the (triangle, tile) queue exactly (one sync)
         unsigned long long c[8];
@@ -571,6 +581,7 @@ int iftrcuSetTilePartition(iftrcuRenderer* h, int rank, int worldSize) {
     return IFRIT_OK;
 }
 int iftrcuSetDebugPrimitiveIds(iftrcuRenderer* h, int enable) { R_CHECK(h); r->debugIds = enable != 0; return IFRIT_OK; }
+int iftrcuSetVertexStageFused(iftrcuRenderer* h, int enable) { R_CHECK(h); r->fusedVS = enable != 0; return IFRIT_OK; }
 
 int iftrcuClear(iftrcuRenderer* h) {
     R_CHECK(h);

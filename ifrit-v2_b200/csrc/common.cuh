@@ -62,7 +62,10 @@ struct DrawParams {
     // geometry
     const uint8_t* vb; int stride, nattr, nvary, nverts; int attrOff[IFR_MAX_VARY + 1];
     const int32_t* ib; int ntri;
-    float4* pos; float4* vary;
+    float4* pos; float4* vary;       // outputs of the stand-alone vertex stage (unused when it is fused into setup)
+    // where the tile kernel reads varying k of vertex i: varyBase + i * varyStride + varyOff[k] (the vertex
+    // buffer itself when the vertex stage is fused: the registry's vertex shaders pass attributes through)
+    const uint8_t* varyBase; int varyStride; int varyOff[IFR_MAX_VARY];
     // assembled triangles: rec[slot*3+v]; slot = prim (fan 0) or ntri + prim (fan 1)
     TriRec* rec; float* clipBary;    // clipBary[slot*6]
     uint2* tileBox;                  // per slot: packed tile bbox, x = x0 | x1<<16, y = y0 | y1<<16 | small<<31; x0>x1 = none
@@ -93,7 +96,7 @@ __host__ __device__ inline int ifr_tile_owner(int tx, int ty, int world) {
 // kernel launchers (defined in the .cu files)
 struct Launch { cudaStream_t stream; };
 cudaError_t ifr_launch_vertex(const DrawParams& p, int vsId, cudaStream_t s);
-cudaError_t ifr_launch_setup_count(const DrawParams& p, cudaStream_t s);
+cudaError_t ifr_launch_setup_count(const DrawParams& p, int vsMode, cudaStream_t s);   // vsMode -1: positions from vs_kernel
 cudaError_t ifr_launch_scan(const DrawParams& p, cudaStream_t s);   // both queues
 cudaError_t ifr_launch_fill(const DrawParams& p, cudaStream_t s);
 cudaError_t ifr_launch_tiles(const DrawParams& p, int fsId, cudaStream_t s);

@@ -18,24 +18,30 @@
 
 // ------------------------------------------------------------------------------------------------
 // Vertex stage: one thread per vertex, 128-bit loads of the interleaved attributes, 128-bit stores.
+// the vertex shader functors of the registry (position only: both pass the other attributes through)
+template <int VS>
+__device__ __forceinline__ float4 run_vs(const DrawParams& p, const float4 a0) {
+    if (VS == IFRIT_VS_MVP) {
+        const float4* m = reinterpret_cast<const float4*>(p.buf[0]);
+        const float4 r0 = __ldg(m), r1 = __ldg(m + 1), r2 = __ldg(m + 2), r3 = __ldg(m + 3);
+        float4 o;
+        o.x = fmaf(r0.w, a0.w, fmaf(r0.z, a0.z, fmaf(r0.y, a0.y, __fmul_rn(r0.x, a0.x))));
+        o.y = fmaf(r1.w, a0.w, fmaf(r1.z, a0.z, fmaf(r1.y, a0.y, __fmul_rn(r1.x, a0.x))));
+        o.z = fmaf(r2.w, a0.w, fmaf(r2.z, a0.z, fmaf(r2.y, a0.y, __fmul_rn(r2.x, a0.x))));
+        o.w = fmaf(r3.w, a0.w, fmaf(r3.z, a0.z, fmaf(r3.y, a0.y, __fmul_rn(r3.x, a0.x))));
+        return o;
+    }
+    return a0;
+}
+
+// Stand-alone vertex stage (used when the fused path is switched off, iftrcuSetVertexStageFused):
+// one thread per vertex, 128-bit loads of the interleaved attributes, 128-bit stores.
 template <int VS>
 __global__ void __launch_bounds__(256) vs_kernel(const __grid_constant__ DrawParams p) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= p.nverts) return;
     const uint8_t* base = p.vb + (size_t)v * p.stride;
-    const float4 a0 = __ldg(reinterpret_cast<const float4*>(base + p.attrOff[0]));
-    float4 o;
-    if (VS == IFRIT_VS_MVP) {
-        const float4* m = reinterpret_cast<const float4*>(p.buf[0]);
-        const float4 r0 = __ldg(m), r1 = __ldg(m + 1), r2 = __ldg(m + 2), r3 = __ldg(m + 3);
-        o.x = fmaf(r0.w, a0.w, fmaf(r0.z, a0.z, fmaf(r0.y, a0.y, __fmul_rn(r0.x, a0.x))));
-        o.y = fmaf(r1.w, a0.w, fmaf(r1.z, a0.z, fmaf(r1.y, a0.y, __fmul_rn(r1.x, a0.x))));
-        o.z = fmaf(r2.w, a0.w, fmaf(r2.z, a0.z, fmaf(r2.y, a0.y, __fmul_rn(r2.x, a0.x))));
-        o.w = fmaf(r3.w, a0.w, fmaf(r3.z, a0.z, fmaf(r3.y, a0.y, __fmul_rn(r3.x, a0.x))));
-    } else {
-        o = a0;
-    }
-    p.pos[v] = o;
+    p.pos[v] = run_vs<VS>(p, __ldg(reinterpret_cast<const float4*>(base + p.attrOff[0])));
     for (int k = 0; k < p.nvary; k++)
         p.vary[(size_t)v * p.nvary + k] = __ldg(reinterpret_cast<const float4*>(base + p.attrOff[k + 1]));
 }
@@ -153,13 +159,22 @@ __device__ __forceinline__ void finish_triangle(const DrawParams& p, const ClipV
 }
 
 // clip one input triangle against the w plane; returns the number of fan triangles (0..2+)
+// VSMODE: IFRIT_VS_* = vertex shader fused here (positions computed per triangle corner straight from the
+// vertex buffer, no pos / vary round trip through HBM); -1 = positions precomputed by vs_kernel
+template <int VSMODE>
+__device__ __forceinline__ float4 fetch_pos(const DrawParams& p, int i) {
+    if (VSMODE < 0) return __ldg(p.pos + i);
+    return run_vs<VSMODE>(p, __ldg(reinterpret_cast<const float4*>(p.vb + (size_t)i * p.stride + p.attrOff[0])));
+}
+
+template <int VSMODE>
 __device__ int assemble(const DrawParams& p, int t, Assembled out[2]) {
     const bool cpu = p.convention == IFRIT_CONVENTION_CPU;
     const int i0 = __ldg(p.ib + 3 * (size_t)t), i1 = __ldg(p.ib + 3 * (size_t)t + 1), i2 = __ldg(p.ib + 3 * (size_t)t + 2);
     ClipV src[3];
-    src[0].p = __ldg(p.pos + i0); src[0].bx = 1.0f; src[0].by = 0.0f;
-    src[1].p = __ldg(p.pos + i1); src[1].bx = 0.0f; src[1].by = 1.0f;
-    src[2].p = __ldg(p.pos + i2); src[2].bx = 0.0f; src[2].by = 0.0f;
+    src[0].p = fetch_pos<VSMODE>(p, i0); src[0].bx = 1.0f; src[0].by = 0.0f;
+    src[1].p = fetch_pos<VSMODE>(p, i1); src[1].bx = 0.0f; src[1].by = 1.0f;
+    src[2].p = fetch_pos<VSMODE>(p, i2); src[2].bx = 0.0f; src[2].by = 0.0f;
     const float w0 = src[0].p.w, w1 = src[1].p.w, w2 = src[2].p.w;
     out[0].ok = false; out[1].ok = false;
     if (!cpu) {
@@ -322,11 +337,12 @@ __device__ __forceinline__ void store_record(const DrawParams& p, uint32_t slot,
 }
 
 // pass 1: one thread per input triangle — clip, snap, cull, store the 64-byte record, count tiles
+template <int VSMODE>
 __global__ void __launch_bounds__(256) setup_count_kernel(const __grid_constant__ DrawParams p) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     Assembled a[2];
     a[0].ok = a[1].ok = false;
-    if (t < p.ntri) assemble(p, t, a);
+    if (t < p.ntri) assemble<VSMODE>(p, t, a);
     unsigned long long nasm = 0;
 #pragma unroll
     for (int f = 0; f < 2; f++) {
@@ -520,9 +536,12 @@ __global__ void __launch_bounds__(1024) scan_kernel(const __grid_constant__ Draw
     }
 }
 
-cudaError_t ifr_launch_setup_count(const DrawParams& p, cudaStream_t s) {
+cudaError_t ifr_launch_setup_count(const DrawParams& p, int vsMode, cudaStream_t s) {
     if (p.ntri <= 0) return cudaSuccess;
-    setup_count_kernel<<<(p.ntri + 255) / 256, 256, 0, s>>>(p);
+    const int blocks = (p.ntri + 255) / 256;
+    if (vsMode == IFRIT_VS_MVP) setup_count_kernel<IFRIT_VS_MVP><<<blocks, 256, 0, s>>>(p);
+    else if (vsMode == IFRIT_VS_PASSTHROUGH) setup_count_kernel<IFRIT_VS_PASSTHROUGH><<<blocks, 256, 0, s>>>(p);
+    else setup_count_kernel<-1><<<blocks, 256, 0, s>>>(p);
     return cudaGetLastError();
 }
 cudaError_t ifr_launch_scan(const DrawParams& p, cudaStream_t s) {

@@ -186,8 +186,10 @@ __device__ __forceinline__ void interp(const DrawParams& p, uint32_t slot, int p
 #pragma unroll
     for (int k = 0; k < NV; k++) {
         if (k >= p.nvary) { out[k] = make_float4(0, 0, 0, 0); continue; }
-        const float4 v0 = __ldg(p.vary + (size_t)idx[0] * p.nvary + k), v1 = __ldg(p.vary + (size_t)idx[1] * p.nvary + k),
-                     v2 = __ldg(p.vary + (size_t)idx[2] * p.nvary + k);
+        const uint8_t* vb = p.varyBase + p.varyOff[k];
+        const float4 v0 = __ldg(reinterpret_cast<const float4*>(vb + (size_t)idx[0] * p.varyStride)),
+                     v1 = __ldg(reinterpret_cast<const float4*>(vb + (size_t)idx[1] * p.varyStride)),
+                     v2 = __ldg(reinterpret_cast<const float4*>(vb + (size_t)idx[2] * p.varyStride));
         out[k].x = fmaf(v2.x, w2, fmaf(v1.x, v, __fmul_rn(v0.x, u)));
         out[k].y = fmaf(v2.y, w2, fmaf(v1.y, v, __fmul_rn(v0.y, u)));
         out[k].z = fmaf(v2.z, w2, fmaf(v1.z, v, __fmul_rn(v0.z, u)));

@@ -128,7 +128,7 @@ def load_library():
         for name in ("iftrcuBindFragmentShader", "iftrcuBindGeometryShader", "iftrcuSetScissorTestEnable",
                      "iftrcuSetMsaaSamples", "iftrcuSetRasterizerPolygonMode", "iftrcuSetDepthFunc",
                      "iftrcuSetDepthTestEnable", "iftrcuSetCullMode", "iftrcuSetSampleConvention",
-                     "iftrcuSetDebugPrimitiveIds"):
+                     "iftrcuSetDebugPrimitiveIds", "iftrcuSetVertexStageFused"):
             getattr(L, name).argtypes = [C.c_void_p, C.c_int]
         L.iftrcuSetTilePartition.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.iftrcuSetProfiling.argtypes = [C.c_void_p, C.c_int]
@@ -323,6 +323,9 @@ class TileRasterRendererCuda:
 
     def setDebugPrimitiveIds(self, enable=True):
         self._ck(self._lib.iftrcuSetDebugPrimitiveIds(self._h, int(enable)))
+
+    def setVertexStageFused(self, enable=True):
+        self._ck(self._lib.iftrcuSetVertexStageFused(self._h, int(enable)))
 
     def synchronize(self):
         self._ck(self._lib.iftrcuSynchronize(self._h))

@@ -206,6 +206,9 @@ IFRIT_B200_API int iftrcuSetSampleConvention(iftrcuRenderer* h, int convention);
 /* sort-first partition: this instance renders only the 64-px super-tiles it owns */
 IFRIT_B200_API int iftrcuSetTilePartition(iftrcuRenderer* h, int rank, int worldSize);
 IFRIT_B200_API int iftrcuSetDebugPrimitiveIds(iftrcuRenderer* h, int enable);
+/* vertex stage fused into triangle setup (default, 1) or run as the stand-alone kernel that mirrors
+ * vertexProcessingKernel CU:330 (0); both produce identical frames */
+IFRIT_B200_API int iftrcuSetVertexStageFused(iftrcuRenderer* h, int enable);
 
 /* ---- draw ----------------------------------------------------------------------------- */
 IFRIT_B200_API int iftrcuClear(iftrcuRenderer* h);        /* RC::clear — fused into the next draw */

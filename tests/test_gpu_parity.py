@@ -55,6 +55,18 @@ def test_depth_funcs(r, func):
     compare(o, g, exact_color=True)
 
 
+def test_standalone_vertex_stage_matches_fused(r):
+    """vertexProcessingKernel CU:330 as its own kernel (pos / vary buffers) vs fused into triangle setup."""
+    W, H = 320, 200
+    vb, idx = scenes.mesh_sphere(n=40)
+    u = scenes.uniform_block(scenes.default_mvp(W, H))
+    o = oracle_draw(W, H, vb, idx, O.VS_MVP, O.FS_NORMAL_COLOR, 2, u, cull=2, msaa=4)
+    for fused in (False, True):
+        g = gpu_draw(r, W, H, vb, idx, O.VS_MVP, O.FS_NORMAL_COLOR, 2, u, cull=2, msaa=4, fused_vs=fused)
+        compare(o, g, exact_color=True)
+    r.setVertexStageFused(True)
+
+
 def test_depth_test_disabled_is_always(r):
     vb, idx = scenes.random_tris(100, 22, size=0.3)
     o = oracle_draw(96, 96, vb, idx, 0, O.FS_VARYING0, 1, IDENT, depth_func=O.CMP_ALWAYS)
