@@ -28,7 +28,7 @@ struct __align__(16) TriRec {
 #define IFR_FLAG_SWAPPED 2   // cull-mode winding swap (v1 <-> v3)
 #define IFR_FLAG_FITS32 4    // edge functions at every pixel corner that gets evaluated fit int32
 #define IFR_FLAG_SMALL 8     // pixel bbox area <= IFR_SMALL_AREA: thread-per-triangle path of the tile kernel
-#define IFR_FLAG_WIDE 16     // an edge delta exceeds 2^22 sub-pixels: int64 coverage path
+#define IFR_FLAG_WIDE 16     // an edge delta exceeds 2^20 sub-pixels (4096 px): int64 coverage path
 #define IFR_SMALL_AREA 16
 
 // Per (triangle, tile) raster setup, written by the fill pass into the tile's big-triangle queue and
@@ -39,7 +39,7 @@ struct __align__(16) TriS {
     int T[3]; uint32_t flags;    // int32 thresholds: inside <=> dX*j - dY*i >= T (i, j in 1/16 px, tile local)
     long long E0[3];             // edge functions at the tile origin (sub-pixel units)
     float ar, z0, z1, z2;
-    int pad[2];
+    int pad[2];                  // pad[0]: coarse-raster mask, bit per 8x4-pixel block of the tile
 };
 
 #define IFR_MAX_MIPS 16

@@ -131,7 +131,7 @@ __device__ __forceinline__ void finish_triangle(const DrawParams& p, const ClipV
             const int j = (i + 1) % 3;
             const long long adx = llabs((long long)a.X[j] - a.X[i]), ady = llabs((long long)a.Y[j] - a.Y[i]);
             span = max(span, adx + ady);
-            wide |= (adx > (1 << 22)) | (ady > (1 << 22));
+            wide |= (adx > (1 << 20)) | (ady > (1 << 20));
         }
         // |E_i| at any pixel corner within two pixels of a covered sample is below |d| + 1024 (|dX| + |dY|)
         if (llabs(d) + 1024 * span < 2147483647LL) a.flags |= IFR_FLAG_FITS32;
@@ -261,7 +261,7 @@ __device__ __forceinline__ void emit_one(const DrawParams& p, const RecRegs& rr,
     } else {
         TriS s;
         int bx0, bx1, by0, by1;
-        if (!setup_from_rec(p, rr, slot, tx, ty, s, bx0, bx1, by0, by1)) s.box = 0x00ff00ffu;   // empty: rows 255..0
+        if (!setup_from_rec<true>(p, rr, slot, tx, ty, s, bx0, bx1, by0, by1)) s.box = 0x00ff00ffu;   // empty: rows 255..0
         int4* dst = reinterpret_cast<int4*>(p.bigQueue + pos);
         const int4* src = reinterpret_cast<const int4*>(&s);
 #pragma unroll

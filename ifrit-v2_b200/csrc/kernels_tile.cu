@@ -15,44 +15,39 @@
 #include "sampler.cuh"
 
 // ---- visibility keys (identical to oracle/ifrit_oracle.c key_*) --------------------------------
+// LESS (mono(d), slot+1) / LESS_OR_EQUAL (mono(d), ~(slot+1)) / GREATER, GREATER_OR_EQUAL with ~mono /
+// ALWAYS and EQUAL (slot+1, depth bits); the minimum key wins.  The compare op is folded into two xor
+// masks so that the hot loops carry no switch.
+struct KeyMode { uint32_t xhi, xlo; bool ordered, equal, never; };
+__device__ __forceinline__ KeyMode key_mode(int func) {
+    KeyMode m;
+    m.ordered = func == IF_COMPARE_OP_LESS || func == IF_COMPARE_OP_LESS_OR_EQUAL || func == IF_COMPARE_OP_GREATER ||
+                func == IF_COMPARE_OP_GREATER_OR_EQUAL;
+    m.xhi = (func == IF_COMPARE_OP_GREATER || func == IF_COMPARE_OP_GREATER_OR_EQUAL) ? 0xffffffffu : 0u;
+    m.xlo = (func == IF_COMPARE_OP_LESS_OR_EQUAL || func == IF_COMPARE_OP_GREATER_OR_EQUAL) ? 0xffffffffu : 0u;
+    m.equal = func == IF_COMPARE_OP_EQUAL;
+    m.never = !m.ordered && !m.equal && func != IF_COMPARE_OP_ALWAYS;
+    return m;
+}
 __device__ __forceinline__ uint32_t mono(float d) {
     d = d + 0.0f;
     const uint32_t b = __float_as_uint(d);
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
-__device__ __forceinline__ float unmono(uint32_t m) {
-    return __uint_as_float((m & 0x80000000u) ? (m & 0x7fffffffu) : ~m);
+__device__ __forceinline__ unsigned long long key_init(const KeyMode& m, float d0) {
+    if (m.ordered) return ((unsigned long long)(mono(d0) ^ m.xhi) << 32) | m.xlo;
+    return ((unsigned long long)0xffffffffu << 32) | __float_as_uint(d0 + 0.0f);
 }
-__device__ __forceinline__ unsigned long long key_init(int func, float d0) {
-    switch (func) {
-        case IF_COMPARE_OP_LESS: return ((unsigned long long)mono(d0) << 32) | 0u;
-        case IF_COMPARE_OP_LESS_OR_EQUAL: return ((unsigned long long)mono(d0) << 32) | 0xffffffffu;
-        case IF_COMPARE_OP_GREATER: return ((unsigned long long)(~mono(d0)) << 32) | 0u;
-        case IF_COMPARE_OP_GREATER_OR_EQUAL: return ((unsigned long long)(~mono(d0)) << 32) | 0xffffffffu;
-        default: return ((unsigned long long)0xffffffffu << 32) | __float_as_uint(d0 + 0.0f);
-    }
+__device__ __forceinline__ bool key_make(const KeyMode& m, float d, float d0, uint32_t slot, unsigned long long& k) {
+    if (m.ordered) { k = ((unsigned long long)(mono(d) ^ m.xhi) << 32) | ((slot + 1u) ^ m.xlo); return true; }
+    if (m.never || (m.equal && !(d == d0))) return false;
+    k = ((unsigned long long)(slot + 1u) << 32) | __float_as_uint(d + 0.0f);
+    return true;
 }
-__device__ __forceinline__ bool key_make(int func, float d, float d0, uint32_t slot, unsigned long long& k) {
-    switch (func) {
-        case IF_COMPARE_OP_LESS: k = ((unsigned long long)mono(d) << 32) | (slot + 1u); return true;
-        case IF_COMPARE_OP_LESS_OR_EQUAL: k = ((unsigned long long)mono(d) << 32) | ~(slot + 1u); return true;
-        case IF_COMPARE_OP_GREATER: k = ((unsigned long long)(~mono(d)) << 32) | (slot + 1u); return true;
-        case IF_COMPARE_OP_GREATER_OR_EQUAL: k = ((unsigned long long)(~mono(d)) << 32) | ~(slot + 1u); return true;
-        case IF_COMPARE_OP_ALWAYS: k = ((unsigned long long)(slot + 1u) << 32) | __float_as_uint(d + 0.0f); return true;
-        case IF_COMPARE_OP_EQUAL:
-            if (!(d == d0)) return false;
-            k = ((unsigned long long)(slot + 1u) << 32) | __float_as_uint(d + 0.0f); return true;
-        default: return false;
-    }
-}
-__device__ __forceinline__ uint32_t key_slot(int func, unsigned long long k) {   // IFR_SLOT_NONE if empty
-    uint32_t s;
-    switch (func) {
-        case IF_COMPARE_OP_LESS: case IF_COMPARE_OP_GREATER: s = (uint32_t)k; return s == 0 ? IFR_SLOT_NONE : s - 1;
-        case IF_COMPARE_OP_LESS_OR_EQUAL: case IF_COMPARE_OP_GREATER_OR_EQUAL:
-            s = ~(uint32_t)k; return s == 0 ? IFR_SLOT_NONE : s - 1;
-        default: s = (uint32_t)(k >> 32); return s == 0xffffffffu ? IFR_SLOT_NONE : s - 1;
-    }
+__device__ __forceinline__ uint32_t key_slot(const KeyMode& m, unsigned long long k) {   // IFR_SLOT_NONE if empty
+    if (m.ordered) { const uint32_t s = (uint32_t)k ^ m.xlo; return s == 0 ? IFR_SLOT_NONE : s - 1; }
+    const uint32_t s = (uint32_t)(k >> 32);
+    return s == 0xffffffffu ? IFR_SLOT_NONE : s - 1;
 }
 
 __device__ __forceinline__ bool scissor_pass(const DrawParams& p, int x, int y) {
@@ -110,9 +105,9 @@ __device__ __forceinline__ float depth_at(const int dX[3], const int dY[3], cons
     return fmaf(z2, beta[2], fmaf(z1, beta[1], __fmul_rn(z0, beta[0])));
 }
 
-// tile-local pixel -> key index = index of the owning thread (quad order: 4 consecutive lanes = 2x2)
+// tile-local pixel -> key index = index of the owning thread (warp = 8x4 block, 4 consecutive lanes = 2x2 quad)
 __device__ __forceinline__ int pix_index(int lx, int ly) {
-    return ((ly >> 1) * 8 + (lx >> 1)) * 4 + (ly & 1) * 2 + (lx & 1);
+    return (((ly >> 2) * 2 + (lx >> 3)) << 5) + ((((ly >> 1) & 1) * 4 + ((lx >> 1) & 3)) << 2) + (ly & 1) * 2 + (lx & 1);
 }
 
 __device__ __forceinline__ void key_min_shared(unsigned long long* addr, unsigned long long k) {
@@ -231,8 +226,9 @@ __global__ void __launch_bounds__(256, 4) tile_kernel(const __grid_constant__ Dr
     const int ntiles = p.tilesX * p.tilesY;
     const int tile = tileY * p.tilesX + tileX;
     const int tid = threadIdx.x;
-    const int q = tid >> 2, l = tid & 3;
-    const int lx = (q & 7) * 2 + (l & 1), ly = (q >> 3) * 2 + (l >> 1);
+    // a warp owns one 8x4-pixel block of the tile (block = warp: x = (w & 1) * 8, y = (w >> 1) * 4), a quad = 4 lanes
+    const int wrp = tid >> 5, q = (tid >> 2) & 7, l = tid & 3;
+    const int lx = (wrp & 1) * 8 + (q & 3) * 2 + (l & 1), ly = (wrp >> 1) * 4 + (q >> 2) * 2 + (l >> 1);
     const int px = tileX * IFR_TILE + lx, py = tileY * IFR_TILE + ly;
     const bool inFrame = px < p.W && py < p.H;
     const bool scis = inFrame && scissor_pass(p, px, py);
@@ -255,10 +251,10 @@ __global__ void __launch_bounds__(256, 4) tile_kernel(const __grid_constant__ Dr
         return;
     }
 
-    const int func = p.depthFunc;
+    const KeyMode km = key_mode(p.depthFunc);
     float d0 = 0.0f;
     if (inFrame) d0 = (p.doClear && scis) ? p.clearDepth : p.depth[pidx];
-    const unsigned long long k0 = key_init(func, d0);
+    const unsigned long long k0 = key_init(km, d0);
     // Per-sample visibility keys.  S == 1: the pixel's key lives in a register (`best`); shared memory
     // is only the mailbox through which small triangles (processed by other threads) reach this pixel.
     if (S > 1 || nSmall) {
@@ -292,9 +288,9 @@ __global__ void __launch_bounds__(256, 4) tile_kernel(const __grid_constant__ Dr
                     const float d = depth_at(s.dX, s.dY, s.E0, s.flags, s.ar, s.z0, s.z1, s.z2, x, y);
                     unsigned long long k;
                     float dd0 = 0.0f;
-                    if (func == IF_COMPARE_OP_EQUAL)
+                    if (km.equal)
                         dd0 = p.doClear ? p.clearDepth : p.depth[(size_t)gy * p.W + gx];
-                    if (!key_make(func, d, dd0, slot, k)) continue;
+                    if (!key_make(km, d, dd0, slot, k)) continue;
                     const int pi = pix_index(x, y);
 #pragma unroll
                     for (int sm = 0; sm < S; sm++)
@@ -308,7 +304,6 @@ __global__ void __launch_bounds__(256, 4) tile_kernel(const __grid_constant__ Dr
     //      every thread tests its own pixel against broadcast LDS.128 words, warps run independently ------
     if (nBig) {
         const int ci = 16 * lx, cj = 16 * ly;
-        const int wy0 = (tid >> 5) * 2;       // a warp owns the 16x2 pixel strip [wy0, wy0+1]
         const uint32_t nchunks = (nBig + IFR_BIG_CHUNK - 1) / IFR_BIG_CHUNK;
         for (uint32_t c = 0; c < nchunks; c++) {
             if (tid == 0 && c + 1 < nchunks) {
@@ -320,9 +315,10 @@ __global__ void __launch_bounds__(256, 4) tile_kernel(const __grid_constant__ Dr
             const uint32_t cnt = min(nBig - c * IFR_BIG_CHUNK, (uint32_t)IFR_BIG_CHUNK);
             const int4* t4 = reinterpret_cast<const int4*>(bigBuf[c & 1]);
             for (uint32_t b = 0; b < cnt; b++, t4 += 6) {
+                // warp-uniform coarse reject: the fill pass rasterised the triangle against the tile's 8x4 blocks
+                const uint32_t blockMask = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(t4) + 88);
+                if (!((blockMask >> wrp) & 1)) continue;
                 const int4 A = t4[0];
-                const int y0 = (A.w >> 16) & 0xff, y1 = (int)((uint32_t)A.w >> 24);
-                if (wy0 + 1 < y0 || wy0 > y1) continue;            // warp-uniform: strip outside the bbox rows
                 const int4 B = t4[1], C = t4[2];
                 const int dX[3] = {A.x, A.y, A.z}, dY[3] = {B.x, B.y, B.z}, T[3] = {C.x, C.y, C.z};
                 const uint32_t flags = (uint32_t)C.w;
@@ -342,7 +338,7 @@ __global__ void __launch_bounds__(256, 4) tile_kernel(const __grid_constant__ Dr
                 const float2 Zr = *reinterpret_cast<const float2*>(t4 + 5);
                 const float d = depth_at(dX, dY, E0, flags, __int_as_float(E.z), __int_as_float(E.w), Zr.x, Zr.y, lx, ly);
                 unsigned long long k;
-                if (!key_make(func, d, d0, (uint32_t)B.w, k)) continue;
+                if (!key_make(km, d, d0, (uint32_t)B.w, k)) continue;
                 if (S == 1) {
                     if (k < best) best = k;
                 } else {
@@ -361,7 +357,7 @@ __global__ void __launch_bounds__(256, 4) tile_kernel(const __grid_constant__ Dr
     for (int s = 0; s < S; s++) {
         unsigned long long k = best;
         if (S > 1 || nSmall) { const unsigned long long ks = keys[s * IFR_TILE_PIX + tid]; if (S > 1 || ks < k) k = ks; }
-        mySlots[s] = key_slot(func, k);
+        mySlots[s] = key_slot(km, k);
     }
 
     float4 acc = make_float4(0, 0, 0, 0);

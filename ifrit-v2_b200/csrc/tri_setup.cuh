@@ -19,6 +19,7 @@ __device__ __forceinline__ void load_rec(const DrawParams& p, uint32_t slot, Rec
     rr.flags = (uint32_t)w3.y;
 }
 
+template <bool COARSE>
 __device__ __forceinline__ bool setup_from_rec(const DrawParams& p, const RecRegs& rr, uint32_t slot, int tileX, int tileY,
                                                TriS& s, int& bx0, int& bx1, int& by0, int& by1) {
     const int* X = rr.X; const int* Y = rr.Y;
@@ -34,8 +35,10 @@ __device__ __forceinline__ bool setup_from_rec(const DrawParams& p, const RecReg
         const int a = (i + 1) % 3, b = (i + 2) % 3;
         s.dX[i] = X[b] - X[a]; s.dY[i] = Y[b] - Y[a];
         s.E0[i] = (long long)s.dX[i] * (long long)(sy0 - Y[a]) - (long long)s.dY[i] * (long long)(sx0 - X[a]);
+        // inside <=> dX*j - dY*i >= T.  Non-wide edges (|dX|,|dY| <= 2^20) keep |dX*j - dY*i| < 2^29 over the
+        // tile, so clamping T to +-2^30 changes no outcome and lets the tile kernel form (dX*j - dY*i - T) in int32
         long long T = ((-s.E0[i]) >> 4) + 1;
-        T = T > 2147483647LL ? 2147483647LL : (T < -2147483648LL ? -2147483648LL : T);
+        T = T > (1LL << 30) ? (1LL << 30) : (T < -(1LL << 30) ? -(1LL << 30) : T);
         s.T[i] = (int)T;
     }
     const int minx = min(X[0], min(X[1], X[2])), maxx = max(X[0], max(X[1], X[2]));
@@ -46,12 +49,36 @@ __device__ __forceinline__ bool setup_from_rec(const DrawParams& p, const RecReg
     bx0 = max(px0 - ox, 0); by0 = max(py0 - oy, 0);
     bx1 = min(min(px1, p.W - 1) - ox, IFR_TILE - 1); by1 = min(min(py1, p.H - 1) - oy, IFR_TILE - 1);
     s.box = (uint32_t)(bx0 & 0xff) | ((uint32_t)(bx1 & 0xff) << 8) | ((uint32_t)(by0 & 0xff) << 16) | ((uint32_t)(by1 & 0xff) << 24);
-    return bx0 <= bx1 && by0 <= by1;
+    const bool ok = bx0 <= bx1 && by0 <= by1;
+    // Coarse raster (secondBinnerWorklistRasterizerKernel CU:1254 keeps 4x4-px sub-tiles): which of the tile's eight
+    // 8x4-pixel blocks (one per warp of the tile kernel; bit = (y >> 2) * 2 + (x >> 3)) can hold a covered sample.
+    // Exact trivial reject: an edge whose function is below threshold at the block's most-inside sample corner.
+    uint32_t mask = 0;
+    if (COARSE && ok) {
+        const int sLoX = p.sampMinX >> 4, sHiX = p.sampMaxX >> 4, sLoY = p.sampMinY >> 4, sHiY = p.sampMaxY >> 4;   // 1/16 px
+#pragma unroll
+        for (int blk = 0; blk < 8; blk++) {
+            const int x0 = (blk & 1) * 8, y0 = (blk >> 1) * 4;
+            if (x0 + 7 < bx0 || x0 > bx1 || y0 + 3 < by0 || y0 > by1) continue;
+            bool may = true;
+            if (!(rr.flags & IFR_FLAG_WIDE)) {
+                const int iLo = 16 * x0 + sLoX, iHi = 16 * (x0 + 7) + sHiX, jLo = 16 * y0 + sLoY, jHi = 16 * (y0 + 3) + sHiY;
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    const int best = s.dX[i] * (s.dX[i] > 0 ? jHi : jLo) - s.dY[i] * (s.dY[i] > 0 ? iLo : iHi);
+                    may = may && best >= s.T[i];
+                }
+            }
+            mask |= (uint32_t)may << blk;
+        }
+    }
+    s.pad[0] = (int)mask;
+    return ok;
 }
 
 __device__ __forceinline__ bool setup_tri(const DrawParams& p, uint32_t slot, int tileX, int tileY, TriS& s,
                                           int& bx0, int& bx1, int& by0, int& by1) {
     RecRegs rr;
     load_rec(p, slot, rr);
-    return setup_from_rec(p, rr, slot, tileX, tileY, s, bx0, bx1, by0, by1);
+    return setup_from_rec<false>(p, rr, slot, tileX, tileY, s, bx0, bx1, by0, by1);
 }
