@@ -173,9 +173,14 @@ def run_ours(args, cfg_name):
     stream = torch.cuda.Stream(device=dev)   # one explicit stream for kernels, NCCL ordering and the timing events
     torch.cuda.set_stream(stream)
     r.setStream(stream.cuda_stream)
-    color = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
-    depth = torch.zeros((H, W), dtype=torch.float32, device=dev)
-    r.bindFrameBufferDevice(color, depth, W, H)
+    mg_mode = args.mgpu if world > 1 else None
+    color = depth = None
+    if mg_mode == "peer":
+        r.width, r.height = W, H            # framebuffer: rank 0 owns it, the others bind it over NVLink (CUDA IPC)
+    else:
+        color = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
+        depth = torch.zeros((H, W), dtype=torch.float32, device=dev)
+        r.bindFrameBufferDevice(color, depth, W, H)
     r.bindVertexBuffer(tvb, tvb.shape[0], tvb.shape[1] // 4, device=True)
     r.bindIndexBuffer(tib, tib.shape[0], device=True)
     r.bindVertexShader(sc["vs"], sc["nvary"])
@@ -193,7 +198,7 @@ def run_ours(args, cfg_name):
     r.SetDepthFunc(R.IF_COMPARE_OP_LESS)
     r.SetDepthTestEnable(True)
     r.setClearValues([(0, 0, 0, 0)], 255.0)   # reference demo clear depth, SG/demo/DefaultDemo.cpp:355
-    sf = MG.SortFirstRenderer(r, dist, dev) if world > 1 else None
+    sf = MG.SortFirstRenderer(r, dist, dev, mode=mg_mode) if world > 1 else None
 
     def step():
         r.clear()
@@ -254,8 +259,10 @@ def run_ours(args, cfg_name):
         if sf:
             sf.gather()
         if rank == 0:
-            hcol.copy_(color, non_blocking=True)                       # D2H of the step's result
+            r.copyColorToHostAsync(hcol.data_ptr())                    # D2H of the step's result (pinned, async)
         torch.cuda.current_stream().synchronize()
+        if mg_mode == "peer":
+            dist.barrier()   # the next frame's peer stores must not overtake rank 0's read-back
 
     for _ in range(2):
         e2e_step()
@@ -296,7 +303,7 @@ def run_ours(args, cfg_name):
             "config": {"workload": cfg["workload"], "name": cfg_name, "triangles": ntri, "resolution": [W, H],
                        "msaa": cfg["msaa"], "l2": "no explicit flush: per-step working set (framebuffer "
                        f"{W * H * 20 / 1e6:.0f} MB + texture) exceeds the 126 MB L2",
-                       "parallelism": f"sort-first x{world}" if world > 1 else "1 GPU"},
+                       "parallelism": f"sort-first x{world} ({mg_mode})" if world > 1 else "1 GPU"},
             "fps": 1e3 / ms_step, "gfrags_per_s": frags / (ms_step * 1e-3) / 1e9,
             "fragments_per_frame": frags,
             "gpu_launches": int(launches),
@@ -360,6 +367,8 @@ def main():
     ap.add_argument("--config", default=None, choices=sorted(CONFIGS))
     ap.add_argument("--extra-configs", default="c3", help="comma list of further configs measured at N=1 (short runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mgpu", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: peer = tiles stored straight into rank 0's framebuffer over NVLink; nccl = pack + gather + unpack")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     cfg_name = args.config or "c2"

@@ -55,6 +55,7 @@ struct iftrcuRenderer {
     bool externalFB = false;
     float* hColor = nullptr; float* hDepth = nullptr;
     void* registeredHost = nullptr;
+    void* peerColor = nullptr; void* peerDepth = nullptr;   // opened CUDA IPC mappings (peer framebuffer)
     bool debugIds = false;
 
     // geometry
@@ -96,6 +97,11 @@ struct iftrcuRenderer {
 };
 
 #define R_CHECK(h) if (!(h)) return IFRIT_ERR_INVALID; iftrcuRenderer* r = (h); cudaSetDevice(r->device)
+
+static void close_peer(iftrcuRenderer* r) {
+    if (r->peerColor) { cudaIpcCloseMemHandle(r->peerColor); r->peerColor = nullptr; }
+    if (r->peerDepth) { cudaIpcCloseMemHandle(r->peerDepth); r->peerDepth = nullptr; }
+}
 
 static void build_params(iftrcuRenderer* r, DrawParams& p) {
     memset(&p, 0, sizeof p);
@@ -282,6 +288,7 @@ int iftrcuDestroyInstance(iftrcuRenderer* h) {
     R_CHECK(h);
     cudaStreamSynchronize(r->stream);
     if (r->registeredHost) cudaHostUnregister(r->registeredHost);
+    close_peer(r);
     DevBuf* bufs[] = {&r->ownColor, &r->ownDepth, &r->primIds, &r->ownVB, &r->ownIB, &r->pos, &r->vary, &r->rec, &r->clipBary,
                       &r->scanPartial, &r->tileBox, &r->fan1List, &r->heavyBits, &r->tileCount, &r->tileStart, &r->tileCursor, &r->queue, &r->bigQueue, &r->counters};
     for (DevBuf* b : bufs) b->release();
@@ -309,6 +316,7 @@ int iftrcuBindFrameBuffer(iftrcuRenderer* h, float* hostColor, float* hostDepth,
     R_CHECK(h);
     if (width <= 0 || height <= 0 || width > 65535 * 16 || height > 65535 * 16) return r->fail(IFRIT_ERR_INVALID, "bindFrameBuffer", "bad size");
     CUDA_TRY(cudaStreamSynchronize(r->stream));
+    close_peer(r);
     CUDA_TRY(r->ownColor.ensure((size_t)width * height * 16));
     CUDA_TRY(r->ownDepth.ensure((size_t)width * height * 4));
     r->dColor = (float4*)r->ownColor.p; r->dDepth = (float*)r->ownDepth.p;
@@ -327,10 +335,40 @@ int iftrcuBindFrameBuffer(iftrcuRenderer* h, float* hostColor, float* hostDepth,
     return IFRIT_OK;
 }
 
+int iftrcuExportFrameBuffer(iftrcuRenderer* h, void* handleOut128) {
+    R_CHECK(h);
+    if (!handleOut128) return IFRIT_ERR_INVALID;
+    if (!r->dColor || r->externalFB || (void*)r->dColor != r->ownColor.p)
+        return r->fail(IFRIT_ERR_STATE, "exportFrameBuffer", "bind a renderer-owned framebuffer first (bindFrameBuffer)");
+    cudaIpcMemHandle_t hc, hd;
+    CUDA_TRY(cudaIpcGetMemHandle(&hc, r->ownColor.p));
+    CUDA_TRY(cudaIpcGetMemHandle(&hd, r->ownDepth.p));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    memcpy(handleOut128, &hc, 64); memcpy((char*)handleOut128 + 64, &hd, 64);
+    return IFRIT_OK;
+}
+
+int iftrcuBindPeerFrameBuffer(iftrcuRenderer* h, const void* handle128, int width, int height) {
+    R_CHECK(h);
+    if (!handle128 || width <= 0 || height <= 0) return r->fail(IFRIT_ERR_INVALID, "bindPeerFrameBuffer", "bad argument");
+    CUDA_TRY(cudaStreamSynchronize(r->stream));
+    close_peer(r);
+    cudaIpcMemHandle_t hc, hd;
+    memcpy(&hc, handle128, 64); memcpy(&hd, (const char*)handle128 + 64, 64);
+    CUDA_TRY(cudaIpcOpenMemHandle(&r->peerColor, hc, cudaIpcMemLazyEnablePeerAccess));
+    CUDA_TRY(cudaIpcOpenMemHandle(&r->peerDepth, hd, cudaIpcMemLazyEnablePeerAccess));
+    if (r->registeredHost) { cudaHostUnregister(r->registeredHost); r->registeredHost = nullptr; }
+    r->dColor = (float4*)r->peerColor; r->dDepth = (float*)r->peerDepth; r->externalFB = true; r->hColor = nullptr; r->hDepth = nullptr;
+    if (r->W != width || r->H != height) r->queueChecked = false;
+    r->W = width; r->H = height;
+    return IFRIT_OK;
+}
+
 int iftrcuBindFrameBufferDevice(iftrcuRenderer* h, float* devColor, float* devDepth, int width, int height) {
     R_CHECK(h);
     if (!devColor || !devDepth || width <= 0 || height <= 0) return r->fail(IFRIT_ERR_INVALID, "bindFrameBufferDevice", "bad argument");
     CUDA_TRY(cudaStreamSynchronize(r->stream));
+    close_peer(r);
     if (r->registeredHost) { cudaHostUnregister(r->registeredHost); r->registeredHost = nullptr; }
     r->dColor = (float4*)devColor; r->dDepth = devDepth; r->externalFB = true; r->hColor = nullptr; r->hDepth = nullptr;
     if (r->W != width || r->H != height) r->queueChecked = false;
@@ -632,6 +670,12 @@ int iftrcuReadPrimitiveIds(iftrcuRenderer* h, int32_t* dst) {
     if (!dst || !r->debugIds || !r->primIds.p) return r->fail(IFRIT_ERR_STATE, "ReadPrimitiveIds", "enable with SetDebugPrimitiveIds before drawing");
     int rc = sync_and_check(r); if (rc) return rc;
     CUDA_TRY(cudaMemcpy(dst, r->primIds.p, (size_t)r->W * r->H * r->msaa * 4, cudaMemcpyDeviceToHost));
+    return IFRIT_OK;
+}
+int iftrcuCopyColorToHostAsync(iftrcuRenderer* h, void* hostDst) {
+    R_CHECK(h);
+    if (!hostDst || !r->dColor) return IFRIT_ERR_INVALID;
+    CUDA_TRY(cudaMemcpyAsync(hostDst, r->dColor, (size_t)r->W * r->H * 16, cudaMemcpyDeviceToHost, r->stream));
     return IFRIT_OK;
 }
 int iftrcuGetDeviceColorPtr(iftrcuRenderer* h, void** out) { R_CHECK(h); if (!out) return IFRIT_ERR_INVALID; *out = r->dColor; return IFRIT_OK; }

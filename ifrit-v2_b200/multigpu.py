@@ -79,15 +79,36 @@ def gather_frame(packed_local, width, height, dist, dst=0):
     return outs
 
 
-class SortFirstRenderer:
-    """Wraps one TileRasterRendererCuda per rank: partition state + pack / NCCL gather / unpack."""
+def share_framebuffer(renderer, width, height, dist, device):
+    """Peer-memory sort-first: rank 0 binds a renderer-owned device framebuffer and exports it (CUDA IPC);
+    every other rank binds rank 0's memory as its render target, so its tile kernel writes the tiles it owns
+    straight into the final frame over NVLink.  Call on every rank before the first draw."""
+    import torch
+    rank = dist.get_rank()
+    blob = torch.zeros(128, dtype=torch.uint8, device=device)
+    if rank == 0:
+        renderer.bindFrameBuffer(None, None, width, height)
+        blob = torch.frombuffer(bytearray(renderer.exportFrameBuffer()), dtype=torch.uint8).to(device)
+    dist.broadcast(blob, 0)
+    if rank != 0:
+        renderer.bindPeerFrameBuffer(bytes(blob.cpu().numpy().tobytes()), width, height)
 
-    def __init__(self, renderer, dist, device, same_stream=True):
+
+class SortFirstRenderer:
+    """Wraps one TileRasterRendererCuda per rank.  mode "peer" (default on NVLink): every rank renders its
+    tiles straight into rank 0's framebuffer (share_framebuffer) and gather() is a one-element all-reduce
+    that orders frame completion on the stream.  mode "nccl": pack -> NCCL gather -> unpack."""
+
+    def __init__(self, renderer, dist, device, same_stream=True, mode="nccl"):
         """same_stream: the renderer was given torch's current stream (setStream), so pack -> NCCL ->
         unpack are ordered on the device and need no host synchronisation."""
         import torch
         self.r, self.dist, self.device, self.same_stream = renderer, dist, device, same_stream
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.mode = mode
+        if mode == "peer" and self.world > 1:
+            share_framebuffer(renderer, renderer.width, renderer.height, dist, device)
+            self.token = torch.zeros(1, dtype=torch.float32, device=device)
         renderer.setTilePartition(self.rank, self.world)
         self.torch = torch
         self.packed = None
@@ -96,6 +117,11 @@ class SortFirstRenderer:
         """After drawElements(): rank 0's device framebuffer becomes the complete frame."""
         torch, r = self.torch, self.r
         if self.world == 1:
+            return
+        if self.mode == "peer":
+            if not self.same_stream:
+                r.synchronize()
+            self.dist.all_reduce(self.token)   # every rank's tile kernel precedes it in stream order
             return
         n = max_owned_floats(r.width, r.height, self.world)
         if self.packed is None or self.packed.numel() != n:

@@ -131,6 +131,9 @@ def load_library():
                      "iftrcuSetDebugPrimitiveIds", "iftrcuSetVertexStageFused"):
             getattr(L, name).argtypes = [C.c_void_p, C.c_int]
         L.iftrcuSetTilePartition.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.iftrcuExportFrameBuffer.argtypes = [C.c_void_p, C.c_void_p]
+        L.iftrcuCopyColorToHostAsync.argtypes = [C.c_void_p, C.c_void_p]
+        L.iftrcuBindPeerFrameBuffer.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.iftrcuSetProfiling.argtypes = [C.c_void_p, C.c_int]
         L.iftrcuGetKernelTimes.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
         L.iftrcuGenerateMipmap.argtypes = [C.c_void_p, C.c_int, C.c_int]
@@ -204,6 +207,22 @@ class TileRasterRendererCuda:
         self._keep["fb"] = (color, depth)
         self.width, self.height = width, height
         self._ck(self._lib.iftrcuBindFrameBufferDevice(self._h, _ptr(color), _ptr(depth), width, height))
+
+    def copyColorToHostAsync(self, host_ptr):
+        self._ck(self._lib.iftrcuCopyColorToHostAsync(self._h, C.c_void_p(host_ptr)))
+
+    def exportFrameBuffer(self):
+        """128-byte CUDA IPC blob of the renderer-owned device framebuffer (colour + depth)."""
+        buf = (C.c_ubyte * 128)()
+        self._ck(self._lib.iftrcuExportFrameBuffer(self._h, buf))
+        return bytes(buf)
+
+    def bindPeerFrameBuffer(self, handle, width, height):
+        """Render straight into another process's / GPU's framebuffer over NVLink (peer memory)."""
+        self._keep["fb"] = None
+        self.width, self.height = width, height
+        buf = (C.c_ubyte * 128).from_buffer_copy(handle)
+        self._ck(self._lib.iftrcuBindPeerFrameBuffer(self._h, buf, width, height))
 
     def bindVertexBuffer(self, data, vertexCount=None, numAttributes=None, device=False):
         """data: float32 [V, 4*nattr] interleaved FLOAT4 attributes (VertexBuffer.h:28-90)."""

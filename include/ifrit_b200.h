@@ -232,6 +232,17 @@ IFRIT_B200_API int iftrcuGetKernelTimes(iftrcuRenderer* h, float* msOut5, int* n
 /* assembled triangles of the last draw, sorted by slot; returns count via *n (cap = capacity of dst) */
 IFRIT_B200_API int iftrcuReadAssembled(iftrcuRenderer* h, iftrcuAssembledTriangle* dst, int cap, int* n);
 /* pack / unpack the super-tiles owned by `rank` (sort-first gather plumbing, device pointers) */
+/* Peer-memory sort-first (NVLink / NVSwitch, one process per GPU): the rank that owns the final frame exports
+ * its device framebuffer (colour + depth, 2 x 64-byte CUDA IPC handles); every other rank binds it as its
+ * render target, so that its tile kernel stores the tiles it owns straight into the owner's memory over
+ * NVLink — no pack, no collective on the data path, no unpack.  The caller orders frame completion with a
+ * barrier on the stream (e.g. a one-element NCCL all-reduce). */
+#define IFRIT_IPC_HANDLE_BYTES 128
+/* asynchronous colour read-back on the renderer's stream (the reference's double-buffered copy, CU:3899-3909);
+ * hostDst should be pinned; ordered after every draw issued so far */
+IFRIT_B200_API int iftrcuCopyColorToHostAsync(iftrcuRenderer* h, void* hostDst);
+IFRIT_B200_API int iftrcuExportFrameBuffer(iftrcuRenderer* h, void* handleOut128);
+IFRIT_B200_API int iftrcuBindPeerFrameBuffer(iftrcuRenderer* h, const void* handle128, int width, int height);
 IFRIT_B200_API int iftrcuPackOwnedTiles(iftrcuRenderer* h, void* devDst, size_t dstBytes, size_t* usedBytes);
 IFRIT_B200_API int iftrcuUnpackOwnedTiles(iftrcuRenderer* h, const void* devSrc, int rank, int worldSize);
 IFRIT_B200_API size_t iftrcuOwnedTileBytes(int width, int height, int rank, int worldSize);

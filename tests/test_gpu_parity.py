@@ -1,6 +1,7 @@
 """GPU parity tests proper (-m gpu): the CUDA path, called through the C-ABI, against the oracle on the
 same seeded inputs.  Bar: coverage, primitive id and depth bit-exact; colour within 1/255 on >= 99.9 % of
 pixels (BASELINE.json north_star); where no libm call is involved colour is checked bit-exact too."""
+import os
 import numpy as np
 import pytest
 import ifrit_v2_b200  # noqa: F401
@@ -307,3 +308,21 @@ def test_full_size_properties_4k(r):
     d = gpu_draw(r, W, H, vb, idx, 1, O.FS_NORMAL_COLOR, 2, u, cull=2, clear=False, color=a["color"], depth=a["depth"])
     assert np.array_equal(d["color"].view(np.uint32), a["color"].view(np.uint32))
     assert (d["prim_id"] == -1).all()
+
+
+@pytest.mark.gpu
+def test_multi_gpu_frame_is_bit_identical():
+    """>= 2 GPUs only: peer-memory (NVLink stores into rank 0's framebuffer) and NCCL-gather sort-first frames
+    equal the single-GPU frame bit for bit (tests/mgpu_check.py under torchrun)."""
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    n = 2 if n < 4 else 4
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(here, "mgpu_check.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert "MGPU_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
