@@ -62,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -96,7 +96,7 @@ class ClockSampler:
                     reasons.add(n)
         mhz.sort()
         return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(mhz)}
+                "samples": len(mhz), "window": "untimed pre-roll of the same steps + the timed region, 20 ms period"}
 
 
 def build_scene(cfg, small=False):
@@ -214,11 +214,27 @@ def run_ours(args, cfg_name):
     for _ in range(max(args.warmup, 3)):
         step()
     r.synchronize()
-    st0 = r.stats()
-    r.setProfiling(True)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    # untimed pre-roll (same steps, about 0.3 s, same count on every rank): clocks settle under load and
+    # nvidia-smi gets samples even when the K timed steps last only a few milliseconds; the sampler keeps
+    # running through the timed region
+    t_pre = time.perf_counter()
+    for _ in range(5):
+        step()
+    r.synchronize()
+    est = torch.tensor([(time.perf_counter() - t_pre) / 5], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(est, op=dist.ReduceOp.MAX)
+    pre = int(min(max(0.3 / max(float(est.item()), 1e-6), 5), 3000))
+    for i in range(pre):
+        step()
+        if i % 50 == 49:
+            r.synchronize()
+    r.synchronize()
+    st0 = r.stats()
+    r.setProfiling(True)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -361,8 +377,8 @@ def run_reference(args, cfg_name, steps, warmup):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default=None, choices=sorted(CONFIGS))
     ap.add_argument("--extra-configs", default="c3", help="comma list of further configs measured at N=1 (short runs)")
