@@ -62,7 +62,8 @@ struct iftrcuRenderer {
     const uint8_t* dVB = nullptr; DevBuf ownVB; int nverts = 0, stride = 0, nattr = 0; int attrOff[IFR_MAX_VARY + 1] = {0};
     const int32_t* dIB = nullptr; DevBuf ownIB; int icount = 0;
     int vsId = -1, fsId = -1, nvary = 0;
-    bool fusedVS = true;   // vertex stage fused into triangle setup (default) or stand-alone vs_kernel
+    bool fusedVS = true;
+    bool hwFilter = true;  // bilinear footprints through the TEX unit (iftrcuSetSamplerHardwareFilter)   // vertex stage fused into triangle setup (default) or stand-alone vs_kernel
 
     // state (defaults: TileRasterRendererCuda.h:42-47, CU:186-189)
     int msaa = 1, depthFunc = IF_COMPARE_OP_LESS, depthTest = 1, cullMode = IF_CULL_MODE_NONE;
@@ -103,6 +104,40 @@ static void close_peer(iftrcuRenderer* r) {
     if (r->peerDepth) { cudaIpcCloseMemHandle(r->peerDepth); r->peerDepth = nullptr; }
 }
 
+static void destroy_tex_objects(iftrcuRenderer* r, int slot) {
+    for (int l = 0; l < IFR_MAX_MIPS; l++)
+        if (r->tex[slot].hw[l]) { cudaDestroyTextureObject((cudaTextureObject_t)r->tex[slot].hw[l]); r->tex[slot].hw[l] = 0; }
+}
+
+// texture objects over layer 0 of every level that the hardware can bind as pitch-linear 2-D memory
+static void create_tex_objects(iftrcuRenderer* r, int slot) {
+    int align = 512, pitchAlign = 32;
+    cudaDeviceGetAttribute(&align, cudaDevAttrTextureAlignment, r->device);
+    cudaDeviceGetAttribute(&pitchAlign, cudaDevAttrTexturePitchAlignment, r->device);
+    TexDesc& t = r->tex[slot];
+    for (int l = 0; l <= t.mips; l++) {
+        const TexLevel& L = t.lvl[l];
+        const char* base = (const char*)t.data + (size_t)L.off * 16;
+        const size_t pitch = (size_t)L.w * 16;
+        if (L.w < 2 || L.h < 2 || ((uintptr_t)base % (size_t)align) || (pitch % (size_t)pitchAlign)) continue;
+        cudaResourceDesc rd;
+        memset(&rd, 0, sizeof rd);
+        rd.resType = cudaResourceTypePitch2D;
+        rd.res.pitch2D.devPtr = (void*)base;
+        rd.res.pitch2D.desc = cudaCreateChannelDesc<float4>();
+        rd.res.pitch2D.width = L.w; rd.res.pitch2D.height = L.h; rd.res.pitch2D.pitchInBytes = pitch;
+        cudaTextureDesc td;
+        memset(&td, 0, sizeof td);
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModeLinear;
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 0;
+        cudaTextureObject_t obj = 0;
+        if (cudaCreateTextureObject(&obj, &rd, &td, nullptr) == cudaSuccess) t.hw[l] = (unsigned long long)obj;
+        else cudaGetLastError();
+    }
+}
+
 static void build_params(iftrcuRenderer* r, DrawParams& p) {
     memset(&p, 0, sizeof p);
     p.color = r->dColor; p.depth = r->dDepth; p.primIds = r->debugIds ? (int32_t*)r->primIds.p : nullptr;
@@ -116,6 +151,7 @@ static void build_params(iftrcuRenderer* r, DrawParams& p) {
     p.scissorEnable = r->scissorEnable; p.nScissor = r->nScissor;
     memcpy(p.scissor, r->scissor, sizeof p.scissor);
     p.rank = r->rank; p.world = r->world;
+    p.hwFilter = r->hwFilter ? 1 : 0;
     int mnx = 255, mxx = 0, mny = 255, mxy = 0;
     const int ns = r->convention == IFRIT_CONVENTION_CPU ? 1 : r->msaa;
     for (int k = 0; k < r->msaa; k++) {
@@ -292,7 +328,7 @@ int iftrcuDestroyInstance(iftrcuRenderer* h) {
     DevBuf* bufs[] = {&r->ownColor, &r->ownDepth, &r->primIds, &r->ownVB, &r->ownIB, &r->pos, &r->vary, &r->rec, &r->clipBary,
                       &r->scanPartial, &r->tileBox, &r->fan1List, &r->heavyBits, &r->tileCount, &r->tileStart, &r->tileCursor, &r->queue, &r->bigQueue, &r->counters};
     for (DevBuf* b : bufs) b->release();
-    for (int i = 0; i < IFR_MAX_TEX; i++) r->texMem[i].release();
+    for (int i = 0; i < IFR_MAX_TEX; i++) { destroy_tex_objects(r, i); r->texMem[i].release(); }
     for (int i = 0; i < IFR_MAX_BUF; i++) r->bufMem[i].release();
     for (auto& e : r->profEvents) cudaEventDestroy(e);
     if (r->hCounters) cudaFreeHost(r->hCounters);
@@ -458,6 +494,7 @@ int iftrcuCreateTexture(iftrcuRenderer* h, int slot, const IfritImageCreateInfo*
     if (ci->mipLevels >= IFR_MAX_MIPS) return r->fail(IFRIT_ERR_INVALID, "CreateTexture", "at most 15 mip levels beyond level 0");
     if (chain_texels(ci->extent.width, ci->extent.height, ci->mipLevels, ci->arrayLayers) > 0x7fffffffull) return r->fail(IFRIT_ERR_INVALID, "CreateTexture", "texture chain too large");
     CUDA_TRY(cudaStreamSynchronize(r->stream));
+    destroy_tex_objects(r, slot);
     const size_t n = chain_texels(ci->extent.width, ci->extent.height, ci->mipLevels, ci->arrayLayers);
     CUDA_TRY(r->texMem[slot].ensure(n * 16));
     CUDA_TRY(cudaMemsetAsync(r->texMem[slot].p, 0, n * 16, r->stream));
@@ -477,6 +514,7 @@ int iftrcuCreateTexture(iftrcuRenderer* h, int slot, const IfritImageCreateInfo*
         }
     }
     r->texTexels[slot] = n;
+    create_tex_objects(r, slot);
     return IFRIT_OK;
 }
 
@@ -620,6 +658,7 @@ int iftrcuSetTilePartition(iftrcuRenderer* h, int rank, int worldSize) {
 }
 int iftrcuSetDebugPrimitiveIds(iftrcuRenderer* h, int enable) { R_CHECK(h); r->debugIds = enable != 0; return IFRIT_OK; }
 int iftrcuSetVertexStageFused(iftrcuRenderer* h, int enable) { R_CHECK(h); r->fusedVS = enable != 0; return IFRIT_OK; }
+int iftrcuSetSamplerHardwareFilter(iftrcuRenderer* h, int enable) { R_CHECK(h); r->hwFilter = enable != 0; return IFRIT_OK; }
 
 int iftrcuClear(iftrcuRenderer* h) {
     R_CHECK(h);

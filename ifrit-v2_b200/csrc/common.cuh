@@ -45,7 +45,9 @@ struct __align__(16) TriS {
 #define IFR_MAX_MIPS 16
 // one mip level: dimensions, texel offset of layer 0, texels per layer, reciprocals for address wrapping
 struct TexLevel { int w, h; uint32_t off, layerStride; float invW, invH, inv2W, inv2H; };
-struct TexDesc { const float4* data; int w, h, mips, layers; TexLevel lvl[IFR_MAX_MIPS]; };
+// hw[l]: CUDA texture object over layer 0 of level l (pitch-linear view of the same memory, clamp addressing,
+// unnormalised coordinates, bilinear filter) or 0 when the level cannot be bound (alignment, 1-texel levels)
+struct TexDesc { const float4* data; int w, h, mips, layers; TexLevel lvl[IFR_MAX_MIPS]; unsigned long long hw[IFR_MAX_MIPS]; };
 struct SampDesc { int filter, addrU, addrV, addrW, border, aniso; float maxAniso; };
 
 struct DrawParams {
@@ -56,6 +58,7 @@ struct DrawParams {
     int doClear; float clearColor[4]; float clearDepth;
     int scissorEnable, nScissor; float scissor[IFR_MAX_SCISSOR][4];
     int rank, world;
+    int hwFilter;   // bilinear footprints through the TEX unit (8-bit weights) instead of four loads + fp32 lerps
     // coverage sample pattern of this draw, in 1/16 pixel (from cMsaaSampleSequenceAgg, CU:223-234)
     int8_t sampX[16], sampY[16];
     int sampMinX, sampMaxX, sampMinY, sampMaxY;   // extents in sub-pixel (1/256) units

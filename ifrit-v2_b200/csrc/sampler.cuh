@@ -53,9 +53,9 @@ __device__ __forceinline__ float4 lerp4(const float4& a, const float4& b, float 
 // Per-level sampling context: everything that depends on the level only, prepared once per
 // texture() call so that the taps of an anisotropic footprint share it (SB:97-105 walks the level
 // table on every fetch).
-struct LevelCtx { const float4* base; int w, h; float fw, fh, fw1, fh1, invW, invH, inv2W, inv2H; };
+struct LevelCtx { const float4* base; unsigned long long hw; int w, h; float fw, fh, fw1, fh1, invW, invH, inv2W, inv2H; };
 
-__device__ __forceinline__ LevelCtx level_ctx(const TexDesc& t, int layer, int lod) {
+__device__ __forceinline__ LevelCtx level_ctx(const TexDesc& t, int layer, int lod, int hwFilter = 0) {
     lod = clampi(lod, 0, t.mips);
     const TexLevel& L = t.lvl[lod];
     LevelCtx c;
@@ -63,6 +63,7 @@ __device__ __forceinline__ LevelCtx level_ctx(const TexDesc& t, int layer, int l
     c.fw = (float)c.w; c.fh = (float)c.h; c.fw1 = (float)(c.w - 1); c.fh1 = (float)(c.h - 1);
     c.invW = L.invW; c.invH = L.invH; c.inv2W = L.inv2W; c.inv2H = L.inv2H;
     c.base = t.data + L.off + (size_t)L.layerStride * layer;
+    c.hw = (hwFilter && layer == 0) ? t.hw[lod] : 0ull;
     return c;
 }
 
@@ -84,6 +85,11 @@ __device__ __forceinline__ float4 sample_level(const LevelCtx& L, const SampDesc
         py = clampi(py % h, 0, h - 1);
         return __ldg(base + py * w + px);
     }
+    if (L.hw && cx >= 0.0f && cy >= 0.0f) {
+        // the same 2x2 footprint and weights (texel = floor(c), neighbour clamped to the edge), fetched and
+        // blended by the texture unit: one TEX instead of 4 loads + 12 lerps; weights are quantised to 8 bits
+        return tex2D<float4>((cudaTextureObject_t)L.hw, cx + 0.5f, cy + 0.5f);
+    }
     const int px = clampi((int)cx, 0, w - 1), py = clampi((int)cy, 0, h - 1);
     const float fx = cx - (float)px, fy = cy - (float)py;
     const int px1 = min(px + 1, w - 1), py1 = min(py + 1, h - 1);
@@ -98,12 +104,12 @@ __device__ __forceinline__ float4 sample_level(const LevelCtx& L, const SampDesc
 // trilinear footprint shared by n taps: levels floor(lod), floor(lod)+1 and the blend factor
 struct TriCtx { LevelCtx lo, hi; float d; };
 
-__device__ __forceinline__ TriCtx tri_ctx(const TexDesc& t, int layer, float lod) {
+__device__ __forceinline__ TriCtx tri_ctx(const TexDesc& t, int layer, float lod, int hwFilter = 0) {
     TriCtx c;
     const int lo = (int)floorf(lod);
     c.d = lod - (float)lo;
-    c.lo = level_ctx(t, layer, lo);
-    c.hi = level_ctx(t, layer, lo + 1);
+    c.lo = level_ctx(t, layer, lo, hwFilter);
+    c.hi = level_ctx(t, layer, lo + 1, hwFilter);
     return c;
 }
 
@@ -115,19 +121,19 @@ __device__ __forceinline__ float4 sample_trilinear(const TriCtx& c, const SampDe
 }
 
 __device__ __forceinline__ float4 sample_trilinear(const TexDesc& t, const SampDesc& s, int layer, float u, float v,
-                                                   int offx, int offy, float lod) {
-    return sample_trilinear(tri_ctx(t, layer, lod), s, u, v, offx, offy);
+                                                   int offx, int offy, float lod, int hwFilter = 0) {
+    return sample_trilinear(tri_ctx(t, layer, lod, hwFilter), s, u, v, offx, offy);
 }
 
 __device__ __forceinline__ float4 sample_adaptive(const TexDesc& t, const SampDesc& s, float u, float v, float2 dx,
-                                                  float2 dy, float bias) {
+                                                  float2 dy, float bias, int hwFilter = 0) {
     const float W = (float)t.w, H = (float)t.h;
     const float ax = dx.x * W, ay = dx.y * H;
     const float bx = dy.x * W, by = dx.y * H;   // (sic) SB:237
     const float a2 = fmaf(ay, ay, ax * ax), b2 = fmaf(by, by, bx * bx);
     const float d = fmaxf(a2, b2);
     const float lod = fmaxf(0.0f, fmaf(0.5f, log2f(d), bias));
-    return sample_trilinear(t, s, 0, u, v, 0, 0, lod);
+    return sample_trilinear(t, s, 0, u, v, 0, 0, lod, hwFilter);
 }
 
 // 1/k for k = 0..33 as correctly rounded floats (identical to the oracle's 1.0f / (float)k)
@@ -140,7 +146,7 @@ __constant__ float kRcpTab[34] = {
 __device__ __forceinline__ float rcp_int(int k) { return k <= 33 ? kRcpTab[k] : __fdiv_rn(1.0f, (float)k); }
 
 __device__ __forceinline__ float4 sample_aniso(const TexDesc& t, const SampDesc& s, float u, float v, float2 du, float2 dv,
-                                               float bias) {
+                                               float bias, int hwFilter = 0) {
     const float dudx = du.x, dudy = du.y, dvdx = dv.x, dvdy = dv.y;
     const float px = sqrtf(fmaf(dvdx, dvdx, dudx * dudx)) * (float)t.w;
     const float py = sqrtf(fmaf(dvdy, dvdy, dudy * dudy)) * (float)t.h;
@@ -154,7 +160,7 @@ __device__ __forceinline__ float4 sample_aniso(const TexDesc& t, const SampDesc&
     const float ddu = (px > py) ? dudx : dudy, ddv = (px > py) ? dvdx : dvdy;
     float4 sum = make_float4(0, 0, 0, 0);
     const float step = rcp_int(n + 1), invN = rcp_int(n);
-    const TriCtx ctx = tri_ctx(t, 0, lambda + bias);
+    const TriCtx ctx = tri_ctx(t, 0, lambda + bias, hwFilter);
     for (int i = 0; i < n; i++) {
         const float tt = (float)i * step - 0.5f;
         const float4 r = sample_trilinear(ctx, s, fmaf(ddu, tt, u), fmaf(ddv, tt, v), 0, 0);
@@ -181,8 +187,8 @@ __device__ __forceinline__ float4 sample_cube(const TexDesc& t, const SampDesc& 
 
 // texture(tex, samp, varyings, uvVaryId, bias) — SB:357-372
 __device__ __forceinline__ float4 tex_grad(const TexDesc& t, const SampDesc& s, float u, float v, float2 ddx,
-                                           float2 ddy, float bias) {
-    return s.aniso ? sample_aniso(t, s, u, v, ddx, ddy, bias) : sample_adaptive(t, s, u, v, ddx, ddy, bias);
+                                           float2 ddy, float bias, int hwFilter = 0) {
+    return s.aniso ? sample_aniso(t, s, u, v, ddx, ddy, bias, hwFilter) : sample_adaptive(t, s, u, v, ddx, ddy, bias, hwFilter);
 }
 
 // ---- fragment shader registry (static functors inlined into the tile kernel) -----------------
@@ -205,9 +211,9 @@ __device__ __forceinline__ float4 run_fs(const DrawParams& p, const float4* v, c
         float4 c;
         if (FS == IFRIT_FS_TEXTURED)
             c = tex_grad(p.tex[0], p.samp[0], v[1].x, v[1].y, make_float2(ddx[1].x, ddx[1].y),
-                         make_float2(ddy[1].x, ddy[1].y), __ldg(u + 20));
+                         make_float2(ddy[1].x, ddy[1].y), __ldg(u + 20), p.hwFilter);
         else
-            c = sample_trilinear(p.tex[0], p.samp[0], 0, v[1].x, v[1].y, 0, 0, 0.0f);
+            c = sample_trilinear(p.tex[0], p.samp[0], 0, v[1].x, v[1].y, 0, 0, 0.0f, p.hwFilter);
         const float nx = v[0].x, ny = v[0].y, nz = v[0].z;
         const float len = sqrtf(fmaf(nz, nz, fmaf(ny, ny, nx * nx)));
         float ndl = fmaf(nz, __ldg(u + 18), fmaf(ny, __ldg(u + 17), nx * __ldg(u + 16))) / len;

@@ -128,7 +128,7 @@ def load_library():
         for name in ("iftrcuBindFragmentShader", "iftrcuBindGeometryShader", "iftrcuSetScissorTestEnable",
                      "iftrcuSetMsaaSamples", "iftrcuSetRasterizerPolygonMode", "iftrcuSetDepthFunc",
                      "iftrcuSetDepthTestEnable", "iftrcuSetCullMode", "iftrcuSetSampleConvention",
-                     "iftrcuSetDebugPrimitiveIds", "iftrcuSetVertexStageFused"):
+                     "iftrcuSetDebugPrimitiveIds", "iftrcuSetVertexStageFused", "iftrcuSetSamplerHardwareFilter"):
             getattr(L, name).argtypes = [C.c_void_p, C.c_int]
         L.iftrcuSetTilePartition.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.iftrcuExportFrameBuffer.argtypes = [C.c_void_p, C.c_void_p]
@@ -342,6 +342,9 @@ class TileRasterRendererCuda:
 
     def setDebugPrimitiveIds(self, enable=True):
         self._ck(self._lib.iftrcuSetDebugPrimitiveIds(self._h, int(enable)))
+
+    def setSamplerHardwareFilter(self, enable=True):
+        self._ck(self._lib.iftrcuSetSamplerHardwareFilter(self._h, int(enable)))
 
     def setVertexStageFused(self, enable=True):
         self._ck(self._lib.iftrcuSetVertexStageFused(self._h, int(enable)))

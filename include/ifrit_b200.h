@@ -209,6 +209,10 @@ IFRIT_B200_API int iftrcuSetDebugPrimitiveIds(iftrcuRenderer* h, int enable);
 /* vertex stage fused into triangle setup (default, 1) or run as the stand-alone kernel that mirrors
  * vertexProcessingKernel CU:330 (0); both produce identical frames */
 IFRIT_B200_API int iftrcuSetVertexStageFused(iftrcuRenderer* h, int enable);
+/* LINEAR-filter 2x2 footprints through the texture unit (default, 1): same texels and weights as
+ * textureImplLegacy (ShaderBuiltinCuda.cuh:106-182) but blended by the hardware with 8-bit weights — colour
+ * within 1/255; 0 = four loads + fp32 lerps in software, bit-identical to the CPU oracle */
+IFRIT_B200_API int iftrcuSetSamplerHardwareFilter(iftrcuRenderer* h, int enable);
 
 /* ---- draw ----------------------------------------------------------------------------- */
 IFRIT_B200_API int iftrcuClear(iftrcuRenderer* h);        /* RC::clear — fused into the next draw */
