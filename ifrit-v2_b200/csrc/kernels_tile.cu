@@ -116,9 +116,47 @@ __device__ __forceinline__ void key_min_shared(unsigned long long* addr, unsigne
 
 
 // ---- attribute interpolation at an integer pixel (pixelShadingExecKernel CU:2168-2215) ---------
-template <int NV>
-__device__ __forceinline__ void interp(const DrawParams& p, uint32_t slot, int px, int py, float4* out, float& depth,
-                                       int& prim, int& fan) {
+// Perspective weights (u, v, 1 - (u + v)) of the clip-space barycentrics from the three edge values at a pixel
+// corner; beta_i = float(E_i) * ar is also what the depth plane uses.
+struct PixW { float u, v, w2; };
+__device__ __forceinline__ PixW persp_weights(const float beta[3], const float IW[3], uint32_t flags, const float* cb) {
+    float b0 = __fmul_rn(beta[0], IW[0]), b1 = __fmul_rn(beta[1], IW[1]), b2 = __fmul_rn(beta[2], IW[2]);
+    const float inv = __frcp_rn(__fadd_rn(__fadd_rn(b0, b1), b2));
+    b0 = __fmul_rn(b0, inv); b1 = __fmul_rn(b1, inv); b2 = __fmul_rn(b2, inv);
+    PixW w;
+    if (flags & IFR_FLAG_CLIPPED) {
+        w.u = fmaf(b2, cb[4], fmaf(b1, cb[2], __fmul_rn(b0, cb[0])));
+        w.v = fmaf(b2, cb[5], fmaf(b1, cb[3], __fmul_rn(b0, cb[1])));
+    } else {
+        // unclipped: clip barycentrics are those of (v2, v3, v1) of the input triangle, first and last
+        // exchanged by a cull swap: B = {(0,1),(0,0),(1,0)} or {(1,0),(0,0),(0,1)}.  The fma chains with
+        // exact 0 / 1 factors reduce to (x * 1 + 0 * y + 0) = x up to the sign of zero, which + 0.0f fixes.
+        const bool sw = flags & IFR_FLAG_SWAPPED;
+        const float B00 = sw ? 1.0f : 0.0f, B01 = sw ? 0.0f : 1.0f;
+        w.u = fmaf(b2, B01, fmaf(b1, 0.0f, __fmul_rn(b0, B00)));
+        w.v = fmaf(b2, B00, fmaf(b1, 0.0f, __fmul_rn(b0, B01)));
+    }
+    w.w2 = __fsub_rn(1.0f, __fadd_rn(w.u, w.v));
+    return w;
+}
+__device__ __forceinline__ float4 mix3(const float4& v0, const float4& v1, const float4& v2, const PixW& w) {
+    float4 o;
+    o.x = fmaf(v2.x, w.w2, fmaf(v1.x, w.v, __fmul_rn(v0.x, w.u)));
+    o.y = fmaf(v2.y, w.w2, fmaf(v1.y, w.v, __fmul_rn(v0.y, w.u)));
+    o.z = fmaf(v2.z, w.w2, fmaf(v1.z, w.v, __fmul_rn(v0.z, w.u)));
+    o.w = fmaf(v2.w, w.w2, fmaf(v1.w, w.v, __fmul_rn(v0.w, w.u)));
+    return o;
+}
+
+// Interpolates slot's varyings at pixel (px, py).  DERIV: also at the two other pixels the 2x2 quad's coarse
+// derivatives need — the horizontal and the vertical neighbour inside the screen-aligned quad (SB:36-76:
+// ddx = right - left of the lane's row, ddy = bottom - top of its column).  The lane evaluates its neighbours'
+// values itself from the same integer edge functions (E steps by -256 dY / +256 dX per pixel), which is
+// bit-identical to what a helper lane would compute, so a pixel shades alone: no helper invocations, no
+// quad-uniform control flow, every FS pass runs with all of its lanes useful.
+template <int NV, bool DERIV>
+__device__ __forceinline__ void interp(const DrawParams& p, uint32_t slot, int px, int py, float4* out, float4* ddx,
+                                       float4* ddy, float& depth, int& prim, int& fan) {
     const int4* r = reinterpret_cast<const int4*>(p.rec + slot);
     int X[3], Y[3];
     float Z[3], IW[3];
@@ -129,7 +167,7 @@ __device__ __forceinline__ void interp(const DrawParams& p, uint32_t slot, int p
     }
     const int4 w3 = __ldg(r + 3);
     const float ar = __int_as_float(w3.x);
-    const int flags = w3.y;
+    const uint32_t flags = (uint32_t)w3.y;
     fan = slot >= (uint32_t)p.ntri;
     prim = fan ? (int)(slot - (uint32_t)p.ntri) : (int)slot;
     int idx[3];
@@ -138,57 +176,67 @@ __device__ __forceinline__ void interp(const DrawParams& p, uint32_t slot, int p
         for (int j = 0; j < 3; j++) idx[j] = __ldg(p.ib + 3 * (size_t)prim + j);
     }
     const int sx = px * IFR_SUBPIX, sy = py * IFR_SUBPIX;
-    float beta[3];
+    const int hs = (px & 1) ? -IFR_SUBPIX : IFR_SUBPIX, vs = (py & 1) ? -IFR_SUBPIX : IFR_SUBPIX;   // towards the quad neighbours
+    float beta[3], betaH[3], betaV[3];
     if (flags & IFR_FLAG_FITS32) {
-        // the edge values fit int32 (triangle-level bound): wrapping 32-bit arithmetic is exact
+        // the edge values fit int32 (triangle-level bound, two pixels around any covered sample): wrapping
+        // 32-bit arithmetic is exact
 #pragma unroll
         for (int i = 0; i < 3; i++) {
             const int a = (i + 1) % 3, b = (i + 2) % 3;
-            const uint32_t E = (uint32_t)(X[b] - X[a]) * (uint32_t)(sy - Y[a]) - (uint32_t)(Y[b] - Y[a]) * (uint32_t)(sx - X[a]);
+            const uint32_t dx = (uint32_t)(X[b] - X[a]), dy = (uint32_t)(Y[b] - Y[a]);
+            const uint32_t E = dx * (uint32_t)(sy - Y[a]) - dy * (uint32_t)(sx - X[a]);
             beta[i] = __fmul_rn((float)(int)E, ar);
+            if (DERIV) {
+                betaH[i] = __fmul_rn((float)(int)(E - dy * (uint32_t)hs), ar);
+                betaV[i] = __fmul_rn((float)(int)(E + dx * (uint32_t)vs), ar);
+            }
         }
     } else {
 #pragma unroll
         for (int i = 0; i < 3; i++) {
             const int a = (i + 1) % 3, b = (i + 2) % 3;
-            const long long E = (long long)(X[b] - X[a]) * (long long)(sy - Y[a]) - (long long)(Y[b] - Y[a]) * (long long)(sx - X[a]);
+            const long long dx = X[b] - X[a], dy = Y[b] - Y[a];
+            const long long E = dx * (long long)(sy - Y[a]) - dy * (long long)(sx - X[a]);
             beta[i] = __fmul_rn((float)E, ar);
+            if (DERIV) {
+                betaH[i] = __fmul_rn((float)(E - dy * hs), ar);
+                betaV[i] = __fmul_rn((float)(E + dx * vs), ar);
+            }
         }
     }
     depth = fmaf(Z[2], beta[2], fmaf(Z[1], beta[1], __fmul_rn(Z[0], beta[0])));
     if (NV == 0) return;
-    float b0 = __fmul_rn(beta[0], IW[0]), b1 = __fmul_rn(beta[1], IW[1]), b2 = __fmul_rn(beta[2], IW[2]);
-    const float inv = __frcp_rn(__fadd_rn(__fadd_rn(b0, b1), b2));
-    b0 = __fmul_rn(b0, inv); b1 = __fmul_rn(b1, inv); b2 = __fmul_rn(b2, inv);
-    float u, v;
+    float cb[6] = {0, 0, 0, 0, 0, 0};
     if (flags & IFR_FLAG_CLIPPED) {
-        const float* cb = p.clipBary + (size_t)slot * 6;
-        float B[3][2];
+        const float* g = p.clipBary + (size_t)slot * 6;
 #pragma unroll
-        for (int j = 0; j < 3; j++) { B[j][0] = __ldg(cb + 2 * j); B[j][1] = __ldg(cb + 2 * j + 1); }
-        u = fmaf(b2, B[2][0], fmaf(b1, B[1][0], __fmul_rn(b0, B[0][0])));
-        v = fmaf(b2, B[2][1], fmaf(b1, B[1][1], __fmul_rn(b0, B[0][1])));
-    } else {
-        // unclipped: clip barycentrics are those of (v2, v3, v1) of the input triangle, first and last
-        // exchanged by a cull swap: B = {(0,1),(0,0),(1,0)} or {(1,0),(0,0),(0,1)}.  The fma chains with
-        // exact 0 / 1 factors reduce to (x * 1 + 0 * y + 0) = x up to the sign of zero, which + 0.0f fixes.
-        const bool sw = flags & IFR_FLAG_SWAPPED;
-        const float B00 = sw ? 1.0f : 0.0f, B01 = sw ? 0.0f : 1.0f;
-        u = fmaf(b2, B01, fmaf(b1, 0.0f, __fmul_rn(b0, B00)));
-        v = fmaf(b2, B00, fmaf(b1, 0.0f, __fmul_rn(b0, B01)));
+        for (int j = 0; j < 6; j++) cb[j] = __ldg(g + j);
     }
-    const float w2 = __fsub_rn(1.0f, __fadd_rn(u, v));
+    const PixW w = persp_weights(beta, IW, flags, cb);
+    PixW wh = w, wv = w;
+    if (DERIV) { wh = persp_weights(betaH, IW, flags, cb); wv = persp_weights(betaV, IW, flags, cb); }
+    const bool right = px & 1, bottom = py & 1;
 #pragma unroll
     for (int k = 0; k < NV; k++) {
-        if (k >= p.nvary) { out[k] = make_float4(0, 0, 0, 0); continue; }
+        if (k >= p.nvary) {
+            out[k] = make_float4(0, 0, 0, 0);
+            if (DERIV) { ddx[k] = out[k]; ddy[k] = out[k]; }
+            continue;
+        }
         const uint8_t* vb = p.varyBase + p.varyOff[k];
         const float4 v0 = __ldg(reinterpret_cast<const float4*>(vb + (size_t)idx[0] * p.varyStride)),
                      v1 = __ldg(reinterpret_cast<const float4*>(vb + (size_t)idx[1] * p.varyStride)),
                      v2 = __ldg(reinterpret_cast<const float4*>(vb + (size_t)idx[2] * p.varyStride));
-        out[k].x = fmaf(v2.x, w2, fmaf(v1.x, v, __fmul_rn(v0.x, u)));
-        out[k].y = fmaf(v2.y, w2, fmaf(v1.y, v, __fmul_rn(v0.y, u)));
-        out[k].z = fmaf(v2.z, w2, fmaf(v1.z, v, __fmul_rn(v0.z, u)));
-        out[k].w = fmaf(v2.w, w2, fmaf(v1.w, v, __fmul_rn(v0.w, u)));
+        const float4 a = mix3(v0, v1, v2, w);
+        out[k] = a;
+        if (DERIV) {
+            const float4 o1 = mix3(v0, v1, v2, wh), o2 = mix3(v0, v1, v2, wv);
+            ddx[k] = right ? make_float4(a.x - o1.x, a.y - o1.y, a.z - o1.z, a.w - o1.w)
+                           : make_float4(o1.x - a.x, o1.y - a.y, o1.z - a.z, o1.w - a.w);
+            ddy[k] = bottom ? make_float4(a.x - o2.x, a.y - o2.y, a.z - o2.z, a.w - o2.w)
+                            : make_float4(o2.x - a.x, o2.y - a.y, o2.z - a.z, o2.w - a.w);
+        }
     }
 }
 
@@ -363,70 +411,41 @@ __global__ void __launch_bounds__(256, 4) tile_kernel(const __grid_constant__ Dr
     float4 acc = make_float4(0, 0, 0, 0);
     float dacc = 0.0f;
     int bg = S;
-    uint32_t last = IFR_SLOT_NONE;   // last slot shaded (ascending order); quad-uniform when derivatives are needed
-    bool first = true;
     unsigned int myFrags = 0;
-    while (true) {
-        uint32_t mine = IFR_SLOT_NONE;
+    // One FS invocation per (pixel, slot) that owns >= 1 sample, slots in ascending order (CU:2264-2310).  A lane
+    // shades alone (see interp), so the loop runs max-over-lanes(distinct slots) times and nothing is quad-uniform.
+    uint32_t last = 0;
+    bool first = true;
+    while (inFrame) {
+        uint32_t cur = IFR_SLOT_NONE;
 #pragma unroll
         for (int s = 0; s < S; s++) {
             const uint32_t v = mySlots[s];
-            if (v != IFR_SLOT_NONE && (first || v > last) && v < mine) mine = v;
+            if (v != IFR_SLOT_NONE && (first || v > last) && v < cur) cur = v;
         }
-        uint32_t cur = mine;
-        if (FsTraits<FS>::needsDerivs) {
-            // helper lanes: the whole quad interpolates every slot visible anywhere in the quad
-            cur = min(cur, __shfl_xor_sync(0xffffffffu, cur, 1));
-            cur = min(cur, __shfl_xor_sync(0xffffffffu, cur, 2));
-            if (__ballot_sync(0xffffffffu, cur != IFR_SLOT_NONE) == 0) break;
-        } else {
-            // no derivatives: a lane shades exactly its own slots (helper invocations have no observable effect)
-            if (cur == IFR_SLOT_NONE) break;
-        }
-        const bool active = cur != IFR_SLOT_NONE;
-        float4 v[NV > 0 ? NV : 1];
+        if (cur == IFR_SLOT_NONE) break;
+        int cnt = 0;
+#pragma unroll
+        for (int s = 0; s < S; s++) cnt += mySlots[s] == cur;
+        float4 v[NV > 0 ? NV : 1], ddx[NV > 0 ? NV : 1], ddy[NV > 0 ? NV : 1];
         float depth = 0.0f;
         int prim = 0, fan = 0;
-        if (active) interp<NV>(p, cur, px, py, v, depth, prim, fan);
-        float4 ddx[NV > 0 ? NV : 1], ddy[NV > 0 ? NV : 1];
-        if (FsTraits<FS>::needsDerivs) {
+        interp<NV, FsTraits<FS>::needsDerivs>(p, cur, px, py, v, ddx, ddy, depth, prim, fan);
+        const float4 c = run_fs<FS>(p, v, ddx, ddy, prim, fan);
+        const float fc = (float)cnt;
+        acc.x = fmaf(fc, c.x, acc.x); acc.y = fmaf(fc, c.y, acc.y);
+        acc.z = fmaf(fc, c.z, acc.z); acc.w = fmaf(fc, c.w, acc.w);
+        dacc = fmaf(fc, depth, dacc);
+        bg -= cnt;
+        myFrags++;
+        if (p.primIds) {
 #pragma unroll
-            for (int k = 0; k < NV; k++) {
-                // coarse derivatives: right - left of the row, bottom - top of the column (SB:36-76)
-                const float4 a = v[k];
-                float4 o1, o2;
-                o1.x = __shfl_xor_sync(0xffffffffu, a.x, 1); o1.y = __shfl_xor_sync(0xffffffffu, a.y, 1);
-                o1.z = __shfl_xor_sync(0xffffffffu, a.z, 1); o1.w = __shfl_xor_sync(0xffffffffu, a.w, 1);
-                o2.x = __shfl_xor_sync(0xffffffffu, a.x, 2); o2.y = __shfl_xor_sync(0xffffffffu, a.y, 2);
-                o2.z = __shfl_xor_sync(0xffffffffu, a.z, 2); o2.w = __shfl_xor_sync(0xffffffffu, a.w, 2);
-                const bool right = l & 1, bottom = l & 2;
-                ddx[k] = right ? make_float4(a.x - o1.x, a.y - o1.y, a.z - o1.z, a.w - o1.w)
-                               : make_float4(o1.x - a.x, o1.y - a.y, o1.z - a.z, o1.w - a.w);
-                ddy[k] = bottom ? make_float4(a.x - o2.x, a.y - o2.y, a.z - o2.z, a.w - o2.w)
-                                : make_float4(o2.x - a.x, o2.y - a.y, o2.z - a.z, o2.w - a.w);
-            }
+            for (int s = 0; s < S; s++)
+                if (mySlots[s] == cur) p.primIds[pidx * S + s] = prim;
         }
-        if (active) {
-            int cnt = 0;
-#pragma unroll
-            for (int s = 0; s < S; s++) cnt += mySlots[s] == cur;
-            if (cnt && inFrame) {
-                const float4 c = run_fs<FS>(p, v, ddx, ddy, prim, fan);
-                const float fc = (float)cnt;
-                acc.x = fmaf(fc, c.x, acc.x); acc.y = fmaf(fc, c.y, acc.y);
-                acc.z = fmaf(fc, c.z, acc.z); acc.w = fmaf(fc, c.w, acc.w);
-                dacc = fmaf(fc, depth, dacc);
-                bg -= cnt;
-                myFrags++;
-                if (p.primIds) {
-#pragma unroll
-                    for (int s = 0; s < S; s++)
-                        if (mySlots[s] == cur) p.primIds[pidx * S + s] = prim;
-                }
-            }
-            last = cur;
-            first = false;
-        }
+        last = cur;
+        first = false;
+        if (S == 1) break;
     }
     if (inFrame) {
         if (p.primIds) {
