@@ -39,7 +39,9 @@ struct __align__(16) TriS {
     int T[3]; uint32_t flags;    // int32 thresholds: inside <=> dX*j - dY*i >= T (i, j in 1/16 px, tile local)
     long long E0[3];             // edge functions at the tile origin (sub-pixel units)
     float ar, z0, z1, z2;
-    int pad[2];                  // pad[0]: coarse-raster mask, bit per 8x4-pixel block of the tile
+    int pad[2];                  // pad[0]: coarse raster, bit per 8x4-pixel block of the tile: 0-7 may hold a covered
+                                 // sample, 8-15 covered at every sample; pad[1]: Hi-Z bound (float bits), the most
+                                 // optimistic depth of the triangle inside its tile-local box
 };
 
 #define IFR_MAX_MIPS 16

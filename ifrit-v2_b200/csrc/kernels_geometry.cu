@@ -261,7 +261,10 @@ __device__ __forceinline__ void emit_one(const DrawParams& p, const RecRegs& rr,
     } else {
         TriS s;
         int bx0, bx1, by0, by1;
-        if (!setup_from_rec<true>(p, rr, slot, tx, ty, s, bx0, bx1, by0, by1)) s.box = 0x00ff00ffu;   // empty: rows 255..0
+        // deep queues only: the Hi-Z bound pays for itself when the tile kernel has many triangles to skip
+        const uint32_t* bs = p.tileStart + (p.tilesX * p.tilesY + 1) + ty * p.tilesX + tx;
+        const bool wantZ = bs[1] - bs[0] >= IFR_HIZ_MIN_QUEUE;
+        if (!setup_from_rec<true>(p, rr, slot, tx, ty, s, bx0, bx1, by0, by1, wantZ)) s.box = 0x00ff00ffu;   // empty: rows 255..0
         int4* dst = reinterpret_cast<int4*>(p.bigQueue + pos);
         const int4* src = reinterpret_cast<const int4*>(&s);
 #pragma unroll

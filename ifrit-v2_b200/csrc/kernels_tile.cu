@@ -352,6 +352,15 @@ __global__ void __launch_bounds__(256, 4) tile_kernel(const __grid_constant__ Dr
     //      every thread tests its own pixel against broadcast LDS.128 words, warps run independently ------
     if (nBig) {
         const int ci = 16 * lx, cj = 16 * ly;
+        // Hierarchical early-Z, one level above the pixel: wfar = the worst (largest) key depth word any sample of
+        // this warp's 8x4 block currently holds.  A triangle whose most optimistic depth inside the tile (TriS
+        // pad[1], from the fill pass) maps above it cannot win a single sample of the block and is skipped by the
+        // whole warp.  Ordered compare ops only; results are unchanged (the reference has no Hi-Z: curTileHierZ is
+        // an unused field, TileRasterWorker.h:80).
+        const bool hiz = km.ordered && nBig >= IFR_HIZ_MIN_QUEUE;
+        if (S == 1 && nSmall) { const unsigned long long ks = keys[tid]; if (ks < best) best = ks; }
+        uint32_t wfar = 0xffffffffu;
+        bool dirty = hiz;
         const uint32_t nchunks = (nBig + IFR_BIG_CHUNK - 1) / IFR_BIG_CHUNK;
         for (uint32_t c = 0; c < nchunks; c++) {
             if (tid == 0 && c + 1 < nchunks) {
@@ -363,37 +372,52 @@ __global__ void __launch_bounds__(256, 4) tile_kernel(const __grid_constant__ Dr
             const uint32_t cnt = min(nBig - c * IFR_BIG_CHUNK, (uint32_t)IFR_BIG_CHUNK);
             const int4* t4 = reinterpret_cast<const int4*>(bigBuf[c & 1]);
             for (uint32_t b = 0; b < cnt; b++, t4 += 6) {
+                if (dirty) {
+                    // refresh the block's far bound (warp-convergent: every reject above / below is warp-uniform)
+                    uint32_t mine;
+                    if (S == 1) mine = (uint32_t)(best >> 32);
+                    else {
+                        mine = 0;
+#pragma unroll
+                        for (int sm = 0; sm < S; sm++) mine = max(mine, (uint32_t)(keys[sm * IFR_TILE_PIX + tid] >> 32));
+                    }
+                    wfar = __reduce_max_sync(0xffffffffu, mine);
+                    dirty = false;
+                }
                 // warp-uniform coarse reject: the fill pass rasterised the triangle against the tile's 8x4 blocks
-                const uint32_t blockMask = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(t4) + 88);
-                if (!((blockMask >> wrp) & 1)) continue;
+                const uint2 cz = *reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(t4) + 88);
+                if (!((cz.x >> wrp) & 1)) continue;
+                if (hiz && (mono(__uint_as_float(cz.y)) ^ km.xhi) > wfar) continue;
                 const int4 A = t4[0];
                 const int4 B = t4[1], C = t4[2];
                 const int dX[3] = {A.x, A.y, A.z}, dY[3] = {B.x, B.y, B.z}, T[3] = {C.x, C.y, C.z};
                 const uint32_t flags = (uint32_t)C.w;
-                uint32_t m = 0;
-                if (!(flags & IFR_FLAG_WIDE)) {
-                    if (scis) m = coverage<S>(p, dX, dY, T, nullptr, 0, ci, cj);
-                    if (!m) continue;
-                }
                 const int4 D = t4[3], E = t4[4];
                 const long long E0[3] = {(long long)(((unsigned long long)(uint32_t)D.y << 32) | (uint32_t)D.x),
                                          (long long)(((unsigned long long)(uint32_t)D.w << 32) | (uint32_t)D.z),
                                          (long long)(((unsigned long long)(uint32_t)E.y << 32) | (uint32_t)E.x)};
-                if (flags & IFR_FLAG_WIDE) {
-                    if (scis) m = coverage<S>(p, dX, dY, T, E0, 1, ci, cj);
-                    if (!m) continue;
+                uint32_t m = 0;
+                if (scis) {
+                    if ((cz.x >> (8 + wrp)) & 1) m = (1u << S) - 1u;          // trivial accept: every sample of the block
+                    else if (!(flags & IFR_FLAG_WIDE)) m = coverage<S>(p, dX, dY, T, nullptr, 0, ci, cj);
+                    else m = coverage<S>(p, dX, dY, T, E0, 1, ci, cj);
                 }
-                const float2 Zr = *reinterpret_cast<const float2*>(t4 + 5);
-                const float d = depth_at(dX, dY, E0, flags, __int_as_float(E.z), __int_as_float(E.w), Zr.x, Zr.y, lx, ly);
-                unsigned long long k;
-                if (!key_make(km, d, d0, (uint32_t)B.w, k)) continue;
-                if (S == 1) {
-                    if (k < best) best = k;
-                } else {
+                bool upd = false;
+                if (m) {
+                    const float2 Zr = *reinterpret_cast<const float2*>(t4 + 5);
+                    const float d = depth_at(dX, dY, E0, flags, __int_as_float(E.z), __int_as_float(E.w), Zr.x, Zr.y, lx, ly);
+                    unsigned long long k;
+                    if (key_make(km, d, d0, (uint32_t)B.w, k)) {
+                        if (S == 1) {
+                            if (k < best) { best = k; upd = true; }
+                        } else {
 #pragma unroll
-                    for (int sm = 0; sm < S; sm++)
-                        if (((m >> sm) & 1) && k < keys[sm * IFR_TILE_PIX + tid]) keys[sm * IFR_TILE_PIX + tid] = k;
+                            for (int sm = 0; sm < S; sm++)
+                                if (((m >> sm) & 1) && k < keys[sm * IFR_TILE_PIX + tid]) { keys[sm * IFR_TILE_PIX + tid] = k; upd = true; }
+                        }
+                    }
                 }
+                if (hiz) dirty = __any_sync(0xffffffffu, upd);
             }
             if (c + 2 < nchunks) __syncthreads();   // buffer (c & 1) is refilled at the top of iteration c + 1
         }
@@ -512,8 +536,8 @@ cudaError_t ifr_launch_tiles(const DrawParams& p, int fsId, cudaStream_t s) {
         case IFRIT_FS_VARYING0: return launch_fs<IFRIT_FS_VARYING0>(p, s);
         case IFRIT_FS_NORMAL_COLOR: return launch_fs<IFRIT_FS_NORMAL_COLOR>(p, s);
         case IFRIT_FS_PRIM_ID: return launch_fs<IFRIT_FS_PRIM_ID>(p, s);
-        case IFRIT_FS_TEXTURED: return launch_fs<IFRIT_FS_TEXTURED>(p, s);
-        case IFRIT_FS_TEXTURED_LOD0: return launch_fs<IFRIT_FS_TEXTURED_LOD0>(p, s);
+        case IFRIT_FS_TEXTURED: return p.hwFilter ? launch_fs<IFRIT_FS_TEXTURED_FAST>(p, s) : launch_fs<IFRIT_FS_TEXTURED>(p, s);
+        case IFRIT_FS_TEXTURED_LOD0: return p.hwFilter ? launch_fs<IFRIT_FS_TEXTURED_LOD0_FAST>(p, s) : launch_fs<IFRIT_FS_TEXTURED_LOD0>(p, s);
         case IFRIT_FS_SKYBOX: return launch_fs<IFRIT_FS_SKYBOX>(p, s);
         case IFRIT_FS_DERIV_VIS: return launch_fs<IFRIT_FS_DERIV_VIS>(p, s);
         default: return cudaErrorInvalidValue;

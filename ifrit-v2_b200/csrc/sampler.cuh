@@ -45,6 +45,12 @@ __device__ __forceinline__ float addr_mode(int mode, float c, float s, float inv
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
+// single-instruction SFU forms, used by the FAST sampler variant only (colour bar: 1/255 on >= 99.9 % of pixels)
+__device__ __forceinline__ float sqrt_fast(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rsqrt_fast(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float lg2_fast(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
 __device__ __forceinline__ float4 lerp4(const float4& a, const float4& b, float t) {
     return make_float4(fmaf(b.x - a.x, t, a.x), fmaf(b.y - a.y, t, a.y), fmaf(b.z - a.z, t, a.z),
                        fmaf(b.w - a.w, t, a.w));
@@ -125,6 +131,7 @@ __device__ __forceinline__ float4 sample_trilinear(const TexDesc& t, const SampD
     return sample_trilinear(tri_ctx(t, layer, lod, hwFilter), s, u, v, offx, offy);
 }
 
+template <bool FAST>
 __device__ __forceinline__ float4 sample_adaptive(const TexDesc& t, const SampDesc& s, float u, float v, float2 dx,
                                                   float2 dy, float bias, int hwFilter = 0) {
     const float W = (float)t.w, H = (float)t.h;
@@ -132,7 +139,7 @@ __device__ __forceinline__ float4 sample_adaptive(const TexDesc& t, const SampDe
     const float bx = dy.x * W, by = dx.y * H;   // (sic) SB:237
     const float a2 = fmaf(ay, ay, ax * ax), b2 = fmaf(by, by, bx * bx);
     const float d = fmaxf(a2, b2);
-    const float lod = fmaxf(0.0f, fmaf(0.5f, log2f(d), bias));
+    const float lod = fmaxf(0.0f, fmaf(0.5f, FAST ? lg2_fast(d) : log2f(d), bias));
     return sample_trilinear(t, s, 0, u, v, 0, 0, lod, hwFilter);
 }
 
@@ -145,26 +152,62 @@ __constant__ float kRcpTab[34] = {
     1.0f / 33.0f};
 __device__ __forceinline__ float rcp_int(int k) { return k <= 33 ? kRcpTab[k] : __fdiv_rn(1.0f, (float)k); }
 
+// texel-space coordinates of one tap on one level (address modes without a border colour)
+__device__ __forceinline__ float2 tap_coords(const LevelCtx& L, const SampDesc& s, float u, float v) {
+    bool border = false;
+    const float cx = addr_mode(s.addrU, fmaf(u, L.fw1, 0.0f), L.fw, L.invW, L.inv2W, border);
+    const float cy = addr_mode(s.addrV, fmaf(v, L.fh1, 0.0f), L.fh, L.invH, L.inv2H, border);
+    return make_float2(cx + 0.5f, cy + 0.5f);
+}
+
+template <bool FAST>
 __device__ __forceinline__ float4 sample_aniso(const TexDesc& t, const SampDesc& s, float u, float v, float2 du, float2 dv,
                                                float bias, int hwFilter = 0) {
     const float dudx = du.x, dudy = du.y, dvdx = dv.x, dvdy = dv.y;
-    const float px = sqrtf(fmaf(dvdx, dvdx, dudx * dudx)) * (float)t.w;
-    const float py = sqrtf(fmaf(dvdy, dvdy, dudy * dudy)) * (float)t.h;
+    const float lx2 = fmaf(dvdx, dvdx, dudx * dudx), ly2 = fmaf(dvdy, dvdy, dudy * dudy);
+    const float px = (FAST ? sqrt_fast(lx2) : sqrtf(lx2)) * (float)t.w;
+    const float py = (FAST ? sqrt_fast(ly2) : sqrtf(ly2)) * (float)t.h;
     const float pmax = fmaxf(px, py), pmin = fminf(px, py);
     const int maxAniso = (int)s.maxAniso;
     // n = (int)fmax(1.0, fmin((double)ceilf(pmax / pmin) + 1e-3, (double)maxAniso + 1e-3)) of SB:252,
     // without the double-precision detour: ceilf() is integral, NaN / inf fall through to maxAniso
-    const float cr = ceilf(pmax / pmin);
+    const float cr = ceilf(FAST ? pmax * rcp_fast(pmin) : pmax / pmin);
     const int n = max(1, (cr < (float)maxAniso) ? (int)cr : maxAniso);
-    const float lambda = fmaxf(0.0f, log2f(pmax / (float)n));
+    const float step = rcp_int(n + 1), invN = rcp_int(n);
+    const float lambda = fmaxf(0.0f, FAST ? lg2_fast(pmax * invN) : log2f(pmax / (float)n));
     const float ddu = (px > py) ? dudx : dudy, ddv = (px > py) ? dvdx : dvdy;
     float4 sum = make_float4(0, 0, 0, 0);
-    const float step = rcp_int(n + 1), invN = rcp_int(n);
     const TriCtx ctx = tri_ctx(t, 0, lambda + bias, hwFilter);
-    for (int i = 0; i < n; i++) {
-        const float tt = (float)i * step - 0.5f;
-        const float4 r = sample_trilinear(ctx, s, fmaf(ddu, tt, u), fmaf(ddv, tt, v), 0, 0);
-        sum.x += r.x; sum.y += r.y; sum.z += r.z; sum.w += r.w;
+    if (FAST && ctx.lo.hw && (ctx.d == 0.0f || ctx.hi.hw) && s.filter == IF_FILTER_LINEAR &&
+        s.addrU != IF_SAMPLER_ADDRESS_MODE_CLAMP_TO_BORDER && s.addrV != IF_SAMPLER_ADDRESS_MODE_CLAMP_TO_BORDER) {
+        // every footprint goes through the texture unit: taps are issued two at a time (up to four fetches in
+        // flight) and summed in tap order
+        const bool two = ctx.d != 0.0f;
+        for (int i = 0; i < n; i += 2) {
+            const float t0 = (float)i * step - 0.5f, t1 = (float)(i + 1) * step - 0.5f;
+            const float u0 = fmaf(ddu, t0, u), v0 = fmaf(ddv, t0, v), u1 = fmaf(ddu, t1, u), v1 = fmaf(ddv, t1, v);
+            const bool has1 = i + 1 < n;
+            const float2 a0 = tap_coords(ctx.lo, s, u0, v0), a1 = tap_coords(ctx.lo, s, u1, v1);
+            float4 r0 = tex2D<float4>((cudaTextureObject_t)ctx.lo.hw, a0.x, a0.y);
+            float4 r1 = make_float4(0, 0, 0, 0);
+            if (has1) r1 = tex2D<float4>((cudaTextureObject_t)ctx.lo.hw, a1.x, a1.y);
+            if (two) {
+                const float2 b0 = tap_coords(ctx.hi, s, u0, v0), b1 = tap_coords(ctx.hi, s, u1, v1);
+                const float4 h0 = tex2D<float4>((cudaTextureObject_t)ctx.hi.hw, b0.x, b0.y);
+                float4 h1 = make_float4(0, 0, 0, 0);
+                if (has1) h1 = tex2D<float4>((cudaTextureObject_t)ctx.hi.hw, b1.x, b1.y);
+                r0 = lerp4(r0, h0, ctx.d);
+                r1 = lerp4(r1, h1, ctx.d);
+            }
+            sum.x += r0.x; sum.y += r0.y; sum.z += r0.z; sum.w += r0.w;
+            if (has1) { sum.x += r1.x; sum.y += r1.y; sum.z += r1.z; sum.w += r1.w; }
+        }
+    } else {
+        for (int i = 0; i < n; i++) {
+            const float tt = (float)i * step - 0.5f;
+            const float4 r = sample_trilinear(ctx, s, fmaf(ddu, tt, u), fmaf(ddv, tt, v), 0, 0);
+            sum.x += r.x; sum.y += r.y; sum.z += r.z; sum.w += r.w;
+        }
     }
     return make_float4(sum.x * invN, sum.y * invN, sum.z * invN, sum.w * invN);
 }
@@ -186,14 +229,24 @@ __device__ __forceinline__ float4 sample_cube(const TexDesc& t, const SampDesc& 
 }
 
 // texture(tex, samp, varyings, uvVaryId, bias) — SB:357-372
+template <bool FAST>
 __device__ __forceinline__ float4 tex_grad(const TexDesc& t, const SampDesc& s, float u, float v, float2 ddx,
                                            float2 ddy, float bias, int hwFilter = 0) {
-    return s.aniso ? sample_aniso(t, s, u, v, ddx, ddy, bias, hwFilter) : sample_adaptive(t, s, u, v, ddx, ddy, bias, hwFilter);
+    return s.aniso ? sample_aniso<FAST>(t, s, u, v, ddx, ddy, bias, hwFilter)
+                   : sample_adaptive<FAST>(t, s, u, v, ddx, ddy, bias, hwFilter);
 }
 
 // ---- fragment shader registry (static functors inlined into the tile kernel) -----------------
 // nv = number of varyings the shader reads (interpolation of the others is skipped)
+// Internal ids (not part of the ABI): the textured shaders with the FAST sampler — bilinear footprints blended by
+// the texture unit (8-bit weights) and single-instruction SFU forms of sqrt / divide / log2 in the LOD and
+// lighting math.  Selected by the launcher when iftrcuSetSamplerHardwareFilter is on (the default); the
+// plain ids keep the oracle's arithmetic op for op.
+#define IFRIT_FS_TEXTURED_FAST 100
+#define IFRIT_FS_TEXTURED_LOD0_FAST 101
 template <int FS> struct FsTraits { static constexpr bool needsDerivs = false; static constexpr int nv = 1; };
+template <> struct FsTraits<IFRIT_FS_TEXTURED_FAST> { static constexpr bool needsDerivs = true; static constexpr int nv = 2; };
+template <> struct FsTraits<IFRIT_FS_TEXTURED_LOD0_FAST> { static constexpr bool needsDerivs = false; static constexpr int nv = 2; };
 template <> struct FsTraits<IFRIT_FS_PRIM_ID> { static constexpr bool needsDerivs = false; static constexpr int nv = 0; };
 template <> struct FsTraits<IFRIT_FS_TEXTURED> { static constexpr bool needsDerivs = true; static constexpr int nv = 2; };
 template <> struct FsTraits<IFRIT_FS_TEXTURED_LOD0> { static constexpr bool needsDerivs = false; static constexpr int nv = 2; };
@@ -207,16 +260,18 @@ __device__ __forceinline__ float4 run_fs(const DrawParams& p, const float4* v, c
     if (FS == IFRIT_FS_NORMAL_COLOR)
         return make_float4(fmaf(v[0].x, 0.5f, 0.5f), fmaf(v[0].y, 0.5f, 0.5f), fmaf(v[0].z, 0.5f, 0.5f), 0.5f);
     if (FS == IFRIT_FS_PRIM_ID) return make_float4((float)prim, (float)fan, 0.0f, 1.0f);
-    if (FS == IFRIT_FS_TEXTURED || FS == IFRIT_FS_TEXTURED_LOD0) {
+    if (FS == IFRIT_FS_TEXTURED || FS == IFRIT_FS_TEXTURED_LOD0 || FS == IFRIT_FS_TEXTURED_FAST || FS == IFRIT_FS_TEXTURED_LOD0_FAST) {
+        constexpr bool FAST = FS == IFRIT_FS_TEXTURED_FAST || FS == IFRIT_FS_TEXTURED_LOD0_FAST;
         float4 c;
-        if (FS == IFRIT_FS_TEXTURED)
-            c = tex_grad(p.tex[0], p.samp[0], v[1].x, v[1].y, make_float2(ddx[1].x, ddx[1].y),
-                         make_float2(ddy[1].x, ddy[1].y), __ldg(u + 20), p.hwFilter);
+        if (FS == IFRIT_FS_TEXTURED || FS == IFRIT_FS_TEXTURED_FAST)
+            c = tex_grad<FAST>(p.tex[0], p.samp[0], v[1].x, v[1].y, make_float2(ddx[1].x, ddx[1].y),
+                               make_float2(ddy[1].x, ddy[1].y), __ldg(u + 20), FAST ? 1 : 0);
         else
-            c = sample_trilinear(p.tex[0], p.samp[0], 0, v[1].x, v[1].y, 0, 0, 0.0f, p.hwFilter);
+            c = sample_trilinear(p.tex[0], p.samp[0], 0, v[1].x, v[1].y, 0, 0, 0.0f, FAST ? 1 : 0);
         const float nx = v[0].x, ny = v[0].y, nz = v[0].z;
-        const float len = sqrtf(fmaf(nz, nz, fmaf(ny, ny, nx * nx)));
-        float ndl = fmaf(nz, __ldg(u + 18), fmaf(ny, __ldg(u + 17), nx * __ldg(u + 16))) / len;
+        const float len2 = fmaf(nz, nz, fmaf(ny, ny, nx * nx));
+        const float dot = fmaf(nz, __ldg(u + 18), fmaf(ny, __ldg(u + 17), nx * __ldg(u + 16)));
+        float ndl = FAST ? dot * rsqrt_fast(len2) : dot / sqrtf(len2);
         ndl = fmaxf(ndl, 0.2f);
         return make_float4(c.x * ndl, c.y * ndl, c.z * ndl, 1.0f);
     }

@@ -4,6 +4,7 @@
 // point instead of FP32 planes.
 #pragma once
 #include "common.cuh"
+#include "../../include/ifrit_b200.h"
 
 struct RecRegs { int X[3], Y[3]; float Z[3]; float ar; uint32_t flags; };
 
@@ -19,9 +20,11 @@ __device__ __forceinline__ void load_rec(const DrawParams& p, uint32_t slot, Rec
     rr.flags = (uint32_t)w3.y;
 }
 
+#define IFR_HIZ_MIN_QUEUE 12   // tiles with fewer big-queue entries skip the Hi-Z bound (fill pass) and the reject (tile kernel)
+
 template <bool COARSE>
 __device__ __forceinline__ bool setup_from_rec(const DrawParams& p, const RecRegs& rr, uint32_t slot, int tileX, int tileY,
-                                               TriS& s, int& bx0, int& bx1, int& by0, int& by1) {
+                                               TriS& s, int& bx0, int& bx1, int& by0, int& by1, bool wantZ = false) {
     const int* X = rr.X; const int* Y = rr.Y;
     s.slot = slot;
     s.ar = rr.ar;
@@ -51,8 +54,10 @@ __device__ __forceinline__ bool setup_from_rec(const DrawParams& p, const RecReg
     s.box = (uint32_t)(bx0 & 0xff) | ((uint32_t)(bx1 & 0xff) << 8) | ((uint32_t)(by0 & 0xff) << 16) | ((uint32_t)(by1 & 0xff) << 24);
     const bool ok = bx0 <= bx1 && by0 <= by1;
     // Coarse raster (secondBinnerWorklistRasterizerKernel CU:1254 keeps 4x4-px sub-tiles): which of the tile's eight
-    // 8x4-pixel blocks (one per warp of the tile kernel; bit = (y >> 2) * 2 + (x >> 3)) can hold a covered sample.
-    // Exact trivial reject: an edge whose function is below threshold at the block's most-inside sample corner.
+    // 8x4-pixel blocks (one per warp of the tile kernel; bit = (y >> 2) * 2 + (x >> 3)) can hold a covered sample
+    // (bits 0-7: exact trivial reject — an edge whose function is below threshold at the block's most-inside sample
+    // corner) and which are covered at every sample (bits 8-15: trivial accept — every edge passes at the block's
+    // most-outside sample corner, CU:287-313), so that the tile kernel skips the per-sample edge tests there.
     uint32_t mask = 0;
     if (COARSE && ok) {
         const int sLoX = p.sampMinX >> 4, sHiX = p.sampMaxX >> 4, sLoY = p.sampMinY >> 4, sHiY = p.sampMaxY >> 4;   // 1/16 px
@@ -60,18 +65,47 @@ __device__ __forceinline__ bool setup_from_rec(const DrawParams& p, const RecReg
         for (int blk = 0; blk < 8; blk++) {
             const int x0 = (blk & 1) * 8, y0 = (blk >> 1) * 4;
             if (x0 + 7 < bx0 || x0 > bx1 || y0 + 3 < by0 || y0 > by1) continue;
-            bool may = true;
+            bool may = true, full = false;
             if (!(rr.flags & IFR_FLAG_WIDE)) {
                 const int iLo = 16 * x0 + sLoX, iHi = 16 * (x0 + 7) + sHiX, jLo = 16 * y0 + sLoY, jHi = 16 * (y0 + 3) + sHiY;
+                full = true;
 #pragma unroll
                 for (int i = 0; i < 3; i++) {
                     const int best = s.dX[i] * (s.dX[i] > 0 ? jHi : jLo) - s.dY[i] * (s.dY[i] > 0 ? iLo : iHi);
+                    const int worst = s.dX[i] * (s.dX[i] > 0 ? jLo : jHi) - s.dY[i] * (s.dY[i] > 0 ? iHi : iLo);
                     may = may && best >= s.T[i];
+                    full = full && worst >= s.T[i];
                 }
             }
-            mask |= (uint32_t)may << blk;
+            mask |= ((uint32_t)may << blk) | ((uint32_t)(may && full) << (8 + blk));
         }
     }
+    // Hierarchical Z: the most optimistic depth this triangle can produce at any pixel of its tile-local box.
+    // The depth the tile kernel computes, F(x, y) = fma chain of z_i * (float(E_i) * ar), follows the exact
+    // plane P = sum z_i E_i / d within eps * M, M = sum |z_i| |E_i / d| (convex), eps < 1.75 * 2^-22.  P is
+    // affine, so over the box F >= min_corners F - 2 eps max_corners M; the margin below is twice that.
+    const bool greater = p.depthFunc == IF_COMPARE_OP_GREATER || p.depthFunc == IF_COMPARE_OP_GREATER_OR_EQUAL;
+    float zbound = greater ? 3.0e38f : -3.0e38f;   // "never reject" unless computed
+    if (COARSE && ok && wantZ) {
+        float lo = 3.0e38f, hi = -3.0e38f, mag = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int lx = (c & 1) ? bx1 : bx0, ly = (c & 2) ? by1 : by0;
+            float beta[3];
+#pragma unroll
+            for (int e = 0; e < 3; e++) {
+                const long long Ec = s.E0[e] + 256 * ((long long)s.dX[e] * ly - (long long)s.dY[e] * lx);
+                beta[e] = __fmul_rn((float)Ec, rr.ar);
+            }
+            const float d = fmaf(rr.Z[2], beta[2], fmaf(rr.Z[1], beta[1], __fmul_rn(rr.Z[0], beta[0])));
+            const float m = fabsf(rr.Z[0] * beta[0]) + fabsf(rr.Z[1] * beta[1]) + fabsf(rr.Z[2] * beta[2]);
+            lo = fminf(lo, d); hi = fmaxf(hi, d); mag = fmaxf(mag, m);
+        }
+        const float margin = mag * 1.9073486e-6f + 1e-30f;   // 2^-19 M
+        zbound = greater ? hi + margin : lo - margin;
+        if (!(zbound == zbound)) zbound = greater ? 3.0e38f : -3.0e38f;   // NaN depth: never reject
+    }
+    s.pad[1] = __float_as_int(zbound);
     s.pad[0] = (int)mask;
     return ok;
 }

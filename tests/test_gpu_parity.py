@@ -56,6 +56,29 @@ def test_depth_funcs(r, func):
     compare(o, g, exact_color=True)
 
 
+@pytest.mark.parametrize("msaa", [1, 8])
+@pytest.mark.parametrize("func", [O.CMP_LESS, O.CMP_LEQUAL, O.CMP_GREATER, O.CMP_GEQUAL])
+def test_hierarchical_z_heavy_overdraw(r, func, msaa):
+    """Screen-filling triangles with steep depth planes, ~60x overdraw: the tile kernel's warp-level Hi-Z reject and
+    its trivial-accept blocks must not change a single sample (ids / depth bit-exact), with and without a clear."""
+    W, H = 200, 120
+    vb, idx = scenes.random_tris(120, 77, size=1.6, extent=0.8)
+    vb2, idx2 = scenes.random_tris(400, 78, size=0.25)
+    vb = np.concatenate([vb, vb2]); idx = np.arange(len(vb), dtype=np.int32)
+    clear_depth = 1.0 if func in (O.CMP_LESS, O.CMP_LEQUAL) else 0.0
+    kw = dict(msaa=msaa, depth_func=func, clear_depth=clear_depth, cull=0)
+    o = oracle_draw(W, H, vb, idx, 0, O.FS_VARYING0, 1, IDENT, **kw)
+    g = gpu_draw(r, W, H, vb, idx, 0, O.FS_VARYING0, 1, IDENT, **kw)
+    compare(o, g, exact_color=True)
+    assert g["fragments_shaded"] == o["frags"]
+    # second draw over the first frame without a clear: the far bound starts from the stored depth
+    vb3, idx3 = scenes.random_tris(60, 79, size=1.2, extent=0.9)
+    kw2 = dict(kw, clear=False, color=o["color"], depth=o["depth"])
+    o2 = oracle_draw(W, H, vb3, idx3, 0, O.FS_VARYING0, 1, IDENT, **kw2)
+    g2 = gpu_draw(r, W, H, vb3, idx3, 0, O.FS_VARYING0, 1, IDENT, **kw2)
+    compare(o2, g2, exact_color=True)
+
+
 def test_standalone_vertex_stage_matches_fused(r):
     """vertexProcessingKernel CU:330 as its own kernel (pos / vary buffers) vs fused into triangle setup."""
     W, H = 320, 200
