@@ -267,13 +267,25 @@ def run_ours(args, cfg_name):
     hcol = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
     e2e_steps = max(3, min(args.steps, 20))
 
+    # N = 1: the reference-facing call sequence — the host image is bound with useDoubleBuffer (the reference's
+    # default, TileRasterRendererCuda.h:88), so drawElements() itself copies a frame back on every call: frame k - 1
+    # travels to the host image on a second stream while frame k renders (CU:3899-3909).  N > 1: explicit read-back
+    # of the gathered frame on rank 0.
+    readback = "explicit copy of the gathered frame after the draw (rank 0)"
+    if world == 1:
+        r.bindFrameBuffer(hcol.numpy(), None, W, H, useDoubleBuffer=True)
+        readback = ("double-buffered, reference useDoubleBuffer semantics: every drawElements() copies one full RGBA32F frame "
+                    "(frame k-1) to the pinned host image on a second stream while frame k renders")
+
     def e2e_step():
         r.bindVertexBuffer(hvb, hvb.shape[0], hvb.shape[1] // 4)        # H2D (pinned, async)
         r.bindIndexBuffer(hib, hib.shape[0])                           # H2D
         r.clear()
         r.drawElements()
-        if sf:
-            sf.gather()
+        if world == 1:
+            r.synchronize()                                            # render stream + copy stream
+            return
+        sf.gather()
         if rank == 0:
             r.copyColorToHostAsync(hcol.data_ptr())                    # D2H of the step's result (pinned, async)
         torch.cuda.current_stream().synchronize()
@@ -331,7 +343,7 @@ def run_ours(args, cfg_name):
                                "frac": ab["frame"] / (ms_step * 1e-3) / 1e9 / peak},
             "e2e": {"value": ntri / (e2e_ms * 1e-3) / 1e6, "unit": "Mtris/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(hvb.numel() * 4 + hib.numel() * 4),
-                    "d2h_bytes_per_step": int(W * H * 16), "steps": e2e_steps},
+                    "d2h_bytes_per_step": int(W * H * 16), "steps": e2e_steps, "readback": readback},
             "clocks": clocks,
         }
     r.close()

@@ -51,8 +51,17 @@ struct iftrcuRenderer {
     // framebuffer
     int W = 0, H = 0;
     float4* dColor = nullptr; float* dDepth = nullptr;
-    DevBuf ownColor, ownDepth, primIds;
+    DevBuf ownColor, ownColor2, ownDepth, primIds;
     bool externalFB = false;
+    // useDoubleBuffer (TileRasterRendererCuda::bindFrameBuffer, CUHOST:46-63; CU:3893-3914): frame k renders into
+    // colour buffer k & 1 while frame k - 1 is copied to the host image on a second stream, so the host image lags
+    // one drawElements() behind; depth is single-buffered as in the reference
+    bool doubleBuffer = false;
+    int cur = 0;                          // colour buffer the next draw renders into
+    float4* lastColor = nullptr;          // colour buffer of the most recent frame (what the read-back verbs return)
+    cudaStream_t copyStream = nullptr;
+    cudaEvent_t evFrame[2] = {nullptr, nullptr}, evCopy[2] = {nullptr, nullptr};
+    bool framePending[2] = {false, false}, copyPending[2] = {false, false};
     float* hColor = nullptr; float* hDepth = nullptr;
     void* registeredHost = nullptr;
     void* peerColor = nullptr; void* peerDepth = nullptr;   // opened CUDA IPC mappings (peer framebuffer)
@@ -249,6 +258,10 @@ static int issue_draw(iftrcuRenderer* r, bool forceCheck) {
     }
     CUDA_TRY(ifr_launch_fill(p, s));
     if (ev) CUDA_TRY(cudaEventRecord(ev[4], s));
+    if (r->doubleBuffer && r->copyPending[r->cur]) {   // this buffer's previous frame is still on its way to the host
+        CUDA_TRY(cudaStreamWaitEvent(s, r->evCopy[r->cur], 0));
+        r->copyPending[r->cur] = false;
+    }
     CUDA_TRY(ifr_launch_tiles(p, r->fsId, s));
     if (ev) { CUDA_TRY(cudaEventRecord(ev[5], s)); r->profDraws++; }
     r->stats.kernel_launches += 3;
@@ -257,8 +270,24 @@ static int issue_draw(iftrcuRenderer* r, bool forceCheck) {
     r->pendingClear = false;
     r->haveDraw = true;
     r->stats.triangles_submitted = (uint64_t)p.ntri;
-    if (r->hColor && !r->externalFB)   // copy-back of the colour image, CU:3899-3909
+    if (r->doubleBuffer) {
+        // CU:3899-3909: the PREVIOUS frame travels to the host image on the copy stream while this one renders
+        const int k = r->cur, prev = 1 - k;
+        CUDA_TRY(cudaEventRecord(r->evFrame[k], s));
+        r->framePending[k] = true;
+        if (r->framePending[prev]) {
+            CUDA_TRY(cudaStreamWaitEvent(r->copyStream, r->evFrame[prev], 0));
+            const float4* src = prev ? (const float4*)r->ownColor2.p : (const float4*)r->ownColor.p;
+            CUDA_TRY(cudaMemcpyAsync(r->hColor, src, (size_t)r->W * r->H * 16, cudaMemcpyDeviceToHost, r->copyStream));
+            CUDA_TRY(cudaEventRecord(r->evCopy[prev], r->copyStream));
+            r->copyPending[prev] = true;
+        }
+        r->lastColor = r->dColor;
+        r->cur = prev;
+        r->dColor = prev ? (float4*)r->ownColor2.p : (float4*)r->ownColor.p;
+    } else if (r->hColor && !r->externalFB) {   // copy-back of the colour image, CU:3910-3914
         CUDA_TRY(cudaMemcpyAsync(r->hColor, r->dColor, (size_t)r->W * r->H * 16, cudaMemcpyDeviceToHost, s));
+    }
     return IFRIT_OK;
 }
 
@@ -269,18 +298,25 @@ static int flush_clear(iftrcuRenderer* r) {
     CUDA_TRY(ifr_launch_clear(p, r->stream));
     r->stats.kernel_launches += 1;
     r->pendingClear = false;
+    if (r->doubleBuffer) r->lastColor = r->dColor;   // a stand-alone clear is what the read-back verbs see next
     return IFRIT_OK;
 }
 
 static int sync_and_check(iftrcuRenderer* r) {
     CUDA_TRY(cudaStreamSynchronize(r->stream));
+    if (r->doubleBuffer) CUDA_TRY(cudaStreamSynchronize(r->copyStream));
     if (r->haveDraw && r->hCounters[3]) {
         // the queue sized from an earlier frame was too small: grow it and re-issue the draw
         r->stats.queue_overflow = 1;
         r->pendingClear = r->lastDrawCleared;
+        if (r->doubleBuffer) {   // same frame, same colour buffer
+            r->cur = 1 - r->cur;
+            r->dColor = r->cur ? (float4*)r->ownColor2.p : (float4*)r->ownColor.p;
+        }
         int rc = issue_draw(r, true);
         if (rc) return rc;
         CUDA_TRY(cudaStreamSynchronize(r->stream));
+        if (r->doubleBuffer) CUDA_TRY(cudaStreamSynchronize(r->copyStream));
     }
     if (r->haveDraw) {
         r->stats.triangles_assembled = r->hCounters[0];
@@ -325,7 +361,9 @@ int iftrcuDestroyInstance(iftrcuRenderer* h) {
     cudaStreamSynchronize(r->stream);
     if (r->registeredHost) cudaHostUnregister(r->registeredHost);
     close_peer(r);
-    DevBuf* bufs[] = {&r->ownColor, &r->ownDepth, &r->primIds, &r->ownVB, &r->ownIB, &r->pos, &r->vary, &r->rec, &r->clipBary,
+    if (r->copyStream) { cudaStreamSynchronize(r->copyStream); cudaStreamDestroy(r->copyStream); }
+    for (int i = 0; i < 2; i++) { if (r->evFrame[i]) cudaEventDestroy(r->evFrame[i]); if (r->evCopy[i]) cudaEventDestroy(r->evCopy[i]); }
+    DevBuf* bufs[] = {&r->ownColor, &r->ownColor2, &r->ownDepth, &r->primIds, &r->ownVB, &r->ownIB, &r->pos, &r->vary, &r->rec, &r->clipBary,
                       &r->scanPartial, &r->tileBox, &r->fan1List, &r->heavyBits, &r->tileCount, &r->tileStart, &r->tileCursor, &r->queue, &r->bigQueue, &r->counters};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < IFR_MAX_TEX; i++) { destroy_tex_objects(r, i); r->texMem[i].release(); }
@@ -348,13 +386,31 @@ int iftrcuSetStream(iftrcuRenderer* h, void* cudaStream) {
     return IFRIT_OK;
 }
 
-int iftrcuBindFrameBuffer(iftrcuRenderer* h, float* hostColor, float* hostDepth, int width, int height, int) {
+static void reset_double_buffer(iftrcuRenderer* r) {
+    if (r->copyStream) cudaStreamSynchronize(r->copyStream);
+    r->doubleBuffer = false; r->cur = 0; r->lastColor = nullptr;
+    r->framePending[0] = r->framePending[1] = r->copyPending[0] = r->copyPending[1] = false;
+}
+
+int iftrcuBindFrameBuffer(iftrcuRenderer* h, float* hostColor, float* hostDepth, int width, int height, int useDoubleBuffer) {
     R_CHECK(h);
     if (width <= 0 || height <= 0 || width > 65535 * 16 || height > 65535 * 16) return r->fail(IFRIT_ERR_INVALID, "bindFrameBuffer", "bad size");
     CUDA_TRY(cudaStreamSynchronize(r->stream));
     close_peer(r);
+    reset_double_buffer(r);
     CUDA_TRY(r->ownColor.ensure((size_t)width * height * 16));
     CUDA_TRY(r->ownDepth.ensure((size_t)width * height * 4));
+    if (useDoubleBuffer && hostColor) {
+        CUDA_TRY(r->ownColor2.ensure((size_t)width * height * 16));
+        if (!r->copyStream) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&r->copyStream, cudaStreamNonBlocking));
+            for (int i = 0; i < 2; i++) {
+                CUDA_TRY(cudaEventCreateWithFlags(&r->evFrame[i], cudaEventDisableTiming));
+                CUDA_TRY(cudaEventCreateWithFlags(&r->evCopy[i], cudaEventDisableTiming));
+            }
+        }
+        r->doubleBuffer = true;
+    }
     r->dColor = (float4*)r->ownColor.p; r->dDepth = (float*)r->ownDepth.p;
     r->externalFB = false;
     if (r->registeredHost) { cudaHostUnregister(r->registeredHost); r->registeredHost = nullptr; }
@@ -364,6 +420,7 @@ int iftrcuBindFrameBuffer(iftrcuRenderer* h, float* hostColor, float* hostDepth,
         if (cudaHostRegister(hostColor, (size_t)width * height * 16, cudaHostRegisterDefault) == cudaSuccess) r->registeredHost = hostColor;
         else cudaGetLastError();
         CUDA_TRY(cudaMemcpyAsync(r->dColor, hostColor, (size_t)width * height * 16, cudaMemcpyHostToDevice, r->stream));
+        if (r->doubleBuffer) CUDA_TRY(cudaMemcpyAsync(r->ownColor2.p, hostColor, (size_t)width * height * 16, cudaMemcpyHostToDevice, r->stream));
     }
     if (hostDepth) CUDA_TRY(cudaMemcpyAsync(r->dDepth, hostDepth, (size_t)width * height * 4, cudaMemcpyHostToDevice, r->stream));
     if (r->W != width || r->H != height) r->queueChecked = false;
@@ -389,6 +446,7 @@ int iftrcuBindPeerFrameBuffer(iftrcuRenderer* h, const void* handle128, int widt
     if (!handle128 || width <= 0 || height <= 0) return r->fail(IFRIT_ERR_INVALID, "bindPeerFrameBuffer", "bad argument");
     CUDA_TRY(cudaStreamSynchronize(r->stream));
     close_peer(r);
+    reset_double_buffer(r);
     cudaIpcMemHandle_t hc, hd;
     memcpy(&hc, handle128, 64); memcpy(&hd, (const char*)handle128 + 64, 64);
     CUDA_TRY(cudaIpcOpenMemHandle(&r->peerColor, hc, cudaIpcMemLazyEnablePeerAccess));
@@ -405,6 +463,7 @@ int iftrcuBindFrameBufferDevice(iftrcuRenderer* h, float* devColor, float* devDe
     if (!devColor || !devDepth || width <= 0 || height <= 0) return r->fail(IFRIT_ERR_INVALID, "bindFrameBufferDevice", "bad argument");
     CUDA_TRY(cudaStreamSynchronize(r->stream));
     close_peer(r);
+    reset_double_buffer(r);
     if (r->registeredHost) { cudaHostUnregister(r->registeredHost); r->registeredHost = nullptr; }
     r->dColor = (float4*)devColor; r->dDepth = devDepth; r->externalFB = true; r->hColor = nullptr; r->hDepth = nullptr;
     if (r->W != width || r->H != height) r->queueChecked = false;
@@ -693,7 +752,7 @@ int iftrcuReadColor(iftrcuRenderer* h, float* dst) {
     if (!dst || !r->dColor) return r->fail(IFRIT_ERR_INVALID, "ReadColor", "bad argument");
     int rc = flush_clear(r); if (rc) return rc;
     rc = sync_and_check(r); if (rc) return rc;
-    CUDA_TRY(cudaMemcpy(dst, r->dColor, (size_t)r->W * r->H * 16, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(dst, (r->doubleBuffer && r->lastColor) ? r->lastColor : r->dColor, (size_t)r->W * r->H * 16, cudaMemcpyDeviceToHost));
     return IFRIT_OK;
 }
 int iftrcuReadDepth(iftrcuRenderer* h, float* dst) {
@@ -714,10 +773,10 @@ int iftrcuReadPrimitiveIds(iftrcuRenderer* h, int32_t* dst) {
 int iftrcuCopyColorToHostAsync(iftrcuRenderer* h, void* hostDst) {
     R_CHECK(h);
     if (!hostDst || !r->dColor) return IFRIT_ERR_INVALID;
-    CUDA_TRY(cudaMemcpyAsync(hostDst, r->dColor, (size_t)r->W * r->H * 16, cudaMemcpyDeviceToHost, r->stream));
+    CUDA_TRY(cudaMemcpyAsync(hostDst, (r->doubleBuffer && r->lastColor) ? r->lastColor : r->dColor, (size_t)r->W * r->H * 16, cudaMemcpyDeviceToHost, r->stream));
     return IFRIT_OK;
 }
-int iftrcuGetDeviceColorPtr(iftrcuRenderer* h, void** out) { R_CHECK(h); if (!out) return IFRIT_ERR_INVALID; *out = r->dColor; return IFRIT_OK; }
+int iftrcuGetDeviceColorPtr(iftrcuRenderer* h, void** out) { R_CHECK(h); if (!out) return IFRIT_ERR_INVALID; *out = (r->doubleBuffer && r->lastColor) ? r->lastColor : r->dColor; return IFRIT_OK; }
 int iftrcuGetDeviceDepthPtr(iftrcuRenderer* h, void** out) { R_CHECK(h); if (!out) return IFRIT_ERR_INVALID; *out = r->dDepth; return IFRIT_OK; }
 int iftrcuGetStats(iftrcuRenderer* h, iftrcuStats* out) {
     R_CHECK(h);

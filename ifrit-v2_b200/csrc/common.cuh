@@ -41,7 +41,8 @@ struct __align__(16) TriS {
     float ar, z0, z1, z2;
     int pad[2];                  // pad[0]: coarse raster, bit per 8x4-pixel block of the tile: 0-7 may hold a covered
                                  // sample, 8-15 covered at every sample; pad[1]: Hi-Z bound (float bits), the most
-                                 // optimistic depth of the triangle inside its tile-local box
+                                 // optimistic depth of the triangle inside its tile-local box (bits 8-15 and
+                                 // pad[1] are filled in by the tile kernel for deep queues, tri_setup.cuh)
 };
 
 #define IFR_MAX_MIPS 16

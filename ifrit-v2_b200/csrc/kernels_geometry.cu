@@ -153,7 +153,8 @@ __device__ __forceinline__ void finish_triangle(const DrawParams& p, const ClipV
     px0 = max(px0, 0); py0 = max(py0, 0);
     px1 = min(px1, p.W - 1); py1 = min(py1, p.H - 1);
     if (px0 > px1 || py0 > py1) return;
-    if ((long long)(px1 - px0 + 1) * (py1 - py0 + 1) <= IFR_SMALL_AREA) a.flags |= IFR_FLAG_SMALL;
+    const long long boxArea = (long long)(px1 - px0 + 1) * (py1 - py0 + 1);
+    if (boxArea <= IFR_SMALL_AREA) a.flags |= IFR_FLAG_SMALL;
     a.tx0 = px0 >> 4; a.tx1 = px1 >> 4; a.ty0 = py0 >> 4; a.ty1 = py1 >> 4;
     a.ok = true;
 }
@@ -261,10 +262,8 @@ __device__ __forceinline__ void emit_one(const DrawParams& p, const RecRegs& rr,
     } else {
         TriS s;
         int bx0, bx1, by0, by1;
-        // deep queues only: the Hi-Z bound pays for itself when the tile kernel has many triangles to skip
-        const uint32_t* bs = p.tileStart + (p.tilesX * p.tilesY + 1) + ty * p.tilesX + tx;
-        const bool wantZ = bs[1] - bs[0] >= IFR_HIZ_MIN_QUEUE;
-        if (!setup_from_rec<true>(p, rr, slot, tx, ty, s, bx0, bx1, by0, by1, wantZ)) s.box = 0x00ff00ffu;   // empty: rows 255..0
+        const bool ok = setup_from_rec<true>(p, rr, slot, tx, ty, s, bx0, bx1, by0, by1);
+        if (!ok) s.box = 0x00ff00ffu;   // empty: rows 255..0
         int4* dst = reinterpret_cast<int4*>(p.bigQueue + pos);
         const int4* src = reinterpret_cast<const int4*>(&s);
 #pragma unroll
@@ -340,8 +339,11 @@ __device__ __forceinline__ void store_record(const DrawParams& p, uint32_t slot,
 }
 
 // pass 1: one thread per input triangle — clip, snap, cull, store the 64-byte record, count tiles
+#ifndef IFR_SETUP_MINB
+#define IFR_SETUP_MINB 3
+#endif
 template <int VSMODE>
-__global__ void __launch_bounds__(256) setup_count_kernel(const __grid_constant__ DrawParams p) {
+__global__ void __launch_bounds__(256, IFR_SETUP_MINB) setup_count_kernel(const __grid_constant__ DrawParams p) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     Assembled a[2];
     a[0].ok = a[1].ok = false;
@@ -422,7 +424,10 @@ __device__ __forceinline__ void fill_heavy_slot(const DrawParams& p, bool has, u
     bin_triangle<true, IFR_FILL_GROUP>(p, has, slot, big, tx0, tx1, ty0, ty1, e, sub);
 }
 
-__global__ void __launch_bounds__(128) fill_heavy_kernel(const __grid_constant__ DrawParams p, const int wordsPerWarp, const int split) {
+#ifndef IFR_FILL_MINB
+#define IFR_FILL_MINB 4
+#endif
+__global__ void __launch_bounds__(128, IFR_FILL_MINB) fill_heavy_kernel(const __grid_constant__ DrawParams p, const int wordsPerWarp, const int split) {
     if (p.counters[3]) return;
     const unsigned long long nfan1 = p.counters[4];
     const long long nwords = (p.ntri + 31) / 32;

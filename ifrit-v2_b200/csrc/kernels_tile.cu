@@ -262,8 +262,99 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     } while (!done);
 }
 
+// ---- big triangles: setups precomputed by the fill pass arrive by TMA bulk copy (double buffered); every thread
+//      tests its own pixel against broadcast LDS.128 words, warps run independently.
+// HIZ: hierarchical early-Z, one level above the pixel: wfar = the worst (largest) key depth word any sample of this
+// warp's 8x4 block currently holds.  A triangle whose most optimistic depth inside the tile (TriS pad[1], from the fill
+// pass) maps above it cannot win a single sample of the block and is skipped by the whole warp.  Deep queues and
+// ordered compare ops only; results are unchanged (the reference has no Hi-Z: curTileHierZ is an unused field,
+// TileRasterWorker.h:80).
+template <int S, bool HIZ>
+__device__ __forceinline__ void big_loop(const DrawParams& p, const KeyMode& km, unsigned long long* keys, TriS (*bigBuf)[IFR_BIG_CHUNK],
+                                         uint64_t* mbar, const TriS* bigSrc, uint32_t nBig, int tid, int wrp, int lx, int ly,
+                                         bool scis, float d0, unsigned long long& best) {
+    const int ci = 16 * lx, cj = 16 * ly;
+    uint32_t wfar = 0xffffffffu;
+    bool dirty = HIZ;
+    const uint32_t nchunks = (nBig + IFR_BIG_CHUNK - 1) / IFR_BIG_CHUNK;
+    for (uint32_t c = 0; c < nchunks; c++) {
+        if (tid == 0 && c + 1 < nchunks) {
+            const uint32_t cnt1 = min(nBig - (c + 1) * IFR_BIG_CHUNK, (uint32_t)IFR_BIG_CHUNK);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            bulk_load(bigBuf[(c + 1) & 1], bigSrc + (size_t)(c + 1) * IFR_BIG_CHUNK, cnt1 * (uint32_t)sizeof(TriS), &mbar[(c + 1) & 1]);
+        }
+        mbar_wait(&mbar[c & 1], (c >> 1) & 1);
+        const uint32_t cnt = min(nBig - c * IFR_BIG_CHUNK, (uint32_t)IFR_BIG_CHUNK);
+        if (HIZ) {
+            // one thread per staged entry: trivial-accept blocks + depth bound, written back into the staged copy
+            if ((uint32_t)tid < cnt)
+                setup_hiz(&bigBuf[c & 1][tid], p.sampMinX, p.sampMaxX, p.sampMinY, p.sampMaxY, km.xhi ? 1 : 0);
+            __syncthreads();
+        }
+        const int4* t4 = reinterpret_cast<const int4*>(bigBuf[c & 1]);
+        for (uint32_t b = 0; b < cnt; b++, t4 += 6) {
+            if (HIZ && dirty) {
+                // refresh the block's far bound (warp-convergent: every reject above / below is warp-uniform)
+                uint32_t mine;
+                if (S == 1) mine = (uint32_t)(best >> 32);
+                else {
+                    mine = 0;
+#pragma unroll
+                    for (int sm = 0; sm < S; sm++) mine = max(mine, (uint32_t)(keys[sm * IFR_TILE_PIX + tid] >> 32));
+                }
+                wfar = __reduce_max_sync(0xffffffffu, mine);
+                dirty = false;
+            }
+            // warp-uniform coarse reject: the fill pass rasterised the triangle against the tile's 8x4 blocks
+            const uint2 cz = *reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(t4) + 88);
+            if (!((cz.x >> wrp) & 1)) continue;
+            if (HIZ && (mono(__uint_as_float(cz.y)) ^ km.xhi) > wfar) continue;
+            const int4 A = t4[0];
+            const int4 B = t4[1], C = t4[2];
+            const int dX[3] = {A.x, A.y, A.z}, dY[3] = {B.x, B.y, B.z}, T[3] = {C.x, C.y, C.z};
+            const uint32_t flags = (uint32_t)C.w;
+            uint32_t m = 0;
+            bool upd = false;
+            if (HIZ && ((cz.x >> (8 + wrp)) & 1)) {
+                if (scis) m = (1u << S) - 1u;          // trivial accept: every sample of the block
+            } else if (!(flags & IFR_FLAG_WIDE)) {
+                if (scis) m = coverage<S>(p, dX, dY, T, nullptr, 0, ci, cj);
+            }
+            if (m || (flags & IFR_FLAG_WIDE)) {
+                const int4 D = t4[3], E = t4[4];
+                const long long E0[3] = {(long long)(((unsigned long long)(uint32_t)D.y << 32) | (uint32_t)D.x),
+                                         (long long)(((unsigned long long)(uint32_t)D.w << 32) | (uint32_t)D.z),
+                                         (long long)(((unsigned long long)(uint32_t)E.y << 32) | (uint32_t)E.x)};
+                if (!m && scis) m = coverage<S>(p, dX, dY, T, E0, 1, ci, cj);
+                if (m) {
+                    const float2 Zr = *reinterpret_cast<const float2*>(t4 + 5);
+                    const float d = depth_at(dX, dY, E0, flags, __int_as_float(E.z), __int_as_float(E.w), Zr.x, Zr.y, lx, ly);
+                    unsigned long long k;
+                    if (key_make(km, d, d0, (uint32_t)B.w, k)) {
+                        if (S == 1) {
+                            if (k < best) { best = k; upd = true; }
+                        } else {
+#pragma unroll
+                            for (int sm = 0; sm < S; sm++)
+                                if (((m >> sm) & 1) && k < keys[sm * IFR_TILE_PIX + tid]) { keys[sm * IFR_TILE_PIX + tid] = k; upd = true; }
+                        }
+                    }
+                }
+            }
+            if (HIZ) dirty = __any_sync(0xffffffffu, upd);
+        }
+        if (c + 2 < nchunks) __syncthreads();   // buffer (c & 1) is refilled at the top of iteration c + 1
+    }
+}
+
+#ifndef IFR_MINB1
+#define IFR_MINB1 6
+#endif
+// resident CTAs per SM the register budget is cut for.  Measured (profiles/r01d_ab.txt): the 1x textured kernels are
+// latency bound on the texture fetches — 6 CTAs (40 registers, some spills) beat 4 by 4 %; the plain-varying 1x
+// kernels (small-triangle soup) lose 20 % with more than 4; the multisampled variants keep 64 registers.
 template <int FS, int S>
-__global__ void __launch_bounds__(256, 4) tile_kernel(const __grid_constant__ DrawParams p) {
+__global__ void __launch_bounds__(256, (S == 1 && FsTraits<FS>::needsDerivs) ? IFR_MINB1 : 4) tile_kernel(const __grid_constant__ DrawParams p) {
     extern __shared__ unsigned long long keys[];        // [S][256], index = owning thread
     __shared__ __align__(128) TriS bigBuf[2][IFR_BIG_CHUNK];
     __shared__ __align__(8) uint64_t mbar[2];
@@ -348,79 +439,14 @@ __global__ void __launch_bounds__(256, 4) tile_kernel(const __grid_constant__ Dr
         __syncthreads();
     }
 
-    // ---- big triangles: setups precomputed by the fill pass arrive by TMA bulk copy (double buffered);
-    //      every thread tests its own pixel against broadcast LDS.128 words, warps run independently ------
     if (nBig) {
-        const int ci = 16 * lx, cj = 16 * ly;
-        // Hierarchical early-Z, one level above the pixel: wfar = the worst (largest) key depth word any sample of
-        // this warp's 8x4 block currently holds.  A triangle whose most optimistic depth inside the tile (TriS
-        // pad[1], from the fill pass) maps above it cannot win a single sample of the block and is skipped by the
-        // whole warp.  Ordered compare ops only; results are unchanged (the reference has no Hi-Z: curTileHierZ is
-        // an unused field, TileRasterWorker.h:80).
-        const bool hiz = km.ordered && nBig >= IFR_HIZ_MIN_QUEUE;
         if (S == 1 && nSmall) { const unsigned long long ks = keys[tid]; if (ks < best) best = ks; }
-        uint32_t wfar = 0xffffffffu;
-        bool dirty = hiz;
-        const uint32_t nchunks = (nBig + IFR_BIG_CHUNK - 1) / IFR_BIG_CHUNK;
-        for (uint32_t c = 0; c < nchunks; c++) {
-            if (tid == 0 && c + 1 < nchunks) {
-                const uint32_t cnt1 = min(nBig - (c + 1) * IFR_BIG_CHUNK, (uint32_t)IFR_BIG_CHUNK);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                bulk_load(bigBuf[(c + 1) & 1], bigSrc + (size_t)(c + 1) * IFR_BIG_CHUNK, cnt1 * (uint32_t)sizeof(TriS), &mbar[(c + 1) & 1]);
-            }
-            mbar_wait(&mbar[c & 1], (c >> 1) & 1);
-            const uint32_t cnt = min(nBig - c * IFR_BIG_CHUNK, (uint32_t)IFR_BIG_CHUNK);
-            const int4* t4 = reinterpret_cast<const int4*>(bigBuf[c & 1]);
-            for (uint32_t b = 0; b < cnt; b++, t4 += 6) {
-                if (dirty) {
-                    // refresh the block's far bound (warp-convergent: every reject above / below is warp-uniform)
-                    uint32_t mine;
-                    if (S == 1) mine = (uint32_t)(best >> 32);
-                    else {
-                        mine = 0;
-#pragma unroll
-                        for (int sm = 0; sm < S; sm++) mine = max(mine, (uint32_t)(keys[sm * IFR_TILE_PIX + tid] >> 32));
-                    }
-                    wfar = __reduce_max_sync(0xffffffffu, mine);
-                    dirty = false;
-                }
-                // warp-uniform coarse reject: the fill pass rasterised the triangle against the tile's 8x4 blocks
-                const uint2 cz = *reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(t4) + 88);
-                if (!((cz.x >> wrp) & 1)) continue;
-                if (hiz && (mono(__uint_as_float(cz.y)) ^ km.xhi) > wfar) continue;
-                const int4 A = t4[0];
-                const int4 B = t4[1], C = t4[2];
-                const int dX[3] = {A.x, A.y, A.z}, dY[3] = {B.x, B.y, B.z}, T[3] = {C.x, C.y, C.z};
-                const uint32_t flags = (uint32_t)C.w;
-                const int4 D = t4[3], E = t4[4];
-                const long long E0[3] = {(long long)(((unsigned long long)(uint32_t)D.y << 32) | (uint32_t)D.x),
-                                         (long long)(((unsigned long long)(uint32_t)D.w << 32) | (uint32_t)D.z),
-                                         (long long)(((unsigned long long)(uint32_t)E.y << 32) | (uint32_t)E.x)};
-                uint32_t m = 0;
-                if (scis) {
-                    if ((cz.x >> (8 + wrp)) & 1) m = (1u << S) - 1u;          // trivial accept: every sample of the block
-                    else if (!(flags & IFR_FLAG_WIDE)) m = coverage<S>(p, dX, dY, T, nullptr, 0, ci, cj);
-                    else m = coverage<S>(p, dX, dY, T, E0, 1, ci, cj);
-                }
-                bool upd = false;
-                if (m) {
-                    const float2 Zr = *reinterpret_cast<const float2*>(t4 + 5);
-                    const float d = depth_at(dX, dY, E0, flags, __int_as_float(E.z), __int_as_float(E.w), Zr.x, Zr.y, lx, ly);
-                    unsigned long long k;
-                    if (key_make(km, d, d0, (uint32_t)B.w, k)) {
-                        if (S == 1) {
-                            if (k < best) { best = k; upd = true; }
-                        } else {
-#pragma unroll
-                            for (int sm = 0; sm < S; sm++)
-                                if (((m >> sm) & 1) && k < keys[sm * IFR_TILE_PIX + tid]) { keys[sm * IFR_TILE_PIX + tid] = k; upd = true; }
-                        }
-                    }
-                }
-                if (hiz) dirty = __any_sync(0xffffffffu, upd);
-            }
-            if (c + 2 < nchunks) __syncthreads();   // buffer (c & 1) is refilled at the top of iteration c + 1
-        }
+#ifndef IFR_NO_HIZ
+        if (km.ordered && nBig >= IFR_HIZ_MIN_QUEUE)
+            big_loop<S, true>(p, km, keys, bigBuf, mbar, bigSrc, nBig, tid, wrp, lx, ly, scis, d0, best);
+        else
+#endif
+            big_loop<S, false>(p, km, keys, bigBuf, mbar, bigSrc, nBig, tid, wrp, lx, ly, scis, d0, best);
     }
 
     // ---- quad shading + resolve -----------------------------------------------------------------
@@ -536,8 +562,13 @@ cudaError_t ifr_launch_tiles(const DrawParams& p, int fsId, cudaStream_t s) {
         case IFRIT_FS_VARYING0: return launch_fs<IFRIT_FS_VARYING0>(p, s);
         case IFRIT_FS_NORMAL_COLOR: return launch_fs<IFRIT_FS_NORMAL_COLOR>(p, s);
         case IFRIT_FS_PRIM_ID: return launch_fs<IFRIT_FS_PRIM_ID>(p, s);
+#ifdef IFR_NO_FAST
+        case IFRIT_FS_TEXTURED: return launch_fs<IFRIT_FS_TEXTURED>(p, s);
+        case IFRIT_FS_TEXTURED_LOD0: return launch_fs<IFRIT_FS_TEXTURED_LOD0>(p, s);
+#else
         case IFRIT_FS_TEXTURED: return p.hwFilter ? launch_fs<IFRIT_FS_TEXTURED_FAST>(p, s) : launch_fs<IFRIT_FS_TEXTURED>(p, s);
         case IFRIT_FS_TEXTURED_LOD0: return p.hwFilter ? launch_fs<IFRIT_FS_TEXTURED_LOD0_FAST>(p, s) : launch_fs<IFRIT_FS_TEXTURED_LOD0>(p, s);
+#endif
         case IFRIT_FS_SKYBOX: return launch_fs<IFRIT_FS_SKYBOX>(p, s);
         case IFRIT_FS_DERIV_VIS: return launch_fs<IFRIT_FS_DERIV_VIS>(p, s);
         default: return cudaErrorInvalidValue;

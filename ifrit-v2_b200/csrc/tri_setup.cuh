@@ -20,11 +20,59 @@ __device__ __forceinline__ void load_rec(const DrawParams& p, uint32_t slot, Rec
     rr.flags = (uint32_t)w3.y;
 }
 
-#define IFR_HIZ_MIN_QUEUE 12   // tiles with fewer big-queue entries skip the Hi-Z bound (fill pass) and the reject (tile kernel)
+// Hi-Z extras of one (triangle, tile) pair: trivial-accept blocks (mask bits 8-15) and the most optimistic depth
+// inside the tile-local box.  Computed by the tile kernel itself, on the staged queue entries (shared memory) of
+// tiles whose big queue is deep enough for the reject to pay off — the fill pass and shallow tiles never see it.
+//
+// The depth the tile kernel computes, F(x, y) = fma chain of z_i * (float(E_i) * ar), follows the exact plane
+// P = sum z_i E_i / d within eps * M, M = sum |z_i| |E_i / d| (convex), eps < 1.75 * 2^-22.  P is affine, so over
+// the box F >= min_corners F - 2 eps max_corners M; the margin below is twice that.
+__device__ __forceinline__ void setup_hiz(TriS* sp, int sampMinX, int sampMaxX, int sampMinY, int sampMaxY, int greater) {
+    TriS& s = *sp;
+    const int bx0 = s.box & 0xff, bx1 = (s.box >> 8) & 0xff, by0 = (s.box >> 16) & 0xff, by1 = s.box >> 24;
+    uint32_t mask = (uint32_t)s.pad[0];
+    if (!(s.flags & IFR_FLAG_WIDE)) {
+        const int sLoX = sampMinX >> 4, sHiX = sampMaxX >> 4, sLoY = sampMinY >> 4, sHiY = sampMaxY >> 4;
+#pragma unroll
+        for (int blk = 0; blk < 8; blk++) {
+            if (!((mask >> blk) & 1)) continue;
+            const int x0 = (blk & 1) * 8, y0 = (blk >> 1) * 4;
+            const int iLo = 16 * x0 + sLoX, iHi = 16 * (x0 + 7) + sHiX, jLo = 16 * y0 + sLoY, jHi = 16 * (y0 + 3) + sHiY;
+            bool full = true;
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                const int worst = s.dX[i] * (s.dX[i] > 0 ? jLo : jHi) - s.dY[i] * (s.dY[i] > 0 ? iHi : iLo);
+                full = full && worst >= s.T[i];
+            }
+            mask |= (uint32_t)full << (8 + blk);
+        }
+    }
+    float lo = 3.0e38f, hi = -3.0e38f, mag = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const int lx = (c & 1) ? bx1 : bx0, ly = (c & 2) ? by1 : by0;
+        float beta[3];
+#pragma unroll
+        for (int e = 0; e < 3; e++) {
+            const long long Ec = s.E0[e] + 256 * ((long long)s.dX[e] * ly - (long long)s.dY[e] * lx);
+            beta[e] = __fmul_rn((float)Ec, s.ar);
+        }
+        const float d = fmaf(s.z2, beta[2], fmaf(s.z1, beta[1], __fmul_rn(s.z0, beta[0])));
+        const float m = fabsf(s.z0 * beta[0]) + fabsf(s.z1 * beta[1]) + fabsf(s.z2 * beta[2]);
+        lo = fminf(lo, d); hi = fmaxf(hi, d); mag = fmaxf(mag, m);
+    }
+    const float margin = mag * 1.9073486e-6f + 1e-30f;   // 2^-19 M
+    float zbound = greater ? hi + margin : lo - margin;
+    if (!(zbound == zbound)) zbound = greater ? 3.0e38f : -3.0e38f;   // NaN depth: never reject
+    s.pad[0] = (int)mask;
+    s.pad[1] = __float_as_int(zbound);
+}
+
+#define IFR_HIZ_MIN_QUEUE 12   // tiles with fewer big-queue entries run the tile kernel's big loop without the Hi-Z reject
 
 template <bool COARSE>
 __device__ __forceinline__ bool setup_from_rec(const DrawParams& p, const RecRegs& rr, uint32_t slot, int tileX, int tileY,
-                                               TriS& s, int& bx0, int& bx1, int& by0, int& by1, bool wantZ = false) {
+                                               TriS& s, int& bx0, int& bx1, int& by0, int& by1) {
     const int* X = rr.X; const int* Y = rr.Y;
     s.slot = slot;
     s.ar = rr.ar;
@@ -65,48 +113,21 @@ __device__ __forceinline__ bool setup_from_rec(const DrawParams& p, const RecReg
         for (int blk = 0; blk < 8; blk++) {
             const int x0 = (blk & 1) * 8, y0 = (blk >> 1) * 4;
             if (x0 + 7 < bx0 || x0 > bx1 || y0 + 3 < by0 || y0 > by1) continue;
-            bool may = true, full = false;
+            bool may = true;
             if (!(rr.flags & IFR_FLAG_WIDE)) {
                 const int iLo = 16 * x0 + sLoX, iHi = 16 * (x0 + 7) + sHiX, jLo = 16 * y0 + sLoY, jHi = 16 * (y0 + 3) + sHiY;
-                full = true;
 #pragma unroll
                 for (int i = 0; i < 3; i++) {
                     const int best = s.dX[i] * (s.dX[i] > 0 ? jHi : jLo) - s.dY[i] * (s.dY[i] > 0 ? iLo : iHi);
-                    const int worst = s.dX[i] * (s.dX[i] > 0 ? jLo : jHi) - s.dY[i] * (s.dY[i] > 0 ? iHi : iLo);
                     may = may && best >= s.T[i];
-                    full = full && worst >= s.T[i];
                 }
             }
-            mask |= ((uint32_t)may << blk) | ((uint32_t)(may && full) << (8 + blk));
+            mask |= (uint32_t)may << blk;
         }
     }
-    // Hierarchical Z: the most optimistic depth this triangle can produce at any pixel of its tile-local box.
-    // The depth the tile kernel computes, F(x, y) = fma chain of z_i * (float(E_i) * ar), follows the exact
-    // plane P = sum z_i E_i / d within eps * M, M = sum |z_i| |E_i / d| (convex), eps < 1.75 * 2^-22.  P is
-    // affine, so over the box F >= min_corners F - 2 eps max_corners M; the margin below is twice that.
     const bool greater = p.depthFunc == IF_COMPARE_OP_GREATER || p.depthFunc == IF_COMPARE_OP_GREATER_OR_EQUAL;
-    float zbound = greater ? 3.0e38f : -3.0e38f;   // "never reject" unless computed
-    if (COARSE && ok && wantZ) {
-        float lo = 3.0e38f, hi = -3.0e38f, mag = 0.0f;
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            const int lx = (c & 1) ? bx1 : bx0, ly = (c & 2) ? by1 : by0;
-            float beta[3];
-#pragma unroll
-            for (int e = 0; e < 3; e++) {
-                const long long Ec = s.E0[e] + 256 * ((long long)s.dX[e] * ly - (long long)s.dY[e] * lx);
-                beta[e] = __fmul_rn((float)Ec, rr.ar);
-            }
-            const float d = fmaf(rr.Z[2], beta[2], fmaf(rr.Z[1], beta[1], __fmul_rn(rr.Z[0], beta[0])));
-            const float m = fabsf(rr.Z[0] * beta[0]) + fabsf(rr.Z[1] * beta[1]) + fabsf(rr.Z[2] * beta[2]);
-            lo = fminf(lo, d); hi = fmaxf(hi, d); mag = fmaxf(mag, m);
-        }
-        const float margin = mag * 1.9073486e-6f + 1e-30f;   // 2^-19 M
-        zbound = greater ? hi + margin : lo - margin;
-        if (!(zbound == zbound)) zbound = greater ? 3.0e38f : -3.0e38f;   // NaN depth: never reject
-    }
-    s.pad[1] = __float_as_int(zbound);
     s.pad[0] = (int)mask;
+    s.pad[1] = __float_as_int(greater ? 3.0e38f : -3.0e38f);   // "never reject" unless setup_hiz computes a bound
     return ok;
 }
 

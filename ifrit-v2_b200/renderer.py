@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libifrit_b200.so")
+# IFRIT_B200_LIB: developer override used by tools/gpu_ab.sh to time build variants side by side
+LIB_PATH = os.environ.get("IFRIT_B200_LIB") or os.path.join(_HERE, "lib", "libifrit_b200.so")
 
 # enums (engine/base/Constants.h:23-96)
 IF_CULL_MODE_NONE, IF_CULL_MODE_FRONT, IF_CULL_MODE_BACK, IF_CULL_MODE_FRONT_AND_BACK = 0, 1, 2, 3
@@ -195,8 +196,11 @@ class TileRasterRendererCuda:
         v = C.c_void_p(-1) if cuda_stream_ptr is None else C.c_void_p(cuda_stream_ptr)
         self._ck(self._lib.iftrcuSetStream(self._h, v))
 
-    def bindFrameBuffer(self, color, depth, width=None, height=None, useDoubleBuffer=True):
-        """color: host float32 [H,W,4] (ImageF32 RGBA) or None; depth: host float32 [H,W] or None."""
+    def bindFrameBuffer(self, color, depth, width=None, height=None, useDoubleBuffer=False):
+        """color: host float32 [H,W,4] (ImageF32 RGBA) or None; depth: host float32 [H,W] or None.
+        useDoubleBuffer (reference default: True, TileRasterRendererCuda.h:88): frame k renders while frame k - 1 is
+        copied into `color` on a second stream, i.e. the host image lags one drawElements() behind.  The mirror
+        defaults to False so that draw -> synchronize -> look at `color` shows the frame just drawn."""
         if width is None:
             height, width = (color.shape[0], color.shape[1]) if color is not None else depth.shape[:2]
         self._keep["fb"] = (color, depth)

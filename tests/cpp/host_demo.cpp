@@ -17,7 +17,7 @@ int main() {
     try {
         TileRasterRendererCuda renderer(0);
         renderer.Init();
-        renderer.bindFrameBuffer(color.data(), depth.data(), W, H);
+        renderer.bindFrameBuffer(color.data(), depth.data(), W, H, /*useDoubleBuffer=*/false);
         renderer.bindVertexBuffer(vb.data(), 3, 2);
         renderer.bindIndexBuffer(ib);
         renderer.bindVertexShader("passthrough", 1);

@@ -79,6 +79,30 @@ def test_hierarchical_z_heavy_overdraw(r, func, msaa):
     compare(o2, g2, exact_color=True)
 
 
+def test_double_buffered_readback_lags_one_frame(gpu_renderer_factory):
+    """useDoubleBuffer (CUHOST:46-63, CU:3899-3909): drawElements() k copies frame k - 1 into the bound host image on
+    a second stream while frame k renders; the read-back verbs return the frame just drawn."""
+    from ifrit_v2_b200 import renderer as R
+    W, H = 160, 96
+    r2 = gpu_renderer_factory()
+    host = np.full((H, W, 4), 7.0, np.float32)
+    r2.bindFrameBuffer(host, None, W, H, useDoubleBuffer=True)
+    frames = []
+    for seed in (61, 62, 63):
+        vb, idx = scenes.random_tris(80, seed, size=0.4)
+        frames.append(oracle_draw(W, H, vb, idx, 0, O.FS_VARYING0, 1, IDENT, clear_color=(.1, .2, .3, 1))["color"])
+        R.setup_scene(r2, vb, idx, 0, O.FS_VARYING0, 1, IDENT)
+        r2.setClearValues([(.1, .2, .3, 1)], 1.0)
+        r2.clear()
+        r2.drawElements()
+        r2.synchronize()
+        assert np.array_equal(r2.readColor().view(np.uint32), frames[-1].view(np.uint32))
+        if len(frames) == 1:
+            assert np.all(host == 7.0)          # nothing has been copied back yet
+        else:
+            assert np.array_equal(host.view(np.uint32), frames[-2].view(np.uint32))
+
+
 def test_standalone_vertex_stage_matches_fused(r):
     """vertexProcessingKernel CU:330 as its own kernel (pos / vary buffers) vs fused into triangle setup."""
     W, H = 320, 200

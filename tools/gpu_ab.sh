@@ -1,0 +1,19 @@
+#!/bin/bash
+# usage (GPU box): tools/gpu_ab.sh <tag> <cfg> <variantdir>... — times build variants (ifrit-v2_b200/lib_ab/<v>/libifrit_b200.so,
+# built here with `make -C ifrit-v2_b200/csrc OUT=../lib_ab/<v> EXTRA=-D...`) back to back on the same box, twice each
+tag=$1; cfg=$2; shift 2; o=gpurun_out; mkdir -p $o
+for rep in 1 2; do for v in "$@"; do
+  lib=$PWD/ifrit-v2_b200/lib_ab/$v/libifrit_b200.so; [ $v = base ] && lib=$PWD/ifrit-v2_b200/lib/libifrit_b200.so
+  IFRIT_B200_LIB=$lib timeout 600 python bench.py --config $cfg --steps 300 --warmup 3 --no-cpu-baseline --extra-configs=$EXTRA_CFG > $o/ab_${tag}_${v}_$rep.json 2> $o/ab_${tag}_${v}_$rep.err
+  python - <<PY
+import json
+try:
+    o=json.loads(open('$o/ab_${tag}_${v}_$rep.json').read().strip().splitlines()[-1])
+    def show(n,d): print('$v rep$rep', n, 'ms/step %.4f'%d['ms_per_step'], {k:round(v,4) for k,v in d['kernel_ms'].items()})
+    show(o['config']['name'], o)
+    for k,v in o.get('extra_configs',{}).items():
+        if 'error' in v: print(k, v)
+        else: show(k, v)
+except Exception as e: print('$v parse fail', e); print(open('$o/ab_${tag}_${v}_$rep.err').read()[-800:])
+PY
+done; done
