@@ -29,11 +29,6 @@ __device__ __forceinline__ KeyMode key_mode(int func) {
     m.never = !m.ordered && !m.equal && func != IF_COMPARE_OP_ALWAYS;
     return m;
 }
-__device__ __forceinline__ uint32_t mono(float d) {
-    d = d + 0.0f;
-    const uint32_t b = __float_as_uint(d);
-    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-}
 __device__ __forceinline__ unsigned long long key_init(const KeyMode& m, float d0) {
     if (m.ordered) return ((unsigned long long)(mono(d0) ^ m.xhi) << 32) | m.xlo;
     return ((unsigned long long)0xffffffffu << 32) | __float_as_uint(d0 + 0.0f);
@@ -264,18 +259,77 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 // ---- big triangles: setups precomputed by the fill pass arrive by TMA bulk copy (double buffered); every thread
 //      tests its own pixel against broadcast LDS.128 words, warps run independently.
-// HIZ: hierarchical early-Z, one level above the pixel: wfar = the worst (largest) key depth word any sample of this
-// warp's 8x4 block currently holds.  A triangle whose most optimistic depth inside the tile (TriS pad[1], from the fill
-// pass) maps above it cannot win a single sample of the block and is skipped by the whole warp.  Deep queues and
-// ordered compare ops only; results are unchanged (the reference has no Hi-Z: curTileHierZ is an unused field,
+// HIZ (deep queues, ordered compare ops): hierarchical early-Z one level above the pixel.  wfar = the worst (largest)
+// key depth word any sample of this warp's 8x4 block currently holds; a triangle whose most optimistic key inside the
+// tile (TriS pad[1], computed by setup_hiz on the staged entries) lies above it cannot win a single sample of the
+// block and is skipped by the whole warp.  One level further up, entries that cannot win anywhere in the tile
+// (bound above every warp's wfar) are dropped while the chunk is prepared: the warps only walk the compacted
+// survivor list.  Results are unchanged (the reference has no Hi-Z: curTileHierZ is an unused field,
 // TileRasterWorker.h:80).
+struct HizShared { uint32_t warpFar[8]; uint32_t nSurv[2]; uint8_t surv[2][32]; };
+
+template <int S>
+__device__ __forceinline__ uint32_t block_far(const unsigned long long* keys, int tid, unsigned long long best) {
+    uint32_t mine;
+    if (S == 1) mine = (uint32_t)(best >> 32);
+    else {
+        mine = 0;
+#pragma unroll
+        for (int sm = 0; sm < S; sm++) mine = max(mine, (uint32_t)(keys[sm * IFR_TILE_PIX + tid] >> 32));
+    }
+    return __reduce_max_sync(0xffffffffu, mine);
+}
+
+// one big-queue entry against this thread's pixel; returns true if a key of the pixel changed
+template <int S, bool HIZ>
+__device__ __forceinline__ bool big_test(const DrawParams& p, const KeyMode& km, unsigned long long* keys, const int4* t4, uint32_t cz,
+                                         int tid, int wrp, int lx, int ly, bool scis, float d0, unsigned long long& best) {
+    const int ci = 16 * lx, cj = 16 * ly;
+    const int4 A = t4[0];
+    const int4 B = t4[1], C = t4[2];
+    const int dX[3] = {A.x, A.y, A.z}, dY[3] = {B.x, B.y, B.z}, T[3] = {C.x, C.y, C.z};
+    const uint32_t flags = (uint32_t)C.w;
+    uint32_t m = 0;
+    bool upd = false;
+    if (HIZ && ((cz >> (8 + wrp)) & 1)) {
+        if (scis) m = (1u << S) - 1u;          // trivial accept: every sample of the block
+    } else if (!(flags & IFR_FLAG_WIDE)) {
+        if (scis) m = coverage<S>(p, dX, dY, T, nullptr, 0, ci, cj);
+    }
+    if (m || (flags & IFR_FLAG_WIDE)) {
+        const int4 D = t4[3], E = t4[4];
+        const long long E0[3] = {(long long)(((unsigned long long)(uint32_t)D.y << 32) | (uint32_t)D.x),
+                                 (long long)(((unsigned long long)(uint32_t)D.w << 32) | (uint32_t)D.z),
+                                 (long long)(((unsigned long long)(uint32_t)E.y << 32) | (uint32_t)E.x)};
+        if (!m && scis) m = coverage<S>(p, dX, dY, T, E0, 1, ci, cj);
+        if (m) {
+            const float2 Zr = *reinterpret_cast<const float2*>(t4 + 5);
+            const float d = depth_at(dX, dY, E0, flags, __int_as_float(E.z), __int_as_float(E.w), Zr.x, Zr.y, lx, ly);
+            unsigned long long k;
+            if (key_make(km, d, d0, (uint32_t)B.w, k)) {
+                if (S == 1) {
+                    if (k < best) { best = k; upd = true; }
+                } else {
+#pragma unroll
+                    for (int sm = 0; sm < S; sm++)
+                        if (((m >> sm) & 1) && k < keys[sm * IFR_TILE_PIX + tid]) { keys[sm * IFR_TILE_PIX + tid] = k; upd = true; }
+                }
+            }
+        }
+    }
+    return upd;
+}
+
 template <int S, bool HIZ>
 __device__ __forceinline__ void big_loop(const DrawParams& p, const KeyMode& km, unsigned long long* keys, TriS (*bigBuf)[IFR_BIG_CHUNK],
-                                         uint64_t* mbar, const TriS* bigSrc, uint32_t nBig, int tid, int wrp, int lx, int ly,
-                                         bool scis, float d0, unsigned long long& best) {
-    const int ci = 16 * lx, cj = 16 * ly;
+                                         uint64_t* mbar, HizShared& hz, const TriS* bigSrc, uint32_t nBig, int tid, int wrp, int lx,
+                                         int ly, bool scis, float d0, unsigned long long& best) {
+    const int lane = tid & 31;
     uint32_t wfar = 0xffffffffu;
-    bool dirty = HIZ;
+    if (HIZ) {
+        wfar = block_far<S>(keys, tid, best);
+        if (lane == 0) hz.warpFar[wrp] = wfar;     // read (possibly stale = larger = conservative) by the chunk preparation
+    }
     const uint32_t nchunks = (nBig + IFR_BIG_CHUNK - 1) / IFR_BIG_CHUNK;
     for (uint32_t c = 0; c < nchunks; c++) {
         if (tid == 0 && c + 1 < nchunks) {
@@ -285,65 +339,51 @@ __device__ __forceinline__ void big_loop(const DrawParams& p, const KeyMode& km,
         }
         mbar_wait(&mbar[c & 1], (c >> 1) & 1);
         const uint32_t cnt = min(nBig - c * IFR_BIG_CHUNK, (uint32_t)IFR_BIG_CHUNK);
-        if (HIZ) {
-            // one thread per staged entry: trivial-accept blocks + depth bound, written back into the staged copy
-            if ((uint32_t)tid < cnt)
-                setup_hiz(&bigBuf[c & 1][tid], p.sampMinX, p.sampMaxX, p.sampMinY, p.sampMaxY, km.xhi ? 1 : 0);
-            __syncthreads();
-        }
-        const int4* t4 = reinterpret_cast<const int4*>(bigBuf[c & 1]);
-        for (uint32_t b = 0; b < cnt; b++, t4 += 6) {
-            if (HIZ && dirty) {
-                // refresh the block's far bound (warp-convergent: every reject above / below is warp-uniform)
-                uint32_t mine;
-                if (S == 1) mine = (uint32_t)(best >> 32);
-                else {
-                    mine = 0;
+        const int4* chunk = reinterpret_cast<const int4*>(bigBuf[c & 1]);
+        if (!HIZ) {
+            const int4* t4 = chunk;
+            for (uint32_t b = 0; b < cnt; b++, t4 += 6) {
+                // warp-uniform coarse reject: the fill pass rasterised the triangle against the tile's 8x4 blocks
+                const uint32_t cz = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(t4) + 88);
+                if (!((cz >> wrp) & 1)) continue;
+                big_test<S, false>(p, km, keys, t4, cz, tid, wrp, lx, ly, scis, d0, best);
+            }
+        } else {
+            // chunk preparation, warps 0 and 1, one thread per staged entry: trivial-accept blocks + key bound written
+            // back into the staged copy, entries that can still win somewhere in the tile compacted per warp
+            if (tid < IFR_BIG_CHUNK) {
+                bool alive = false;
+                if ((uint32_t)tid < cnt) {
+                    uint32_t tileFar = 0;
 #pragma unroll
-                    for (int sm = 0; sm < S; sm++) mine = max(mine, (uint32_t)(keys[sm * IFR_TILE_PIX + tid] >> 32));
+                    for (int w = 0; w < 8; w++) tileFar = max(tileFar, hz.warpFar[w]);
+                    TriS* e = &bigBuf[c & 1][tid];
+                    const uint32_t tb = setup_hiz(e, p.sampMinX, p.sampMaxX, p.sampMinY, p.sampMaxY, km.xhi);
+                    alive = ((uint32_t)e->pad[0] & 0xffu) != 0 && tb <= tileFar;
                 }
-                wfar = __reduce_max_sync(0xffffffffu, mine);
-                dirty = false;
+                const unsigned bal = __ballot_sync(0xffffffffu, alive);
+                if (alive) hz.surv[wrp][__popc(bal & ((1u << lane) - 1u))] = (uint8_t)tid;
+                if (lane == 0) hz.nSurv[wrp] = __popc(bal);
             }
-            // warp-uniform coarse reject: the fill pass rasterised the triangle against the tile's 8x4 blocks
-            const uint2 cz = *reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(t4) + 88);
-            if (!((cz.x >> wrp) & 1)) continue;
-            if (HIZ && (mono(__uint_as_float(cz.y)) ^ km.xhi) > wfar) continue;
-            const int4 A = t4[0];
-            const int4 B = t4[1], C = t4[2];
-            const int dX[3] = {A.x, A.y, A.z}, dY[3] = {B.x, B.y, B.z}, T[3] = {C.x, C.y, C.z};
-            const uint32_t flags = (uint32_t)C.w;
-            uint32_t m = 0;
-            bool upd = false;
-            if (HIZ && ((cz.x >> (8 + wrp)) & 1)) {
-                if (scis) m = (1u << S) - 1u;          // trivial accept: every sample of the block
-            } else if (!(flags & IFR_FLAG_WIDE)) {
-                if (scis) m = coverage<S>(p, dX, dY, T, nullptr, 0, ci, cj);
-            }
-            if (m || (flags & IFR_FLAG_WIDE)) {
-                const int4 D = t4[3], E = t4[4];
-                const long long E0[3] = {(long long)(((unsigned long long)(uint32_t)D.y << 32) | (uint32_t)D.x),
-                                         (long long)(((unsigned long long)(uint32_t)D.w << 32) | (uint32_t)D.z),
-                                         (long long)(((unsigned long long)(uint32_t)E.y << 32) | (uint32_t)E.x)};
-                if (!m && scis) m = coverage<S>(p, dX, dY, T, E0, 1, ci, cj);
-                if (m) {
-                    const float2 Zr = *reinterpret_cast<const float2*>(t4 + 5);
-                    const float d = depth_at(dX, dY, E0, flags, __int_as_float(E.z), __int_as_float(E.w), Zr.x, Zr.y, lx, ly);
-                    unsigned long long k;
-                    if (key_make(km, d, d0, (uint32_t)B.w, k)) {
-                        if (S == 1) {
-                            if (k < best) { best = k; upd = true; }
-                        } else {
-#pragma unroll
-                            for (int sm = 0; sm < S; sm++)
-                                if (((m >> sm) & 1) && k < keys[sm * IFR_TILE_PIX + tid]) { keys[sm * IFR_TILE_PIX + tid] = k; upd = true; }
-                        }
+            __syncthreads();
+            for (int half = 0; half < 2; half++) {
+                const uint32_t ns = hz.nSurv[half];
+                for (uint32_t i = 0; i < ns; i++) {
+                    const int4* t4 = chunk + 6 * (int)hz.surv[half][i];
+                    const uint2 cz = *reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(t4) + 88);
+                    if (!((cz.x >> wrp) & 1)) continue;
+                    if (cz.y > wfar) continue;          // warp-uniform Hi-Z reject
+                    const bool upd = big_test<S, true>(p, km, keys, t4, cz.x, tid, wrp, lx, ly, scis, d0, best);
+                    if (__any_sync(0xffffffffu, upd)) {  // warp-convergent: every reject above is warp-uniform
+                        wfar = block_far<S>(keys, tid, best);
+                        if (lane == 0) hz.warpFar[wrp] = wfar;
                     }
                 }
             }
-            if (HIZ) dirty = __any_sync(0xffffffffu, upd);
         }
-        if (c + 2 < nchunks) __syncthreads();   // buffer (c & 1) is refilled at the top of iteration c + 1
+        // the staged buffer (and, with HIZ, the survivor lists) are rewritten by the next iteration's preparation / the
+        // bulk copy issued at the top of iteration c + 1
+        if (HIZ ? (c + 1 < nchunks) : (c + 2 < nchunks)) __syncthreads();
     }
 }
 
@@ -358,6 +398,7 @@ __global__ void __launch_bounds__(256, (S == 1 && FsTraits<FS>::needsDerivs) ? I
     extern __shared__ unsigned long long keys[];        // [S][256], index = owning thread
     __shared__ __align__(128) TriS bigBuf[2][IFR_BIG_CHUNK];
     __shared__ __align__(8) uint64_t mbar[2];
+    __shared__ HizShared hz;
     constexpr int NV = FsTraits<FS>::nv;
 
     const int tileX = blockIdx.x, tileY = blockIdx.y;
@@ -394,24 +435,44 @@ __global__ void __launch_bounds__(256, (S == 1 && FsTraits<FS>::needsDerivs) ? I
     float d0 = 0.0f;
     if (inFrame) d0 = (p.doClear && scis) ? p.clearDepth : p.depth[pidx];
     const unsigned long long k0 = key_init(km, d0);
-    // Per-sample visibility keys.  S == 1: the pixel's key lives in a register (`best`); shared memory
-    // is only the mailbox through which small triangles (processed by other threads) reach this pixel.
-    if (S > 1 || nSmall) {
+    // Per-sample visibility keys.  S == 1: the pixel's key lives in a register (`best`); shared memory is only the
+    // mailbox through which small triangles (processed by other threads) reach this pixel, filled from `best`
+    // once the big triangles are done.
+    if (S > 1) {
 #pragma unroll
         for (int s = 0; s < S; s++) keys[s * IFR_TILE_PIX + tid] = k0;
     }
     unsigned long long best = k0;
-    if (nBig && tid == 0) {
-        mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const bool deep = km.ordered && nBig >= IFR_HIZ_MIN_QUEUE;
+
+    // ---- big triangles first: their result gives the small-triangle pass a far bound per 8x4 block ----
+    if (nBig) {
+        if (tid == 0) {
+            mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        if (tid < 8) hz.warpFar[tid] = 0xffffffffu;
+        __syncthreads();      // mbarriers initialised
+        const TriS* bigSrc = p.bigQueue + bStart;
+        if (tid == 0) bulk_load(bigBuf[0], bigSrc, min(nBig, (uint32_t)IFR_BIG_CHUNK) * (uint32_t)sizeof(TriS), &mbar[0]);
+#ifndef IFR_NO_HIZ
+        if (deep) big_loop<S, true>(p, km, keys, bigBuf, mbar, hz, bigSrc, nBig, tid, wrp, lx, ly, scis, d0, best);
+        else
+#endif
+            big_loop<S, false>(p, km, keys, bigBuf, mbar, hz, bigSrc, nBig, tid, wrp, lx, ly, scis, d0, best);
     }
-    __syncthreads();      // keys + mbarriers initialised
-    const TriS* bigSrc = p.bigQueue + bStart;
-    if (nBig && tid == 0)  // stage the first chunk of precomputed setups while the small triangles are processed
-        bulk_load(bigBuf[0], bigSrc, min(nBig, (uint32_t)IFR_BIG_CHUNK) * (uint32_t)sizeof(TriS), &mbar[0]);
 
     // ---- small triangles: one thread per (triangle, tile) pair, shared-memory atomicMin --------------
     if (nSmall) {
+        if (S == 1) keys[tid] = best;
+        // per-pixel early-Z against the block's far bound (deep tiles: most small triangles are hidden behind the big
+        // ones): depth first, coverage only for pixels that can still win a sample
+        const bool useFar = deep;
+        if (useFar) {
+            const uint32_t f = block_far<S>(keys, tid, best);
+            if ((tid & 31) == 0) hz.warpFar[wrp] = f;
+        }
+        __syncthreads();      // keys complete, far bounds published
         for (uint32_t qi = tid; qi < nSmall; qi += IFR_CHUNK) {
             TriS s;
             int bx0, bx1, by0, by1;
@@ -420,16 +481,23 @@ __global__ void __launch_bounds__(256, (S == 1 && FsTraits<FS>::needsDerivs) ? I
             const int wide = s.flags & IFR_FLAG_WIDE;
             for (int y = by0; y <= by1; y++)
                 for (int x = bx0; x <= bx1; x++) {
+                    unsigned long long k = 0;
+                    if (useFar) {
+                        const float d = depth_at(s.dX, s.dY, s.E0, s.flags, s.ar, s.z0, s.z1, s.z2, x, y);
+                        key_make(km, d, 0.0f, slot, k);      // ordered compare op: always a key
+                        if ((uint32_t)(k >> 32) > hz.warpFar[(y >> 2) * 2 + (x >> 3)]) continue;
+                    }
                     const uint32_t m = coverage<S>(p, s.dX, s.dY, s.T, s.E0, wide, 16 * x, 16 * y);
                     if (!m) continue;
                     const int gx = tileX * IFR_TILE + x, gy = tileY * IFR_TILE + y;
                     if (p.scissorEnable && !scissor_pass(p, gx, gy)) continue;
-                    const float d = depth_at(s.dX, s.dY, s.E0, s.flags, s.ar, s.z0, s.z1, s.z2, x, y);
-                    unsigned long long k;
-                    float dd0 = 0.0f;
-                    if (km.equal)
-                        dd0 = p.doClear ? p.clearDepth : p.depth[(size_t)gy * p.W + gx];
-                    if (!key_make(km, d, dd0, slot, k)) continue;
+                    if (!useFar) {
+                        const float d = depth_at(s.dX, s.dY, s.E0, s.flags, s.ar, s.z0, s.z1, s.z2, x, y);
+                        float dd0 = 0.0f;
+                        if (km.equal)
+                            dd0 = p.doClear ? p.clearDepth : p.depth[(size_t)gy * p.W + gx];
+                        if (!key_make(km, d, dd0, slot, k)) continue;
+                    }
                     const int pi = pix_index(x, y);
 #pragma unroll
                     for (int sm = 0; sm < S; sm++)
@@ -439,22 +507,12 @@ __global__ void __launch_bounds__(256, (S == 1 && FsTraits<FS>::needsDerivs) ? I
         __syncthreads();
     }
 
-    if (nBig) {
-        if (S == 1 && nSmall) { const unsigned long long ks = keys[tid]; if (ks < best) best = ks; }
-#ifndef IFR_NO_HIZ
-        if (km.ordered && nBig >= IFR_HIZ_MIN_QUEUE)
-            big_loop<S, true>(p, km, keys, bigBuf, mbar, bigSrc, nBig, tid, wrp, lx, ly, scis, d0, best);
-        else
-#endif
-            big_loop<S, false>(p, km, keys, bigBuf, mbar, bigSrc, nBig, tid, wrp, lx, ly, scis, d0, best);
-    }
-
     // ---- quad shading + resolve -----------------------------------------------------------------
     uint32_t mySlots[S];
 #pragma unroll
     for (int s = 0; s < S; s++) {
         unsigned long long k = best;
-        if (S > 1 || nSmall) { const unsigned long long ks = keys[s * IFR_TILE_PIX + tid]; if (S > 1 || ks < k) k = ks; }
+        if (S > 1 || nSmall) k = keys[s * IFR_TILE_PIX + tid];
         mySlots[s] = key_slot(km, k);
     }
 

@@ -6,6 +6,13 @@
 #include "common.cuh"
 #include "../../include/ifrit_b200.h"
 
+// order-preserving float -> uint map of the visibility keys (oracle: key_* in ifrit_oracle.c)
+__device__ __forceinline__ uint32_t mono(float d) {
+    d = d + 0.0f;
+    const uint32_t b = __float_as_uint(d);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
 struct RecRegs { int X[3], Y[3]; float Z[3]; float ar; uint32_t flags; };
 
 __device__ __forceinline__ void load_rec(const DrawParams& p, uint32_t slot, RecRegs& rr) {
@@ -27,7 +34,8 @@ __device__ __forceinline__ void load_rec(const DrawParams& p, uint32_t slot, Rec
 // The depth the tile kernel computes, F(x, y) = fma chain of z_i * (float(E_i) * ar), follows the exact plane
 // P = sum z_i E_i / d within eps * M, M = sum |z_i| |E_i / d| (convex), eps < 1.75 * 2^-22.  P is affine, so over
 // the box F >= min_corners F - 2 eps max_corners M; the margin below is twice that.
-__device__ __forceinline__ void setup_hiz(TriS* sp, int sampMinX, int sampMaxX, int sampMinY, int sampMaxY, int greater) {
+__device__ __forceinline__ uint32_t setup_hiz(TriS* sp, int sampMinX, int sampMaxX, int sampMinY, int sampMaxY, uint32_t xhi) {
+    const bool greater = xhi != 0;
     TriS& s = *sp;
     const int bx0 = s.box & 0xff, bx1 = (s.box >> 8) & 0xff, by0 = (s.box >> 16) & 0xff, by1 = s.box >> 24;
     uint32_t mask = (uint32_t)s.pad[0];
@@ -64,8 +72,11 @@ __device__ __forceinline__ void setup_hiz(TriS* sp, int sampMinX, int sampMaxX, 
     const float margin = mag * 1.9073486e-6f + 1e-30f;   // 2^-19 M
     float zbound = greater ? hi + margin : lo - margin;
     if (!(zbound == zbound)) zbound = greater ? 3.0e38f : -3.0e38f;   // NaN depth: never reject
+    // stored as the key depth word (mono(z) ^ xhi, the form the tile kernel compares): smaller = more optimistic
+    const uint32_t tb = mono(zbound) ^ xhi;
     s.pad[0] = (int)mask;
-    s.pad[1] = __float_as_int(zbound);
+    s.pad[1] = (int)tb;
+    return tb;
 }
 
 #define IFR_HIZ_MIN_QUEUE 12   // tiles with fewer big-queue entries run the tile kernel's big loop without the Hi-Z reject
@@ -125,9 +136,8 @@ __device__ __forceinline__ bool setup_from_rec(const DrawParams& p, const RecReg
             mask |= (uint32_t)may << blk;
         }
     }
-    const bool greater = p.depthFunc == IF_COMPARE_OP_GREATER || p.depthFunc == IF_COMPARE_OP_GREATER_OR_EQUAL;
     s.pad[0] = (int)mask;
-    s.pad[1] = __float_as_int(greater ? 3.0e38f : -3.0e38f);   // "never reject" unless setup_hiz computes a bound
+    s.pad[1] = 0;   // Hi-Z key bound: filled in by the tile kernel (setup_hiz) for deep queues
     return ok;
 }
 
