@@ -285,12 +285,11 @@ def run_ours(args, cfg_name):
         if world == 1:
             r.synchronize()                                            # render stream + copy stream
             return
-        sf.gather()
+        sf.gather(hold=True)
         if rank == 0:
             r.copyColorToHostAsync(hcol.data_ptr())                    # D2H of the step's result (pinned, async)
+        sf.release()         # peer mode: only now may the other ranks overwrite the frame (device-side flag)
         torch.cuda.current_stream().synchronize()
-        if mg_mode == "peer":
-            dist.barrier()   # the next frame's peer stores must not overtake rank 0's read-back
 
     for _ in range(2):
         e2e_step()

@@ -66,6 +66,9 @@ struct iftrcuRenderer {
     void* registeredHost = nullptr;
     void* peerColor = nullptr; void* peerDepth = nullptr;   // opened CUDA IPC mappings (peer framebuffer)
     bool debugIds = false;
+    uint32_t* frameFlags = nullptr;       // frame-flag block of the bound framebuffer (own or peer), see kernels_image.cu
+    uint32_t* hTimedOut = nullptr;        // pinned: set by a flag wait that gave up
+    uint32_t fenceFrame = 0; bool fencePending = false;   // peer: next tile kernel waits for the owner's release
 
     // geometry
     const uint8_t* dVB = nullptr; DevBuf ownVB; int nverts = 0, stride = 0, nattr = 0; int attrOff[IFR_MAX_VARY + 1] = {0};
@@ -258,6 +261,10 @@ static int issue_draw(iftrcuRenderer* r, bool forceCheck) {
     }
     CUDA_TRY(ifr_launch_fill(p, s));
     if (ev) CUDA_TRY(cudaEventRecord(ev[4], s));
+    if (r->fencePending && r->frameFlags) {   // sort-first peer: the owner must have released the frame these tiles overwrite
+        CUDA_TRY(ifr_launch_flag_wait(r->frameFlags + 64, 1, r->fenceFrame, r->hTimedOut, s));
+        r->fencePending = false;
+    }
     if (r->doubleBuffer && r->copyPending[r->cur]) {   // this buffer's previous frame is still on its way to the host
         CUDA_TRY(cudaStreamWaitEvent(s, r->evCopy[r->cur], 0));
         r->copyPending[r->cur] = false;
@@ -318,6 +325,7 @@ static int sync_and_check(iftrcuRenderer* r) {
         CUDA_TRY(cudaStreamSynchronize(r->stream));
         if (r->doubleBuffer) CUDA_TRY(cudaStreamSynchronize(r->copyStream));
     }
+    if (r->hTimedOut && *r->hTimedOut) { *r->hTimedOut = 0; return r->fail(IFRIT_ERR_STATE, "frame flags", "a sort-first rank did not signal within 2 s"); }
     if (r->haveDraw) {
         r->stats.triangles_assembled = r->hCounters[0];
         r->stats.tile_pairs = r->hCounters[1] + r->hCounters[5];
@@ -346,11 +354,12 @@ int iftrcuCreateInstance(int cudaDevice, iftrcuRenderer** out) {
     memset(r->tex, 0, sizeof r->tex); memset(r->samp, 0, sizeof r->samp); memset(&r->stats, 0, sizeof r->stats);
     memset(r->scissor, 0, sizeof r->scissor);
     if (cudaSetDevice(cudaDevice) != cudaSuccess || cudaStreamCreateWithFlags(&r->ownStream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMallocHost((void**)&r->hCounters, 64) != cudaSuccess) {
+        cudaMallocHost((void**)&r->hCounters, 64) != cudaSuccess || cudaMallocHost((void**)&r->hTimedOut, 64) != cudaSuccess) {
         delete r;
         return IFRIT_ERR_CUDA;
     }
     memset(r->hCounters, 0, 64);
+    memset(r->hTimedOut, 0, 64);
     r->stream = r->ownStream;
     *out = r;
     return IFRIT_OK;
@@ -370,6 +379,7 @@ int iftrcuDestroyInstance(iftrcuRenderer* h) {
     for (int i = 0; i < IFR_MAX_BUF; i++) r->bufMem[i].release();
     for (auto& e : r->profEvents) cudaEventDestroy(e);
     if (r->hCounters) cudaFreeHost(r->hCounters);
+    if (r->hTimedOut) cudaFreeHost(r->hTimedOut);
     if (r->ownStream) cudaStreamDestroy(r->ownStream);
     delete r;
     return IFRIT_OK;
@@ -386,6 +396,8 @@ int iftrcuSetStream(iftrcuRenderer* h, void* cudaStream) {
     return IFRIT_OK;
 }
 
+static size_t flag_offset(int width, int height) { return (((size_t)width * height * 4) + 255) & ~(size_t)255; }
+
 static void reset_double_buffer(iftrcuRenderer* r) {
     if (r->copyStream) cudaStreamSynchronize(r->copyStream);
     r->doubleBuffer = false; r->cur = 0; r->lastColor = nullptr;
@@ -399,7 +411,10 @@ int iftrcuBindFrameBuffer(iftrcuRenderer* h, float* hostColor, float* hostDepth,
     close_peer(r);
     reset_double_buffer(r);
     CUDA_TRY(r->ownColor.ensure((size_t)width * height * 16));
-    CUDA_TRY(r->ownDepth.ensure((size_t)width * height * 4));
+    CUDA_TRY(r->ownDepth.ensure(flag_offset(width, height) + IFR_FLAG_WORDS * 4));
+    r->frameFlags = (uint32_t*)((char*)r->ownDepth.p + flag_offset(width, height));
+    CUDA_TRY(cudaMemsetAsync(r->frameFlags, 0, IFR_FLAG_WORDS * 4, r->stream));
+    r->fencePending = false;
     if (useDoubleBuffer && hostColor) {
         CUDA_TRY(r->ownColor2.ensure((size_t)width * height * 16));
         if (!r->copyStream) {
@@ -453,6 +468,8 @@ int iftrcuBindPeerFrameBuffer(iftrcuRenderer* h, const void* handle128, int widt
     CUDA_TRY(cudaIpcOpenMemHandle(&r->peerDepth, hd, cudaIpcMemLazyEnablePeerAccess));
     if (r->registeredHost) { cudaHostUnregister(r->registeredHost); r->registeredHost = nullptr; }
     r->dColor = (float4*)r->peerColor; r->dDepth = (float*)r->peerDepth; r->externalFB = true; r->hColor = nullptr; r->hDepth = nullptr;
+    r->frameFlags = (uint32_t*)((char*)r->peerDepth + flag_offset(width, height));
+    r->fencePending = false;
     if (r->W != width || r->H != height) r->queueChecked = false;
     r->W = width; r->H = height;
     return IFRIT_OK;
@@ -466,6 +483,7 @@ int iftrcuBindFrameBufferDevice(iftrcuRenderer* h, float* devColor, float* devDe
     reset_double_buffer(r);
     if (r->registeredHost) { cudaHostUnregister(r->registeredHost); r->registeredHost = nullptr; }
     r->dColor = (float4*)devColor; r->dDepth = devDepth; r->externalFB = true; r->hColor = nullptr; r->hDepth = nullptr;
+    r->frameFlags = nullptr; r->fencePending = false;
     if (r->W != width || r->H != height) r->queueChecked = false;
     r->W = width; r->H = height;
     return IFRIT_OK;
@@ -869,6 +887,31 @@ size_t iftrcuOwnedTileBytes(int width, int height, int rank, int worldSize) {
     for (int y = 0; y < sy; y++)
         for (int x = 0; x < sx; x++) n += ((x + 3 * y) % worldSize) == rank;
     return n * IFR_SUPER * IFR_SUPER * 16;
+}
+
+// ---- sort-first frame flags (peer-memory mode): see kernels_image.cu ----
+int iftrcuFrameSignal(iftrcuRenderer* h, uint32_t frameId) {
+    R_CHECK(h);
+    if (!r->frameFlags || r->rank < 0 || r->rank >= 64) return r->fail(IFRIT_ERR_STATE, "FrameSignal", "no renderer-owned or peer framebuffer bound");
+    CUDA_TRY(ifr_launch_flag_store(r->frameFlags + r->rank, frameId, r->stream));
+    return IFRIT_OK;
+}
+int iftrcuFrameWait(iftrcuRenderer* h, uint32_t frameId) {
+    R_CHECK(h);
+    if (!r->frameFlags || r->world > 64) return r->fail(IFRIT_ERR_STATE, "FrameWait", "no renderer-owned or peer framebuffer bound");
+    CUDA_TRY(ifr_launch_flag_wait(r->frameFlags, r->world, frameId, r->hTimedOut, r->stream));
+    return IFRIT_OK;
+}
+int iftrcuFrameRelease(iftrcuRenderer* h, uint32_t frameId) {
+    R_CHECK(h);
+    if (!r->frameFlags) return r->fail(IFRIT_ERR_STATE, "FrameRelease", "no renderer-owned or peer framebuffer bound");
+    CUDA_TRY(ifr_launch_flag_store(r->frameFlags + 64, frameId, r->stream));
+    return IFRIT_OK;
+}
+int iftrcuFrameFence(iftrcuRenderer* h, uint32_t frameId) {
+    R_CHECK(h);
+    r->fenceFrame = frameId; r->fencePending = true;
+    return IFRIT_OK;
 }
 
 int iftrcuPackOwnedTiles(iftrcuRenderer* h, void* devDst, size_t dstBytes, size_t* usedBytes) {

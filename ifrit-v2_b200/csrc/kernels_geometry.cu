@@ -156,6 +156,17 @@ __device__ __forceinline__ void finish_triangle(const DrawParams& p, const ClipV
     const long long boxArea = (long long)(px1 - px0 + 1) * (py1 - py0 + 1);
     if (boxArea <= IFR_SMALL_AREA) a.flags |= IFR_FLAG_SMALL;
     a.tx0 = px0 >> 4; a.tx1 = px1 >> 4; a.ty0 = py0 >> 4; a.ty1 = py1 >> 4;
+    if (p.world > 1) {
+        // sort-first: a triangle whose box touches no super-tile of this rank contributes nothing here — drop it
+        // before the 64-byte record store and the fill pass (geometry is replicated; this keeps the replicated
+        // part to reading it).  Boxes spanning >= world super-tiles in a row always contain an owned one.
+        const int per = IFR_SUPER / IFR_TILE;
+        const int sx0 = a.tx0 / per, sx1 = a.tx1 / per, sy0 = a.ty0 / per, sy1 = a.ty1 / per;
+        bool owned = sx1 - sx0 + 1 >= p.world;
+        for (int sy = sy0; sy <= sy1 && !owned; sy++)
+            for (int sx = sx0; sx <= sx1 && !owned; sx++) owned = (sx + 3 * sy) % p.world == p.rank;
+        if (!owned) return;
+    }
     a.ok = true;
 }
 

@@ -117,3 +117,35 @@ cudaError_t ifr_launch_pack(const DrawParams& p, float* dst, int rank, int world
     pack_kernel<<<grid, 256, 0, s>>>(p, reinterpret_cast<float4*>(dst), rank, world, unpack);
     return cudaGetLastError();
 }
+
+// ---- sort-first frame flags (peer-memory mode) ---------------------------------------------------------
+// A block of 32-bit words at the tail of the framebuffer owner's depth allocation, mapped into every rank by
+// the same CUDA IPC handle as the framebuffer: word r = last frame whose tiles rank r has stored, word 64 = last
+// frame the owner has released for overwriting.  A store kernel after the tile kernel publishes, a one-warp
+// kernel polls — no NCCL call and no host round trip per frame.
+__global__ void flag_store_kernel(volatile uint32_t* word, uint32_t value) {
+    __threadfence_system();     // the tile kernel's peer stores (previous kernel on this stream) before the flag
+    *word = value;
+    __threadfence_system();
+}
+__global__ void flag_wait_kernel(const volatile uint32_t* words, int n, uint32_t value, uint32_t* timedOut) {
+    const int lane = threadIdx.x;
+    if (lane >= n) return;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    // frame ids wrap: "reached" = not behind by half the range
+    while ((int32_t)(words[lane] - value) < 0) {
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 2000000000ull) { *timedOut = 1u; break; }   // 2 s: a peer is gone — never hang the device
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+cudaError_t ifr_launch_flag_store(uint32_t* word, uint32_t value, cudaStream_t s) {
+    flag_store_kernel<<<1, 1, 0, s>>>(word, value);
+    return cudaGetLastError();
+}
+cudaError_t ifr_launch_flag_wait(const uint32_t* words, int n, uint32_t value, uint32_t* timedOut, cudaStream_t s) {
+    flag_wait_kernel<<<1, 64, 0, s>>>(words, n, value, timedOut);
+    return cudaGetLastError();
+}

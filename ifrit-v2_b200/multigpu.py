@@ -88,6 +88,7 @@ def share_framebuffer(renderer, width, height, dist, device):
     blob = torch.zeros(128, dtype=torch.uint8, device=device)
     if rank == 0:
         renderer.bindFrameBuffer(None, None, width, height)
+        renderer.synchronize()      # the frame-flag block is zeroed before any peer can reach it
         blob = torch.frombuffer(bytearray(renderer.exportFrameBuffer()), dtype=torch.uint8).to(device)
     dist.broadcast(blob, 0)
     if rank != 0:
@@ -96,8 +97,9 @@ def share_framebuffer(renderer, width, height, dist, device):
 
 class SortFirstRenderer:
     """Wraps one TileRasterRendererCuda per rank.  mode "peer" (default on NVLink): every rank renders its
-    tiles straight into rank 0's framebuffer (share_framebuffer) and gather() is a one-element all-reduce
-    that orders frame completion on the stream.  mode "nccl": pack -> NCCL gather -> unpack."""
+    tiles straight into rank 0's framebuffer (share_framebuffer); frame completion and buffer re-use are ordered
+    on the device through flag words in rank 0's memory (iftrcuFrameSignal / Wait / Release / Fence) — no NCCL
+    call and no host round trip per frame.  mode "nccl": pack -> NCCL gather -> unpack."""
 
     def __init__(self, renderer, dist, device, same_stream=True, mode="nccl"):
         """same_stream: the renderer was given torch's current stream (setStream), so pack -> NCCL ->
@@ -108,20 +110,26 @@ class SortFirstRenderer:
         self.mode = mode
         if mode == "peer" and self.world > 1:
             share_framebuffer(renderer, renderer.width, renderer.height, dist, device)
-            self.token = torch.zeros(1, dtype=torch.float32, device=device)
+            self.frame = 0
         renderer.setTilePartition(self.rank, self.world)
         self.torch = torch
         self.packed = None
 
-    def gather(self):
-        """After drawElements(): rank 0's device framebuffer becomes the complete frame."""
+    def gather(self, hold=False):
+        """After drawElements(): rank 0's device framebuffer becomes the complete frame (in stream order on rank 0).
+        hold=True (peer mode): rank 0 keeps the frame until release() — e.g. until its read-back is enqueued."""
         torch, r = self.torch, self.r
         if self.world == 1:
             return
         if self.mode == "peer":
-            if not self.same_stream:
-                r.synchronize()
-            self.dist.all_reduce(self.token)   # every rank's tile kernel precedes it in stream order
+            self.frame = (self.frame + 1) & 0xffffffff   # compared modulo 2^32 on the device
+            r.frameSignal(self.frame)             # my tiles of this frame are stored (after my tile kernel)
+            if self.rank == 0:
+                r.frameWait(self.frame)           # polls until every rank has signalled
+                if not hold:
+                    r.frameRelease(self.frame)
+            else:
+                r.frameFence(self.frame)          # my next tile kernel waits until rank 0 has released this frame
             return
         n = max_owned_floats(r.width, r.height, self.world)
         if self.packed is None or self.packed.numel() != n:
@@ -138,3 +146,8 @@ class SortFirstRenderer:
             if not self.same_stream:
                 r.synchronize()
             self._keep = outs   # keep the receive buffers alive until the unpack kernels have run
+
+    def release(self):
+        """Peer mode, after gather(hold=True): rank 0 lets the other ranks overwrite the frame."""
+        if self.world > 1 and self.mode == "peer" and self.rank == 0:
+            self.r.frameRelease(self.frame)

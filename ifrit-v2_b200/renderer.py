@@ -404,6 +404,19 @@ class TileRasterRendererCuda:
         self._ck(self._lib.iftrcuReadAssembled(self._h, _ptr(out), cap, C.byref(n)))
         return out[: min(n.value, cap)], n.value
 
+    # sort-first frame flags (peer-memory mode), see include/ifrit_b200.h
+    def frameSignal(self, frame_id):
+        self._ck(self._lib.iftrcuFrameSignal(self._h, C.c_uint32(frame_id)))
+
+    def frameWait(self, frame_id):
+        self._ck(self._lib.iftrcuFrameWait(self._h, C.c_uint32(frame_id)))
+
+    def frameRelease(self, frame_id):
+        self._ck(self._lib.iftrcuFrameRelease(self._h, C.c_uint32(frame_id)))
+
+    def frameFence(self, frame_id):
+        self._ck(self._lib.iftrcuFrameFence(self._h, C.c_uint32(frame_id)))
+
     def packOwnedTiles(self, dev_ptr, nbytes):
         used = C.c_size_t()
         self._ck(self._lib.iftrcuPackOwnedTiles(self._h, C.c_void_p(dev_ptr), nbytes, C.byref(used)))

@@ -247,6 +247,18 @@ IFRIT_B200_API int iftrcuReadAssembled(iftrcuRenderer* h, iftrcuAssembledTriangl
 IFRIT_B200_API int iftrcuCopyColorToHostAsync(iftrcuRenderer* h, void* hostDst);
 IFRIT_B200_API int iftrcuExportFrameBuffer(iftrcuRenderer* h, void* handleOut128);
 IFRIT_B200_API int iftrcuBindPeerFrameBuffer(iftrcuRenderer* h, const void* handle128, int width, int height);
+/* Sort-first frame flags (peer-memory mode; no reference counterpart — the reference is single-GPU).
+ * The framebuffer owner's allocation carries a block of 32-bit flag words that every rank reaches through the same
+ * CUDA IPC mapping as the framebuffer.  Per frame, in stream order and without NCCL or host round trips:
+ *   every rank : iftrcuDrawElements; iftrcuFrameSignal(id)      "my tiles of frame id are stored"
+ *   owner      : iftrcuFrameWait(id)                            polls until all `worldSize` ranks have signalled
+ *                ... consume the frame ...; iftrcuFrameRelease(id)  "frame id may be overwritten"
+ *   peers      : iftrcuFrameFence(id)                           the NEXT tile kernel first waits for the release of id
+ * A wait gives up after 2 s (a later iftrcuSynchronize then returns IFRIT_ERR_STATE); the device never hangs. */
+IFRIT_B200_API int iftrcuFrameSignal(iftrcuRenderer* h, uint32_t frameId);
+IFRIT_B200_API int iftrcuFrameWait(iftrcuRenderer* h, uint32_t frameId);
+IFRIT_B200_API int iftrcuFrameRelease(iftrcuRenderer* h, uint32_t frameId);
+IFRIT_B200_API int iftrcuFrameFence(iftrcuRenderer* h, uint32_t frameId);
 IFRIT_B200_API int iftrcuPackOwnedTiles(iftrcuRenderer* h, void* devDst, size_t dstBytes, size_t* usedBytes);
 IFRIT_B200_API int iftrcuUnpackOwnedTiles(iftrcuRenderer* h, const void* devSrc, int rank, int worldSize);
 IFRIT_B200_API size_t iftrcuOwnedTileBytes(int width, int height, int rank, int worldSize);
