@@ -52,6 +52,8 @@ struct iftrcuRenderer {
     int W = 0, H = 0;
     float4* dColor = nullptr; float* dDepth = nullptr;
     DevBuf ownColor, ownColor2, ownDepth, primIds;
+    DevBuf presentBuf[2]; void* hPresent = nullptr; int presentFormat = 0; void* registeredPresent = nullptr;   // iftrcuBindPresentBuffer
+    bool wantDouble = false;
     bool externalFB = false;
     // useDoubleBuffer (TileRasterRendererCuda::bindFrameBuffer, CUHOST:46-63; CU:3893-3914): frame k renders into
     // colour buffer k & 1 while frame k - 1 is copied to the host image on a second stream, so the host image lags
@@ -153,6 +155,7 @@ static void create_tex_objects(iftrcuRenderer* r, int slot) {
 static void build_params(iftrcuRenderer* r, DrawParams& p) {
     memset(&p, 0, sizeof p);
     p.color = r->dColor; p.depth = r->dDepth; p.primIds = r->debugIds ? (int32_t*)r->primIds.p : nullptr;
+    p.present = r->presentFormat ? (uint32_t*)r->presentBuf[r->doubleBuffer ? r->cur : 0].p : nullptr;
     p.W = r->W; p.H = r->H;
     p.tilesX = (r->W + IFR_TILE - 1) / IFR_TILE; p.tilesY = (r->H + IFR_TILE - 1) / IFR_TILE;
     p.msaa = r->msaa; p.depthFunc = r->depthTest ? r->depthFunc : IF_COMPARE_OP_ALWAYS;   // CUHOST:207-218
@@ -284,14 +287,20 @@ static int issue_draw(iftrcuRenderer* r, bool forceCheck) {
         r->framePending[k] = true;
         if (r->framePending[prev]) {
             CUDA_TRY(cudaStreamWaitEvent(r->copyStream, r->evFrame[prev], 0));
-            const float4* src = prev ? (const float4*)r->ownColor2.p : (const float4*)r->ownColor.p;
-            CUDA_TRY(cudaMemcpyAsync(r->hColor, src, (size_t)r->W * r->H * 16, cudaMemcpyDeviceToHost, r->copyStream));
+            if (r->hPresent) {
+                CUDA_TRY(cudaMemcpyAsync(r->hPresent, r->presentBuf[prev].p, (size_t)r->W * r->H * 4, cudaMemcpyDeviceToHost, r->copyStream));
+            } else {
+                const float4* src = prev ? (const float4*)r->ownColor2.p : (const float4*)r->ownColor.p;
+                CUDA_TRY(cudaMemcpyAsync(r->hColor, src, (size_t)r->W * r->H * 16, cudaMemcpyDeviceToHost, r->copyStream));
+            }
             CUDA_TRY(cudaEventRecord(r->evCopy[prev], r->copyStream));
             r->copyPending[prev] = true;
         }
         r->lastColor = r->dColor;
         r->cur = prev;
         r->dColor = prev ? (float4*)r->ownColor2.p : (float4*)r->ownColor.p;
+    } else if (r->hPresent && !r->externalFB) {  // packed presentation image instead of the float one
+        CUDA_TRY(cudaMemcpyAsync(r->hPresent, r->presentBuf[0].p, (size_t)r->W * r->H * 4, cudaMemcpyDeviceToHost, s));
     } else if (r->hColor && !r->externalFB) {   // copy-back of the colour image, CU:3910-3914
         CUDA_TRY(cudaMemcpyAsync(r->hColor, r->dColor, (size_t)r->W * r->H * 16, cudaMemcpyDeviceToHost, s));
     }
@@ -398,6 +407,29 @@ int iftrcuSetStream(iftrcuRenderer* h, void* cudaStream) {
 
 static size_t flag_offset(int width, int height) { return (((size_t)width * height * 4) + 255) & ~(size_t)255; }
 
+// double buffering is on when it was asked for at bindFrameBuffer and there is a host image to copy into
+static int update_double_buffer(iftrcuRenderer* r) {
+    const bool want = r->wantDouble && !r->externalFB && (r->hColor || r->hPresent);
+    if (want == r->doubleBuffer) return IFRIT_OK;
+    CUDA_TRY(cudaStreamSynchronize(r->stream));
+    if (r->copyStream) CUDA_TRY(cudaStreamSynchronize(r->copyStream));
+    if (want) {
+        CUDA_TRY(r->ownColor2.ensure((size_t)r->W * r->H * 16));
+        CUDA_TRY(cudaMemcpyAsync(r->ownColor2.p, r->ownColor.p, (size_t)r->W * r->H * 16, cudaMemcpyDeviceToDevice, r->stream));
+        if (!r->copyStream) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&r->copyStream, cudaStreamNonBlocking));
+            for (int i = 0; i < 2; i++) {
+                CUDA_TRY(cudaEventCreateWithFlags(&r->evFrame[i], cudaEventDisableTiming));
+                CUDA_TRY(cudaEventCreateWithFlags(&r->evCopy[i], cudaEventDisableTiming));
+            }
+        }
+    }
+    r->doubleBuffer = want; r->cur = 0; r->lastColor = nullptr;
+    r->framePending[0] = r->framePending[1] = r->copyPending[0] = r->copyPending[1] = false;
+    r->dColor = (float4*)r->ownColor.p;
+    return IFRIT_OK;
+}
+
 static void reset_double_buffer(iftrcuRenderer* r) {
     if (r->copyStream) cudaStreamSynchronize(r->copyStream);
     r->doubleBuffer = false; r->cur = 0; r->lastColor = nullptr;
@@ -415,17 +447,7 @@ int iftrcuBindFrameBuffer(iftrcuRenderer* h, float* hostColor, float* hostDepth,
     r->frameFlags = (uint32_t*)((char*)r->ownDepth.p + flag_offset(width, height));
     CUDA_TRY(cudaMemsetAsync(r->frameFlags, 0, IFR_FLAG_WORDS * 4, r->stream));
     r->fencePending = false;
-    if (useDoubleBuffer && hostColor) {
-        CUDA_TRY(r->ownColor2.ensure((size_t)width * height * 16));
-        if (!r->copyStream) {
-            CUDA_TRY(cudaStreamCreateWithFlags(&r->copyStream, cudaStreamNonBlocking));
-            for (int i = 0; i < 2; i++) {
-                CUDA_TRY(cudaEventCreateWithFlags(&r->evFrame[i], cudaEventDisableTiming));
-                CUDA_TRY(cudaEventCreateWithFlags(&r->evCopy[i], cudaEventDisableTiming));
-            }
-        }
-        r->doubleBuffer = true;
-    }
+    r->wantDouble = useDoubleBuffer != 0;
     r->dColor = (float4*)r->ownColor.p; r->dDepth = (float*)r->ownDepth.p;
     r->externalFB = false;
     if (r->registeredHost) { cudaHostUnregister(r->registeredHost); r->registeredHost = nullptr; }
@@ -435,11 +457,49 @@ int iftrcuBindFrameBuffer(iftrcuRenderer* h, float* hostColor, float* hostDepth,
         if (cudaHostRegister(hostColor, (size_t)width * height * 16, cudaHostRegisterDefault) == cudaSuccess) r->registeredHost = hostColor;
         else cudaGetLastError();
         CUDA_TRY(cudaMemcpyAsync(r->dColor, hostColor, (size_t)width * height * 16, cudaMemcpyHostToDevice, r->stream));
-        if (r->doubleBuffer) CUDA_TRY(cudaMemcpyAsync(r->ownColor2.p, hostColor, (size_t)width * height * 16, cudaMemcpyHostToDevice, r->stream));
     }
     if (hostDepth) CUDA_TRY(cudaMemcpyAsync(r->dDepth, hostDepth, (size_t)width * height * 4, cudaMemcpyHostToDevice, r->stream));
     if (r->W != width || r->H != height) r->queueChecked = false;
     r->W = width; r->H = height;
+    if (r->presentFormat) {   // a presentation image stays bound across a re-bind of the same size
+        for (int i = 0; i < 2; i++) CUDA_TRY(r->presentBuf[i].ensure((size_t)width * height * 4));
+    }
+    return update_double_buffer(r);
+}
+
+/* Packed presentation image (the reference converts and copies RGBA32F on the host side of PCIe,
+ * CU:3893-3914 + docs/performance.md).  hostRGBA8: W*H*4 bytes, row-major, r in the low byte; NULL = device-only
+ * (iftrcuReadPresent).  While bound, every draw / clear also writes round(saturate(c) * 255) per channel next to
+ * the float colour (same kernel, no re-read), and the per-draw copy-back carries this image INSTEAD of the RGBA32F
+ * one (4x fewer bytes over PCIe); double buffering applies to it as to the float image. */
+int iftrcuBindPresentBuffer(iftrcuRenderer* h, void* hostRGBA8, int format) {
+    R_CHECK(h);
+    if (format != 0 && format != 1) return r->fail(IFRIT_ERR_UNSUPPORTED, "bindPresentBuffer", "format must be 0 (off) or 1 (RGBA8 UNORM)");
+    if (format && (!r->dColor || r->externalFB)) return r->fail(IFRIT_ERR_STATE, "bindPresentBuffer", "bind a renderer-owned framebuffer first (bindFrameBuffer)");
+    CUDA_TRY(cudaStreamSynchronize(r->stream));
+    if (r->copyStream) CUDA_TRY(cudaStreamSynchronize(r->copyStream));
+    if (r->registeredPresent) { cudaHostUnregister(r->registeredPresent); r->registeredPresent = nullptr; }
+    r->presentFormat = format; r->hPresent = format ? hostRGBA8 : nullptr;
+    if (format) {
+        for (int i = 0; i < 2; i++) {
+            CUDA_TRY(r->presentBuf[i].ensure((size_t)r->W * r->H * 4));
+            CUDA_TRY(cudaMemsetAsync(r->presentBuf[i].p, 0, (size_t)r->W * r->H * 4, r->stream));
+        }
+        if (hostRGBA8) {
+            if (cudaHostRegister(hostRGBA8, (size_t)r->W * r->H * 4, cudaHostRegisterDefault) == cudaSuccess) r->registeredPresent = hostRGBA8;
+            else cudaGetLastError();
+        }
+    }
+    return update_double_buffer(r);
+}
+
+int iftrcuReadPresent(iftrcuRenderer* h, void* dst) {
+    R_CHECK(h);
+    if (!dst || !r->presentFormat) return r->fail(IFRIT_ERR_STATE, "ReadPresent", "no presentation image bound");
+    int rc = flush_clear(r); if (rc) return rc;
+    rc = sync_and_check(r); if (rc) return rc;
+    const int k = (r->doubleBuffer && r->lastColor) ? (r->lastColor == (float4*)r->ownColor2.p ? 1 : 0) : 0;
+    CUDA_TRY(cudaMemcpy(dst, r->presentBuf[k].p, (size_t)r->W * r->H * 4, cudaMemcpyDeviceToHost));
     return IFRIT_OK;
 }
 
@@ -462,6 +522,7 @@ int iftrcuBindPeerFrameBuffer(iftrcuRenderer* h, const void* handle128, int widt
     CUDA_TRY(cudaStreamSynchronize(r->stream));
     close_peer(r);
     reset_double_buffer(r);
+    r->presentFormat = 0; r->hPresent = nullptr; r->wantDouble = false;
     cudaIpcMemHandle_t hc, hd;
     memcpy(&hc, handle128, 64); memcpy(&hd, (const char*)handle128 + 64, 64);
     CUDA_TRY(cudaIpcOpenMemHandle(&r->peerColor, hc, cudaIpcMemLazyEnablePeerAccess));
@@ -481,6 +542,7 @@ int iftrcuBindFrameBufferDevice(iftrcuRenderer* h, float* devColor, float* devDe
     CUDA_TRY(cudaStreamSynchronize(r->stream));
     close_peer(r);
     reset_double_buffer(r);
+    r->presentFormat = 0; r->hPresent = nullptr; r->wantDouble = false;
     if (r->registeredHost) { cudaHostUnregister(r->registeredHost); r->registeredHost = nullptr; }
     r->dColor = (float4*)devColor; r->dDepth = devDepth; r->externalFB = true; r->hColor = nullptr; r->hDepth = nullptr;
     r->frameFlags = nullptr; r->fencePending = false;

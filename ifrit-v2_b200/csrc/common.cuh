@@ -56,6 +56,7 @@ struct SampDesc { int filter, addrU, addrV, addrW, border, aniso; float maxAniso
 struct DrawParams {
     // framebuffer
     float4* color; float* depth; int32_t* primIds;
+    uint32_t* present;   // optional packed RGBA8 presentation image (iftrcuBindPresentBuffer), written with the colour
     int W, H, tilesX, tilesY;
     int msaa, depthFunc, cullMode, convention;
     int doClear; float clearColor[4]; float clearDepth;
@@ -86,6 +87,12 @@ struct DrawParams {
     // resources
     TexDesc tex[IFR_MAX_TEX]; SampDesc samp[IFR_MAX_TEX]; const float* buf[IFR_MAX_BUF];
 };
+
+// RGBA32F -> packed RGBA8 UNORM (r in the low byte): round-to-nearest-even of saturate(c) * 255
+__device__ __forceinline__ uint32_t ifr_pack_rgba8(const float4& c) {
+    return __float2uint_rn(__saturatef(c.x) * 255.0f) | (__float2uint_rn(__saturatef(c.y) * 255.0f) << 8) |
+           (__float2uint_rn(__saturatef(c.z) * 255.0f) << 16) | (__float2uint_rn(__saturatef(c.w) * 255.0f) << 24);
+}
 
 // sort-first ownership of a tile: 64-px super-tiles interleaved over ranks
 __host__ __device__ inline int ifr_tile_owner(int tx, int ty, int world) {

@@ -17,11 +17,12 @@ __global__ void __launch_bounds__(256) clear_kernel(const __grid_constant__ Draw
                 const float* s = p.scissor[k];
                 if ((float)x >= s[0] && (float)x <= s[0] + s[2] && (float)y >= s[1] && (float)y <= s[1] + s[3]) pass = true;
             }
-            if (!pass) continue;
+            if (!pass) { if (p.present) p.present[i] = ifr_pack_rgba8(p.color[i]); continue; }
         }
         if (p.world > 1 && ifr_tile_owner((int)(i % p.W) / IFR_TILE, (int)(i / p.W) / IFR_TILE, p.world) != p.rank) continue;
         p.color[i] = c;
         p.depth[i] = p.clearDepth;
+        if (p.present) p.present[i] = ifr_pack_rgba8(c);
     }
 }
 

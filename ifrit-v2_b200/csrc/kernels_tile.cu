@@ -419,10 +419,16 @@ __global__ void __launch_bounds__(256, (S == 1 && FsTraits<FS>::needsDerivs) ? I
     const size_t pidx = (size_t)py * p.W + px;
     if (nSmall + nBig == 0) {
         // nothing binned here: the fused clear is all there is to do (imageResetFloat32* CU:3337/3363)
-        if (!p.doClear || !inFrame) return;
+        if (!inFrame) return;
+        if (!p.doClear || !scis) {
+            if (p.present) p.present[pidx] = ifr_pack_rgba8(p.color[pidx]);   // untouched pixel: present what is there
+            if (!p.doClear) return;
+        }
         if (scis) {
-            p.color[pidx] = make_float4(p.clearColor[0], p.clearColor[1], p.clearColor[2], p.clearColor[3]);
+            const float4 cc = make_float4(p.clearColor[0], p.clearColor[1], p.clearColor[2], p.clearColor[3]);
+            p.color[pidx] = cc;
             p.depth[pidx] = p.clearDepth;
+            if (p.present) p.present[pidx] = ifr_pack_rgba8(cc);
         }
         if (p.primIds) {
 #pragma unroll
@@ -583,6 +589,9 @@ __global__ void __launch_bounds__(256, (S == 1 && FsTraits<FS>::needsDerivs) ? I
             }
             p.color[pidx] = out;
             p.depth[pidx] = dout;
+            if (p.present) p.present[pidx] = ifr_pack_rgba8(out);
+        } else if (p.present) {
+            p.present[pidx] = ifr_pack_rgba8(p.color[pidx]);   // untouched pixel (no clear, nothing drawn): present what is there
         }
     }
     myFrags = __reduce_add_sync(0xffffffffu, myFrags);

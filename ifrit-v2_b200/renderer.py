@@ -212,6 +212,17 @@ class TileRasterRendererCuda:
         self.width, self.height = width, height
         self._ck(self._lib.iftrcuBindFrameBufferDevice(self._h, _ptr(color), _ptr(depth), width, height))
 
+    def bindPresentBuffer(self, host_rgba8, fmt=1):
+        """host_rgba8: uint8 [H,W,4] (or None for a device-only image); fmt 1 = RGBA8 UNORM, 0 = off.  While bound,
+        the per-draw copy-back carries this packed image instead of the RGBA32F one."""
+        self._keep["present"] = host_rgba8
+        self._ck(self._lib.iftrcuBindPresentBuffer(self._h, _ptr(host_rgba8), int(fmt)))
+
+    def readPresent(self):
+        out = np.empty((self.height, self.width, 4), dtype=np.uint8)
+        self._ck(self._lib.iftrcuReadPresent(self._h, _ptr(out)))
+        return out
+
     def copyColorToHostAsync(self, host_ptr):
         self._ck(self._lib.iftrcuCopyColorToHostAsync(self._h, C.c_void_p(host_ptr)))
 

@@ -245,6 +245,13 @@ IFRIT_B200_API int iftrcuReadAssembled(iftrcuRenderer* h, iftrcuAssembledTriangl
 /* asynchronous colour read-back on the renderer's stream (the reference's double-buffered copy, CU:3899-3909);
  * hostDst should be pinned; ordered after every draw issued so far */
 IFRIT_B200_API int iftrcuCopyColorToHostAsync(iftrcuRenderer* h, void* hostDst);
+/* Packed presentation image (the step after the path — the reference copies RGBA32F over PCIe
+ * and is bound by it, CU:3893-3914, docs/performance.md).  hostRGBA8: width*height*4 bytes, row-major, r in the low
+ * byte, or NULL for a device-only image; format 1 = RGBA8 UNORM, 0 = off.  While bound, every draw / clear also
+ * writes round(saturate(c) * 255) per channel next to the float colour (same kernel, no re-read) and the per-draw
+ * copy-back carries this image INSTEAD of the RGBA32F one; useDoubleBuffer applies to it as to the float image. */
+IFRIT_B200_API int iftrcuBindPresentBuffer(iftrcuRenderer* h, void* hostRGBA8, int format);
+IFRIT_B200_API int iftrcuReadPresent(iftrcuRenderer* h, void* dstRGBA8);
 IFRIT_B200_API int iftrcuExportFrameBuffer(iftrcuRenderer* h, void* handleOut128);
 IFRIT_B200_API int iftrcuBindPeerFrameBuffer(iftrcuRenderer* h, const void* handle128, int width, int height);
 /* Sort-first frame flags (peer-memory mode; no reference counterpart — the reference is single-GPU).

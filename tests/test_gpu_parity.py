@@ -103,6 +103,50 @@ def test_double_buffered_readback_lags_one_frame(gpu_renderer_factory):
             assert np.array_equal(host.view(np.uint32), frames[-2].view(np.uint32))
 
 
+def _pack8(color):
+    return np.rint(np.clip(color, 0, 1) * np.float32(255)).astype(np.uint8)
+
+
+def test_rgba8_present_image(gpu_renderer_factory):
+    """the packed presentation image is written by the same kernels as the float colour and is what
+    the per-draw copy-back carries; it equals round(saturate(colour) * 255) of the float frame for every pixel —
+    drawn, cleared, scissored out or left untouched by a draw without clear — with and without double buffering."""
+    from ifrit_v2_b200 import renderer as R
+    W, H = 200, 120
+    r2 = gpu_renderer_factory()
+    host8 = np.zeros((H, W, 4), np.uint8)
+    start = np.random.default_rng(5).random((H, W, 4), dtype=np.float32)
+    r2.bindFrameBuffer(start.copy(), None, W, H, useDoubleBuffer=False)
+    r2.bindPresentBuffer(host8)
+    vb, idx = scenes.random_tris(60, 91, size=0.4)
+    vb[:, 4:8] = vb[:, 4:8] * 1.6 - 0.3          # colours outside [0, 1]: saturation
+    sc = [(10, 8, 120, 70)]
+    kw = dict(msaa=4, scissors=sc, clear=False, color=start, depth=np.zeros((H, W), np.float32), depth_func=O.CMP_ALWAYS)
+    o = oracle_draw(W, H, vb, idx, 0, O.FS_VARYING0, 1, IDENT, **kw)
+    R.setup_scene(r2, vb, idx, 0, O.FS_VARYING0, 1, IDENT)
+    r2.setMsaaSamples(4); r2.SetDepthFunc(O.CMP_ALWAYS)
+    r2.SetScissors(sc); r2.setScissorTestEnable(True)
+    r2.drawElements()                                # no clear: untouched pixels present what the framebuffer holds
+    r2.synchronize()
+    col = r2.readColor()
+    assert (np.abs(col - o["color"]).max(-1) <= 1e-6).mean() > 0.999
+    assert np.array_equal(host8, _pack8(col))
+    assert np.array_equal(r2.readPresent(), host8)
+    # cleared frame, double buffered: the host image lags one draw
+    r2.bindFrameBuffer(np.zeros((H, W, 4), np.float32), None, W, H, useDoubleBuffer=True)
+    r2.setScissorTestEnable(False); r2.setMsaaSamples(1)
+    r2.setClearValues([(.25, .5, .75, 1)], 1.0)
+    frames = []
+    for seed in (92, 93):
+        vb, idx = scenes.random_tris(60, seed, size=0.4)
+        R.setup_scene(r2, vb, idx, 0, O.FS_VARYING0, 1, IDENT)
+        r2.clear(); r2.drawElements(); r2.synchronize()
+        frames.append(_pack8(r2.readColor()))
+        assert np.array_equal(r2.readPresent(), frames[-1])
+    assert np.array_equal(host8, frames[0])
+    r2.bindPresentBuffer(None, 0)
+
+
 def test_standalone_vertex_stage_matches_fused(r):
     """vertexProcessingKernel CU:330 as its own kernel (pos / vary buffers) vs fused into triangle setup."""
     W, H = 320, 200
