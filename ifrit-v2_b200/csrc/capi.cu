@@ -14,7 +14,7 @@
 #include "../../include/ifrit_b200.h"
 
 #define IFR_PROF_RING 256
-#define IFR_PROF_EVENTS 6   // before vs | setup | scan | fill | tile | after tile
+#define IFR_PROF_EVENTS 7   // before vs | setup | scan | fill | after fill (geometry stream) || before tile | after tile (draw stream)
 
 namespace {
 
@@ -92,10 +92,18 @@ struct iftrcuRenderer {
     SampDesc samp[IFR_MAX_TEX];
     DevBuf bufMem[IFR_MAX_BUF]; int bufSize[IFR_MAX_BUF] = {0};
 
-    // scratch
-    DevBuf scanPartial; uint32_t epoch = 0;
-    DevBuf pos, vary, rec, clipBary, tileBox, fan1List, heavyBits, tileCount, tileStart, tileCursor, queue, bigQueue, counters;
-    bool queueChecked = false;   // queue capacity verified for the current geometry / state
+    // scratch: two sets, so that the geometry stage of frame k + 1 (setup / scan / fill on the geometry stream) can run
+    // while the tile kernel of frame k (draw stream) still reads the queues of frame k — iftrcuSetFramePipelining
+    struct Scratch {
+        DevBuf scanPartial, pos, vary, rec, clipBary, tileBox, fan1List, heavyBits, tileCount, tileStart, tileCursor, queue, bigQueue, counters;
+        bool queueChecked = false;   // queue capacity verified for the current geometry / state
+    } scr[2];
+    int set = 0;                 // scratch set of the current / most recent draw
+    uint32_t epoch = 0;
+    bool pipelining = true;
+    cudaStream_t geomStream = nullptr;
+    cudaEvent_t evGeomDone[2] = {nullptr, nullptr}, evTileDone[2] = {nullptr, nullptr}, evInputs = nullptr;
+    bool tilePending[2] = {false, false}, inputsDirty = false;
     unsigned long long* hCounters = nullptr;   // pinned, 8 entries
     bool haveDraw = false;
     iftrcuStats stats;
@@ -182,23 +190,23 @@ static void build_params(iftrcuRenderer* r, DrawParams& p) {
     p.vb = r->dVB; p.stride = r->stride; p.nattr = r->nattr; p.nvary = r->nvary; p.nverts = r->nverts;
     memcpy(p.attrOff, r->attrOff, sizeof p.attrOff);
     p.ib = r->dIB; p.ntri = r->icount / 3;
-    p.pos = (float4*)r->pos.p; p.vary = (float4*)r->vary.p;
+    p.pos = (float4*)r->scr[r->set].pos.p; p.vary = (float4*)r->scr[r->set].vary.p;
     if (r->fusedVS) {
         p.varyBase = r->dVB; p.varyStride = r->stride;
         for (int k = 0; k < IFR_MAX_VARY; k++) p.varyOff[k] = r->attrOff[k + 1];
     } else {
-        p.varyBase = (const uint8_t*)r->vary.p; p.varyStride = r->nvary * 16;
+        p.varyBase = (const uint8_t*)r->scr[r->set].vary.p; p.varyStride = r->nvary * 16;
         for (int k = 0; k < IFR_MAX_VARY; k++) p.varyOff[k] = 16 * k;
     }
-    p.rec = (TriRec*)r->rec.p; p.clipBary = (float*)r->clipBary.p; p.tileBox = (uint2*)r->tileBox.p;
-    p.fan1List = (uint32_t*)r->fan1List.p; p.heavyBits = (uint32_t*)r->heavyBits.p;
-    p.tileCount = (uint32_t*)r->tileCount.p; p.tileStart = (uint32_t*)r->tileStart.p;
-    p.tileCursor = (uint32_t*)r->tileCursor.p; p.queue = (uint32_t*)r->queue.p;
-    p.queueCap = (uint32_t)std::min<size_t>(r->queue.cap / 4, 0xffffffffu);
-    p.bigQueue = (TriS*)r->bigQueue.p;
-    p.bigCap = (uint32_t)std::min<size_t>(r->bigQueue.cap / sizeof(TriS), 0xffffffffu);
-    p.counters = (unsigned long long*)r->counters.p;
-    p.scanPartial = (unsigned long long*)r->scanPartial.p; p.epoch = r->epoch;
+    p.rec = (TriRec*)r->scr[r->set].rec.p; p.clipBary = (float*)r->scr[r->set].clipBary.p; p.tileBox = (uint2*)r->scr[r->set].tileBox.p;
+    p.fan1List = (uint32_t*)r->scr[r->set].fan1List.p; p.heavyBits = (uint32_t*)r->scr[r->set].heavyBits.p;
+    p.tileCount = (uint32_t*)r->scr[r->set].tileCount.p; p.tileStart = (uint32_t*)r->scr[r->set].tileStart.p;
+    p.tileCursor = (uint32_t*)r->scr[r->set].tileCursor.p; p.queue = (uint32_t*)r->scr[r->set].queue.p;
+    p.queueCap = (uint32_t)std::min<size_t>(r->scr[r->set].queue.cap / 4, 0xffffffffu);
+    p.bigQueue = (TriS*)r->scr[r->set].bigQueue.p;
+    p.bigCap = (uint32_t)std::min<size_t>(r->scr[r->set].bigQueue.cap / sizeof(TriS), 0xffffffffu);
+    p.counters = (unsigned long long*)r->scr[r->set].counters.p;
+    p.scanPartial = (unsigned long long*)r->scr[r->set].scanPartial.p; p.epoch = r->epoch;
     for (int i = 0; i < IFR_MAX_TEX; i++) { p.tex[i] = r->tex[i]; p.samp[i] = r->samp[i]; }
     for (int i = 0; i < IFR_MAX_BUF; i++) p.buf[i] = (const float*)r->bufMem[i].p;
 }
@@ -206,29 +214,56 @@ static void build_params(iftrcuRenderer* r, DrawParams& p) {
 static int ensure_scratch(iftrcuRenderer* r) {
     const size_t ntri = (size_t)r->icount / 3, ntiles = (size_t)((r->W + 15) / 16) * ((r->H + 15) / 16);
     if (!r->fusedVS) {
-        CUDA_TRY(r->pos.ensure(std::max<size_t>(1, r->nverts) * sizeof(float4)));
-        CUDA_TRY(r->vary.ensure(std::max<size_t>(1, (size_t)r->nverts * std::max(1, r->nvary)) * sizeof(float4)));
+        CUDA_TRY(r->scr[r->set].pos.ensure(std::max<size_t>(1, r->nverts) * sizeof(float4)));
+        CUDA_TRY(r->scr[r->set].vary.ensure(std::max<size_t>(1, (size_t)r->nverts * std::max(1, r->nvary)) * sizeof(float4)));
     }
-    CUDA_TRY(r->rec.ensure(std::max<size_t>(1, 2 * ntri) * sizeof(TriRec)));
-    CUDA_TRY(r->clipBary.ensure(std::max<size_t>(1, 2 * ntri) * 6 * sizeof(float)));
-    CUDA_TRY(r->tileBox.ensure(std::max<size_t>(1, 2 * ntri) * sizeof(uint2)));
-    CUDA_TRY(r->fan1List.ensure(std::max<size_t>(1, ntri) * sizeof(uint32_t)));
-    CUDA_TRY(r->heavyBits.ensure((ntri / 32 + 2) * sizeof(uint32_t)));
-    CUDA_TRY(r->tileCount.ensure(2 * ntiles * 4));
-    CUDA_TRY(r->tileStart.ensure(2 * (ntiles + 1) * 4));
-    CUDA_TRY(r->tileCursor.ensure(2 * ntiles * 4));
-    CUDA_TRY(r->counters.ensure(8 * 8));
-    if (!r->scanPartial.p || r->scanPartial.cap < 2 * (ntiles / 4096 + 1) * 8) {
-        CUDA_TRY(r->scanPartial.ensure(2 * (ntiles / 4096 + 1) * 8));
-        CUDA_TRY(cudaMemsetAsync(r->scanPartial.p, 0, r->scanPartial.cap, r->stream));
+    CUDA_TRY(r->scr[r->set].rec.ensure(std::max<size_t>(1, 2 * ntri) * sizeof(TriRec)));
+    CUDA_TRY(r->scr[r->set].clipBary.ensure(std::max<size_t>(1, 2 * ntri) * 6 * sizeof(float)));
+    CUDA_TRY(r->scr[r->set].tileBox.ensure(std::max<size_t>(1, 2 * ntri) * sizeof(uint2)));
+    CUDA_TRY(r->scr[r->set].fan1List.ensure(std::max<size_t>(1, ntri) * sizeof(uint32_t)));
+    CUDA_TRY(r->scr[r->set].heavyBits.ensure((ntri / 32 + 2) * sizeof(uint32_t)));
+    CUDA_TRY(r->scr[r->set].tileCount.ensure(2 * ntiles * 4));
+    CUDA_TRY(r->scr[r->set].tileStart.ensure(2 * (ntiles + 1) * 4));
+    CUDA_TRY(r->scr[r->set].tileCursor.ensure(2 * ntiles * 4));
+    CUDA_TRY(r->scr[r->set].counters.ensure(8 * 8));
+    if (!r->scr[r->set].scanPartial.p || r->scr[r->set].scanPartial.cap < 2 * (ntiles / 4096 + 1) * 8) {
+        CUDA_TRY(r->scr[r->set].scanPartial.ensure(2 * (ntiles / 4096 + 1) * 8));
+        CUDA_TRY(cudaMemsetAsync(r->scr[r->set].scanPartial.p, 0, r->scr[r->set].scanPartial.cap, (r->pipelining && r->geomStream) ? r->geomStream : r->stream));
     }
-    if (!r->queue.p) CUDA_TRY(r->queue.ensure(std::max<size_t>(ntri * 2 + ntiles, 1024) * 4));
-    if (!r->bigQueue.p) CUDA_TRY(r->bigQueue.ensure(std::max<size_t>(ntri / 4 + ntiles, 1024) * sizeof(TriS)));
+    if (!r->scr[r->set].queue.p) CUDA_TRY(r->scr[r->set].queue.ensure(std::max<size_t>(ntri * 2 + ntiles, 1024) * 4));
+    if (!r->scr[r->set].bigQueue.p) CUDA_TRY(r->scr[r->set].bigQueue.ensure(std::max<size_t>(ntri / 4 + ntiles, 1024) * sizeof(TriS)));
     if (r->debugIds) CUDA_TRY(r->primIds.ensure((size_t)r->W * r->H * r->msaa * 4));
     return IFRIT_OK;
 }
 
-static int issue_draw(iftrcuRenderer* r, bool forceCheck) {
+static int ensure_pipeline(iftrcuRenderer* r) {
+    if (r->geomStream) return IFRIT_OK;
+    // highest priority: the geometry kernels are small and latency bound; their CTAs must not queue behind the tens of
+    // thousands of tile-kernel CTAs of the previous frame, or nothing overlaps
+    int prLow = 0, prHigh = 0;
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prLow, &prHigh));
+    CUDA_TRY(cudaStreamCreateWithPriority(&r->geomStream, cudaStreamNonBlocking, prHigh));
+    for (int k = 0; k < 2; k++) {
+        CUDA_TRY(cudaEventCreateWithFlags(&r->evGeomDone[k], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&r->evTileDone[k], cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventCreateWithFlags(&r->evInputs, cudaEventDisableTiming));
+    return IFRIT_OK;
+}
+
+// inputs of the geometry stage (vertex / index / uniform buffers) were touched on the draw stream
+static void mark_inputs(iftrcuRenderer* r) {
+    if (r->evInputs && cudaEventRecord(r->evInputs, r->stream) == cudaSuccess) r->inputsDirty = true;
+}
+
+// One draw = geometry stage (memsets, setup + count, scan, fill) + tile kernel.  With frame pipelining (default) the
+// geometry stage runs on its own stream into scratch set k & 1 and only the tile kernel sits on the caller's stream:
+// frame k + 1's geometry overlaps frame k's tile kernel; events order (a) geometry after the last change of its
+// inputs, (b) geometry after the tile kernel that last read the same scratch set, (c) the tile kernel after its geometry.
+static int issue_draw(iftrcuRenderer* r, bool forceCheck, bool sameSet = false) {
+    const bool pipe = r->pipelining;
+    if (pipe) { int rc0 = ensure_pipeline(r); if (rc0) return rc0; }
+    if (!sameSet) r->set = pipe ? 1 - r->set : 0;
     int rc = ensure_scratch(r);
     if (rc) return rc;
     DrawParams p;
@@ -236,34 +271,45 @@ static int issue_draw(iftrcuRenderer* r, bool forceCheck) {
     if (r->epoch == 0) r->epoch = 1;
     build_params(r, p);
     const size_t ntiles = (size_t)p.tilesX * p.tilesY;
-    cudaStream_t s = r->stream;
-    CUDA_TRY(cudaMemsetAsync(r->tileCount.p, 0, 2 * ntiles * 4, s));
-    CUDA_TRY(cudaMemsetAsync(r->counters.p, 0, 64, s));
+    cudaStream_t s = r->stream;                       // draw stream: tile kernel, read-backs
+    cudaStream_t g = pipe ? r->geomStream : s;        // geometry stream
+    iftrcuRenderer::Scratch& sc = r->scr[r->set];
+    if (pipe) {
+        if (r->tilePending[r->set]) { CUDA_TRY(cudaStreamWaitEvent(g, r->evTileDone[r->set], 0)); r->tilePending[r->set] = false; }
+        if (r->inputsDirty) { CUDA_TRY(cudaStreamWaitEvent(g, r->evInputs, 0)); r->inputsDirty = false; }
+    }
+    CUDA_TRY(cudaMemsetAsync(sc.tileCount.p, 0, 2 * ntiles * 4, g));
+    CUDA_TRY(cudaMemsetAsync(sc.counters.p, 0, 64, g));
     cudaEvent_t* ev = nullptr;
-    if (r->profiling && !forceCheck && r->queueChecked) ev = &r->profEvents[(r->profDraws % IFR_PROF_RING) * IFR_PROF_EVENTS];
-    if (ev) CUDA_TRY(cudaEventRecord(ev[0], s));
-    if (!r->fusedVS) { CUDA_TRY(ifr_launch_vertex(p, r->vsId, s)); r->stats.kernel_launches += 1; }
-    if (ev) CUDA_TRY(cudaEventRecord(ev[1], s));
-    CUDA_TRY(ifr_launch_setup_count(p, r->fusedVS ? r->vsId : -1, s));
-    if (ev) CUDA_TRY(cudaEventRecord(ev[2], s));
-    CUDA_TRY(ifr_launch_scan(p, s));
-    if (ev) CUDA_TRY(cudaEventRecord(ev[3], s));
+    if (r->profiling && !forceCheck && sc.queueChecked) ev = &r->profEvents[(r->profDraws % IFR_PROF_RING) * IFR_PROF_EVENTS];
+    if (ev) CUDA_TRY(cudaEventRecord(ev[0], g));
+    if (!r->fusedVS) { CUDA_TRY(ifr_launch_vertex(p, r->vsId, g)); r->stats.kernel_launches += 1; }
+    if (ev) CUDA_TRY(cudaEventRecord(ev[1], g));
+    CUDA_TRY(ifr_launch_setup_count(p, r->fusedVS ? r->vsId : -1, g));
+    if (ev) CUDA_TRY(cudaEventRecord(ev[2], g));
+    CUDA_TRY(ifr_launch_scan(p, g));
+    if (ev) CUDA_TRY(cudaEventRecord(ev[3], g));
     r->stats.kernel_launches += 2;
-    if (forceCheck || !r->queueChecked) {
+    if (forceCheck || !sc.queueChecked) {
         // first draw with this geometry / state: size the (triangle, tile) queue exactly (one sync)
         unsigned long long c[8];
-        CUDA_TRY(cudaMemcpyAsync(c, r->counters.p, 64, cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaStreamSynchronize(s));
+        CUDA_TRY(cudaMemcpyAsync(c, sc.counters.p, 64, cudaMemcpyDeviceToHost, g));
+        CUDA_TRY(cudaStreamSynchronize(g));
         if (c[3]) {
-            CUDA_TRY(r->queue.ensure((size_t)(c[1] + c[1] / 4 + 1024) * 4));
-            CUDA_TRY(r->bigQueue.ensure((size_t)(c[5] + c[5] / 4 + 1024) * sizeof(TriS)));
-            CUDA_TRY(cudaMemsetAsync((char*)r->counters.p + 24, 0, 8, s));
+            CUDA_TRY(cudaStreamSynchronize(s));   // DevBuf::ensure frees: nothing may still read the old queues
+            CUDA_TRY(sc.queue.ensure((size_t)(c[1] + c[1] / 4 + 1024) * 4));
+            CUDA_TRY(sc.bigQueue.ensure((size_t)(c[5] + c[5] / 4 + 1024) * sizeof(TriS)));
+            CUDA_TRY(cudaMemsetAsync((char*)sc.counters.p + 24, 0, 8, g));
             build_params(r, p);
         }
-        r->queueChecked = true;
+        sc.queueChecked = true;
     }
-    CUDA_TRY(ifr_launch_fill(p, s));
-    if (ev) CUDA_TRY(cudaEventRecord(ev[4], s));
+    CUDA_TRY(ifr_launch_fill(p, g));
+    if (ev) CUDA_TRY(cudaEventRecord(ev[4], g));
+    if (pipe) {
+        CUDA_TRY(cudaEventRecord(r->evGeomDone[r->set], g));
+        CUDA_TRY(cudaStreamWaitEvent(s, r->evGeomDone[r->set], 0));
+    }
     if (r->fencePending && r->frameFlags) {   // sort-first peer: the owner must have released the frame these tiles overwrite
         CUDA_TRY(ifr_launch_flag_wait(r->frameFlags + 64, 1, r->fenceFrame, r->hTimedOut, s));
         r->fencePending = false;
@@ -272,10 +318,12 @@ static int issue_draw(iftrcuRenderer* r, bool forceCheck) {
         CUDA_TRY(cudaStreamWaitEvent(s, r->evCopy[r->cur], 0));
         r->copyPending[r->cur] = false;
     }
+    if (ev) CUDA_TRY(cudaEventRecord(ev[5], s));
     CUDA_TRY(ifr_launch_tiles(p, r->fsId, s));
-    if (ev) { CUDA_TRY(cudaEventRecord(ev[5], s)); r->profDraws++; }
+    if (ev) { CUDA_TRY(cudaEventRecord(ev[6], s)); r->profDraws++; }
+    if (pipe) { CUDA_TRY(cudaEventRecord(r->evTileDone[r->set], s)); r->tilePending[r->set] = true; }
     r->stats.kernel_launches += 3;
-    CUDA_TRY(cudaMemcpyAsync(r->hCounters, r->counters.p, 64, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(r->hCounters, r->scr[r->set].counters.p, 64, cudaMemcpyDeviceToHost, s));
     r->lastDrawCleared = r->pendingClear;
     r->pendingClear = false;
     r->haveDraw = true;
@@ -319,6 +367,7 @@ static int flush_clear(iftrcuRenderer* r) {
 }
 
 static int sync_and_check(iftrcuRenderer* r) {
+    if (r->geomStream) CUDA_TRY(cudaStreamSynchronize(r->geomStream));
     CUDA_TRY(cudaStreamSynchronize(r->stream));
     if (r->doubleBuffer) CUDA_TRY(cudaStreamSynchronize(r->copyStream));
     if (r->haveDraw && r->hCounters[3]) {
@@ -329,7 +378,7 @@ static int sync_and_check(iftrcuRenderer* r) {
             r->cur = 1 - r->cur;
             r->dColor = r->cur ? (float4*)r->ownColor2.p : (float4*)r->ownColor.p;
         }
-        int rc = issue_draw(r, true);
+        int rc = issue_draw(r, true, true);
         if (rc) return rc;
         CUDA_TRY(cudaStreamSynchronize(r->stream));
         if (r->doubleBuffer) CUDA_TRY(cudaStreamSynchronize(r->copyStream));
@@ -369,6 +418,7 @@ int iftrcuCreateInstance(int cudaDevice, iftrcuRenderer** out) {
     }
     memset(r->hCounters, 0, 64);
     memset(r->hTimedOut, 0, 64);
+    if (ensure_pipeline(r) != IFRIT_OK) { iftrcuDestroyInstance(r); return IFRIT_ERR_CUDA; }
     r->stream = r->ownStream;
     *out = r;
     return IFRIT_OK;
@@ -381,8 +431,17 @@ int iftrcuDestroyInstance(iftrcuRenderer* h) {
     close_peer(r);
     if (r->copyStream) { cudaStreamSynchronize(r->copyStream); cudaStreamDestroy(r->copyStream); }
     for (int i = 0; i < 2; i++) { if (r->evFrame[i]) cudaEventDestroy(r->evFrame[i]); if (r->evCopy[i]) cudaEventDestroy(r->evCopy[i]); }
-    DevBuf* bufs[] = {&r->ownColor, &r->ownColor2, &r->ownDepth, &r->primIds, &r->ownVB, &r->ownIB, &r->pos, &r->vary, &r->rec, &r->clipBary,
-                      &r->scanPartial, &r->tileBox, &r->fan1List, &r->heavyBits, &r->tileCount, &r->tileStart, &r->tileCursor, &r->queue, &r->bigQueue, &r->counters};
+    DevBuf* bufs[] = {&r->ownColor, &r->ownColor2, &r->ownDepth, &r->primIds, &r->ownVB, &r->ownIB};
+    for (int k = 0; k < 2; k++) {
+        iftrcuRenderer::Scratch& c = r->scr[k];
+        DevBuf* sb[] = {&c.scanPartial, &c.pos, &c.vary, &c.rec, &c.clipBary, &c.tileBox, &c.fan1List, &c.heavyBits, &c.tileCount, &c.tileStart,
+                        &c.tileCursor, &c.queue, &c.bigQueue, &c.counters};
+        for (DevBuf* b : sb) b->release();
+        if (r->evGeomDone[k]) cudaEventDestroy(r->evGeomDone[k]);
+        if (r->evTileDone[k]) cudaEventDestroy(r->evTileDone[k]);
+    }
+    if (r->evInputs) cudaEventDestroy(r->evInputs);
+    if (r->geomStream) { cudaStreamSynchronize(r->geomStream); cudaStreamDestroy(r->geomStream); }
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < IFR_MAX_TEX; i++) { destroy_tex_objects(r, i); r->texMem[i].release(); }
     for (int i = 0; i < IFR_MAX_BUF; i++) r->bufMem[i].release();
@@ -400,8 +459,11 @@ const char* iftrcuGetLastError(iftrcuRenderer* h) { return h ? h->lastError.c_st
 
 int iftrcuSetStream(iftrcuRenderer* h, void* cudaStream) {
     R_CHECK(h);
+    if (r->geomStream) cudaStreamSynchronize(r->geomStream);
     cudaStreamSynchronize(r->stream);
+    r->tilePending[0] = r->tilePending[1] = false;
     r->stream = (cudaStream == (void*)-1) ? r->ownStream : (cudaStream_t)cudaStream;   // NULL = legacy default stream
+    mark_inputs(r);
     return IFRIT_OK;
 }
 
@@ -459,7 +521,7 @@ int iftrcuBindFrameBuffer(iftrcuRenderer* h, float* hostColor, float* hostDepth,
         CUDA_TRY(cudaMemcpyAsync(r->dColor, hostColor, (size_t)width * height * 16, cudaMemcpyHostToDevice, r->stream));
     }
     if (hostDepth) CUDA_TRY(cudaMemcpyAsync(r->dDepth, hostDepth, (size_t)width * height * 4, cudaMemcpyHostToDevice, r->stream));
-    if (r->W != width || r->H != height) r->queueChecked = false;
+    if (r->W != width || r->H != height) r->scr[0].queueChecked = r->scr[1].queueChecked = false;
     r->W = width; r->H = height;
     if (r->presentFormat) {   // a presentation image stays bound across a re-bind of the same size
         for (int i = 0; i < 2; i++) CUDA_TRY(r->presentBuf[i].ensure((size_t)width * height * 4));
@@ -531,7 +593,7 @@ int iftrcuBindPeerFrameBuffer(iftrcuRenderer* h, const void* handle128, int widt
     r->dColor = (float4*)r->peerColor; r->dDepth = (float*)r->peerDepth; r->externalFB = true; r->hColor = nullptr; r->hDepth = nullptr;
     r->frameFlags = (uint32_t*)((char*)r->peerDepth + flag_offset(width, height));
     r->fencePending = false;
-    if (r->W != width || r->H != height) r->queueChecked = false;
+    if (r->W != width || r->H != height) r->scr[0].queueChecked = r->scr[1].queueChecked = false;
     r->W = width; r->H = height;
     return IFRIT_OK;
 }
@@ -546,7 +608,7 @@ int iftrcuBindFrameBufferDevice(iftrcuRenderer* h, float* devColor, float* devDe
     if (r->registeredHost) { cudaHostUnregister(r->registeredHost); r->registeredHost = nullptr; }
     r->dColor = (float4*)devColor; r->dDepth = devDepth; r->externalFB = true; r->hColor = nullptr; r->hDepth = nullptr;
     r->frameFlags = nullptr; r->fencePending = false;
-    if (r->W != width || r->H != height) r->queueChecked = false;
+    if (r->W != width || r->H != height) r->scr[0].queueChecked = r->scr[1].queueChecked = false;
     r->W = width; r->H = height;
     return IFRIT_OK;
 }
@@ -564,6 +626,7 @@ static int bind_vb(iftrcuRenderer* r, const void* data, int vertexCount, const i
         CUDA_TRY(cudaMemcpyAsync(r->ownVB.p, data, (size_t)vertexCount * r->stride, cudaMemcpyHostToDevice, r->stream));
         r->dVB = (const uint8_t*)r->ownVB.p;
     }
+    mark_inputs(r);
     return IFRIT_OK;
 }
 int iftrcuBindVertexBuffer(iftrcuRenderer* h, const void* hostData, int vertexCount, const int* typeDescs, int n) {
@@ -575,7 +638,7 @@ int iftrcuBindVertexBufferDevice(iftrcuRenderer* h, const void* devData, int ver
 
 static int bind_ib(iftrcuRenderer* r, const int* idx, int count, bool device) {
     if (!idx || count < 0 || count % 3) return r->fail(IFRIT_ERR_INVALID, "bindIndexBuffer", "count must be a multiple of 3");
-    if (count != r->icount) r->queueChecked = false;
+    if (count != r->icount) r->scr[0].queueChecked = r->scr[1].queueChecked = false;
     r->icount = count;
     if (device) {
         r->dIB = idx;
@@ -584,6 +647,7 @@ static int bind_ib(iftrcuRenderer* r, const int* idx, int count, bool device) {
         CUDA_TRY(cudaMemcpyAsync(r->ownIB.p, idx, (size_t)count * 4, cudaMemcpyHostToDevice, r->stream));
         r->dIB = (const int32_t*)r->ownIB.p;
     }
+    mark_inputs(r);
     return IFRIT_OK;
 }
 int iftrcuBindIndexBuffer(iftrcuRenderer* h, const int* hostIndices, int indexCount) { R_CHECK(h); return bind_ib(r, hostIndices, indexCount, false); }
@@ -725,14 +789,17 @@ int iftrcuCreateBuffer(iftrcuRenderer* h, int slot, int bufSize) {
     R_CHECK(h);
     if (slot < 0 || slot >= IFR_MAX_BUF || bufSize <= 0) return r->fail(IFRIT_ERR_INVALID, "CreateBuffer", "bad argument");
     CUDA_TRY(cudaStreamSynchronize(r->stream));
+    if (r->geomStream) CUDA_TRY(cudaStreamSynchronize(r->geomStream));
     CUDA_TRY(r->bufMem[slot].ensure((size_t)bufSize));
     r->bufSize[slot] = bufSize;
+    mark_inputs(r);
     return IFRIT_OK;
 }
 int iftrcuCopyHostBufferToBuffer(iftrcuRenderer* h, const void* src, int dstSlot, int size) {
     R_CHECK(h);
     if (dstSlot < 0 || dstSlot >= IFR_MAX_BUF || !src || size < 0 || size > r->bufSize[dstSlot]) return r->fail(IFRIT_ERR_INVALID, "copyHostBufferToBuffer", "bad argument");
     CUDA_TRY(cudaMemcpyAsync(r->bufMem[dstSlot].p, src, (size_t)size, cudaMemcpyHostToDevice, r->stream));
+    mark_inputs(r);
     return IFRIT_OK;
 }
 
@@ -747,7 +814,7 @@ int iftrcuSetScissorTestEnable(iftrcuRenderer* h, int enable) { R_CHECK(h); r->s
 int iftrcuSetMsaaSamples(iftrcuRenderer* h, IfritSampleCountFlagBits s) {
     R_CHECK(h);
     if (s != 1 && s != 2 && s != 4 && s != 8 && s != 16) return r->fail(IFRIT_ERR_INVALID, "setMsaaSamples", "1, 2, 4, 8 or 16");
-    if (r->msaa != (int)s) r->queueChecked = false;
+    if (r->msaa != (int)s) r->scr[0].queueChecked = r->scr[1].queueChecked = false;
     r->msaa = (int)s;
     return IFRIT_OK;
 }
@@ -773,7 +840,7 @@ int iftrcuSetDepthTestEnable(iftrcuRenderer* h, int enable) { R_CHECK(h); r->dep
 int iftrcuSetCullMode(iftrcuRenderer* h, IfritCullMode mode) {
     R_CHECK(h);
     if ((int)mode < 0 || (int)mode > 3) return IFRIT_ERR_INVALID;
-    if (r->cullMode != (int)mode) r->queueChecked = false;
+    if (r->cullMode != (int)mode) r->scr[0].queueChecked = r->scr[1].queueChecked = false;
     r->cullMode = mode;
     return IFRIT_OK;
 }
@@ -786,16 +853,23 @@ int iftrcuSetClearValues(iftrcuRenderer* h, const float* rgba, int numColors, fl
 int iftrcuSetSampleConvention(iftrcuRenderer* h, int convention) {
     R_CHECK(h);
     if (convention != IFRIT_CONVENTION_CUDA && convention != IFRIT_CONVENTION_CPU) return IFRIT_ERR_INVALID;
-    r->convention = convention; r->queueChecked = false;
+    r->convention = convention; r->scr[0].queueChecked = r->scr[1].queueChecked = false;
     return IFRIT_OK;
 }
 int iftrcuSetTilePartition(iftrcuRenderer* h, int rank, int worldSize) {
     R_CHECK(h);
     if (worldSize < 1 || rank < 0 || rank >= worldSize) return r->fail(IFRIT_ERR_INVALID, "SetTilePartition", "bad rank / world size");
-    r->rank = rank; r->world = worldSize; r->queueChecked = false;
+    r->rank = rank; r->world = worldSize; r->scr[0].queueChecked = r->scr[1].queueChecked = false;
     return IFRIT_OK;
 }
 int iftrcuSetDebugPrimitiveIds(iftrcuRenderer* h, int enable) { R_CHECK(h); r->debugIds = enable != 0; return IFRIT_OK; }
+int iftrcuSetFramePipelining(iftrcuRenderer* h, int enable) {
+    R_CHECK(h);
+    int rc = sync_and_check(r); if (rc) return rc;
+    r->pipelining = enable != 0;
+    r->tilePending[0] = r->tilePending[1] = false;
+    return IFRIT_OK;
+}
 int iftrcuSetVertexStageFused(iftrcuRenderer* h, int enable) { R_CHECK(h); r->fusedVS = enable != 0; return IFRIT_OK; }
 int iftrcuSetSamplerHardwareFilter(iftrcuRenderer* h, int enable) { R_CHECK(h); r->hwFilter = enable != 0; return IFRIT_OK; }
 
@@ -819,7 +893,7 @@ int iftrcuDrawElements(iftrcuRenderer* h) {
         if (r->nvary < need) return r->fail(IFRIT_ERR_STATE, "drawElements", "fragment shader needs more varyings than the vertex shader outputs");
     }
     if (r->fsId == IFRIT_FS_DERIV_VIS && !r->bufMem[0].p) return r->fail(IFRIT_ERR_STATE, "drawElements", "buffer slot 0 (uniform block) not created");
-    if (r->haveDraw && !r->queueChecked) { int rc = sync_and_check(r); if (rc) return rc; }
+    if (r->haveDraw && !r->scr[r->pipelining ? 1 - r->set : 0].queueChecked) { int rc = sync_and_check(r); if (rc) return rc; }
     return issue_draw(r, false);
 }
 
@@ -877,10 +951,10 @@ int iftrcuReadAssembled(iftrcuRenderer* h, iftrcuAssembledTriangle* dst, int cap
     const size_t nfan1 = (size_t)r->hCounters[4];
     std::vector<uint32_t> fan1(std::max<size_t>(1, nfan1));
     if (ntri) {
-        CUDA_TRY(cudaMemcpy(rec.data(), r->rec.p, rec.size() * sizeof(TriRec), cudaMemcpyDeviceToHost));
-        CUDA_TRY(cudaMemcpy(box.data(), r->tileBox.p, box.size() * sizeof(uint2), cudaMemcpyDeviceToHost));
-        CUDA_TRY(cudaMemcpy(cb.data(), r->clipBary.p, cb.size() * sizeof(float), cudaMemcpyDeviceToHost));
-        if (nfan1) CUDA_TRY(cudaMemcpy(fan1.data(), r->fan1List.p, nfan1 * 4, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(rec.data(), r->scr[r->set].rec.p, rec.size() * sizeof(TriRec), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(box.data(), r->scr[r->set].tileBox.p, box.size() * sizeof(uint2), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(cb.data(), r->scr[r->set].clipBary.p, cb.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        if (nfan1) CUDA_TRY(cudaMemcpy(fan1.data(), r->scr[r->set].fan1List.p, nfan1 * 4, cudaMemcpyDeviceToHost));
     }
     std::vector<uint32_t> slots;
     for (size_t t = 0; t < ntri; t++) if ((box[t].x & 0xffff) <= (box[t].x >> 16)) slots.push_back((uint32_t)t);
@@ -933,7 +1007,8 @@ int iftrcuGetKernelTimes(iftrcuRenderer* h, float* msOut5, int* numDraws) {
         cudaEvent_t* ev = &r->profEvents[d * IFR_PROF_EVENTS];
         for (int k = 0; k < 5; k++) {
             float ms = 0.f;
-            CUDA_TRY(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
+            const int e0 = k < 4 ? k : 5;     // the tile kernel is bracketed on the draw stream (events 5, 6)
+            CUDA_TRY(cudaEventElapsedTime(&ms, ev[e0], ev[e0 + 1]));
             acc[k] += ms;
         }
     }

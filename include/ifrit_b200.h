@@ -250,6 +250,12 @@ IFRIT_B200_API int iftrcuCopyColorToHostAsync(iftrcuRenderer* h, void* hostDst);
  * byte, or NULL for a device-only image; format 1 = RGBA8 UNORM, 0 = off.  While bound, every draw / clear also
  * writes round(saturate(c) * 255) per channel next to the float colour (same kernel, no re-read) and the per-draw
  * copy-back carries this image INSTEAD of the RGBA32F one; useDoubleBuffer applies to it as to the float image. */
+/* Frame pipelining (default on): the geometry stage of a draw (setup + count, scan, fill) runs on an internal stream
+ * into one of two scratch sets, only the tile kernel runs on the caller's stream, so the geometry of frame k + 1
+ * overlaps the tile kernel of frame k.  Results and their order on the caller's stream are unchanged.  The geometry
+ * stage is ordered after the last bind / upload of its inputs (vertex, index, uniform buffers): a caller that
+ * rewrites a DEVICE-bound buffer in place must re-bind it (or switch pipelining off) before the next draw. */
+IFRIT_B200_API int iftrcuSetFramePipelining(iftrcuRenderer* h, int enable);
 IFRIT_B200_API int iftrcuBindPresentBuffer(iftrcuRenderer* h, void* hostRGBA8, int format);
 IFRIT_B200_API int iftrcuReadPresent(iftrcuRenderer* h, void* dstRGBA8);
 IFRIT_B200_API int iftrcuExportFrameBuffer(iftrcuRenderer* h, void* handleOut128);

@@ -147,6 +147,38 @@ def test_rgba8_present_image(gpu_renderer_factory):
     r2.bindPresentBuffer(None, 0)
 
 
+@pytest.mark.parametrize("pipelining", [True, False])
+def test_back_to_back_draws_with_rebinding(gpu_renderer_factory, pipelining):
+    """Frame pipelining (geometry stage of draw k + 1 on its own stream, overlapping draw k's tile kernel): four draws
+    issued back to back without a host sync, each after re-binding the vertex / index buffers and rewriting the uniform
+    block, must give the frame the oracle gets by drawing them in order (second pair without a clear)."""
+    from ifrit_v2_b200 import renderer as R
+    W, H = 320, 180
+    r2 = gpu_renderer_factory()
+    r2.setFramePipelining(pipelining)
+    r2.bindFrameBuffer(None, None, W, H)
+    vbm, idxm = scenes.mesh_sphere(n=32)
+    col = dep = None
+    r2.bindVertexShader(R.VS_MVP, 2); r2.bindFragmentShader(O.FS_NORMAL_COLOR)
+    r2.CreateBuffer(0, scenes.uniform_block(np.eye(4)).nbytes)
+    r2.SetCullMode(2); r2.setClearValues([(0, 0, 0, 0)], 1.0)
+    for i in range(4):
+        mvp = scenes.default_mvp(W, H) @ np.diag([1 + 0.15 * i, 1 - 0.1 * i, 1, 1]).astype(np.float32)
+        u = scenes.uniform_block(mvp)
+        vb = vbm.copy(); vb[:, 0] += 0.2 * i - 0.3
+        idx = idxm if i % 2 == 0 else idxm[: 3 * (len(idxm) // 6)]
+        clear = i in (0, 2)
+        o = oracle_draw(W, H, vb, idx, 1, O.FS_NORMAL_COLOR, 2, u, cull=2, clear=clear, color=col, depth=dep)
+        col, dep = o["color"], o["depth"]
+        r2.bindVertexBuffer(np.ascontiguousarray(vb)); r2.bindIndexBuffer(np.ascontiguousarray(idx))
+        r2.copyHostBufferToBuffer(u, 0)
+        if clear:
+            r2.clear()
+        r2.drawElements()                       # no synchronize() between the draws
+    assert np.array_equal(r2.readDepth().view(np.uint32), dep.view(np.uint32))
+    assert np.array_equal(r2.readColor().view(np.uint32), col.view(np.uint32))
+
+
 def test_standalone_vertex_stage_matches_fused(r):
     """vertexProcessingKernel CU:330 as its own kernel (pos / vary buffers) vs fused into triangle setup."""
     W, H = 320, 200

@@ -9,7 +9,7 @@ for cfg in $cfgs; do
 import json
 try:
     o=json.loads(open('$o/bench_${cfg}_$tag.json').read().strip().splitlines()[-1])
-    def show(n,d): print(n, 'ms/step %.4f'%d['ms_per_step'], 'Mtris/s %.1f'%d['value'], {k:round(v,4) for k,v in d['kernel_ms'].items()}, 'frac %.4f'%d['roofline']['frac'], 'e2e ms %.3f'%d['e2e']['ms_per_step'])
+    def show(n,d): print(n, "ms/step %.4f"%d["ms_per_step"], "lat %.4f"%(d.get("frame_latency_ms") or 0), "Mtris/s %.1f"%d["value"], {k:round(v,4) for k,v in (d.get("kernel_ms_unpipelined") or d["kernel_ms"]).items()}, "frac %.4f"%d["roofline"]["frac"], "e2e ms %.3f"%d["e2e"]["ms_per_step"])
     show(o['config']['name'], o)
     for k,v in o.get('extra_configs',{}).items():
         if 'error' in v: print(k, v)
