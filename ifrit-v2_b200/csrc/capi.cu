@@ -86,6 +86,7 @@ struct iftrcuRenderer {
     int scissorEnable = 0, nScissor = 0; float scissor[IFR_MAX_SCISSOR][4];
     int rank = 0, world = 1;
     bool pendingClear = false, lastDrawCleared = false;
+    int blendEnable = 0; float blendCoef[4][4];   // iftrcuSetBlendFunc
 
     // resources
     TexDesc tex[IFR_MAX_TEX]; DevBuf texMem[IFR_MAX_TEX]; size_t texTexels[IFR_MAX_TEX] = {0};
@@ -175,6 +176,7 @@ static void build_params(iftrcuRenderer* r, DrawParams& p) {
     memcpy(p.scissor, r->scissor, sizeof p.scissor);
     p.rank = r->rank; p.world = r->world;
     p.hwFilter = r->hwFilter ? 1 : 0;
+    p.blendEnable = r->blendEnable; memcpy(p.blendCoef, r->blendCoef, sizeof p.blendCoef);
     int mnx = 255, mxx = 0, mny = 255, mxy = 0;
     const int ns = r->convention == IFRIT_CONVENTION_CPU ? 1 : r->msaa;
     for (int k = 0; k < r->msaa; k++) {
@@ -319,7 +321,8 @@ static int issue_draw(iftrcuRenderer* r, bool forceCheck, bool sameSet = false) 
         r->copyPending[r->cur] = false;
     }
     if (ev) CUDA_TRY(cudaEventRecord(ev[5], s));
-    CUDA_TRY(ifr_launch_tiles(p, r->fsId, s));
+    if (r->blendEnable) CUDA_TRY(ifr_launch_tiles_blend(p, r->fsId, s));
+    else CUDA_TRY(ifr_launch_tiles(p, r->fsId, s));
     if (ev) { CUDA_TRY(cudaEventRecord(ev[6], s)); r->profDraws++; }
     if (pipe) { CUDA_TRY(cudaEventRecord(r->evTileDone[r->set], s)); r->tilePending[r->set] = true; }
     r->stats.kernel_launches += 3;
@@ -383,6 +386,7 @@ static int sync_and_check(iftrcuRenderer* r) {
         CUDA_TRY(cudaStreamSynchronize(r->stream));
         if (r->doubleBuffer) CUDA_TRY(cudaStreamSynchronize(r->copyStream));
     }
+    if (r->haveDraw && r->hCounters[6]) { r->hCounters[6] = 0; return r->fail(IFRIT_ERR_UNSUPPORTED, "drawElements", "alpha blending: a tile holds more than 4096 triangles"); }
     if (r->hTimedOut && *r->hTimedOut) { *r->hTimedOut = 0; return r->fail(IFRIT_ERR_STATE, "frame flags", "a sort-first rank did not signal within 2 s"); }
     if (r->haveDraw) {
         r->stats.triangles_assembled = r->hCounters[0];
@@ -826,7 +830,26 @@ int iftrcuSetRasterizerPolygonMode(iftrcuRenderer* h, IfritPolygonMode mode) {
 int iftrcuSetBlendFunc(iftrcuRenderer* h, const IfritColorAttachmentBlendState* s) {
     R_CHECK(h);
     if (!s) return IFRIT_ERR_INVALID;
-    if (s->blendEnable) return r->fail(IFRIT_ERR_UNSUPPORTED, "setBlendFunc", "ordered alpha blending is out of scope (SURVEY 8f rank 1)");
+    if (!s->blendEnable) { r->blendEnable = 0; return IFRIT_OK; }
+    // updateBlendStateKernel CU:3436-3537: {x1, x(1 - src.a), x(1 - dst.a), zero flag}; the reference's SRC_ALPHA / DST_ALPHA
+    // rows select (1 - a) and its ONE_MINUS_* rows select a (sic) — replicated; the colour factors abort there
+    const IfritBlendFactor f[4] = {s->srcColorBlendFactor, s->dstColorBlendFactor, s->srcAlphaBlendFactor, s->dstAlphaBlendFactor};
+    float coef[4][4];
+    for (int i = 0; i < 4; i++) {
+        float c[4];
+        switch (f[i]) {
+            case IF_BLEND_FACTOR_ONE: c[0] = 1; c[1] = 0; c[2] = 0; c[3] = 0; break;
+            case IF_BLEND_FACTOR_ZERO: c[0] = 0; c[1] = 0; c[2] = 0; c[3] = 1; break;
+            case IF_BLEND_FACTOR_DST_ALPHA: c[0] = 0; c[1] = 0; c[2] = 1; c[3] = 0; break;
+            case IF_BLEND_FACTOR_SRC_ALPHA: c[0] = 0; c[1] = 1; c[2] = 0; c[3] = 0; break;
+            case IF_BLEND_FACTOR_ONE_MINUS_DST_ALPHA: c[0] = 1; c[1] = 0; c[2] = -1; c[3] = 0; break;
+            case IF_BLEND_FACTOR_ONE_MINUS_SRC_ALPHA: c[0] = 1; c[1] = -1; c[2] = 0; c[3] = 0; break;
+            default: return r->fail(IFRIT_ERR_UNSUPPORTED, "setBlendFunc", "blend factor not supported (the reference aborts on the colour factors, CU:3466)");
+        }
+        memcpy(coef[i], c, sizeof c);
+    }
+    memcpy(r->blendCoef, coef, sizeof coef);
+    r->blendEnable = 1;
     return IFRIT_OK;
 }
 int iftrcuSetDepthFunc(iftrcuRenderer* h, IfritCompareOp op) {
@@ -892,6 +915,7 @@ int iftrcuDrawElements(iftrcuRenderer* h) {
                          : (r->fsId == IFRIT_FS_TEXTURED || r->fsId == IFRIT_FS_TEXTURED_LOD0 || r->fsId == IFRIT_FS_DERIV_VIS) ? 2 : 1;
         if (r->nvary < need) return r->fail(IFRIT_ERR_STATE, "drawElements", "fragment shader needs more varyings than the vertex shader outputs");
     }
+    if (r->blendEnable && r->msaa != 1) return r->fail(IFRIT_ERR_UNSUPPORTED, "drawElements", "alpha blending is 1x only (the reference's blend kernel has no sample loop, CU:1649)");
     if (r->fsId == IFRIT_FS_DERIV_VIS && !r->bufMem[0].p) return r->fail(IFRIT_ERR_STATE, "drawElements", "buffer slot 0 (uniform block) not created");
     if (r->haveDraw && !r->scr[r->pipelining ? 1 - r->set : 0].queueChecked) { int rc = sync_and_check(r); if (rc) return rc; }
     return issue_draw(r, false);

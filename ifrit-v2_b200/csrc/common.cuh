@@ -62,6 +62,9 @@ struct DrawParams {
     int doClear; float clearColor[4]; float clearDepth;
     int scissorEnable, nScissor; float scissor[IFR_MAX_SCISSOR][4];
     int rank, world;
+    // ordered alpha blending (pixelShadingAlphaBlendKernel CU:1649-1897): colour src / colour dst / alpha src / alpha dst
+    // coefficients {x1, x(1 - src.a), x(1 - dst.a), zero flag} (updateBlendStateKernel CU:3436-3537)
+    int blendEnable; float blendCoef[4][4];
     int hwFilter;   // bilinear footprints through the TEX unit (8-bit weights) instead of four loads + fp32 lerps
     // coverage sample pattern of this draw, in 1/16 pixel (from cMsaaSampleSequenceAgg, CU:223-234)
     int8_t sampX[16], sampY[16];
@@ -83,7 +86,8 @@ struct DrawParams {
     uint32_t* tileCount; uint32_t* tileStart; uint32_t* tileCursor;
     uint32_t* queue; uint32_t queueCap; TriS* bigQueue; uint32_t bigCap;
     uint32_t epoch; unsigned long long* scanPartial;   // chained scan: (epoch << 32 | block total) per scan CTA
-    unsigned long long* counters;    // [0] assembled, [1] small pairs, [2] frags, [3] overflow flag, [4] fan1 count, [5] big pairs
+    unsigned long long* counters;    // [0] assembled, [1] small pairs, [2] frags, [3] overflow flag, [4] fan1 count, [5] big pairs,
+                                     // [6] blending: a tile held more than IFR_BLEND_CAP triangles
     // resources
     TexDesc tex[IFR_MAX_TEX]; SampDesc samp[IFR_MAX_TEX]; const float* buf[IFR_MAX_BUF];
 };
@@ -113,6 +117,7 @@ cudaError_t ifr_launch_setup_count(const DrawParams& p, int vsMode, cudaStream_t
 cudaError_t ifr_launch_scan(const DrawParams& p, cudaStream_t s);   // both queues
 cudaError_t ifr_launch_fill(const DrawParams& p, cudaStream_t s);
 cudaError_t ifr_launch_tiles(const DrawParams& p, int fsId, cudaStream_t s);
+cudaError_t ifr_launch_tiles_blend(const DrawParams& p, int fsId, cudaStream_t s);
 cudaError_t ifr_launch_clear(const DrawParams& p, cudaStream_t s);
 cudaError_t ifr_launch_blit(const TexDesc& src, int srcLevel, int srcLayer, const TexDesc& dst, int dstLevel,
                             int dstLayer, const uint32_t srcRect[4], const uint32_t dstRect[4], int filter,

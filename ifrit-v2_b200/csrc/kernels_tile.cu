@@ -598,6 +598,161 @@ __global__ void __launch_bounds__(256, (S == 1 && FsTraits<FS>::needsDerivs) ? I
     if ((tid & 31) == 0 && myFrags) atomicAdd(&p.counters[2], (unsigned long long)myFrags);   // no CTA barrier: warps retire independently
 }
 
+// ---- ordered alpha blending ----------------------------------------------------------------------
+// pixelShadingAlphaBlendKernel CU:1649-1897: per pixel, primitives in submission order (the reference merges its three
+// per-bin lists by original primitive id, CU:1853-1895; its bins are heap-sorted first, CU:563-719); a covered fragment
+// is depth-tested against the depth the previous fragment left, shaded, blended into the colour and writes depth.
+// Here: the tile's two queues are merged and sorted by (prim, fan) in shared memory (bitonic), then walked in batches
+// of 64 — one thread per entry builds the raster setup, every thread tests its own pixel.  1x only, as the reference.
+#define IFR_BLEND_CAP 4096
+__device__ __forceinline__ bool depth_pass(int func, float d, float cur) {   // PS_DEPTHTEST, CU:1790-1800
+    switch (func) {
+        case IF_COMPARE_OP_NEVER: return false;
+        case IF_COMPARE_OP_LESS: return d < cur;
+        case IF_COMPARE_OP_EQUAL: return d == cur;
+        case IF_COMPARE_OP_LESS_OR_EQUAL: return d <= cur;
+        case IF_COMPARE_OP_GREATER: return d > cur;
+        case IF_COMPARE_OP_NOT_EQUAL: return d != cur;
+        case IF_COMPARE_OP_GREATER_OR_EQUAL: return d >= cur;
+        default: return true;
+    }
+}
+__device__ __forceinline__ float blend_factor(const float c[4], float oms, float omd) {   // CU:1817-1820, op order of the oracle
+    return __fmul_rn(__fadd_rn(__fadd_rn(c[0], __fmul_rn(c[1], oms)), __fmul_rn(c[2], omd)), __fsub_rn(1.0f, c[3]));
+}
+
+template <int FS>
+__global__ void __launch_bounds__(256, 2) tile_blend_kernel(const __grid_constant__ DrawParams p) {
+    __shared__ uint32_t skey[IFR_BLEND_CAP];
+    __shared__ __align__(16) TriS batch[64];
+    __shared__ uint8_t batchOk[64];
+    constexpr int NV = FsTraits<FS>::nv;
+    const int tileX = blockIdx.x, tileY = blockIdx.y;
+    if (p.world > 1 && ifr_tile_owner(tileX, tileY, p.world) != p.rank) return;
+    const int ntiles = p.tilesX * p.tilesY;
+    const int tile = tileY * p.tilesX + tileX;
+    const int tid = threadIdx.x;
+    const int wrp = tid >> 5, q = (tid >> 2) & 7, l = tid & 3;
+    const int lx = (wrp & 1) * 8 + (q & 3) * 2 + (l & 1), ly = (wrp >> 1) * 4 + (q >> 2) * 2 + (l >> 1);
+    const int px = tileX * IFR_TILE + lx, py = tileY * IFR_TILE + ly;
+    const bool inFrame = px < p.W && py < p.H;
+    const bool scis = inFrame && scissor_pass(p, px, py);
+    const bool overflow = p.counters[3] != 0;
+    const uint32_t sStart = p.tileStart[tile], bStart = p.tileStart[ntiles + 1 + tile];
+    const uint32_t nSmall = overflow ? 0u : p.tileStart[tile + 1] - sStart;
+    const uint32_t nBig = overflow ? 0u : p.tileStart[ntiles + 1 + tile + 1] - bStart;
+    const size_t pidx = (size_t)py * p.W + px;
+    uint32_t n = nSmall + nBig;
+    if (n > IFR_BLEND_CAP) {             // reported by iftrcuSynchronize; the tile is cleared but not drawn
+        if (tid == 0) p.counters[6] = 1ull;
+        n = 0;
+    }
+    const bool cleared = p.doClear && scis;
+    float4 dst = make_float4(p.clearColor[0], p.clearColor[1], p.clearColor[2], p.clearColor[3]);
+    float cur = p.clearDepth;
+    if (inFrame && !cleared) { dst = p.color[pidx]; cur = p.depth[pidx]; }
+    int lastPrim = -1;
+    bool touched = false;
+    unsigned int myFrags = 0;
+    if (n) {
+        uint32_t npow2 = 2;
+        while (npow2 < n) npow2 <<= 1;
+        // sort key = prim * 2 + fan: submission order (a slot appears at most once in a tile)
+        for (uint32_t i = tid; i < npow2; i += 256) {
+            uint32_t k = 0xffffffffu;
+            if (i < n) {
+                const uint32_t slot = i < nSmall ? __ldg(p.queue + sStart + i) : p.bigQueue[bStart + (i - nSmall)].slot;
+                k = slot >= (uint32_t)p.ntri ? (slot - (uint32_t)p.ntri) * 2u + 1u : slot * 2u;
+            }
+            skey[i] = k;
+        }
+        __syncthreads();
+        for (uint32_t k = 2; k <= npow2; k <<= 1)
+            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                for (uint32_t i = tid; i < npow2; i += 256) {
+                    const uint32_t ixj = i ^ j;
+                    if (ixj > i) {
+                        const uint32_t a = skey[i], b = skey[ixj];
+                        if ((a > b) == ((i & k) == 0)) { skey[i] = b; skey[ixj] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        for (uint32_t base = 0; base < n; base += 64) {
+            const uint32_t cnt = min(64u, n - base);
+            if ((uint32_t)tid < cnt) {
+                const uint32_t key = skey[base + tid];
+                const uint32_t slot = (key & 1u) ? (uint32_t)p.ntri + (key >> 1) : (key >> 1);
+                TriS s;
+                int bx0, bx1, by0, by1;
+                batchOk[tid] = setup_tri(p, slot, tileX, tileY, s, bx0, bx1, by0, by1) ? 1 : 0;
+                batch[tid] = s;
+            }
+            __syncthreads();
+            for (uint32_t b = 0; b < cnt; b++) {
+                if (!batchOk[b]) continue;
+                const TriS& s = batch[b];
+                const int bx0 = s.box & 0xff, bx1 = (s.box >> 8) & 0xff, by0 = (s.box >> 16) & 0xff, by1 = s.box >> 24;
+                if (!scis || lx < bx0 || lx > bx1 || ly < by0 || ly > by1) continue;
+                const int dX[3] = {s.dX[0], s.dX[1], s.dX[2]}, dY[3] = {s.dY[0], s.dY[1], s.dY[2]}, T[3] = {s.T[0], s.T[1], s.T[2]};
+                const long long E0[3] = {s.E0[0], s.E0[1], s.E0[2]};
+                if (!coverage<1>(p, dX, dY, T, E0, s.flags & IFR_FLAG_WIDE, 16 * lx, 16 * ly)) continue;
+                const float d = depth_at(dX, dY, E0, s.flags, s.ar, s.z0, s.z1, s.z2, lx, ly);
+                if (!depth_pass(p.depthFunc, d, cur)) continue;
+                float4 v[NV > 0 ? NV : 1], ddx[NV > 0 ? NV : 1], ddy[NV > 0 ? NV : 1];
+                float depth2 = 0.0f;
+                int prim = 0, fan = 0;
+                interp<NV, FsTraits<FS>::needsDerivs>(p, s.slot, px, py, v, ddx, ddy, depth2, prim, fan);
+                const float4 c = run_fs<FS>(p, v, ddx, ddy, prim, fan);
+                const float oms = __fsub_rn(1.0f, c.w), omd = __fsub_rn(1.0f, dst.w);
+                const float ms = blend_factor(p.blendCoef[0], oms, omd), md = blend_factor(p.blendCoef[1], oms, omd);
+                const float msa = blend_factor(p.blendCoef[2], oms, omd), mda = blend_factor(p.blendCoef[3], oms, omd);
+                dst.x = __fadd_rn(__fmul_rn(dst.x, md), __fmul_rn(c.x, ms));
+                dst.y = __fadd_rn(__fmul_rn(dst.y, md), __fmul_rn(c.y, ms));
+                dst.z = __fadd_rn(__fmul_rn(dst.z, md), __fmul_rn(c.z, ms));
+                dst.w = __fadd_rn(__fmul_rn(dst.w, mda), __fmul_rn(c.w, msa));
+                cur = d;                     // CU:1828-1829: depth written, the next fragment tests against it
+                lastPrim = prim;
+                touched = true;
+                myFrags++;
+            }
+            __syncthreads();
+        }
+    }
+    if (inFrame) {
+        if (touched || cleared) {
+            p.color[pidx] = dst;
+            p.depth[pidx] = cur;
+            if (p.present) p.present[pidx] = ifr_pack_rgba8(dst);
+        } else if (p.present) {
+            p.present[pidx] = ifr_pack_rgba8(p.color[pidx]);
+        }
+        if (p.primIds) p.primIds[pidx] = lastPrim;
+    }
+    myFrags = __reduce_add_sync(0xffffffffu, myFrags);
+    if ((tid & 31) == 0 && myFrags) atomicAdd(&p.counters[2], (unsigned long long)myFrags);
+}
+
+template <int FS>
+static cudaError_t launch_blend(const DrawParams& p, cudaStream_t s) {
+    tile_blend_kernel<FS><<<dim3(p.tilesX, p.tilesY), 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t ifr_launch_tiles_blend(const DrawParams& p, int fsId, cudaStream_t s) {
+    if (p.msaa != 1) return cudaErrorInvalidValue;
+    switch (fsId) {
+        case IFRIT_FS_VARYING0: return launch_blend<IFRIT_FS_VARYING0>(p, s);
+        case IFRIT_FS_NORMAL_COLOR: return launch_blend<IFRIT_FS_NORMAL_COLOR>(p, s);
+        case IFRIT_FS_PRIM_ID: return launch_blend<IFRIT_FS_PRIM_ID>(p, s);
+        case IFRIT_FS_TEXTURED: return p.hwFilter ? launch_blend<IFRIT_FS_TEXTURED_FAST>(p, s) : launch_blend<IFRIT_FS_TEXTURED>(p, s);
+        case IFRIT_FS_TEXTURED_LOD0: return p.hwFilter ? launch_blend<IFRIT_FS_TEXTURED_LOD0_FAST>(p, s) : launch_blend<IFRIT_FS_TEXTURED_LOD0>(p, s);
+        case IFRIT_FS_SKYBOX: return launch_blend<IFRIT_FS_SKYBOX>(p, s);
+        case IFRIT_FS_DERIV_VIS: return launch_blend<IFRIT_FS_DERIV_VIS>(p, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
 template <int FS>
 static cudaError_t launch_fs(const DrawParams& p, cudaStream_t s) {
     const dim3 grid(p.tilesX, p.tilesY);

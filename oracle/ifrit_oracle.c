@@ -603,13 +603,99 @@ static void interp(const orc_tri* r, int px, int py, const orc_f4* vary, int nva
 #define MAXV 4
 #define MAXS 16
 
+/* Direct depth compare of the blending path (PS_DEPTHTEST, CU:1790-1800) */
+static int depth_pass(int func, float d, float cur) {
+    switch (func) {
+        case ORC_CMP_NEVER: return 0;
+        case ORC_CMP_LESS: return d < cur;
+        case ORC_CMP_EQUAL: return d == cur;
+        case ORC_CMP_LESS_OR_EQUAL: return d <= cur;
+        case ORC_CMP_GREATER: return d > cur;
+        case ORC_CMP_NOT_EQUAL: return d != cur;
+        case ORC_CMP_GREATER_OR_EQUAL: return d >= cur;
+        default: return 1;
+    }
+}
+
+/* (s.x + s.y (1 - src.a) + s.z (1 - dst.a)) (1 - s.w), CU:1817-1820 — op order fixed here and in the kernel */
+static float blend_factor(const float c[4], float oms, float omd) {
+    return ((c[0] + c[1] * oms) + c[2] * omd) * (1.0f - c[3]);
+}
+
+/* Ordered alpha blending (pixelShadingAlphaBlendKernel CU:1649-1897): primitives in submission order (the reference
+ * merges its three per-bin lists by original primitive id, CU:1853-1895); per covered pixel: depth test against the
+ * depth the previous fragment left, FS, blend into the colour, depth written.  1x only (the kernel has no sample loop). */
+static int render_blend(const orc_state* st, const orc_f4* vary, int nvary, const int32_t* idx, const orc_tri* tris, int ntris,
+                        int fs_id, const fs_env* env, float* color, float* depth, int32_t* prim_id, int64_t* stats) {
+    const int W = st->width, H = st->height, func = st->depth_func;
+    int64_t frags = 0, covered = 0;
+    for (size_t p = 0; p < (size_t)W * H; p++) prim_id[p] = -1;
+    for (int i = 0; i < ntris; i++) {
+        const orc_tri* r = &tris[i];
+        int64_t minx = r->X[0], maxx = r->X[0], miny = r->Y[0], maxy = r->Y[0];
+        for (int j = 1; j < 3; j++) {
+            if (r->X[j] < minx) minx = r->X[j];
+            if (r->X[j] > maxx) maxx = r->X[j];
+            if (r->Y[j] < miny) miny = r->Y[j];
+            if (r->Y[j] > maxy) maxy = r->Y[j];
+        }
+        int x0 = (int)(minx >> 8) - 1, x1 = (int)(maxx >> 8) + 1;
+        int y0 = (int)(miny >> 8) - 1, y1 = (int)(maxy >> 8) + 1;
+        if (x0 < 0) x0 = 0;
+        if (y0 < 0) y0 = 0;
+        if (x1 > W - 1) x1 = W - 1;
+        if (y1 > H - 1) y1 = H - 1;
+        for (int y = y0; y <= y1; y++)
+            for (int x = x0; x <= x1; x++) {
+                int ox, oy;
+                sample_offset16(st, 0, &ox, &oy);
+                int64_t e[3];
+                edges_at(r, (int64_t)x * SUBPIX + ox * 16, (int64_t)y * SUBPIX + oy * 16, e);
+                if (!(e[0] > 0 && e[1] > 0 && e[2] > 0)) continue;
+                if (!scissor_pass(st, x, y)) continue;
+                covered++;
+                const size_t p = (size_t)y * W + x;
+                float beta[3];
+                bary_at(r, x, y, beta);
+                const float d = depth_at(r, beta);
+                if (!depth_pass(func, d, depth[p])) continue;
+                /* the pixel and its two quad neighbours (coarse derivatives, SB:36-76) */
+                const int qx = x & ~1, qy = y & ~1, l = (x & 1) + 2 * (y & 1);
+                orc_f4 v[4][MAXV];
+                for (int k = 0; k < 4; k++) interp(r, qx + (k & 1), qy + (k >> 1), vary, nvary, idx, v[k]);
+                orc_f4 ddx[MAXV], ddy[MAXV];
+                const int row = l >> 1, col = l & 1;
+                for (int k = 0; k < nvary; k++) {
+                    const orc_f4 *xl = &v[row * 2][k], *xr = &v[row * 2 + 1][k];
+                    const orc_f4 *yt = &v[col][k], *yb = &v[2 + col][k];
+                    ddx[k].x = xr->x - xl->x; ddx[k].y = xr->y - xl->y; ddx[k].z = xr->z - xl->z; ddx[k].w = xr->w - xl->w;
+                    ddy[k].x = yb->x - yt->x; ddy[k].y = yb->y - yt->y; ddy[k].z = yb->z - yt->z; ddy[k].w = yb->w - yt->w;
+                }
+                float c[4];
+                run_fs(fs_id, env, v[l], ddx, ddy, r->prim, r->fan, c);
+                frags++;
+                float* dst = color + 4 * p;
+                const float oms = 1.0f - c[3], omd = 1.0f - dst[3];
+                const float ms = blend_factor(st->blend_coef[0], oms, omd), md = blend_factor(st->blend_coef[1], oms, omd);
+                const float msa = blend_factor(st->blend_coef[2], oms, omd), mda = blend_factor(st->blend_coef[3], oms, omd);
+                const float o0 = dst[0] * md + c[0] * ms, o1 = dst[1] * md + c[1] * ms, o2 = dst[2] * md + c[2] * ms;
+                const float o3 = dst[3] * mda + c[3] * msa;
+                dst[0] = o0; dst[1] = o1; dst[2] = o2; dst[3] = o3;
+                depth[p] = d;            /* CU:1828-1829: depth written, next fragment tests against it */
+                prim_id[p] = r->prim;    /* last writer */
+            }
+    }
+    if (stats) { stats[0] = frags; stats[1] = covered; stats[2] = ntris; }
+    return 0;
+}
+
 int orc_render(const orc_state* st, const orc_f4* pos, const orc_f4* vary, int nvary,
                const int32_t* idx, int ntri, int fs_id, const void* uniforms,
                const orc_texture* textures, const orc_sampler* samplers,
                float* color, float* depth, int32_t* prim_id, int64_t* stats) {
     const int W = st->width, H = st->height, S = st->msaa, func = st->depth_func;
     if (nvary > MAXV || S > MAXS) return -1;
-    if (func == ORC_CMP_NOT_EQUAL) return -2;
+    if (func == ORC_CMP_NOT_EQUAL && !st->blend_enable) return -2;
     orc_tri* tris = (orc_tri*)malloc(sizeof(orc_tri) * 2 * (size_t)(ntri > 0 ? ntri : 1));
     const int ntris = orc_assemble(st, pos, idx, ntri, tris);
     /* slot -> assembled triangle */
@@ -618,6 +704,14 @@ int orc_render(const orc_state* st, const orc_f4* pos, const orc_f4* vary, int n
     for (int i = 0; i < ntris; i++) by_slot[tris[i].slot] = i;
 
     if (st->do_clear) orc_clear(st, color, depth);
+
+    if (st->blend_enable) {
+        if (S != 1) { free(by_slot); free(tris); return -3; }
+        fs_env benv = {(const float*)uniforms, textures, samplers};
+        const int rc = render_blend(st, vary, nvary, idx, tris, ntris, fs_id, &benv, color, depth, prim_id, stats);
+        free(by_slot); free(tris);
+        return rc;
+    }
 
     uint64_t* keys = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)W * H * S);
     for (size_t p = 0; p < (size_t)W * H; p++)

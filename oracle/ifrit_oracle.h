@@ -53,6 +53,10 @@ typedef struct {
     int32_t do_clear;
     float   clear_color[4];
     float   clear_depth;
+    /* ordered alpha blending (pixelShadingAlphaBlendKernel CU:1649-1897, updateBlendStateKernel CU:3436-3537):
+     * blend_coef[0..3] = colour src, colour dst, alpha src, alpha dst, each {x1, x(1-src.a), x(1-dst.a), zero flag} */
+    int32_t blend_enable;
+    float   blend_coef[4][4];
 } orc_state;
 
 typedef struct {

@@ -18,7 +18,15 @@ class State(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("msaa", C.c_int32), ("cull_mode", C.c_int32),
                 ("depth_func", C.c_int32), ("convention", C.c_int32), ("scissor_enable", C.c_int32),
                 ("nscissor", C.c_int32), ("scissor", (C.c_float * 4) * 16), ("do_clear", C.c_int32),
-                ("clear_color", C.c_float * 4), ("clear_depth", C.c_float)]
+                ("clear_color", C.c_float * 4), ("clear_depth", C.c_float),
+                ("blend_enable", C.c_int32), ("blend_coef", (C.c_float * 4) * 4)]
+
+
+# updateBlendStateKernel CU:3436-3537: {x1, x(1 - src.a), x(1 - dst.a), zero flag} per IfritBlendFactor — note that
+# the reference's SRC_ALPHA / DST_ALPHA rows select (1 - a) and its ONE_MINUS_* rows select a (sic, replicated)
+BLEND_ZERO, BLEND_ONE, BLEND_SRC_ALPHA, BLEND_ONE_MINUS_SRC_ALPHA, BLEND_DST_ALPHA, BLEND_ONE_MINUS_DST_ALPHA = 0, 1, 6, 7, 8, 9
+BLEND_COEF = {BLEND_ONE: (1, 0, 0, 0), BLEND_ZERO: (0, 0, 0, 1), BLEND_DST_ALPHA: (0, 0, 1, 0), BLEND_SRC_ALPHA: (0, 1, 0, 0),
+              BLEND_ONE_MINUS_DST_ALPHA: (1, 0, -1, 0), BLEND_ONE_MINUS_SRC_ALPHA: (1, -1, 0, 0)}
 
 
 class Texture(C.Structure):
@@ -58,12 +66,16 @@ def _p(a):
 
 
 def make_state(width, height, msaa=1, cull=CULL_NONE, depth_func=CMP_LESS, convention=CONV_CUDA, clear=True,
-               clear_color=(0, 0, 0, 0), clear_depth=1.0, scissors=None):
+               clear_color=(0, 0, 0, 0), clear_depth=1.0, scissors=None, blend=None):
     st = State()
     st.width, st.height, st.msaa, st.cull_mode = width, height, msaa, cull
     st.depth_func, st.convention, st.do_clear = depth_func, convention, int(clear)
     st.clear_color[:] = clear_color
     st.clear_depth = clear_depth
+    if blend:     # (srcColor, dstColor, srcAlpha, dstAlpha) IfritBlendFactor values
+        st.blend_enable = 1
+        for i, f in enumerate(blend):
+            st.blend_coef[i][:] = BLEND_COEF[f]
     if scissors:
         st.scissor_enable, st.nscissor = 1, len(scissors)
         for i, s in enumerate(scissors):

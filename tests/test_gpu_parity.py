@@ -179,6 +179,50 @@ def test_back_to_back_draws_with_rebinding(gpu_renderer_factory, pipelining):
     assert np.array_equal(r2.readColor().view(np.uint32), col.view(np.uint32))
 
 
+@pytest.mark.parametrize("func", [O.CMP_ALWAYS, O.CMP_LESS, O.CMP_GEQUAL])
+@pytest.mark.parametrize("blend", [(6, 7, 1, 0), (1, 9, 9, 1), (8, 1, 0, 6)])
+def test_ordered_alpha_blending(r, blend, func):
+    """SURVEY §8f rank 1 (pixelShadingAlphaBlendKernel CU:1649-1897): fragments of a pixel are depth-tested against the
+    depth the previous fragment left, shaded and blended in submission order.  Colour, depth and last-writer id
+    bit-exact against the oracle; small + large triangles, clipped fans, a scissor, ragged frame."""
+    W, H = 200, 120
+    vb, idx = scenes.random_tris(160, 301, neg_w_frac=0.1, size=0.35)
+    vb2, idx2 = scenes.random_tris(900, 302, size=0.03)
+    vb = np.concatenate([vb, vb2]); idx = np.arange(len(vb), dtype=np.int32)
+    vb[:, 7] = 0.15 + 0.7 * vb[:, 7]            # alpha
+    kw = dict(depth_func=func, clear_color=(.2, .3, .4, .5), clear_depth=0.5, blend=blend, scissors=[(5, 3, 180, 110)])
+    o = oracle_draw(W, H, vb, idx, 0, O.FS_VARYING0, 1, IDENT, **kw)
+    g = gpu_draw(r, W, H, vb, idx, 0, O.FS_VARYING0, 1, IDENT, **kw)
+    compare(o, g, exact_color=True)
+    assert g["fragments_shaded"] == o["frags"] > 5000
+    # on top of the first frame without a clear
+    vb3, idx3 = scenes.random_tris(60, 303, size=0.5)
+    kw2 = dict(kw, clear=False, color=o["color"], depth=o["depth"], scissors=None)
+    o2 = oracle_draw(W, H, vb3, idx3, 0, O.FS_VARYING0, 1, IDENT, **kw2)
+    g2 = gpu_draw(r, W, H, vb3, idx3, 0, O.FS_VARYING0, 1, IDENT, **kw2)
+    compare(o2, g2, exact_color=True)
+    r.setBlendFunc(False)
+
+
+def test_alpha_blending_textured_and_limits(r):
+    from ifrit_v2_b200 import renderer as R
+    W, H = 320, 180
+    vb, idx, u = _mesh_case(W, H)
+    tex = scenes.texture_checker(size=128, seed=7)
+    chain = O.texture_chain(tex, 7)
+    samp = dict(filterMode=1, anisotropyEnable=True, maxAnisotropy=16.0)
+    kw = dict(cull=0, depth_func=O.CMP_ALWAYS, blend=(1, 1, 1, 1), mip_levels=7, sampler=samp)   # additive: both faces of the sphere
+    o = oracle_draw(W, H, vb, idx, 1, O.FS_TEXTURED, 2, u, texture_chain=chain, tex_dims=(128, 128), **kw)
+    g = gpu_draw(r, W, H, vb, idx, 1, O.FS_TEXTURED, 2, u, texture=tex, **kw)
+    compare(o, g)
+    r.setMsaaSamples(4)
+    with pytest.raises(R.IfritError) as e:      # 1x only, as the reference's blend kernel
+        r.drawElements()
+    assert e.value.code == R.IFRIT_ERR_UNSUPPORTED
+    r.setMsaaSamples(1)
+    r.setBlendFunc(False)
+
+
 def test_standalone_vertex_stage_matches_fused(r):
     """vertexProcessingKernel CU:330 as its own kernel (pos / vary buffers) vs fused into triangle setup."""
     W, H = 320, 200
@@ -371,7 +415,7 @@ def test_unsupported_verbs_return_status(r):
             fn(*args)
         assert e.value.code == R.IFRIT_ERR_UNSUPPORTED
     with pytest.raises(R.IfritError) as e:
-        r.setBlendFunc(blendEnable=True)
+        r.setBlendFunc(True, 2, 3, 1, 0)      # SRC_COLOR / ONE_MINUS_SRC_COLOR: the reference aborts on them (CU:3466)
     assert e.value.code == R.IFRIT_ERR_UNSUPPORTED
     r.setBlendFunc(blendEnable=False)
 

@@ -8,9 +8,9 @@ from oracle import oracle as O
 
 def oracle_draw(W, H, vb, idx, vs, fs, nvary, uniforms, msaa=1, cull=0, depth_func=1, convention=0, clear=True,
                 clear_color=(0, 0, 0, 0), clear_depth=1.0, scissors=None, texture_chain=None, tex_dims=None,
-                mip_levels=0, layers=1, sampler=None, color=None, depth=None):
+                mip_levels=0, layers=1, sampler=None, color=None, depth=None, blend=None):
     st = O.make_state(W, H, msaa=msaa, cull=cull, depth_func=depth_func, convention=convention, clear=clear,
-                      clear_color=clear_color, clear_depth=clear_depth, scissors=scissors)
+                      clear_color=clear_color, clear_depth=clear_depth, scissors=scissors, blend=blend)
     texs = samps = None
     if texture_chain is not None:
         texs = [O.make_texture(texture_chain, tex_dims[0], tex_dims[1], mip_levels, layers)]
@@ -23,7 +23,8 @@ def oracle_draw(W, H, vb, idx, vs, fs, nvary, uniforms, msaa=1, cull=0, depth_fu
 
 def gpu_draw(r, W, H, vb, idx, vs, fs, nvary, uniforms, msaa=1, cull=0, depth_func=1, convention=0, clear=True,
              clear_color=(0, 0, 0, 0), clear_depth=1.0, scissors=None, texture=None, mip_levels=0, layers=1,
-             sampler=None, color=None, depth=None, depth_test=True, partition=None, fused_vs=True, hw_filter=True):
+             sampler=None, color=None, depth=None, depth_test=True, partition=None, fused_vs=True, hw_filter=True,
+             blend=None):
     from ifrit_v2_b200 import renderer as R
     c0 = np.zeros((H, W, 4), np.float32) if color is None else np.ascontiguousarray(color, np.float32)
     d0 = np.zeros((H, W), np.float32) if depth is None else np.ascontiguousarray(depth, np.float32)
@@ -42,6 +43,10 @@ def gpu_draw(r, W, H, vb, idx, vs, fs, nvary, uniforms, msaa=1, cull=0, depth_fu
     r.setDebugPrimitiveIds(True)
     r.setVertexStageFused(fused_vs)
     r.setSamplerHardwareFilter(hw_filter)
+    if blend:
+        r.setBlendFunc(True, *blend)
+    else:
+        r.setBlendFunc(False)
     if clear:
         r.clear()
     r.drawElements()
