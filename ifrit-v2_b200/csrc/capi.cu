@@ -227,7 +227,7 @@ static int ensure_scratch(iftrcuRenderer* r) {
     CUDA_TRY(r->scr[r->set].tileCount.ensure(2 * ntiles * 4));
     CUDA_TRY(r->scr[r->set].tileStart.ensure(2 * (ntiles + 1) * 4));
     CUDA_TRY(r->scr[r->set].tileCursor.ensure(2 * ntiles * 4));
-    CUDA_TRY(r->scr[r->set].counters.ensure(8 * 8));
+    CUDA_TRY(r->scr[r->set].counters.ensure(IFR_COUNTER_BYTES));
     if (!r->scr[r->set].scanPartial.p || r->scr[r->set].scanPartial.cap < 2 * (ntiles / 4096 + 1) * 8) {
         CUDA_TRY(r->scr[r->set].scanPartial.ensure(2 * (ntiles / 4096 + 1) * 8));
         CUDA_TRY(cudaMemsetAsync(r->scr[r->set].scanPartial.p, 0, r->scr[r->set].scanPartial.cap, (r->pipelining && r->geomStream) ? r->geomStream : r->stream));
@@ -281,7 +281,7 @@ static int issue_draw(iftrcuRenderer* r, bool forceCheck, bool sameSet = false) 
         if (r->inputsDirty) { CUDA_TRY(cudaStreamWaitEvent(g, r->evInputs, 0)); r->inputsDirty = false; }
     }
     CUDA_TRY(cudaMemsetAsync(sc.tileCount.p, 0, 2 * ntiles * 4, g));
-    CUDA_TRY(cudaMemsetAsync(sc.counters.p, 0, 64, g));
+    CUDA_TRY(cudaMemsetAsync(sc.counters.p, 0, IFR_COUNTER_BYTES, g));
     cudaEvent_t* ev = nullptr;
     if (r->profiling && !forceCheck && sc.queueChecked) ev = &r->profEvents[(r->profDraws % IFR_PROF_RING) * IFR_PROF_EVENTS];
     if (ev) CUDA_TRY(cudaEventRecord(ev[0], g));
@@ -326,7 +326,7 @@ static int issue_draw(iftrcuRenderer* r, bool forceCheck, bool sameSet = false) 
     if (ev) { CUDA_TRY(cudaEventRecord(ev[6], s)); r->profDraws++; }
     if (pipe) { CUDA_TRY(cudaEventRecord(r->evTileDone[r->set], s)); r->tilePending[r->set] = true; }
     r->stats.kernel_launches += 3;
-    CUDA_TRY(cudaMemcpyAsync(r->hCounters, r->scr[r->set].counters.p, 64, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(r->hCounters, r->scr[r->set].counters.p, IFR_COUNTER_BYTES, cudaMemcpyDeviceToHost, s));
     r->lastDrawCleared = r->pendingClear;
     r->pendingClear = false;
     r->haveDraw = true;
@@ -389,6 +389,11 @@ static int sync_and_check(iftrcuRenderer* r) {
     if (r->haveDraw && r->hCounters[6]) { r->hCounters[6] = 0; return r->fail(IFRIT_ERR_UNSUPPORTED, "drawElements", "alpha blending: a tile holds more than 4096 triangles"); }
     if (r->hTimedOut && *r->hTimedOut) { *r->hTimedOut = 0; return r->fail(IFRIT_ERR_STATE, "frame flags", "a sort-first rank did not signal within 2 s"); }
     if (r->haveDraw) {
+        // the two spread counters (common.cuh): one 32-byte sector per slot behind the 8 scalars
+        unsigned long long sum[2] = {0, 0};
+        for (int w = 0; w < 2; w++)
+            for (int i = 0; i < IFR_SPREAD; i++) sum[w] += r->hCounters[8 + ((size_t)w * IFR_SPREAD + i) * 4];
+        r->hCounters[0] = sum[0]; r->hCounters[2] = sum[1];
         r->stats.triangles_assembled = r->hCounters[0];
         r->stats.tile_pairs = r->hCounters[1] + r->hCounters[5];
         r->stats.fragments_shaded = r->hCounters[2];
@@ -416,11 +421,11 @@ int iftrcuCreateInstance(int cudaDevice, iftrcuRenderer** out) {
     memset(r->tex, 0, sizeof r->tex); memset(r->samp, 0, sizeof r->samp); memset(&r->stats, 0, sizeof r->stats);
     memset(r->scissor, 0, sizeof r->scissor);
     if (cudaSetDevice(cudaDevice) != cudaSuccess || cudaStreamCreateWithFlags(&r->ownStream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMallocHost((void**)&r->hCounters, 64) != cudaSuccess || cudaMallocHost((void**)&r->hTimedOut, 64) != cudaSuccess) {
+        cudaMallocHost((void**)&r->hCounters, IFR_COUNTER_BYTES) != cudaSuccess || cudaMallocHost((void**)&r->hTimedOut, 64) != cudaSuccess) {
         delete r;
         return IFRIT_ERR_CUDA;
     }
-    memset(r->hCounters, 0, 64);
+    memset(r->hCounters, 0, IFR_COUNTER_BYTES);
     memset(r->hTimedOut, 0, 64);
     if (ensure_pipeline(r) != IFRIT_OK) { iftrcuDestroyInstance(r); return IFRIT_ERR_CUDA; }
     r->stream = r->ownStream;

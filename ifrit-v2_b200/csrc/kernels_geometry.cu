@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(256, IFR_SETUP_MINB) setup_count_kernel(const 
     }
     // block-aggregated statistics
     nasm = __reduce_add_sync(0xffffffffu, (unsigned)nasm);
-    if ((threadIdx.x & 31) == 0 && nasm) atomicAdd(&p.counters[0], nasm);
+    if ((threadIdx.x & 31) == 0 && nasm) ifr_count_spread(p.counters, 0, blockIdx.x * 8u + (threadIdx.x >> 5), nasm);
 }
 
 // pass 3a: single-tile small triangles of the first fan — one thread per input triangle, nothing but

@@ -393,8 +393,11 @@ __device__ __forceinline__ void big_loop(const DrawParams& p, const KeyMode& km,
 // resident CTAs per SM the register budget is cut for.  Measured (profiles/r01d_ab.txt): the 1x textured kernels are
 // latency bound on the texture fetches — 6 CTAs (40 registers, some spills) beat 4 by 4 %; the plain-varying 1x
 // kernels (small-triangle soup) lose 20 % with more than 4; the multisampled variants keep 64 registers.
+#ifndef IFR_MINB8
+#define IFR_MINB8 4
+#endif
 template <int FS, int S>
-__global__ void __launch_bounds__(256, (S == 1 && FsTraits<FS>::needsDerivs) ? IFR_MINB1 : 4) tile_kernel(const __grid_constant__ DrawParams p) {
+__global__ void __launch_bounds__(256, FsTraits<FS>::needsDerivs ? (S == 1 ? IFR_MINB1 : IFR_MINB8) : 4) tile_kernel(const __grid_constant__ DrawParams p) {
     extern __shared__ unsigned long long keys[];        // [S][256], index = owning thread
     __shared__ __align__(128) TriS bigBuf[2][IFR_BIG_CHUNK];
     __shared__ __align__(8) uint64_t mbar[2];
@@ -595,7 +598,8 @@ __global__ void __launch_bounds__(256, (S == 1 && FsTraits<FS>::needsDerivs) ? I
         }
     }
     myFrags = __reduce_add_sync(0xffffffffu, myFrags);
-    if ((tid & 31) == 0 && myFrags) atomicAdd(&p.counters[2], (unsigned long long)myFrags);   // no CTA barrier: warps retire independently
+    if ((tid & 31) == 0 && myFrags)   // no CTA barrier: warps retire independently; spread over 256 sectors (common.cuh)
+        ifr_count_spread(p.counters, 1, (unsigned)(tile * 8 + wrp) * 2654435761u >> 16, (unsigned long long)myFrags);
 }
 
 // ---- ordered alpha blending ----------------------------------------------------------------------
@@ -730,7 +734,7 @@ __global__ void __launch_bounds__(256, 2) tile_blend_kernel(const __grid_constan
         if (p.primIds) p.primIds[pidx] = lastPrim;
     }
     myFrags = __reduce_add_sync(0xffffffffu, myFrags);
-    if ((tid & 31) == 0 && myFrags) atomicAdd(&p.counters[2], (unsigned long long)myFrags);
+    if ((tid & 31) == 0 && myFrags) ifr_count_spread(p.counters, 1, (unsigned)(tile * 8 + wrp) * 2654435761u >> 16, (unsigned long long)myFrags);
 }
 
 template <int FS>
