@@ -531,7 +531,9 @@ __global__ void __launch_bounds__(256, FsTraits<FS>::needsDerivs ? (S == 1 ? IFR
     unsigned int myFrags = 0;
     // One FS invocation per (pixel, slot) that owns >= 1 sample, slots in ascending order (CU:2264-2310).  A lane
     // shades alone (see interp), so the loop runs max-over-lanes(distinct slots) times and nothing is quad-uniform.
-    // (Tried and measured slower, c3 tile 0.44 -> 0.57 ms: compacting the second / third slots of edge pixels into a
+    // (Tried and measured slower.  Two tiles per CTA with both queue headers and both first chunks fetched up front:
+    // c2 tile 0.280 -> 0.311 ms, c3 0.441 -> 0.506 — the prologue latency of a fresh CTA is already covered by the other
+    // resident CTAs.  c3 tile 0.44 -> 0.57 ms: compacting the second / third slots of edge pixels into a
     // shared work list shaded one per thread — the kernel is latency bound, and the two CTA barriers plus one warp
     // shading the list while seven wait cost more than the divergent second pass they replace.)
     uint32_t last = 0;
