@@ -169,6 +169,14 @@ static void build_params(iftrcuRenderer* r, DrawParams& p) {
     p.tilesX = (r->W + IFR_TILE - 1) / IFR_TILE; p.tilesY = (r->H + IFR_TILE - 1) / IFR_TILE;
     p.msaa = r->msaa; p.depthFunc = r->depthTest ? r->depthFunc : IF_COMPARE_OP_ALWAYS;   // CUHOST:207-218
     p.cullMode = r->cullMode; p.convention = r->convention;
+    {
+        const int f = p.depthFunc;
+        p.keyOrdered = f == IF_COMPARE_OP_LESS || f == IF_COMPARE_OP_LESS_OR_EQUAL || f == IF_COMPARE_OP_GREATER || f == IF_COMPARE_OP_GREATER_OR_EQUAL;
+        p.keyXhi = (f == IF_COMPARE_OP_GREATER || f == IF_COMPARE_OP_GREATER_OR_EQUAL) ? 0xffffffffu : 0u;
+        p.keyXlo = (f == IF_COMPARE_OP_LESS_OR_EQUAL || f == IF_COMPARE_OP_GREATER_OR_EQUAL) ? 0xffffffffu : 0u;
+        p.keyEqual = f == IF_COMPARE_OP_EQUAL;
+        p.keyNever = !p.keyOrdered && !p.keyEqual && f != IF_COMPARE_OP_ALWAYS;
+    }
     p.doClear = r->pendingClear ? 1 : 0;
     memcpy(p.clearColor, r->clearColor, sizeof p.clearColor);
     p.clearDepth = r->clearDepth;

@@ -59,6 +59,9 @@ struct DrawParams {
     uint32_t* present;   // optional packed RGBA8 presentation image (iftrcuBindPresentBuffer), written with the colour
     int W, H, tilesX, tilesY;
     int msaa, depthFunc, cullMode, convention;
+    // visibility-key mode of depthFunc, precomputed by the host (kernels_tile.cu: KeyMode) so that the hot loops read
+    // it from the constant bank instead of re-deriving it from the compare op
+    uint32_t keyXhi, keyXlo; int keyOrdered, keyEqual, keyNever;
     int doClear; float clearColor[4]; float clearDepth;
     int scissorEnable, nScissor; float scissor[IFR_MAX_SCISSOR][4];
     int rank, world;

@@ -411,7 +411,11 @@ __global__ void __launch_bounds__(256, FsTraits<FS>::needsDerivs ? (S == 1 ? IFR
     const int tid = threadIdx.x;
     // a warp owns one 8x4-pixel block of the tile (block = warp: x = (w & 1) * 8, y = (w >> 1) * 4), a quad = 4 lanes
     const int wrp = tid >> 5, q = (tid >> 2) & 7, l = tid & 3;
-    const int lx = (wrp & 1) * 8 + (q & 3) * 2 + (l & 1), ly = (wrp >> 1) * 4 + (q >> 2) * 2 + (l >> 1);
+    // under the 40-register budget of the 1x kernels the compiler re-derives lx / ly from the thread id (a dozen bit
+    // operations) at every use inside the hot loops; an opaque packed copy makes it keep (or at worst reload) the value
+    int lxy = ((wrp & 1) * 8 + (q & 3) * 2 + (l & 1)) | (((wrp >> 1) * 4 + (q >> 2) * 2 + (l >> 1)) << 16);
+    asm volatile("" : "+r"(lxy));
+    const int lx = lxy & 0xffff, ly = lxy >> 16;
     const int px = tileX * IFR_TILE + lx, py = tileY * IFR_TILE + ly;
     const bool inFrame = px < p.W && py < p.H;
     const bool scis = inFrame && scissor_pass(p, px, py);
@@ -440,7 +444,8 @@ __global__ void __launch_bounds__(256, FsTraits<FS>::needsDerivs ? (S == 1 ? IFR
         return;
     }
 
-    const KeyMode km = key_mode(p.depthFunc);
+    KeyMode km;     // precomputed by the host from p.depthFunc (same table as key_mode)
+    km.xhi = p.keyXhi; km.xlo = p.keyXlo; km.ordered = p.keyOrdered != 0; km.equal = p.keyEqual != 0; km.never = p.keyNever != 0;
     float d0 = 0.0f;
     if (inFrame) d0 = (p.doClear && scis) ? p.clearDepth : p.depth[pidx];
     const unsigned long long k0 = key_init(km, d0);

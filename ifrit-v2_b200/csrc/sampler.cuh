@@ -181,27 +181,36 @@ __device__ __forceinline__ float4 sample_aniso(const TexDesc& t, const SampDesc&
     if (FAST && ctx.lo.hw && (ctx.d == 0.0f || ctx.hi.hw) && s.filter == IF_FILTER_LINEAR &&
         s.addrU != IF_SAMPLER_ADDRESS_MODE_CLAMP_TO_BORDER && s.addrV != IF_SAMPLER_ADDRESS_MODE_CLAMP_TO_BORDER) {
         // every footprint goes through the texture unit: taps are issued two at a time (up to four fetches in
-        // flight) and summed in tap order
+        // flight) and summed in tap order; REPEAT / REPEAT (the common sampler) runs a copy of the loop without the
+        // per-tap switch on the address mode
         const bool two = ctx.d != 0.0f;
-        for (int i = 0; i < n; i += 2) {
-            const float t0 = (float)i * step - 0.5f, t1 = (float)(i + 1) * step - 0.5f;
-            const float u0 = fmaf(ddu, t0, u), v0 = fmaf(ddv, t0, v), u1 = fmaf(ddu, t1, u), v1 = fmaf(ddv, t1, v);
-            const bool has1 = i + 1 < n;
-            const float2 a0 = tap_coords(ctx.lo, s, u0, v0), a1 = tap_coords(ctx.lo, s, u1, v1);
-            float4 r0 = tex2D<float4>((cudaTextureObject_t)ctx.lo.hw, a0.x, a0.y);
-            float4 r1 = make_float4(0, 0, 0, 0);
-            if (has1) r1 = tex2D<float4>((cudaTextureObject_t)ctx.lo.hw, a1.x, a1.y);
-            if (two) {
-                const float2 b0 = tap_coords(ctx.hi, s, u0, v0), b1 = tap_coords(ctx.hi, s, u1, v1);
-                const float4 h0 = tex2D<float4>((cudaTextureObject_t)ctx.hi.hw, b0.x, b0.y);
-                float4 h1 = make_float4(0, 0, 0, 0);
-                if (has1) h1 = tex2D<float4>((cudaTextureObject_t)ctx.hi.hw, b1.x, b1.y);
-                r0 = lerp4(r0, h0, ctx.d);
-                r1 = lerp4(r1, h1, ctx.d);
+        auto taps = [&](auto coords) {
+            for (int i = 0; i < n; i += 2) {
+                const float t0 = (float)i * step - 0.5f, t1 = (float)(i + 1) * step - 0.5f;
+                const float u0 = fmaf(ddu, t0, u), v0 = fmaf(ddv, t0, v), u1 = fmaf(ddu, t1, u), v1 = fmaf(ddv, t1, v);
+                const bool has1 = i + 1 < n;
+                const float2 a0 = coords(ctx.lo, u0, v0), a1 = coords(ctx.lo, u1, v1);
+                float4 r0 = tex2D<float4>((cudaTextureObject_t)ctx.lo.hw, a0.x, a0.y);
+                float4 r1 = make_float4(0, 0, 0, 0);
+                if (has1) r1 = tex2D<float4>((cudaTextureObject_t)ctx.lo.hw, a1.x, a1.y);
+                if (two) {
+                    const float2 b0 = coords(ctx.hi, u0, v0), b1 = coords(ctx.hi, u1, v1);
+                    const float4 h0 = tex2D<float4>((cudaTextureObject_t)ctx.hi.hw, b0.x, b0.y);
+                    float4 h1 = make_float4(0, 0, 0, 0);
+                    if (has1) h1 = tex2D<float4>((cudaTextureObject_t)ctx.hi.hw, b1.x, b1.y);
+                    r0 = lerp4(r0, h0, ctx.d);
+                    r1 = lerp4(r1, h1, ctx.d);
+                }
+                sum.x += r0.x; sum.y += r0.y; sum.z += r0.z; sum.w += r0.w;
+                if (has1) { sum.x += r1.x; sum.y += r1.y; sum.z += r1.z; sum.w += r1.w; }
             }
-            sum.x += r0.x; sum.y += r0.y; sum.z += r0.z; sum.w += r0.w;
-            if (has1) { sum.x += r1.x; sum.y += r1.y; sum.z += r1.z; sum.w += r1.w; }
-        }
+        };
+        if (s.addrU == IF_SAMPLER_ADDRESS_MODE_REPEAT && s.addrV == IF_SAMPLER_ADDRESS_MODE_REPEAT)
+            taps([&](const LevelCtx& L, float uu, float vv) {
+                return make_float2(wrapf(fmaf(uu, L.fw1, 0.0f), L.fw, L.invW) + 0.5f, wrapf(fmaf(vv, L.fh1, 0.0f), L.fh, L.invH) + 0.5f);
+            });
+        else
+            taps([&](const LevelCtx& L, float uu, float vv) { return tap_coords(L, s, uu, vv); });
     } else {
         for (int i = 0; i < n; i++) {
             const float tt = (float)i * step - 0.5f;
