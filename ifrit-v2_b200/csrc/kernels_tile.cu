@@ -114,9 +114,13 @@ __device__ __forceinline__ void key_min_shared(unsigned long long* addr, unsigne
 // Perspective weights (u, v, 1 - (u + v)) of the clip-space barycentrics from the three edge values at a pixel
 // corner; beta_i = float(E_i) * ar is also what the depth plane uses.
 struct PixW { float u, v, w2; };
+// FASTW (the FAST textured shaders only — colour within 1/255, depth is not computed from these): SFU reciprocal, and the
+// unclipped barycentric mapping as plain selects instead of fma chains with 0 / 1 factors
+template <bool FASTW>
 __device__ __forceinline__ PixW persp_weights(const float beta[3], const float IW[3], uint32_t flags, const float* cb) {
     float b0 = __fmul_rn(beta[0], IW[0]), b1 = __fmul_rn(beta[1], IW[1]), b2 = __fmul_rn(beta[2], IW[2]);
-    const float inv = __frcp_rn(__fadd_rn(__fadd_rn(b0, b1), b2));
+    const float sum = __fadd_rn(__fadd_rn(b0, b1), b2);
+    const float inv = FASTW ? rcp_fast(sum) : __frcp_rn(sum);
     b0 = __fmul_rn(b0, inv); b1 = __fmul_rn(b1, inv); b2 = __fmul_rn(b2, inv);
     PixW w;
     if (flags & IFR_FLAG_CLIPPED) {
@@ -127,9 +131,12 @@ __device__ __forceinline__ PixW persp_weights(const float beta[3], const float I
         // exchanged by a cull swap: B = {(0,1),(0,0),(1,0)} or {(1,0),(0,0),(0,1)}.  The fma chains with
         // exact 0 / 1 factors reduce to (x * 1 + 0 * y + 0) = x up to the sign of zero, which + 0.0f fixes.
         const bool sw = flags & IFR_FLAG_SWAPPED;
-        const float B00 = sw ? 1.0f : 0.0f, B01 = sw ? 0.0f : 1.0f;
-        w.u = fmaf(b2, B01, fmaf(b1, 0.0f, __fmul_rn(b0, B00)));
-        w.v = fmaf(b2, B00, fmaf(b1, 0.0f, __fmul_rn(b0, B01)));
+        if (FASTW) { w.u = sw ? b0 : b2; w.v = sw ? b2 : b0; }
+        else {
+            const float B00 = sw ? 1.0f : 0.0f, B01 = sw ? 0.0f : 1.0f;
+            w.u = fmaf(b2, B01, fmaf(b1, 0.0f, __fmul_rn(b0, B00)));
+            w.v = fmaf(b2, B00, fmaf(b1, 0.0f, __fmul_rn(b0, B01)));
+        }
     }
     w.w2 = __fsub_rn(1.0f, __fadd_rn(w.u, w.v));
     return w;
@@ -149,7 +156,7 @@ __device__ __forceinline__ float4 mix3(const float4& v0, const float4& v1, const
 // values itself from the same integer edge functions (E steps by -256 dY / +256 dX per pixel), which is
 // bit-identical to what a helper lane would compute, so a pixel shades alone: no helper invocations, no
 // quad-uniform control flow, every FS pass runs with all of its lanes useful.
-template <int NV, bool DERIV>
+template <int NV, bool DERIV, bool FASTW = false>
 __device__ __forceinline__ void interp(const DrawParams& p, uint32_t slot, int px, int py, float4* out, float4* ddx,
                                        float4* ddy, float& depth, int& prim, int& fan) {
     const int4* r = reinterpret_cast<const int4*>(p.rec + slot);
@@ -208,9 +215,9 @@ __device__ __forceinline__ void interp(const DrawParams& p, uint32_t slot, int p
 #pragma unroll
         for (int j = 0; j < 6; j++) cb[j] = __ldg(g + j);
     }
-    const PixW w = persp_weights(beta, IW, flags, cb);
+    const PixW w = persp_weights<FASTW>(beta, IW, flags, cb);
     PixW wh = w, wv = w;
-    if (DERIV) { wh = persp_weights(betaH, IW, flags, cb); wv = persp_weights(betaV, IW, flags, cb); }
+    if (DERIV) { wh = persp_weights<FASTW>(betaH, IW, flags, cb); wv = persp_weights<FASTW>(betaV, IW, flags, cb); }
     const bool right = px & 1, bottom = py & 1;
 #pragma unroll
     for (int k = 0; k < NV; k++) {
@@ -557,7 +564,7 @@ __global__ void __launch_bounds__(256, FsTraits<FS>::needsDerivs ? (S == 1 ? IFR
         float4 v[NV > 0 ? NV : 1], ddx[NV > 0 ? NV : 1], ddy[NV > 0 ? NV : 1];
         float depth = 0.0f;
         int prim = 0, fan = 0;
-        interp<NV, FsTraits<FS>::needsDerivs>(p, cur, px, py, v, ddx, ddy, depth, prim, fan);
+        interp<NV, FsTraits<FS>::needsDerivs, FS == IFRIT_FS_TEXTURED_FAST || FS == IFRIT_FS_TEXTURED_LOD0_FAST>(p, cur, px, py, v, ddx, ddy, depth, prim, fan);
         const float4 c = run_fs<FS>(p, v, ddx, ddy, prim, fan);
         const float fc = (float)cnt;
         acc.x = fmaf(fc, c.x, acc.x); acc.y = fmaf(fc, c.y, acc.y);

@@ -8,9 +8,10 @@
 
 // order-preserving float -> uint map of the visibility keys (oracle: key_* in ifrit_oracle.c)
 __device__ __forceinline__ uint32_t mono(float d) {
-    d = d + 0.0f;
+    d = d + 0.0f;                                   // -0 -> +0
     const uint32_t b = __float_as_uint(d);
-    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    // negative: all bits flipped, otherwise the sign bit set — one arithmetic shift + two logic ops
+    return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
 }
 
 struct RecRegs { int X[3], Y[3]; float Z[3]; float ar; uint32_t flags; };
