@@ -276,9 +276,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 struct HizShared { uint32_t warpFar[8]; uint32_t nSurv[2]; uint8_t surv[2][32]; };
 
 template <int S>
-__device__ __forceinline__ uint32_t block_far(const unsigned long long* keys, int tid, unsigned long long best) {
+__device__ __forceinline__ uint32_t block_far(const unsigned long long* keys, int tid, unsigned long long best, bool uni) {
     uint32_t mine;
-    if (S == 1) mine = (uint32_t)(best >> 32);
+    if (S == 1 || uni) mine = (uint32_t)(best >> 32);
     else {
         mine = 0;
 #pragma unroll
@@ -290,7 +290,7 @@ __device__ __forceinline__ uint32_t block_far(const unsigned long long* keys, in
 // one big-queue entry against this thread's pixel; returns true if a key of the pixel changed
 template <int S, bool HIZ>
 __device__ __forceinline__ bool big_test(const DrawParams& p, const KeyMode& km, unsigned long long* keys, const int4* t4, uint32_t cz,
-                                         int tid, int wrp, int lx, int ly, bool scis, float d0, unsigned long long& best) {
+                                         int tid, int wrp, int lx, int ly, bool scis, float d0, unsigned long long& best, bool& uni) {
     const int ci = 16 * lx, cj = 16 * ly;
     const int4 A = t4[0];
     const int4 B = t4[1], C = t4[2];
@@ -316,6 +316,18 @@ __device__ __forceinline__ bool big_test(const DrawParams& p, const KeyMode& km,
             if (key_make(km, d, d0, (uint32_t)B.w, k)) {
                 if (S == 1) {
                     if (k < best) { best = k; upd = true; }
+                } else if (uni) {
+                    // every sample of the pixel still holds the same key (`best`, in a register: pixels inside one
+                    // triangle never touch shared memory); the first partially covering winner materialises it
+                    if (k < best) {
+                        upd = true;
+                        if (m == (1u << S) - 1u) best = k;
+                        else {
+#pragma unroll
+                            for (int sm = 0; sm < S; sm++) keys[sm * IFR_TILE_PIX + tid] = ((m >> sm) & 1) ? k : best;
+                            uni = false;
+                        }
+                    }
                 } else {
 #pragma unroll
                     for (int sm = 0; sm < S; sm++)
@@ -330,11 +342,11 @@ __device__ __forceinline__ bool big_test(const DrawParams& p, const KeyMode& km,
 template <int S, bool HIZ>
 __device__ __forceinline__ void big_loop(const DrawParams& p, const KeyMode& km, unsigned long long* keys, TriS (*bigBuf)[IFR_BIG_CHUNK],
                                          uint64_t* mbar, HizShared& hz, const TriS* bigSrc, uint32_t nBig, int tid, int wrp, int lx,
-                                         int ly, bool scis, float d0, unsigned long long& best) {
+                                         int ly, bool scis, float d0, unsigned long long& best, bool& uni) {
     const int lane = tid & 31;
     uint32_t wfar = 0xffffffffu;
     if (HIZ) {
-        wfar = block_far<S>(keys, tid, best);
+        wfar = block_far<S>(keys, tid, best, uni);
         if (lane == 0) hz.warpFar[wrp] = wfar;     // read (possibly stale = larger = conservative) by the chunk preparation
     }
     const uint32_t nchunks = (nBig + IFR_BIG_CHUNK - 1) / IFR_BIG_CHUNK;
@@ -353,7 +365,7 @@ __device__ __forceinline__ void big_loop(const DrawParams& p, const KeyMode& km,
                 // warp-uniform coarse reject: the fill pass rasterised the triangle against the tile's 8x4 blocks
                 const uint32_t cz = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(t4) + 88);
                 if (!((cz >> wrp) & 1)) continue;
-                big_test<S, false>(p, km, keys, t4, cz, tid, wrp, lx, ly, scis, d0, best);
+                big_test<S, false>(p, km, keys, t4, cz, tid, wrp, lx, ly, scis, d0, best, uni);
             }
         } else {
             // chunk preparation, warps 0 and 1, one thread per staged entry: trivial-accept blocks + key bound written
@@ -380,9 +392,9 @@ __device__ __forceinline__ void big_loop(const DrawParams& p, const KeyMode& km,
                     const uint2 cz = *reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(t4) + 88);
                     if (!((cz.x >> wrp) & 1)) continue;
                     if (cz.y > wfar) continue;          // warp-uniform Hi-Z reject
-                    const bool upd = big_test<S, true>(p, km, keys, t4, cz.x, tid, wrp, lx, ly, scis, d0, best);
+                    const bool upd = big_test<S, true>(p, km, keys, t4, cz.x, tid, wrp, lx, ly, scis, d0, best, uni);
                     if (__any_sync(0xffffffffu, upd)) {  // warp-convergent: every reject above is warp-uniform
-                        wfar = block_far<S>(keys, tid, best);
+                        wfar = block_far<S>(keys, tid, best, uni);
                         if (lane == 0) hz.warpFar[wrp] = wfar;
                     }
                 }
@@ -459,11 +471,10 @@ __global__ void __launch_bounds__(256, FsTraits<FS>::needsDerivs ? (S == 1 ? IFR
     // Per-sample visibility keys.  S == 1: the pixel's key lives in a register (`best`); shared memory is only the
     // mailbox through which small triangles (processed by other threads) reach this pixel, filled from `best`
     // once the big triangles are done.
-    if (S > 1) {
-#pragma unroll
-        for (int s = 0; s < S; s++) keys[s * IFR_TILE_PIX + tid] = k0;
-    }
+    // S > 1: while every sample of the pixel holds the same key it lives in `best` too (`uni`); the per-sample keys in
+    // shared memory are only written once a triangle covers the pixel partially (or a small-triangle pass follows).
     unsigned long long best = k0;
+    bool uni = true;
     const bool deep = km.ordered && nBig >= IFR_HIZ_MIN_QUEUE;
 
     // ---- big triangles first: their result gives the small-triangle pass a far bound per 8x4 block ----
@@ -477,20 +488,25 @@ __global__ void __launch_bounds__(256, FsTraits<FS>::needsDerivs ? (S == 1 ? IFR
         const TriS* bigSrc = p.bigQueue + bStart;
         if (tid == 0) bulk_load(bigBuf[0], bigSrc, min(nBig, (uint32_t)IFR_BIG_CHUNK) * (uint32_t)sizeof(TriS), &mbar[0]);
 #ifndef IFR_NO_HIZ
-        if (deep) big_loop<S, true>(p, km, keys, bigBuf, mbar, hz, bigSrc, nBig, tid, wrp, lx, ly, scis, d0, best);
+        if (deep) big_loop<S, true>(p, km, keys, bigBuf, mbar, hz, bigSrc, nBig, tid, wrp, lx, ly, scis, d0, best, uni);
         else
 #endif
-            big_loop<S, false>(p, km, keys, bigBuf, mbar, hz, bigSrc, nBig, tid, wrp, lx, ly, scis, d0, best);
+            big_loop<S, false>(p, km, keys, bigBuf, mbar, hz, bigSrc, nBig, tid, wrp, lx, ly, scis, d0, best, uni);
     }
 
     // ---- small triangles: one thread per (triangle, tile) pair, shared-memory atomicMin --------------
     if (nSmall) {
         if (S == 1) keys[tid] = best;
+        else if (uni) {
+#pragma unroll
+            for (int s = 0; s < S; s++) keys[s * IFR_TILE_PIX + tid] = best;
+            uni = false;
+        }
         // per-pixel early-Z against the block's far bound (deep tiles: most small triangles are hidden behind the big
         // ones): depth first, coverage only for pixels that can still win a sample
         const bool useFar = deep;
         if (useFar) {
-            const uint32_t f = block_far<S>(keys, tid, best);
+            const uint32_t f = block_far<S>(keys, tid, best, uni);
             if ((tid & 31) == 0) hz.warpFar[wrp] = f;
         }
         __syncthreads();      // keys complete, far bounds published
@@ -533,7 +549,7 @@ __global__ void __launch_bounds__(256, FsTraits<FS>::needsDerivs ? (S == 1 ? IFR
 #pragma unroll
     for (int s = 0; s < S; s++) {
         unsigned long long k = best;
-        if (S > 1 || nSmall) k = keys[s * IFR_TILE_PIX + tid];
+        if (S > 1 ? !uni : nSmall != 0) k = keys[s * IFR_TILE_PIX + tid];
         mySlots[s] = key_slot(km, k);
     }
 
