@@ -607,7 +607,10 @@ int iftrcuBindPeerFrameBuffer(iftrcuRenderer* h, const void* handle128, int widt
     CUDA_TRY(cudaIpcOpenMemHandle(&r->peerColor, hc, cudaIpcMemLazyEnablePeerAccess));
     CUDA_TRY(cudaIpcOpenMemHandle(&r->peerDepth, hd, cudaIpcMemLazyEnablePeerAccess));
     if (r->registeredHost) { cudaHostUnregister(r->registeredHost); r->registeredHost = nullptr; }
-    r->dColor = (float4*)r->peerColor; r->dDepth = (float*)r->peerDepth; r->externalFB = true; r->hColor = nullptr; r->hDepth = nullptr;
+    // colour goes straight into the owner's frame; depth stays local (the reference's read-back carries colour only,
+    // CU:3899-3909, and the owner's NVLink ingress is what bounds the exchange: 16 instead of 20 bytes per pixel)
+    CUDA_TRY(r->ownDepth.ensure((size_t)width * height * 4));
+    r->dColor = (float4*)r->peerColor; r->dDepth = (float*)r->ownDepth.p; r->externalFB = true; r->hColor = nullptr; r->hDepth = nullptr;
     r->frameFlags = (uint32_t*)((char*)r->peerDepth + flag_offset(width, height));
     r->fencePending = false;
     if (r->W != width || r->H != height) r->scr[0].queueChecked = r->scr[1].queueChecked = false;

@@ -263,6 +263,8 @@ IFRIT_B200_API int iftrcuSetFramePipelining(iftrcuRenderer* h, int enable);
 IFRIT_B200_API int iftrcuBindPresentBuffer(iftrcuRenderer* h, void* hostRGBA8, int format);
 IFRIT_B200_API int iftrcuReadPresent(iftrcuRenderer* h, void* dstRGBA8);
 IFRIT_B200_API int iftrcuExportFrameBuffer(iftrcuRenderer* h, void* handleOut128);
+/* peer: the owner's COLOUR buffer becomes this instance's render target (its tiles are stored over NVLink); depth stays
+ * in a local buffer — after a sort-first frame the owner holds the complete colour image and the depth of its own tiles */
 IFRIT_B200_API int iftrcuBindPeerFrameBuffer(iftrcuRenderer* h, const void* handle128, int width, int height);
 /* Sort-first frame flags (peer-memory mode; no reference counterpart — the reference is single-GPU).
  * The framebuffer owner's allocation carries a block of 32-bit flag words that every rank reaches through the same
