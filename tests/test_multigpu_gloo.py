@@ -60,3 +60,49 @@ def test_sort_first_gather_gloo(world):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert ok
+
+
+def test_peer_mode_frame_flag_protocol():
+    """SortFirstRenderer in peer mode drives the device-side frame flags (include/ifrit_b200.h: iftrcuFrameSignal / Wait /
+    Release / Fence): every rank signals its frame; rank 0 waits for all and releases (or holds until release()); the
+    other ranks fence their next tile kernel on that release.  Host logic only, with a recording stand-in renderer."""
+    from ifrit_v2_b200 import multigpu as MG
+
+    class Rec:
+        width, height = 128, 64
+
+        def __init__(self):
+            self.calls = []
+
+        def setTilePartition(self, rank, world):
+            self.calls.append(("partition", rank, world))
+
+        def __getattr__(self, name):
+            if name.startswith("frame"):
+                return lambda fid: self.calls.append((name, fid))
+            raise AttributeError(name)
+
+    class Dist:
+        def __init__(self, rank, world):
+            self.rank, self.world = rank, world
+
+        def get_rank(self):
+            return self.rank
+
+        def get_world_size(self):
+            return self.world
+
+    share = MG.share_framebuffer
+    MG.share_framebuffer = lambda *a, **k: None          # CUDA IPC export / bind: exercised by tests/mgpu_check.py
+    try:
+        r0, r1 = Rec(), Rec()
+        s0 = MG.SortFirstRenderer(r0, Dist(0, 2), None, mode="peer")
+        s1 = MG.SortFirstRenderer(r1, Dist(1, 2), None, mode="peer")
+        s0.gather(); s1.gather()
+        s0.gather(hold=True); s1.gather(hold=True)
+        s0.release(); s1.release()
+    finally:
+        MG.share_framebuffer = share
+    assert r0.calls == [("partition", 0, 2), ("frameSignal", 1), ("frameWait", 1), ("frameRelease", 1),
+                        ("frameSignal", 2), ("frameWait", 2), ("frameRelease", 2)]
+    assert r1.calls == [("partition", 1, 2), ("frameSignal", 1), ("frameFence", 1), ("frameSignal", 2), ("frameFence", 2)]
