@@ -54,6 +54,7 @@ def lib():
         L.iftrOptsetForceDeterministic.argtypes = [vp, C.c_int]
         L.iftrOptSetDepthTestEnable.argtypes = [vp, C.c_int]
         L.iftrDrawLegacy.argtypes = [vp, C.c_int, C.c_int]
+        L.iftrSetBlendFunc.argtypes = [vp, vp]
         _LIB = L
     return _LIB
 
@@ -113,6 +114,19 @@ class RefRenderer:
         L.iftrSetDepthFunc(self.h, _orc.CMP_LESS)
         L.iftrOptsetForceDeterministic(self.h, 0)
         L.iftrOptSetDepthTestEnable(self.h, 1)
+
+    def set_blend(self, src, dst, src_a, dst_a):
+        """iftrSetBlendFunc (TileRasterRendererExport.h; TileRasterRenderer.cpp:212-330): IfritColorAttachmentBlendState =
+        {bool blendEnable; IfritBlendFactor src, dst, srcAlpha, dstAlpha}.  Blending switches the reference to its
+        ordered (deterministic) mode, TileRasterWorker.cpp:410."""
+        class _BS(C.Structure):
+            _fields_ = [("blendEnable", C.c_uint8), ("src", C.c_int32), ("dst", C.c_int32), ("srcA", C.c_int32),
+                        ("dstA", C.c_int32)]
+        self._blend = _BS(1, src, dst, src_a, dst_a)
+        lib().iftrSetBlendFunc(self.h, C.byref(self._blend))
+
+    def set_depth_test(self, enable):
+        lib().iftrOptSetDepthTestEnable(self.h, int(enable))
 
     def draw(self, clear=True):
         lib().iftrDrawLegacy(self.h, len(self.idx), int(clear))

@@ -102,3 +102,29 @@ def test_oracle_textured_lod0_vs_live_reference():
     o = O.draw(st, vb, idx, 1, O.FS_TEXTURED_LOD0, 2, u, textures=[O.make_texture(tex.reshape(-1), 128, 128, 0, 1)],
                samplers=[O.make_sampler(filter=1)])
     _check(o, ref.color(), ref.depth(), "mesh_textured")
+
+
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref/libifrit_ref.so not built (needs /root/reference)")
+@pytest.mark.parametrize("blend,seed,n,size,bar", [((6, 7, 1, 0), 5, 40, 0.4, 0.99), ((1, 1, 1, 1), 5, 40, 0.4, 0.999),
+                                                   ((6, 7, 1, 0), 6, 300, 0.08, 0.999)])
+def test_oracle_blending_vs_live_reference(blend, seed, n, size, bar):
+    """Ordered alpha blending: the oracle's render_blend (restated from the CUDA kernel CU:1649-1897) against the
+    reference CPU renderer's blending (TileRasterWorker.cpp:2346-2373 — same formula and coefficient table,
+    TileRasterRenderer.cpp:212-330).  Colour only: the reference's ordered mode leaves an unreliable depth image
+    (SURVEY.md §8c).  Every layer of a pixel counts under blending, so FP32 edge flips of the reference show up more
+    often than in the opaque fixtures: the bar is 99 % of pixels within 1/255 for the order-dependent overlap-heavy
+    case, 99.9 % for the commutative (ONE, ONE) one and for small triangles."""
+    W, H = 160, 96
+    vb, idx = scenes.random_tris(n, seed, size=size)
+    vb[:, 7] = 0.2 + 0.6 * vb[:, 7]
+    u = scenes.uniform_block(np.eye(4))
+    ref = R.RefRenderer(W, H, vb, idx, 0, O.FS_VARYING0, 1, u)
+    ref.set_blend(*blend)
+    ref.set_depth_test(False)
+    ref.draw()
+    st = O.make_state(W, H, convention=O.CONV_CPU, cull=O.CULL_BACK, clear_depth=float(R.REF_DEPTH_CLEAR),
+                      depth_func=O.CMP_ALWAYS, blend=blend)
+    o = O.draw(st, vb, idx, 0, O.FS_VARYING0, 1, u)
+    ok = np.abs(o["color"] - ref.color()).max(-1) <= 1 / 255
+    assert ok.mean() >= bar, f"blend {blend}: {ok.mean():.5f} of pixels within 1/255"
+    assert ((o["prim_id"][..., 0] >= 0) != (ref.depth() < 1e38)).mean() <= 5e-4
