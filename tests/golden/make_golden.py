@@ -30,6 +30,22 @@ CASES = {
 }
 
 
+# ordered alpha blending on the reference CPU renderer (iftrSetBlendFunc, depth test off): name -> (blend factors, seed,
+# triangles, size); 160x96, alpha in [0.2, 0.8]; only the colour image is kept (ordered-mode depth is unreliable)
+BLEND_CASES = {
+    "blend_over": ((6, 7, 1, 0), 5, 40, 0.4),
+    "blend_add": ((1, 1, 1, 1), 5, 40, 0.4),
+    "blend_small": ((6, 7, 1, 0), 6, 300, 0.08),
+}
+BLEND_W, BLEND_H = 160, 96
+
+
+def blend_scene(seed, n, size):
+    vb, idx = scenes.random_tris(n, seed, size=size)
+    vb[:, 7] = 0.2 + 0.6 * vb[:, 7]
+    return vb, idx
+
+
 def ids(scene):
     """flat per-triangle id in varying 0 (the reference exports no id buffer)."""
     vb, idx = scene
@@ -55,6 +71,17 @@ def main():
         assert np.array_equal(d1, ref.depth()) and np.abs(c1 - ref.color()).max() < 1e-5, "reference not deterministic"
         np.savez_compressed(os.path.join(HERE, name + ".npz"), color=c1, depth=d1, W=W, H=H)
         print(name, "covered", int((d1 < 1e38).sum()))
+    for name, (blend, seed, n, size) in BLEND_CASES.items():
+        vb, idx = blend_scene(seed, n, size)
+        ref = R.RefRenderer(BLEND_W, BLEND_H, vb, idx, 0, O.FS_VARYING0, 1, scenes.uniform_block(np.eye(4)))
+        ref.set_blend(*blend)
+        ref.set_depth_test(False)
+        ref.draw()
+        c1 = ref.color()
+        ref.draw()
+        assert np.abs(c1 - ref.color()).max() < 1e-5, "reference blending not deterministic"
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), color=c1, covered=ref.depth() < 1e38)
+        print(name, "covered", int((ref.depth() < 1e38).sum()))
 
 
 if __name__ == "__main__":

@@ -128,3 +128,17 @@ def test_oracle_blending_vs_live_reference(blend, seed, n, size, bar):
     ok = np.abs(o["color"] - ref.color()).max(-1) <= 1 / 255
     assert ok.mean() >= bar, f"blend {blend}: {ok.mean():.5f} of pixels within 1/255"
     assert ((o["prim_id"][..., 0] >= 0) != (ref.depth() < 1e38)).mean() <= 5e-4
+
+
+@pytest.mark.parametrize("name,bar", [("blend_over", 0.99), ("blend_add", 0.999), ("blend_small", 0.999)])
+def test_oracle_blending_vs_golden_fixture(name, bar):
+    """Same comparison against the committed outputs of the reference (tests/golden/make_golden.py: BLEND_CASES)."""
+    blend, seed, n, size = MG.BLEND_CASES[name]
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    vb, idx = MG.blend_scene(seed, n, size)
+    st = O.make_state(MG.BLEND_W, MG.BLEND_H, convention=O.CONV_CPU, cull=O.CULL_BACK, clear_depth=float(R.REF_DEPTH_CLEAR),
+                      depth_func=O.CMP_ALWAYS, blend=blend)
+    o = O.draw(st, vb, idx, 0, O.FS_VARYING0, 1, scenes.uniform_block(np.eye(4)))
+    ok = np.abs(o["color"] - g["color"]).max(-1) <= 1 / 255
+    assert ok.mean() >= bar, f"{name}: {ok.mean():.5f} of pixels within 1/255"
+    assert ((o["prim_id"][..., 0] >= 0) != g["covered"]).mean() <= 5e-4
