@@ -190,7 +190,7 @@ static void build_params(iftrcuRenderer* r, DrawParams& p) {
     for (int k = 0; k < r->msaa; k++) {
         int ox = kSampleAgg[r->msaa - 1 + k][0], oy = kSampleAgg[r->msaa - 1 + k][1];
         if (r->convention == IFRIT_CONVENTION_CPU) { ox = 0; oy = 0; }   // WK:1043-1055: pixel corner
-        p.sampX[k] = (int8_t)ox; p.sampY[k] = (int8_t)oy;
+        p.sampX[k] = ox; p.sampY[k] = oy;
         if (k < ns) {
             mnx = std::min(mnx, ox * 16); mxx = std::max(mxx, ox * 16);
             mny = std::min(mny, oy * 16); mxy = std::max(mxy, oy * 16);

@@ -70,7 +70,7 @@ struct DrawParams {
     int blendEnable; float blendCoef[4][4];
     int hwFilter;   // bilinear footprints through the TEX unit (8-bit weights) instead of four loads + fp32 lerps
     // coverage sample pattern of this draw, in 1/16 pixel (from cMsaaSampleSequenceAgg, CU:223-234)
-    int8_t sampX[16], sampY[16];
+    alignas(16) int32_t sampX[16]; alignas(16) int32_t sampY[16];   // 32-bit: read with wide constant-bank loads, no byte extraction in the sample loop
     int sampMinX, sampMaxX, sampMinY, sampMaxY;   // extents in sub-pixel (1/256) units
     // geometry
     const uint8_t* vb; int stride, nattr, nvary, nverts; int attrOff[IFR_MAX_VARY + 1];
