@@ -347,7 +347,10 @@ __device__ __forceinline__ void big_loop(const DrawParams& p, const KeyMode& km,
     uint32_t wfar = 0xffffffffu;
     if (HIZ) {
         wfar = block_far<S>(keys, tid, best, uni);
-        if (lane == 0) hz.warpFar[wrp] = wfar;     // read (possibly stale = larger = conservative) by the chunk preparation
+        // published for the chunk preparation of warps 0 / 1, which may run concurrently: a stale value is larger, hence
+        // conservative; the bound only ever shrinks, so the publication is an atomicMin and the readers use atomics too
+        // (compute-sanitizer racecheck: no hazards)
+        if (lane == 0) atomicMin(&hz.warpFar[wrp], wfar);
     }
     const uint32_t nchunks = (nBig + IFR_BIG_CHUNK - 1) / IFR_BIG_CHUNK;
     for (uint32_t c = 0; c < nchunks; c++) {
@@ -375,7 +378,7 @@ __device__ __forceinline__ void big_loop(const DrawParams& p, const KeyMode& km,
                 if ((uint32_t)tid < cnt) {
                     uint32_t tileFar = 0;
 #pragma unroll
-                    for (int w = 0; w < 8; w++) tileFar = max(tileFar, hz.warpFar[w]);
+                    for (int w = 0; w < 8; w++) tileFar = max(tileFar, atomicOr(&hz.warpFar[w], 0u));
                     TriS* e = &bigBuf[c & 1][tid];
                     const uint32_t tb = setup_hiz(e, p.sampMinX, p.sampMaxX, p.sampMinY, p.sampMaxY, km.xhi);
                     alive = ((uint32_t)e->pad[0] & 0xffu) != 0 && tb <= tileFar;
@@ -395,7 +398,7 @@ __device__ __forceinline__ void big_loop(const DrawParams& p, const KeyMode& km,
                     const bool upd = big_test<S, true>(p, km, keys, t4, cz.x, tid, wrp, lx, ly, scis, d0, best, uni);
                     if (__any_sync(0xffffffffu, upd)) {  // warp-convergent: every reject above is warp-uniform
                         wfar = block_far<S>(keys, tid, best, uni);
-                        if (lane == 0) hz.warpFar[wrp] = wfar;
+                        if (lane == 0) atomicMin(&hz.warpFar[wrp], wfar);
                     }
                 }
             }
