@@ -84,3 +84,23 @@ def test_pack_unpack_host_roundtrip():
         for rank in range(world):
             MG.unpack_host(out, MG.pack_host(frame, rank, world), rank, world)
         assert np.array_equal(out, frame)
+
+
+def test_bench_algorithmic_bytes_follow_survey_8d():
+    """bench.py's roofline numerator: B = V*Sv + I*4 + P*(16+4) + Tex, Tex = min(1.33*covered, texels in chain)*16
+    (SURVEY.md §8d); C2 figures quoted there: 1.2 MB + 0.6 MB + 165.9 MB + <= 89.5 MB."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    cfg = bench.CONFIGS["c2"]
+    sc = dict(vb=np.zeros((25921, 12), np.float32), idx=np.zeros(153600, np.int32), tex=np.zeros((2048, 2048, 4), np.float32), mips=11)
+    chain = sum(((2048 + (1 << l) - 1) >> l) ** 2 for l in range(12))
+    ab = bench.algorithmic_bytes(cfg, sc, covered_pixels=4_691_104)        # C2: 1.33 x covered exceeds the chain
+    assert ab["geometry"] == 25921 * 48 + 153600 * 4
+    assert ab["tex"] == chain * 16 and abs(ab["tex"] - 89.5e6) < 0.1e6
+    assert ab["tile"] == 3840 * 2160 * 20 + ab["tex"]
+    assert ab["frame"] == ab["geometry"] + ab["tile"]
+    few = bench.algorithmic_bytes(cfg, sc, covered_pixels=1_000_000)
+    assert few["tex"] == int(1.33 * 1_000_000) * 16
+    assert set(bench.CONFIGS) == {"c2", "c3", "c4", "c5"} and bench.CONFIGS["c3"]["msaa"] == 8
