@@ -2,7 +2,7 @@
 # usage (GPU box): tools/gpu_ab.sh <tag> <cfg> <variantdir>... — times build variants (ifrit-v2_b200/lib_ab/<v>/libifrit_b200.so,
 # built here with `make -C ifrit-v2_b200/csrc OUT=../lib_ab/<v> EXTRA=-D...`) back to back on the same box, twice each
 tag=$1; cfg=$2; shift 2; o=gpurun_out; mkdir -p $o
-for rep in 1 2; do for v in "$@"; do
+for rep in ${REPS:-1 2}; do for v in "$@"; do
   lib=$PWD/ifrit-v2_b200/lib_ab/$v/libifrit_b200.so; [ $v = base ] && lib=$PWD/ifrit-v2_b200/lib/libifrit_b200.so
   IFRIT_B200_LIB=$lib timeout 600 python bench.py --config $cfg --steps 300 --warmup 3 --no-cpu-baseline --extra-configs=$EXTRA_CFG > $o/ab_${tag}_${v}_$rep.json 2> $o/ab_${tag}_${v}_$rep.err
   python - <<PY
