@@ -95,6 +95,10 @@ public:
     void synchronize() { ck(iftrcuSynchronize(h_)); }
     void setTilePartition(int rank, int world) { ck(iftrcuSetTilePartition(h_, rank, world)); }
     void setSampleConvention(int c) { ck(iftrcuSetSampleConvention(h_, c)); }
+    void setFramePipelining(bool on) { ck(iftrcuSetFramePipelining(h_, on)); }
+    // packed RGBA8 presentation image, copied back instead of the RGBA32F one (hostRGBA8: width * height * 4 bytes or null)
+    void bindPresentBuffer(void* hostRGBA8, bool enable = true) { ck(iftrcuBindPresentBuffer(h_, hostRGBA8, enable ? 1 : 0)); }
+    void readPresent(void* dstRGBA8) { ck(iftrcuReadPresent(h_, dstRGBA8)); }
     iftrcuStats stats() { iftrcuStats s; ck(iftrcuGetStats(h_, &s)); return s; }
     iftrcuRenderer* handle() { return h_; }
 
