@@ -132,7 +132,7 @@ def algorithmic_bytes(cfg, sc, covered_pixels):
 
 
 # ------------------------------------------------------------------------------------------------------
-def run_ours(args, cfg_name):
+def run_ours(args, cfg_name, do_e2e=True, fast_sampler=False):
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -147,7 +147,7 @@ def run_ours(args, cfg_name):
         raise SystemExit("bench.py: no CUDA device — the product has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=dev)
     W, H = cfg["W"], cfg["H"]
 
@@ -181,23 +181,28 @@ def run_ours(args, cfg_name):
         color = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
         depth = torch.zeros((H, W), dtype=torch.float32, device=dev)
         r.bindFrameBufferDevice(color, depth, W, H)
-    r.bindVertexBuffer(tvb, tvb.shape[0], tvb.shape[1] // 4, device=True)
-    r.bindIndexBuffer(tib, tib.shape[0], device=True)
-    r.bindVertexShader(sc["vs"], sc["nvary"])
-    r.bindFragmentShader(cfg["fs"])
-    r.CreateBuffer(0, sc["u"].nbytes)
-    r.copyHostBufferToBuffer(sc["u"], 0)
-    if sc["tex"] is not None:
-        s = sc["tex"].shape[0]
-        r.CreateTexture(0, s, s, sc["mips"], 1)
-        r.copyHostBufferToImage(np.ascontiguousarray(sc["tex"][None]), 0, s, s)
-        r.generateMipmap(0, R.IF_FILTER_LINEAR)
-        r.CreateSampler(0, filterMode=R.IF_FILTER_LINEAR, anisotropyEnable=True, maxAnisotropy=16.0)
-    r.setMsaaSamples(cfg["msaa"])
-    r.SetCullMode(cfg["cull"])
-    r.SetDepthFunc(R.IF_COMPARE_OP_LESS)
-    r.SetDepthTestEnable(True)
-    r.setClearValues([(0, 0, 0, 0)], 255.0)   # reference demo clear depth, SG/demo/DefaultDemo.cpp:355
+
+    def configure(rr):
+        rr.bindVertexBuffer(tvb, tvb.shape[0], tvb.shape[1] // 4, device=True)
+        rr.bindIndexBuffer(tib, tib.shape[0], device=True)
+        rr.bindVertexShader(sc["vs"], sc["nvary"])
+        rr.bindFragmentShader(cfg["fs"])
+        rr.CreateBuffer(0, sc["u"].nbytes)
+        rr.copyHostBufferToBuffer(sc["u"], 0)
+        if sc["tex"] is not None:
+            s = sc["tex"].shape[0]
+            rr.CreateTexture(0, s, s, sc["mips"], 1)
+            rr.copyHostBufferToImage(np.ascontiguousarray(sc["tex"][None]), 0, s, s)
+            rr.generateMipmap(0, R.IF_FILTER_LINEAR)
+            rr.CreateSampler(0, filterMode=R.IF_FILTER_LINEAR, anisotropyEnable=True, maxAnisotropy=16.0)
+        rr.setMsaaSamples(cfg["msaa"])
+        rr.SetCullMode(cfg["cull"])
+        rr.SetDepthFunc(R.IF_COMPARE_OP_LESS)
+        rr.SetDepthTestEnable(True)
+        rr.setClearValues([(0, 0, 0, 0)], 255.0)   # reference demo clear depth, SG/demo/DefaultDemo.cpp:355
+        rr.setSamplerHardwareFilter(fast_sampler)   # default: the oracle's arithmetic (software fp32 lerps); opt-in FAST = texture unit
+
+    configure(r)
     sf = MG.SortFirstRenderer(r, dist, dev, mode=mg_mode) if world > 1 else None
 
     def step():
@@ -279,64 +284,89 @@ def run_ours(args, cfg_name):
         r.setProfiling(False)
         r.setFramePipelining(True)
 
-    # ---- e2e: host buffers through the C-ABI, H2D + D2H inside the timed region -----------------------
-    hvb = torch.from_numpy(sc["vb"]).pin_memory() if rank == 0 or world == 1 else torch.empty(tvb.shape, dtype=torch.float32).pin_memory()
-    hib = torch.from_numpy(sc["idx"]).pin_memory() if rank == 0 or world == 1 else torch.empty(tib.shape, dtype=torch.int32).pin_memory()
-    if world > 1 and rank != 0:
-        hvb.copy_(tvb.cpu()); hib.copy_(tib.cpu())
-    hcol = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
-    e2e_steps = max(3, min(args.steps, 20))
-
-    # N = 1: the reference-facing call sequence — the host image is bound with useDoubleBuffer (the reference's
-    # default, TileRasterRendererCuda.h:88), so drawElements() itself copies a frame back on every call: frame k - 1
-    # travels to the host image on a second stream while frame k renders (CU:3899-3909).  N > 1: explicit read-back
-    # of the gathered frame on rank 0.
-    readback = "explicit copy of the gathered frame after the draw (rank 0)"
-    if world == 1:
-        r.bindFrameBuffer(hcol.numpy(), None, W, H, useDoubleBuffer=True)
-        readback = ("double-buffered, reference useDoubleBuffer semantics: every drawElements() copies one full RGBA32F frame "
-                    "(frame k-1) to the pinned host image on a second stream while frame k renders")
-
-    def e2e_step():
-        r.bindVertexBuffer(hvb, hvb.shape[0], hvb.shape[1] // 4)        # H2D (pinned, async)
-        r.bindIndexBuffer(hib, hib.shape[0])                           # H2D
-        r.clear()
-        r.drawElements()
-        if world == 1:
-            r.synchronize()                                            # render stream + copy stream
-            return
-        sf.gather(hold=True)
-        if rank == 0:
-            r.copyColorToHostAsync(hcol.data_ptr())                    # D2H of the step's result (pinned, async)
-        sf.release()         # peer mode: only now may the other ranks overwrite the frame (device-side flag)
-        torch.cuda.current_stream().synchronize()
-
-    def time_e2e():
-        for _ in range(2):
-            e2e_step()
-        barrier()
-        e0.record(stream)
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
-        e1.record(stream)
-        barrier()
-        return max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
-
-    e2e_ms = time_e2e()
-    # the same call sequence with the packed RGBA8 presentation image bound: the per-draw
-    # copy-back carries 4 bytes per pixel instead of 16.  Reported next to `e2e`, never instead of it.
-    e2e8_ms = None
-    if world == 1:
-        hcol8 = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory()
-        r.bindPresentBuffer(hcol8.numpy())
-        e2e8_ms = time_e2e() / e2e_steps
-        r.bindPresentBuffer(None, 0)
+    # ---- N > 1: the gathered frame on rank 0 must equal the single-GPU frame bit for bit --------------------------
+    frame_same = None
     if world > 1:
-        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-    e2e_ms /= e2e_steps
+        step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:
+            got = r.readColor()
+            one = R.TileRasterRendererCuda(local)
+            one.Init()
+            one.bindFrameBuffer(None, None, W, H)
+            configure(one)
+            one.clear()
+            one.drawElements()
+            one.synchronize()
+            frame_same = bool(np.array_equal(got.view(np.uint32), one.readColor().view(np.uint32)))
+            one.close()
+            del got
+        dist.barrier()
+
+    # ---- e2e: host buffers through the C-ABI, H2D + D2H inside the timed region -----------------------
+    e2e_ms = e2e8_ms = None
+    e2e_steps, readback, h2d_bytes = 0, None, 0
+    if do_e2e:
+        hvb = torch.from_numpy(sc["vb"]).pin_memory() if rank == 0 or world == 1 else torch.empty(tvb.shape, dtype=torch.float32).pin_memory()
+        hib = torch.from_numpy(sc["idx"]).pin_memory() if rank == 0 or world == 1 else torch.empty(tib.shape, dtype=torch.int32).pin_memory()
+        if world > 1 and rank != 0:
+            hvb.copy_(tvb.cpu()); hib.copy_(tib.cpu())
+        hcol = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
+        e2e_steps = max(3, min(args.steps, 20))
+
+        # N = 1: the reference-facing call sequence — the host image is bound with useDoubleBuffer (the reference's
+        # default, TileRasterRendererCuda.h:88), so drawElements() itself copies a frame back on every call: frame k - 1
+        # travels to the host image on a second stream while frame k renders (CU:3899-3909).  N > 1: explicit read-back
+        # of the gathered frame on rank 0.
+        readback = "explicit copy of the gathered frame after the draw (rank 0)"
+        if world == 1:
+            r.bindFrameBuffer(hcol.numpy(), None, W, H, useDoubleBuffer=True)
+            readback = ("double-buffered, reference useDoubleBuffer semantics: every drawElements() copies one full RGBA32F frame "
+                        "(frame k-1) to the pinned host image on a second stream while frame k renders")
+
+        def e2e_step():
+            r.bindVertexBuffer(hvb, hvb.shape[0], hvb.shape[1] // 4)        # H2D (pinned, async)
+            r.bindIndexBuffer(hib, hib.shape[0])                           # H2D
+            r.clear()
+            r.drawElements()
+            if world == 1:
+                r.synchronize()                                            # render stream + copy stream
+                return
+            sf.gather(hold=True)
+            if rank == 0:
+                r.copyColorToHostAsync(hcol.data_ptr())                    # D2H of the step's result (pinned, async)
+            sf.release()         # peer mode: only now may the other ranks overwrite the frame (device-side flag)
+            torch.cuda.current_stream().synchronize()
+
+        def time_e2e():
+            for _ in range(2):
+                e2e_step()
+            barrier()
+            e0.record(stream)
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                e2e_step()
+            e1.record(stream)
+            barrier()
+            return max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+
+        e2e_ms = time_e2e()
+        # the same call sequence with the packed RGBA8 presentation image bound: the per-draw
+        # copy-back carries 4 bytes per pixel instead of 16.  Reported next to `e2e`, never instead of it.
+        e2e8_ms = None
+        if world == 1:
+            hcol8 = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory()
+            r.bindPresentBuffer(hcol8.numpy())
+            e2e8_ms = time_e2e() / e2e_steps
+            r.bindPresentBuffer(None, 0)
+        if world > 1:
+            t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t.item())
+        e2e_ms /= e2e_steps
+        h2d_bytes = int(hvb.numel() * 4 + hib.numel() * 4)
+        del hvb, hib, hcol
 
     out = None
     if rank == 0:
@@ -347,7 +377,7 @@ def run_ours(args, cfg_name):
         achieved = ab["tile"] / world / (tile_ms * 1e-3) / 1e9 if tile_ms > 0 else 0.0
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
+        if os.path.exists(tp) and world == 1:   # dram bytes of one launch from the committed ncu --set full capture (1 GPU only)
             try:
                 traffic = json.load(open(tp)).get(cfg_name)
             except Exception:
@@ -360,6 +390,8 @@ def run_ours(args, cfg_name):
             "config": {"workload": cfg["workload"], "name": cfg_name, "triangles": ntri, "resolution": [W, H],
                        "msaa": cfg["msaa"], "l2": "no explicit flush: per-step working set (framebuffer "
                        f"{W * H * 20 / 1e6:.0f} MB + texture) exceeds the 126 MB L2",
+                       "sampler": ("FAST (opt-in): texture-unit bilinear blend, 8-bit weights, SFU lod math" if fast_sampler else
+                                   "default: software fp32 lerps, the oracle's arithmetic op for op") if sc["tex"] is not None else "none",
                        "parallelism": f"sort-first x{world} ({mg_mode})" if world > 1 else "1 GPU"},
             "fps": 1e3 / ms_step, "gfrags_per_s": frags / (ms_step * 1e-3) / 1e9,
             "frame_latency_ms": lat_ms,
@@ -375,19 +407,23 @@ def run_ours(args, cfg_name):
                          "frac_unpipelined": (ab["tile"] / world / (ktimes_alone["tile"] * 1e-3) / 1e9 / peak) if ktimes_alone and ktimes_alone["tile"] > 0 else None},
             "frame_roofline": {"algorithmic_bytes": ab["frame"], "achieved": ab["frame"] / (ms_step * 1e-3) / 1e9,
                                "frac": ab["frame"] / (ms_step * 1e-3) / 1e9 / peak},
-            "e2e": {"value": ntri / (e2e_ms * 1e-3) / 1e6, "unit": "Mtris/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int(hvb.numel() * 4 + hib.numel() * 4),
-                    "d2h_bytes_per_step": int(W * H * 16), "steps": e2e_steps, "readback": readback},
             "clocks": clocks,
         }
+        if e2e_ms:
+            out["e2e"] = {"value": ntri / (e2e_ms * 1e-3) / 1e6, "unit": "Mtris/s", "ms_per_step": e2e_ms,
+                          "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(W * H * 16), "steps": e2e_steps,
+                          "readback": readback}
+        if world > 1:
+            out["frame_hash_equals_1gpu"] = frame_same
         if e2e8_ms:
             out["e2e_rgba8"] = {"value": ntri / (e2e8_ms * 1e-3) / 1e6, "unit": "Mtris/s", "ms_per_step": e2e8_ms,
-                                "h2d_bytes_per_step": int(hvb.numel() * 4 + hib.numel() * 4), "d2h_bytes_per_step": int(W * H * 4),
+                                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(W * H * 4),
                                 "note": "same steps with iftrcuBindPresentBuffer(RGBA8): packed presentation image copied back instead of RGBA32F"}
     r.close()
+    del tvb, tib
+    torch.cuda.empty_cache()
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
     return out
 
 
@@ -431,13 +467,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default=None, choices=sorted(CONFIGS))
-    ap.add_argument("--extra-configs", default="c3", help="comma list of further configs measured at N=1 (short runs)")
+    ap.add_argument("--extra-configs", default=None, help="comma list of further configs in the same line (short runs); default c2,c4,c5 at N=1, c5 at N>1")
+    ap.add_argument("--no-fast-sampler", action="store_true", help="skip the extra run with the opt-in FAST sampler")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mgpu", default="peer", choices=["peer", "nccl"],
                     help="N > 1: peer = tiles stored straight into rank 0's framebuffer over NVLink; nccl = pack + gather + unpack")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
-    cfg_name = args.config or "c2"
+    cfg_name = args.config or "c3"   # the configuration BASELINE.json quotes the roofline target on (4K, 8x MSAA, textured)
 
     if args.impl == "reference":
         if rank != 0:
@@ -460,23 +497,44 @@ def main():
             "gpu_launches": 0}))
         return
 
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     out = run_ours(args, cfg_name)
+    # Further configurations in the same line (short runs): N = 1: the other single-GPU BASELINE configs and C5;
+    # N > 1: C5, the configuration BASELINE.json quotes the multi-GPU partition on — every rank takes part.
+    default_extras = "c2,c4,c5" if world == 1 else "c5"
+    extra_names = [c for c in (default_extras if args.extra_configs is None else args.extra_configs).split(",") if c and c != cfg_name]
+    extras = {}
+    keys = ("value", "ms_per_step", "frame_latency_ms", "fps", "gfrags_per_s", "kernel_ms", "kernel_ms_unpipelined", "roofline",
+            "frame_roofline", "e2e", "gpu_launches", "n_gpus", "frame_hash_equals_1gpu")
+    for name in extra_names:
+        sub = argparse.Namespace(**vars(args))
+        sub.steps, sub.warmup = max(5, min(args.steps, 20)), 3
+        try:
+            o = run_ours(sub, name, do_e2e=(world == 1 and name in ("c2", "c3")))
+            if rank == 0:
+                extras[name] = {k: o[k] for k in keys if k in o}
+                extras[name]["workload"] = o["config"]["workload"]
+        except Exception as ex:   # an extra config must never take the headline down
+            extras[name] = {"error": repr(ex)}
+    if world == 1 and CONFIGS[cfg_name]["fs"] == "textured" and not args.no_fast_sampler:
+        sub = argparse.Namespace(**vars(args))
+        sub.steps, sub.warmup = max(5, min(args.steps, 100)), 3
+        try:
+            o = run_ours(sub, cfg_name, do_e2e=False, fast_sampler=True)
+            out["fast_sampler"] = {"ms_per_step": o["ms_per_step"], "value": o["value"], "kernel_ms": o["kernel_ms"],
+                                   "roofline_frac": o["roofline"]["frac"],
+                                   "note": "same workload with iftrcuSetSamplerHardwareFilter(1) (opt-in, see include/ifrit_b200.h); not the headline"}
+        except Exception as ex:
+            out["fast_sampler"] = {"error": repr(ex)}
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world == 1:
-        extras = {}
-        for name in [c for c in args.extra_configs.split(",") if c and c != cfg_name]:
-            sub = argparse.Namespace(**vars(args))
-            sub.steps, sub.warmup = max(5, min(args.steps, 20)), 3
-            try:
-                o = run_ours(sub, name)
-                extras[name] = {k: o[k] for k in ("value", "ms_per_step", "frame_latency_ms", "fps", "gfrags_per_s", "kernel_ms", "kernel_ms_unpipelined", "roofline",
-                                                  "frame_roofline", "e2e", "gpu_launches")}
-                extras[name]["workload"] = o["config"]["workload"]
-            except Exception as ex:   # an extra config must never take the headline down
-                extras[name] = {"error": repr(ex)}
+    if extras:
         out["extra_configs"] = extras
+    if world == 1:
         if not args.no_cpu_baseline:
             try:
                 res = run_reference(args, cfg_name, steps=10, warmup=2)

@@ -76,8 +76,8 @@ struct iftrcuRenderer {
     const uint8_t* dVB = nullptr; DevBuf ownVB; int nverts = 0, stride = 0, nattr = 0; int attrOff[IFR_MAX_VARY + 1] = {0};
     const int32_t* dIB = nullptr; DevBuf ownIB; int icount = 0;
     int vsId = -1, fsId = -1, nvary = 0;
-    bool fusedVS = true;
-    bool hwFilter = true;  // bilinear footprints through the TEX unit (iftrcuSetSamplerHardwareFilter)   // vertex stage fused into triangle setup (default) or stand-alone vs_kernel
+    bool fusedVS = true;   // vertex stage fused into triangle setup (default) or stand-alone vs_kernel
+    bool hwFilter = false; // opt-in (iftrcuSetSamplerHardwareFilter): bilinear footprints through the TEX unit, 8-bit weights, SFU forms
 
     // state (defaults: TileRasterRendererCuda.h:42-47, CU:186-189)
     int msaa = 1, depthFunc = IF_COMPARE_OP_LESS, depthTest = 1, cullMode = IF_CULL_MODE_NONE;
@@ -262,8 +262,12 @@ static int ensure_pipeline(iftrcuRenderer* r) {
 }
 
 // inputs of the geometry stage (vertex / index / uniform buffers) were touched on the draw stream
+// The (triangle, tile) pair count is a function of these inputs, so the queue capacity verified for the previous
+// contents proves nothing any more: the next draw sizes the queues again (one wait on the geometry stream after the
+// scan, while the previous frame's tile kernel keeps the GPU busy) instead of risking a silently dropped draw.
 static void mark_inputs(iftrcuRenderer* r) {
     if (r->evInputs && cudaEventRecord(r->evInputs, r->stream) == cudaSuccess) r->inputsDirty = true;
+    r->scr[0].queueChecked = r->scr[1].queueChecked = false;
 }
 
 // One draw = geometry stage (memsets, setup + count, scan, fill) + tile kernel.  With frame pipelining (default) the
@@ -445,10 +449,11 @@ int iftrcuDestroyInstance(iftrcuRenderer* h) {
     R_CHECK(h);
     cudaStreamSynchronize(r->stream);
     if (r->registeredHost) cudaHostUnregister(r->registeredHost);
+    if (r->registeredPresent) cudaHostUnregister(r->registeredPresent);
     close_peer(r);
     if (r->copyStream) { cudaStreamSynchronize(r->copyStream); cudaStreamDestroy(r->copyStream); }
     for (int i = 0; i < 2; i++) { if (r->evFrame[i]) cudaEventDestroy(r->evFrame[i]); if (r->evCopy[i]) cudaEventDestroy(r->evCopy[i]); }
-    DevBuf* bufs[] = {&r->ownColor, &r->ownColor2, &r->ownDepth, &r->primIds, &r->ownVB, &r->ownIB};
+    DevBuf* bufs[] = {&r->ownColor, &r->ownColor2, &r->ownDepth, &r->primIds, &r->ownVB, &r->ownIB, &r->presentBuf[0], &r->presentBuf[1]};
     for (int k = 0; k < 2; k++) {
         iftrcuRenderer::Scratch& c = r->scr[k];
         DevBuf* sb[] = {&c.scanPartial, &c.pos, &c.vary, &c.rec, &c.clipBary, &c.tileBox, &c.fan1List, &c.heavyBits, &c.tileCount, &c.tileStart,
@@ -507,6 +512,11 @@ static int update_double_buffer(iftrcuRenderer* r) {
     r->framePending[0] = r->framePending[1] = r->copyPending[0] = r->copyPending[1] = false;
     r->dColor = (float4*)r->ownColor.p;
     return IFRIT_OK;
+}
+
+static void drop_present(iftrcuRenderer* r) {
+    if (r->registeredPresent) { cudaHostUnregister(r->registeredPresent); r->registeredPresent = nullptr; }
+    r->presentFormat = 0; r->hPresent = nullptr;
 }
 
 static void reset_double_buffer(iftrcuRenderer* r) {
@@ -601,7 +611,8 @@ int iftrcuBindPeerFrameBuffer(iftrcuRenderer* h, const void* handle128, int widt
     CUDA_TRY(cudaStreamSynchronize(r->stream));
     close_peer(r);
     reset_double_buffer(r);
-    r->presentFormat = 0; r->hPresent = nullptr; r->wantDouble = false;
+    drop_present(r);
+    r->wantDouble = false;
     cudaIpcMemHandle_t hc, hd;
     memcpy(&hc, handle128, 64); memcpy(&hd, (const char*)handle128 + 64, 64);
     CUDA_TRY(cudaIpcOpenMemHandle(&r->peerColor, hc, cudaIpcMemLazyEnablePeerAccess));
@@ -624,7 +635,8 @@ int iftrcuBindFrameBufferDevice(iftrcuRenderer* h, float* devColor, float* devDe
     CUDA_TRY(cudaStreamSynchronize(r->stream));
     close_peer(r);
     reset_double_buffer(r);
-    r->presentFormat = 0; r->hPresent = nullptr; r->wantDouble = false;
+    drop_present(r);
+    r->wantDouble = false;
     if (r->registeredHost) { cudaHostUnregister(r->registeredHost); r->registeredHost = nullptr; }
     r->dColor = (float4*)devColor; r->dDepth = devDepth; r->externalFB = true; r->hColor = nullptr; r->hDepth = nullptr;
     r->frameFlags = nullptr; r->fencePending = false;
@@ -758,6 +770,15 @@ int iftrcuBlitImage(iftrcuRenderer* h, int srcSlot, int dstSlot, const IfritImag
         return r->fail(IFRIT_ERR_INVALID, "blitImage", "mip level out of range");
     const uint32_t sr[4] = {b->srcExtentSt.width, b->srcExtentSt.height, b->srcExtentEd.width, b->srcExtentEd.height};
     const uint32_t dr[4] = {b->dstExtentSt.width, b->dstExtentSt.height, b->dstExtentEd.width, b->dstExtentEd.height};
+    {
+        const TexDesc& st = r->tex[srcSlot]; const TexDesc& dt = r->tex[dstSlot];
+        const TexLevel& sl = st.lvl[b->srcSubresource.mipLevel]; const TexLevel& dl = dt.lvl[b->dstSubresource.mipLevel];
+        if ((int)b->srcSubresource.baseArrayLayer >= st.layers || (int)b->dstSubresource.baseArrayLayer >= dt.layers)
+            return r->fail(IFRIT_ERR_INVALID, "blitImage", "array layer out of range");
+        if (sr[0] >= sr[2] || sr[1] >= sr[3] || dr[0] >= dr[2] || dr[1] >= dr[3] || sr[2] > (uint32_t)sl.w || sr[3] > (uint32_t)sl.h ||
+            dr[2] > (uint32_t)dl.w || dr[3] > (uint32_t)dl.h)
+            return r->fail(IFRIT_ERR_INVALID, "blitImage", "rectangle empty or outside the mip level");
+    }
     CUDA_TRY(ifr_launch_blit(r->tex[srcSlot], b->srcSubresource.mipLevel, b->srcSubresource.baseArrayLayer, r->tex[dstSlot],
                              b->dstSubresource.mipLevel, b->dstSubresource.baseArrayLayer, sr, dr, filter, r->stream));
     r->stats.kernel_launches += 1;
@@ -931,9 +952,12 @@ int iftrcuDrawElements(iftrcuRenderer* h) {
                          : (r->fsId == IFRIT_FS_TEXTURED || r->fsId == IFRIT_FS_TEXTURED_LOD0 || r->fsId == IFRIT_FS_DERIV_VIS) ? 2 : 1;
         if (r->nvary < need) return r->fail(IFRIT_ERR_STATE, "drawElements", "fragment shader needs more varyings than the vertex shader outputs");
     }
+    if (r->fsId == IFRIT_FS_SKYBOX && r->tex[0].layers < 6) return r->fail(IFRIT_ERR_STATE, "drawElements", "the skybox shader samples a cube: texture slot 0 needs 6 layers");
+    if ((r->fsId == IFRIT_FS_TEXTURED || r->fsId == IFRIT_FS_TEXTURED_LOD0 || r->fsId == IFRIT_FS_SKYBOX || r->fsId == IFRIT_FS_DERIV_VIS) && r->bufSize[0] < 88)
+        return r->fail(IFRIT_ERR_STATE, "drawElements", "buffer slot 0 must hold the 88-byte uniform block (MVP, light, lod bias, derivative scale)");
+    if (r->vsId == IFRIT_VS_MVP && r->bufSize[0] < 64) return r->fail(IFRIT_ERR_STATE, "drawElements", "buffer slot 0 must hold the 64-byte MVP");
     if (r->blendEnable && r->msaa != 1) return r->fail(IFRIT_ERR_UNSUPPORTED, "drawElements", "alpha blending is 1x only (the reference's blend kernel has no sample loop, CU:1649)");
     if (r->fsId == IFRIT_FS_DERIV_VIS && !r->bufMem[0].p) return r->fail(IFRIT_ERR_STATE, "drawElements", "buffer slot 0 (uniform block) not created");
-    if (r->haveDraw && !r->scr[r->pipelining ? 1 - r->set : 0].queueChecked) { int rc = sync_and_check(r); if (rc) return rc; }
     return issue_draw(r, false);
 }
 

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(256) blit_kernel(const BlitArgs a) {
     const float sx = fmaf(px, (float)(a.sx1 - a.sx0), (float)a.sx0), sy = fmaf(py, (float)(a.sy1 - a.sy0), (float)a.sy0);
     float4 out;
     if (a.filter == IF_FILTER_LINEAR) {
-        const int ix = (int)sx, iy = (int)sy;
+        const int ix = min(max((int)sx, 0), a.srcW - 1), iy = min(max((int)sy, 0), a.srcH - 1);   // in range for validated rectangles
         const float fx = sx - (float)ix, fy = sy - (float)iy;
         const int ix1 = min(ix + 1, a.srcW - 1), iy1 = min(iy + 1, a.srcH - 1);
         const float4 c00 = __ldg(a.src + (size_t)iy * a.srcW + ix), c01 = __ldg(a.src + (size_t)iy * a.srcW + ix1);
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(256) blit_kernel(const BlitArgs a) {
         out = make_float4(fmaf(p1.x - p0.x, fy, p0.x), fmaf(p1.y - p0.y, fy, p0.y), fmaf(p1.z - p0.z, fy, p0.z),
                           fmaf(p1.w - p0.w, fy, p0.w));
     } else {
-        const int ix = min((int)roundf(sx), a.srcW - 1), iy = min((int)roundf(sy), a.srcH - 1);
+        const int ix = min(max((int)roundf(sx), 0), a.srcW - 1), iy = min(max((int)roundf(sy), 0), a.srcH - 1);
         out = __ldg(a.src + (size_t)iy * a.srcW + ix);
     }
     a.dst[(size_t)(y + a.dy0) * a.dstW + (x + a.dx0)] = out;

@@ -213,9 +213,12 @@ IFRIT_B200_API int iftrcuSetDebugPrimitiveIds(iftrcuRenderer* h, int enable);
 /* vertex stage fused into triangle setup (default, 1) or run as the stand-alone kernel that mirrors
  * vertexProcessingKernel CU:330 (0); both produce identical frames */
 IFRIT_B200_API int iftrcuSetVertexStageFused(iftrcuRenderer* h, int enable);
-/* LINEAR-filter 2x2 footprints through the texture unit (default, 1): same texels and weights as
- * textureImplLegacy (ShaderBuiltinCuda.cuh:106-182) but blended by the hardware with 8-bit weights — colour
- * within 1/255; 0 = four loads + fp32 lerps in software, bit-identical to the CPU oracle */
+/* Sampler precision contract.  DEFAULT (0): four loads + fp32 lerps in software, the reference's arithmetic op for op
+ * (textureImplLegacy / Lod / AnisotropicFilter, ShaderBuiltinCuda.cuh:106-272) — bit-identical to the CPU oracle up to
+ * the last ulp of log2f, for texels of any range.  OPT-IN (1), "FAST": LINEAR 2x2 footprints are fetched and blended by
+ * the texture unit (same texels, weights quantised to 8 bits) and sqrt / divide / log2 of the LOD and lighting math
+ * use the SFU approximations.  Error <= ~2^-9 x (texel range): within 1/255 per channel for textures in [0, 1], NOT
+ * for HDR-range texels (tests/test_gpu_parity.py::test_fast_sampler_precision_contract). */
 IFRIT_B200_API int iftrcuSetSamplerHardwareFilter(iftrcuRenderer* h, int enable);
 
 /* ---- draw ----------------------------------------------------------------------------- */

@@ -9,8 +9,11 @@
  * Build: see oracle/Makefile (-ffp-contract=off: every fused multiply-add in
  * this file is an explicit fmaf(), so the float op sequence is the spec).
  */
+#define _GNU_SOURCE
 #include "ifrit_oracle.h"
 #include <math.h>
+#include <pthread.h>
+#include <unistd.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -376,6 +379,27 @@ void orc_texture_cube_lod(const orc_texture* t, const orc_sampler* s, float x, f
     sample_cube(t, s, x, y, z, lod, out);
 }
 
+/* Batch form of the sampler entry points, same `kind` / argument layout as oracle/ref_sampler_shim.cu
+ * (the reference's own ShaderBuiltinCuda.cuh compiled for the host): 0 = one integer level (a[0] = lod, a[1] = layer),
+ * 1 = trilinear (a[0] = lod), 2 = adaptive lod (dx = a[0..1], dy = a[2..3], bias = a[4]), 3 = anisotropic
+ * (du = a[0..1], dv = a[2..3], bias = a[4]; max anisotropy from the sampler), 4 = cube (x, y = uv, z = a[1], lod = a[0]). */
+int orc_sample_batch(int kind, const orc_texture* t, const orc_sampler* s, int n, const float* uv, const float* args, float* out) {
+    for (int i = 0; i < n; i++) {
+        const float* a = args + 6 * (size_t)i;
+        const float u = uv[2 * (size_t)i], v = uv[2 * (size_t)i + 1];
+        float* o = out + 4 * (size_t)i;
+        switch (kind) {
+            case 0: sample_level(t, s, (int)a[1], u, v, 0, 0, (int)a[0], o); break;
+            case 1: sample_trilinear(t, s, 0, u, v, 0, 0, a[0], o); break;
+            case 2: sample_adaptive(t, s, u, v, a, a + 2, a[4], o); break;
+            case 3: sample_aniso(t, s, u, v, a, a + 2, a[4], o); break;
+            case 4: sample_cube(t, s, u, v, a[1], a[0], o); break;
+            default: return -1;
+        }
+    }
+    return 0;
+}
+
 int64_t orc_texture_total_texels(int w, int h, int mip_levels, int layers) {
     int64_t n = 0;
     for (int i = 0; i <= mip_levels; i++) {
@@ -689,34 +713,30 @@ static int render_blend(const orc_state* st, const orc_f4* vary, int nvary, cons
     return 0;
 }
 
-int orc_render(const orc_state* st, const orc_f4* pos, const orc_f4* vary, int nvary,
-               const int32_t* idx, int ntri, int fs_id, const void* uniforms,
-               const orc_texture* textures, const orc_sampler* samplers,
-               float* color, float* depth, int32_t* prim_id, int64_t* stats) {
+/* one horizontal band of the frame (rows y_begin .. y_end - 1, whole quad rows): coverage + visibility keys, then
+ * quad shading + resolve.  Bands touch disjoint pixels, so the threads share nothing they write. */
+typedef struct {
+    const orc_state* st; const orc_f4* vary; int nvary; const int32_t* idx; const orc_tri* tris; int ntris;
+    const int32_t* by_slot; int fs_id; const void* uniforms; const orc_texture* textures; const orc_sampler* samplers;
+    float* color; float* depth; int32_t* prim_id; uint64_t* keys; int y_begin, y_end; int64_t covered, frags;
+} band_job;
+
+static int orc_thread_count(void) {
+    const char* e = getenv("ORC_THREADS");
+    if (e && atoi(e) > 0) return atoi(e);
+    long n = sysconf(_SC_NPROCESSORS_ONLN);
+    return n < 1 ? 1 : (n > 32 ? 32 : (int)n);
+}
+
+static void* band_worker(void* arg) {
+    band_job* j = (band_job*)arg;
+    const orc_state* st = j->st;
     const int W = st->width, H = st->height, S = st->msaa, func = st->depth_func;
-    if (nvary > MAXV || S > MAXS) return -1;
-    if (func == ORC_CMP_NOT_EQUAL && !st->blend_enable) return -2;
-    orc_tri* tris = (orc_tri*)malloc(sizeof(orc_tri) * 2 * (size_t)(ntri > 0 ? ntri : 1));
-    const int ntris = orc_assemble(st, pos, idx, ntri, tris);
-    /* slot -> assembled triangle */
-    int32_t* by_slot = (int32_t*)malloc(sizeof(int32_t) * 2 * (size_t)(ntri > 0 ? ntri : 1));
-    for (int i = 0; i < 2 * ntri; i++) by_slot[i] = -1;
-    for (int i = 0; i < ntris; i++) by_slot[tris[i].slot] = i;
-
-    if (st->do_clear) orc_clear(st, color, depth);
-
-    if (st->blend_enable) {
-        if (S != 1) { free(by_slot); free(tris); return -3; }
-        fs_env benv = {(const float*)uniforms, textures, samplers};
-        const int rc = render_blend(st, vary, nvary, idx, tris, ntris, fs_id, &benv, color, depth, prim_id, stats);
-        free(by_slot); free(tris);
-        return rc;
-    }
-
-    uint64_t* keys = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)W * H * S);
-    for (size_t p = 0; p < (size_t)W * H; p++)
-        for (int s = 0; s < S; s++) keys[p * S + s] = key_init(func, depth[p]);
-
+    const orc_f4* vary = j->vary; const int nvary = j->nvary; const int32_t* idx = j->idx;
+    const orc_tri* tris = j->tris; const int ntris = j->ntris; const int32_t* by_slot = j->by_slot;
+    const int fs_id = j->fs_id; const void* uniforms = j->uniforms;
+    const orc_texture* textures = j->textures; const orc_sampler* samplers = j->samplers;
+    float* color = j->color; float* depth = j->depth; int32_t* prim_id = j->prim_id; uint64_t* keys = j->keys;
     int64_t covered = 0, frags = 0;
     for (int i = 0; i < ntris; i++) {
         const orc_tri* r = &tris[i];
@@ -733,6 +753,8 @@ int orc_render(const orc_state* st, const orc_f4* pos, const orc_f4* vary, int n
         if (y0 < 0) y0 = 0;
         if (x1 > W - 1) x1 = W - 1;
         if (y1 > H - 1) y1 = H - 1;
+        if (y0 < j->y_begin) y0 = j->y_begin;
+        if (y1 > j->y_end - 1) y1 = j->y_end - 1;
         for (int y = y0; y <= y1; y++)
             for (int x = x0; x <= x1; x++) {
                 int mask = 0;
@@ -762,7 +784,7 @@ int orc_render(const orc_state* st, const orc_f4* pos, const orc_f4* vary, int n
     /* shading: 2x2 quads, one FS invocation per (pixel, distinct visible triangle);
      * every lane of the quad interpolates so that ddx/ddy exist (CU:2264-2310, SB:36-76) */
     fs_env env = {(const float*)uniforms, textures, samplers};
-    for (int qy = 0; qy < H; qy += 2)
+    for (int qy = j->y_begin; qy < j->y_end; qy += 2)
         for (int qx = 0; qx < W; qx += 2) {
             uint32_t slots[4 * MAXS];
             int nslots = 0;
@@ -851,6 +873,64 @@ int orc_render(const orc_state* st, const orc_f4* pos, const orc_f4* vary, int n
                 depth[p] = da / (float)S;
             }
         }
+    j->covered = covered; j->frags = frags;
+    return NULL;
+}
+
+int orc_render(const orc_state* st, const orc_f4* pos, const orc_f4* vary, int nvary,
+               const int32_t* idx, int ntri, int fs_id, const void* uniforms,
+               const orc_texture* textures, const orc_sampler* samplers,
+               float* color, float* depth, int32_t* prim_id, int64_t* stats) {
+    const int W = st->width, H = st->height, S = st->msaa, func = st->depth_func;
+    if (nvary > MAXV || S > MAXS) return -1;
+    if (func == ORC_CMP_NOT_EQUAL && !st->blend_enable) return -2;
+    orc_tri* tris = (orc_tri*)malloc(sizeof(orc_tri) * 2 * (size_t)(ntri > 0 ? ntri : 1));
+    const int ntris = orc_assemble(st, pos, idx, ntri, tris);
+    /* slot -> assembled triangle */
+    int32_t* by_slot = (int32_t*)malloc(sizeof(int32_t) * 2 * (size_t)(ntri > 0 ? ntri : 1));
+    for (int i = 0; i < 2 * ntri; i++) by_slot[i] = -1;
+    for (int i = 0; i < ntris; i++) by_slot[tris[i].slot] = i;
+
+    if (st->do_clear) orc_clear(st, color, depth);
+
+    if (st->blend_enable) {
+        if (S != 1) { free(by_slot); free(tris); return -3; }
+        fs_env benv = {(const float*)uniforms, textures, samplers};
+        const int rc = render_blend(st, vary, nvary, idx, tris, ntris, fs_id, &benv, color, depth, prim_id, stats);
+        free(by_slot); free(tris);
+        return rc;
+    }
+
+    uint64_t* keys = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)W * H * S);
+    for (size_t p = 0; p < (size_t)W * H; p++)
+        for (int s = 0; s < S; s++) keys[p * S + s] = key_init(func, depth[p]);
+
+    /* The frame is cut into horizontal bands of whole quad rows, one thread per band: every thread walks all
+     * triangles but only the rows of its band, so the per-sample minimum and the per-quad shading are computed by
+     * exactly the loops below whatever the thread count (results do not depend on it). */
+    int nthreads = orc_thread_count();
+    if (nthreads > (H + 1) / 2) nthreads = (H + 1) / 2;
+    if (nthreads < 1) nthreads = 1;
+    band_job* jobs = (band_job*)calloc((size_t)nthreads, sizeof(band_job));
+    pthread_t* th = (pthread_t*)calloc((size_t)nthreads, sizeof(pthread_t));
+    const int qrows = (H + 1) / 2;
+    for (int t = 0; t < nthreads; t++) {
+        band_job* j = &jobs[t];
+        j->st = st; j->vary = vary; j->nvary = nvary; j->idx = idx; j->tris = tris; j->ntris = ntris; j->by_slot = by_slot;
+        j->fs_id = fs_id; j->uniforms = uniforms; j->textures = textures; j->samplers = samplers;
+        j->color = color; j->depth = depth; j->prim_id = prim_id; j->keys = keys;
+        j->y_begin = 2 * (int)((int64_t)qrows * t / nthreads);
+        j->y_end = 2 * (int)((int64_t)qrows * (t + 1) / nthreads);
+        if (j->y_end > H) j->y_end = H;
+    }
+    for (int t = 1; t < nthreads; t++) pthread_create(&th[t], NULL, band_worker, &jobs[t]);
+    band_worker(&jobs[0]);
+    int64_t covered = 0, frags = 0;
+    for (int t = 0; t < nthreads; t++) {
+        if (t) pthread_join(th[t], NULL);
+        covered += jobs[t].covered; frags += jobs[t].frags;
+    }
+    free(jobs); free(th);
     if (stats) { stats[0] = frags; stats[1] = covered; stats[2] = ntris; }
     free(keys); free(by_slot); free(tris);
     return 0;

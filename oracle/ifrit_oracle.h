@@ -106,6 +106,9 @@ void orc_texture_grad(const orc_texture* t, const orc_sampler* s, float u, float
 void orc_texture_cube_lod(const orc_texture* t, const orc_sampler* s, float x, float y, float z,
                           float lod, float out[4]);
 
+/* batch sampler entry point (see ifrit_oracle.c); mirrors oracle/ref_sampler_shim.cu */
+int orc_sample_batch(int kind, const orc_texture* t, const orc_sampler* s, int n, const float* uv, const float* args, float* out);
+
 /* --- shader functions handed to the UNMODIFIED reference CPU renderer through
  * iftrBind{Vertex,Fragment}ShaderFunc (TileRasterRendererExport.h:45-51).  They
  * read the globals set by orc_ref_set_uniforms / orc_ref_set_texture. */

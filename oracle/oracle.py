@@ -162,3 +162,38 @@ def render(st, pos, vary, idx, fs_id, uniforms, textures=None, samplers=None, co
 def draw(st, vb, idx, vs_id, fs_id, nvary, uniforms, **kw):
     pos, vary = vertex_stage(vs_id, uniforms, vb, nvary)
     return render(st, pos, vary, idx, fs_id, uniforms, **kw)
+
+
+# ---- sampler batch entry points (oracle restatement and, when built, the reference's own source) --------------
+_REFSB = None
+
+
+def ref_sampler_available():
+    return os.path.exists(os.path.join(_HERE, "_ref", "libifrit_ref_sampler.so"))
+
+
+def sample_batch(kind, chain, w, h, mips, layers, sampler, uv, args, reference=False):
+    """kind / args layout: see orc_sample_batch (ifrit_oracle.c) and oracle/ref_sampler_shim.cu.
+    sampler: dict(filter, addr_u, addr_v, border, aniso, max_aniso).  reference=True runs the reference's
+    ShaderBuiltinCuda.cuh (host instantiation, oracle/_ref/libifrit_ref_sampler.so) instead of the restatement."""
+    global _REFSB
+    uv = np.ascontiguousarray(uv, np.float32)
+    args = np.ascontiguousarray(args, np.float32)
+    n = uv.shape[0]
+    assert args.shape == (n, 6) and uv.shape == (n, 2)
+    out = np.zeros((n, 4), np.float32)
+    chain = np.ascontiguousarray(chain, np.float32)
+    if reference:
+        if _REFSB is None:
+            _REFSB = C.CDLL(os.path.join(_HERE, "_ref", "libifrit_ref_sampler.so"))
+        s4 = np.array([sampler.get("filter", 1), sampler.get("addr_u", 0), sampler.get("addr_v", 0), sampler.get("border", 0)], np.int32)
+        if kind == 3:
+            args = args.copy(); args[:, 5] = sampler.get("max_aniso", 1.0)
+        rc = _REFSB.refsb_sample(kind, _p(s4), _p(chain), w, h, layers, n, _p(uv), _p(args), _p(out))
+    else:
+        t = make_texture(chain, w, h, mips, layers)
+        s = make_sampler(filter=sampler.get("filter", 1), addr_u=sampler.get("addr_u", 0), addr_v=sampler.get("addr_v", 0),
+                         border=sampler.get("border", 0), aniso=sampler.get("aniso", False), max_aniso=sampler.get("max_aniso", 1.0))
+        rc = lib().orc_sample_batch(kind, C.byref(t), C.byref(s), n, _p(uv), _p(args), _p(out))
+    assert rc == 0, rc
+    return out

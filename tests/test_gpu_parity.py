@@ -338,7 +338,7 @@ def test_derivatives_quad(r):
 @pytest.mark.parametrize("aniso", [False, True])
 @pytest.mark.parametrize("addr", [0, 1, 2, 3, 4])
 def test_textured_mesh(r, aniso, addr, hw):
-    """hw = False: four loads + fp32 lerps (the oracle's arithmetic); hw = True (default): the same 2x2 footprint
+    """hw = False (default): four loads + fp32 lerps (the oracle's arithmetic); hw = True (opt-in FAST): the same 2x2 footprint
     blended by the texture unit with 8-bit weights.  Both must meet the 1/255 on >= 99.9 % bar."""
     W, H = 384, 216
     vb, idx, u = _mesh_case(W, H)
@@ -499,3 +499,138 @@ def test_multi_gpu_frame_is_bit_identical():
                           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(here, "mgpu_check.py")],
                          capture_output=True, text=True, timeout=600)
     assert "MGPU_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+# ---- BASELINE.json configurations at FULL size, against the oracle -------------------------------------------------
+def _bench_scene(name):
+    import bench
+    cfg = bench.CONFIGS[name]
+    return cfg, bench.build_scene(cfg)
+
+
+@pytest.mark.parametrize("fast", [False, True])
+@pytest.mark.parametrize("name", ["c2", "c3"])
+def test_full_size_c2_c3_vs_oracle(r, name, fast):
+    """C2 / C3 exactly as bench.py builds them (mesh50k, 3840x2160, 2048^2 RGBA32F texture with 11 mips, aniso 16;
+    C3: 8x MSAA + BACK cull): primitive ids per sample and depth bit-exact, colour within 1/255 on >= 99.9 % of the
+    pixels, for the default sampler and for the opt-in FAST (texture-unit) sampler; FS invocation counts equal."""
+    cfg, sc = _bench_scene(name)
+    W, H = cfg["W"], cfg["H"]
+    samp = dict(filterMode=1, anisotropyEnable=True, maxAnisotropy=16.0)
+    chain = O.texture_chain(sc["tex"], sc["mips"])
+    s = sc["tex"].shape[0]
+    kw = dict(msaa=cfg["msaa"], cull=cfg["cull"], clear_depth=255.0, mip_levels=sc["mips"], sampler=samp)
+    o = oracle_draw(W, H, sc["vb"], sc["idx"], sc["vs"], O.FS_TEXTURED, sc["nvary"], sc["u"], texture_chain=chain, tex_dims=(s, s), **kw)
+    g = gpu_draw(r, W, H, sc["vb"], sc["idx"], sc["vs"], O.FS_TEXTURED, sc["nvary"], sc["u"], texture=sc["tex"], hw_filter=fast, **kw)
+    compare(o, g)
+    assert g["fragments_shaded"] == o["frags"] and g["triangles_assembled"] == o["assembled"]
+    if not fast:   # default sampler: the oracle's arithmetic op for op; only log2f's last ulp may differ
+        assert (o["color"].view(np.uint32) == g["color"].view(np.uint32)).mean() > 0.99
+
+
+def test_full_size_c4_soup_vs_oracle(r):
+    """C4 scene generator at 4K, 1 M of its triangles (small-triangle binning path): everything bit-exact."""
+    cfg, _ = None, None
+    W, H = 3840, 2160
+    vb, idx = scenes.soup(ntri=1_000_000, width=W, height=H)
+    kw = dict(cull=2, clear_depth=255.0)
+    o = oracle_draw(W, H, vb, idx, 0, O.FS_VARYING0, 1, IDENT, **kw)
+    g = gpu_draw(r, W, H, vb, idx, 0, O.FS_VARYING0, 1, IDENT, **kw)
+    compare(o, g, exact_color=True)
+    assert g["fragments_shaded"] == o["frags"] and g["triangles_assembled"] == o["assembled"]
+
+
+def test_full_size_c5_mix_vs_oracle(r):
+    """C5 scene generator at 7680x4320, 8x MSAA, 1 M of its triangles (90 % tiny, 9.9 % mid, 0.1 % up to 512 px:
+    both queue classes, Hi-Z on deep tiles): everything bit-exact."""
+    W, H = 7680, 4320
+    vb, idx = scenes.scene_mix(ntri=1_000_000, width=W, height=H)
+    kw = dict(msaa=8, cull=2, clear_depth=255.0)
+    o = oracle_draw(W, H, vb, idx, 0, O.FS_VARYING0, 1, IDENT, **kw)
+    g = gpu_draw(r, W, H, vb, idx, 0, O.FS_VARYING0, 1, IDENT, **kw)
+    compare(o, g, exact_color=True)
+    assert g["fragments_shaded"] == o["frags"] and g["triangles_assembled"] == o["assembled"]
+
+
+def test_fast_sampler_precision_contract(r):
+    """include/ifrit_b200.h, iftrcuSetSamplerHardwareFilter: the default sampler follows the oracle for texels of any
+    range; the opt-in FAST sampler (texture-unit blend, 8-bit weights) is held to 1/255 only for texels in [0, 1] —
+    on an HDR-range texture (x 64) its error scales with the range while the default stays exact."""
+    W, H = 384, 216
+    vb, idx, u = _mesh_case(W, H)
+    tex = scenes.texture_checker(size=256, seed=7) * np.float32(64.0)
+    samp = dict(filterMode=1, anisotropyEnable=True, maxAnisotropy=16.0)
+    chain = O.texture_chain(tex, 8)
+    o = oracle_draw(W, H, vb, idx, 1, O.FS_TEXTURED, 2, u, cull=2, texture_chain=chain, tex_dims=(256, 256), mip_levels=8, sampler=samp)
+    g = gpu_draw(r, W, H, vb, idx, 1, O.FS_TEXTURED, 2, u, cull=2, texture=tex, mip_levels=8, sampler=samp, hw_filter=False)
+    compare(o, g)
+    assert (o["color"].view(np.uint32) == g["color"].view(np.uint32)).mean() > 0.99
+    f = gpu_draw(r, W, H, vb, idx, 1, O.FS_TEXTURED, 2, u, cull=2, texture=tex, mip_levels=8, sampler=samp, hw_filter=True)
+    assert np.array_equal(o["prim_id"], f["prim_id"]) and np.array_equal(o["depth"].view(np.uint32), f["depth"].view(np.uint32))
+    d = np.abs(o["color"] - f["color"]).max(-1)
+    assert (d <= 64.0 / 255).mean() >= 0.999      # the documented bound: 1/255 x texel range
+
+
+def test_unsynchronised_draws_with_growing_pair_count(gpu_renderer_factory):
+    """draws streamed without a synchronize while the camera zooms in, so that the (triangle, tile)
+    pair count more than doubles from frame to frame — every frame must still be complete (the queues are re-sized
+    whenever an input of the geometry stage changed), checked against the oracle frame by frame via the
+    double-buffered host image."""
+    from ifrit_v2_b200 import renderer as R
+    W, H = 640, 360
+    r2 = gpu_renderer_factory()
+    vb, idx = scenes.mesh_sphere(n=48)
+    host = np.zeros((H, W, 4), np.float32)
+    r2.bindFrameBuffer(host, None, W, H, useDoubleBuffer=True)
+    eyes = [(0.0, 0.0, 9.0), (0.0, 0.0, 4.0), (0.0, 0.0, 2.2), (0.0, 0.0, 1.6), (0.0, 0.0, 1.6)]
+    exp, pairs = [], []
+    R.setup_scene(r2, vb, idx, 1, O.FS_NORMAL_COLOR, 2, scenes.uniform_block(scenes.default_mvp(W, H, eye=eyes[0])))
+    r2.SetCullMode(2)
+    r2.setClearValues([(.1, .2, .3, 1)], 1.0)
+    for k, eye in enumerate(eyes):
+        u = scenes.uniform_block(scenes.default_mvp(W, H, eye=eye))
+        exp.append(oracle_draw(W, H, vb, idx, 1, O.FS_NORMAL_COLOR, 2, u, cull=2, clear_color=(.1, .2, .3, 1))["color"])
+        r2.copyHostBufferToBuffer(u, 0)            # new MVP, no synchronize
+        r2.clear()
+        r2.drawElements()
+        if k >= 1:
+            # frame k - 1 arrives in the host image while frame k renders; wait for that copy only
+            r2.synchronize()
+            assert np.array_equal(host.view(np.uint32), exp[k - 1].view(np.uint32)), f"frame {k - 1} incomplete"
+            pairs.append(r2.stats()["tile_pairs"])
+    assert pairs[-1] > 2 * pairs[0]
+    r2.close()
+
+
+def test_argument_validation(gpu_renderer_factory):
+    """out-of-range blit rectangles / layers, a skybox texture without 6 layers and a too-small
+    uniform block are rejected with a status code instead of reaching a kernel."""
+    from ifrit_v2_b200 import renderer as R
+    r2 = gpu_renderer_factory()
+    r2.CreateTexture(1, 32, 32, 2, 1)
+
+    def blit(srcLevel=0, dstLevel=1, srcLayer=0, dstLayer=0, srcRect=(0, 0, 32, 32), dstRect=(0, 0, 16, 16)):
+        b = R.IfritImageBlit()
+        b.srcSubresource.mipLevel, b.srcSubresource.baseArrayLayer = srcLevel, srcLayer
+        b.dstSubresource.mipLevel, b.dstSubresource.baseArrayLayer = dstLevel, dstLayer
+        b.srcExtentSt.width, b.srcExtentSt.height, b.srcExtentEd.width, b.srcExtentEd.height = srcRect
+        b.dstExtentSt.width, b.dstExtentSt.height, b.dstExtentEd.width, b.dstExtentEd.height = dstRect
+        r2.blitImage(1, 1, b, 1)
+    blit()                                      # the valid one
+    for args in (dict(srcRect=(0, 0, 33, 32)), dict(dstRect=(0, 0, 16, 17)), dict(srcLayer=1), dict(dstRect=(4, 4, 4, 8)), dict(dstLevel=3)):
+        with pytest.raises(R.IfritError):
+            blit(**args)
+    W, H = 64, 64
+    vb, idx = scenes.kat2()
+    r2.bindFrameBuffer(np.zeros((H, W, 4), np.float32), np.zeros((H, W), np.float32))
+    R.setup_scene(r2, vb, idx, 0, O.FS_SKYBOX, 1, IDENT, texture=np.zeros((1, 8, 8, 4), np.float32), mip_levels=0)
+    with pytest.raises(R.IfritError):
+        r2.drawElements()                       # one layer, the cube sampler reads six
+    R.setup_scene(r2, vb, idx, 0, O.FS_DERIV_VIS, 1, IDENT)
+    vb2 = np.zeros((3, 12), np.float32); vb2[:, :8] = vb
+    r2.bindVertexBuffer(vb2)
+    r2.bindVertexShader(0, 2)
+    r2.CreateBuffer(0, 64)                      # MVP only: deriv_vis reads float 21
+    with pytest.raises(R.IfritError):
+        r2.drawElements()
+    r2.close()
