@@ -92,11 +92,12 @@ struct iftrcuRenderer {
     TexDesc tex[IFR_MAX_TEX]; DevBuf texMem[IFR_MAX_TEX]; size_t texTexels[IFR_MAX_TEX] = {0};
     SampDesc samp[IFR_MAX_TEX];
     DevBuf bufMem[IFR_MAX_BUF]; int bufSize[IFR_MAX_BUF] = {0};
+    float u0[32] = {0};   // host shadow of the first 128 bytes of buffer slot 0 (uniform block), see DrawParams::u0
 
     // scratch: two sets, so that the geometry stage of frame k + 1 (setup / scan / fill on the geometry stream) can run
     // while the tile kernel of frame k (draw stream) still reads the queues of frame k — iftrcuSetFramePipelining
     struct Scratch {
-        DevBuf scanPartial, pos, vary, rec, clipBary, tileBox, fan1List, heavyBits, tileCount, tileStart, tileCursor, queue, bigQueue, counters;
+        DevBuf scanPartial, pos, vary, rec, clipBary, tileBox, fan1List, heavyBits, tileCount, tileStart, tileCursor, tileOrder, queue, bigQueue, counters;
         bool queueChecked = false;   // queue capacity verified for the current geometry / state
     } scr[2];
     int set = 0;                 // scratch set of the current / most recent draw
@@ -212,6 +213,7 @@ static void build_params(iftrcuRenderer* r, DrawParams& p) {
     p.fan1List = (uint32_t*)r->scr[r->set].fan1List.p; p.heavyBits = (uint32_t*)r->scr[r->set].heavyBits.p;
     p.tileCount = (uint32_t*)r->scr[r->set].tileCount.p; p.tileStart = (uint32_t*)r->scr[r->set].tileStart.p;
     p.tileCursor = (uint32_t*)r->scr[r->set].tileCursor.p; p.queue = (uint32_t*)r->scr[r->set].queue.p;
+    p.tileOrder = (uint32_t*)r->scr[r->set].tileOrder.p;
     p.queueCap = (uint32_t)std::min<size_t>(r->scr[r->set].queue.cap / 4, 0xffffffffu);
     p.bigQueue = (TriS*)r->scr[r->set].bigQueue.p;
     p.bigCap = (uint32_t)std::min<size_t>(r->scr[r->set].bigQueue.cap / sizeof(TriS), 0xffffffffu);
@@ -219,6 +221,7 @@ static void build_params(iftrcuRenderer* r, DrawParams& p) {
     p.scanPartial = (unsigned long long*)r->scr[r->set].scanPartial.p; p.epoch = r->epoch;
     for (int i = 0; i < IFR_MAX_TEX; i++) { p.tex[i] = r->tex[i]; p.samp[i] = r->samp[i]; }
     for (int i = 0; i < IFR_MAX_BUF; i++) p.buf[i] = (const float*)r->bufMem[i].p;
+    memcpy(p.u0, r->u0, sizeof p.u0);
 }
 
 static int ensure_scratch(iftrcuRenderer* r) {
@@ -235,9 +238,10 @@ static int ensure_scratch(iftrcuRenderer* r) {
     CUDA_TRY(r->scr[r->set].tileCount.ensure(2 * ntiles * 4));
     CUDA_TRY(r->scr[r->set].tileStart.ensure(2 * (ntiles + 1) * 4));
     CUDA_TRY(r->scr[r->set].tileCursor.ensure(2 * ntiles * 4));
+    CUDA_TRY(r->scr[r->set].tileOrder.ensure(ntiles * 4));
     CUDA_TRY(r->scr[r->set].counters.ensure(IFR_COUNTER_BYTES));
-    if (!r->scr[r->set].scanPartial.p || r->scr[r->set].scanPartial.cap < 2 * (ntiles / 4096 + 1) * 8) {
-        CUDA_TRY(r->scr[r->set].scanPartial.ensure(2 * (ntiles / 4096 + 1) * 8));
+    if (!r->scr[r->set].scanPartial.p || r->scr[r->set].scanPartial.cap < 4 * (ntiles / 4096 + 1) * 8) {
+        CUDA_TRY(r->scr[r->set].scanPartial.ensure(4 * (ntiles / 4096 + 1) * 8));
         CUDA_TRY(cudaMemsetAsync(r->scr[r->set].scanPartial.p, 0, r->scr[r->set].scanPartial.cap, (r->pipelining && r->geomStream) ? r->geomStream : r->stream));
     }
     if (!r->scr[r->set].queue.p) CUDA_TRY(r->scr[r->set].queue.ensure(std::max<size_t>(ntri * 2 + ntiles, 1024) * 4));
@@ -401,10 +405,10 @@ static int sync_and_check(iftrcuRenderer* r) {
     if (r->haveDraw && r->hCounters[6]) { r->hCounters[6] = 0; return r->fail(IFRIT_ERR_UNSUPPORTED, "drawElements", "alpha blending: a tile holds more than 4096 triangles"); }
     if (r->hTimedOut && *r->hTimedOut) { *r->hTimedOut = 0; return r->fail(IFRIT_ERR_STATE, "frame flags", "a sort-first rank did not signal within 2 s"); }
     if (r->haveDraw) {
-        // the two spread counters (common.cuh): one 32-byte sector per slot behind the 8 scalars
+        // the two spread counters (common.cuh): one 32-byte sector per slot behind the scalars
         unsigned long long sum[2] = {0, 0};
         for (int w = 0; w < 2; w++)
-            for (int i = 0; i < IFR_SPREAD; i++) sum[w] += r->hCounters[8 + ((size_t)w * IFR_SPREAD + i) * 4];
+            for (int i = 0; i < IFR_SPREAD; i++) sum[w] += r->hCounters[IFR_COUNTER_SCALARS + ((size_t)w * IFR_SPREAD + i) * 4];
         r->hCounters[0] = sum[0]; r->hCounters[2] = sum[1];
         r->stats.triangles_assembled = r->hCounters[0];
         r->stats.tile_pairs = r->hCounters[1] + r->hCounters[5];
@@ -457,7 +461,7 @@ int iftrcuDestroyInstance(iftrcuRenderer* h) {
     for (int k = 0; k < 2; k++) {
         iftrcuRenderer::Scratch& c = r->scr[k];
         DevBuf* sb[] = {&c.scanPartial, &c.pos, &c.vary, &c.rec, &c.clipBary, &c.tileBox, &c.fan1List, &c.heavyBits, &c.tileCount, &c.tileStart,
-                        &c.tileCursor, &c.queue, &c.bigQueue, &c.counters};
+                        &c.tileCursor, &c.tileOrder, &c.queue, &c.bigQueue, &c.counters};
         for (DevBuf* b : sb) b->release();
         if (r->evGeomDone[k]) cudaEventDestroy(r->evGeomDone[k]);
         if (r->evTileDone[k]) cudaEventDestroy(r->evTileDone[k]);
@@ -744,6 +748,7 @@ int iftrcuCreateTexture(iftrcuRenderer* h, int slot, const IfritImageCreateInfo*
             L.w = lw; L.h = lh; L.off = (uint32_t)off; L.layerStride = (uint32_t)((uint64_t)lw * lh);
             L.invW = 1.0f / (float)lw; L.invH = 1.0f / (float)lh;
             L.inv2W = 1.0f / (2.0f * (float)lw); L.inv2H = 1.0f / (2.0f * (float)lh);
+            L.fw = (float)lw; L.fh = (float)lh; L.fw1 = (float)(lw - 1); L.fh1 = (float)(lh - 1);
             off += (uint64_t)lw * lh * ci->arrayLayers;
             lw = (lw + 1) >> 1; lh = (lh + 1) >> 1;
         }
@@ -833,6 +838,7 @@ int iftrcuCreateBuffer(iftrcuRenderer* h, int slot, int bufSize) {
     if (r->geomStream) CUDA_TRY(cudaStreamSynchronize(r->geomStream));
     CUDA_TRY(r->bufMem[slot].ensure((size_t)bufSize));
     r->bufSize[slot] = bufSize;
+    if (slot == 0) memset(r->u0, 0, sizeof r->u0);
     mark_inputs(r);
     return IFRIT_OK;
 }
@@ -840,6 +846,7 @@ int iftrcuCopyHostBufferToBuffer(iftrcuRenderer* h, const void* src, int dstSlot
     R_CHECK(h);
     if (dstSlot < 0 || dstSlot >= IFR_MAX_BUF || !src || size < 0 || size > r->bufSize[dstSlot]) return r->fail(IFRIT_ERR_INVALID, "copyHostBufferToBuffer", "bad argument");
     CUDA_TRY(cudaMemcpyAsync(r->bufMem[dstSlot].p, src, (size_t)size, cudaMemcpyHostToDevice, r->stream));
+    if (dstSlot == 0) memcpy(r->u0, src, std::min<size_t>((size_t)size, sizeof r->u0));
     mark_inputs(r);
     return IFRIT_OK;
 }

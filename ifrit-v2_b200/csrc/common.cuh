@@ -47,7 +47,7 @@ struct __align__(16) TriS {
 
 #define IFR_MAX_MIPS 16
 // one mip level: dimensions, texel offset of layer 0, texels per layer, reciprocals for address wrapping
-struct TexLevel { int w, h; uint32_t off, layerStride; float invW, invH, inv2W, inv2H; };
+struct TexLevel { int w, h; uint32_t off, layerStride; float invW, invH, inv2W, inv2H; float fw, fh, fw1, fh1; };   // fw1 = float(w - 1)
 // hw[l]: CUDA texture object over layer 0 of level l (pitch-linear view of the same memory, clamp addressing,
 // unnormalised coordinates, bilinear filter) or 0 when the level cannot be bound (alignment, 1-texel levels)
 struct TexDesc { const float4* data; int w, h, mips, layers; TexLevel lvl[IFR_MAX_MIPS]; unsigned long long hw[IFR_MAX_MIPS]; };
@@ -87,12 +87,22 @@ struct DrawParams {
     // binning: two queues per tile.  Index 0 = small triangles (u32 slot per pair), 1 = big triangles
     // (one TriS per pair).  tileCount / tileCursor: [2][ntiles]; tileStart: [2][ntiles + 1]
     uint32_t* tileCount; uint32_t* tileStart; uint32_t* tileCursor;
+    // tile kernel work list, written by the scan pass: tileOrder[0 .. nWork) = owned tiles with a non-empty queue,
+    // tileOrder[ntiles - 1 - k], k < nEmpty = owned tiles with nothing binned (fused clear only); nWork = counters[2],
+    // nEmpty = counters[7].  CTA b of the tile kernel takes tileOrder[b]; CTAs beyond nWork clear IFR_EMPTY_PER_CTA
+    // empty tiles each.
+    uint32_t* tileOrder;
     uint32_t* queue; uint32_t queueCap; TriS* bigQueue; uint32_t bigCap;
     uint32_t epoch; unsigned long long* scanPartial;   // chained scan: (epoch << 32 | block total) per scan CTA
-    unsigned long long* counters;    // [0] assembled, [1] small pairs, [2] frags, [3] overflow flag, [4] fan1 count, [5] big pairs,
-                                     // [6] blending: a tile held more than IFR_BLEND_CAP triangles
+    unsigned long long* counters;    // [0] assembled (host sum), [1] small pairs, [2] nWork (device) / frags (host sum), [3] overflow flag,
+                                     // [4] fan1 count, [5] big pairs, [6] blending: a tile held more than IFR_BLEND_CAP triangles,
+                                     // [7] nEmpty, [8..11] scan tickets (one per scan class), [12..15] spare
     // resources
     TexDesc tex[IFR_MAX_TEX]; SampDesc samp[IFR_MAX_TEX]; const float* buf[IFR_MAX_BUF];
+    // the uniform block of the shader registry = the first 128 bytes of buffer slot 0 as last written through
+    // copyHostBufferToBuffer, shadowed by the host so that the kernels read it from the constant bank (the reference's
+    // shaders read GetBufferPtr(slot) from global memory per invocation, SB:394)
+    alignas(16) float u0[32];
 };
 
 // RGBA32F -> packed RGBA8 UNORM (r in the low byte): round-to-nearest-even of saturate(c) * 255
@@ -102,12 +112,14 @@ __device__ __forceinline__ uint32_t ifr_pack_rgba8(const float4& c) {
 }
 
 // Statistics counters that every warp of a big grid bumps (assembled triangles, shaded fragments) are spread over
-// IFR_SPREAD slots, one 32-byte sector each, behind the 8 scalar counters: a single address would serialise hundreds
+// IFR_SPREAD slots, one 32-byte sector each, behind the 16 scalar counters: a single address would serialise hundreds
 // of thousands of reductions in one L2 slice (measured: 90 us of a 195 us tile kernel).  The host sums them.
 #define IFR_SPREAD 256
-#define IFR_COUNTER_BYTES (64 + 2 * IFR_SPREAD * 32)
+#define IFR_COUNTER_SCALARS 16
+#define IFR_COUNTER_BYTES (IFR_COUNTER_SCALARS * 8 + 2 * IFR_SPREAD * 32)
+#define IFR_EMPTY_PER_CTA 8
 __device__ __forceinline__ void ifr_count_spread(unsigned long long* counters, int which, unsigned int slotHint, unsigned long long v) {
-    atomicAdd(counters + 8 + ((size_t)which * IFR_SPREAD + (slotHint & (IFR_SPREAD - 1))) * 4, v);
+    atomicAdd(counters + IFR_COUNTER_SCALARS + ((size_t)which * IFR_SPREAD + (slotHint & (IFR_SPREAD - 1))) * 4, v);
 }
 
 // sort-first ownership of a tile: 64-px super-tiles interleaved over ranks

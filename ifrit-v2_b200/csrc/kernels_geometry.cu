@@ -22,8 +22,8 @@
 template <int VS>
 __device__ __forceinline__ float4 run_vs(const DrawParams& p, const float4 a0) {
     if (VS == IFRIT_VS_MVP) {
-        const float4* m = reinterpret_cast<const float4*>(p.buf[0]);
-        const float4 r0 = __ldg(m), r1 = __ldg(m + 1), r2 = __ldg(m + 2), r3 = __ldg(m + 3);
+        const float4* m = reinterpret_cast<const float4*>(p.u0);   // constant bank
+        const float4 r0 = m[0], r1 = m[1], r2 = m[2], r3 = m[3];
         float4 o;
         o.x = fmaf(r0.w, a0.w, fmaf(r0.z, a0.z, fmaf(r0.y, a0.y, __fmul_rn(r0.x, a0.x))));
         o.y = fmaf(r1.w, a0.w, fmaf(r1.z, a0.z, fmaf(r1.y, a0.y, __fmul_rn(r1.x, a0.x))));
@@ -480,29 +480,49 @@ __global__ void __launch_bounds__(128, IFR_FILL_MINB) fill_heavy_kernel(const __
     }
 }
 
-// pass 2: exclusive scan of the per-tile counts of both queue classes.  Chained multi-CTA scan: CTA b
-// scans 4096 counts locally, publishes (epoch, total) and sums the totals of its predecessors (all
-// resident: <= 64 CTAs at 8K).  Cursor reset, totals -> counters[1] (small pairs) / counters[5]
-// (big pairs), overflow flag -> counters[3].
+// pass 2: exclusive scans over the tiles, four classes in one launch (blockIdx.y):
+//   0 / 1  per-tile counts of the small / big queue  -> tileStart, cursor reset, totals -> counters[1] / counters[5],
+//          overflow flag -> counters[3]
+//   2      owned tiles with a non-empty queue         -> tileOrder[rank] = tileX | tileY << 16 (front of the work list), total -> counters[2]
+//   3      owned tiles with nothing binned            -> tileOrder[ntiles - 1 - rank] = tile (back), total -> counters[7]
+// Chained multi-CTA scan: CTA b scans 4096 items locally, publishes (epoch, total) and sums the totals of its
+// predecessors.  The logical block index is a ticket taken on arrival (counters[8 + class], zeroed with the counters
+// every draw), so every predecessor a CTA spins on has started before it: no assumption about the dispatch order of
+// blockIdx or about the whole grid being resident (at most 32 CTAs per class at 8K).
 #define IFR_SCAN_ITEMS 4096
 __global__ void __launch_bounds__(1024) scan_kernel(const __grid_constant__ DrawParams p) {
     __shared__ uint32_t warpSums[32];
     __shared__ uint32_t prefix;
+    __shared__ int ticket;
     const int n = p.tilesX * p.tilesY;
-    const int cls = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
-    const uint32_t* count = p.tileCount + (size_t)cls * n;
-    uint32_t* start = p.tileStart + (size_t)cls * (n + 1);
-    uint32_t* cursor = p.tileCursor + (size_t)cls * n;
-    volatile unsigned long long* partial = p.scanPartial + (size_t)cls * nblk;
+    const int cls = blockIdx.y, nblk = gridDim.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) ticket = (int)atomicAdd(&p.counters[8 + cls], 1ull);
+    __syncthreads();
+    const int blk = ticket;
+    volatile unsigned long long* partial = p.scanPartial + (size_t)cls * nblk;
     const int i0 = blk * IFR_SCAN_ITEMS + tid * 4;
     uint32_t v[4];
-    if (i0 + 3 < n && ((n & 3) == 0)) {
-        const uint4 q = *reinterpret_cast<const uint4*>(count + i0);
-        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    if (cls < 2) {
+        const uint32_t* count = p.tileCount + (size_t)cls * n;
+        if (i0 + 3 < n && ((n & 3) == 0)) {
+            const uint4 q = *reinterpret_cast<const uint4*>(count + i0);
+            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) v[k] = i0 + k < n ? count[i0 + k] : 0u;
+        }
     } else {
 #pragma unroll
-        for (int k = 0; k < 4; k++) v[k] = i0 + k < n ? count[i0 + k] : 0u;
+        for (int k = 0; k < 4; k++) {
+            const int i = i0 + k;
+            v[k] = 0u;
+            if (i < n) {
+                const bool work = (p.tileCount[i] | p.tileCount[n + i]) != 0u;
+                const bool owned = p.world <= 1 || ifr_tile_owner(i % p.tilesX, i / p.tilesX, p.world) == p.rank;
+                v[k] = (owned && (work == (cls == 2))) ? 1u : 0u;
+            }
+        }
     }
     const uint32_t sum = v[0] + v[1] + v[2] + v[3];
     uint32_t incl = sum;
@@ -541,17 +561,31 @@ __global__ void __launch_bounds__(1024) scan_kernel(const __grid_constant__ Draw
         if (lane == 0) prefix = pre;
         if (blk == nblk - 1 && lane == 0) {
             const uint32_t all = pre + total;
-            start[n] = all;
-            p.counters[cls ? 5 : 1] = all;
-            if (all > (cls ? p.bigCap : p.queueCap)) p.counters[3] = 1ull;
+            if (cls < 2) {
+                p.tileStart[(size_t)cls * (n + 1) + n] = all;
+                p.counters[cls ? 5 : 1] = all;
+                if (all > (cls ? p.bigCap : p.queueCap)) p.counters[3] = 1ull;
+            } else {
+                p.counters[cls == 2 ? 2 : 7] = all;
+            }
         }
     }
     __syncthreads();
     uint32_t run = prefix + warpSums[wid] + (incl - sum);
+    if (cls < 2) {
+        uint32_t* start = p.tileStart + (size_t)cls * (n + 1);
+        uint32_t* cursor = p.tileCursor + (size_t)cls * n;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        if (i0 + k < n) { start[i0 + k] = run; cursor[i0 + k] = 0u; }
-        run += v[k];
+        for (int k = 0; k < 4; k++) {
+            if (i0 + k < n) { start[i0 + k] = run; cursor[i0 + k] = 0u; }
+            run += v[k];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (v[k]) p.tileOrder[cls == 2 ? run : (uint32_t)n - 1u - run] = (uint32_t)((i0 + k) % p.tilesX) | ((uint32_t)((i0 + k) / p.tilesX) << 16);
+            run += v[k];
+        }
     }
 }
 
@@ -565,7 +599,7 @@ cudaError_t ifr_launch_setup_count(const DrawParams& p, int vsMode, cudaStream_t
 }
 cudaError_t ifr_launch_scan(const DrawParams& p, cudaStream_t s) {
     const int n = p.tilesX * p.tilesY;
-    scan_kernel<<<dim3((n + IFR_SCAN_ITEMS - 1) / IFR_SCAN_ITEMS, 2), 1024, 0, s>>>(p);
+    scan_kernel<<<dim3((n + IFR_SCAN_ITEMS - 1) / IFR_SCAN_ITEMS, 4), 1024, 0, s>>>(p);
     return cudaGetLastError();
 }
 cudaError_t ifr_launch_fill(const DrawParams& p, cudaStream_t s) {

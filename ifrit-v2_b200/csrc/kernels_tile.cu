@@ -409,6 +409,30 @@ __device__ __forceinline__ void big_loop(const DrawParams& p, const KeyMode& km,
     }
 }
 
+// A tile with nothing binned: the fused clear is all there is to do (imageResetFloat32* CU:3337/3363).  Thread = pixel,
+// row-major inside the tile: a warp writes two full 256-byte colour rows.
+template <int S>
+__device__ __forceinline__ void clear_tile(const DrawParams& p, int tileX, int tileY, int tid) {
+    const int px = tileX * IFR_TILE + (tid & 15), py = tileY * IFR_TILE + (tid >> 4);
+    if (px >= p.W || py >= p.H) return;
+    const size_t pidx = (size_t)py * p.W + px;
+    const bool scis = scissor_pass(p, px, py);
+    if (!p.doClear || !scis) {
+        if (p.present) p.present[pidx] = ifr_pack_rgba8(p.color[pidx]);   // untouched pixel: present what is there
+        if (!p.doClear) return;
+    }
+    if (scis) {
+        const float4 cc = make_float4(p.clearColor[0], p.clearColor[1], p.clearColor[2], p.clearColor[3]);
+        p.color[pidx] = cc;
+        p.depth[pidx] = p.clearDepth;
+        if (p.present) p.present[pidx] = ifr_pack_rgba8(cc);
+    }
+    if (p.primIds) {
+#pragma unroll
+        for (int s = 0; s < S; s++) p.primIds[pidx * S + s] = -1;
+    }
+}
+
 #ifndef IFR_MINB1
 #define IFR_MINB1 6
 #endif
@@ -426,11 +450,29 @@ __global__ void __launch_bounds__(256, FsTraits<FS>::needsDerivs ? (S == 1 ? IFR
     __shared__ HizShared hz;
     constexpr int NV = FsTraits<FS>::nv;
 
-    const int tileX = blockIdx.x, tileY = blockIdx.y;
-    if (p.world > 1 && ifr_tile_owner(tileX, tileY, p.world) != p.rank) return;
+    // Work list (scan pass): CTA b < nWork takes a tile with a non-empty queue; the CTAs behind them share the owned tiles
+    // with nothing binned, IFR_EMPTY_PER_CTA each (fused clear only); tiles of other ranks appear in neither list.
     const int ntiles = p.tilesX * p.tilesY;
-    const int tile = tileY * p.tilesX + tileX;
     const int tid = threadIdx.x;
+    const ulonglong2 hdr = *reinterpret_cast<const ulonglong2*>(p.counters + 2);   // {nWork, overflow flag}
+    const uint32_t nWork = (uint32_t)hdr.x;
+    const bool overflow = hdr.y != 0;
+    if (blockIdx.x >= nWork) {
+        const uint32_t e0 = (blockIdx.x - nWork) * IFR_EMPTY_PER_CTA;
+        const uint32_t nEmpty = (uint32_t)p.counters[7];
+        for (uint32_t e = e0; e < min(e0 + IFR_EMPTY_PER_CTA, nEmpty); e++) {
+            const uint32_t t = p.tileOrder[ntiles - 1 - (int)e];
+            clear_tile<S>(p, (int)(t & 0xffffu), (int)(t >> 16), tid);
+        }
+        return;
+    }
+    const uint32_t torder = p.tileOrder[blockIdx.x];
+    const int tileX = (int)(torder & 0xffffu), tileY = (int)(torder >> 16);
+    const int tile = tileY * p.tilesX + tileX;
+    if (overflow) {    // a queue is too small: the host re-issues the draw with larger ones; until then the frame is cleared only
+        clear_tile<S>(p, tileX, tileY, tid);
+        return;
+    }
     // a warp owns one 8x4-pixel block of the tile (block = warp: x = (w & 1) * 8, y = (w >> 1) * 4), a quad = 4 lanes
     const int wrp = tid >> 5, q = (tid >> 2) & 7, l = tid & 3;
     // under the 40-register budget of the 1x kernels the compiler re-derives lx / ly from the thread id (a dozen bit
@@ -441,30 +483,10 @@ __global__ void __launch_bounds__(256, FsTraits<FS>::needsDerivs ? (S == 1 ? IFR
     const int px = tileX * IFR_TILE + lx, py = tileY * IFR_TILE + ly;
     const bool inFrame = px < p.W && py < p.H;
     const bool scis = inFrame && scissor_pass(p, px, py);
-    const bool overflow = p.counters[3] != 0;
     const uint32_t sStart = p.tileStart[tile], bStart = p.tileStart[ntiles + 1 + tile];
-    const uint32_t nSmall = overflow ? 0u : p.tileStart[tile + 1] - sStart;
-    const uint32_t nBig = overflow ? 0u : p.tileStart[ntiles + 1 + tile + 1] - bStart;
+    const uint32_t nSmall = p.tileStart[tile + 1] - sStart;
+    const uint32_t nBig = p.tileStart[ntiles + 1 + tile + 1] - bStart;
     const size_t pidx = (size_t)py * p.W + px;
-    if (nSmall + nBig == 0) {
-        // nothing binned here: the fused clear is all there is to do (imageResetFloat32* CU:3337/3363)
-        if (!inFrame) return;
-        if (!p.doClear || !scis) {
-            if (p.present) p.present[pidx] = ifr_pack_rgba8(p.color[pidx]);   // untouched pixel: present what is there
-            if (!p.doClear) return;
-        }
-        if (scis) {
-            const float4 cc = make_float4(p.clearColor[0], p.clearColor[1], p.clearColor[2], p.clearColor[3]);
-            p.color[pidx] = cc;
-            p.depth[pidx] = p.clearDepth;
-            if (p.present) p.present[pidx] = ifr_pack_rgba8(cc);
-        }
-        if (p.primIds) {
-#pragma unroll
-            for (int s = 0; s < S; s++) p.primIds[pidx * S + s] = -1;
-        }
-        return;
-    }
 
     KeyMode km;     // precomputed by the host from p.depthFunc (same table as key_mode)
     km.xhi = p.keyXhi; km.xlo = p.keyXlo; km.ordered = p.keyOrdered != 0; km.equal = p.keyEqual != 0; km.never = p.keyNever != 0;
@@ -548,12 +570,30 @@ __global__ void __launch_bounds__(256, FsTraits<FS>::needsDerivs ? (S == 1 ? IFR
     }
 
     // ---- quad shading + resolve -----------------------------------------------------------------
-    uint32_t mySlots[S];
+    // A pixel whose samples all hold the same key (S == 1, `uni`, or found equal below) needs no search: one FS
+    // invocation with count S.  Otherwise the per-sample slots are re-read from the shared-memory keys by every search
+    // (edge pixels only), so that nothing but the accumulators stays live across the fragment shader.
+    bool same = true;
+    uint32_t slot0;
+    int todo = 0;             // samples that still wait for their fragment
+    if (S == 1 || uni) {
+        const unsigned long long k = (S == 1 && nSmall != 0) ? keys[tid] : best;
+        slot0 = key_slot(km, k);
+        todo = slot0 != IFR_SLOT_NONE ? S : 0;
+    } else {
+        slot0 = key_slot(km, keys[tid]);
+        todo = slot0 != IFR_SLOT_NONE;
 #pragma unroll
-    for (int s = 0; s < S; s++) {
-        unsigned long long k = best;
-        if (S > 1 ? !uni : nSmall != 0) k = keys[s * IFR_TILE_PIX + tid];
-        mySlots[s] = key_slot(km, k);
+        for (int s = 1; s < S; s++) {
+            const uint32_t v = key_slot(km, keys[s * IFR_TILE_PIX + tid]);
+            same = same && v == slot0;
+            todo += v != IFR_SLOT_NONE;
+        }
+    }
+    if (!inFrame) todo = 0;
+    if (p.primIds && inFrame) {
+#pragma unroll
+        for (int s = 0; s < S; s++) p.primIds[pidx * S + s] = -1;     // overwritten below for the covered samples
     }
 
     float4 acc = make_float4(0, 0, 0, 0);
@@ -569,43 +609,47 @@ __global__ void __launch_bounds__(256, FsTraits<FS>::needsDerivs ? (S == 1 ? IFR
     // shading the list while seven wait cost more than the divergent second pass they replace.)
     uint32_t last = 0;
     bool first = true;
-    while (inFrame) {
-        uint32_t cur = IFR_SLOT_NONE;
+    while (todo > 0) {
+        uint32_t cur = slot0;
+        int cnt = S;
+        if (S > 1 && !same) {
+            cur = IFR_SLOT_NONE;
+            cnt = 0;
 #pragma unroll
-        for (int s = 0; s < S; s++) {
-            const uint32_t v = mySlots[s];
-            if (v != IFR_SLOT_NONE && (first || v > last) && v < cur) cur = v;
+            for (int s = 0; s < S; s++) {
+                const uint32_t v = key_slot(km, keys[s * IFR_TILE_PIX + tid]);
+                if (v != IFR_SLOT_NONE && (first || v > last)) {
+                    if (v < cur) { cur = v; cnt = 1; }
+                    else if (v == cur) cnt++;
+                }
+            }
         }
-        if (cur == IFR_SLOT_NONE) break;
-        int cnt = 0;
-#pragma unroll
-        for (int s = 0; s < S; s++) cnt += mySlots[s] == cur;
         float4 v[NV > 0 ? NV : 1], ddx[NV > 0 ? NV : 1], ddy[NV > 0 ? NV : 1];
         float depth = 0.0f;
         int prim = 0, fan = 0;
-        interp<NV, FsTraits<FS>::needsDerivs, FS == IFRIT_FS_TEXTURED_FAST || FS == IFRIT_FS_TEXTURED_LOD0_FAST>(p, cur, px, py, v, ddx, ddy, depth, prim, fan);
+        interp<NV, FsTraits<FS>::needsDerivs, FS == IFRIT_FS_TEXTURED_FAST || FS == IFRIT_FS_TEXTURED_LOD0_FAST || FS == IFRIT_FS_TEXTURED_FAST_RA>(p, cur, px, py, v, ddx, ddy, depth, prim, fan);
         const float4 c = run_fs<FS>(p, v, ddx, ddy, prim, fan);
         const float fc = (float)cnt;
         acc.x = fmaf(fc, c.x, acc.x); acc.y = fmaf(fc, c.y, acc.y);
         acc.z = fmaf(fc, c.z, acc.z); acc.w = fmaf(fc, c.w, acc.w);
         dacc = fmaf(fc, depth, dacc);
         bg -= cnt;
+        todo -= cnt;
         myFrags++;
         if (p.primIds) {
+            if (S == 1 || same) {
 #pragma unroll
-            for (int s = 0; s < S; s++)
-                if (mySlots[s] == cur) p.primIds[pidx * S + s] = prim;
+                for (int s = 0; s < S; s++) p.primIds[pidx * S + s] = prim;
+            } else {
+#pragma unroll
+                for (int s = 0; s < S; s++)
+                    if (key_slot(km, keys[s * IFR_TILE_PIX + tid]) == cur) p.primIds[pidx * S + s] = prim;
+            }
         }
         last = cur;
         first = false;
-        if (S == 1) break;
     }
     if (inFrame) {
-        if (p.primIds) {
-#pragma unroll
-            for (int s = 0; s < S; s++)
-                if (mySlots[s] == IFR_SLOT_NONE) p.primIds[pidx * S + s] = -1;
-        }
         const bool cleared = p.doClear && scis;
         if (bg != S || cleared) {
             float4 out = acc;
@@ -795,7 +839,7 @@ cudaError_t ifr_launch_tiles_blend(const DrawParams& p, int fsId, cudaStream_t s
 
 template <int FS>
 static cudaError_t launch_fs(const DrawParams& p, cudaStream_t s) {
-    const dim3 grid(p.tilesX, p.tilesY);
+    const dim3 grid(p.tilesX * p.tilesY);   // upper bound of the work list: surplus CTAs exit at once
     const size_t smem = (size_t)p.msaa * IFR_TILE_PIX * sizeof(unsigned long long);
 #define IFR_LAUNCH(SS)                                                                                   \
     case SS: {                                                                                           \
@@ -828,7 +872,13 @@ cudaError_t ifr_launch_tiles(const DrawParams& p, int fsId, cudaStream_t s) {
         case IFRIT_FS_TEXTURED: return launch_fs<IFRIT_FS_TEXTURED>(p, s);
         case IFRIT_FS_TEXTURED_LOD0: return launch_fs<IFRIT_FS_TEXTURED_LOD0>(p, s);
 #else
-        case IFRIT_FS_TEXTURED: return p.hwFilter ? launch_fs<IFRIT_FS_TEXTURED_FAST>(p, s) : launch_fs<IFRIT_FS_TEXTURED>(p, s);
+        case IFRIT_FS_TEXTURED: {
+            // the common sampler state has its own instantiation (sampler.cuh: sample_aniso_repeat)
+            const SampDesc& sd = p.samp[0];
+            const bool ra = sd.filter == IF_FILTER_LINEAR && sd.addrU == IF_SAMPLER_ADDRESS_MODE_REPEAT && sd.addrV == IF_SAMPLER_ADDRESS_MODE_REPEAT && sd.aniso;
+            if (ra) return p.hwFilter ? launch_fs<IFRIT_FS_TEXTURED_FAST_RA>(p, s) : launch_fs<IFRIT_FS_TEXTURED_RA>(p, s);
+            return p.hwFilter ? launch_fs<IFRIT_FS_TEXTURED_FAST>(p, s) : launch_fs<IFRIT_FS_TEXTURED>(p, s);
+        }
         case IFRIT_FS_TEXTURED_LOD0: return p.hwFilter ? launch_fs<IFRIT_FS_TEXTURED_LOD0_FAST>(p, s) : launch_fs<IFRIT_FS_TEXTURED_LOD0>(p, s);
 #endif
         case IFRIT_FS_SKYBOX: return launch_fs<IFRIT_FS_SKYBOX>(p, s);

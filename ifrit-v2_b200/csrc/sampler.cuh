@@ -221,6 +221,78 @@ __device__ __forceinline__ float4 sample_aniso(const TexDesc& t, const SampDesc&
     return make_float4(sum.x * invN, sum.y * invN, sum.z * invN, sum.w * invN);
 }
 
+// ---- the common sampler, specialised: LINEAR filter, REPEAT / REPEAT addressing, anisotropic (C2 / C3 of BASELINE.json).
+// Same arithmetic as sample_aniso -> sample_trilinear -> sample_level with those modes (FAST = false: op for op; FAST = true:
+// footprints through the texture unit), without the switches on the sampler state, with the per-level constants read
+// from the constant bank where they are used instead of being carried in registers across the tap loop.  Selected by
+// the launcher when the bound sampler matches (kernels_tile.cu: ifr_launch_tiles).
+template <bool FAST>
+__device__ __forceinline__ float4 bilinear_repeat(const TexDesc& t, int lod, float u, float v) {
+    const TexLevel& L = t.lvl[lod];
+    if (FAST) {
+        // REPEAT wrap without the two last-ulp fix-ups of wrapf: a coordinate that lands a hair outside [0, size) is
+        // clamped by the texture unit
+        const float cx = u * L.fw1, cy = v * L.fh1;
+        const float x = fmaf(-floorf(cx * L.invW), L.fw, cx) + 0.5f, y = fmaf(-floorf(cy * L.invH), L.fh, cy) + 0.5f;
+        const unsigned long long hw = t.hw[lod];
+        if (hw) return tex2D<float4>((cudaTextureObject_t)hw, x, y);
+        const int w = L.w, h = L.h;      // levels the texture unit cannot bind (1-texel rows, unaligned pitch)
+        const int ix = clampi((int)(x - 0.5f), 0, w - 1), iy = clampi((int)(y - 0.5f), 0, h - 1);
+        const float fx = (x - 0.5f) - (float)ix, fy = (y - 0.5f) - (float)iy;
+        const float4* b = t.data + L.off;
+        const int ix1 = min(ix + 1, w - 1), iy1 = min(iy + 1, h - 1);
+        return lerp4(lerp4(__ldg(b + iy * w + ix), __ldg(b + iy * w + ix1), fx), lerp4(__ldg(b + iy1 * w + ix), __ldg(b + iy1 * w + ix1), fx), fy);
+    } else {
+        const int w = L.w, h = L.h;
+        const float cx = wrapf(fmaf(u, L.fw1, 0.0f), L.fw, L.invW), cy = wrapf(fmaf(v, L.fh1, 0.0f), L.fh, L.invH);
+        const int px = clampi((int)cx, 0, w - 1), py = clampi((int)cy, 0, h - 1);
+        const float fx = cx - (float)px, fy = cy - (float)py;
+        const int px1 = min(px + 1, w - 1), py1 = min(py + 1, h - 1);
+        const float4* r0 = t.data + L.off + py * w;
+        const float4* r1 = t.data + L.off + py1 * w;
+        const float4 c00 = __ldg(r0 + px), c01 = __ldg(r0 + px1), c10 = __ldg(r1 + px), c11 = __ldg(r1 + px1);
+        return lerp4(lerp4(c00, c01, fx), lerp4(c10, c11, fx), fy);
+    }
+}
+
+template <bool FAST>
+__device__ __forceinline__ float4 sample_aniso_repeat(const TexDesc& t, float maxAnisoF, float u, float v, float2 du, float2 dv, float bias) {
+    const float dudx = du.x, dudy = du.y, dvdx = dv.x, dvdy = dv.y;
+    const float lx2 = fmaf(dvdx, dvdx, dudx * dudx), ly2 = fmaf(dvdy, dvdy, dudy * dudy);
+    const float px = (FAST ? sqrt_fast(lx2) : sqrtf(lx2)) * (float)t.w;
+    const float py = (FAST ? sqrt_fast(ly2) : sqrtf(ly2)) * (float)t.h;
+    const float pmax = fmaxf(px, py), pmin = fminf(px, py);
+    const int maxAniso = (int)maxAnisoF;
+    const float cr = ceilf(FAST ? pmax * rcp_fast(pmin) : pmax / pmin);
+    const int n = max(1, (cr < (float)maxAniso) ? (int)cr : maxAniso);
+    const float step = rcp_int(n + 1), invN = rcp_int(n);
+    const float lambda = fmaxf(0.0f, FAST ? lg2_fast(pmax * invN) : log2f(pmax / (float)n));
+    const float ddu = (px > py) ? dudx : dudy, ddv = (px > py) ? dvdx : dvdy;
+    const float lod = lambda + bias;
+    const int lo0 = (int)floorf(lod);
+    const float d = lod - (float)lo0;
+    const int lo = clampi(lo0, 0, t.mips), hi = clampi(lo0 + 1, 0, t.mips);
+    float4 sum = make_float4(0, 0, 0, 0);
+    if (d == 0.0f) {      // lerp(a, b, 0) == a: one level (the magnified case)
+#pragma unroll 2
+        for (int i = 0; i < n; i++) {
+            const float tt = (float)i * step - 0.5f;
+            const float4 r = bilinear_repeat<FAST>(t, lo, fmaf(ddu, tt, u), fmaf(ddv, tt, v));
+            sum.x += r.x; sum.y += r.y; sum.z += r.z; sum.w += r.w;
+        }
+    } else {
+#pragma unroll 2
+        for (int i = 0; i < n; i++) {
+            const float tt = (float)i * step - 0.5f;
+            const float uu = fmaf(ddu, tt, u), vv = fmaf(ddv, tt, v);
+            const float4 a = bilinear_repeat<FAST>(t, lo, uu, vv), b = bilinear_repeat<FAST>(t, hi, uu, vv);
+            const float4 r = lerp4(a, b, d);
+            sum.x += r.x; sum.y += r.y; sum.z += r.z; sum.w += r.w;
+        }
+    }
+    return make_float4(sum.x * invN, sum.y * invN, sum.z * invN, sum.w * invN);
+}
+
 __device__ __forceinline__ float4 sample_cube(const TexDesc& t, const SampDesc& s, float x, float y, float z, float lod) {
     const float ax = fabsf(x), ay = fabsf(y), az = fabsf(z);
     float u, v, norm;
@@ -253,9 +325,14 @@ __device__ __forceinline__ float4 tex_grad(const TexDesc& t, const SampDesc& s, 
 // plain ids keep the oracle's arithmetic op for op.
 #define IFRIT_FS_TEXTURED_FAST 100
 #define IFRIT_FS_TEXTURED_LOD0_FAST 101
+// `textured` with the sampler state LINEAR / REPEAT / REPEAT / anisotropic compiled in (sample_aniso_repeat)
+#define IFRIT_FS_TEXTURED_RA 102
+#define IFRIT_FS_TEXTURED_FAST_RA 103
 template <int FS> struct FsTraits { static constexpr bool needsDerivs = false; static constexpr int nv = 1; };
 template <> struct FsTraits<IFRIT_FS_TEXTURED_FAST> { static constexpr bool needsDerivs = true; static constexpr int nv = 2; };
 template <> struct FsTraits<IFRIT_FS_TEXTURED_LOD0_FAST> { static constexpr bool needsDerivs = false; static constexpr int nv = 2; };
+template <> struct FsTraits<IFRIT_FS_TEXTURED_RA> { static constexpr bool needsDerivs = true; static constexpr int nv = 2; };
+template <> struct FsTraits<IFRIT_FS_TEXTURED_FAST_RA> { static constexpr bool needsDerivs = true; static constexpr int nv = 2; };
 template <> struct FsTraits<IFRIT_FS_PRIM_ID> { static constexpr bool needsDerivs = false; static constexpr int nv = 0; };
 template <> struct FsTraits<IFRIT_FS_TEXTURED> { static constexpr bool needsDerivs = true; static constexpr int nv = 2; };
 template <> struct FsTraits<IFRIT_FS_TEXTURED_LOD0> { static constexpr bool needsDerivs = false; static constexpr int nv = 2; };
@@ -264,29 +341,33 @@ template <> struct FsTraits<IFRIT_FS_DERIV_VIS> { static constexpr bool needsDer
 template <int FS>
 __device__ __forceinline__ float4 run_fs(const DrawParams& p, const float4* v, const float4* ddx,
                                          const float4* ddy, int prim, int fan) {
-    const float* u = p.buf[0];
+    const float* u = p.u0;   // uniform block, constant bank
     if (FS == IFRIT_FS_VARYING0) return v[0];
     if (FS == IFRIT_FS_NORMAL_COLOR)
         return make_float4(fmaf(v[0].x, 0.5f, 0.5f), fmaf(v[0].y, 0.5f, 0.5f), fmaf(v[0].z, 0.5f, 0.5f), 0.5f);
     if (FS == IFRIT_FS_PRIM_ID) return make_float4((float)prim, (float)fan, 0.0f, 1.0f);
-    if (FS == IFRIT_FS_TEXTURED || FS == IFRIT_FS_TEXTURED_LOD0 || FS == IFRIT_FS_TEXTURED_FAST || FS == IFRIT_FS_TEXTURED_LOD0_FAST) {
-        constexpr bool FAST = FS == IFRIT_FS_TEXTURED_FAST || FS == IFRIT_FS_TEXTURED_LOD0_FAST;
+    if (FS == IFRIT_FS_TEXTURED || FS == IFRIT_FS_TEXTURED_LOD0 || FS == IFRIT_FS_TEXTURED_FAST || FS == IFRIT_FS_TEXTURED_LOD0_FAST ||
+        FS == IFRIT_FS_TEXTURED_RA || FS == IFRIT_FS_TEXTURED_FAST_RA) {
+        constexpr bool FAST = FS == IFRIT_FS_TEXTURED_FAST || FS == IFRIT_FS_TEXTURED_LOD0_FAST || FS == IFRIT_FS_TEXTURED_FAST_RA;
         float4 c;
-        if (FS == IFRIT_FS_TEXTURED || FS == IFRIT_FS_TEXTURED_FAST)
+        if (FS == IFRIT_FS_TEXTURED_RA || FS == IFRIT_FS_TEXTURED_FAST_RA)
+            c = sample_aniso_repeat<FAST>(p.tex[0], p.samp[0].maxAniso, v[1].x, v[1].y, make_float2(ddx[1].x, ddx[1].y),
+                                          make_float2(ddy[1].x, ddy[1].y), u[20]);
+        else if (FS == IFRIT_FS_TEXTURED || FS == IFRIT_FS_TEXTURED_FAST)
             c = tex_grad<FAST>(p.tex[0], p.samp[0], v[1].x, v[1].y, make_float2(ddx[1].x, ddx[1].y),
-                               make_float2(ddy[1].x, ddy[1].y), __ldg(u + 20), FAST ? 1 : 0);
+                               make_float2(ddy[1].x, ddy[1].y), u[20], FAST ? 1 : 0);
         else
             c = sample_trilinear(p.tex[0], p.samp[0], 0, v[1].x, v[1].y, 0, 0, 0.0f, FAST ? 1 : 0);
         const float nx = v[0].x, ny = v[0].y, nz = v[0].z;
         const float len2 = fmaf(nz, nz, fmaf(ny, ny, nx * nx));
-        const float dot = fmaf(nz, __ldg(u + 18), fmaf(ny, __ldg(u + 17), nx * __ldg(u + 16)));
+        const float dot = fmaf(nz, u[18], fmaf(ny, u[17], nx * u[16]));
         float ndl = FAST ? dot * rsqrt_fast(len2) : dot / sqrtf(len2);
         ndl = fmaxf(ndl, 0.2f);
         return make_float4(c.x * ndl, c.y * ndl, c.z * ndl, 1.0f);
     }
-    if (FS == IFRIT_FS_SKYBOX) return sample_cube(p.tex[0], p.samp[0], v[0].x, v[0].y, v[0].z, __ldg(u + 20));
+    if (FS == IFRIT_FS_SKYBOX) return sample_cube(p.tex[0], p.samp[0], v[0].x, v[0].y, v[0].z, u[20]);
     if (FS == IFRIT_FS_DERIV_VIS) {
-        const float sc = __ldg(u + 21);
+        const float sc = u[21];
         return make_float4(ddx[1].x * sc, ddx[1].y * sc, ddy[1].x * sc, ddy[1].y * sc);
     }
     return make_float4(0, 0, 0, 0);

@@ -579,26 +579,35 @@ def test_unsynchronised_draws_with_growing_pair_count(gpu_renderer_factory):
     from ifrit_v2_b200 import renderer as R
     W, H = 640, 360
     r2 = gpu_renderer_factory()
-    vb, idx = scenes.mesh_sphere(n=48)
+    vb, idx = scenes.mesh_sphere(n=96)
     host = np.zeros((H, W, 4), np.float32)
     r2.bindFrameBuffer(host, None, W, H, useDoubleBuffer=True)
-    eyes = [(0.0, 0.0, 9.0), (0.0, 0.0, 4.0), (0.0, 0.0, 2.2), (0.0, 0.0, 1.6), (0.0, 0.0, 1.6)]
-    exp, pairs = [], []
+    eyes = [(0.0, 0.0, 30.0), (0.0, 0.0, 8.0), (0.0, 0.0, 3.0), (0.0, 0.0, 1.7), (0.0, 0.0, 1.7)]
     R.setup_scene(r2, vb, idx, 1, O.FS_NORMAL_COLOR, 2, scenes.uniform_block(scenes.default_mvp(W, H, eye=eyes[0])))
-    r2.SetCullMode(2)
     r2.setClearValues([(.1, .2, .3, 1)], 1.0)
+    r2.clear()
+    r2.drawElements()
+    first_pairs = r2.stats()["tile_pairs"]         # (synchronises) the far view, before the streamed sequence
+    exp = []
     for k, eye in enumerate(eyes):
         u = scenes.uniform_block(scenes.default_mvp(W, H, eye=eye))
-        exp.append(oracle_draw(W, H, vb, idx, 1, O.FS_NORMAL_COLOR, 2, u, cull=2, clear_color=(.1, .2, .3, 1))["color"])
-        r2.copyHostBufferToBuffer(u, 0)            # new MVP, no synchronize
+        exp.append(oracle_draw(W, H, vb, idx, 1, O.FS_NORMAL_COLOR, 2, u, clear_color=(.1, .2, .3, 1))["color"])
+        r2.copyHostBufferToBuffer(u, 0)            # new MVP, no synchronize between the draws
         r2.clear()
         r2.drawElements()
-        if k >= 1:
-            # frame k - 1 arrives in the host image while frame k renders; wait for that copy only
-            r2.synchronize()
-            assert np.array_equal(host.view(np.uint32), exp[k - 1].view(np.uint32)), f"frame {k - 1} incomplete"
-            pairs.append(r2.stats()["tile_pairs"])
-    assert pairs[-1] > 2 * pairs[0]
+    r2.synchronize()
+    # double buffered: the host image holds the frame before the last one, the device the last one
+    assert np.array_equal(host.view(np.uint32), exp[-2].view(np.uint32)), "frame before last incomplete"
+    assert np.array_equal(r2.readColor().view(np.uint32), exp[-1].view(np.uint32)), "last frame incomplete"
+    assert r2.stats()["tile_pairs"] > 2 * first_pairs
+    # and every intermediate frame, one by one, without a synchronize between its draw and the next
+    for k in range(1, len(eyes)):
+        for j in (k - 1, k):
+            r2.copyHostBufferToBuffer(scenes.uniform_block(scenes.default_mvp(W, H, eye=eyes[j])), 0)
+            r2.clear()
+            r2.drawElements()
+        r2.synchronize()
+        assert np.array_equal(host.view(np.uint32), exp[k - 1].view(np.uint32)), f"frame {k - 1} incomplete"
     r2.close()
 
 

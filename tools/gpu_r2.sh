@@ -28,7 +28,7 @@ try:
     for k,v in o.get('extra_configs',{}).items():
         if 'error' in v: print(k, v)
         else: show(k, v)
-    print('fast', o.get('fast_sampler'))
+    print("exact", o.get("exact_sampler"))
     if 'cpu_baseline' in o: print('cpu', o['cpu_baseline'])
 except Exception as e: print('parse fail', e)
 PY
