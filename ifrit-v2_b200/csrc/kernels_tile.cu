@@ -1,686 +1,5 @@
-// kernels_tile.cu — the per-tile raster + early-Z + quad shading + MSAA resolve kernel.
-//
-// One CTA (256 threads) owns one 16x16 screen tile from coverage through resolve; per-sample
-// visibility keys live in shared memory, so HBM sees the framebuffer once (written once when the
-// clear is fused).  Replaces, in one kernel:
-//   secondBinnerWorklistRasterizerKernel CU:1254 + devFinerTilingRasterizationChildProcess CU:892
-//       -> coverage: exact integer edge functions per sample (small triangles: one thread per
-//          triangle + shared-memory atomicMin; large triangles: one thread per pixel)
-//   pixelTaggingExecKernel CU:1901  -> order-independent 64-bit (depth, slot) keys in shared memory
-//   pixelShadingExecKernel CU:2145  -> 2x2 quads = 4 consecutive lanes, ddx/ddy by __shfl_xor
-//   pixelMultisampleCoverageModulationKernel CU:2319 -> resolve from the shared-memory keys
-//   imageResetFloat32{Mono,RGBA}Kernel CU:3337/3363 -> fused clear
-#include "common.cuh"
-#include "tri_setup.cuh"
-#include "sampler.cuh"
-
-// ---- visibility keys (identical to oracle/ifrit_oracle.c key_*) --------------------------------
-// LESS (mono(d), slot+1) / LESS_OR_EQUAL (mono(d), ~(slot+1)) / GREATER, GREATER_OR_EQUAL with ~mono /
-// ALWAYS and EQUAL (slot+1, depth bits); the minimum key wins.  The compare op is folded into two xor
-// masks so that the hot loops carry no switch.
-struct KeyMode { uint32_t xhi, xlo; bool ordered, equal, never; };
-__device__ __forceinline__ KeyMode key_mode(int func) {
-    KeyMode m;
-    m.ordered = func == IF_COMPARE_OP_LESS || func == IF_COMPARE_OP_LESS_OR_EQUAL || func == IF_COMPARE_OP_GREATER ||
-                func == IF_COMPARE_OP_GREATER_OR_EQUAL;
-    m.xhi = (func == IF_COMPARE_OP_GREATER || func == IF_COMPARE_OP_GREATER_OR_EQUAL) ? 0xffffffffu : 0u;
-    m.xlo = (func == IF_COMPARE_OP_LESS_OR_EQUAL || func == IF_COMPARE_OP_GREATER_OR_EQUAL) ? 0xffffffffu : 0u;
-    m.equal = func == IF_COMPARE_OP_EQUAL;
-    m.never = !m.ordered && !m.equal && func != IF_COMPARE_OP_ALWAYS;
-    return m;
-}
-__device__ __forceinline__ unsigned long long key_init(const KeyMode& m, float d0) {
-    if (m.ordered) return ((unsigned long long)(mono(d0) ^ m.xhi) << 32) | m.xlo;
-    return ((unsigned long long)0xffffffffu << 32) | __float_as_uint(d0 + 0.0f);
-}
-__device__ __forceinline__ bool key_make(const KeyMode& m, float d, float d0, uint32_t slot, unsigned long long& k) {
-    if (m.ordered) { k = ((unsigned long long)(mono(d) ^ m.xhi) << 32) | ((slot + 1u) ^ m.xlo); return true; }
-    if (m.never || (m.equal && !(d == d0))) return false;
-    k = ((unsigned long long)(slot + 1u) << 32) | __float_as_uint(d + 0.0f);
-    return true;
-}
-__device__ __forceinline__ uint32_t key_slot(const KeyMode& m, unsigned long long k) {   // IFR_SLOT_NONE if empty
-    if (m.ordered) { const uint32_t s = (uint32_t)k ^ m.xlo; return s == 0 ? IFR_SLOT_NONE : s - 1; }
-    const uint32_t s = (uint32_t)(k >> 32);
-    return s == 0xffffffffu ? IFR_SLOT_NONE : s - 1;
-}
-
-__device__ __forceinline__ bool scissor_pass(const DrawParams& p, int x, int y) {
-    if (!p.scissorEnable || p.nScissor == 0) return true;
-    for (int i = 0; i < p.nScissor; i++) {
-        const float* s = p.scissor[i];
-        if ((float)x >= s[0] && (float)x <= s[0] + s[2] && (float)y >= s[1] && (float)y <= s[1] + s[3]) return true;
-    }
-    return false;
-}
-
-// coverage mask of the pixel whose origin is (ci, cj) = (16 lx, 16 ly) in 1/16 px, over the S samples
-template <int S>
-__device__ __forceinline__ uint32_t coverage(const DrawParams& p, const int dX[3], const int dY[3], const int T[3],
-                                             const long long E0[3], int wide, int ci, int cj) {
-    uint32_t mask = 0;
-    if (!wide) {
-#pragma unroll
-        for (int k = 0; k < S; k++) {
-            const int i = ci + p.sampX[k], j = cj + p.sampY[k];
-            const bool in = (dX[0] * j - dY[0] * i >= T[0]) && (dX[1] * j - dY[1] * i >= T[1]) &&
-                            (dX[2] * j - dY[2] * i >= T[2]);
-            mask |= (uint32_t)in << k;
-        }
-    } else {
-        for (int k = 0; k < S; k++) {
-            const long long i = ci + p.sampX[k], j = cj + p.sampY[k];
-            bool in = true;
-#pragma unroll
-            for (int e = 0; e < 3; e++) in = in && (E0[e] + 16 * (dX[e] * j - dY[e] * i) > 0);
-            mask |= (uint32_t)in << k;
-        }
-    }
-    return mask;
-}
-
-// depth at the integer pixel (lx, ly): beta_i = E_i(corner) / d, from exact integer edge values
-__device__ __forceinline__ float depth_at(const int dX[3], const int dY[3], const long long E0[3], uint32_t flags, float ar,
-                                          float z0, float z1, float z2, int lx, int ly) {
-    float beta[3];
-    if (flags & IFR_FLAG_FITS32) {
-        // triangle-level bound: the edge values at this corner fit int32 -> wrapping 32-bit arithmetic, I2F.S32
-#pragma unroll
-        for (int e = 0; e < 3; e++) {
-            const uint32_t Ec = (uint32_t)E0[e] + (((uint32_t)dX[e] * (uint32_t)ly - (uint32_t)dY[e] * (uint32_t)lx) << 8);
-            beta[e] = __fmul_rn((float)(int)Ec, ar);
-        }
-    } else {
-#pragma unroll
-        for (int e = 0; e < 3; e++) {
-            const long long Ec = E0[e] + 256 * ((long long)dX[e] * ly - (long long)dY[e] * lx);
-            beta[e] = __fmul_rn((float)Ec, ar);
-        }
-    }
-    return fmaf(z2, beta[2], fmaf(z1, beta[1], __fmul_rn(z0, beta[0])));
-}
-
-// tile-local pixel -> key index = index of the owning thread (warp = 8x4 block, 4 consecutive lanes = 2x2 quad)
-__device__ __forceinline__ int pix_index(int lx, int ly) {
-    return (((ly >> 2) * 2 + (lx >> 3)) << 5) + ((((ly >> 1) & 1) * 4 + ((lx >> 1) & 3)) << 2) + (ly & 1) * 2 + (lx & 1);
-}
-
-__device__ __forceinline__ void key_min_shared(unsigned long long* addr, unsigned long long k) {
-    if (k < *reinterpret_cast<volatile unsigned long long*>(addr)) atomicMin(addr, k);
-}
-
-
-// ---- attribute interpolation at an integer pixel (pixelShadingExecKernel CU:2168-2215) ---------
-// Perspective weights (u, v, 1 - (u + v)) of the clip-space barycentrics from the three edge values at a pixel
-// corner; beta_i = float(E_i) * ar is also what the depth plane uses.
-struct PixW { float u, v, w2; };
-// FASTW (the FAST textured shaders only — colour within 1/255, depth is not computed from these): SFU reciprocal, and the
-// unclipped barycentric mapping as plain selects instead of fma chains with 0 / 1 factors
-template <bool FASTW>
-__device__ __forceinline__ PixW persp_weights(const float beta[3], const float IW[3], uint32_t flags, const float* cb) {
-    float b0 = __fmul_rn(beta[0], IW[0]), b1 = __fmul_rn(beta[1], IW[1]), b2 = __fmul_rn(beta[2], IW[2]);
-    const float sum = __fadd_rn(__fadd_rn(b0, b1), b2);
-    const float inv = FASTW ? rcp_fast(sum) : __frcp_rn(sum);
-    b0 = __fmul_rn(b0, inv); b1 = __fmul_rn(b1, inv); b2 = __fmul_rn(b2, inv);
-    PixW w;
-    if (flags & IFR_FLAG_CLIPPED) {
-        w.u = fmaf(b2, cb[4], fmaf(b1, cb[2], __fmul_rn(b0, cb[0])));
-        w.v = fmaf(b2, cb[5], fmaf(b1, cb[3], __fmul_rn(b0, cb[1])));
-    } else {
-        // unclipped: clip barycentrics are those of (v2, v3, v1) of the input triangle, first and last
-        // exchanged by a cull swap: B = {(0,1),(0,0),(1,0)} or {(1,0),(0,0),(0,1)}.  The fma chains with
-        // exact 0 / 1 factors reduce to (x * 1 + 0 * y + 0) = x up to the sign of zero, which + 0.0f fixes.
-        const bool sw = flags & IFR_FLAG_SWAPPED;
-        if (FASTW) { w.u = sw ? b0 : b2; w.v = sw ? b2 : b0; }
-        else {
-            const float B00 = sw ? 1.0f : 0.0f, B01 = sw ? 0.0f : 1.0f;
-            w.u = fmaf(b2, B01, fmaf(b1, 0.0f, __fmul_rn(b0, B00)));
-            w.v = fmaf(b2, B00, fmaf(b1, 0.0f, __fmul_rn(b0, B01)));
-        }
-    }
-    w.w2 = __fsub_rn(1.0f, __fadd_rn(w.u, w.v));
-    return w;
-}
-__device__ __forceinline__ float4 mix3(const float4& v0, const float4& v1, const float4& v2, const PixW& w) {
-    float4 o;
-    o.x = fmaf(v2.x, w.w2, fmaf(v1.x, w.v, __fmul_rn(v0.x, w.u)));
-    o.y = fmaf(v2.y, w.w2, fmaf(v1.y, w.v, __fmul_rn(v0.y, w.u)));
-    o.z = fmaf(v2.z, w.w2, fmaf(v1.z, w.v, __fmul_rn(v0.z, w.u)));
-    o.w = fmaf(v2.w, w.w2, fmaf(v1.w, w.v, __fmul_rn(v0.w, w.u)));
-    return o;
-}
-
-// Interpolates slot's varyings at pixel (px, py).  DERIV: also at the two other pixels the 2x2 quad's coarse
-// derivatives need — the horizontal and the vertical neighbour inside the screen-aligned quad (SB:36-76:
-// ddx = right - left of the lane's row, ddy = bottom - top of its column).  The lane evaluates its neighbours'
-// values itself from the same integer edge functions (E steps by -256 dY / +256 dX per pixel), which is
-// bit-identical to what a helper lane would compute, so a pixel shades alone: no helper invocations, no
-// quad-uniform control flow, every FS pass runs with all of its lanes useful.
-template <int NV, bool DERIV, bool FASTW = false>
-__device__ __forceinline__ void interp(const DrawParams& p, uint32_t slot, int px, int py, float4* out, float4* ddx,
-                                       float4* ddy, float& depth, int& prim, int& fan) {
-    const int4* r = reinterpret_cast<const int4*>(p.rec + slot);
-    int X[3], Y[3];
-    float Z[3], IW[3];
-#pragma unroll
-    for (int j = 0; j < 3; j++) {
-        const int4 v = __ldg(r + j);
-        X[j] = v.x; Y[j] = v.y; Z[j] = __int_as_float(v.z); IW[j] = __int_as_float(v.w);
-    }
-    const int4 w3 = __ldg(r + 3);
-    const float ar = __int_as_float(w3.x);
-    const uint32_t flags = (uint32_t)w3.y;
-    fan = slot >= (uint32_t)p.ntri;
-    prim = fan ? (int)(slot - (uint32_t)p.ntri) : (int)slot;
-    int idx[3];
-    if (NV > 0) {
-#pragma unroll
-        for (int j = 0; j < 3; j++) idx[j] = __ldg(p.ib + 3 * (size_t)prim + j);
-    }
-    const int sx = px * IFR_SUBPIX, sy = py * IFR_SUBPIX;
-    const int hs = (px & 1) ? -IFR_SUBPIX : IFR_SUBPIX, vs = (py & 1) ? -IFR_SUBPIX : IFR_SUBPIX;   // towards the quad neighbours
-    float beta[3], betaH[3], betaV[3];
-    if (flags & IFR_FLAG_FITS32) {
-        // the edge values fit int32 (triangle-level bound, two pixels around any covered sample): wrapping
-        // 32-bit arithmetic is exact
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-            const int a = (i + 1) % 3, b = (i + 2) % 3;
-            const uint32_t dx = (uint32_t)(X[b] - X[a]), dy = (uint32_t)(Y[b] - Y[a]);
-            const uint32_t E = dx * (uint32_t)(sy - Y[a]) - dy * (uint32_t)(sx - X[a]);
-            beta[i] = __fmul_rn((float)(int)E, ar);
-            if (DERIV) {
-                betaH[i] = __fmul_rn((float)(int)(E - dy * (uint32_t)hs), ar);
-                betaV[i] = __fmul_rn((float)(int)(E + dx * (uint32_t)vs), ar);
-            }
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-            const int a = (i + 1) % 3, b = (i + 2) % 3;
-            const long long dx = X[b] - X[a], dy = Y[b] - Y[a];
-            const long long E = dx * (long long)(sy - Y[a]) - dy * (long long)(sx - X[a]);
-            beta[i] = __fmul_rn((float)E, ar);
-            if (DERIV) {
-                betaH[i] = __fmul_rn((float)(E - dy * hs), ar);
-                betaV[i] = __fmul_rn((float)(E + dx * vs), ar);
-            }
-        }
-    }
-    depth = fmaf(Z[2], beta[2], fmaf(Z[1], beta[1], __fmul_rn(Z[0], beta[0])));
-    if (NV == 0) return;
-    float cb[6] = {0, 0, 0, 0, 0, 0};
-    if (flags & IFR_FLAG_CLIPPED) {
-        const float* g = p.clipBary + (size_t)slot * 6;
-#pragma unroll
-        for (int j = 0; j < 6; j++) cb[j] = __ldg(g + j);
-    }
-    const PixW w = persp_weights<FASTW>(beta, IW, flags, cb);
-    PixW wh = w, wv = w;
-    if (DERIV) { wh = persp_weights<FASTW>(betaH, IW, flags, cb); wv = persp_weights<FASTW>(betaV, IW, flags, cb); }
-    const bool right = px & 1, bottom = py & 1;
-#pragma unroll
-    for (int k = 0; k < NV; k++) {
-        if (k >= p.nvary) {
-            out[k] = make_float4(0, 0, 0, 0);
-            if (DERIV) { ddx[k] = out[k]; ddy[k] = out[k]; }
-            continue;
-        }
-        const uint8_t* vb = p.varyBase + p.varyOff[k];
-        const float4 v0 = __ldg(reinterpret_cast<const float4*>(vb + (size_t)idx[0] * p.varyStride)),
-                     v1 = __ldg(reinterpret_cast<const float4*>(vb + (size_t)idx[1] * p.varyStride)),
-                     v2 = __ldg(reinterpret_cast<const float4*>(vb + (size_t)idx[2] * p.varyStride));
-        const float4 a = mix3(v0, v1, v2, w);
-        out[k] = a;
-        if (DERIV) {
-            const float4 o1 = mix3(v0, v1, v2, wh), o2 = mix3(v0, v1, v2, wv);
-            ddx[k] = right ? make_float4(a.x - o1.x, a.y - o1.y, a.z - o1.z, a.w - o1.w)
-                           : make_float4(o1.x - a.x, o1.y - a.y, o1.z - a.z, o1.w - a.w);
-            ddy[k] = bottom ? make_float4(a.x - o2.x, a.y - o2.y, a.z - o2.z, a.w - o2.w)
-                            : make_float4(o2.x - a.x, o2.y - a.y, o2.z - a.z, o2.w - a.w);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-#define IFR_CHUNK 256
-#define IFR_BIG_CHUNK 64     // big-queue entries staged per bulk copy (6 KB), double buffered
-
-// ---- TMA bulk copy (global -> shared) completing on an mbarrier -----------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!done);
-}
-
-// ---- big triangles: setups precomputed by the fill pass arrive by TMA bulk copy (double buffered); every thread
-//      tests its own pixel against broadcast LDS.128 words, warps run independently.
-// HIZ (deep queues, ordered compare ops): hierarchical early-Z one level above the pixel.  wfar = the worst (largest)
-// key depth word any sample of this warp's 8x4 block currently holds; a triangle whose most optimistic key inside the
-// tile (TriS pad[1], computed by setup_hiz on the staged entries) lies above it cannot win a single sample of the
-// block and is skipped by the whole warp.  One level further up, entries that cannot win anywhere in the tile
-// (bound above every warp's wfar) are dropped while the chunk is prepared: the warps only walk the compacted
-// survivor list.  Results are unchanged (the reference has no Hi-Z: curTileHierZ is an unused field,
-// TileRasterWorker.h:80).
-struct HizShared { uint32_t warpFar[8]; uint32_t nSurv[2]; uint8_t surv[2][32]; };
-
-template <int S>
-__device__ __forceinline__ uint32_t block_far(const unsigned long long* keys, int tid, unsigned long long best, bool uni) {
-    uint32_t mine;
-    if (S == 1 || uni) mine = (uint32_t)(best >> 32);
-    else {
-        mine = 0;
-#pragma unroll
-        for (int sm = 0; sm < S; sm++) mine = max(mine, (uint32_t)(keys[sm * IFR_TILE_PIX + tid] >> 32));
-    }
-    return __reduce_max_sync(0xffffffffu, mine);
-}
-
-// one big-queue entry against this thread's pixel; returns true if a key of the pixel changed
-template <int S, bool HIZ>
-__device__ __forceinline__ bool big_test(const DrawParams& p, const KeyMode& km, unsigned long long* keys, const int4* t4, uint32_t cz,
-                                         int tid, int wrp, int lx, int ly, bool scis, float d0, unsigned long long& best, bool& uni) {
-    const int ci = 16 * lx, cj = 16 * ly;
-    const int4 A = t4[0];
-    const int4 B = t4[1], C = t4[2];
-    const int dX[3] = {A.x, A.y, A.z}, dY[3] = {B.x, B.y, B.z}, T[3] = {C.x, C.y, C.z};
-    const uint32_t flags = (uint32_t)C.w;
-    uint32_t m = 0;
-    bool upd = false;
-    if (HIZ && ((cz >> (8 + wrp)) & 1)) {
-        if (scis) m = (1u << S) - 1u;          // trivial accept: every sample of the block
-    } else if (!(flags & IFR_FLAG_WIDE)) {
-        if (scis) m = coverage<S>(p, dX, dY, T, nullptr, 0, ci, cj);
-    }
-    if (m || (flags & IFR_FLAG_WIDE)) {
-        const int4 D = t4[3], E = t4[4];
-        const long long E0[3] = {(long long)(((unsigned long long)(uint32_t)D.y << 32) | (uint32_t)D.x),
-                                 (long long)(((unsigned long long)(uint32_t)D.w << 32) | (uint32_t)D.z),
-                                 (long long)(((unsigned long long)(uint32_t)E.y << 32) | (uint32_t)E.x)};
-        if (!m && scis) m = coverage<S>(p, dX, dY, T, E0, 1, ci, cj);
-        if (m) {
-            const float2 Zr = *reinterpret_cast<const float2*>(t4 + 5);
-            const float d = depth_at(dX, dY, E0, flags, __int_as_float(E.z), __int_as_float(E.w), Zr.x, Zr.y, lx, ly);
-            unsigned long long k;
-            if (key_make(km, d, d0, (uint32_t)B.w, k)) {
-                if (S == 1) {
-                    if (k < best) { best = k; upd = true; }
-                } else if (uni) {
-                    // every sample of the pixel still holds the same key (`best`, in a register: pixels inside one
-                    // triangle never touch shared memory); the first partially covering winner materialises it
-                    if (k < best) {
-                        upd = true;
-                        if (m == (1u << S) - 1u) best = k;
-                        else {
-#pragma unroll
-                            for (int sm = 0; sm < S; sm++) keys[sm * IFR_TILE_PIX + tid] = ((m >> sm) & 1) ? k : best;
-                            uni = false;
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int sm = 0; sm < S; sm++)
-                        if (((m >> sm) & 1) && k < keys[sm * IFR_TILE_PIX + tid]) { keys[sm * IFR_TILE_PIX + tid] = k; upd = true; }
-                }
-            }
-        }
-    }
-    return upd;
-}
-
-template <int S, bool HIZ>
-__device__ __forceinline__ void big_loop(const DrawParams& p, const KeyMode& km, unsigned long long* keys, TriS (*bigBuf)[IFR_BIG_CHUNK],
-                                         uint64_t* mbar, HizShared& hz, const TriS* bigSrc, uint32_t nBig, int tid, int wrp, int lx,
-                                         int ly, bool scis, float d0, unsigned long long& best, bool& uni) {
-    const int lane = tid & 31;
-    uint32_t wfar = 0xffffffffu;
-    if (HIZ) {
-        wfar = block_far<S>(keys, tid, best, uni);
-        // published for the chunk preparation of warps 0 / 1, which may run concurrently: a stale value is larger, hence
-        // conservative; the bound only ever shrinks, so the publication is an atomicMin and the readers use atomics too
-        // (compute-sanitizer racecheck: no hazards)
-        if (lane == 0) atomicMin(&hz.warpFar[wrp], wfar);
-    }
-    const uint32_t nchunks = (nBig + IFR_BIG_CHUNK - 1) / IFR_BIG_CHUNK;
-    for (uint32_t c = 0; c < nchunks; c++) {
-        if (tid == 0 && c + 1 < nchunks) {
-            const uint32_t cnt1 = min(nBig - (c + 1) * IFR_BIG_CHUNK, (uint32_t)IFR_BIG_CHUNK);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            bulk_load(bigBuf[(c + 1) & 1], bigSrc + (size_t)(c + 1) * IFR_BIG_CHUNK, cnt1 * (uint32_t)sizeof(TriS), &mbar[(c + 1) & 1]);
-        }
-        mbar_wait(&mbar[c & 1], (c >> 1) & 1);
-        const uint32_t cnt = min(nBig - c * IFR_BIG_CHUNK, (uint32_t)IFR_BIG_CHUNK);
-        const int4* chunk = reinterpret_cast<const int4*>(bigBuf[c & 1]);
-        if (!HIZ) {
-            const int4* t4 = chunk;
-            for (uint32_t b = 0; b < cnt; b++, t4 += 6) {
-                // warp-uniform coarse reject: the fill pass rasterised the triangle against the tile's 8x4 blocks
-                const uint32_t cz = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(t4) + 88);
-                if (!((cz >> wrp) & 1)) continue;
-                big_test<S, false>(p, km, keys, t4, cz, tid, wrp, lx, ly, scis, d0, best, uni);
-            }
-        } else {
-            // chunk preparation, warps 0 and 1, one thread per staged entry: trivial-accept blocks + key bound written
-            // back into the staged copy, entries that can still win somewhere in the tile compacted per warp
-            if (tid < IFR_BIG_CHUNK) {
-                bool alive = false;
-                if ((uint32_t)tid < cnt) {
-                    uint32_t tileFar = 0;
-#pragma unroll
-                    for (int w = 0; w < 8; w++) tileFar = max(tileFar, atomicOr(&hz.warpFar[w], 0u));
-                    TriS* e = &bigBuf[c & 1][tid];
-                    const uint32_t tb = setup_hiz(e, p.sampMinX, p.sampMaxX, p.sampMinY, p.sampMaxY, km.xhi);
-                    alive = ((uint32_t)e->pad[0] & 0xffu) != 0 && tb <= tileFar;
-                }
-                const unsigned bal = __ballot_sync(0xffffffffu, alive);
-                if (alive) hz.surv[wrp][__popc(bal & ((1u << lane) - 1u))] = (uint8_t)tid;
-                if (lane == 0) hz.nSurv[wrp] = __popc(bal);
-            }
-            __syncthreads();
-            for (int half = 0; half < 2; half++) {
-                const uint32_t ns = hz.nSurv[half];
-                for (uint32_t i = 0; i < ns; i++) {
-                    const int4* t4 = chunk + 6 * (int)hz.surv[half][i];
-                    const uint2 cz = *reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(t4) + 88);
-                    if (!((cz.x >> wrp) & 1)) continue;
-                    if (cz.y > wfar) continue;          // warp-uniform Hi-Z reject
-                    const bool upd = big_test<S, true>(p, km, keys, t4, cz.x, tid, wrp, lx, ly, scis, d0, best, uni);
-                    if (__any_sync(0xffffffffu, upd)) {  // warp-convergent: every reject above is warp-uniform
-                        wfar = block_far<S>(keys, tid, best, uni);
-                        if (lane == 0) atomicMin(&hz.warpFar[wrp], wfar);
-                    }
-                }
-            }
-        }
-        // the staged buffer (and, with HIZ, the survivor lists) are rewritten by the next iteration's preparation / the
-        // bulk copy issued at the top of iteration c + 1
-        if (HIZ ? (c + 1 < nchunks) : (c + 2 < nchunks)) __syncthreads();
-    }
-}
-
-// A tile with nothing binned: the fused clear is all there is to do (imageResetFloat32* CU:3337/3363).  Thread = pixel,
-// row-major inside the tile: a warp writes two full 256-byte colour rows.
-template <int S>
-__device__ __forceinline__ void clear_tile(const DrawParams& p, int tileX, int tileY, int tid) {
-    const int px = tileX * IFR_TILE + (tid & 15), py = tileY * IFR_TILE + (tid >> 4);
-    if (px >= p.W || py >= p.H) return;
-    const size_t pidx = (size_t)py * p.W + px;
-    const bool scis = scissor_pass(p, px, py);
-    if (!p.doClear || !scis) {
-        if (p.present) p.present[pidx] = ifr_pack_rgba8(p.color[pidx]);   // untouched pixel: present what is there
-        if (!p.doClear) return;
-    }
-    if (scis) {
-        const float4 cc = make_float4(p.clearColor[0], p.clearColor[1], p.clearColor[2], p.clearColor[3]);
-        p.color[pidx] = cc;
-        p.depth[pidx] = p.clearDepth;
-        if (p.present) p.present[pidx] = ifr_pack_rgba8(cc);
-    }
-    if (p.primIds) {
-#pragma unroll
-        for (int s = 0; s < S; s++) p.primIds[pidx * S + s] = -1;
-    }
-}
-
-#ifndef IFR_MINB1
-#define IFR_MINB1 6
-#endif
-// resident CTAs per SM the register budget is cut for.  Measured (profiles/r01d_ab.txt): the 1x textured kernels are
-// latency bound on the texture fetches — 6 CTAs (40 registers, some spills) beat 4 by 4 %; the plain-varying 1x
-// kernels (small-triangle soup) lose 20 % with more than 4; the multisampled variants keep 64 registers.
-#ifndef IFR_MINB8
-#define IFR_MINB8 4
-#endif
-template <int FS, int S>
-__global__ void __launch_bounds__(256, FsTraits<FS>::needsDerivs ? (S == 1 ? IFR_MINB1 : IFR_MINB8) : 4) tile_kernel(const __grid_constant__ DrawParams p) {
-    extern __shared__ unsigned long long keys[];        // [S][256], index = owning thread
-    __shared__ __align__(128) TriS bigBuf[2][IFR_BIG_CHUNK];
-    __shared__ __align__(8) uint64_t mbar[2];
-    __shared__ HizShared hz;
-    constexpr int NV = FsTraits<FS>::nv;
-
-    // Work list (scan pass): CTA b < nWork takes a tile with a non-empty queue; the CTAs behind them share the owned tiles
-    // with nothing binned, IFR_EMPTY_PER_CTA each (fused clear only); tiles of other ranks appear in neither list.
-    const int ntiles = p.tilesX * p.tilesY;
-    const int tid = threadIdx.x;
-    const ulonglong2 hdr = *reinterpret_cast<const ulonglong2*>(p.counters + 2);   // {nWork, overflow flag}
-    const uint32_t nWork = (uint32_t)hdr.x;
-    const bool overflow = hdr.y != 0;
-    if (blockIdx.x >= nWork) {
-        const uint32_t e0 = (blockIdx.x - nWork) * IFR_EMPTY_PER_CTA;
-        const uint32_t nEmpty = (uint32_t)p.counters[7];
-        for (uint32_t e = e0; e < min(e0 + IFR_EMPTY_PER_CTA, nEmpty); e++) {
-            const uint32_t t = p.tileOrder[ntiles - 1 - (int)e];
-            clear_tile<S>(p, (int)(t & 0xffffu), (int)(t >> 16), tid);
-        }
-        return;
-    }
-    const uint32_t torder = p.tileOrder[blockIdx.x];
-    const int tileX = (int)(torder & 0xffffu), tileY = (int)(torder >> 16);
-    const int tile = tileY * p.tilesX + tileX;
-    if (overflow) {    // a queue is too small: the host re-issues the draw with larger ones; until then the frame is cleared only
-        clear_tile<S>(p, tileX, tileY, tid);
-        return;
-    }
-    // a warp owns one 8x4-pixel block of the tile (block = warp: x = (w & 1) * 8, y = (w >> 1) * 4), a quad = 4 lanes
-    const int wrp = tid >> 5, q = (tid >> 2) & 7, l = tid & 3;
-    // under the 40-register budget of the 1x kernels the compiler re-derives lx / ly from the thread id (a dozen bit
-    // operations) at every use inside the hot loops; an opaque packed copy makes it keep (or at worst reload) the value
-    int lxy = ((wrp & 1) * 8 + (q & 3) * 2 + (l & 1)) | (((wrp >> 1) * 4 + (q >> 2) * 2 + (l >> 1)) << 16);
-    asm volatile("" : "+r"(lxy));
-    const int lx = lxy & 0xffff, ly = lxy >> 16;
-    const int px = tileX * IFR_TILE + lx, py = tileY * IFR_TILE + ly;
-    const bool inFrame = px < p.W && py < p.H;
-    const bool scis = inFrame && scissor_pass(p, px, py);
-    const uint32_t sStart = p.tileStart[tile], bStart = p.tileStart[ntiles + 1 + tile];
-    const uint32_t nSmall = p.tileStart[tile + 1] - sStart;
-    const uint32_t nBig = p.tileStart[ntiles + 1 + tile + 1] - bStart;
-    const size_t pidx = (size_t)py * p.W + px;
-
-    KeyMode km;     // precomputed by the host from p.depthFunc (same table as key_mode)
-    km.xhi = p.keyXhi; km.xlo = p.keyXlo; km.ordered = p.keyOrdered != 0; km.equal = p.keyEqual != 0; km.never = p.keyNever != 0;
-    float d0 = 0.0f;
-    if (inFrame) d0 = (p.doClear && scis) ? p.clearDepth : p.depth[pidx];
-    const unsigned long long k0 = key_init(km, d0);
-    // Per-sample visibility keys.  S == 1: the pixel's key lives in a register (`best`); shared memory is only the
-    // mailbox through which small triangles (processed by other threads) reach this pixel, filled from `best`
-    // once the big triangles are done.
-    // S > 1: while every sample of the pixel holds the same key it lives in `best` too (`uni`); the per-sample keys in
-    // shared memory are only written once a triangle covers the pixel partially (or a small-triangle pass follows).
-    unsigned long long best = k0;
-    bool uni = true;
-    const bool deep = km.ordered && nBig >= IFR_HIZ_MIN_QUEUE;
-
-    // ---- big triangles first: their result gives the small-triangle pass a far bound per 8x4 block ----
-    if (nBig) {
-        if (tid == 0) {
-            mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        if (tid < 8) hz.warpFar[tid] = 0xffffffffu;
-        __syncthreads();      // mbarriers initialised
-        const TriS* bigSrc = p.bigQueue + bStart;
-        if (tid == 0) bulk_load(bigBuf[0], bigSrc, min(nBig, (uint32_t)IFR_BIG_CHUNK) * (uint32_t)sizeof(TriS), &mbar[0]);
-#ifndef IFR_NO_HIZ
-        if (deep) big_loop<S, true>(p, km, keys, bigBuf, mbar, hz, bigSrc, nBig, tid, wrp, lx, ly, scis, d0, best, uni);
-        else
-#endif
-            big_loop<S, false>(p, km, keys, bigBuf, mbar, hz, bigSrc, nBig, tid, wrp, lx, ly, scis, d0, best, uni);
-    }
-
-    // ---- small triangles: one thread per (triangle, tile) pair, shared-memory atomicMin --------------
-    if (nSmall) {
-        if (S == 1) keys[tid] = best;
-        else if (uni) {
-#pragma unroll
-            for (int s = 0; s < S; s++) keys[s * IFR_TILE_PIX + tid] = best;
-            uni = false;
-        }
-        // per-pixel early-Z against the block's far bound (deep tiles: most small triangles are hidden behind the big
-        // ones): depth first, coverage only for pixels that can still win a sample
-        const bool useFar = deep;
-        if (useFar) {
-            const uint32_t f = block_far<S>(keys, tid, best, uni);
-            if ((tid & 31) == 0) hz.warpFar[wrp] = f;
-        }
-        __syncthreads();      // keys complete, far bounds published
-        for (uint32_t qi = tid; qi < nSmall; qi += IFR_CHUNK) {
-            TriS s;
-            int bx0, bx1, by0, by1;
-            const uint32_t slot = __ldg(p.queue + sStart + qi);
-            if (!setup_tri(p, slot, tileX, tileY, s, bx0, bx1, by0, by1)) continue;
-            const int wide = s.flags & IFR_FLAG_WIDE;
-            for (int y = by0; y <= by1; y++)
-                for (int x = bx0; x <= bx1; x++) {
-                    unsigned long long k = 0;
-                    if (useFar) {
-                        const float d = depth_at(s.dX, s.dY, s.E0, s.flags, s.ar, s.z0, s.z1, s.z2, x, y);
-                        key_make(km, d, 0.0f, slot, k);      // ordered compare op: always a key
-                        if ((uint32_t)(k >> 32) > hz.warpFar[(y >> 2) * 2 + (x >> 3)]) continue;
-                    }
-                    const uint32_t m = coverage<S>(p, s.dX, s.dY, s.T, s.E0, wide, 16 * x, 16 * y);
-                    if (!m) continue;
-                    const int gx = tileX * IFR_TILE + x, gy = tileY * IFR_TILE + y;
-                    if (p.scissorEnable && !scissor_pass(p, gx, gy)) continue;
-                    if (!useFar) {
-                        const float d = depth_at(s.dX, s.dY, s.E0, s.flags, s.ar, s.z0, s.z1, s.z2, x, y);
-                        float dd0 = 0.0f;
-                        if (km.equal)
-                            dd0 = p.doClear ? p.clearDepth : p.depth[(size_t)gy * p.W + gx];
-                        if (!key_make(km, d, dd0, slot, k)) continue;
-                    }
-                    const int pi = pix_index(x, y);
-#pragma unroll
-                    for (int sm = 0; sm < S; sm++)
-                        if ((m >> sm) & 1) key_min_shared(&keys[sm * IFR_TILE_PIX + pi], k);
-                }
-        }
-        __syncthreads();
-    }
-
-    // ---- quad shading + resolve -----------------------------------------------------------------
-    // A pixel whose samples all hold the same key (S == 1, `uni`, or found equal below) needs no search: one FS
-    // invocation with count S.  Otherwise the per-sample slots are re-read from the shared-memory keys by every search
-    // (edge pixels only), so that nothing but the accumulators stays live across the fragment shader.
-    bool same = true;
-    uint32_t slot0;
-    int todo = 0;             // samples that still wait for their fragment
-    if (S == 1 || uni) {
-        const unsigned long long k = (S == 1 && nSmall != 0) ? keys[tid] : best;
-        slot0 = key_slot(km, k);
-        todo = slot0 != IFR_SLOT_NONE ? S : 0;
-    } else {
-        slot0 = key_slot(km, keys[tid]);
-        todo = slot0 != IFR_SLOT_NONE;
-#pragma unroll
-        for (int s = 1; s < S; s++) {
-            const uint32_t v = key_slot(km, keys[s * IFR_TILE_PIX + tid]);
-            same = same && v == slot0;
-            todo += v != IFR_SLOT_NONE;
-        }
-    }
-    if (!inFrame) todo = 0;
-    if (p.primIds && inFrame) {
-#pragma unroll
-        for (int s = 0; s < S; s++) p.primIds[pidx * S + s] = -1;     // overwritten below for the covered samples
-    }
-
-    float4 acc = make_float4(0, 0, 0, 0);
-    float dacc = 0.0f;
-    int bg = S;
-    unsigned int myFrags = 0;
-    // One FS invocation per (pixel, slot) that owns >= 1 sample, slots in ascending order (CU:2264-2310).  A lane
-    // shades alone (see interp), so the loop runs max-over-lanes(distinct slots) times and nothing is quad-uniform.
-    // (Tried and measured slower.  Two tiles per CTA with both queue headers and both first chunks fetched up front:
-    // c2 tile 0.280 -> 0.311 ms, c3 0.441 -> 0.506 — the prologue latency of a fresh CTA is already covered by the other
-    // resident CTAs.  c3 tile 0.44 -> 0.57 ms: compacting the second / third slots of edge pixels into a
-    // shared work list shaded one per thread — the kernel is latency bound, and the two CTA barriers plus one warp
-    // shading the list while seven wait cost more than the divergent second pass they replace.)
-    uint32_t last = 0;
-    bool first = true;
-    while (todo > 0) {
-        uint32_t cur = slot0;
-        int cnt = S;
-        if (S > 1 && !same) {
-            cur = IFR_SLOT_NONE;
-            cnt = 0;
-#pragma unroll
-            for (int s = 0; s < S; s++) {
-                const uint32_t v = key_slot(km, keys[s * IFR_TILE_PIX + tid]);
-                if (v != IFR_SLOT_NONE && (first || v > last)) {
-                    if (v < cur) { cur = v; cnt = 1; }
-                    else if (v == cur) cnt++;
-                }
-            }
-        }
-        float4 v[NV > 0 ? NV : 1], ddx[NV > 0 ? NV : 1], ddy[NV > 0 ? NV : 1];
-        float depth = 0.0f;
-        int prim = 0, fan = 0;
-        interp<NV, FsTraits<FS>::needsDerivs, FS == IFRIT_FS_TEXTURED_FAST || FS == IFRIT_FS_TEXTURED_LOD0_FAST || FS == IFRIT_FS_TEXTURED_FAST_RA>(p, cur, px, py, v, ddx, ddy, depth, prim, fan);
-        const float4 c = run_fs<FS>(p, v, ddx, ddy, prim, fan);
-        const float fc = (float)cnt;
-        acc.x = fmaf(fc, c.x, acc.x); acc.y = fmaf(fc, c.y, acc.y);
-        acc.z = fmaf(fc, c.z, acc.z); acc.w = fmaf(fc, c.w, acc.w);
-        dacc = fmaf(fc, depth, dacc);
-        bg -= cnt;
-        todo -= cnt;
-        myFrags++;
-        if (p.primIds) {
-            if (S == 1 || same) {
-#pragma unroll
-                for (int s = 0; s < S; s++) p.primIds[pidx * S + s] = prim;
-            } else {
-#pragma unroll
-                for (int s = 0; s < S; s++)
-                    if (key_slot(km, keys[s * IFR_TILE_PIX + tid]) == cur) p.primIds[pidx * S + s] = prim;
-            }
-        }
-        last = cur;
-        first = false;
-    }
-    if (inFrame) {
-        const bool cleared = p.doClear && scis;
-        if (bg != S || cleared) {
-            float4 out = acc;
-            float dout = dacc;
-            if (bg > 0) {
-                const float fb = (float)bg;
-                const float4 prev = cleared ? make_float4(p.clearColor[0], p.clearColor[1], p.clearColor[2], p.clearColor[3])
-                                            : p.color[pidx];
-                out.x = fmaf(fb, prev.x, out.x); out.y = fmaf(fb, prev.y, out.y);
-                out.z = fmaf(fb, prev.z, out.z); out.w = fmaf(fb, prev.w, out.w);
-                dout = fmaf(fb, d0, dout);
-            }
-            if (bg == S) {   // nothing drawn here: plain clear
-                out = make_float4(p.clearColor[0], p.clearColor[1], p.clearColor[2], p.clearColor[3]);
-                dout = p.clearDepth;
-            } else if (S > 1) {
-                const float fs = (float)S;
-                out.x = out.x / fs; out.y = out.y / fs; out.z = out.z / fs; out.w = out.w / fs;
-                dout = dout / fs;
-            }
-            p.color[pidx] = out;
-            p.depth[pidx] = dout;
-            if (p.present) p.present[pidx] = ifr_pack_rgba8(out);
-        } else if (p.present) {
-            p.present[pidx] = ifr_pack_rgba8(p.color[pidx]);   // untouched pixel (no clear, nothing drawn): present what is there
-        }
-    }
-    myFrags = __reduce_add_sync(0xffffffffu, myFrags);
-    if ((tid & 31) == 0 && myFrags)   // no CTA barrier: warps retire independently; spread over 256 sectors (common.cuh)
-        ifr_count_spread(p.counters, 1, (unsigned)(tile * 8 + wrp) * 2654435761u >> 16, (unsigned long long)myFrags);
-}
+// kernels_tile.cu — ordered alpha blending kernel and the fragment-shader dispatch of the tile kernel (tile_kernel.cuh).
+#include "tile_kernel.cuh"
 
 // ---- ordered alpha blending ----------------------------------------------------------------------
 // pixelShadingAlphaBlendKernel CU:1649-1897: per pixel, primitives in submission order (the reference merges its three
@@ -837,52 +156,31 @@ cudaError_t ifr_launch_tiles_blend(const DrawParams& p, int fsId, cudaStream_t s
     }
 }
 
-template <int FS>
-static cudaError_t launch_fs(const DrawParams& p, cudaStream_t s) {
-    const dim3 grid(p.tilesX * p.tilesY);   // upper bound of the work list: surplus CTAs exit at once
-    const size_t smem = (size_t)p.msaa * IFR_TILE_PIX * sizeof(unsigned long long);
-#define IFR_LAUNCH(SS)                                                                                   \
-    case SS: {                                                                                           \
-        static bool attrSet = false;                                                                     \
-        if (!attrSet) {                                                                                  \
-            cudaFuncSetAttribute(tile_kernel<FS, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); \
-            attrSet = true;                                                                              \
-        }                                                                                                \
-        tile_kernel<FS, SS><<<grid, 256, smem, s>>>(p);                                                  \
-        break;                                                                                           \
-    }
-    switch (p.msaa) {
-        IFR_LAUNCH(1)
-        IFR_LAUNCH(2)
-        IFR_LAUNCH(4)
-        IFR_LAUNCH(8)
-        IFR_LAUNCH(16)
-        default: return cudaErrorInvalidValue;
-    }
-#undef IFR_LAUNCH
-    return cudaGetLastError();
-}
+#define IFR_DECL_FS(ID) cudaError_t ifr_launch_fs_##ID(const DrawParams& p, cudaStream_t s);
+IFR_DECL_FS(0) IFR_DECL_FS(1) IFR_DECL_FS(2) IFR_DECL_FS(3) IFR_DECL_FS(4) IFR_DECL_FS(5) IFR_DECL_FS(6)
+IFR_DECL_FS(100) IFR_DECL_FS(101) IFR_DECL_FS(102) IFR_DECL_FS(103)
+#undef IFR_DECL_FS
 
 cudaError_t ifr_launch_tiles(const DrawParams& p, int fsId, cudaStream_t s) {
     switch (fsId) {
-        case IFRIT_FS_VARYING0: return launch_fs<IFRIT_FS_VARYING0>(p, s);
-        case IFRIT_FS_NORMAL_COLOR: return launch_fs<IFRIT_FS_NORMAL_COLOR>(p, s);
-        case IFRIT_FS_PRIM_ID: return launch_fs<IFRIT_FS_PRIM_ID>(p, s);
+        case IFRIT_FS_VARYING0: return ifr_launch_fs_0(p, s);
+        case IFRIT_FS_NORMAL_COLOR: return ifr_launch_fs_1(p, s);
+        case IFRIT_FS_PRIM_ID: return ifr_launch_fs_2(p, s);
 #ifdef IFR_NO_FAST
-        case IFRIT_FS_TEXTURED: return launch_fs<IFRIT_FS_TEXTURED>(p, s);
-        case IFRIT_FS_TEXTURED_LOD0: return launch_fs<IFRIT_FS_TEXTURED_LOD0>(p, s);
+        case IFRIT_FS_TEXTURED: return ifr_launch_fs_3(p, s);
+        case IFRIT_FS_TEXTURED_LOD0: return ifr_launch_fs_4(p, s);
 #else
         case IFRIT_FS_TEXTURED: {
             // the common sampler state has its own instantiation (sampler.cuh: sample_aniso_repeat)
             const SampDesc& sd = p.samp[0];
             const bool ra = sd.filter == IF_FILTER_LINEAR && sd.addrU == IF_SAMPLER_ADDRESS_MODE_REPEAT && sd.addrV == IF_SAMPLER_ADDRESS_MODE_REPEAT && sd.aniso;
-            if (ra) return p.hwFilter ? launch_fs<IFRIT_FS_TEXTURED_FAST_RA>(p, s) : launch_fs<IFRIT_FS_TEXTURED_RA>(p, s);
-            return p.hwFilter ? launch_fs<IFRIT_FS_TEXTURED_FAST>(p, s) : launch_fs<IFRIT_FS_TEXTURED>(p, s);
+            if (ra) return p.hwFilter ? ifr_launch_fs_103(p, s) : ifr_launch_fs_102(p, s);
+            return p.hwFilter ? ifr_launch_fs_100(p, s) : ifr_launch_fs_3(p, s);
         }
-        case IFRIT_FS_TEXTURED_LOD0: return p.hwFilter ? launch_fs<IFRIT_FS_TEXTURED_LOD0_FAST>(p, s) : launch_fs<IFRIT_FS_TEXTURED_LOD0>(p, s);
+        case IFRIT_FS_TEXTURED_LOD0: return p.hwFilter ? ifr_launch_fs_101(p, s) : ifr_launch_fs_4(p, s);
 #endif
-        case IFRIT_FS_SKYBOX: return launch_fs<IFRIT_FS_SKYBOX>(p, s);
-        case IFRIT_FS_DERIV_VIS: return launch_fs<IFRIT_FS_DERIV_VIS>(p, s);
+        case IFRIT_FS_SKYBOX: return ifr_launch_fs_5(p, s);
+        case IFRIT_FS_DERIV_VIS: return ifr_launch_fs_6(p, s);
         default: return cudaErrorInvalidValue;
     }
 }

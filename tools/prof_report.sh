@@ -2,7 +2,7 @@
 # usage (here): tools/prof_report.sh <report.ncu-rep> <mangled kernel> [topN] — headline counters + per-line hotspots
 rep=$1; kern=$2; top=${3:-40}
 mkdir -p /tmp/sass && (cd /tmp/sass && rm -f *.cubin && cuobjdump -xelf all /root/repo/ifrit-v2_b200/lib/libifrit_b200.so > /dev/null)
-cub=$(grep -l "$kern" /tmp/sass/kernels_*.cubin | head -1)
+cub=$(grep -l "$kern" /tmp/sass/*.cubin | head -1)
 ncu -i $rep --page raw --csv | python -c "
 import csv,sys
 rows=list(csv.reader(sys.stdin)); h,u,v=rows[0],rows[1],rows[2]
