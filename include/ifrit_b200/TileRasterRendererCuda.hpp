@@ -16,7 +16,14 @@
 
 namespace ifrit_b200 {
 
+// Four floats {x, y, z, w}.  The reference's math header defines Vector4f as a MACRO (ifrit/core/math/VectorDefs.h:211,
+// CoreVec4<float>, same layout); when it has been included before this header that type is used as is.
+#ifdef Vector4f
+using Float4 = Vector4f;
+#else
 struct Vector4f { float x, y, z, w; };
+using Float4 = Vector4f;
+#endif
 
 class TileRasterRendererCuda {
 public:
@@ -75,7 +82,7 @@ public:
     void CreateBuffer(int slotId, int bufSize) { ck(iftrcuCreateBuffer(h_, slotId, bufSize)); }
     void copyHostBufferToBuffer(const void* srcBuffer, int dstSlot, int size) { ck(iftrcuCopyHostBufferToBuffer(h_, srcBuffer, dstSlot, size)); }
 
-    void SetScissors(const std::vector<Vector4f>& scissors) { ck(iftrcuSetScissors(h_, scissors.empty() ? nullptr : &scissors[0].x, (int)scissors.size())); }
+    void SetScissors(const std::vector<Float4>& scissors) { ck(iftrcuSetScissors(h_, scissors.empty() ? nullptr : &scissors[0].x, (int)scissors.size())); }
     void setScissorTestEnable(bool option) { ck(iftrcuSetScissorTestEnable(h_, option)); }
     void setMsaaSamples(IfritSampleCountFlagBits msaaSamples) { ck(iftrcuSetMsaaSamples(h_, msaaSamples)); }
     void setRasterizerPolygonMode(IfritPolygonMode mode) { ck(iftrcuSetRasterizerPolygonMode(h_, mode)); }
@@ -83,7 +90,7 @@ public:
     void SetDepthFunc(IfritCompareOp depthFunc) { ck(iftrcuSetDepthFunc(h_, depthFunc)); }
     void SetDepthTestEnable(bool option) { ck(iftrcuSetDepthTestEnable(h_, option)); }
     void SetCullMode(IfritCullMode cullMode) { ck(iftrcuSetCullMode(h_, cullMode)); }
-    void setClearValues(const std::vector<Vector4f>& clearColors, float clearDepth) {
+    void setClearValues(const std::vector<Float4>& clearColors, float clearDepth) {
         ck(iftrcuSetClearValues(h_, clearColors.empty() ? nullptr : &clearColors[0].x, (int)clearColors.size(), clearDepth));
     }
 
