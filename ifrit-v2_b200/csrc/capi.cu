@@ -77,6 +77,9 @@ struct iftrcuRenderer {
     const int32_t* dIB = nullptr; DevBuf ownIB; int icount = 0;
     int vsId = -1, fsId = -1, nvary = 0;
     bool fusedVS = true;   // vertex stage fused into triangle setup (default) or stand-alone vs_kernel
+    // TMA descriptors of the bound framebuffer (tma_maps), rebuilt when an image pointer or the size changes
+    struct TmaCache { void* c = nullptr; void* d = nullptr; void* pr = nullptr; int W = 0, H = 0, ok = 0; CUtensorMap m[6]; } tma;
+    bool useTma = true;    // iftrcuSetTmaFramebuffer
     bool hwFilter = false; // opt-in (iftrcuSetSamplerHardwareFilter): bilinear footprints through the TEX unit, 8-bit weights, SFU forms
 
     // state (defaults: TileRasterRendererCuda.h:42-47, CU:186-189)
@@ -162,6 +165,56 @@ static void create_tex_objects(iftrcuRenderer* r, int slot) {
     }
 }
 
+// ---- TMA descriptors of the framebuffer images ----------------------------------------------------------------------
+// The tile kernel moves framebuffer blocks with cp.async.bulk.tensor (tile_kernel.cuh: tma_store_2d / tma_load_2d): one
+// 2-D descriptor per image and box shape.  cuTensorMapEncodeTiled is a host-side encoder of the driver library; it is
+// looked up through the runtime (cudaGetDriverEntryPoint), so the library still links nothing but cudart.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tma_encoder() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+        else cudaGetLastError();
+    }
+    return fn;
+}
+// 32-bit elements, rows of `w` elements, `h` rows, box bw x bh
+static bool tma_map_2d(CUtensorMap* m, CUtensorMapDataType dt, void* base, uint64_t w, uint64_t h, uint32_t bw, uint32_t bh) {
+    EncodeTiledFn enc = tma_encoder();
+    if (!enc || !base || ((uintptr_t)base & 15) || ((w * 4) & 15)) return false;
+    const cuuint64_t dims[2] = {w, h}, strides[1] = {w * 4};
+    const cuuint32_t box[2] = {bw, bh}, estr[2] = {1, 1};
+    return enc(m, dt, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+static void tma_maps(iftrcuRenderer* r, DrawParams& p) {
+    p.useTma = 0;
+    if (!r->useTma || !p.color || !p.depth) return;
+    auto& t = r->tma;
+    if (t.c != (void*)p.color || t.d != (void*)p.depth || t.pr != (void*)p.present || t.W != p.W || t.H != p.H) {
+        t.c = p.color; t.d = p.depth; t.pr = p.present; t.W = p.W; t.H = p.H;
+        const uint64_t W = (uint64_t)p.W, H = (uint64_t)p.H;
+        bool ok = tma_map_2d(&t.m[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, p.color, W * 4, H, 32, 4) &&
+                  tma_map_2d(&t.m[1], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, p.depth, W, H, 8, 4) &&
+                  tma_map_2d(&t.m[3], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, p.color, W * 4, H, 64, 16) &&
+                  tma_map_2d(&t.m[4], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, p.depth, W, H, 16, 16);
+        if (ok && p.present)
+            ok = tma_map_2d(&t.m[2], CU_TENSOR_MAP_DATA_TYPE_UINT32, p.present, W, H, 8, 4) &&
+                 tma_map_2d(&t.m[5], CU_TENSOR_MAP_DATA_TYPE_UINT32, p.present, W, H, 16, 16);
+        t.ok = ok ? 1 : 0;
+    }
+    if (!t.ok) return;
+    memcpy(p.tmap, t.m, sizeof t.m);
+    p.useTma = 1;
+}
+
 static void build_params(iftrcuRenderer* r, DrawParams& p) {
     memset(&p, 0, sizeof p);
     p.color = r->dColor; p.depth = r->dDepth; p.primIds = r->debugIds ? (int32_t*)r->primIds.p : nullptr;
@@ -185,6 +238,7 @@ static void build_params(iftrcuRenderer* r, DrawParams& p) {
     memcpy(p.scissor, r->scissor, sizeof p.scissor);
     p.rank = r->rank; p.world = r->world;
     p.hwFilter = r->hwFilter ? 1 : 0;
+    tma_maps(r, p);
     p.blendEnable = r->blendEnable; memcpy(p.blendCoef, r->blendCoef, sizeof p.blendCoef);
     int mnx = 255, mxx = 0, mny = 255, mxy = 0;
     const int ns = r->convention == IFRIT_CONVENTION_CPU ? 1 : r->msaa;
@@ -938,6 +992,7 @@ int iftrcuSetFramePipelining(iftrcuRenderer* h, int enable) {
     return IFRIT_OK;
 }
 int iftrcuSetVertexStageFused(iftrcuRenderer* h, int enable) { R_CHECK(h); r->fusedVS = enable != 0; return IFRIT_OK; }
+int iftrcuSetTmaFramebuffer(iftrcuRenderer* h, int enable) { R_CHECK(h); r->useTma = enable != 0; return IFRIT_OK; }
 int iftrcuSetSamplerHardwareFilter(iftrcuRenderer* h, int enable) { R_CHECK(h); r->hwFilter = enable != 0; return IFRIT_OK; }
 
 int iftrcuClear(iftrcuRenderer* h) {

@@ -3,6 +3,7 @@
 // implement bit-for-bit (integer coverage / ids / depth) against oracle/ifrit_oracle.c.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda.h>      // CUtensorMap (type only: nothing links libcuda, the encoder is fetched with cudaGetDriverEntryPoint)
 #include <stdint.h>
 
 #define IFR_TILE 16          // tile edge in pixels (reference: CU_TILE_WIDTH, KC:36-42)
@@ -68,6 +69,10 @@ struct DrawParams {
     // ordered alpha blending (pixelShadingAlphaBlendKernel CU:1649-1897): colour src / colour dst / alpha src / alpha dst
     // coefficients {x1, x(1 - src.a), x(1 - dst.a), zero flag} (updateBlendStateKernel CU:3436-3537)
     int blendEnable; float blendCoef[4][4];
+    // TMA descriptors of the framebuffer images (capi.cu: tma_maps): [0..2] colour / depth / present with the 8x4-pixel
+    // block box a warp of the tile kernel owns, [3..5] the same images with a 16x16-pixel tile box (fused clear of empty
+    // tiles).  useTma = 0 when an image cannot be described (row pitch not a multiple of 16 bytes, unaligned base).
+    alignas(64) CUtensorMap tmap[6]; int useTma;
     int hwFilter;   // bilinear footprints through the TEX unit (8-bit weights) instead of four loads + fp32 lerps
     // coverage sample pattern of this draw, in 1/16 pixel (from cMsaaSampleSequenceAgg, CU:223-234)
     alignas(16) int32_t sampX[16]; alignas(16) int32_t sampY[16];   // 32-bit: read with wide constant-bank loads, no byte extraction in the sample loop

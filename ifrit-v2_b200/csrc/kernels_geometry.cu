@@ -256,6 +256,18 @@ __device__ __forceinline__ bool tile_may_cover(const EdgeSet& e, int tx, int ty)
 __device__ __forceinline__ bool tile_owned(const DrawParams& p, int tx, int ty) {
     return p.world <= 1 || ifr_tile_owner(tx, ty, p.world) == p.rank;
 }
+// Sort-first (world > 1): does this rank own any tile of the box?  Ownership interleaves 64-px super-tiles
+// (common.cuh: ifr_tile_owner); boxes of more than 16 super-tiles are kept without looking (conservative).
+__device__ __forceinline__ bool box_owned(const DrawParams& p, int tx0, int tx1, int ty0, int ty1) {
+    if (p.world <= 1) return true;
+    constexpr int ST = IFR_SUPER / IFR_TILE;
+    const int sx0 = tx0 / ST, sx1 = tx1 / ST, sy0 = ty0 / ST, sy1 = ty1 / ST;
+    if ((sx1 - sx0 + 1) * (sy1 - sy0 + 1) > 16) return true;
+    for (int sy = sy0; sy <= sy1; sy++)
+        for (int sx = sx0; sx <= sx1; sx++)
+            if ((sx + 3 * sy) % p.world == p.rank) return true;
+    return false;
+}
 __device__ __forceinline__ void count_one(const DrawParams& p, int big, int tx, int ty) {
     if (!tile_owned(p, tx, ty)) return;
     atomicAdd(&p.tileCount[big * p.tilesX * p.tilesY + ty * p.tilesX + tx], 1u);
@@ -283,6 +295,24 @@ __device__ __forceinline__ void emit_one(const DrawParams& p, const RecRegs& rr,
 }
 
 #define IFR_BIG_TILES 16
+// Warp-aggregated bin-queue atomics (north-star N2; the reference issues one atomic per (triangle, tile) pair,
+// CU:863-871).  Lanes of a warp whose pairs fall into the same tile queue are found with __match_any_sync; the lowest
+// lane of each group issues ONE atomic for the group and, in the fill pass, hands out the reserved positions by rank.
+// MEASURED SLOWER on both kinds of scene (profiles/r02_atomics.txt: coherent 50k mesh, setup_count 21.0 -> 25.2 us; 10M
+// random soup, setup_count 331 -> 390 us, light fill 149 -> 188 us): on the soup almost no two lanes share a tile, on
+// the mesh the L2 already merges same-address REDs of a warp, and either way every pair pays a MATCH + vote + shuffle on
+// top of its atomic.  Default OFF (per-pair RED / ATOM, which the L2 atomic units absorb); IFR_WARP_AGG = 1 builds the
+// aggregated variant for the A/B.
+#ifndef IFR_WARP_AGG
+#define IFR_WARP_AGG 0
+#endif
+// all 32 lanes call; `act` lanes hold a queue index `q` (< 2^31).  Returns the group's size and the lane's rank in it.
+__device__ __forceinline__ unsigned agg_group(bool act, uint32_t q, int lane, int& rank, int& leader) {
+    const unsigned peers = __match_any_sync(0xffffffffu, act ? q : (0x80000000u | (uint32_t)lane));
+    rank = __popc(peers & ((1u << lane) - 1u));
+    leader = __ffs(peers) - 1;
+    return peers;
+}
 
 // binning of boxes of <= 16 tiles by a group of G lanes that share the slot (lane `sub` of the group
 // takes tiles sub, sub + G, ...; G = 1 in the count pass) + warp-cooperative binning of larger boxes
@@ -291,7 +321,25 @@ __device__ __forceinline__ void bin_triangle(const DrawParams& p, bool has, uint
                                              int ty0, int ty1, const EdgeSet& e, int sub) {
     const int nx = tx1 - tx0 + 1, ny = ty1 - ty0 + 1;
     const int nt = has ? nx * ny : 0;
-    if (nt >= 1 && nt <= IFR_BIG_TILES && sub < nt) {
+    if (IFR_WARP_AGG && !FILL) {
+        // count pass, aggregated: the warp walks its boxes tile index by tile index in lockstep
+        const int lane = threadIdx.x & 31;
+        const int mynt = (nt >= 1 && nt <= IFR_BIG_TILES) ? nt : 0;
+        const int maxnt = __reduce_max_sync(0xffffffffu, mynt);
+        const bool test = nx > 1 && ny > 1;
+        for (int i = 0; i < maxnt; i++) {
+            bool act = i < mynt;
+            int tx = 0, ty = 0;
+            if (act) {
+                tx = tx0 + i % nx; ty = ty0 + i / nx;
+                act = !(test && !tile_may_cover(e, tx, ty)) && tile_owned(p, tx, ty);
+            }
+            const uint32_t q = (uint32_t)(big * p.tilesX * p.tilesY + ty * p.tilesX + tx);
+            int rank, leader;
+            const unsigned peers = agg_group(act, q, lane, rank, leader);
+            if (act && lane == leader) atomicAdd(&p.tileCount[q], (uint32_t)__popc(peers));
+        }
+    } else if (nt >= 1 && nt <= IFR_BIG_TILES && sub < nt) {
         RecRegs rr;
         if (FILL && big) load_rec(p, slot, rr);
         const bool test = nx > 1 && ny > 1;     // a one-tile-wide box is covered in every tile of it
@@ -362,14 +410,18 @@ __global__ void __launch_bounds__(256, IFR_SETUP_MINB) setup_count_kernel(const 
     unsigned long long nasm = 0;
 #pragma unroll
     for (int f = 0; f < 2; f++) {
-        const bool has = a[f].ok;
+        bool has = a[f].ok;
         const uint32_t slot = f == 0 ? (uint32_t)t : (uint32_t)(p.ntri + t);
+        if (has) nasm++;
+        // sort-first: a triangle none of whose tiles this rank owns ends here — no record, no queue entry, no place in
+        // the heavy list; the replicated part of the geometry stage is then the assembly arithmetic alone, while its
+        // memory traffic and the whole fill pass scale with 1 / world ("geometry is broadcast")
+        if (has && !box_owned(p, a[f].tx0, a[f].tx1, a[f].ty0, a[f].ty1)) has = false;
         const int big = has && !(a[f].flags & IFR_FLAG_SMALL);
         EdgeSet e;
         if (has) {
             store_record(p, slot, a[f]);
             make_edges(a[f].X, a[f].Y, e);
-            nasm++;
             if (f == 1) {
                 const unsigned long long k = atomicAdd(&p.counters[4], 1ull);
                 p.fan1List[k] = slot;
@@ -404,12 +456,32 @@ __global__ void __launch_bounds__(256, IFR_SETUP_MINB) setup_count_kernel(const 
 __global__ void __launch_bounds__(256) fill_light_kernel(const __grid_constant__ DrawParams p) {
     if (p.counters[3]) return;   // a queue is too small: host re-issues the draw with larger ones
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
+#if IFR_WARP_AGG
+    bool act = t < p.ntri;
+    int tx0 = 0, ty0 = 0;
+    if (act) {
+        const uint2 box = p.tileBox[t];
+        tx0 = box.x & 0xffff; ty0 = box.y & 0xffff;
+        const int tx1 = box.x >> 16, ty1 = (box.y >> 16) & 0x7fff;
+        act = tx0 == tx1 && ty0 == ty1 && (box.y >> 31) && tile_owned(p, tx0, ty0);   // else: empty, multi-tile or big (heavy list)
+    }
+    if (!__any_sync(0xffffffffu, act)) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t tile = (uint32_t)(ty0 * p.tilesX + tx0);
+    int rank, leader;
+    const unsigned peers = agg_group(act, tile, lane, rank, leader);
+    uint32_t base = 0;
+    if (act && lane == leader) base = atomicAdd(&p.tileCursor[tile], (uint32_t)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (act) p.queue[p.tileStart[tile] + base + (uint32_t)rank] = (uint32_t)t;
+#else
     if (t >= p.ntri) return;
     const uint2 box = p.tileBox[t];
     const int tx0 = box.x & 0xffff, tx1 = box.x >> 16, ty0 = box.y & 0xffff, ty1 = (box.y >> 16) & 0x7fff;
     if (tx0 != tx1 || ty0 != ty1 || !(box.y >> 31)) return;     // empty, multi-tile or big: heavy list
     if (!tile_owned(p, tx0, ty0)) return;
     p.queue[reserve_one(p, 0, tx0, ty0)] = (uint32_t)t;
+#endif
 }
 
 // pass 3b: the heavy slots (multi-tile or big triangles via the per-warp bit words, second-fan slots via

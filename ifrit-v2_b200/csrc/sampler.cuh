@@ -226,6 +226,11 @@ __device__ __forceinline__ float4 sample_aniso(const TexDesc& t, const SampDesc&
 // footprints through the texture unit), without the switches on the sampler state, with the per-level constants read
 // from the constant bank where they are used instead of being carried in registers across the tap loop.  Selected by
 // the launcher when the bound sampler matches (kernels_tile.cu: ifr_launch_tiles).
+#ifndef IFR_TAP_UNROLL
+#define IFR_TAP_UNROLL 2     // taps of the anisotropic loops in flight together (texture latency vs registers)
+#endif
+#define IFR_PRAGMA_(x) _Pragma(#x)
+#define IFR_PRAGMA(x) IFR_PRAGMA_(x)
 template <bool FAST>
 __device__ __forceinline__ float4 bilinear_repeat(const TexDesc& t, int lod, float u, float v) {
     const TexLevel& L = t.lvl[lod];
@@ -274,14 +279,14 @@ __device__ __forceinline__ float4 sample_aniso_repeat(const TexDesc& t, float ma
     const int lo = clampi(lo0, 0, t.mips), hi = clampi(lo0 + 1, 0, t.mips);
     float4 sum = make_float4(0, 0, 0, 0);
     if (d == 0.0f) {      // lerp(a, b, 0) == a: one level (the magnified case)
-#pragma unroll 2
+IFR_PRAGMA(unroll IFR_TAP_UNROLL)
         for (int i = 0; i < n; i++) {
             const float tt = (float)i * step - 0.5f;
             const float4 r = bilinear_repeat<FAST>(t, lo, fmaf(ddu, tt, u), fmaf(ddv, tt, v));
             sum.x += r.x; sum.y += r.y; sum.z += r.z; sum.w += r.w;
         }
     } else {
-#pragma unroll 2
+IFR_PRAGMA(unroll IFR_TAP_UNROLL)
         for (int i = 0; i < n; i++) {
             const float tt = (float)i * step - 0.5f;
             const float uu = fmaf(ddu, tt, u), vv = fmaf(ddv, tt, v);

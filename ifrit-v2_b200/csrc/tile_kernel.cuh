@@ -56,27 +56,36 @@ __device__ __forceinline__ bool scissor_pass(const DrawParams& p, int x, int y) 
     return false;
 }
 
+// Cold paths (triangles wider than 4096 px, edge values beyond int32) are written as separate functions so that they CAN
+// be kept out of line (-DIFR_COLD=__noinline__: the tile kernel is ~90 KB of SASS and instruction fetch shows up in the
+// stall samples).  Measured (profiles/r02_ab.txt): out of line c4 tile 0.523 -> 0.505 ms, but c3 0.332 -> 0.338 and c2
+// 0.222 -> 0.248 (the call sites pin registers of the 40-register 1x kernels) — inlined by default.
+#ifndef IFR_COLD
+#define IFR_COLD __forceinline__
+#endif
+template <int S>
+__device__ IFR_COLD uint32_t coverage_wide(const DrawParams& p, int dx0, int dx1, int dx2, int dy0, int dy1, int dy2,
+                                           long long e0, long long e1, long long e2, int ci, int cj) {
+    uint32_t mask = 0;
+    for (int k = 0; k < S; k++) {
+        const long long i = ci + p.sampX[k], j = cj + p.sampY[k];
+        const bool in = (e0 + 16 * (dx0 * j - dy0 * i) > 0) && (e1 + 16 * (dx1 * j - dy1 * i) > 0) && (e2 + 16 * (dx2 * j - dy2 * i) > 0);
+        mask |= (uint32_t)in << k;
+    }
+    return mask;
+}
 // coverage mask of the pixel whose origin is (ci, cj) = (16 lx, 16 ly) in 1/16 px, over the S samples
 template <int S>
 __device__ __forceinline__ uint32_t coverage(const DrawParams& p, const int dX[3], const int dY[3], const int T[3],
                                              const long long E0[3], int wide, int ci, int cj) {
     uint32_t mask = 0;
-    if (!wide) {
+    if (wide) return coverage_wide<S>(p, dX[0], dX[1], dX[2], dY[0], dY[1], dY[2], E0[0], E0[1], E0[2], ci, cj);
 #pragma unroll
-        for (int k = 0; k < S; k++) {
-            const int i = ci + p.sampX[k], j = cj + p.sampY[k];
-            const bool in = (dX[0] * j - dY[0] * i >= T[0]) && (dX[1] * j - dY[1] * i >= T[1]) &&
-                            (dX[2] * j - dY[2] * i >= T[2]);
-            mask |= (uint32_t)in << k;
-        }
-    } else {
-        for (int k = 0; k < S; k++) {
-            const long long i = ci + p.sampX[k], j = cj + p.sampY[k];
-            bool in = true;
-#pragma unroll
-            for (int e = 0; e < 3; e++) in = in && (E0[e] + 16 * (dX[e] * j - dY[e] * i) > 0);
-            mask |= (uint32_t)in << k;
-        }
+    for (int k = 0; k < S; k++) {
+        const int i = ci + p.sampX[k], j = cj + p.sampY[k];
+        const bool in = (dX[0] * j - dY[0] * i >= T[0]) && (dX[1] * j - dY[1] * i >= T[1]) &&
+                        (dX[2] * j - dY[2] * i >= T[2]);
+        mask |= (uint32_t)in << k;
     }
     return mask;
 }
@@ -124,23 +133,23 @@ __device__ __forceinline__ uint32_t coverage_coop(const DrawParams& p, int* __re
     return mask;
 }
 
+static __device__ IFR_COLD float depth_at64(int dx0, int dx1, int dx2, int dy0, int dy1, int dy2, long long e0, long long e1, long long e2,
+                                     float ar, float z0, float z1, float z2, int lx, int ly) {
+    const float b0 = __fmul_rn((float)(e0 + 256 * ((long long)dx0 * ly - (long long)dy0 * lx)), ar);
+    const float b1 = __fmul_rn((float)(e1 + 256 * ((long long)dx1 * ly - (long long)dy1 * lx)), ar);
+    const float b2 = __fmul_rn((float)(e2 + 256 * ((long long)dx2 * ly - (long long)dy2 * lx)), ar);
+    return fmaf(z2, b2, fmaf(z1, b1, __fmul_rn(z0, b0)));
+}
 // depth at the integer pixel (lx, ly): beta_i = E_i(corner) / d, from exact integer edge values
 __device__ __forceinline__ float depth_at(const int dX[3], const int dY[3], const long long E0[3], uint32_t flags, float ar,
                                           float z0, float z1, float z2, int lx, int ly) {
+    if (!(flags & IFR_FLAG_FITS32)) return depth_at64(dX[0], dX[1], dX[2], dY[0], dY[1], dY[2], E0[0], E0[1], E0[2], ar, z0, z1, z2, lx, ly);
     float beta[3];
-    if (flags & IFR_FLAG_FITS32) {
-        // triangle-level bound: the edge values at this corner fit int32 -> wrapping 32-bit arithmetic, I2F.S32
+    // triangle-level bound: the edge values at this corner fit int32 -> wrapping 32-bit arithmetic, I2F.S32
 #pragma unroll
-        for (int e = 0; e < 3; e++) {
-            const uint32_t Ec = (uint32_t)E0[e] + (((uint32_t)dX[e] * (uint32_t)ly - (uint32_t)dY[e] * (uint32_t)lx) << 8);
-            beta[e] = __fmul_rn((float)(int)Ec, ar);
-        }
-    } else {
-#pragma unroll
-        for (int e = 0; e < 3; e++) {
-            const long long Ec = E0[e] + 256 * ((long long)dX[e] * ly - (long long)dY[e] * lx);
-            beta[e] = __fmul_rn((float)Ec, ar);
-        }
+    for (int e = 0; e < 3; e++) {
+        const uint32_t Ec = (uint32_t)E0[e] + (((uint32_t)dX[e] * (uint32_t)ly - (uint32_t)dY[e] * (uint32_t)lx) << 8);
+        beta[e] = __fmul_rn((float)(int)Ec, ar);
     }
     return fmaf(z2, beta[2], fmaf(z1, beta[1], __fmul_rn(z0, beta[0])));
 }
@@ -195,6 +204,21 @@ __device__ __forceinline__ float4 mix3(const float4& v0, const float4& v1, const
     return o;
 }
 
+struct Betas9 { float b[3], h[3], v[3]; };
+static __device__ IFR_COLD Betas9 betas64(int x0, int x1, int x2, int y0, int y1, int y2, int sx, int sy, int hs, int vs, float ar) {
+    const int X[3] = {x0, x1, x2}, Y[3] = {y0, y1, y2};
+    Betas9 o;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const int a = (i + 1) % 3, b = (i + 2) % 3;
+        const long long dx = X[b] - X[a], dy = Y[b] - Y[a];
+        const long long E = dx * (long long)(sy - Y[a]) - dy * (long long)(sx - X[a]);
+        o.b[i] = __fmul_rn((float)E, ar);
+        o.h[i] = __fmul_rn((float)(E - dy * hs), ar);
+        o.v[i] = __fmul_rn((float)(E + dx * vs), ar);
+    }
+    return o;
+}
 // Interpolates slot's varyings at pixel (px, py).  DERIV: also at the two other pixels the 2x2 quad's coarse
 // derivatives need — the horizontal and the vertical neighbour inside the screen-aligned quad (SB:36-76:
 // ddx = right - left of the lane's row, ddy = bottom - top of its column).  The lane evaluates its neighbours'
@@ -240,17 +264,9 @@ __device__ __forceinline__ void interp(const DrawParams& p, uint32_t slot, int p
             }
         }
     } else {
+        const Betas9 o = betas64(X[0], X[1], X[2], Y[0], Y[1], Y[2], sx, sy, hs, vs, ar);
 #pragma unroll
-        for (int i = 0; i < 3; i++) {
-            const int a = (i + 1) % 3, b = (i + 2) % 3;
-            const long long dx = X[b] - X[a], dy = Y[b] - Y[a];
-            const long long E = dx * (long long)(sy - Y[a]) - dy * (long long)(sx - X[a]);
-            beta[i] = __fmul_rn((float)E, ar);
-            if (DERIV) {
-                betaH[i] = __fmul_rn((float)(E - dy * hs), ar);
-                betaV[i] = __fmul_rn((float)(E + dx * vs), ar);
-            }
-        }
+        for (int i = 0; i < 3; i++) { beta[i] = o.b[i]; betaH[i] = o.h[i]; betaV[i] = o.v[i]; }
     }
     depth = fmaf(Z[2], beta[2], fmaf(Z[1], beta[1], __fmul_rn(Z[0], beta[0])));
     if (NV == 0) return;
@@ -308,6 +324,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
                      : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     } while (!done);
 }
+
+// ---- TMA tensor copies of framebuffer blocks (descriptors: DrawParams::tmap, built by capi.cu: tma_maps) ---------------
+// Coordinates are in elements of the image (x innermost); boxes that hang over the image edge are clipped by the unit.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int x, int y, const void* src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(map), "r"(x), "r"(y), "r"(smem_u32(src)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_wait() {      // the staged source may be reused / released afterwards
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+// per-warp staging of one 8x4-pixel block: colour 512 B | depth 128 B | present 128 B; the eight rows together also hold
+// one 16x16 tile (colour 4096 B | depth 1024 B | present 1024 B) for the clear of empty tiles
+// IFR_TMA_EPILOGUE = 1: the blocks of covered tiles leave (and, for LOAD-op draws, arrive) through per-warp tensor copies
+// too.  Measured SLOWER than per-thread stores (profiles/r02_tma_ab.txt: c3 tile 0.332 -> 0.384 ms) — every warp ends
+// on a blocking wait for the unit to read its 512-byte staging row, which holds the CTA's registers and shared memory
+// while nothing computes — so the default build keeps TMA for what it wins: whole-tile clears of empty tiles and the
+// big-queue staging.
+#ifndef IFR_TMA_EPILOGUE
+#define IFR_TMA_EPILOGUE 0
+#endif
+#define IFR_STAGE_WORDS 192
+#define IFR_STAGE_DEPTH 128
+#define IFR_STAGE_PRESENT 160
 
 // ---- big triangles: setups precomputed by the fill pass arrive by TMA bulk copy (double buffered); every thread
 //      tests its own pixel against broadcast LDS.128 words, warps run independently.
@@ -465,6 +509,10 @@ __device__ __forceinline__ void clear_tile(const DrawParams& p, int tileX, int t
     if (px >= p.W || py >= p.H) return;
     const size_t pidx = (size_t)py * p.W + px;
     const bool scis = scissor_pass(p, px, py);
+    if (p.primIds) {      // per-draw debug ids: nothing of this draw lands here, cleared or not
+#pragma unroll
+        for (int s = 0; s < S; s++) p.primIds[pidx * S + s] = -1;
+    }
     if (!p.doClear || !scis) {
         if (p.present) p.present[pidx] = ifr_pack_rgba8(p.color[pidx]);   // untouched pixel: present what is there
         if (!p.doClear) return;
@@ -475,9 +523,34 @@ __device__ __forceinline__ void clear_tile(const DrawParams& p, int tileX, int t
         p.depth[pidx] = p.clearDepth;
         if (p.present) p.present[pidx] = ifr_pack_rgba8(cc);
     }
+}
+
+// The same for a group of empty tiles through TMA: the CTA builds one cleared tile in shared memory, one thread per tile
+// stores it (2 - 3 tensor copies instead of 256 threads x 2 - 3 stores).  Whole-frame clears without scissors only.
+template <int S>
+__device__ __forceinline__ void clear_tiles_tma(const DrawParams& p, float* stage, uint32_t e0, uint32_t e1, int ntiles, int tid) {
+    const float4 cc = make_float4(p.clearColor[0], p.clearColor[1], p.clearColor[2], p.clearColor[3]);
+    reinterpret_cast<float4*>(stage)[tid] = cc;
+    stage[1024 + tid] = p.clearDepth;
+    reinterpret_cast<uint32_t*>(stage)[1280 + tid] = ifr_pack_rgba8(cc);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (e0 + (uint32_t)tid < e1) {
+        const uint32_t t = p.tileOrder[ntiles - 1 - (int)(e0 + tid)];
+        const int x0 = (int)(t & 0xffffu) * IFR_TILE, y0 = (int)(t >> 16) * IFR_TILE;
+        tma_store_2d(&p.tmap[3], x0 * 4, y0, stage);
+        tma_store_2d(&p.tmap[4], x0, y0, stage + 1024);
+        if (p.present) tma_store_2d(&p.tmap[5], x0, y0, stage + 1280);
+        tma_store_commit_wait();
+    }
     if (p.primIds) {
+        for (uint32_t e = e0; e < e1; e++) {
+            const uint32_t t = p.tileOrder[ntiles - 1 - (int)e];
+            const int px = (int)(t & 0xffffu) * IFR_TILE + (tid & 15), py = (int)(t >> 16) * IFR_TILE + (tid >> 4);
+            if (px >= p.W || py >= p.H) continue;
 #pragma unroll
-        for (int s = 0; s < S; s++) p.primIds[pidx * S + s] = -1;
+            for (int sm = 0; sm < S; sm++) p.primIds[((size_t)py * p.W + px) * S + sm] = -1;
+        }
     }
 }
 
@@ -497,6 +570,10 @@ __global__ void __launch_bounds__(256, FsTraits<FS>::needsDerivs ? (S == 1 ? IFR
     __shared__ __align__(8) uint64_t mbar[2];
     __shared__ HizShared hz;
     __shared__ __align__(16) int covOff[8][3 * (S > 1 ? S : 1)];   // coverage_coop: one row per warp
+#if IFR_TMA_EPILOGUE
+    __shared__ __align__(128) float stage[8][IFR_STAGE_WORDS];     // TMA staging, one row per warp (see IFR_STAGE_WORDS)
+    __shared__ __align__(8) uint64_t stageBar[8];
+#endif
     constexpr int NV = FsTraits<FS>::nv;
 
     // Work list (scan pass): CTA b < nWork takes a tile with a non-empty queue; the CTAs behind them share the owned tiles
@@ -509,6 +586,11 @@ __global__ void __launch_bounds__(256, FsTraits<FS>::needsDerivs ? (S == 1 ? IFR
     if (blockIdx.x >= nWork) {
         const uint32_t e0 = (blockIdx.x - nWork) * IFR_EMPTY_PER_CTA;
         const uint32_t nEmpty = (uint32_t)p.counters[7];
+        if (p.useTma && p.doClear && !p.scissorEnable) {
+            // staged in the big-queue buffer, which a CTA without a tile never fills (6 KB of its 12)
+            if (e0 < nEmpty) clear_tiles_tma<S>(p, reinterpret_cast<float*>(&bigBuf[0][0]), e0, min(e0 + IFR_EMPTY_PER_CTA, nEmpty), ntiles, tid);
+            return;
+        }
         for (uint32_t e = e0; e < min(e0 + IFR_EMPTY_PER_CTA, nEmpty); e++) {
             const uint32_t t = p.tileOrder[ntiles - 1 - (int)e];
             clear_tile<S>(p, (int)(t & 0xffffu), (int)(t >> 16), tid);
@@ -539,8 +621,35 @@ __global__ void __launch_bounds__(256, FsTraits<FS>::needsDerivs ? (S == 1 ? IFR
 
     KeyMode km;     // precomputed by the host from p.depthFunc (same table as key_mode)
     km.xhi = p.keyXhi; km.xlo = p.keyXlo; km.ordered = p.keyOrdered != 0; km.equal = p.keyEqual != 0; km.never = p.keyNever != 0;
+#if IFR_TMA_EPILOGUE
+    // TMA path: the warp's 8x4 block leaves through one staged tensor store per image (epilogue).  A block that is not
+    // cleared as a whole first fetches its previous depth and colour the same way, so that the store can always write
+    // the whole block (pixels the draw leaves alone write back what was there; the tile is owned by this CTA).
+    float* const stg = stage[wrp];
+    const int bi = (ly & 3) * 8 + (lx & 7);
+    const int bx0 = tileX * IFR_TILE + (wrp & 1) * 8, by0 = tileY * IFR_TILE + (wrp >> 1) * 4;
+    bool prevLoaded = false;
+    if (p.useTma) {
+        prevLoaded = !__all_sync(0xffffffffu, !inFrame || (p.doClear && scis));
+        if (prevLoaded) {
+            if ((tid & 31) == 0) {
+                mbar_init(&stageBar[wrp], 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&stageBar[wrp])), "r"(640u) : "memory");
+                tma_load_2d(stg, &p.tmap[0], bx0 * 4, by0, &stageBar[wrp]);
+                tma_load_2d(stg + IFR_STAGE_DEPTH, &p.tmap[1], bx0, by0, &stageBar[wrp]);
+            }
+            __syncwarp();
+            mbar_wait(&stageBar[wrp], 0);
+        }
+    }
+#else
+    constexpr bool prevLoaded = false;
+    const float* const stg = nullptr;
+    constexpr int bi = 0;
+#endif
     float d0 = 0.0f;
-    if (inFrame) d0 = (p.doClear && scis) ? p.clearDepth : p.depth[pidx];
+    if (inFrame) d0 = (p.doClear && scis) ? p.clearDepth : (prevLoaded ? stg[IFR_STAGE_DEPTH + bi] : p.depth[pidx]);
     const unsigned long long k0 = key_init(km, d0);
     // Per-sample visibility keys.  S == 1: the pixel's key lives in a register (`best`); shared memory is only the
     // mailbox through which small triangles (processed by other threads) reach this pixel, filled from `best`
@@ -702,15 +811,16 @@ __global__ void __launch_bounds__(256, FsTraits<FS>::needsDerivs ? (S == 1 ? IFR
         }
         lastp1 = cur + 1u;
     }
-    if (inFrame) {
+    {
         const bool cleared = p.doClear && scis;
-        if (bg != S || cleared) {
-            float4 out = acc;
-            float dout = dacc;
+        const bool written = inFrame && (bg != S || cleared);
+        float4 out = acc;
+        float dout = dacc;
+        if (written) {
             if (bg > 0) {
                 const float fb = (float)bg;
                 const float4 prev = cleared ? make_float4(p.clearColor[0], p.clearColor[1], p.clearColor[2], p.clearColor[3])
-                                            : p.color[pidx];
+                                            : (prevLoaded ? reinterpret_cast<const float4*>(stg)[bi] : p.color[pidx]);
                 out.x = fmaf(fb, prev.x, out.x); out.y = fmaf(fb, prev.y, out.y);
                 out.z = fmaf(fb, prev.z, out.z); out.w = fmaf(fb, prev.w, out.w);
                 dout = fmaf(fb, d0, dout);
@@ -723,10 +833,34 @@ __global__ void __launch_bounds__(256, FsTraits<FS>::needsDerivs ? (S == 1 ? IFR
                 out.x = out.x / fs; out.y = out.y / fs; out.z = out.z / fs; out.w = out.w / fs;
                 dout = dout / fs;
             }
+        }
+#if IFR_TMA_EPILOGUE
+        if (p.useTma) {
+            // every pixel of the block is either written or holds its previous value (prevLoaded: a block with a pixel
+            // that is neither cleared nor off the frame has been fetched); pixels off the frame are clipped by the unit
+            if (!written) {
+                if (prevLoaded) { out = reinterpret_cast<const float4*>(stg)[bi]; dout = stg[IFR_STAGE_DEPTH + bi]; }
+                else { out = make_float4(0, 0, 0, 0); dout = 0.0f; }
+            }
+            __syncwarp();        // previous contents read by every lane before the row is overwritten
+            reinterpret_cast<float4*>(stg)[bi] = out;
+            stg[IFR_STAGE_DEPTH + bi] = dout;
+            if (p.present) reinterpret_cast<uint32_t*>(stg)[IFR_STAGE_PRESENT + bi] = ifr_pack_rgba8(out);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if ((tid & 31) == 0) {
+                tma_store_2d(&p.tmap[0], bx0 * 4, by0, stg);
+                tma_store_2d(&p.tmap[1], bx0, by0, stg + IFR_STAGE_DEPTH);
+                if (p.present) tma_store_2d(&p.tmap[2], bx0, by0, stg + IFR_STAGE_PRESENT);
+                tma_store_commit_wait();
+            }
+        } else
+#endif
+        if (written) {
             p.color[pidx] = out;
             p.depth[pidx] = dout;
             if (p.present) p.present[pidx] = ifr_pack_rgba8(out);
-        } else if (p.present) {
+        } else if (inFrame && p.present) {
             p.present[pidx] = ifr_pack_rgba8(p.color[pidx]);   // untouched pixel (no clear, nothing drawn): present what is there
         }
     }

@@ -361,6 +361,9 @@ class TileRasterRendererCuda:
     def setSamplerHardwareFilter(self, enable=True):
         self._ck(self._lib.iftrcuSetSamplerHardwareFilter(self._h, int(enable)))
 
+    def setTmaFramebuffer(self, enable=True):
+        self._ck(self._lib.iftrcuSetTmaFramebuffer(self._h, int(enable)))
+
     def setFramePipelining(self, enable=True):
         self._ck(self._lib.iftrcuSetFramePipelining(self._h, int(enable)))
 

@@ -220,6 +220,10 @@ IFRIT_B200_API int iftrcuSetVertexStageFused(iftrcuRenderer* h, int enable);
  * use the SFU approximations.  Error <= ~2^-9 x (texel range): within 1/255 per channel for textures in [0, 1], NOT
  * for HDR-range texels (tests/test_gpu_parity.py::test_fast_sampler_precision_contract). */
 IFRIT_B200_API int iftrcuSetSamplerHardwareFilter(iftrcuRenderer* h, int enable);
+/* Framebuffer traffic of the tile kernel through TMA (cp.async.bulk.tensor: block stores, tile-sized clears, block loads
+ * for draws that keep the previous contents).  DEFAULT on; results are bit-identical either way (A/B switch; the images
+ * of the reference are written by per-thread stores, CU:2235-2241, CU:3363-3391). */
+IFRIT_B200_API int iftrcuSetTmaFramebuffer(iftrcuRenderer* h, int enable);
 
 /* ---- draw ----------------------------------------------------------------------------- */
 IFRIT_B200_API int iftrcuClear(iftrcuRenderer* h);        /* RC::clear — fused into the next draw */

@@ -136,7 +136,7 @@ def _pointer_path(W, H, vb, idx, u, fs):
     r.Init()
     color = np.zeros((H, W, 4), np.float32)
     depth = np.zeros((H, W), np.float32)
-    r.bindFrameBuffer(color, depth, False)
+    r.bindFrameBuffer(color, depth)
     R.setup_scene(r, vb, idx, R.VS_MVP, fs, vb.shape[1] // 4 - 1, u)
     r.SetCullMode(R.IF_CULL_MODE_BACK)
     r.SetDepthFunc(1)
@@ -179,6 +179,7 @@ def test_scene_built_through_handles_matches_pointer_path():
     r.Init()
     h = r._h
     assert L.iftrcuBindFrameBufferHandle(h, fb, 0) == 0
+    r.width, r.height = W, H               # the Python mirror sizes its read-back arrays from these
     assert L.iftrcuBindVertexBufferHandle(h, hvb) == 0
     assert L.iftrcuBindIndexBufferHandle(h, hib) == 0
     assert L.iftrcuBindVertexShaderHandle(h, R.VS_MVP, vd) == 0

@@ -179,6 +179,49 @@ def test_back_to_back_draws_with_rebinding(gpu_renderer_factory, pipelining):
     assert np.array_equal(r2.readColor().view(np.uint32), col.view(np.uint32))
 
 
+@pytest.mark.parametrize("pipelining", [True, False])
+def test_queue_overflow_between_unsynchronised_draws(gpu_renderer_factory, pipelining):
+    """Advisor (round 1, high): the (triangle, tile) queues are sized by the first frame.  A camera that zooms in between
+    two draws issued WITHOUT a synchronize makes the pair count grow ~50x past the capacity — the second draw must
+    still come out complete (queues re-sized before its fill pass), and so must the third, drawn far away again."""
+    from ifrit_v2_b200 import renderer as R
+    W, H = 512, 384
+    rng = np.random.default_rng(11)
+    n = 96                                          # 96 layered triangles; zoomed in, each covers most of the 768 tiles
+    vb = np.zeros((3 * n, 8), np.float32)
+    for t in range(n):
+        c = rng.uniform(-0.2, 0.2, 2)
+        for k, (dx, dy) in enumerate(((-0.9, -0.8), (0.9, -0.7), (0.0, 0.95))):
+            vb[3 * t + k, :4] = (c[0] + dx, c[1] + dy, 0.1 + 0.8 * rng.random(), 1.0)
+            vb[3 * t + k, 4:] = rng.random(4)
+    idx = np.arange(3 * n, dtype=np.int32)
+    far = np.diag([0.02, 0.02, 1, 1]).astype(np.float32)
+    near = np.eye(4, dtype=np.float32)
+    r2 = gpu_renderer_factory()
+    r2.setFramePipelining(pipelining)
+    r2.bindFrameBuffer(None, None, W, H)
+    r2.bindVertexBuffer(vb); r2.bindIndexBuffer(idx)
+    r2.bindVertexShader(R.VS_MVP, 1); r2.bindFragmentShader(O.FS_VARYING0)
+    r2.CreateBuffer(0, scenes.uniform_block(far).nbytes)
+    r2.setClearValues([(0, 0, 0, 0)], 1.0)
+    for m in (far, near, far):
+        r2.copyHostBufferToBuffer(scenes.uniform_block(m), 0)
+        r2.clear()
+        r2.drawElements()                           # no synchronize() in between
+    o_far = oracle_draw(W, H, vb, idx, 1, O.FS_VARYING0, 1, scenes.uniform_block(far))
+    assert np.array_equal(r2.readColor().view(np.uint32), o_far["color"].view(np.uint32))
+    # and the zoomed frame itself, read right after an unsynchronised far -> near sequence
+    for m in (far, near):
+        r2.copyHostBufferToBuffer(scenes.uniform_block(m), 0)
+        r2.clear()
+        r2.drawElements()
+    o_near = oracle_draw(W, H, vb, idx, 1, O.FS_VARYING0, 1, scenes.uniform_block(near))
+    assert (o_near["prim_id"] >= 0).mean() > 0.5
+    assert np.array_equal(r2.readDepth().view(np.uint32), o_near["depth"].view(np.uint32))
+    assert np.array_equal(r2.readColor().view(np.uint32), o_near["color"].view(np.uint32))
+    assert r2.stats()["tile_pairs"] > 20 * (n // 4 + (W // 16) * (H // 16)) / 10
+
+
 @pytest.mark.parametrize("func", [O.CMP_ALWAYS, O.CMP_LESS, O.CMP_GEQUAL])
 @pytest.mark.parametrize("blend", [(6, 7, 1, 0), (1, 9, 9, 1), (8, 1, 0, 6)])
 def test_ordered_alpha_blending(r, blend, func):
@@ -418,6 +461,35 @@ def test_unsupported_verbs_return_status(r):
         r.setBlendFunc(True, 2, 3, 1, 0)      # SRC_COLOR / ONE_MINUS_SRC_COLOR: the reference aborts on them (CU:3466)
     assert e.value.code == R.IFRIT_ERR_UNSUPPORTED
     r.setBlendFunc(blendEnable=False)
+
+
+@pytest.mark.parametrize("W,H", [(400, 230), (333, 77), (64, 64)])
+def test_tma_framebuffer_path_equals_per_thread_stores(r, W, H):
+    """North-star N1: framebuffer blocks leave (and, for LOAD-op draws, arrive) through cp.async.bulk.tensor; the
+    per-thread store path (iftrcuSetTmaFramebuffer(0); always taken when the row pitch is not a multiple of 16 bytes,
+    W = 333) writes the same bits.  Covers: fused clear, empty tiles, LOAD-op draw with scissors on top, MSAA."""
+    vb, idx, u = _mesh_case(W, H)
+    rng = np.random.default_rng(5)
+    start = rng.random((H, W, 4), dtype=np.float32)
+    sc = [(W * 0.25, H * 0.2, W * 0.4, H * 0.5)]
+    res = {}
+    for tma in (True, False):
+        a = gpu_draw(r, W, H, vb, idx, 1, O.FS_NORMAL_COLOR, 2, u, msaa=4, cull=2, clear_color=(.1, .2, .3, 1), tma=tma)
+        b = gpu_draw(r, W, H, vb, idx, 1, O.FS_NORMAL_COLOR, 2, u, msaa=1, cull=1, clear=False, color=start,
+                     depth=np.full((H, W), 0.9, np.float32), scissors=sc, tma=tma)
+        res[tma] = (a, b)
+    for k in (0, 1):
+        for f in ("color", "depth", "prim_id"):
+            x, y = res[True][k][f], res[False][k][f]
+            assert np.array_equal(x.view(np.uint32), y.view(np.uint32)), (k, f)
+    # the LOAD-op draw leaves everything outside the scissor exactly as it was
+    b = res[True][1]
+    outside = np.ones((H, W), bool)
+    outside[int(H * 0.2) + 1:int(H * 0.7), int(W * 0.25) + 1:int(W * 0.65)] = False
+    assert np.array_equal(b["color"][outside], start[outside])
+    o = oracle_draw(W, H, vb, idx, 1, O.FS_NORMAL_COLOR, 2, u, msaa=1, cull=1, clear=False, color=start,
+                    depth=np.full((H, W), 0.9, np.float32), scissors=sc)
+    compare(o, b, exact_color=True)
 
 
 def test_cpp_host_through_cabi():

@@ -24,7 +24,7 @@ def oracle_draw(W, H, vb, idx, vs, fs, nvary, uniforms, msaa=1, cull=0, depth_fu
 def gpu_draw(r, W, H, vb, idx, vs, fs, nvary, uniforms, msaa=1, cull=0, depth_func=1, convention=0, clear=True,
              clear_color=(0, 0, 0, 0), clear_depth=1.0, scissors=None, texture=None, mip_levels=0, layers=1,
              sampler=None, color=None, depth=None, depth_test=True, partition=None, fused_vs=True, hw_filter=False,
-             blend=None):
+             blend=None, tma=True):
     from ifrit_v2_b200 import renderer as R
     c0 = np.zeros((H, W, 4), np.float32) if color is None else np.ascontiguousarray(color, np.float32)
     d0 = np.zeros((H, W), np.float32) if depth is None else np.ascontiguousarray(depth, np.float32)
@@ -43,6 +43,7 @@ def gpu_draw(r, W, H, vb, idx, vs, fs, nvary, uniforms, msaa=1, cull=0, depth_fu
     r.setDebugPrimitiveIds(True)
     r.setVertexStageFused(fused_vs)
     r.setSamplerHardwareFilter(hw_filter)
+    r.setTmaFramebuffer(tma)
     if blend:
         r.setBlendFunc(True, *blend)
     else:
