@@ -240,6 +240,10 @@ static void build_params(iftrcuRenderer* r, DrawParams& p) {
     p.hwFilter = r->hwFilter ? 1 : 0;
     tma_maps(r, p);
     p.blendEnable = r->blendEnable; memcpy(p.blendCoef, r->blendCoef, sizeof p.blendCoef);
+    if (!r->blendEnable) {      // blending off: src x 1 + dst x 0 (updateBlendStateKernel CU:3438-3443) — used by the ordered path of depth-writing shaders
+        const float off[4][4] = {{1, 0, 0, 0}, {0, 0, 0, 1}, {1, 0, 0, 0}, {0, 0, 0, 1}};
+        memcpy(p.blendCoef, off, sizeof off);
+    }
     int mnx = 255, mxx = 0, mny = 255, mxy = 0;
     const int ns = r->convention == IFRIT_CONVENTION_CPU ? 1 : r->msaa;
     for (int k = 0; k < r->msaa; k++) {
@@ -391,7 +395,8 @@ static int issue_draw(iftrcuRenderer* r, bool forceCheck, bool sameSet = false) 
         r->copyPending[r->cur] = false;
     }
     if (ev) CUDA_TRY(cudaEventRecord(ev[5], s));
-    if (r->blendEnable) CUDA_TRY(ifr_launch_tiles_blend(p, r->fsId, s));
+    // ordered path: blending, or a shader that writes depth (forceSort, CU:2517-2527)
+    if (r->blendEnable || r->fsId == IFRIT_FS_DEPTH_MOD) CUDA_TRY(ifr_launch_tiles_blend(p, r->fsId, s));
     else CUDA_TRY(ifr_launch_tiles(p, r->fsId, s));
     if (ev) { CUDA_TRY(cudaEventRecord(ev[6], s)); r->profDraws++; }
     if (pipe) { CUDA_TRY(cudaEventRecord(r->evTileDone[r->set], s)); r->tilePending[r->set] = true; }
@@ -753,7 +758,7 @@ int iftrcuBindVertexShader(iftrcuRenderer* h, int id, const int* varyingDescs, i
 }
 int iftrcuBindFragmentShader(iftrcuRenderer* h, int id) {
     R_CHECK(h);
-    if (id < IFRIT_FS_VARYING0 || id > IFRIT_FS_DERIV_VIS) return r->fail(IFRIT_ERR_INVALID, "bindFragmentShader", "unknown shader id");
+    if (id < IFRIT_FS_VARYING0 || id > IFRIT_FS_DEPTH_MOD) return r->fail(IFRIT_ERR_INVALID, "bindFragmentShader", "unknown shader id");
     r->fsId = id;
     return IFRIT_OK;
 }
@@ -764,9 +769,9 @@ int iftrcuLookupVertexShader(const char* name) {
     return -1;
 }
 int iftrcuLookupFragmentShader(const char* name) {
-    static const char* names[] = {"varying0", "normal_color", "prim_id", "textured", "textured_lod0", "skybox", "deriv_vis"};
+    static const char* names[] = {"varying0", "normal_color", "prim_id", "textured", "textured_lod0", "skybox", "deriv_vis", "depth_mod"};
     if (!name) return -1;
-    for (int i = 0; i < 7; i++) if (!strcmp(name, names[i])) return i;
+    for (int i = 0; i < 8; i++) if (!strcmp(name, names[i])) return i;
     return -1;
 }
 int iftrcuBindGeometryShader(iftrcuRenderer* h, int) { R_CHECK(h); return r->fail(IFRIT_ERR_UNSUPPORTED, "bindGeometryShader", "out of scope"); }
@@ -1018,7 +1023,8 @@ int iftrcuDrawElements(iftrcuRenderer* h) {
     if ((r->fsId == IFRIT_FS_TEXTURED || r->fsId == IFRIT_FS_TEXTURED_LOD0 || r->fsId == IFRIT_FS_SKYBOX || r->fsId == IFRIT_FS_DERIV_VIS) && r->bufSize[0] < 88)
         return r->fail(IFRIT_ERR_STATE, "drawElements", "buffer slot 0 must hold the 88-byte uniform block (MVP, light, lod bias, derivative scale)");
     if (r->vsId == IFRIT_VS_MVP && r->bufSize[0] < 64) return r->fail(IFRIT_ERR_STATE, "drawElements", "buffer slot 0 must hold the 64-byte MVP");
-    if (r->blendEnable && r->msaa != 1) return r->fail(IFRIT_ERR_UNSUPPORTED, "drawElements", "alpha blending is 1x only (the reference's blend kernel has no sample loop, CU:1649)");
+    if ((r->blendEnable || r->fsId == IFRIT_FS_DEPTH_MOD) && r->msaa != 1) return r->fail(IFRIT_ERR_UNSUPPORTED, "drawElements", "alpha blending / depth-writing shaders are 1x only (the reference's ordered kernel has no sample loop, CU:1649)");
+    if (r->fsId == IFRIT_FS_DEPTH_MOD && (!r->bufMem[0].p || r->bufSize[0] < 92)) return r->fail(IFRIT_ERR_STATE, "drawElements", "buffer slot 0 must hold the uniform block up to float[22] (depth offset scale)");
     if (r->fsId == IFRIT_FS_DERIV_VIS && !r->bufMem[0].p) return r->fail(IFRIT_ERR_STATE, "drawElements", "buffer slot 0 (uniform block) not created");
     return issue_draw(r, false);
 }

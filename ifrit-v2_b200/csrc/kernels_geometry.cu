@@ -262,6 +262,7 @@ __device__ __forceinline__ bool box_owned(const DrawParams& p, int tx0, int tx1,
     if (p.world <= 1) return true;
     constexpr int ST = IFR_SUPER / IFR_TILE;
     const int sx0 = tx0 / ST, sx1 = tx1 / ST, sy0 = ty0 / ST, sy1 = ty1 / ST;
+    if (sx0 == sx1 && sy0 == sy1) return (sx0 + 3 * sy0) % p.world == p.rank;     // the common case: one super-tile
     if ((sx1 - sx0 + 1) * (sy1 - sy0 + 1) > 16) return true;
     for (int sy = sy0; sy <= sy1; sy++)
         for (int sx = sx0; sx <= sx1; sx++)

@@ -107,6 +107,9 @@ __global__ void __launch_bounds__(256, 2) tile_blend_kernel(const __grid_constan
                 int prim = 0, fan = 0;
                 interp<NV, FsTraits<FS>::needsDerivs>(p, s.slot, px, py, v, ddx, ddy, depth2, prim, fan);
                 const float4 c = run_fs<FS>(p, v, ddx, ddy, prim, fan);
+                myFrags++;
+                const float d2 = fs_depth<FS>(p, v, d);
+                if (fs_modifies_depth(FS) && !depth_pass(p.depthFunc, d2, cur)) continue;     // late Z: second PS_DEPTHTEST, CU:1805
                 const float oms = __fsub_rn(1.0f, c.w), omd = __fsub_rn(1.0f, dst.w);
                 const float ms = blend_factor(p.blendCoef[0], oms, omd), md = blend_factor(p.blendCoef[1], oms, omd);
                 const float msa = blend_factor(p.blendCoef[2], oms, omd), mda = blend_factor(p.blendCoef[3], oms, omd);
@@ -114,10 +117,9 @@ __global__ void __launch_bounds__(256, 2) tile_blend_kernel(const __grid_constan
                 dst.y = __fadd_rn(__fmul_rn(dst.y, md), __fmul_rn(c.y, ms));
                 dst.z = __fadd_rn(__fmul_rn(dst.z, md), __fmul_rn(c.z, ms));
                 dst.w = __fadd_rn(__fmul_rn(dst.w, mda), __fmul_rn(c.w, msa));
-                cur = d;                     // CU:1828-1829: depth written, the next fragment tests against it
+                cur = d2;                    // CU:1828-1829: depth written, the next fragment tests against it
                 lastPrim = prim;
                 touched = true;
-                myFrags++;
             }
             __syncthreads();
         }
@@ -152,6 +154,7 @@ cudaError_t ifr_launch_tiles_blend(const DrawParams& p, int fsId, cudaStream_t s
         case IFRIT_FS_TEXTURED_LOD0: return p.hwFilter ? launch_blend<IFRIT_FS_TEXTURED_LOD0_FAST>(p, s) : launch_blend<IFRIT_FS_TEXTURED_LOD0>(p, s);
         case IFRIT_FS_SKYBOX: return launch_blend<IFRIT_FS_SKYBOX>(p, s);
         case IFRIT_FS_DERIV_VIS: return launch_blend<IFRIT_FS_DERIV_VIS>(p, s);
+        case IFRIT_FS_DEPTH_MOD: return launch_blend<IFRIT_FS_DEPTH_MOD>(p, s);
         default: return cudaErrorInvalidValue;
     }
 }

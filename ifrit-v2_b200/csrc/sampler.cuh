@@ -343,11 +343,20 @@ template <> struct FsTraits<IFRIT_FS_TEXTURED> { static constexpr bool needsDeri
 template <> struct FsTraits<IFRIT_FS_TEXTURED_LOD0> { static constexpr bool needsDerivs = false; static constexpr int nv = 2; };
 template <> struct FsTraits<IFRIT_FS_DERIV_VIS> { static constexpr bool needsDerivs = true; static constexpr int nv = 2; };
 
+// A shader that writes depth (FragmentShader::allowDepthModification, Shaders.h:61; `float* fragmentDepth`, CU:1803): its
+// draws take the ordered path with the depth test before and after the shader (kernels_tile.cu: tile_blend_kernel).
+__host__ __device__ constexpr bool fs_modifies_depth(int fs) { return fs == IFRIT_FS_DEPTH_MOD; }
+template <int FS>
+__device__ __forceinline__ float fs_depth(const DrawParams& p, const float4* v, float depth) {
+    if (FS == IFRIT_FS_DEPTH_MOD) return fmaf(p.u0[22], v[0].x, depth);
+    return depth;
+}
+
 template <int FS>
 __device__ __forceinline__ float4 run_fs(const DrawParams& p, const float4* v, const float4* ddx,
                                          const float4* ddy, int prim, int fan) {
     const float* u = p.u0;   // uniform block, constant bank
-    if (FS == IFRIT_FS_VARYING0) return v[0];
+    if (FS == IFRIT_FS_VARYING0 || FS == IFRIT_FS_DEPTH_MOD) return v[0];
     if (FS == IFRIT_FS_NORMAL_COLOR)
         return make_float4(fmaf(v[0].x, 0.5f, 0.5f), fmaf(v[0].y, 0.5f, 0.5f), fmaf(v[0].z, 0.5f, 0.5f), 0.5f);
     if (FS == IFRIT_FS_PRIM_ID) return make_float4((float)prim, (float)fan, 0.0f, 1.0f);

@@ -24,7 +24,7 @@ IF_POLYGON_MODE_FILL, IF_POLYGON_MODE_LINE, IF_POLYGON_MODE_POINT = 0, 1, 2
 IF_FORMAT_R32G32B32A32_SFLOAT = 1
 IFTP_FLOAT4 = 4
 VS_PASSTHROUGH, VS_MVP = 0, 1
-FS_VARYING0, FS_NORMAL_COLOR, FS_PRIM_ID, FS_TEXTURED, FS_TEXTURED_LOD0, FS_SKYBOX, FS_DERIV_VIS = range(7)
+FS_VARYING0, FS_NORMAL_COLOR, FS_PRIM_ID, FS_TEXTURED, FS_TEXTURED_LOD0, FS_SKYBOX, FS_DERIV_VIS, FS_DEPTH_MOD = range(8)
 CONVENTION_CUDA, CONVENTION_CPU = 0, 1
 IFRIT_OK, IFRIT_ERR_INVALID, IFRIT_ERR_UNSUPPORTED, IFRIT_ERR_CUDA, IFRIT_ERR_STATE = range(5)
 

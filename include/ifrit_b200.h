@@ -104,7 +104,7 @@ typedef struct {
 /* ---- shader registry (replaces the VertexShader / FragmentShader objects of Shaders.h:46-78) --
  * Uniform block = buffer slot 0 (reference: GetBufferPtr(slot), ShaderBuiltinCuda.cuh:394):
  *   float[0..15] MVP row-major, [16..18] light direction, [20] lod bias / cube lod,
- *   [21] derivative-visualisation scale. */
+ *   [21] derivative-visualisation scale, [22] depth offset scale of IFRIT_FS_DEPTH_MOD. */
 enum { IFRIT_VS_PASSTHROUGH = 0, /* pos = attr0, varying k = attr k+1 */
        IFRIT_VS_MVP = 1          /* pos = MVP * attr0, varying k = attr k+1 (DemoVertexShaderCuda) */ };
 enum { IFRIT_FS_VARYING0 = 0,     /* colour = varying 0 */
@@ -113,7 +113,10 @@ enum { IFRIT_FS_VARYING0 = 0,     /* colour = varying 0 */
        IFRIT_FS_TEXTURED = 3,     /* texture(0,0,vary,1,bias) * max(N.L, 0.2): adaptive-LOD or anisotropic */
        IFRIT_FS_TEXTURED_LOD0 = 4,/* textureLod(0,0,uv,0) * max(N.L, 0.2) */
        IFRIT_FS_SKYBOX = 5,       /* textureCubeLod(0,0,varying0.xyz,lod) */
-       IFRIT_FS_DERIV_VIS = 6     /* (ddx(v1).xy, ddy(v1).xy) * scale */ };
+       IFRIT_FS_DERIV_VIS = 6,    /* (ddx(v1).xy, ddy(v1).xy) * scale */
+       IFRIT_FS_DEPTH_MOD = 7     /* colour = varying 0, fragment depth += u[22] * varying0.x: a shader with
+                                   * allowDepthModification (Shaders.h:61) -> ordered path, depth test before AND after
+                                   * the shader (late Z, CU:1803-1805, CU:2517-2527); 1x only, as the reference */ };
 
 /* coverage-sample convention: which of the reference's two renderers is reproduced */
 enum { IFRIT_CONVENTION_CUDA = 0, /* TileRasterRendererCuda: pixel centre / MSAA table, clip at w=1e-3 */

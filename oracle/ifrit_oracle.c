@@ -489,8 +489,19 @@ static void run_fs(int fs_id, const fs_env* e, const orc_f4* v, const orc_f4* dd
         case ORC_FS_DERIV_VIS:
             out[0] = ddx[1].x * e->u[21]; out[1] = ddx[1].y * e->u[21];
             out[2] = ddy[1].x * e->u[21]; out[3] = ddy[1].y * e->u[21]; break;
+        case ORC_FS_DEPTH_MOD:      /* colour = varying 0; writes depth (fs_depth) */
+            out[0] = v[0].x; out[1] = v[0].y; out[2] = v[0].z; out[3] = v[0].w; break;
         default: out[0] = out[1] = out[2] = out[3] = 0.0f;
     }
+}
+
+/* Fragment shaders that write depth (reference: FragmentShader::allowDepthModification, Shaders.h:61; the shader receives
+ * `float* fragmentDepth`, CU:1803).  Such a draw takes the ordered path (CU:2517-2527: forceSort, pixelShadingAlphaBlendKernel)
+ * with the depth test run twice: before the shader on the interpolated depth, after it on the depth the shader left. */
+static int fs_modifies_depth(int fs_id) { return fs_id == ORC_FS_DEPTH_MOD; }
+static float fs_depth(int fs_id, const fs_env* e, const orc_f4* v, float depth) {
+    if (fs_id == ORC_FS_DEPTH_MOD) return fmaf(e->u[22], v[0].x, depth);      /* depth + u[22] * varying0.x */
+    return depth;
 }
 
 /* ------------------------------------------------------------------------- */
@@ -698,6 +709,8 @@ static int render_blend(const orc_state* st, const orc_f4* vary, int nvary, cons
                 float c[4];
                 run_fs(fs_id, env, v[l], ddx, ddy, r->prim, r->fan, c);
                 frags++;
+                const float d2 = fs_depth(fs_id, env, v[l], d);
+                if (!depth_pass(func, d2, depth[p])) continue;      /* second PS_DEPTHTEST, CU:1805 (late Z) */
                 float* dst = color + 4 * p;
                 const float oms = 1.0f - c[3], omd = 1.0f - dst[3];
                 const float ms = blend_factor(st->blend_coef[0], oms, omd), md = blend_factor(st->blend_coef[1], oms, omd);
@@ -705,7 +718,7 @@ static int render_blend(const orc_state* st, const orc_f4* vary, int nvary, cons
                 const float o0 = dst[0] * md + c[0] * ms, o1 = dst[1] * md + c[1] * ms, o2 = dst[2] * md + c[2] * ms;
                 const float o3 = dst[3] * mda + c[3] * msa;
                 dst[0] = o0; dst[1] = o1; dst[2] = o2; dst[3] = o3;
-                depth[p] = d;            /* CU:1828-1829: depth written, next fragment tests against it */
+                depth[p] = d2;           /* CU:1828-1829: depth written, next fragment tests against it */
                 prim_id[p] = r->prim;    /* last writer */
             }
     }
@@ -883,7 +896,7 @@ int orc_render(const orc_state* st, const orc_f4* pos, const orc_f4* vary, int n
                float* color, float* depth, int32_t* prim_id, int64_t* stats) {
     const int W = st->width, H = st->height, S = st->msaa, func = st->depth_func;
     if (nvary > MAXV || S > MAXS) return -1;
-    if (func == ORC_CMP_NOT_EQUAL && !st->blend_enable) return -2;
+    if (func == ORC_CMP_NOT_EQUAL && !st->blend_enable && !fs_modifies_depth(fs_id)) return -2;
     orc_tri* tris = (orc_tri*)malloc(sizeof(orc_tri) * 2 * (size_t)(ntri > 0 ? ntri : 1));
     const int ntris = orc_assemble(st, pos, idx, ntri, tris);
     /* slot -> assembled triangle */
@@ -893,7 +906,7 @@ int orc_render(const orc_state* st, const orc_f4* pos, const orc_f4* vary, int n
 
     if (st->do_clear) orc_clear(st, color, depth);
 
-    if (st->blend_enable) {
+    if (st->blend_enable || fs_modifies_depth(fs_id)) {
         if (S != 1) { free(by_slot); free(tris); return -3; }
         fs_env benv = {(const float*)uniforms, textures, samplers};
         const int rc = render_blend(st, vary, nvary, idx, tris, ntris, fs_id, &benv, color, depth, prim_id, stats);

@@ -40,7 +40,7 @@ enum { ORC_FILTER_NEAREST = 0, ORC_FILTER_LINEAR = 1 };
 /* vertex / fragment shader registry ids (same ids as include/ifrit_b200.h) */
 enum { ORC_VS_PASSTHROUGH = 0, ORC_VS_MVP = 1 };
 enum { ORC_FS_VARYING0 = 0, ORC_FS_NORMAL_COLOR = 1, ORC_FS_PRIM_ID = 2, ORC_FS_TEXTURED = 3,
-       ORC_FS_TEXTURED_LOD0 = 4, ORC_FS_SKYBOX = 5, ORC_FS_DERIV_VIS = 6 };
+       ORC_FS_TEXTURED_LOD0 = 4, ORC_FS_SKYBOX = 5, ORC_FS_DERIV_VIS = 6, ORC_FS_DEPTH_MOD = 7 };
 
 typedef struct {
     int32_t width, height;

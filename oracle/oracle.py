@@ -11,7 +11,7 @@ CONV_CUDA, CONV_CPU = 0, 1
 CULL_NONE, CULL_FRONT, CULL_BACK, CULL_FRONT_AND_BACK = 0, 1, 2, 3
 CMP_NEVER, CMP_LESS, CMP_EQUAL, CMP_LEQUAL, CMP_GREATER, CMP_NOT_EQUAL, CMP_GEQUAL, CMP_ALWAYS = range(8)
 VS_PASSTHROUGH, VS_MVP = 0, 1
-FS_VARYING0, FS_NORMAL_COLOR, FS_PRIM_ID, FS_TEXTURED, FS_TEXTURED_LOD0, FS_SKYBOX, FS_DERIV_VIS = range(7)
+FS_VARYING0, FS_NORMAL_COLOR, FS_PRIM_ID, FS_TEXTURED, FS_TEXTURED_LOD0, FS_SKYBOX, FS_DERIV_VIS, FS_DEPTH_MOD = range(8)
 
 
 class State(C.Structure):
@@ -76,6 +76,9 @@ def make_state(width, height, msaa=1, cull=CULL_NONE, depth_func=CMP_LESS, conve
         st.blend_enable = 1
         for i, f in enumerate(blend):
             st.blend_coef[i][:] = BLEND_COEF[f]
+    else:         # blending off: src x 1 + dst x 0 (updateBlendStateKernel CU:3438-3443) — what the ordered path of a
+        for i, c in enumerate(((1, 0, 0, 0), (0, 0, 0, 1), (1, 0, 0, 0), (0, 0, 0, 1))):   # depth-writing shader blends with
+            st.blend_coef[i][:] = c
     if scissors:
         st.scissor_enable, st.nscissor = 1, len(scissors)
         for i, s in enumerate(scissors):

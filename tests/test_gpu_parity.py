@@ -222,6 +222,35 @@ def test_queue_overflow_between_unsynchronised_draws(gpu_renderer_factory, pipel
     assert r2.stats()["tile_pairs"] > 20 * (n // 4 + (W // 16) * (H // 16)) / 10
 
 
+@pytest.mark.parametrize("func", [O.CMP_LESS, O.CMP_GEQUAL, O.CMP_ALWAYS])
+@pytest.mark.parametrize("blend", [None, (6, 7, 1, 0)])
+def test_fragment_shader_depth_write_late_z(r, func, blend):
+    """SURVEY §8f rank 1, late-Z arm: a fragment shader with allowDepthModification (Shaders.h:61) sends the draw down the
+    ordered path (forceSort, CU:2517-2527): per pixel, primitives in submission order, depth test on the interpolated
+    depth, shader, depth test again on the depth the SHADER left (CU:1803-1805), then colour (blended or replaced) and that
+    depth are written.  `depth_mod`: depth += u[22] * varying0.x.  Bit-exact against the oracle, blending on and off."""
+    W, H = 200, 120
+    vb, idx = scenes.random_tris(140, 311, neg_w_frac=0.1, size=0.35)
+    vb2, idx2 = scenes.random_tris(700, 312, size=0.03)
+    vb = np.concatenate([vb, vb2]); idx = np.arange(len(vb), dtype=np.int32)
+    vb[:, 7] = 0.2 + 0.6 * vb[:, 7]
+    u = IDENT.copy() if IDENT.size >= 32 else np.concatenate([IDENT.ravel(), np.zeros(32 - IDENT.size, np.float32)])
+    u[22] = -0.35                                   # large enough to reorder overlapping fragments
+    kw = dict(depth_func=func, clear_color=(.2, .3, .4, .5), clear_depth=0.6, blend=blend)
+    o = oracle_draw(W, H, vb, idx, 0, O.FS_DEPTH_MOD, 1, u, **kw)
+    g = gpu_draw(r, W, H, vb, idx, 0, O.FS_DEPTH_MOD, 1, u, **kw)
+    compare(o, g, exact_color=True)
+    # the shader's depth is what lands in the depth buffer: it differs from the plain draw of the same scene
+    plain = oracle_draw(W, H, vb, idx, 0, O.FS_VARYING0, 1, u, depth_func=func, clear_color=(.2, .3, .4, .5), clear_depth=0.6)
+    assert (o["depth"] != plain["depth"]).mean() > 0.2
+    from ifrit_v2_b200 import renderer as R
+    r.setMsaaSamples(4)
+    with pytest.raises(R.IfritError) as e:          # 1x only, as the reference's ordered kernel
+        r.drawElements()
+    assert e.value.code == R.IFRIT_ERR_UNSUPPORTED
+    r.setMsaaSamples(1)
+
+
 @pytest.mark.parametrize("func", [O.CMP_ALWAYS, O.CMP_LESS, O.CMP_GEQUAL])
 @pytest.mark.parametrize("blend", [(6, 7, 1, 0), (1, 9, 9, 1), (8, 1, 0, 6)])
 def test_ordered_alpha_blending(r, blend, func):

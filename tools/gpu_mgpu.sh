@@ -3,7 +3,7 @@
 N=${1:-2}; tag=${2:-x}; o=gpurun_out; mkdir -p $o
 nvidia-smi -L > $o/smi_mgpu_$tag.txt 2>&1
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 tests/mgpu_check.py > $o/mgpu_check_$tag.log 2>&1; echo "mgpu_check rc=$?"; grep -E "identical|MGPU" $o/mgpu_check_$tag.log
-for cfg in c2 c5; do
+for cfg in ${CFGS:-c3 c5}; do
 for n in 1 $N; do
   if [ $n = 1 ]; then cmd="python"; else cmd="python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29544"; fi
   steps=200; [ $cfg = c5 ] && steps=5
