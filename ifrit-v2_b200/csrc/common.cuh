@@ -2,9 +2,18 @@
 // B200 (sm_100a) only.  See DESIGN.md §3 for the arithmetic specification these kernels
 // implement bit-for-bit (integer coverage / ids / depth) against oracle/ifrit_oracle.c.
 #pragma once
+#ifdef __CUDACC_RTC__
+// Runtime compilation of user fragment shaders (capi.cu: iftrcuCreateFragmentShaderFromSource): NVRTC has the CUDA device
+// API built in and no host headers; the few host-side names the shared structs mention get stand-ins.
+typedef signed char int8_t; typedef unsigned char uint8_t; typedef short int16_t; typedef unsigned short uint16_t;
+typedef int int32_t; typedef unsigned int uint32_t; typedef long long int64_t; typedef unsigned long long uint64_t;
+typedef unsigned long long uintptr_t;
+struct alignas(64) CUtensorMap { unsigned long long opaque[16]; };
+#else
 #include <cuda_runtime.h>
 #include <cuda.h>      // CUtensorMap (type only: nothing links libcuda, the encoder is fetched with cudaGetDriverEntryPoint)
 #include <stdint.h>
+#endif
 
 #define IFR_TILE 16          // tile edge in pixels (reference: CU_TILE_WIDTH, KC:36-42)
 #define IFR_TILE_PIX 256
@@ -133,6 +142,7 @@ __host__ __device__ inline int ifr_tile_owner(int tx, int ty, int world) {
     return (sx + 3 * sy) % world;
 }
 
+#ifndef __CUDACC_RTC__
 #define CUDA_TRY(expr)                                                                       \
     do {                                                                                     \
         cudaError_t _e = (expr);                                                             \
@@ -156,3 +166,7 @@ cudaError_t ifr_launch_flag_store(uint32_t* word, uint32_t value, cudaStream_t s
 cudaError_t ifr_launch_flag_wait(const uint32_t* words, int n, uint32_t value, uint32_t* timedOut, cudaStream_t s);
 #define IFR_FLAG_WORDS 128    // frame-flag block at the tail of the depth allocation: [0..63] per-rank, [64] owner's release
 int ifr_kernels_per_draw();
+#endif   // !__CUDACC_RTC__
+#ifndef IFR_FLAG_WORDS
+#define IFR_FLAG_WORDS 128
+#endif

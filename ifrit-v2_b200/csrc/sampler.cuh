@@ -328,6 +328,12 @@ __device__ __forceinline__ float4 tex_grad(const TexDesc& t, const SampDesc& s, 
 // the texture unit (8-bit weights) and single-instruction SFU forms of sqrt / divide / log2 in the LOD and
 // lighting math.  Selected by the launcher when iftrcuSetSamplerHardwareFilter is on (the default); the
 // plain ids keep the oracle's arithmetic op for op.
+// a fragment shader compiled at run time from CUDA source (iftrcuCreateFragmentShaderFromSource): the user's function is
+// declared here and defined by the generated translation unit (capi.cu: rtc_compile)
+#ifdef __CUDACC_RTC__
+struct IfritFsInput;
+__device__ float4 ifrit_user_fs_entry(const DrawParams& p, const float4* v, const float4* ddx, const float4* ddy, int prim, int fan);
+#endif
 #define IFRIT_FS_TEXTURED_FAST 100
 #define IFRIT_FS_TEXTURED_LOD0_FAST 101
 // `textured` with the sampler state LINEAR / REPEAT / REPEAT / anisotropic compiled in (sample_aniso_repeat)
@@ -356,6 +362,9 @@ template <int FS>
 __device__ __forceinline__ float4 run_fs(const DrawParams& p, const float4* v, const float4* ddx,
                                          const float4* ddy, int prim, int fan) {
     const float* u = p.u0;   // uniform block, constant bank
+#ifdef __CUDACC_RTC__
+    if (FS == IFRIT_FS_USER) return ifrit_user_fs_entry(p, v, ddx, ddy, prim, fan);
+#endif
     if (FS == IFRIT_FS_VARYING0 || FS == IFRIT_FS_DEPTH_MOD) return v[0];
     if (FS == IFRIT_FS_NORMAL_COLOR)
         return make_float4(fmaf(v[0].x, 0.5f, 0.5f), fmaf(v[0].y, 0.5f, 0.5f), fmaf(v[0].z, 0.5f, 0.5f), 0.5f);

@@ -870,6 +870,7 @@ __global__ void __launch_bounds__(256, FsTraits<FS>::needsDerivs ? (S == 1 ? IFR
 }
 
 
+#ifndef __CUDACC_RTC__
 template <int FS>
 static inline cudaError_t launch_fs(const DrawParams& p, cudaStream_t s) {
     const dim3 grid(p.tilesX * p.tilesY);   // upper bound of the work list: surplus CTAs exit at once
@@ -895,3 +896,4 @@ static inline cudaError_t launch_fs(const DrawParams& p, cudaStream_t s) {
 #undef IFR_LAUNCH
     return cudaGetLastError();
 }
+#endif   // !__CUDACC_RTC__

@@ -94,6 +94,8 @@ def load_library():
             raise IfritError(IFRIT_ERR_CUDA, f"{LIB_PATH} is missing: run `make -C ifrit-v2_b200/csrc` "
                                              "(or __graft_entry__.build()); there is no CPU fallback")
         L = C.CDLL(LIB_PATH)
+        L.iftrcuCreateFragmentShaderFromSource.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.iftrcuCheckFragmentShaderSource.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
         L.iftrcuGetLastError.restype = C.c_char_p
         L.iftrcuGetLastError.argtypes = [C.c_void_p]
         L.iftrcuOwnedTileBytes.restype = C.c_size_t
@@ -263,6 +265,14 @@ class TileRasterRendererCuda:
     def bindFragmentShader(self, shader):
         sid = shader if isinstance(shader, int) else self._lib.iftrcuLookupFragmentShader(shader.encode())
         self._ck(self._lib.iftrcuBindFragmentShader(self._h, sid))
+
+    def createFragmentShaderFromSource(self, source, numVaryings, needsDerivatives=False, name="user_fs"):
+        """CUDA source defining `__device__ float4 fs_main(const IfritFsInput& in)` -> shader id for bindFragmentShader
+        (NVRTC; include/ifrit_b200.h: iftrcuCreateFragmentShaderFromSource)."""
+        sid = C.c_int(-1)
+        self._ck(self._lib.iftrcuCreateFragmentShaderFromSource(self._h, name.encode(), source.encode(), int(numVaryings),
+                                                                int(bool(needsDerivatives)), C.byref(sid)))
+        return sid.value
 
     def bindGeometryShader(self, shader=0):
         self._ck(self._lib.iftrcuBindGeometryShader(self._h, shader))
@@ -445,6 +455,14 @@ class TileRasterRendererCuda:
 
 def owned_tile_bytes(width, height, rank, world):
     return load_library().iftrcuOwnedTileBytes(width, height, rank, world)
+
+
+def check_fragment_shader_source(source, numVaryings, needsDerivatives=False, msaa=1):
+    """Compile-only check of a run-time fragment shader (no GPU needed): (status code, compiler log)."""
+    L = load_library()
+    buf = C.create_string_buffer(1 << 16)
+    rc = L.iftrcuCheckFragmentShaderSource(source.encode(), int(numVaryings), int(bool(needsDerivatives)), int(msaa), buf, len(buf))
+    return rc, buf.value.decode(errors="replace")
 
 
 def setup_scene(r, vb, idx, vs, fs, nvary, uniforms, texture=None, mip_levels=0, sampler=None, layers=1):

@@ -23,8 +23,10 @@
  */
 #ifndef IFRIT_B200_H
 #define IFRIT_B200_H
+#ifndef __CUDACC_RTC__ /* NVRTC (runtime-compiled fragment shaders) has no host headers; the kernels' common.cuh supplies the integer types */
 #include <stddef.h>
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -114,9 +116,10 @@ enum { IFRIT_FS_VARYING0 = 0,     /* colour = varying 0 */
        IFRIT_FS_TEXTURED_LOD0 = 4,/* textureLod(0,0,uv,0) * max(N.L, 0.2) */
        IFRIT_FS_SKYBOX = 5,       /* textureCubeLod(0,0,varying0.xyz,lod) */
        IFRIT_FS_DERIV_VIS = 6,    /* (ddx(v1).xy, ddy(v1).xy) * scale */
-       IFRIT_FS_DEPTH_MOD = 7     /* colour = varying 0, fragment depth += u[22] * varying0.x: a shader with
+       IFRIT_FS_DEPTH_MOD = 7,    /* colour = varying 0, fragment depth += u[22] * varying0.x: a shader with
                                    * allowDepthModification (Shaders.h:61) -> ordered path, depth test before AND after
-                                   * the shader (late Z, CU:1803-1805, CU:2517-2527); 1x only, as the reference */ };
+                                   * the shader (late Z, CU:1803-1805, CU:2517-2527); 1x only, as the reference */
+       IFRIT_FS_USER = 1000       /* first id handed out by iftrcuCreateFragmentShaderFromSource */ };
 
 /* coverage-sample convention: which of the reference's two renderers is reproduced */
 enum { IFRIT_CONVENTION_CUDA = 0, /* TileRasterRendererCuda: pixel centre / MSAA table, clip at w=1e-3 */
@@ -142,6 +145,7 @@ typedef struct {
     float bary[3][2];
 } iftrcuAssembledTriangle;
 
+#ifndef __CUDACC_RTC__ /* entry points: host side only (the header is also compiled by NVRTC for its enums and PODs) */
 /* ---- lifetime (iftrCreateInstance / iftrDestroyInstance / iftrInit) ------------------ */
 IFRIT_B200_API int iftrcuCreateInstance(int cudaDevice, iftrcuRenderer** out);
 IFRIT_B200_API int iftrcuDestroyInstance(iftrcuRenderer* h);
@@ -173,6 +177,22 @@ IFRIT_B200_API int iftrcuBindIndexBufferDevice(iftrcuRenderer* h, const int* dev
 IFRIT_B200_API int iftrcuBindVertexShader(iftrcuRenderer* h, int vertexShaderId, const int* varyingTypeDescs,
                                           int numVaryings);
 IFRIT_B200_API int iftrcuBindFragmentShader(iftrcuRenderer* h, int fragmentShaderId);
+/* Fragment shader compiled at run time from CUDA source (the reference's counterpart is its shader JIT,
+ * engine/base/ShaderRuntime.h:24-37 + ComLLVMRuntime).  `cudaSource` defines
+ *     __device__ float4 fs_main(const IfritFsInput& in);
+ * with  in.varying[k] / in.ddx[k] / in.ddy[k] (float4, k < numVaryings; derivatives only if needsDerivatives),
+ * in.primitiveId, in.fanIndex, in.uniform[0..31] (buffer slot 0), and the sampling library
+ *     ifritTexture(in, texSlot, sampSlot, float2 uv, float2 duvdx, float2 duvdy, bias)     texture()
+ *     ifritTextureLod(in, texSlot, sampSlot, float2 uv, lod)                                 textureLod()
+ *     ifritTextureCubeLod(in, texSlot, sampSlot, float3 dir, lod)                            textureCubeLod()
+ * NVRTC (libnvrtc.so.12, loaded on first use) compiles the tile kernel around the function for sm_100a; the returned id
+ * (>= IFRIT_FS_USER) goes to iftrcuBindFragmentShader.  A source error returns IFRIT_ERR_INVALID with the compiler log in
+ * iftrcuGetLastError.  Not available on the ordered (blending) path. */
+IFRIT_B200_API int iftrcuCreateFragmentShaderFromSource(iftrcuRenderer* h, const char* name, const char* cudaSource,
+                                                        int numVaryings, int needsDerivatives, int* shaderIdOut);
+/* compile only (no device, no instance): IFRIT_OK, IFRIT_ERR_INVALID + the compiler log, or IFRIT_ERR_UNSUPPORTED without libnvrtc */
+IFRIT_B200_API int iftrcuCheckFragmentShaderSource(const char* cudaSource, int numVaryings, int needsDerivatives,
+                                                   int msaaSamples, char* logOut, size_t logCap);
 IFRIT_B200_API int iftrcuLookupVertexShader(const char* name);   /* -1 if unknown */
 IFRIT_B200_API int iftrcuLookupFragmentShader(const char* name); /* -1 if unknown */
 /* out of scope: always IFRIT_ERR_UNSUPPORTED */
@@ -292,6 +312,7 @@ IFRIT_B200_API int iftrcuPackOwnedTiles(iftrcuRenderer* h, void* devDst, size_t 
 IFRIT_B200_API int iftrcuUnpackOwnedTiles(iftrcuRenderer* h, const void* devSrc, int rank, int worldSize);
 IFRIT_B200_API size_t iftrcuOwnedTileBytes(int width, int height, int rank, int worldSize);
 
+#endif /* !__CUDACC_RTC__ */
 #ifdef __cplusplus
 }
 #endif

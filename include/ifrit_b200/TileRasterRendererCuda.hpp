@@ -68,6 +68,12 @@ public:
     void bindVertexShader(const char* name, int numVaryings) { bindVertexShader(iftrcuLookupVertexShader(name), numVaryings); }
     void bindFragmentShader(int fragmentShaderId) { ck(iftrcuBindFragmentShader(h_, fragmentShaderId)); }
     void bindFragmentShader(const char* name) { bindFragmentShader(iftrcuLookupFragmentShader(name)); }
+    // CUDA source of `__device__ float4 fs_main(const IfritFsInput& in)` compiled at run time (NVRTC) -> id for bindFragmentShader
+    int createFragmentShaderFromSource(const char* name, const char* cudaSource, int numVaryings, bool needsDerivatives) {
+        int id = -1;
+        ck(iftrcuCreateFragmentShaderFromSource(h_, name, cudaSource, numVaryings, needsDerivatives ? 1 : 0, &id));
+        return id;
+    }
     void bindGeometryShader(int id) { ck(iftrcuBindGeometryShader(h_, id)); }
 
     void CreateTexture(int slotId, const IfritImageCreateInfo& createInfo) { ck(iftrcuCreateTexture(h_, slotId, &createInfo)); }
