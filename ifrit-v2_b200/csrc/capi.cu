@@ -82,6 +82,8 @@ struct iftrcuRenderer {
     // fragment shaders compiled at run time (iftrcuCreateFragmentShaderFromSource): id = IFRIT_FS_USER + index
     struct RtcShader { std::string name, source; int nvary = 0, derivs = 0; cudaLibrary_t lib[5] = {}; cudaKernel_t kern[5] = {}; };
     std::vector<RtcShader> rtc;
+    int polygonMode = IF_POLYGON_MODE_FILL;     // iftrcuSetRasterizerPolygonMode
+    DevBuf primKeys, primSeg;                   // point / line modes: per-pixel winner keys, mapped segment ends (kernels_prim.cu)
     // TMA descriptors of the bound framebuffer (tma_maps), rebuilt when an image pointer or the size changes
     struct TmaCache { void* c = nullptr; void* d = nullptr; void* pr = nullptr; int W = 0, H = 0, ok = 0; CUtensorMap m[6]; } tma;
     bool useTma = true;    // iftrcuSetTmaFramebuffer
@@ -569,6 +571,37 @@ static int issue_draw(iftrcuRenderer* r, bool forceCheck, bool sameSet = false) 
     return IFRIT_OK;
 }
 
+static int flush_clear(iftrcuRenderer* r);
+cudaError_t ifr_launch_prims(const DrawParams& p, int mode, int vsId, int fsId, unsigned long long* keys, float4* seg, cudaStream_t s);
+// Point / line polygon modes (unifiedPointRasterEngineKernel CU:2932, unifiedLineRasterEngineKernel CU:3295): no binning, no
+// tiles — insertion by per-pixel 64-bit atomicMin, then one shading pass over the frame (kernels_prim.cu).
+static int issue_draw_prims(iftrcuRenderer* r) {
+    if (r->msaa != 1 || r->blendEnable || r->world > 1 || r->doubleBuffer || r->fsId >= IFRIT_FS_USER)
+        return r->fail(IFRIT_ERR_UNSUPPORTED, "drawElements", "point / line modes: 1x, no blending, no tile partition, no double buffering, registry shaders (as the reference's point / line pipelines)");
+    int rc = flush_clear(r);
+    if (rc) return rc;
+    if (r->geomStream) CUDA_TRY(cudaStreamSynchronize(r->geomStream));
+    CUDA_TRY(r->primKeys.ensure((size_t)r->W * r->H * 8));
+    CUDA_TRY(r->primSeg.ensure(std::max<size_t>(1, (size_t)r->icount) * 2 * sizeof(float4)));
+    CUDA_TRY(r->scr[0].counters.ensure(IFR_COUNTER_BYTES));
+    const int set = r->set;
+    r->set = 0;
+    DrawParams p;
+    build_params(r, p);
+    r->set = set;
+    if (!r->fusedVS) return r->fail(IFRIT_ERR_UNSUPPORTED, "drawElements", "point / line modes run the vertex shader in place (iftrcuSetVertexStageFused(1))");
+    CUDA_TRY(cudaMemsetAsync(r->scr[0].counters.p, 0, IFR_COUNTER_BYTES, r->stream));
+    CUDA_TRY(ifr_launch_prims(p, r->polygonMode, r->vsId, r->fsId, (unsigned long long*)r->primKeys.p, (float4*)r->primSeg.p, r->stream));
+    r->stats.kernel_launches += 3;
+    CUDA_TRY(cudaMemcpyAsync(r->hCounters, r->scr[0].counters.p, IFR_COUNTER_BYTES, cudaMemcpyDeviceToHost, r->stream));
+    r->haveDraw = true;
+    r->lastDrawCleared = false;
+    r->stats.triangles_submitted = (uint64_t)(r->icount / 3);
+    if (r->hPresent && !r->externalFB) CUDA_TRY(cudaMemcpyAsync(r->hPresent, r->presentBuf[0].p, (size_t)r->W * r->H * 4, cudaMemcpyDeviceToHost, r->stream));
+    else if (r->hColor && !r->externalFB) CUDA_TRY(cudaMemcpyAsync(r->hColor, r->dColor, (size_t)r->W * r->H * 16, cudaMemcpyDeviceToHost, r->stream));
+    return IFRIT_OK;
+}
+
 static int flush_clear(iftrcuRenderer* r) {
     if (!r->pendingClear || !r->dColor) return IFRIT_OK;
     DrawParams p;
@@ -653,7 +686,7 @@ int iftrcuDestroyInstance(iftrcuRenderer* h) {
     close_peer(r);
     if (r->copyStream) { cudaStreamSynchronize(r->copyStream); cudaStreamDestroy(r->copyStream); }
     for (int i = 0; i < 2; i++) { if (r->evFrame[i]) cudaEventDestroy(r->evFrame[i]); if (r->evCopy[i]) cudaEventDestroy(r->evCopy[i]); }
-    DevBuf* bufs[] = {&r->ownColor, &r->ownColor2, &r->ownDepth, &r->primIds, &r->ownVB, &r->ownIB, &r->presentBuf[0], &r->presentBuf[1]};
+    DevBuf* bufs[] = {&r->ownColor, &r->ownColor2, &r->ownDepth, &r->primIds, &r->ownVB, &r->ownIB, &r->presentBuf[0], &r->presentBuf[1], &r->primKeys, &r->primSeg};
     for (int k = 0; k < 2; k++) {
         iftrcuRenderer::Scratch& c = r->scr[k];
         DevBuf* sb[] = {&c.scanPartial, &c.pos, &c.vary, &c.rec, &c.clipBary, &c.tileBox, &c.fan1List, &c.heavyBits, &c.tileCount, &c.tileStart,
@@ -1091,7 +1124,8 @@ int iftrcuSetMsaaSamples(iftrcuRenderer* h, IfritSampleCountFlagBits s) {
 }
 int iftrcuSetRasterizerPolygonMode(iftrcuRenderer* h, IfritPolygonMode mode) {
     R_CHECK(h);
-    if (mode != IF_POLYGON_MODE_FILL) return r->fail(IFRIT_ERR_UNSUPPORTED, "setRasterizerPolygonMode", "line / point modes are out of scope");
+    if (mode != IF_POLYGON_MODE_FILL && mode != IF_POLYGON_MODE_LINE && mode != IF_POLYGON_MODE_POINT) return r->fail(IFRIT_ERR_INVALID, "setRasterizerPolygonMode", "unknown mode");
+    r->polygonMode = mode;
     return IFRIT_OK;
 }
 int iftrcuSetBlendFunc(iftrcuRenderer* h, const IfritColorAttachmentBlendState* s) {
@@ -1178,6 +1212,11 @@ int iftrcuDrawElements(iftrcuRenderer* h) {
     if (r->vsId == IFRIT_VS_MVP && !r->bufMem[0].p) return r->fail(IFRIT_ERR_STATE, "drawElements", "buffer slot 0 (uniform block) not created");
     if ((r->fsId == IFRIT_FS_TEXTURED || r->fsId == IFRIT_FS_TEXTURED_LOD0 || r->fsId == IFRIT_FS_SKYBOX) && (!r->tex[0].data || !r->bufMem[0].p))
         return r->fail(IFRIT_ERR_STATE, "drawElements", "texture slot 0 / buffer slot 0 not created");
+    if (r->polygonMode != IF_POLYGON_MODE_FILL) {
+        const int need = (r->fsId == IFRIT_FS_PRIM_ID) ? 0 : (r->fsId == IFRIT_FS_TEXTURED || r->fsId == IFRIT_FS_TEXTURED_LOD0 || r->fsId == IFRIT_FS_DERIV_VIS) ? 2 : 1;
+        if (r->fsId < IFRIT_FS_USER && r->nvary < need) return r->fail(IFRIT_ERR_STATE, "drawElements", "fragment shader needs more varyings than the vertex shader outputs");
+        return issue_draw_prims(r);
+    }
     if (r->fsId >= IFRIT_FS_USER) {
         const int ui = r->fsId - IFRIT_FS_USER;
         if (ui >= (int)r->rtc.size()) return r->fail(IFRIT_ERR_STATE, "drawElements", "unknown run-time shader");

@@ -14,6 +14,23 @@ __device__ __forceinline__ uint32_t mono(float d) {
     return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
 }
 
+// the vertex shader functors of the registry (position only: both pass the other attributes through)
+template <int VS>
+__device__ __forceinline__ float4 run_vs(const DrawParams& p, const float4 a0) {
+    if (VS == IFRIT_VS_MVP) {
+        const float4* m = reinterpret_cast<const float4*>(p.u0);   // constant bank
+        const float4 r0 = m[0], r1 = m[1], r2 = m[2], r3 = m[3];
+        float4 o;
+        o.x = fmaf(r0.w, a0.w, fmaf(r0.z, a0.z, fmaf(r0.y, a0.y, __fmul_rn(r0.x, a0.x))));
+        o.y = fmaf(r1.w, a0.w, fmaf(r1.z, a0.z, fmaf(r1.y, a0.y, __fmul_rn(r1.x, a0.x))));
+        o.z = fmaf(r2.w, a0.w, fmaf(r2.z, a0.z, fmaf(r2.y, a0.y, __fmul_rn(r2.x, a0.x))));
+        o.w = fmaf(r3.w, a0.w, fmaf(r3.z, a0.z, fmaf(r3.y, a0.y, __fmul_rn(r3.x, a0.x))));
+        return o;
+    }
+    return a0;
+}
+
+
 struct RecRegs { int X[3], Y[3]; float Z[3]; float ar; uint32_t flags; };
 
 __device__ __forceinline__ void load_rec(const DrawParams& p, uint32_t slot, RecRegs& rr) {

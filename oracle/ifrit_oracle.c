@@ -726,6 +726,153 @@ static int render_blend(const orc_state* st, const orc_f4* vary, int nvary, cons
     return 0;
 }
 
+/* ------------------------------------------------------------------------- */
+/* Point and line polygon modes.  PARITY UNPINNED: the reference implements them only in its CUDA
+ * renderer, which does not build here, so these restate CU:2782-2973 (points) and CU:2976-3334 (lines) from the source
+ * alone.  Both work per PIXEL: every candidate that lands on the pixel competes with the smallest z (strict <; the
+ * reference keeps whichever candidate its atomics listed first on a tie — here the lowest candidate id), the winner is
+ * shaded if its z is strictly below the stored depth (the compare op is ignored, CU:2917 / CU:3280), colour replaces,
+ * depth = z.  No MSAA, no blending, no derivatives (zeros).  Deliberate deviations, each a slip of the reference:
+ *   - pixelShadingKernel derives the row from `globalInvo / csFrameHeight` (CU:2859 / CU:3175): correct only for
+ *     square frames; restated with the frame width;
+ *   - devLineCullClip tests v1 twice against the upper bound (CU:3012): a segment whose SECOND end lies beyond 1.0 is
+ *     kept and rasterised past the frame edge; here its pixels outside the frame are skipped. */
+static float to_unit(float v) { return (float)((double)v * 0.5 + 0.5); }       /* `v * 0.5 + 0.5` with double literals */
+
+typedef struct { float x, y, z, w; } prim_v;
+static int point_pixel(const orc_state* st, orc_f4 v, int* px, int* py, float* z) {
+    if (v.w < 1e-8f) return 0;                                  /* CU_EPS, CU:2802 */
+    v.x /= v.w; v.y /= v.w; v.z /= v.w;
+    v.x = to_unit(v.x); v.y = to_unit(v.y);
+    if ((double)v.x < 0.0 || (double)v.x > 1.0 || (double)v.y < 0.0 || (double)v.y > 1.0) return 0;
+    *px = (int)(v.x * (float)(st->width - 1));
+    *py = (int)(v.y * (float)(st->height - 1));
+    *z = v.z;
+    return 1;
+}
+static float lerpf_ref(float a, float b, float t) { return a + (b - a) * t; }    /* ShaderOpsCuda.cuh:107-109 */
+
+/* clip + map of one segment (devLineCullClip CU:2976-3019); returns 0 if dropped */
+static int line_setup(orc_f4 v1, orc_f4 v2, orc_f4* o1, orc_f4* o2) {
+    if (v1.w < 0 && v2.w < 0) return 0;
+    if (v1.w < 0) {
+        const float deno = v2.w - v1.w, numo = (float)(-1.0 + (double)v2.w), t = numo / deno;
+        v1.x = lerpf_ref(v2.x, v1.x, t); v1.y = lerpf_ref(v2.y, v1.y, t); v1.z = lerpf_ref(v2.z, v1.z, t); v1.w = lerpf_ref(v2.w, v1.w, t);
+    }
+    if (v2.w < 0) {
+        const float deno = v1.w - v2.w, numo = (float)(-1.0 + (double)v1.w), t = numo / deno;
+        v2.x = lerpf_ref(v1.x, v2.x, t); v2.y = lerpf_ref(v1.y, v2.y, t); v2.z = lerpf_ref(v1.z, v2.z, t); v2.w = lerpf_ref(v1.w, v2.w, t);
+    }
+    v1.x /= v1.w; v1.y /= v1.w; v1.z /= v1.w;
+    v2.x /= v2.w; v2.y /= v2.w; v2.z /= v2.w;
+    v1.x = to_unit(v1.x); v1.y = to_unit(v1.y); v2.x = to_unit(v2.x); v2.y = to_unit(v2.y);
+    if (v1.x < 0.0f || v1.y < 0.0f || v1.x > 1.0f || v1.y > 1.0f) return 0;
+    if (v2.x < 0.0f || v2.y < 0.0f) return 0;                   /* (sic) upper bound of v2 not tested, CU:3012 */
+    *o1 = v1; *o2 = v2;
+    return 1;
+}
+/* position of pixel (px, py) along the segment (getPercent CU:3181-3197) */
+static float line_percent(const orc_state* st, orc_f4 v1, orc_f4 v2, int px, int py) {
+    v1.x *= (float)st->width; v1.y *= (float)st->height; v2.x *= (float)st->width; v2.y *= (float)st->height;
+    const float dx = fabsf(v2.x - v1.x), dy = fabsf(v2.y - v1.y);
+    if (dx >= dy) return ((float)px - v1.x) / (v2.x - v1.x);
+    return ((float)py - v1.y) / (v2.y - v1.y);
+}
+
+int orc_render_prims(const orc_state* st, int mode, const orc_f4* pos, const orc_f4* vary, int nvary, const int32_t* idx,
+                     int nidx, int fs_id, const void* uniforms, const orc_texture* textures, const orc_sampler* samplers,
+                     float* color, float* depth, int32_t* prim_id, int64_t* stats) {
+    const int W = st->width, H = st->height;
+    if (st->msaa != 1 || nvary > MAXV || (mode != 1 && mode != 2)) return -1;
+    if (st->do_clear) orc_clear(st, color, depth);
+    const size_t np = (size_t)W * H;
+    float* bestz = (float*)malloc(sizeof(float) * np);
+    int32_t* best = (int32_t*)malloc(sizeof(int32_t) * np);
+    for (size_t p = 0; p < np; p++) { bestz[p] = 1e9f; best[p] = -1; prim_id[p] = -1; }
+    fs_env env = {(const float*)uniforms, textures, samplers};
+    int64_t frags = 0;
+    if (mode == 2) {                                            /* IF_POLYGON_MODE_POINT: one point per index */
+        for (int i = 0; i < nidx; i++) {
+            int px, py; float z;
+            if (!point_pixel(st, pos[idx[i]], &px, &py, &z)) continue;
+            const size_t p = (size_t)py * W + px;
+            if (z < bestz[p]) { bestz[p] = z + 0.0f; best[p] = i; }
+        }
+        for (size_t p = 0; p < np; p++) {
+            if (best[p] < 0 || !(bestz[p] < depth[p])) continue;
+            const int vi = idx[best[p]];
+            orc_f4 v[MAXV], zero[MAXV];
+            memset(zero, 0, sizeof zero);
+            for (int k = 0; k < nvary; k++) v[k] = vary[(size_t)vi * nvary + k];
+            float c[4];
+            run_fs(fs_id, &env, v, zero, zero, vi, 0, c);
+            frags++;
+            memcpy(color + 4 * p, c, sizeof c);
+            depth[p] = bestz[p];
+            prim_id[p] = vi;                                   /* dAtriOriginalPrimId = the vertex index, CU:2815 */
+        }
+    } else {                                                    /* IF_POLYGON_MODE_LINE: the three edges of every triangle */
+        const int nl = (nidx / 3) * 3;
+        orc_f4* a = (orc_f4*)malloc(sizeof(orc_f4) * 2 * (size_t)(nl > 0 ? nl : 1));
+        uint8_t* ok = (uint8_t*)calloc((size_t)(nl > 0 ? nl : 1), 1);
+        for (int l = 0; l < nl; l++) {
+            const int t = l / 3, e = l % 3;
+            const orc_f4 v1 = pos[idx[3 * t + e]], v2 = pos[idx[3 * t + (e + 1) % 3]];
+            ok[l] = (uint8_t)line_setup(v1, v2, &a[2 * l], &a[2 * l + 1]);
+            if (!ok[l]) continue;
+            /* bresenhamRasterizationKernel CU:3060-3127 */
+            int x1 = (int)(a[2 * l].x * (float)(W - 1)), y1 = (int)(a[2 * l].y * (float)(H - 1));
+            int x2 = (int)(a[2 * l + 1].x * (float)(W - 1)), y2 = (int)(a[2 * l + 1].y * (float)(H - 1));
+            const int dxi = abs(x1 - x2), dyi = abs(y1 - y2);
+            const int major_x = dxi > dyi;
+            if (major_x ? (x2 < x1) : (y2 < y1)) { int tq = x1; x1 = x2; x2 = tq; tq = y1; y1 = y2; y2 = tq; }
+            int cx = x1, cy = y1;
+            const int n = major_x ? (x2 - x1) : (y2 - y1);
+            const float dslope = major_x ? fabsf(1.0f * (float)(y2 - y1) / (float)(x2 - x1)) : fabsf(1.0f * (float)(x2 - x1) / (float)(y2 - y1));
+            const int step = major_x ? ((y2 - y1) > 0 ? 1 : -1) : ((x2 - x1) > 0 ? 1 : -1);
+            float d = 0.0f;
+            for (int i = 0; i <= n; i++) {
+                if (cx >= 0 && cx < W && cy >= 0 && cy < H) {
+                    const size_t p = (size_t)cy * W + cx;
+                    const float pc = line_percent(st, a[2 * l], a[2 * l + 1], cx, cy);
+                    const float z = lerpf_ref(a[2 * l].z, a[2 * l + 1].z, pc);
+                    if (z < bestz[p]) { bestz[p] = z + 0.0f; best[p] = l; }      /* ascending l: ties keep the lowest id */
+                }
+                d += dslope;
+                if (d > 0.5f) { if (major_x) cy += step; else cx += step; d -= 1.0f; }
+                if (major_x) cx++; else cy++;
+            }
+        }
+        for (size_t p = 0; p < np; p++) {
+            if (best[p] < 0 || !(bestz[p] < depth[p])) continue;
+            const int l = best[p], t = l / 3, e = l % 3;
+            const orc_f4 v1 = a[2 * l], v2 = a[2 * l + 1];
+            const float pc = line_percent(st, v1, v2, (int)(p % W), (int)(p / W));
+            const float z1 = v1.w, z2 = v2.w;
+            const float zt = z1 * z2 / (z2 + pc * (z1 - z2));
+            const int i1 = idx[3 * t + e], i2 = idx[3 * t + (e + 1) % 3];
+            orc_f4 v[MAXV], zero[MAXV];
+            memset(zero, 0, sizeof zero);
+            for (int k = 0; k < nvary; k++) {
+                orc_f4 a1 = vary[(size_t)i1 * nvary + k], a2 = vary[(size_t)i2 * nvary + k];
+                a1.x /= z1; a1.y /= z1; a1.z /= z1; a1.w /= z1; a2.x /= z2; a2.y /= z2; a2.z /= z2; a2.w /= z2;
+                v[k].x = (pc * (a2.x - a1.x) + a1.x) * zt; v[k].y = (pc * (a2.y - a1.y) + a1.y) * zt;
+                v[k].z = (pc * (a2.z - a1.z) + a1.z) * zt; v[k].w = (pc * (a2.w - a1.w) + a1.w) * zt;
+            }
+            float c[4];
+            run_fs(fs_id, &env, v, zero, zero, t, 0, c);
+            frags++;
+            memcpy(color + 4 * p, c, sizeof c);
+            depth[p] = bestz[p];
+            prim_id[p] = l;                                    /* dAtriOriginalPrimId = triangle * 3 + edge, CU:3048-3050 */
+        }
+        free(a); free(ok);
+    }
+    free(bestz); free(best);
+    if (stats) { stats[0] = frags; stats[1] = frags; stats[2] = 0; }
+    return 0;
+}
+
 /* one horizontal band of the frame (rows y_begin .. y_end - 1, whole quad rows): coverage + visibility keys, then
  * quad shading + resolve.  Bands touch disjoint pixels, so the threads share nothing they write. */
 typedef struct {

@@ -93,6 +93,11 @@ int orc_render(const orc_state* st, const orc_f4* pos, const orc_f4* vary, int n
                const orc_texture* textures, const orc_sampler* samplers,
                float* color, float* depth, int32_t* prim_id, int64_t* stats);
 
+/* point (mode 2) / line (mode 1) polygon modes: one point per index / the three edges of every triangle; 1x only */
+int orc_render_prims(const orc_state* st, int mode, const orc_f4* pos, const orc_f4* vary, int nvary, const int32_t* idx,
+                     int nidx, int fs_id, const void* uniforms, const orc_texture* textures, const orc_sampler* samplers,
+                     float* color, float* depth, int32_t* prim_id, int64_t* stats);
+
 void orc_clear(const orc_state* st, float* color, float* depth);
 
 /* mip chain by repeated 2:1 blit (CUIMG:36-155); data holds all levels */

@@ -137,8 +137,8 @@ def texture_chain(level0, mip_levels, layers=1, filter=1):
     return data
 
 
-def render(st, pos, vary, idx, fs_id, uniforms, textures=None, samplers=None, color=None, depth=None):
-    """Returns dict(color [H,W,4], depth [H,W], prim_id [H,W,S], stats)."""
+def render(st, pos, vary, idx, fs_id, uniforms, textures=None, samplers=None, color=None, depth=None, polygon_mode=0):
+    """Returns dict(color [H,W,4], depth [H,W], prim_id [H,W,S], stats).  polygon_mode: 0 fill, 1 line, 2 point."""
     W, H, S = st.width, st.height, st.msaa
     idx = np.ascontiguousarray(idx, dtype=np.int32)
     pos = np.ascontiguousarray(pos, dtype=np.float32)
@@ -155,8 +155,12 @@ def render(st, pos, vary, idx, fs_id, uniforms, textures=None, samplers=None, co
     for i, s in enumerate(samplers or []):
         samps[i] = s
     uniforms = np.ascontiguousarray(uniforms if uniforms is not None else np.zeros(32), dtype=np.float32)
-    rc = lib().orc_render(C.byref(st), _p(pos), _p(vary), nvary, _p(idx), len(idx) // 3, fs_id, _p(uniforms),
-                          texs, samps, _p(color), _p(depth), _p(prim), _p(stats))
+    if polygon_mode:
+        rc = lib().orc_render_prims(C.byref(st), int(polygon_mode), _p(pos), _p(vary), nvary, _p(idx), len(idx), fs_id,
+                                    _p(uniforms), texs, samps, _p(color), _p(depth), _p(prim), _p(stats))
+    else:
+        rc = lib().orc_render(C.byref(st), _p(pos), _p(vary), nvary, _p(idx), len(idx) // 3, fs_id, _p(uniforms),
+                              texs, samps, _p(color), _p(depth), _p(prim), _p(stats))
     assert rc == 0, rc
     return dict(color=color, depth=depth, prim_id=prim, frags=int(stats[0]), covered=int(stats[1]),
                 assembled=int(stats[2]))

@@ -481,7 +481,7 @@ def test_small_triangle_soup_binning_stress(r):
 
 def test_unsupported_verbs_return_status(r):
     from ifrit_v2_b200 import renderer as R
-    for fn, args in ((r.bindGeometryShader, ()), (r.DrawMeshTasks, (1, 0)), (r.setRasterizerPolygonMode, (1,)),
+    for fn, args in ((r.bindGeometryShader, ()), (r.DrawMeshTasks, (1, 0)),
                      (r.SetDepthFunc, (R.IF_COMPARE_OP_NOT_EQUAL,))):
         with pytest.raises(R.IfritError) as e:
             fn(*args)
@@ -519,6 +519,37 @@ def test_tma_framebuffer_path_equals_per_thread_stores(r, W, H):
     o = oracle_draw(W, H, vb, idx, 1, O.FS_NORMAL_COLOR, 2, u, msaa=1, cull=1, clear=False, color=start,
                     depth=np.full((H, W), 0.9, np.float32), scissors=sc)
     compare(o, b, exact_color=True)
+
+
+@pytest.mark.parametrize("mode", [2, 1])
+def test_point_and_line_polygon_modes(r, mode):
+    """SURVEY §8f rank 4 (unifiedPointRasterEngineKernel CU:2932 / unifiedLineRasterEngineKernel CU:3295): one point per
+    index / the three Bresenham edges of every triangle; per pixel the candidate with the smallest z wins, is tested
+    strictly against the stored depth, shaded from the vertex's / the perspective-interpolated varyings, and replaces the
+    colour.  Bit-exact against the restatement (parity unpinned: the reference's CUDA renderer does not build)."""
+    from ifrit_v2_b200 import renderer as R
+    W, H = 320, 200
+    vb, idx, u = _mesh_case(W, H, n=48)
+    rng = np.random.default_rng(3)
+    start_c = rng.random((H, W, 4), dtype=np.float32)
+    start_d = np.full((H, W), 0.9, np.float32)           # part of the sphere lies behind it
+    for kw in (dict(clear_color=(.1, .2, .3, 1), clear_depth=255.0), dict(clear=False, color=start_c, depth=start_d)):
+        for fs in (O.FS_NORMAL_COLOR, O.FS_PRIM_ID):
+            o = oracle_draw(W, H, vb, idx, 1, fs, 2, u, polygon_mode=mode, **kw)
+            g = gpu_draw(r, W, H, vb, idx, 1, fs, 2, u, polygon_mode=mode, **kw)
+            compare(o, g, exact_color=True)
+            assert g["fragments_shaded"] == o["frags"] > (100 if mode == 2 else 1000)
+    # segments that cross w = 0 are clipped at w = 1; vertices behind the eye are dropped in point mode
+    vbr, idxr = scenes.random_tris(300, 77, neg_w_frac=0.3, size=0.5)
+    o = oracle_draw(W, H, vbr, idxr, 0, O.FS_VARYING0, 1, IDENT, polygon_mode=mode)
+    g = gpu_draw(r, W, H, vbr, idxr, 0, O.FS_VARYING0, 1, IDENT, polygon_mode=mode)
+    compare(o, g, exact_color=True)
+    r.setMsaaSamples(4)
+    with pytest.raises(R.IfritError) as e:
+        r.drawElements()
+    assert e.value.code == R.IFRIT_ERR_UNSUPPORTED
+    r.setMsaaSamples(1)
+    r.setRasterizerPolygonMode(0)
 
 
 def test_cpp_host_through_cabi():

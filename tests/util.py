@@ -8,7 +8,7 @@ from oracle import oracle as O
 
 def oracle_draw(W, H, vb, idx, vs, fs, nvary, uniforms, msaa=1, cull=0, depth_func=1, convention=0, clear=True,
                 clear_color=(0, 0, 0, 0), clear_depth=1.0, scissors=None, texture_chain=None, tex_dims=None,
-                mip_levels=0, layers=1, sampler=None, color=None, depth=None, blend=None):
+                mip_levels=0, layers=1, sampler=None, color=None, depth=None, blend=None, polygon_mode=0):
     st = O.make_state(W, H, msaa=msaa, cull=cull, depth_func=depth_func, convention=convention, clear=clear,
                       clear_color=clear_color, clear_depth=clear_depth, scissors=scissors, blend=blend)
     texs = samps = None
@@ -18,13 +18,13 @@ def oracle_draw(W, H, vb, idx, vs, fs, nvary, uniforms, msaa=1, cull=0, depth_fu
         samps = [O.make_sampler(filter=s.get("filterMode", 1), addr_u=s.get("addressModeU", 0),
                                 addr_v=s.get("addressModeV", 0), border=s.get("borderColor", 0),
                                 aniso=s.get("anisotropyEnable", False), max_aniso=s.get("maxAnisotropy", 1.0))]
-    return O.draw(st, vb, idx, vs, fs, nvary, uniforms, textures=texs, samplers=samps, color=color, depth=depth)
+    return O.draw(st, vb, idx, vs, fs, nvary, uniforms, textures=texs, samplers=samps, color=color, depth=depth, polygon_mode=polygon_mode)
 
 
 def gpu_draw(r, W, H, vb, idx, vs, fs, nvary, uniforms, msaa=1, cull=0, depth_func=1, convention=0, clear=True,
              clear_color=(0, 0, 0, 0), clear_depth=1.0, scissors=None, texture=None, mip_levels=0, layers=1,
              sampler=None, color=None, depth=None, depth_test=True, partition=None, fused_vs=True, hw_filter=False,
-             blend=None, tma=True):
+             blend=None, tma=True, polygon_mode=0):
     from ifrit_v2_b200 import renderer as R
     c0 = np.zeros((H, W, 4), np.float32) if color is None else np.ascontiguousarray(color, np.float32)
     d0 = np.zeros((H, W), np.float32) if depth is None else np.ascontiguousarray(depth, np.float32)
@@ -44,6 +44,7 @@ def gpu_draw(r, W, H, vb, idx, vs, fs, nvary, uniforms, msaa=1, cull=0, depth_fu
     r.setVertexStageFused(fused_vs)
     r.setSamplerHardwareFilter(hw_filter)
     r.setTmaFramebuffer(tma)
+    r.setRasterizerPolygonMode(polygon_mode)
     if blend:
         r.setBlendFunc(True, *blend)
     else:
