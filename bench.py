@@ -205,7 +205,7 @@ def run_ours(args, cfg_name, do_e2e=True, fast_sampler=True):
         rr.setSamplerHardwareFilter(fast_sampler)   # library default: the oracle's arithmetic (software fp32 lerps); the bench opts in to FAST (texture unit)
 
     configure(r)
-    sf = MG.SortFirstRenderer(r, dist, dev, mode=mg_mode) if world > 1 else None
+    sf = MG.SortFirstRenderer(r, dist, dev, mode=mg_mode, clears_every_frame=not getattr(args, 'no_preclear', False)) if world > 1 else None   # every bench frame is clear() + drawElements()
 
     def step():
         r.clear()
@@ -289,11 +289,14 @@ def run_ours(args, cfg_name, do_e2e=True, fast_sampler=True):
     # ---- N > 1: the gathered frame on rank 0 must equal the single-GPU frame bit for bit --------------------------
     frame_same = None
     if world > 1:
-        step()
+        r.clear()
+        r.drawElements()
+        sf.gather(hold=True)         # held until it has been read: a (pre-clearing) release lets the frame be overwritten
         torch.cuda.synchronize()
         dist.barrier()
         if rank == 0:
             got = r.readColor()
+            sf.release()
             one = R.TileRasterRendererCuda(local)
             one.Init()
             one.bindFrameBuffer(None, None, W, H)
@@ -473,6 +476,7 @@ def main():
     ap.add_argument("--no-exact-sampler", "--no-fast-sampler", dest="no_exact_sampler", action="store_true",
                     help="skip the extra run with the library's default (exact) sampler")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-preclear", action="store_true", help="A/B (N > 1, peer mode): plain frame release, every rank sends all of its tiles")
     ap.add_argument("--no-tma", action="store_true", help="A/B: framebuffer stores / clears by per-thread STG instead of TMA tensor copies")
     ap.add_argument("--mgpu", default="peer", choices=["peer", "nccl"],
                     help="N > 1: peer = tiles stored straight into rank 0's framebuffer over NVLink; nccl = pack + gather + unpack")

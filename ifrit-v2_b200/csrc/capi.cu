@@ -73,6 +73,7 @@ struct iftrcuRenderer {
     uint32_t* frameFlags = nullptr;       // frame-flag block of the bound framebuffer (own or peer), see kernels_image.cu
     uint32_t* hTimedOut = nullptr;        // pinned: set by a flag wait that gave up
     uint32_t fenceFrame = 0; bool fencePending = false;   // peer: next tile kernel waits for the owner's release
+    bool skipArmed = false; int lastSkip = 0;             // peer: the owner pre-cleared the frame (iftrcuFrameFenceCleared)
 
     // geometry
     const uint8_t* dVB = nullptr; DevBuf ownVB; int nverts = 0, stride = 0, nattr = 0; int attrOff[IFR_MAX_VARY + 1] = {0};
@@ -483,6 +484,8 @@ static int issue_draw(iftrcuRenderer* r, bool forceCheck, bool sameSet = false) 
     r->epoch++;
     if (r->epoch == 0) r->epoch = 1;
     build_params(r, p);
+    if (!sameSet) { r->lastSkip = (r->skipArmed && p.doClear && !p.scissorEnable && r->peerColor) ? 1 : 0; r->skipArmed = false; }
+    p.skipEmptyStores = r->lastSkip;
     const size_t ntiles = (size_t)p.tilesX * p.tilesY;
     cudaStream_t s = r->stream;                       // draw stream: tile kernel, read-backs
     cudaStream_t g = pipe ? r->geomStream : s;        // geometry stream
@@ -514,6 +517,7 @@ static int issue_draw(iftrcuRenderer* r, bool forceCheck, bool sameSet = false) 
             CUDA_TRY(sc.bigQueue.ensure((size_t)(c[5] + c[5] / 4 + 1024) * sizeof(TriS)));
             CUDA_TRY(cudaMemsetAsync((char*)sc.counters.p + 24, 0, 8, g));
             build_params(r, p);
+            p.skipEmptyStores = r->lastSkip;
         }
         sc.queueChecked = true;
     }
@@ -1170,6 +1174,7 @@ int iftrcuSetCullMode(iftrcuRenderer* h, IfritCullMode mode) {
 }
 int iftrcuSetClearValues(iftrcuRenderer* h, const float* rgba, int numColors, float clearDepth) {
     R_CHECK(h);
+    r->skipArmed = false;      // the owner's pre-clear used the previous values: send every tile of the next frame
     if (numColors > 0 && rgba) memcpy(r->clearColor, rgba, 16);
     r->clearDepth = clearDepth;
     return IFRIT_OK;
@@ -1389,7 +1394,28 @@ int iftrcuFrameRelease(iftrcuRenderer* h, uint32_t frameId) {
 }
 int iftrcuFrameFence(iftrcuRenderer* h, uint32_t frameId) {
     R_CHECK(h);
-    r->fenceFrame = frameId; r->fencePending = true;
+    r->fenceFrame = frameId; r->fencePending = true; r->skipArmed = false;
+    return IFRIT_OK;
+}
+/* Owner: release + the promise that the NEXT draw into this framebuffer starts with clear().  The tiles of the other ranks are
+ * cleared here, locally (one pass of HBM writes), before the release flag is raised; peers that fence with
+ * iftrcuFrameFenceCleared then keep the colour of their EMPTY tiles off NVLink (40 % of the c3 frame). */
+int iftrcuFrameReleaseCleared(iftrcuRenderer* h, uint32_t frameId) {
+    R_CHECK(h);
+    if (!r->frameFlags || !r->dColor) return r->fail(IFRIT_ERR_STATE, "FrameReleaseCleared", "no renderer-owned framebuffer bound");
+    if (r->world > 1) {
+        DrawParams p;
+        build_params(r, p);
+        p.skipEmptyStores = 2; p.scissorEnable = 0; p.present = nullptr;
+        CUDA_TRY(ifr_launch_clear(p, r->stream));
+        r->stats.kernel_launches += 1;
+    }
+    CUDA_TRY(ifr_launch_flag_store(r->frameFlags + 64, frameId, r->stream));
+    return IFRIT_OK;
+}
+int iftrcuFrameFenceCleared(iftrcuRenderer* h, uint32_t frameId) {
+    R_CHECK(h);
+    r->fenceFrame = frameId; r->fencePending = true; r->skipArmed = true;
     return IFRIT_OK;
 }
 

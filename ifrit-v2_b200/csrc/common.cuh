@@ -75,6 +75,9 @@ struct DrawParams {
     int doClear; float clearColor[4]; float clearDepth;
     int scissorEnable, nScissor; float scissor[IFR_MAX_SCISSOR][4];
     int rank, world;
+    // sort-first exchange: 1 = a peer whose owner has pre-cleared the frame (iftrcuFrameReleaseCleared) does not send the
+    // colour of its EMPTY tiles over NVLink in a clearing draw; 2 (clear_kernel only) = clear the tiles of the OTHER ranks
+    int skipEmptyStores;
     // ordered alpha blending (pixelShadingAlphaBlendKernel CU:1649-1897): colour src / colour dst / alpha src / alpha dst
     // coefficients {x1, x(1 - src.a), x(1 - dst.a), zero flag} (updateBlendStateKernel CU:3436-3537)
     int blendEnable; float blendCoef[4][4];

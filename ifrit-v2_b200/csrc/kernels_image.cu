@@ -19,8 +19,9 @@ __global__ void __launch_bounds__(256) clear_kernel(const __grid_constant__ Draw
             }
             if (!pass) { if (p.present) p.present[i] = ifr_pack_rgba8(p.color[i]); continue; }
         }
-        if (p.world > 1 && ifr_tile_owner((int)(i % p.W) / IFR_TILE, (int)(i / p.W) / IFR_TILE, p.world) != p.rank) continue;
+        if (p.world > 1 && (ifr_tile_owner((int)(i % p.W) / IFR_TILE, (int)(i / p.W) / IFR_TILE, p.world) != p.rank) != (p.skipEmptyStores == 2)) continue;
         p.color[i] = c;
+        if (p.skipEmptyStores == 2) continue;        // pre-clear of the other ranks' tiles: colour only (their depth stays with them)
         p.depth[i] = p.clearDepth;
         if (p.present) p.present[i] = ifr_pack_rgba8(c);
     }

@@ -519,7 +519,7 @@ __device__ __forceinline__ void clear_tile(const DrawParams& p, int tileX, int t
     }
     if (scis) {
         const float4 cc = make_float4(p.clearColor[0], p.clearColor[1], p.clearColor[2], p.clearColor[3]);
-        p.color[pidx] = cc;
+        if (p.skipEmptyStores != 1 || p.scissorEnable) p.color[pidx] = cc;
         p.depth[pidx] = p.clearDepth;
         if (p.present) p.present[pidx] = ifr_pack_rgba8(cc);
     }
@@ -538,7 +538,7 @@ __device__ __forceinline__ void clear_tiles_tma(const DrawParams& p, float* stag
     if (e0 + (uint32_t)tid < e1) {
         const uint32_t t = p.tileOrder[ntiles - 1 - (int)(e0 + tid)];
         const int x0 = (int)(t & 0xffffu) * IFR_TILE, y0 = (int)(t >> 16) * IFR_TILE;
-        tma_store_2d(&p.tmap[3], x0 * 4, y0, stage);
+        if (p.skipEmptyStores != 1) tma_store_2d(&p.tmap[3], x0 * 4, y0, stage);     // 1: the frame's owner has cleared it already
         tma_store_2d(&p.tmap[4], x0, y0, stage + 1024);
         if (p.present) tma_store_2d(&p.tmap[5], x0, y0, stage + 1280);
         tma_store_commit_wait();

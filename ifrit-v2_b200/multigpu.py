@@ -101,13 +101,16 @@ class SortFirstRenderer:
     on the device through flag words in rank 0's memory (iftrcuFrameSignal / Wait / Release / Fence) — no NCCL
     call and no host round trip per frame.  mode "nccl": pack -> NCCL gather -> unpack."""
 
-    def __init__(self, renderer, dist, device, same_stream=True, mode="nccl"):
+    def __init__(self, renderer, dist, device, same_stream=True, mode="nccl", clears_every_frame=False):
         """same_stream: the renderer was given torch's current stream (setStream), so pack -> NCCL ->
         unpack are ordered on the device and need no host synchronisation."""
         import torch
         self.r, self.dist, self.device, self.same_stream = renderer, dist, device, same_stream
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.mode = mode
+        # peer mode: the caller promises that every frame starts with clear() -> rank 0 pre-clears the other ranks' tiles when
+        # it releases a frame and the peers keep the colour of their empty tiles off NVLink (iftrcuFrameReleaseCleared)
+        self.clears_every_frame = clears_every_frame
         if mode == "peer" and self.world > 1:
             share_framebuffer(renderer, renderer.width, renderer.height, dist, device)
             self.frame = 0
@@ -127,9 +130,9 @@ class SortFirstRenderer:
             if self.rank == 0:
                 r.frameWait(self.frame)           # polls until every rank has signalled
                 if not hold:
-                    r.frameRelease(self.frame)
+                    r.frameRelease(self.frame, cleared=self.clears_every_frame)
             else:
-                r.frameFence(self.frame)          # my next tile kernel waits until rank 0 has released this frame
+                r.frameFence(self.frame, cleared=self.clears_every_frame)   # my next tile kernel waits until rank 0 has released this frame
             return
         n = max_owned_floats(r.width, r.height, self.world)
         if self.packed is None or self.packed.numel() != n:
@@ -150,4 +153,4 @@ class SortFirstRenderer:
     def release(self):
         """Peer mode, after gather(hold=True): rank 0 lets the other ranks overwrite the frame."""
         if self.world > 1 and self.mode == "peer" and self.rank == 0:
-            self.r.frameRelease(self.frame)
+            self.r.frameRelease(self.frame, cleared=self.clears_every_frame)

@@ -438,11 +438,13 @@ class TileRasterRendererCuda:
     def frameWait(self, frame_id):
         self._ck(self._lib.iftrcuFrameWait(self._h, C.c_uint32(frame_id)))
 
-    def frameRelease(self, frame_id):
-        self._ck(self._lib.iftrcuFrameRelease(self._h, C.c_uint32(frame_id)))
+    def frameRelease(self, frame_id, cleared=False):
+        fn = self._lib.iftrcuFrameReleaseCleared if cleared else self._lib.iftrcuFrameRelease
+        self._ck(fn(self._h, C.c_uint32(frame_id)))
 
-    def frameFence(self, frame_id):
-        self._ck(self._lib.iftrcuFrameFence(self._h, C.c_uint32(frame_id)))
+    def frameFence(self, frame_id, cleared=False):
+        fn = self._lib.iftrcuFrameFenceCleared if cleared else self._lib.iftrcuFrameFence
+        self._ck(fn(self._h, C.c_uint32(frame_id)))
 
     def packOwnedTiles(self, dev_ptr, nbytes):
         used = C.c_size_t()

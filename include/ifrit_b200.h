@@ -308,6 +308,11 @@ IFRIT_B200_API int iftrcuFrameSignal(iftrcuRenderer* h, uint32_t frameId);
 IFRIT_B200_API int iftrcuFrameWait(iftrcuRenderer* h, uint32_t frameId);
 IFRIT_B200_API int iftrcuFrameRelease(iftrcuRenderer* h, uint32_t frameId);
 IFRIT_B200_API int iftrcuFrameFence(iftrcuRenderer* h, uint32_t frameId);
+/* The same pair with a promise: the NEXT draw into this framebuffer begins with iftrcuClear (same clear values on every
+ * rank).  The owner clears the other ranks' tiles locally before raising the release; a peer that fences with the Cleared
+ * variant then skips the NVLink stores of the colour of its empty tiles in that draw.  Frames stay bit-identical. */
+IFRIT_B200_API int iftrcuFrameReleaseCleared(iftrcuRenderer* h, uint32_t frameId);
+IFRIT_B200_API int iftrcuFrameFenceCleared(iftrcuRenderer* h, uint32_t frameId);
 IFRIT_B200_API int iftrcuPackOwnedTiles(iftrcuRenderer* h, void* devDst, size_t dstBytes, size_t* usedBytes);
 IFRIT_B200_API int iftrcuUnpackOwnedTiles(iftrcuRenderer* h, const void* devSrc, int rank, int worldSize);
 IFRIT_B200_API size_t iftrcuOwnedTileBytes(int width, int height, int rank, int worldSize);
