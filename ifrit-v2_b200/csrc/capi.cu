@@ -88,6 +88,7 @@ struct iftrcuRenderer {
     // TMA descriptors of the bound framebuffer (tma_maps), rebuilt when an image pointer or the size changes
     struct TmaCache { void* c = nullptr; void* d = nullptr; void* pr = nullptr; int W = 0, H = 0, ok = 0; CUtensorMap m[6]; } tma;
     bool useTma = true;    // iftrcuSetTmaFramebuffer
+    bool useGridHint = false;   // measured: no effect (profiles/r02_ab.txt), so the conservative grid stays the default
     bool hwFilter = false; // opt-in (iftrcuSetSamplerHardwareFilter): bilinear footprints through the TEX unit, 8-bit weights, SFU forms
 
     // state (defaults: TileRasterRendererCuda.h:42-47, CU:186-189)
@@ -110,6 +111,7 @@ struct iftrcuRenderer {
     struct Scratch {
         DevBuf scanPartial, pos, vary, rec, clipBary, tileBox, fan1List, heavyBits, tileCount, tileStart, tileCursor, tileOrder, queue, bigQueue, counters;
         bool queueChecked = false;   // queue capacity verified for the current geometry / state
+        uint32_t gridHint = 0;       // exact CTA count of the tile kernel for that geometry / state (DrawParams::gridHint)
     } scr[2];
     int set = 0;                 // scratch set of the current / most recent draw
     uint32_t epoch = 0;
@@ -347,7 +349,7 @@ int rtc_launch(iftrcuRenderer* r, const DrawParams& p, cudaStream_t s) {
     iftrcuRenderer::RtcShader& sh = r->rtc[idx];
     if (!sh.kern[mi]) { int rc = rtc_compile(r, sh, mi); if (rc) return rc; }   // first draw with this sample count
     void* args[] = {(void*)&p};
-    CUDA_TRY(cudaLaunchKernel((const void*)sh.kern[mi], dim3(p.tilesX * p.tilesY), dim3(256), args,
+    CUDA_TRY(cudaLaunchKernel((const void*)sh.kern[mi], dim3(p.gridHint ? p.gridHint : (uint32_t)(p.tilesX * p.tilesY)), dim3(256), args,
                               (size_t)p.msaa * IFR_TILE_PIX * sizeof(unsigned long long), s));
     return IFRIT_OK;
 }
@@ -520,7 +522,11 @@ static int issue_draw(iftrcuRenderer* r, bool forceCheck, bool sameSet = false) 
             p.skipEmptyStores = r->lastSkip;
         }
         sc.queueChecked = true;
+        // c[2] = tiles with work, c[7] = empty tiles: the tile kernel needs exactly this many CTAs for these inputs
+        sc.gridHint = (uint32_t)std::min<unsigned long long>(c[2] + (c[7] + IFR_EMPTY_PER_CTA - 1) / IFR_EMPTY_PER_CTA, ntiles);
+        if (sc.gridHint == 0) sc.gridHint = 1;
     }
+    p.gridHint = (sc.queueChecked && r->useGridHint) ? sc.gridHint : 0;
     CUDA_TRY(ifr_launch_fill(p, g));
     if (ev) CUDA_TRY(cudaEventRecord(ev[4], g));
     if (pipe) {
@@ -621,7 +627,7 @@ static int sync_and_check(iftrcuRenderer* r) {
     if (r->geomStream) CUDA_TRY(cudaStreamSynchronize(r->geomStream));
     CUDA_TRY(cudaStreamSynchronize(r->stream));
     if (r->doubleBuffer) CUDA_TRY(cudaStreamSynchronize(r->copyStream));
-    if (r->haveDraw && r->hCounters[3]) {
+    if (r->haveDraw && (r->hCounters[3] || r->hCounters[12])) {
         // the queue sized from an earlier frame was too small: grow it and re-issue the draw
         r->stats.queue_overflow = 1;
         r->pendingClear = r->lastDrawCleared;
@@ -1201,6 +1207,7 @@ int iftrcuSetFramePipelining(iftrcuRenderer* h, int enable) {
 }
 int iftrcuSetVertexStageFused(iftrcuRenderer* h, int enable) { R_CHECK(h); r->fusedVS = enable != 0; return IFRIT_OK; }
 int iftrcuSetTmaFramebuffer(iftrcuRenderer* h, int enable) { R_CHECK(h); r->useTma = enable != 0; return IFRIT_OK; }
+int iftrcuSetTileGridHint(iftrcuRenderer* h, int enable) { R_CHECK(h); r->useGridHint = enable != 0; return IFRIT_OK; }
 int iftrcuSetSamplerHardwareFilter(iftrcuRenderer* h, int enable) { R_CHECK(h); r->hwFilter = enable != 0; return IFRIT_OK; }
 
 int iftrcuClear(iftrcuRenderer* h) {

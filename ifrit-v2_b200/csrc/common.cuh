@@ -110,10 +110,14 @@ struct DrawParams {
     // empty tiles each.
     uint32_t* tileOrder;
     uint32_t* queue; uint32_t queueCap; TriS* bigQueue; uint32_t bigCap;
+    // tile kernel grid: the exact CTA count (work tiles + groups of empty tiles) read back by the draw that sized the queues for
+    // this geometry / state, 0 = not known (one CTA per tile, the surplus exits).  A grid that turns out too small (inputs changed
+    // behind the library's back) raises counters[9]; the host then re-issues the draw like a queue overflow.
+    uint32_t gridHint;
     uint32_t epoch; unsigned long long* scanPartial;   // chained scan: (epoch << 32 | block total) per scan CTA
     unsigned long long* counters;    // [0] assembled (host sum), [1] small pairs, [2] nWork (device) / frags (host sum), [3] overflow flag,
                                      // [4] fan1 count, [5] big pairs, [6] blending: a tile held more than IFR_BLEND_CAP triangles,
-                                     // [7] nEmpty, [8..11] scan tickets (one per scan class), [12..15] spare
+                                     // [7] nEmpty, [8..11] scan tickets (one per scan class), [12] tile grid too small, [13..15] spare
     // resources
     TexDesc tex[IFR_MAX_TEX]; SampDesc samp[IFR_MAX_TEX]; const float* buf[IFR_MAX_BUF];
     // the uniform block of the shader registry = the first 128 bytes of buffer slot 0 as last written through

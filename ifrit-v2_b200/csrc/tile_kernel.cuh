@@ -583,9 +583,13 @@ __global__ void __launch_bounds__(256, FsTraits<FS>::needsDerivs ? (S == 1 ? IFR
     const ulonglong2 hdr = *reinterpret_cast<const ulonglong2*>(p.counters + 2);   // {nWork, overflow flag}
     const uint32_t nWork = (uint32_t)hdr.x;
     const bool overflow = hdr.y != 0;
+    // the grid may come from an earlier draw of the same inputs (DrawParams::gridHint): tell the host if it no longer fits
+    if (blockIdx.x == gridDim.x - 1 && tid == 0 &&
+        nWork + ((uint32_t)p.counters[7] + IFR_EMPTY_PER_CTA - 1) / IFR_EMPTY_PER_CTA > gridDim.x) p.counters[12] = 1ull;
     if (blockIdx.x >= nWork) {
         const uint32_t e0 = (blockIdx.x - nWork) * IFR_EMPTY_PER_CTA;
         const uint32_t nEmpty = (uint32_t)p.counters[7];
+
         if (p.useTma && p.doClear && !p.scissorEnable) {
             // staged in the big-queue buffer, which a CTA without a tile never fills (6 KB of its 12)
             if (e0 < nEmpty) clear_tiles_tma<S>(p, reinterpret_cast<float*>(&bigBuf[0][0]), e0, min(e0 + IFR_EMPTY_PER_CTA, nEmpty), ntiles, tid);
@@ -873,7 +877,8 @@ __global__ void __launch_bounds__(256, FsTraits<FS>::needsDerivs ? (S == 1 ? IFR
 #ifndef __CUDACC_RTC__
 template <int FS>
 static inline cudaError_t launch_fs(const DrawParams& p, cudaStream_t s) {
-    const dim3 grid(p.tilesX * p.tilesY);   // upper bound of the work list: surplus CTAs exit at once
+    // one CTA per tile is the upper bound of the work list (surplus CTAs exit at once); the exact count when the host knows it
+    const dim3 grid(p.gridHint ? p.gridHint : (uint32_t)(p.tilesX * p.tilesY));
     const size_t smem = (size_t)p.msaa * IFR_TILE_PIX * sizeof(unsigned long long);
 #define IFR_LAUNCH(SS)                                                                                   \
     case SS: {                                                                                           \

@@ -374,6 +374,9 @@ class TileRasterRendererCuda:
     def setTmaFramebuffer(self, enable=True):
         self._ck(self._lib.iftrcuSetTmaFramebuffer(self._h, int(enable)))
 
+    def setTileGridHint(self, enable=True):
+        self._ck(self._lib.iftrcuSetTileGridHint(self._h, int(enable)))
+
     def setFramePipelining(self, enable=True):
         self._ck(self._lib.iftrcuSetFramePipelining(self._h, int(enable)))
 

@@ -247,6 +247,10 @@ IFRIT_B200_API int iftrcuSetSamplerHardwareFilter(iftrcuRenderer* h, int enable)
  * for draws that keep the previous contents).  DEFAULT on; results are bit-identical either way (A/B switch; the images
  * of the reference are written by per-thread stores, CU:2235-2241, CU:3363-3391). */
 IFRIT_B200_API int iftrcuSetTmaFramebuffer(iftrcuRenderer* h, int enable);
+/* Tile kernel grid = the exact CTA count measured by the draw that sized the queues for the bound inputs, instead of one
+ * CTA per tile with the surplus exiting.  DEFAULT off: measured no gain (c3 tile 0.3323 vs 0.3327 ms, profiles/r02_ab.txt).  Inputs changed behind the library's back are caught
+ * like a queue overflow: the draw is re-issued at the next synchronisation. */
+IFRIT_B200_API int iftrcuSetTileGridHint(iftrcuRenderer* h, int enable);
 
 /* ---- draw ----------------------------------------------------------------------------- */
 IFRIT_B200_API int iftrcuClear(iftrcuRenderer* h);        /* RC::clear — fused into the next draw */
