@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(256, 2) tile_blend_kernel(const __grid_constan
     __shared__ uint32_t skey[IFR_BLEND_CAP];
     __shared__ __align__(16) TriS batch[64];
     __shared__ uint8_t batchOk[64];
+    __shared__ uint32_t ctaSum;
     constexpr int NV = FsTraits<FS>::nv;
     const int tileX = blockIdx.x, tileY = blockIdx.y;
     if (p.world > 1 && ifr_tile_owner(tileX, tileY, p.world) != p.rank) return;
@@ -45,11 +46,7 @@ __global__ void __launch_bounds__(256, 2) tile_blend_kernel(const __grid_constan
     const uint32_t nSmall = overflow ? 0u : p.tileStart[tile + 1] - sStart;
     const uint32_t nBig = overflow ? 0u : p.tileStart[ntiles + 1 + tile + 1] - bStart;
     const size_t pidx = (size_t)py * p.W + px;
-    uint32_t n = nSmall + nBig;
-    if (n > IFR_BLEND_CAP) {             // reported by iftrcuSynchronize; the tile is cleared but not drawn
-        if (tid == 0) p.counters[6] = 1ull;
-        n = 0;
-    }
+    const uint32_t nAll = nSmall + nBig;
     const bool cleared = p.doClear && scis;
     float4 dst = make_float4(p.clearColor[0], p.clearColor[1], p.clearColor[2], p.clearColor[3]);
     float cur = p.clearDepth;
@@ -57,17 +54,55 @@ __global__ void __launch_bounds__(256, 2) tile_blend_kernel(const __grid_constan
     int lastPrim = -1;
     bool touched = false;
     unsigned int myFrags = 0;
-    if (n) {
+    // sort key = prim * 2 + fan: submission order (a slot appears at most once in a tile)
+    auto key_of = [&](uint32_t i) -> uint32_t {
+        const uint32_t slot = i < nSmall ? __ldg(p.queue + sStart + i) : p.bigQueue[bStart + (i - nSmall)].slot;
+        return slot >= (uint32_t)p.ntri ? (slot - (uint32_t)p.ntri) * 2u + 1u : slot * 2u;
+    };
+    // entries with lo <= key < hi, summed over the CTA
+    auto count_range = [&](uint32_t lo, uint32_t hi) -> uint32_t {
+        uint32_t c = 0;
+        for (uint32_t i = tid; i < nAll; i += 256) { const uint32_t k = key_of(i); c += (k >= lo && k < hi); }
+        c = __reduce_add_sync(0xffffffffu, c);
+        __syncthreads();
+        if (tid == 0) ctaSum = 0;
+        __syncthreads();
+        if ((tid & 31) == 0 && c) atomicAdd(&ctaSum, c);
+        __syncthreads();
+        return ctaSum;
+    };
+    // A tile with more than IFR_BLEND_CAP triangles is walked in rounds of consecutive key ranges [lo, hi), each holding at most
+    // IFR_BLEND_CAP entries (hi found by bisection over the key space: ~30 counting passes over the tile's queues per round —
+    // the spill path of very deep tiles; the usual tile takes the first branch and never counts).
+    const uint32_t keyEnd = 4u * (uint32_t)p.ntri + 2u;      // above every key
+    uint32_t lo = 0;
+    for (;;) {
+        uint32_t hi = keyEnd, n = nAll;
+        if (nAll > IFR_BLEND_CAP) {
+            n = count_range(lo, keyEnd);
+            if (n > IFR_BLEND_CAP) {
+                uint32_t a = lo + 1u, b = keyEnd;            // count(lo, a) <= 1: always feasible
+                while (a < b) {
+                    const uint32_t mid = a + (b - a + 1u) / 2u;
+                    if (count_range(lo, mid) <= IFR_BLEND_CAP) a = mid; else b = mid - 1u;
+                }
+                hi = a;
+                n = count_range(lo, hi);
+            }
+        } else if (lo) n = 0;
+        if (!n) break;
         uint32_t npow2 = 2;
         while (npow2 < n) npow2 <<= 1;
-        // sort key = prim * 2 + fan: submission order (a slot appears at most once in a tile)
-        for (uint32_t i = tid; i < npow2; i += 256) {
-            uint32_t k = 0xffffffffu;
-            if (i < n) {
-                const uint32_t slot = i < nSmall ? __ldg(p.queue + sStart + i) : p.bigQueue[bStart + (i - nSmall)].slot;
-                k = slot >= (uint32_t)p.ntri ? (slot - (uint32_t)p.ntri) * 2u + 1u : slot * 2u;
+        if (nAll <= IFR_BLEND_CAP) {
+            for (uint32_t i = tid; i < npow2; i += 256) skey[i] = i < n ? key_of(i) : 0xffffffffu;
+        } else {
+            for (uint32_t i = tid; i < npow2; i += 256) skey[i] = 0xffffffffu;
+            if (tid == 0) ctaSum = 0;
+            __syncthreads();
+            for (uint32_t i = tid; i < nAll; i += 256) {
+                const uint32_t k = key_of(i);
+                if (k >= lo && k < hi) skey[atomicAdd(&ctaSum, 1u)] = k;
             }
-            skey[i] = k;
         }
         __syncthreads();
         for (uint32_t k = 2; k <= npow2; k <<= 1)
@@ -123,6 +158,8 @@ __global__ void __launch_bounds__(256, 2) tile_blend_kernel(const __grid_constan
             }
             __syncthreads();
         }
+        if (hi == keyEnd) break;
+        lo = hi;
     }
     if (inFrame) {
         if (touched || cleared) {

@@ -221,7 +221,7 @@ IFRIT_B200_API int iftrcuSetRasterizerPolygonMode(iftrcuRenderer* h, IfritPolygo
 /* Ordered alpha blending (pixelShadingAlphaBlendKernel CU:1649-1897): fragments of a pixel are depth-tested, shaded and
  * blended in submission order, depth is written by every passing fragment.  Factors: ZERO, ONE, SRC_ALPHA, DST_ALPHA,
  * ONE_MINUS_SRC_ALPHA, ONE_MINUS_DST_ALPHA with the reference's coefficient table (CU:3436-3537: its *_ALPHA rows
- * select 1 - a and its ONE_MINUS_* rows a — replicated); 1x MSAA only; at most 4096 triangles per 16x16 tile. */
+ * select 1 - a and its ONE_MINUS_* rows a — replicated); 1x MSAA only.  Tiles holding more than 4096 triangles are walked in rounds of submission-order ranges. */
 IFRIT_B200_API int iftrcuSetBlendFunc(iftrcuRenderer* h, const IfritColorAttachmentBlendState* s);
 IFRIT_B200_API int iftrcuSetDepthFunc(iftrcuRenderer* h, IfritCompareOp op);
 IFRIT_B200_API int iftrcuSetDepthTestEnable(iftrcuRenderer* h, int enable);

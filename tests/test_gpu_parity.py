@@ -222,6 +222,22 @@ def test_queue_overflow_between_unsynchronised_draws(gpu_renderer_factory, pipel
     assert r2.stats()["tile_pairs"] > 20 * (n // 4 + (W // 16) * (H // 16)) / 10
 
 
+def test_ordered_path_beyond_4096_triangles_per_tile(r):
+    """The ordered (blending) path sorts a tile's triangles in shared memory, 4096 keys at a time: a tile with more than
+    that is walked in rounds of consecutive submission-order ranges (round 1 returned IFRIT_ERR_UNSUPPORTED here).  ~9000
+    triangles, most of them crowded into two tiles, clipped fans included; colour / depth / last writer bit-exact."""
+    W, H = 96, 64
+    vb, idx = scenes.random_tris(9000, 411, extent=0.12, size=0.16, neg_w_frac=0.02)
+    vb2, idx2 = scenes.random_tris(60, 412, size=0.5)
+    vb = np.concatenate([vb, vb2]); idx = np.arange(len(vb), dtype=np.int32)
+    vb[:, 7] = 0.05 + 0.3 * vb[:, 7]
+    kw = dict(depth_func=O.CMP_ALWAYS, clear_color=(.2, .3, .4, .5), clear_depth=0.5, blend=(6, 7, 1, 0))
+    o = oracle_draw(W, H, vb, idx, 0, O.FS_VARYING0, 1, IDENT, **kw)
+    g = gpu_draw(r, W, H, vb, idx, 0, O.FS_VARYING0, 1, IDENT, **kw)
+    compare(o, g, exact_color=True)
+    assert g["tile_pairs"] > 12000 and g["fragments_shaded"] == o["frags"]
+
+
 @pytest.mark.parametrize("func", [O.CMP_LESS, O.CMP_GEQUAL, O.CMP_ALWAYS])
 @pytest.mark.parametrize("blend", [None, (6, 7, 1, 0)])
 def test_fragment_shader_depth_write_late_z(r, func, blend):
