@@ -200,6 +200,8 @@ def run_ours(args, cfg_name, do_e2e=True, fast_sampler=True):
         rr.SetDepthFunc(R.IF_COMPARE_OP_LESS)
         rr.SetDepthTestEnable(True)
         rr.setClearValues([(0, 0, 0, 0)], 255.0)   # reference demo clear depth, SG/demo/DefaultDemo.cpp:355
+        if getattr(args, "tile_chunk", 0):
+            rr.setTileChunk(args.tile_chunk)     # A/B: pin the staged chunk of the tile kernel
         if getattr(args, "no_grid_hint", False):
             rr.setTileGridHint(False)        # A/B: one CTA per tile, the surplus exits
         if getattr(args, "no_tma", False):
@@ -479,6 +481,7 @@ def main():
                     help="skip the extra run with the library's default (exact) sampler")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-preclear", action="store_true", help="A/B (N > 1, peer mode): plain frame release, every rank sends all of its tiles")
+    ap.add_argument("--tile-chunk", type=int, default=0, choices=[0, 32, 64], help="A/B: big-queue entries per staged chunk of the tile kernel (0 = automatic)")
     ap.add_argument("--no-grid-hint", action="store_true", help="A/B: tile kernel grid of one CTA per tile instead of the measured CTA count")
     ap.add_argument("--no-tma", action="store_true", help="A/B: framebuffer stores / clears by per-thread STG instead of TMA tensor copies")
     ap.add_argument("--mgpu", default="peer", choices=["peer", "nccl"],

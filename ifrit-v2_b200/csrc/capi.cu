@@ -88,6 +88,7 @@ struct iftrcuRenderer {
     // TMA descriptors of the bound framebuffer (tma_maps), rebuilt when an image pointer or the size changes
     struct TmaCache { void* c = nullptr; void* d = nullptr; void* pr = nullptr; int W = 0, H = 0, ok = 0; CUtensorMap m[6]; } tma;
     bool useTma = true;    // iftrcuSetTmaFramebuffer
+    int forceBigChunk = 0;      // A/B: 32 / 64 pin the staged chunk size (iftrcuSetTileChunk)
     bool useGridHint = false;   // measured: no effect (profiles/r02_ab.txt), so the conservative grid stays the default
     bool hwFilter = false; // opt-in (iftrcuSetSamplerHardwareFilter): bilinear footprints through the TEX unit, 8-bit weights, SFU forms
 
@@ -112,6 +113,7 @@ struct iftrcuRenderer {
         DevBuf scanPartial, pos, vary, rec, clipBary, tileBox, fan1List, heavyBits, tileCount, tileStart, tileCursor, tileOrder, queue, bigQueue, counters;
         bool queueChecked = false;   // queue capacity verified for the current geometry / state
         uint32_t gridHint = 0;       // exact CTA count of the tile kernel for that geometry / state (DrawParams::gridHint)
+        uint32_t avgBig = 0xffffffffu;   // big-queue entries per non-empty tile of that draw (unknown: treated as deep)
     } scr[2];
     int set = 0;                 // scratch set of the current / most recent draw
     uint32_t epoch = 0;
@@ -350,7 +352,7 @@ int rtc_launch(iftrcuRenderer* r, const DrawParams& p, cudaStream_t s) {
     if (!sh.kern[mi]) { int rc = rtc_compile(r, sh, mi); if (rc) return rc; }   // first draw with this sample count
     void* args[] = {(void*)&p};
     CUDA_TRY(cudaLaunchKernel((const void*)sh.kern[mi], dim3(p.gridHint ? p.gridHint : (uint32_t)(p.tilesX * p.tilesY)), dim3(256), args,
-                              (size_t)p.msaa * IFR_TILE_PIX * sizeof(unsigned long long), s));
+                              (size_t)p.msaa * IFR_TILE_PIX * sizeof(unsigned long long) + 2 * (size_t)p.bigChunk * sizeof(TriS), s));
     return IFRIT_OK;
 }
 }   // namespace
@@ -378,6 +380,7 @@ static void build_params(iftrcuRenderer* r, DrawParams& p) {
     memcpy(p.scissor, r->scissor, sizeof p.scissor);
     p.rank = r->rank; p.world = r->world;
     p.hwFilter = r->hwFilter ? 1 : 0;
+    p.bigChunk = 64;
     tma_maps(r, p);
     p.blendEnable = r->blendEnable; memcpy(p.blendCoef, r->blendCoef, sizeof p.blendCoef);
     if (!r->blendEnable) {      // blending off: src x 1 + dst x 0 (updateBlendStateKernel CU:3438-3443) — used by the ordered path of depth-writing shaders
@@ -525,7 +528,11 @@ static int issue_draw(iftrcuRenderer* r, bool forceCheck, bool sameSet = false) 
         // c[2] = tiles with work, c[7] = empty tiles: the tile kernel needs exactly this many CTAs for these inputs
         sc.gridHint = (uint32_t)std::min<unsigned long long>(c[2] + (c[7] + IFR_EMPTY_PER_CTA - 1) / IFR_EMPTY_PER_CTA, ntiles);
         if (sc.gridHint == 0) sc.gridHint = 1;
+        sc.avgBig = (uint32_t)(c[5] / std::max<unsigned long long>(c[2], 1));
     }
+    // staged chunk of the tile kernel (tile_kernel.cuh: DrawParams::bigChunk): multisampled draws of shallow queues take the small one
+    p.bigChunk = (sc.queueChecked && p.msaa > 1 && sc.avgBig <= 40 && !r->forceBigChunk) ? 32 : 64;
+    if (r->forceBigChunk == 32) p.bigChunk = 32;
     p.gridHint = (sc.queueChecked && r->useGridHint) ? sc.gridHint : 0;
     CUDA_TRY(ifr_launch_fill(p, g));
     if (ev) CUDA_TRY(cudaEventRecord(ev[4], g));
@@ -1207,6 +1214,12 @@ int iftrcuSetFramePipelining(iftrcuRenderer* h, int enable) {
 }
 int iftrcuSetVertexStageFused(iftrcuRenderer* h, int enable) { R_CHECK(h); r->fusedVS = enable != 0; return IFRIT_OK; }
 int iftrcuSetTmaFramebuffer(iftrcuRenderer* h, int enable) { R_CHECK(h); r->useTma = enable != 0; return IFRIT_OK; }
+int iftrcuSetTileChunk(iftrcuRenderer* h, int entries) {
+    R_CHECK(h);
+    if (entries != 0 && entries != 32 && entries != 64) return r->fail(IFRIT_ERR_INVALID, "SetTileChunk", "0 (automatic), 32 or 64");
+    r->forceBigChunk = entries;
+    return IFRIT_OK;
+}
 int iftrcuSetTileGridHint(iftrcuRenderer* h, int enable) { R_CHECK(h); r->useGridHint = enable != 0; return IFRIT_OK; }
 int iftrcuSetSamplerHardwareFilter(iftrcuRenderer* h, int enable) { R_CHECK(h); r->hwFilter = enable != 0; return IFRIT_OK; }
 

@@ -114,6 +114,7 @@ struct DrawParams {
     // this geometry / state, 0 = not known (one CTA per tile, the surplus exits).  A grid that turns out too small (inputs changed
     // behind the library's back) raises counters[9]; the host then re-issues the draw like a queue overflow.
     uint32_t gridHint;
+    int bigChunk;                    // big-queue entries per staged chunk of the tile kernel: 32 or 64 (tile_kernel.cuh)
     uint32_t epoch; unsigned long long* scanPartial;   // chained scan: (epoch << 32 | block total) per scan CTA
     unsigned long long* counters;    // [0] assembled (host sum), [1] small pairs, [2] nWork (device) / frags (host sum), [3] overflow flag,
                                      // [4] fan1 count, [5] big pairs, [6] blending: a tile held more than IFR_BLEND_CAP triangles,

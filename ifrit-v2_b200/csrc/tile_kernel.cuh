@@ -305,7 +305,11 @@ __device__ __forceinline__ void interp(const DrawParams& p, uint32_t slot, int p
 
 // ------------------------------------------------------------------------------------------------
 #define IFR_CHUNK 256
-#define IFR_BIG_CHUNK 64     // big-queue entries staged per bulk copy (6 KB), double buffered
+// Big-queue entries staged per bulk copy, double buffered: DrawParams::bigChunk = 32 or 64, chosen per draw by the host (capi.cu:
+// issue_draw).  The staging lives in dynamic shared memory behind the keys, so that a draw of shallow queues allocates 6 KB instead
+// of 12: at 8x MSAA (16 KB of keys) that takes four resident CTAs from 117 to 93 KB and moves the L1 / shared split one step
+// towards L1 — c3 tile 0.331 -> 0.319 ms; deep queues (c5) and the 1x kernels keep 64 (fewer chunk turns; profiles/r02_ab.txt).
+#define IFR_BIG_CHUNK_MAX 64
 
 // ---- TMA bulk copy (global -> shared) completing on an mbarrier -----------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -432,7 +436,7 @@ __device__ __forceinline__ bool big_test(const DrawParams& p, const KeyMode& km,
 }
 
 template <int S, bool HIZ>
-__device__ __forceinline__ void big_loop(const DrawParams& p, const KeyMode& km, unsigned long long* keys, int* covScratch, TriS (*bigBuf)[IFR_BIG_CHUNK],
+__device__ __forceinline__ void big_loop(const DrawParams& p, const KeyMode& km, unsigned long long* keys, int* covScratch, TriS* bigBuf,
                                          uint64_t* mbar, HizShared& hz, const TriS* bigSrc, uint32_t nBig, int tid, int wrp, int lx,
                                          int ly, bool scis, float d0, unsigned long long& best, bool& uni) {
     const int lane = tid & 31;
@@ -444,16 +448,17 @@ __device__ __forceinline__ void big_loop(const DrawParams& p, const KeyMode& km,
         // (compute-sanitizer racecheck: no hazards)
         if (lane == 0) atomicMin(&hz.warpFar[wrp], wfar);
     }
-    const uint32_t nchunks = (nBig + IFR_BIG_CHUNK - 1) / IFR_BIG_CHUNK;
+    const uint32_t CH = (uint32_t)p.bigChunk;
+    const uint32_t nchunks = (nBig + CH - 1) / CH;
     for (uint32_t c = 0; c < nchunks; c++) {
         if (tid == 0 && c + 1 < nchunks) {
-            const uint32_t cnt1 = min(nBig - (c + 1) * IFR_BIG_CHUNK, (uint32_t)IFR_BIG_CHUNK);
+            const uint32_t cnt1 = min(nBig - (c + 1) * CH, CH);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            bulk_load(bigBuf[(c + 1) & 1], bigSrc + (size_t)(c + 1) * IFR_BIG_CHUNK, cnt1 * (uint32_t)sizeof(TriS), &mbar[(c + 1) & 1]);
+            bulk_load(bigBuf + ((c + 1) & 1) * CH, bigSrc + (size_t)(c + 1) * CH, cnt1 * (uint32_t)sizeof(TriS), &mbar[(c + 1) & 1]);
         }
         mbar_wait(&mbar[c & 1], (c >> 1) & 1);
-        const uint32_t cnt = min(nBig - c * IFR_BIG_CHUNK, (uint32_t)IFR_BIG_CHUNK);
-        const int4* chunk = reinterpret_cast<const int4*>(bigBuf[c & 1]);
+        const uint32_t cnt = min(nBig - c * CH, CH);
+        const int4* chunk = reinterpret_cast<const int4*>(bigBuf + (c & 1) * CH);
         if (!HIZ) {
             const int4* t4 = chunk;
             for (uint32_t b = 0; b < cnt; b++, t4 += 6) {
@@ -465,13 +470,13 @@ __device__ __forceinline__ void big_loop(const DrawParams& p, const KeyMode& km,
         } else {
             // chunk preparation, warps 0 and 1, one thread per staged entry: trivial-accept blocks + key bound written
             // back into the staged copy, entries that can still win somewhere in the tile compacted per warp
-            if (tid < IFR_BIG_CHUNK) {
+            if ((uint32_t)tid < CH) {
                 bool alive = false;
                 if ((uint32_t)tid < cnt) {
                     uint32_t tileFar = 0;
 #pragma unroll
                     for (int w = 0; w < 8; w++) tileFar = max(tileFar, atomicOr(&hz.warpFar[w], 0u));
-                    TriS* e = &bigBuf[c & 1][tid];
+                    TriS* e = bigBuf + (c & 1) * CH + tid;
                     const uint32_t tb = setup_hiz(e, p.sampMinX, p.sampMaxX, p.sampMinY, p.sampMaxY, km.xhi);
                     alive = ((uint32_t)e->pad[0] & 0xffu) != 0 && tb <= tileFar;
                 }
@@ -480,7 +485,7 @@ __device__ __forceinline__ void big_loop(const DrawParams& p, const KeyMode& km,
                 if (lane == 0) hz.nSurv[wrp] = __popc(bal);
             }
             __syncthreads();
-            for (int half = 0; half < 2; half++) {
+            for (uint32_t half = 0; half < CH / 32; half++) {
                 const uint32_t ns = hz.nSurv[half];
                 for (uint32_t i = 0; i < ns; i++) {
                     const int4* t4 = chunk + 6 * (int)hz.surv[half][i];
@@ -565,8 +570,8 @@ __device__ __forceinline__ void clear_tiles_tma(const DrawParams& p, float* stag
 #endif
 template <int FS, int S>
 __global__ void __launch_bounds__(256, FsTraits<FS>::needsDerivs ? (S == 1 ? IFR_MINB1 : IFR_MINB8) : 4) tile_kernel(const __grid_constant__ DrawParams p) {
-    extern __shared__ unsigned long long keys[];        // [S][256], index = owning thread
-    __shared__ __align__(128) TriS bigBuf[2][IFR_BIG_CHUNK];
+    extern __shared__ __align__(128) unsigned long long keys[];        // [S][256], index = owning thread; then the big-queue staging
+    TriS* const bigBuf = reinterpret_cast<TriS*>(keys + S * IFR_TILE_PIX);   // [2][p.bigChunk]
     __shared__ __align__(8) uint64_t mbar[2];
     __shared__ HizShared hz;
     __shared__ __align__(16) int covOff[8][3 * (S > 1 ? S : 1)];   // coverage_coop: one row per warp
@@ -592,7 +597,7 @@ __global__ void __launch_bounds__(256, FsTraits<FS>::needsDerivs ? (S == 1 ? IFR
 
         if (p.useTma && p.doClear && !p.scissorEnable) {
             // staged in the big-queue buffer, which a CTA without a tile never fills (6 KB of its 12)
-            if (e0 < nEmpty) clear_tiles_tma<S>(p, reinterpret_cast<float*>(&bigBuf[0][0]), e0, min(e0 + IFR_EMPTY_PER_CTA, nEmpty), ntiles, tid);
+            if (e0 < nEmpty) clear_tiles_tma<S>(p, reinterpret_cast<float*>(bigBuf), e0, min(e0 + IFR_EMPTY_PER_CTA, nEmpty), ntiles, tid);
             return;
         }
         for (uint32_t e = e0; e < min(e0 + IFR_EMPTY_PER_CTA, nEmpty); e++) {
@@ -674,7 +679,7 @@ __global__ void __launch_bounds__(256, FsTraits<FS>::needsDerivs ? (S == 1 ? IFR
         __syncthreads();      // mbarriers initialised
         const TriS* bigSrc = p.bigQueue + bStart;
         int* covScratch = covOff[wrp];
-        if (tid == 0) bulk_load(bigBuf[0], bigSrc, min(nBig, (uint32_t)IFR_BIG_CHUNK) * (uint32_t)sizeof(TriS), &mbar[0]);
+        if (tid == 0) bulk_load(bigBuf, bigSrc, min(nBig, (uint32_t)p.bigChunk) * (uint32_t)sizeof(TriS), &mbar[0]);
 #ifndef IFR_NO_HIZ
         if (deep) big_loop<S, true>(p, km, keys, covScratch, bigBuf, mbar, hz, bigSrc, nBig, tid, wrp, lx, ly, scis, d0, best, uni);
         else
@@ -875,11 +880,15 @@ __global__ void __launch_bounds__(256, FsTraits<FS>::needsDerivs ? (S == 1 ? IFR
 
 
 #ifndef __CUDACC_RTC__
+// dynamic shared memory of the tile kernel: keys [msaa][256] + staging [2][bigChunk]
+static inline size_t ifr_tile_smem_bytes(const DrawParams& p) {
+    return (size_t)p.msaa * IFR_TILE_PIX * sizeof(unsigned long long) + 2 * (size_t)p.bigChunk * sizeof(TriS);
+}
 template <int FS>
 static inline cudaError_t launch_fs(const DrawParams& p, cudaStream_t s) {
     // one CTA per tile is the upper bound of the work list (surplus CTAs exit at once); the exact count when the host knows it
     const dim3 grid(p.gridHint ? p.gridHint : (uint32_t)(p.tilesX * p.tilesY));
-    const size_t smem = (size_t)p.msaa * IFR_TILE_PIX * sizeof(unsigned long long);
+    const size_t smem = ifr_tile_smem_bytes(p);
 #define IFR_LAUNCH(SS)                                                                                   \
     case SS: {                                                                                           \
         static bool attrSet = false;                                                                     \

@@ -374,6 +374,9 @@ class TileRasterRendererCuda:
     def setTmaFramebuffer(self, enable=True):
         self._ck(self._lib.iftrcuSetTmaFramebuffer(self._h, int(enable)))
 
+    def setTileChunk(self, entries=0):
+        self._ck(self._lib.iftrcuSetTileChunk(self._h, int(entries)))
+
     def setTileGridHint(self, enable=True):
         self._ck(self._lib.iftrcuSetTileGridHint(self._h, int(enable)))
 

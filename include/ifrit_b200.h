@@ -251,6 +251,9 @@ IFRIT_B200_API int iftrcuSetTmaFramebuffer(iftrcuRenderer* h, int enable);
  * CTA per tile with the surplus exiting.  DEFAULT off: measured no gain (c3 tile 0.3323 vs 0.3327 ms, profiles/r02_ab.txt).  Inputs changed behind the library's back are caught
  * like a queue overflow: the draw is re-issued at the next synchronisation. */
 IFRIT_B200_API int iftrcuSetTileGridHint(iftrcuRenderer* h, int enable);
+/* Big-queue entries the tile kernel stages per bulk copy: 0 = automatic (32 for multisampled draws whose tiles hold few large
+ * triangles — less shared memory, more L1 — else 64), or pinned to 32 / 64 (A/B switch). */
+IFRIT_B200_API int iftrcuSetTileChunk(iftrcuRenderer* h, int entries);
 
 /* ---- draw ----------------------------------------------------------------------------- */
 IFRIT_B200_API int iftrcuClear(iftrcuRenderer* h);        /* RC::clear — fused into the next draw */
