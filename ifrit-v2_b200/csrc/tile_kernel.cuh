@@ -310,6 +310,11 @@ __device__ __forceinline__ void interp(const DrawParams& p, uint32_t slot, int p
 // of 12: at 8x MSAA (16 KB of keys) that takes four resident CTAs from 117 to 93 KB and moves the L1 / shared split one step
 // towards L1 — c3 tile 0.331 -> 0.319 ms; deep queues (c5) and the 1x kernels keep 64 (fewer chunk turns; profiles/r02_ab.txt).
 #define IFR_BIG_CHUNK_MAX 64
+#ifdef IFR_NO_STCS
+#define IFR_FB_STORE(ptr, v) (*(ptr) = (v))
+#else
+#define IFR_FB_STORE(ptr, v) __stcs(ptr, v)
+#endif
 
 // ---- TMA bulk copy (global -> shared) completing on an mbarrier -----------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -866,9 +871,11 @@ __global__ void __launch_bounds__(256, FsTraits<FS>::needsDerivs ? (S == 1 ? IFR
         } else
 #endif
         if (written) {
-            p.color[pidx] = out;
-            p.depth[pidx] = dout;
-            if (p.present) p.present[pidx] = ifr_pack_rgba8(out);
+            // write-once data: streaming (evict-first) stores keep the framebuffer from pushing the texture mip chain and the
+            // triangle records out of L2 (c3: 166 MB of framebuffer per frame against a 126 MB L2)
+            IFR_FB_STORE(&p.color[pidx], out);
+            IFR_FB_STORE(&p.depth[pidx], dout);
+            if (p.present) IFR_FB_STORE(&p.present[pidx], ifr_pack_rgba8(out));
         } else if (inFrame && p.present) {
             p.present[pidx] = ifr_pack_rgba8(p.color[pidx]);   // untouched pixel (no clear, nothing drawn): present what is there
         }
