@@ -83,6 +83,11 @@ struct iftrcuRenderer {
     // fragment shaders compiled at run time (iftrcuCreateFragmentShaderFromSource): id = IFRIT_FS_USER + index
     struct RtcShader { std::string name, source; int nvary = 0, derivs = 0; cudaLibrary_t lib[5] = {}; cudaKernel_t kern[5] = {}; };
     std::vector<RtcShader> rtc;
+    // mesh / task front end (iftrcuCreateMeshShaderFromSource / iftrcuCreateTaskShaderFromSource, iftrcuDrawMeshTasks)
+    struct RtcStage { std::string name, source; int nvary = 0; cudaLibrary_t lib = nullptr; cudaKernel_t kern = nullptr; };
+    std::vector<RtcStage> meshShaders, taskShaders;
+    int meshId = -1, taskId = -1, meshNvary = 0, meshLocal[3] = {1, 1, 1};
+    DevBuf msPos, msVary, msIdx, msCounts, msStarts, msVB, msIB, tsPayload, tsSub, tsNum, tsParent, tsList;
     int polygonMode = IF_POLYGON_MODE_FILL;     // iftrcuSetRasterizerPolygonMode
     DevBuf primKeys, primSeg;                   // point / line modes: per-pixel winner keys, mapped segment ends (kernels_prim.cu)
     // TMA descriptors of the bound framebuffer (tma_maps), rebuilt when an image pointer or the size changes
@@ -345,6 +350,102 @@ int rtc_compile(iftrcuRenderer* r, iftrcuRenderer::RtcShader& sh, int mi) {
     CUDA_TRY(cudaFuncSetAttribute((const void*)sh.kern[mi], cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     return IFRIT_OK;
 }
+
+// ---- mesh / task front end ---------------------------------------------------------------------------------------------------
+// meshShadingEntryPoint / meshShadingWithTaskShaderEntryPoint CU:375-500: user device code emits up to 768 vertices and 768 indices per
+// work group into the same triangle pipeline.  Here the user hands in CUDA source of
+//     __device__ void ms_main(const IfritMeshInput& in, float4* outPos, float4* outVaryings, int* outIndices, int& outNumVertices, int& outNumIndices);
+//     __device__ void ts_main(int workGroupId, void* outPayload, int3* outMeshWorkGroups, int& outNumMeshWorkGroups);
+// (the argument lists of MeshShader::execute / TaskShader::execute, Shaders.h:84-116), NVRTC compiles one kernel around each, and the
+// outputs are compacted IN WORK-GROUP ORDER (the reference allocates with atomics: "TODO: Ordering", CU:385) into an interleaved vertex
+// buffer + index buffer that the ordinary draw consumes with the passthrough vertex stage.
+#define IFR_MS_MAX_VERTS 768     // CU_MESHSHADER_MAX_VERTICES
+#define IFR_MS_MAX_IDX 768       // CU_MESHSHADER_MAX_INDICES
+#define IFR_TS_MAX_OUT 32        // CU_MESHSHADER_MAX_TASK_OUTPUT
+#define IFR_TS_PAYLOAD 128       // CU_MESHSHADER_MAX_TASK_PAYLOAD_SIZE
+struct MeshArgs {
+    float4* pos; float4* vary; int* idx; int* counts;      // per work group: [768], [768 * nvary], [768], {nverts, nidx}
+    int nvary, firstWorkGroup;
+    const int4* subGroups;      // task path: {x, y, z, parent} per mesh work group, else null
+    const int* parentStart;     // task path: first mesh work group of every task work group
+    const char* payload;        // task path: 128 bytes per task work group
+};
+struct TaskArgs { char* payload; int3* sub; int* num; int total, first; };
+const char* kMeshPrologue = R"IFRSRC(#include "common.cuh"
+#include "tri_setup.cuh"
+struct MeshArgs { float4* pos; float4* vary; int* idx; int* counts; int nvary, firstWorkGroup; const int4* subGroups; const int* parentStart; const char* payload; };
+struct TaskArgs { char* payload; int3* sub; int* num; int total, first; };
+struct IfritMeshInput {
+    int3 localInvocation;      // thread index inside the work group
+    int workGroupId;           // DrawMeshTasks index, or the index among the mesh work groups its task work group emitted
+    const void* payload;       // 128 bytes written by the task shader (null without one)
+    const float* uniform;      // the 32 floats of buffer slot 0
+    const DrawParams* draw;
+};
+__device__ __forceinline__ const float* ifritBuffer(const IfritMeshInput& in, int slot) { return in.draw->buf[slot]; }
+// the registry's `mvp` vertex shader, op for op: MVP (uniform[0..15], row-major) * position
+__device__ __forceinline__ float4 ifritMvp(const IfritMeshInput& in, float4 pos) { return run_vs<IFRIT_VS_MVP>(*in.draw, pos); }
+)IFRSRC";
+const char* kMeshTail = R"IFRSRC(
+extern "C" __global__ void ifrit_mesh_kernel(const __grid_constant__ DrawParams p, const MeshArgs a) {
+    const int wg = blockIdx.x;
+    IfritMeshInput in;
+    in.localInvocation = make_int3(threadIdx.x, threadIdx.y, threadIdx.z);
+    in.workGroupId = wg + a.firstWorkGroup; in.payload = nullptr; in.uniform = p.u0; in.draw = &p;
+    if (a.subGroups) {      // taskShadingLaunchSubGroupsKernel CU:446-460
+        const int4 sg = a.subGroups[wg];
+        if ((int)threadIdx.x >= sg.x || (int)threadIdx.y >= sg.y || (int)threadIdx.z >= sg.z) return;
+        in.workGroupId = wg - a.parentStart[sg.w];
+        in.payload = a.payload + 128 * (size_t)sg.w;
+    }
+    ms_main(in, a.pos + (size_t)wg * 768, a.vary + (size_t)wg * 768 * a.nvary, a.idx + (size_t)wg * 768, a.counts[2 * wg], a.counts[2 * wg + 1]);
+}
+)IFRSRC";
+const char* kTaskPrologue = R"IFRSRC(#include "common.cuh"
+struct TaskArgs { char* payload; int3* sub; int* num; int total, first; };
+)IFRSRC";
+const char* kTaskTail = R"IFRSRC(
+extern "C" __global__ void ifrit_task_kernel(const TaskArgs a) {      // taskShadingKernel CU:409-416: one thread per work group
+    const int wg = threadIdx.x + blockDim.x * blockIdx.x;
+    if (wg >= a.total) return;
+    ts_main(wg + a.first, a.payload + 128 * (size_t)wg, a.sub + 32 * (size_t)wg, a.num[wg]);
+}
+)IFRSRC";
+
+int rtc_build_stage(const std::string& name, const std::string& body, const char* prologue, const char* tail, const char* kernelName,
+                    std::vector<char>& cubin, std::string& log) {
+    Nvrtc& n = nvrtc();
+    if (!n.ok) { log = "libnvrtc.so.12 could not be loaded"; return 1; }
+    std::string nm = name;
+    for (char& c : nm) if (c == '"' || c == '\\' || c == '\n') c = '_';
+    const std::string src = std::string(prologue) + "#line 1 \"" + nm + "\"\n" + body + tail;
+    void* prog = nullptr;
+    if (n.CreateProgram(&prog, src.c_str(), "ifrit_user_stage.cu", kEmbedCount, kEmbedSrcs, kEmbedNames) != 0) { log = "nvrtcCreateProgram failed"; return 2; }
+    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=false", "-default-device", "-lineinfo"};
+    const int rc = n.CompileProgram(prog, 5, opts);
+    size_t ls = 0;
+    n.GetProgramLogSize(prog, &ls);
+    log.assign(ls + 1, '\0');
+    if (ls) n.GetProgramLog(prog, &log[0]);
+    log.resize(strlen(log.c_str()));
+    size_t cs = 0;
+    if (rc != 0 || n.GetCUBINSize(prog, &cs) != 0 || !cs) { n.DestroyProgram(&prog); if (log.empty()) log = "no cubin"; return 2; }
+    cubin.resize(cs);
+    n.GetCUBIN(prog, cubin.data());
+    n.DestroyProgram(&prog);
+    (void)kernelName;
+    return 0;
+}
+int rtc_load_stage(iftrcuRenderer* r, iftrcuRenderer::RtcStage& st, const char* prologue, const char* tail, const char* kernelName) {
+    std::vector<char> cubin;
+    std::string log;
+    const int rc = rtc_build_stage(st.name, st.source, prologue, tail, kernelName, cubin, log);
+    if (rc == 1) return r->fail(IFRIT_ERR_UNSUPPORTED, "shader from source", log.c_str());
+    if (rc) return r->fail(IFRIT_ERR_INVALID, "shader compilation failed", log.c_str());
+    CUDA_TRY(cudaLibraryLoadData(&st.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+    CUDA_TRY(cudaLibraryGetKernel(&st.kern, st.lib, kernelName));
+    return IFRIT_OK;
+}
 int rtc_launch(iftrcuRenderer* r, const DrawParams& p, cudaStream_t s) {
     const int idx = r->fsId - IFRIT_FS_USER, mi = msaa_index(p.msaa);
     if (idx < 0 || idx >= (int)r->rtc.size() || mi < 0) return r->fail(IFRIT_ERR_STATE, "drawElements", "unknown run-time shader");
@@ -589,7 +690,6 @@ static int issue_draw(iftrcuRenderer* r, bool forceCheck, bool sameSet = false) 
 }
 
 static int flush_clear(iftrcuRenderer* r);
-cudaError_t ifr_launch_prims(const DrawParams& p, int mode, int vsId, int fsId, unsigned long long* keys, float4* seg, cudaStream_t s);
 // Point / line polygon modes (unifiedPointRasterEngineKernel CU:2932, unifiedLineRasterEngineKernel CU:3295): no binning, no
 // tiles — insertion by per-pixel 64-bit atomicMin, then one shading pass over the frame (kernels_prim.cu).
 static int issue_draw_prims(iftrcuRenderer* r) {
@@ -700,10 +800,13 @@ int iftrcuDestroyInstance(iftrcuRenderer* h) {
     if (r->registeredHost) cudaHostUnregister(r->registeredHost);
     if (r->registeredPresent) cudaHostUnregister(r->registeredPresent);
     for (auto& sh : r->rtc) for (int i = 0; i < 5; i++) if (sh.lib[i]) cudaLibraryUnload(sh.lib[i]);
+    for (auto& st : r->meshShaders) if (st.lib) cudaLibraryUnload(st.lib);
+    for (auto& st : r->taskShaders) if (st.lib) cudaLibraryUnload(st.lib);
     close_peer(r);
     if (r->copyStream) { cudaStreamSynchronize(r->copyStream); cudaStreamDestroy(r->copyStream); }
     for (int i = 0; i < 2; i++) { if (r->evFrame[i]) cudaEventDestroy(r->evFrame[i]); if (r->evCopy[i]) cudaEventDestroy(r->evCopy[i]); }
-    DevBuf* bufs[] = {&r->ownColor, &r->ownColor2, &r->ownDepth, &r->primIds, &r->ownVB, &r->ownIB, &r->presentBuf[0], &r->presentBuf[1], &r->primKeys, &r->primSeg};
+    DevBuf* bufs[] = {&r->ownColor, &r->ownColor2, &r->ownDepth, &r->primIds, &r->ownVB, &r->ownIB, &r->presentBuf[0], &r->presentBuf[1], &r->primKeys, &r->primSeg, &r->msPos, &r->msVary, &r->msIdx,
+                      &r->msCounts, &r->msStarts, &r->msVB, &r->msIB, &r->tsPayload, &r->tsSub, &r->tsNum, &r->tsParent, &r->tsList};
     for (int k = 0; k < 2; k++) {
         iftrcuRenderer::Scratch& c = r->scr[k];
         DevBuf* sb[] = {&c.scanPartial, &c.pos, &c.vary, &c.rec, &c.clipBary, &c.tileBox, &c.fan1List, &c.heavyBits, &c.tileCount, &c.tileStart,
@@ -989,8 +1092,52 @@ int iftrcuLookupFragmentShader(const char* name) {
     return -1;
 }
 int iftrcuBindGeometryShader(iftrcuRenderer* h, int) { R_CHECK(h); return r->fail(IFRIT_ERR_UNSUPPORTED, "bindGeometryShader", "out of scope"); }
-int iftrcuBindMeshShader(iftrcuRenderer* h, int, const int*, int, int, int, int) { R_CHECK(h); return r->fail(IFRIT_ERR_UNSUPPORTED, "bindMeshShader", "out of scope"); }
-int iftrcuBindTaskShader(iftrcuRenderer* h, int, const int*, int) { R_CHECK(h); return r->fail(IFRIT_ERR_UNSUPPORTED, "bindTaskShader", "out of scope"); }
+int iftrcuCheckMeshShaderSource(const char* cudaSource, int isTaskShader, char* logOut, size_t logCap) {
+    if (!cudaSource) return IFRIT_ERR_INVALID;
+    std::vector<char> cubin;
+    std::string log;
+    const int rc = isTaskShader ? rtc_build_stage("user_ts", cudaSource, kTaskPrologue, kTaskTail, "ifrit_task_kernel", cubin, log)
+                                : rtc_build_stage("user_ms", cudaSource, kMeshPrologue, kMeshTail, "ifrit_mesh_kernel", cubin, log);
+    if (logOut && logCap) { strncpy(logOut, log.c_str(), logCap - 1); logOut[logCap - 1] = 0; }
+    return rc == 0 ? IFRIT_OK : rc == 1 ? IFRIT_ERR_UNSUPPORTED : IFRIT_ERR_INVALID;
+}
+int iftrcuCreateMeshShaderFromSource(iftrcuRenderer* h, const char* name, const char* cudaSource, int* shaderIdOut) {
+    R_CHECK(h);
+    if (!cudaSource || !shaderIdOut) return r->fail(IFRIT_ERR_INVALID, "CreateMeshShaderFromSource", "bad argument");
+    iftrcuRenderer::RtcStage st;
+    st.name = (name && *name) ? name : "user_ms"; st.source = cudaSource;
+    int rc = rtc_load_stage(r, st, kMeshPrologue, kMeshTail, "ifrit_mesh_kernel");
+    if (rc) return rc;
+    r->meshShaders.push_back(st);
+    *shaderIdOut = (int)r->meshShaders.size() - 1;
+    return IFRIT_OK;
+}
+int iftrcuCreateTaskShaderFromSource(iftrcuRenderer* h, const char* name, const char* cudaSource, int* shaderIdOut) {
+    R_CHECK(h);
+    if (!cudaSource || !shaderIdOut) return r->fail(IFRIT_ERR_INVALID, "CreateTaskShaderFromSource", "bad argument");
+    iftrcuRenderer::RtcStage st;
+    st.name = (name && *name) ? name : "user_ts"; st.source = cudaSource;
+    int rc = rtc_load_stage(r, st, kTaskPrologue, kTaskTail, "ifrit_task_kernel");
+    if (rc) return rc;
+    r->taskShaders.push_back(st);
+    *shaderIdOut = (int)r->taskShaders.size() - 1;
+    return IFRIT_OK;
+}
+int iftrcuBindMeshShader(iftrcuRenderer* h, int shaderId, const int* varyingDescs, int n, int lx, int ly, int lz) {
+    R_CHECK(h);
+    if (shaderId < 0 || shaderId >= (int)r->meshShaders.size()) return r->fail(IFRIT_ERR_INVALID, "bindMeshShader", "unknown shader id (iftrcuCreateMeshShaderFromSource)");
+    int rc = check_types(r, varyingDescs, n, IFR_MAX_VARY);
+    if (rc) return rc;
+    if (lx < 1 || ly < 1 || lz < 1 || (long long)lx * ly * lz > 1024) return r->fail(IFRIT_ERR_INVALID, "bindMeshShader", "local size must be 1..1024 threads");
+    r->meshId = shaderId; r->meshNvary = n; r->meshLocal[0] = lx; r->meshLocal[1] = ly; r->meshLocal[2] = lz;
+    return IFRIT_OK;
+}
+int iftrcuBindTaskShader(iftrcuRenderer* h, int shaderId, const int*, int) {
+    R_CHECK(h);
+    if (shaderId < -1 || shaderId >= (int)r->taskShaders.size()) return r->fail(IFRIT_ERR_INVALID, "bindTaskShader", "unknown shader id (iftrcuCreateTaskShaderFromSource); -1 unbinds");
+    r->taskId = shaderId;
+    return IFRIT_OK;
+}
 
 static size_t chain_texels(int w, int h, int mips, int layers) {
     size_t n = 0;
@@ -1264,7 +1411,85 @@ int iftrcuDrawElements(iftrcuRenderer* h) {
     return issue_draw(r, false);
 }
 
-int iftrcuDrawMeshTasks(iftrcuRenderer* h, int, int) { R_CHECK(h); return r->fail(IFRIT_ERR_UNSUPPORTED, "DrawMeshTasks", "out of scope"); }
+int iftrcuDrawMeshTasks(iftrcuRenderer* h, int numWorkGroups, int firstWorkGroup) {
+    R_CHECK(h);
+    if (r->meshId < 0) return r->fail(IFRIT_ERR_STATE, "DrawMeshTasks", "no mesh shader bound");
+    if (numWorkGroups <= 0 || firstWorkGroup < 0) return r->fail(IFRIT_ERR_INVALID, "DrawMeshTasks", "bad work group range");
+    if (!r->dColor || r->fsId < 0) return r->fail(IFRIT_ERR_STATE, "DrawMeshTasks", "framebuffer and fragment shader must be bound");
+    cudaStream_t s = r->stream;
+    if (r->geomStream) CUDA_TRY(cudaStreamSynchronize(r->geomStream));
+    DrawParams p;
+    build_params(r, p);
+    int nwg = numWorkGroups;
+    MeshArgs a;
+    memset(&a, 0, sizeof a);
+    dim3 block(r->meshLocal[0], r->meshLocal[1], r->meshLocal[2]);
+    if (r->taskId >= 0) {
+        // task stage: one thread per task work group -> up to 32 mesh work groups each, compacted in order
+        CUDA_TRY(r->tsPayload.ensure((size_t)numWorkGroups * IFR_TS_PAYLOAD));
+        CUDA_TRY(r->tsSub.ensure((size_t)numWorkGroups * IFR_TS_MAX_OUT * sizeof(int3)));
+        CUDA_TRY(r->tsNum.ensure((size_t)numWorkGroups * 4));
+        CUDA_TRY(r->tsParent.ensure((size_t)numWorkGroups * 4 + 16));     // first mesh work group per task work group, then {total, max x, y, z}
+        CUDA_TRY(r->tsList.ensure((size_t)numWorkGroups * IFR_TS_MAX_OUT * sizeof(int4)));
+        CUDA_TRY(cudaMemsetAsync(r->tsNum.p, 0, (size_t)numWorkGroups * 4, s));
+        TaskArgs ta = {(char*)r->tsPayload.p, (int3*)r->tsSub.p, (int*)r->tsNum.p, numWorkGroups, firstWorkGroup};
+        void* targs[] = {(void*)&ta};
+        CUDA_TRY(cudaLaunchKernel((const void*)r->taskShaders[r->taskId].kern, dim3((numWorkGroups + 31) / 32), dim3(32), targs, 0, s));
+        int* totals = (int*)r->tsParent.p + numWorkGroups;
+        CUDA_TRY(ifr_launch_task_compact((const int3*)r->tsSub.p, (const int*)r->tsNum.p, numWorkGroups, (int*)r->tsParent.p, (int4*)r->tsList.p, totals, 0, s));
+        int ht[4];
+        CUDA_TRY(cudaMemcpyAsync(ht, totals, 16, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        r->stats.kernel_launches += 2;
+        if (ht[0] <= 0) return flush_clear(r);
+        if ((long long)std::max(ht[1], 1) * std::max(ht[2], 1) * std::max(ht[3], 1) > 1024) return r->fail(IFRIT_ERR_INVALID, "DrawMeshTasks", "a task shader asked for a mesh work group of more than 1024 threads");
+        nwg = ht[0];
+        block = dim3(std::max(ht[1], 1), std::max(ht[2], 1), std::max(ht[3], 1));
+        a.subGroups = (const int4*)r->tsList.p;
+        a.parentStart = (const int*)r->tsParent.p;
+        a.payload = (const char*)r->tsPayload.p;
+    }
+    const int nv = r->meshNvary;
+    CUDA_TRY(r->msPos.ensure((size_t)nwg * IFR_MS_MAX_VERTS * sizeof(float4)));
+    CUDA_TRY(r->msVary.ensure(std::max<size_t>(16, (size_t)nwg * IFR_MS_MAX_VERTS * nv * sizeof(float4))));
+    CUDA_TRY(r->msIdx.ensure((size_t)nwg * IFR_MS_MAX_IDX * 4));
+    CUDA_TRY(r->msCounts.ensure((size_t)nwg * 8 + 64));
+    DevBuf& starts = r->msStarts;     // {first vertex, first index} per work group, then the two totals
+    CUDA_TRY(starts.ensure((size_t)nwg * 8 + 16));
+    CUDA_TRY(cudaMemsetAsync(r->msCounts.p, 0, (size_t)nwg * 8, s));
+    a.pos = (float4*)r->msPos.p; a.vary = (float4*)r->msVary.p; a.idx = (int*)r->msIdx.p; a.counts = (int*)r->msCounts.p;
+    a.nvary = nv; a.firstWorkGroup = firstWorkGroup;
+    void* margs[] = {(void*)&p, (void*)&a};
+    CUDA_TRY(cudaLaunchKernel((const void*)r->meshShaders[r->meshId].kern, dim3(nwg), block, margs, 0, s));
+    // ordered compaction: scan of the per-work-group counts, totals to the host, then the interleaved copy
+    int* dstarts = (int*)starts.p;
+    CUDA_TRY(ifr_launch_mesh_compact((const int*)r->msCounts.p, dstarts, nwg, nullptr, nullptr, nullptr, nv, nullptr, nullptr, 0, s));
+    int tot[2];
+    CUDA_TRY(cudaMemcpyAsync(tot, dstarts + 2 * (size_t)nwg, 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    r->stats.kernel_launches += 2;
+    const int nverts = tot[0], nidx = tot[1] - tot[1] % 3;
+    if (nverts <= 0 || nidx <= 0) { int rc0 = flush_clear(r); return rc0; }
+    CUDA_TRY(r->msVB.ensure((size_t)nverts * (1 + nv) * sizeof(float4)));
+    CUDA_TRY(r->msIB.ensure((size_t)tot[1] * 4 + 16));
+    CUDA_TRY(ifr_launch_mesh_compact((const int*)r->msCounts.p, dstarts, nwg, (const float4*)r->msPos.p, (const float4*)r->msVary.p, (const int*)r->msIdx.p, nv,
+                                     (float4*)r->msVB.p, (int*)r->msIB.p, 1, s));
+    r->stats.kernel_launches += 1;
+    // the ordinary draw over the compacted buffers: positions are clip space already -> passthrough vertex stage
+    const uint8_t* sVB = r->dVB; const int32_t* sIB = r->dIB;
+    const int sNverts = r->nverts, sNattr = r->nattr, sStride = r->stride, sIcount = r->icount, sVs = r->vsId, sNvary = r->nvary;
+    int sOff[IFR_MAX_VARY + 1]; memcpy(sOff, r->attrOff, sizeof sOff);
+    r->dVB = (const uint8_t*)r->msVB.p; r->dIB = (const int32_t*)r->msIB.p;
+    r->nverts = nverts; r->nattr = 1 + nv; r->stride = (1 + nv) * 16; r->icount = nidx; r->vsId = IFRIT_VS_PASSTHROUGH; r->nvary = nv;
+    for (int i = 0; i <= nv; i++) r->attrOff[i] = 16 * i;
+    mark_inputs(r);
+    int rc = iftrcuDrawElements(h);
+    if (!rc) rc = sync_and_check(r);      // the internal buffers are rebound below: this draw must be through with them
+    r->dVB = sVB; r->dIB = sIB; r->nverts = sNverts; r->nattr = sNattr; r->stride = sStride; r->icount = sIcount; r->vsId = sVs; r->nvary = sNvary;
+    memcpy(r->attrOff, sOff, sizeof sOff);
+    mark_inputs(r);
+    return rc;
+}
 
 int iftrcuSynchronize(iftrcuRenderer* h) { R_CHECK(h); return sync_and_check(r); }
 

@@ -173,6 +173,10 @@ cudaError_t ifr_launch_pack(const DrawParams& p, float* dst, int rank, int world
 cudaError_t ifr_launch_flag_store(uint32_t* word, uint32_t value, cudaStream_t s);
 cudaError_t ifr_launch_flag_wait(const uint32_t* words, int n, uint32_t value, uint32_t* timedOut, cudaStream_t s);
 #define IFR_FLAG_WORDS 128    // frame-flag block at the tail of the depth allocation: [0..63] per-rank, [64] owner's release
+cudaError_t ifr_launch_prims(const DrawParams& p, int mode, int vsId, int fsId, unsigned long long* keys, float4* seg, cudaStream_t s);
+cudaError_t ifr_launch_mesh_compact(const int* counts, int* starts, int nwg, const float4* pos, const float4* vary, const int* idx, int nvary,
+                                    float4* vb, int* ib, int stage, cudaStream_t s);
+cudaError_t ifr_launch_task_compact(const int3* sub, const int* num, int ntask, int* parentStart, int4* list, int* totals, int stage, cudaStream_t s);
 int ifr_kernels_per_draw();
 #endif   // !__CUDACC_RTC__
 #ifndef IFR_FLAG_WORDS

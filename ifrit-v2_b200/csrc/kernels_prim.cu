@@ -185,3 +185,87 @@ cudaError_t ifr_launch_prims(const DrawParams& p, int mode, int vsId, int fsId, 
         default: return cudaErrorInvalidValue;
     }
 }
+
+
+// ---- mesh / task front end: ordered compaction (meshShadingCompactionKernel CU:384-401, taskShadingScan / CompactKernel CU:418-444) -----
+// The reference allocates output ranges with atomics ("TODO: Ordering"); here a single-CTA scan keeps work-group order, so primitive ids —
+// and with them depth-tie resolution — are those of the same geometry drawn through drawElements.
+#define IFR_MS_MAX 768
+__global__ void __launch_bounds__(1024) mesh_scan_kernel(const int* __restrict__ counts, int* __restrict__ starts, int nwg) {
+    __shared__ int wsumV[32], wsumI[32], carryV, carryI;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) { carryV = 0; carryI = 0; }
+    __syncthreads();
+    for (int base = 0; base < nwg; base += 1024) {
+        const int w = base + tid;
+        const int nv = w < nwg ? min(max(counts[2 * w], 0), IFR_MS_MAX) : 0, ni = w < nwg ? min(max(counts[2 * w + 1], 0), IFR_MS_MAX) : 0;
+        int iv = nv, ii = ni;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int a = __shfl_up_sync(0xffffffffu, iv, o), b = __shfl_up_sync(0xffffffffu, ii, o);
+            if (lane >= o) { iv += a; ii += b; }
+        }
+        if (lane == 31) { wsumV[wid] = iv; wsumI[wid] = ii; }
+        __syncthreads();
+        if (wid == 0) {
+            int a = wsumV[lane], b = wsumI[lane];
+            const int a0 = a, b0 = b;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int x = __shfl_up_sync(0xffffffffu, a, o), y = __shfl_up_sync(0xffffffffu, b, o);
+                if (lane >= o) { a += x; b += y; }
+            }
+            wsumV[lane] = a - a0; wsumI[lane] = b - b0;
+        }
+        __syncthreads();
+        const int cv = carryV, ci = carryI;
+        if (w < nwg) { starts[2 * w] = cv + wsumV[wid] + iv - nv; starts[2 * w + 1] = ci + wsumI[wid] + ii - ni; }
+        __syncthreads();
+        if (tid == 1023) { carryV = cv + wsumV[31] + iv; carryI = ci + wsumI[31] + ii; }
+        __syncthreads();
+    }
+    if (tid == 0) { starts[2 * nwg] = carryV; starts[2 * nwg + 1] = carryI; }
+}
+__global__ void __launch_bounds__(256) mesh_copy_kernel(const int* __restrict__ counts, const int* __restrict__ starts, const float4* __restrict__ pos,
+                                                        const float4* __restrict__ vary, const int* __restrict__ idx, int nvary, float4* __restrict__ vb, int* __restrict__ ib) {
+    const int w = blockIdx.x;
+    const int nv = min(max(counts[2 * w], 0), IFR_MS_MAX), ni = min(max(counts[2 * w + 1], 0), IFR_MS_MAX);
+    const int v0 = starts[2 * w], i0 = starts[2 * w + 1];
+    for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+        float4* dst = vb + (size_t)(v0 + v) * (1 + nvary);
+        dst[0] = pos[(size_t)w * IFR_MS_MAX + v];
+        for (int k = 0; k < nvary; k++) dst[1 + k] = vary[((size_t)w * IFR_MS_MAX + v) * nvary + k];
+    }
+    for (int i = threadIdx.x; i < ni; i += blockDim.x) ib[i0 + i] = idx[(size_t)w * IFR_MS_MAX + i] + v0;
+}
+cudaError_t ifr_launch_mesh_compact(const int* counts, int* starts, int nwg, const float4* pos, const float4* vary, const int* idx, int nvary,
+                                    float4* vb, int* ib, int stage, cudaStream_t s) {
+    if (stage == 0) mesh_scan_kernel<<<1, 1024, 0, s>>>(counts, starts, nwg);
+    else mesh_copy_kernel<<<nwg, 256, 0, s>>>(counts, starts, pos, vary, idx, nvary, vb, ib);
+    return cudaGetLastError();
+}
+// one CTA: ordered list of the mesh work groups the task shaders asked for
+__global__ void __launch_bounds__(256) task_compact_kernel(const int3* __restrict__ sub, const int* __restrict__ num, int ntask, int* __restrict__ parentStart,
+                                                           int4* __restrict__ list, int* __restrict__ totals) {
+    __shared__ int run, mx, my, mz;
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int w = 0; w < ntask; w++) { parentStart[w] = acc; acc += min(max(num[w], 0), 32); }
+        run = acc; mx = 0; my = 0; mz = 0;
+    }
+    __syncthreads();
+    for (int w = threadIdx.x; w < ntask; w += blockDim.x) {
+        const int n = min(max(num[w], 0), 32), s0 = parentStart[w];
+        for (int i = 0; i < n; i++) {
+            const int3 d = sub[(size_t)w * 32 + i];
+            list[s0 + i] = make_int4(d.x, d.y, d.z, w);
+            atomicMax(&mx, d.x); atomicMax(&my, d.y); atomicMax(&mz, d.z);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { totals[0] = run; totals[1] = mx; totals[2] = my; totals[3] = mz; }
+}
+cudaError_t ifr_launch_task_compact(const int3* sub, const int* num, int ntask, int* parentStart, int4* list, int* totals, int, cudaStream_t s) {
+    task_compact_kernel<<<1, 256, 0, s>>>(sub, num, ntask, parentStart, list, totals);
+    return cudaGetLastError();
+}

@@ -69,7 +69,9 @@ __global__ void __launch_bounds__(256, 2) tile_blend_kernel(const __grid_constan
         __syncthreads();
         if ((tid & 31) == 0 && c) atomicAdd(&ctaSum, c);
         __syncthreads();
-        return ctaSum;
+        const uint32_t total = ctaSum;
+        __syncthreads();          // everyone has read the sum before the word is reused (compute-sanitizer racecheck)
+        return total;
     };
     // A tile with more than IFR_BLEND_CAP triangles is walked in rounds of consecutive key ranges [lo, hi), each holding at most
     // IFR_BLEND_CAP entries (hi found by bisection over the key space: ~30 counting passes over the tile's queues per round —

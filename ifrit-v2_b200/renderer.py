@@ -95,6 +95,9 @@ def load_library():
                                              "(or __graft_entry__.build()); there is no CPU fallback")
         L = C.CDLL(LIB_PATH)
         L.iftrcuCreateFragmentShaderFromSource.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.iftrcuCreateMeshShaderFromSource.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int)]
+        L.iftrcuCreateTaskShaderFromSource.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int)]
+        L.iftrcuCheckMeshShaderSource.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_size_t]
         L.iftrcuCheckFragmentShaderSource.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
         L.iftrcuGetLastError.restype = C.c_char_p
         L.iftrcuGetLastError.argtypes = [C.c_void_p]
@@ -274,8 +277,25 @@ class TileRasterRendererCuda:
                                                                 int(bool(needsDerivatives)), C.byref(sid)))
         return sid.value
 
+    def createMeshShaderFromSource(self, source, name="user_ms"):
+        sid = C.c_int(-1)
+        self._ck(self._lib.iftrcuCreateMeshShaderFromSource(self._h, name.encode(), source.encode(), C.byref(sid)))
+        return sid.value
+
+    def createTaskShaderFromSource(self, source, name="user_ts"):
+        sid = C.c_int(-1)
+        self._ck(self._lib.iftrcuCreateTaskShaderFromSource(self._h, name.encode(), source.encode(), C.byref(sid)))
+        return sid.value
+
     def bindGeometryShader(self, shader=0):
         self._ck(self._lib.iftrcuBindGeometryShader(self._h, shader))
+
+    def bindMeshShader(self, shaderId, numVaryings, localSize=(1, 1, 1)):
+        d = (C.c_int * max(numVaryings, 1))(*([IFTP_FLOAT4] * max(numVaryings, 1)))
+        self._ck(self._lib.iftrcuBindMeshShader(self._h, shaderId, d, numVaryings, *[int(x) for x in localSize]))
+
+    def bindTaskShader(self, shaderId=-1):
+        self._ck(self._lib.iftrcuBindTaskShader(self._h, shaderId, None, 0))
 
     def CreateTexture(self, slotId, width, height, mipLevels=0, arrayLayers=1):
         ci = IfritImageCreateInfo()
@@ -463,6 +483,14 @@ class TileRasterRendererCuda:
 
 def owned_tile_bytes(width, height, rank, world):
     return load_library().iftrcuOwnedTileBytes(width, height, rank, world)
+
+
+def check_mesh_shader_source(source, is_task=False):
+    """Compile-only check of a run-time mesh / task shader (no GPU needed): (status code, compiler log)."""
+    L = load_library()
+    buf = C.create_string_buffer(1 << 16)
+    rc = L.iftrcuCheckMeshShaderSource(source.encode(), int(bool(is_task)), buf, len(buf))
+    return rc, buf.value.decode(errors="replace")
 
 
 def check_fragment_shader_source(source, numVaryings, needsDerivatives=False, msaa=1):

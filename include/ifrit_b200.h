@@ -197,9 +197,20 @@ IFRIT_B200_API int iftrcuLookupVertexShader(const char* name);   /* -1 if unknow
 IFRIT_B200_API int iftrcuLookupFragmentShader(const char* name); /* -1 if unknown */
 /* out of scope: always IFRIT_ERR_UNSUPPORTED */
 IFRIT_B200_API int iftrcuBindGeometryShader(iftrcuRenderer* h, int shaderId);
+/* Mesh / task front end (RC::bindMeshShader / bindTaskShader / DrawMeshTasks, RC:88-89, 115; meshShadingEntryPoint CU:375-500).
+ * The shaders are CUDA source compiled at run time (NVRTC), with the argument lists of MeshShader::execute / TaskShader::execute:
+ *     __device__ void ms_main(const IfritMeshInput& in, float4* outPos, float4* outVaryings, int* outIndices,
+ *                             int& outNumVertices, int& outNumIndices);          // <= 768 vertices, <= 768 indices per work group
+ *     __device__ void ts_main(int workGroupId, void* outPayload, int3* outMeshWorkGroups, int& outNumMeshWorkGroups);   // <= 32, 128-byte payload
+ * in.localInvocation / in.workGroupId / in.payload / in.uniform[0..31]; ifritBuffer(in, slot) = buffer slot `slot` (float*);
+ * ifritMvp(in, pos) = the registry's `mvp` vertex shader.  outPos is clip space; outVaryings[vertex * numVaryings + k].
+ * iftrcuDrawMeshTasks runs [task ->] mesh work groups, compacts their output IN WORK-GROUP ORDER and draws it like drawElements. */
+IFRIT_B200_API int iftrcuCreateMeshShaderFromSource(iftrcuRenderer* h, const char* name, const char* cudaSource, int* shaderIdOut);
+IFRIT_B200_API int iftrcuCreateTaskShaderFromSource(iftrcuRenderer* h, const char* name, const char* cudaSource, int* shaderIdOut);
+IFRIT_B200_API int iftrcuCheckMeshShaderSource(const char* cudaSource, int isTaskShader, char* logOut, size_t logCap); /* compile only, no device */
 IFRIT_B200_API int iftrcuBindMeshShader(iftrcuRenderer* h, int shaderId, const int* varyingTypeDescs, int n,
                                         int lx, int ly, int lz);
-IFRIT_B200_API int iftrcuBindTaskShader(iftrcuRenderer* h, int shaderId, const int* varyingTypeDescs, int n);
+IFRIT_B200_API int iftrcuBindTaskShader(iftrcuRenderer* h, int shaderId /* -1 unbinds */, const int* varyingTypeDescs, int n);
 
 /* ---- resources ------------------------------------------------------------------------ */
 IFRIT_B200_API int iftrcuCreateTexture(iftrcuRenderer* h, int slot, const IfritImageCreateInfo* ci); /* RC::CreateTexture */
@@ -258,7 +269,7 @@ IFRIT_B200_API int iftrcuSetTileChunk(iftrcuRenderer* h, int entries);
 /* ---- draw ----------------------------------------------------------------------------- */
 IFRIT_B200_API int iftrcuClear(iftrcuRenderer* h);        /* RC::clear — fused into the next draw */
 IFRIT_B200_API int iftrcuDrawElements(iftrcuRenderer* h); /* RC::drawElements — asynchronous */
-IFRIT_B200_API int iftrcuDrawMeshTasks(iftrcuRenderer* h, int numWorkGroups, int firstWorkGroup); /* unsupported */
+IFRIT_B200_API int iftrcuDrawMeshTasks(iftrcuRenderer* h, int numWorkGroups, int firstWorkGroup); /* RC::DrawMeshTasks — synchronous */
 /* wait for everything issued so far (incl. the host copy-back of the colour image) */
 IFRIT_B200_API int iftrcuSynchronize(iftrcuRenderer* h);
 

@@ -75,6 +75,22 @@ public:
         return id;
     }
     void bindGeometryShader(int id) { ck(iftrcuBindGeometryShader(h_, id)); }
+    // mesh / task front end: shaders are CUDA source of ms_main / ts_main compiled at run time (include/ifrit_b200.h)
+    int createMeshShaderFromSource(const char* name, const char* cudaSource) {
+        int id = -1; ck(iftrcuCreateMeshShaderFromSource(h_, name, cudaSource, &id)); return id;
+    }
+    int createTaskShaderFromSource(const char* name, const char* cudaSource) {
+        int id = -1; ck(iftrcuCreateTaskShaderFromSource(h_, name, cudaSource, &id)); return id;
+    }
+    void bindMeshShader(int meshShaderId, int numVaryings, int lx, int ly, int lz) {
+        std::vector<int> layout(numVaryings > 0 ? numVaryings : 1, IFTP_FLOAT4);
+        ck(iftrcuBindMeshShader(h_, meshShaderId, layout.data(), numVaryings, lx, ly, lz));
+    }
+    template <class VaryingDescriptorT>
+    void bindMeshShader(int meshShaderId, VaryingDescriptorT& varyingDescriptor, int lx, int ly, int lz) {
+        bindMeshShader(meshShaderId, (int)varyingDescriptor.getVaryingCounts(), lx, ly, lz);
+    }
+    void bindTaskShader(int taskShaderId) { ck(iftrcuBindTaskShader(h_, taskShaderId, nullptr, 0)); }
 
     void CreateTexture(int slotId, const IfritImageCreateInfo& createInfo) { ck(iftrcuCreateTexture(h_, slotId, &createInfo)); }
     void CreateSampler(int slotId, const IfritSamplerT& samplerState) { ck(iftrcuCreateSampler(h_, slotId, &samplerState)); }

@@ -497,11 +497,13 @@ def test_small_triangle_soup_binning_stress(r):
 
 def test_unsupported_verbs_return_status(r):
     from ifrit_v2_b200 import renderer as R
-    for fn, args in ((r.bindGeometryShader, ()), (r.DrawMeshTasks, (1, 0)),
-                     (r.SetDepthFunc, (R.IF_COMPARE_OP_NOT_EQUAL,))):
+    for fn, args in ((r.bindGeometryShader, ()), (r.SetDepthFunc, (R.IF_COMPARE_OP_NOT_EQUAL,))):
         with pytest.raises(R.IfritError) as e:
             fn(*args)
         assert e.value.code == R.IFRIT_ERR_UNSUPPORTED
+    with pytest.raises(R.IfritError) as e:
+        r.DrawMeshTasks(1, 0)                 # no mesh shader bound (tests/test_mesh_shaders.py covers the front end)
+    assert e.value.code == R.IFRIT_ERR_STATE
     with pytest.raises(R.IfritError) as e:
         r.setBlendFunc(True, 2, 3, 1, 0)      # SRC_COLOR / ONE_MINUS_SRC_COLOR: the reference aborts on them (CU:3466)
     assert e.value.code == R.IFRIT_ERR_UNSUPPORTED
