@@ -211,8 +211,18 @@ def run_ours(args, cfg_name, do_e2e=True, fast_sampler=True):
     configure(r)
     sf = MG.SortFirstRenderer(r, dist, dev, mode=mg_mode, clears_every_frame=not getattr(args, 'no_preclear', False)) if world > 1 else None   # every bench frame is clear() + drawElements()
 
+    # N >= 4: draws of a million triangles and more split the triangle setup over the ranks (one all-gather of owner masks per
+    # frame, multigpu.SortFirstRenderer.distribute_setup); below that the replicated setup is cheaper than the collective.  The
+    # setup pass is memory bound (indices + vertex gather in, records out): with the masks a rank reads 2 / N of the geometry
+    # instead of all of it, which is nothing at N = 2 (measured: c5 12.48 vs 11.91 ms, profiles/r02_mgpu.txt) and 3x less at N = 8
+    dsetup = bool(sf) and 4 <= world <= 8 and ntri >= (1 << 20) and not getattr(args, "no_distributed_setup", False)
+    if getattr(args, "force_distributed_setup", False) and sf and world <= 8:
+        dsetup = True
+
     def step():
         r.clear()
+        if dsetup:
+            sf.distribute_setup(ntri)
         r.drawElements()
         if sf:
             sf.gather()
@@ -401,7 +411,8 @@ def run_ours(args, cfg_name, do_e2e=True, fast_sampler=True):
                        f"{W * H * 20 / 1e6:.0f} MB + texture) exceeds the 126 MB L2",
                        "sampler": ("FAST (opt-in): texture-unit bilinear blend, 8-bit weights, SFU lod math" if fast_sampler else
                                    "default: software fp32 lerps, the oracle's arithmetic op for op") if sc["tex"] is not None else "none",
-                       "parallelism": f"sort-first x{world} ({mg_mode})" if world > 1 else "1 GPU"},
+                       "parallelism": (f"sort-first x{world} ({mg_mode}" + (", pre-cleared release" if not getattr(args, "no_preclear", False) else "") +
+                                       (", triangle setup split over the ranks + NCCL all-gather of owner masks every frame" if dsetup else "") + ")") if world > 1 else "1 GPU"},
             "fps": 1e3 / ms_step, "gfrags_per_s": frags / (ms_step * 1e-3) / 1e9,
             "frame_latency_ms": lat_ms,
             "pipelining": "geometry stage of frame k+1 (own stream, second scratch set) overlaps the tile kernel of frame k; frame_latency_ms = same steps with it off",
@@ -480,6 +491,8 @@ def main():
     ap.add_argument("--no-exact-sampler", "--no-fast-sampler", dest="no_exact_sampler", action="store_true",
                     help="skip the extra run with the library's default (exact) sampler")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-distributed-setup", action="store_true", help="A/B (N > 1): every rank assembles every triangle")
+    ap.add_argument("--force-distributed-setup", action="store_true", help="A/B (N > 1): split the triangle setup whatever the rank / triangle count")
     ap.add_argument("--no-preclear", action="store_true", help="A/B (N > 1, peer mode): plain frame release, every rank sends all of its tiles")
     ap.add_argument("--tile-chunk", type=int, default=0, choices=[0, 32, 64], help="A/B: big-queue entries per staged chunk of the tile kernel (0 = automatic)")
     ap.add_argument("--no-grid-hint", action="store_true", help="A/B: tile kernel grid of one CTA per tile instead of the measured CTA count")

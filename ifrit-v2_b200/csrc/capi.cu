@@ -73,6 +73,7 @@ struct iftrcuRenderer {
     uint32_t* frameFlags = nullptr;       // frame-flag block of the bound framebuffer (own or peer), see kernels_image.cu
     uint32_t* hTimedOut = nullptr;        // pinned: set by a flag wait that gave up
     uint32_t fenceFrame = 0; bool fencePending = false;   // peer: next tile kernel waits for the owner's release
+    const uint8_t* triMask = nullptr;                     // iftrcuSetTriangleOwnerMask (distributed triangle setup)
     bool skipArmed = false; int lastSkip = 0;             // peer: the owner pre-cleared the frame (iftrcuFrameFenceCleared)
 
     // geometry
@@ -480,6 +481,7 @@ static void build_params(iftrcuRenderer* r, DrawParams& p) {
     p.scissorEnable = r->scissorEnable; p.nScissor = r->nScissor;
     memcpy(p.scissor, r->scissor, sizeof p.scissor);
     p.rank = r->rank; p.world = r->world;
+    p.triMask = (r->world > 1 && r->world <= 8) ? r->triMask : nullptr;
     p.hwFilter = r->hwFilter ? 1 : 0;
     p.bigChunk = 64;
     tma_maps(r, p);
@@ -564,6 +566,9 @@ static int ensure_pipeline(iftrcuRenderer* r) {
         CUDA_TRY(cudaEventCreateWithFlags(&r->evTileDone[k], cudaEventDisableTiming));
     }
     CUDA_TRY(cudaEventCreateWithFlags(&r->evInputs, cudaEventDisableTiming));
+    // everything issued on the draw stream so far (uploads of the bound buffers, a triangle owner mask) precedes the first
+    // geometry stage on the new stream
+    if (cudaEventRecord(r->evInputs, r->stream) == cudaSuccess) r->inputsDirty = true;
     return IFRIT_OK;
 }
 
@@ -1619,6 +1624,42 @@ size_t iftrcuOwnedTileBytes(int width, int height, int rank, int worldSize) {
 }
 
 // ---- sort-first frame flags (peer-memory mode): see kernels_image.cu ----
+/* Distributed triangle setup (sort-first, world <= 8).  iftrcuClassifyTriangles: this rank assembles triangles [first, first + count) of
+ * the bound draw and writes their owner masks into devMask[first ...] (one byte per triangle of the whole draw, caller-owned device
+ * memory) on the geometry stream (iftrcuGetGeometryStream).  After the ranks have exchanged their slices (NCCL all-gather, ordered on that stream),
+ * iftrcuSetTriangleOwnerMask hands the complete array to the next draws; NULL returns to "every rank assembles everything". */
+int iftrcuClassifyTriangles(iftrcuRenderer* h, int firstTriangle, int count, void* devMask) {
+    R_CHECK(h);
+    if (!devMask || firstTriangle < 0 || count < 0 || firstTriangle + count > r->icount / 3) return r->fail(IFRIT_ERR_INVALID, "ClassifyTriangles", "bad range");
+    if (r->world < 2 || r->world > 8) return r->fail(IFRIT_ERR_STATE, "ClassifyTriangles", "needs a tile partition over 2..8 ranks");
+    if (!r->dVB || !r->dIB || r->vsId < 0 || !r->W) return r->fail(IFRIT_ERR_STATE, "ClassifyTriangles", "framebuffer, vertex / index buffers and vertex shader must be bound");
+    if (!r->fusedVS) return r->fail(IFRIT_ERR_UNSUPPORTED, "ClassifyTriangles", "needs the fused vertex stage");
+    // on the GEOMETRY stream (iftrcuGetGeometryStream): the classification, the all-gather the caller orders behind it on that
+    // stream and the setup pass that reads the masks all overlap the previous frame's tile kernel, like the rest of the stage
+    cudaStream_t g = r->stream;
+    if (r->pipelining) {
+        int rc = ensure_pipeline(r); if (rc) return rc;
+        g = r->geomStream;
+        if (r->inputsDirty) { CUDA_TRY(cudaStreamWaitEvent(g, r->evInputs, 0)); r->inputsDirty = false; }
+    }
+    DrawParams p;
+    build_params(r, p);
+    CUDA_TRY(ifr_launch_classify(p, r->vsId, firstTriangle, count, (uint8_t*)devMask, g));
+    r->stats.kernel_launches += 1;
+    return IFRIT_OK;
+}
+int iftrcuGetGeometryStream(iftrcuRenderer* h, void** cudaStreamOut) {
+    R_CHECK(h);
+    if (!cudaStreamOut) return IFRIT_ERR_INVALID;
+    if (r->pipelining) { int rc = ensure_pipeline(r); if (rc) return rc; }
+    *cudaStreamOut = (void*)(r->pipelining ? r->geomStream : r->stream);
+    return IFRIT_OK;
+}
+int iftrcuSetTriangleOwnerMask(iftrcuRenderer* h, const void* devMask) {
+    R_CHECK(h);
+    r->triMask = (const uint8_t*)devMask;      // read by the next setup pass, on the geometry stream, behind whatever the caller ordered there
+    return IFRIT_OK;
+}
 int iftrcuFrameSignal(iftrcuRenderer* h, uint32_t frameId) {
     R_CHECK(h);
     if (!r->frameFlags || r->rank < 0 || r->rank >= 64) return r->fail(IFRIT_ERR_STATE, "FrameSignal", "no renderer-owned or peer framebuffer bound");

@@ -78,6 +78,9 @@ struct DrawParams {
     // sort-first exchange: 1 = a peer whose owner has pre-cleared the frame (iftrcuFrameReleaseCleared) does not send the
     // colour of its EMPTY tiles over NVLink in a clearing draw; 2 (clear_kernel only) = clear the tiles of the OTHER ranks
     int skipEmptyStores;
+    // distributed triangle setup (kernels_geometry.cu: classify_kernel): one owner-mask byte per input triangle, bit r = rank r owns
+    // a tile of its box; null = every rank assembles every triangle
+    const uint8_t* triMask;
     // ordered alpha blending (pixelShadingAlphaBlendKernel CU:1649-1897): colour src / colour dst / alpha src / alpha dst
     // coefficients {x1, x(1 - src.a), x(1 - dst.a), zero flag} (updateBlendStateKernel CU:3436-3537)
     int blendEnable; float blendCoef[4][4];
@@ -173,6 +176,7 @@ cudaError_t ifr_launch_pack(const DrawParams& p, float* dst, int rank, int world
 cudaError_t ifr_launch_flag_store(uint32_t* word, uint32_t value, cudaStream_t s);
 cudaError_t ifr_launch_flag_wait(const uint32_t* words, int n, uint32_t value, uint32_t* timedOut, cudaStream_t s);
 #define IFR_FLAG_WORDS 128    // frame-flag block at the tail of the depth allocation: [0..63] per-rank, [64] owner's release
+cudaError_t ifr_launch_classify(const DrawParams& p, int vsMode, int first, int count, uint8_t* mask, cudaStream_t s);
 cudaError_t ifr_launch_prims(const DrawParams& p, int mode, int vsId, int fsId, unsigned long long* keys, float4* seg, cudaStream_t s);
 cudaError_t ifr_launch_mesh_compact(const int* counts, int* starts, int nwg, const float4* pos, const float4* vary, const int* idx, int nvary,
                                     float4* vb, int* ib, int stage, cudaStream_t s);

@@ -70,6 +70,7 @@ struct Assembled {
 };
 
 // viewport + snap + rejects + cull for one fan triangle (devGeometryCullClip CU:1399-1483)
+template <bool ALLRANKS = false>
 __device__ __forceinline__ void finish_triangle(const DrawParams& p, const ClipV& v0, const ClipV& v1,
                                                 const ClipV& v2, bool clipped, Assembled& a) {
     a.ok = false;
@@ -141,7 +142,7 @@ __device__ __forceinline__ void finish_triangle(const DrawParams& p, const ClipV
     const long long boxArea = (long long)(px1 - px0 + 1) * (py1 - py0 + 1);
     if (boxArea <= IFR_SMALL_AREA) a.flags |= IFR_FLAG_SMALL;
     a.tx0 = px0 >> 4; a.tx1 = px1 >> 4; a.ty0 = py0 >> 4; a.ty1 = py1 >> 4;
-    if (p.world > 1) {
+    if (!ALLRANKS && p.world > 1) {      // ALLRANKS: the classification pass of the distributed setup decides for every rank
         // sort-first: a triangle whose box touches no super-tile of this rank contributes nothing here — drop it
         // before the 64-byte record store and the fill pass (geometry is replicated; this keeps the replicated
         // part to reading it).  Boxes spanning >= world super-tiles in a row always contain an owned one.
@@ -164,7 +165,7 @@ __device__ __forceinline__ float4 fetch_pos(const DrawParams& p, int i) {
     return run_vs<VSMODE>(p, __ldg(reinterpret_cast<const float4*>(p.vb + (size_t)i * p.stride + p.attrOff[0])));
 }
 
-template <int VSMODE>
+template <int VSMODE, bool ALLRANKS = false>
 __device__ int assemble(const DrawParams& p, int t, Assembled out[2]) {
     const bool cpu = p.convention == IFRIT_CONVENTION_CPU;
     const int i0 = __ldg(p.ib + 3 * (size_t)t), i1 = __ldg(p.ib + 3 * (size_t)t + 1), i2 = __ldg(p.ib + 3 * (size_t)t + 2);
@@ -182,7 +183,7 @@ __device__ int assemble(const DrawParams& p, int t, Assembled out[2]) {
     }
     if (w0 > 0 && w1 > 0 && w2 > 0) {
         // no sign change: Sutherland–Hodgman emits (v2, v3, v1) — CU:1361-1396
-        finish_triangle(p, src[1], src[2], src[0], false, out[0]);
+        finish_triangle<ALLRANKS>(p, src[1], src[2], src[0], false, out[0]);
         return 1;
     }
     ClipV poly[6];
@@ -204,7 +205,7 @@ __device__ int assemble(const DrawParams& p, int t, Assembled out[2]) {
     if (np < 3) return 0;
     int nf = 0;
     for (int f = 0; f < np - 2 && f < 2; f++) {
-        finish_triangle(p, poly[0], poly[f + 1], poly[f + 2], clipped, out[f]);
+        finish_triangle<ALLRANKS>(p, poly[0], poly[f + 1], poly[f + 2], clipped, out[f]);
         nf = f + 1;
     }
     return nf;
@@ -241,18 +242,17 @@ __device__ __forceinline__ bool tile_may_cover(const EdgeSet& e, int tx, int ty)
 __device__ __forceinline__ bool tile_owned(const DrawParams& p, int tx, int ty) {
     return p.world <= 1 || ifr_tile_owner(tx, ty, p.world) == p.rank;
 }
-// Sort-first (world > 1): does this rank own any tile of the box?  Ownership interleaves 64-px super-tiles
-// (common.cuh: ifr_tile_owner); boxes of more than 16 super-tiles are kept without looking (conservative).
-__device__ __forceinline__ bool box_owned(const DrawParams& p, int tx0, int tx1, int ty0, int ty1) {
-    if (p.world <= 1) return true;
+// bit r set <=> rank r owns a tile of the box (ownership interleaves 64-px super-tiles, common.cuh: ifr_tile_owner; boxes of more
+// than 16 super-tiles go to everyone) — a superset of the ranks finish_triangle keeps the triangle on
+__device__ __forceinline__ uint32_t box_owner_mask(int world, int tx0, int tx1, int ty0, int ty1) {
     constexpr int ST = IFR_SUPER / IFR_TILE;
+    const uint32_t all = world >= 32 ? 0xffffffffu : ((1u << world) - 1u);
     const int sx0 = tx0 / ST, sx1 = tx1 / ST, sy0 = ty0 / ST, sy1 = ty1 / ST;
-    if (sx0 == sx1 && sy0 == sy1) return (sx0 + 3 * sy0) % p.world == p.rank;     // the common case: one super-tile
-    if ((sx1 - sx0 + 1) * (sy1 - sy0 + 1) > 16) return true;
+    if ((sx1 - sx0 + 1) * (sy1 - sy0 + 1) > 16) return all;
+    uint32_t m = 0;
     for (int sy = sy0; sy <= sy1; sy++)
-        for (int sx = sx0; sx <= sx1; sx++)
-            if ((sx + 3 * sy) % p.world == p.rank) return true;
-    return false;
+        for (int sx = sx0; sx <= sx1; sx++) m |= 1u << ((sx + 3 * sy) % world);
+    return m;
 }
 __device__ __forceinline__ void count_one(const DrawParams& p, int big, int tx, int ty) {
     if (!tile_owned(p, tx, ty)) return;
@@ -387,22 +387,47 @@ __device__ __forceinline__ void store_record(const DrawParams& p, uint32_t slot,
 #ifndef IFR_SETUP_MINB
 #define IFR_SETUP_MINB 3
 #endif
+// Sort-first with a DISTRIBUTED triangle setup (iftrcuClassifyTriangles): rank r assembles triangles [first, first + count)
+// — 1 / world of the draw — only far enough to know which ranks own a tile of each triangle's box, and writes one owner-mask byte per
+// triangle.  The ranks all-gather the masks (NCCL, world x ntri / world bytes), after which setup_count_kernel runs the assembly
+// only for the triangles whose mask names this rank: the per-triangle arithmetic that every rank used to repeat for the whole
+// draw (3 ms of c5 whatever the rank count) is divided by world, plus the overlap of triangles that straddle super-tiles.
+template <int VSMODE>
+__global__ void __launch_bounds__(256, IFR_SETUP_MINB) classify_kernel(const __grid_constant__ DrawParams p, int first, int count, uint8_t* __restrict__ mask) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int t = first + i;
+    Assembled a[2];
+    a[0].ok = a[1].ok = false;
+    assemble<VSMODE, true>(p, t, a);
+    uint32_t m = 0;
+#pragma unroll
+    for (int f = 0; f < 2; f++)
+        if (a[f].ok) m |= box_owner_mask(p.world, a[f].tx0, a[f].tx1, a[f].ty0, a[f].ty1);
+    mask[t] = (uint8_t)m;
+}
+cudaError_t ifr_launch_classify(const DrawParams& p, int vsMode, int first, int count, uint8_t* mask, cudaStream_t s) {
+    if (count <= 0) return cudaSuccess;
+    const int blocks = (count + 255) / 256;
+    if (vsMode == IFRIT_VS_MVP) classify_kernel<IFRIT_VS_MVP><<<blocks, 256, 0, s>>>(p, first, count, mask);
+    else if (vsMode == IFRIT_VS_PASSTHROUGH) classify_kernel<IFRIT_VS_PASSTHROUGH><<<blocks, 256, 0, s>>>(p, first, count, mask);
+    else classify_kernel<-1><<<blocks, 256, 0, s>>>(p, first, count, mask);
+    return cudaGetLastError();
+}
+
 template <int VSMODE>
 __global__ void __launch_bounds__(256, IFR_SETUP_MINB) setup_count_kernel(const __grid_constant__ DrawParams p) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     Assembled a[2];
     a[0].ok = a[1].ok = false;
-    if (t < p.ntri) assemble<VSMODE>(p, t, a);
+    // distributed setup: some rank has already established that no tile of this triangle is ours
+    if (t < p.ntri && !(p.triMask && !((p.triMask[t] >> p.rank) & 1))) assemble<VSMODE>(p, t, a);
     unsigned long long nasm = 0;
 #pragma unroll
     for (int f = 0; f < 2; f++) {
         bool has = a[f].ok;
         const uint32_t slot = f == 0 ? (uint32_t)t : (uint32_t)(p.ntri + t);
         if (has) nasm++;
-        // sort-first: a triangle none of whose tiles this rank owns ends here — no record, no queue entry, no place in
-        // the heavy list; the replicated part of the geometry stage is then the assembly arithmetic alone, while its
-        // memory traffic and the whole fill pass scale with 1 / world ("geometry is broadcast")
-        if (has && !box_owned(p, a[f].tx0, a[f].tx1, a[f].ty0, a[f].ty1)) has = false;
         const int big = has && !(a[f].flags & IFR_FLAG_SMALL);
         EdgeSet e;
         if (has) {

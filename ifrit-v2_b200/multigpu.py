@@ -117,6 +117,29 @@ class SortFirstRenderer:
         renderer.setTilePartition(self.rank, self.world)
         self.torch = torch
         self.packed = None
+        self._mask = None
+
+    def distribute_setup(self, ntri):
+        """Before drawElements(): split the triangle setup over the ranks (peer / nccl mode alike).  Every rank classifies its 1 / world
+        slice of the draw's triangles (which ranks own a tile of each), the slices are all-gathered over NCCL on the renderer's stream,
+        and the following draw assembles only the triangles that name this rank (iftrcuClassifyTriangles / SetTriangleOwnerMask).  Must
+        be called again whenever the geometry or the transform changes — i.e. every frame of an animated scene."""
+        torch, r = self.torch, self.r
+        if self.world < 2 or self.world > 8:
+            return
+        chunk = (ntri + self.world - 1) // self.world
+        chunk = (chunk + 15) // 16 * 16
+        if self._mask is None or self._mask.numel() != chunk * self.world:
+            self._mask = torch.zeros(chunk * self.world, dtype=torch.uint8, device=self.device)
+        first = self.rank * chunk
+        count = max(0, min(ntri, first + chunk) - first)
+        # everything on the renderer's GEOMETRY stream: classification -> all-gather -> (next draw's) setup pass, so that the whole
+        # chain overlaps the previous frame's tile kernel on the draw stream
+        r.classifyTriangles(first, count, self._mask.data_ptr())
+        g = torch.cuda.ExternalStream(r.geometryStream(), device=self.device)
+        with torch.cuda.stream(g):
+            self.dist.all_gather_into_tensor(self._mask, self._mask[first:first + chunk])
+        r.setTriangleOwnerMask(self._mask.data_ptr())
 
     def gather(self, hold=False):
         """After drawElements(): rank 0's device framebuffer becomes the complete frame (in stream order on rank 0).

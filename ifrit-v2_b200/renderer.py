@@ -458,6 +458,17 @@ class TileRasterRendererCuda:
         return out[: min(n.value, cap)], n.value
 
     # sort-first frame flags (peer-memory mode), see include/ifrit_b200.h
+    def classifyTriangles(self, first, count, dev_mask_ptr):
+        self._ck(self._lib.iftrcuClassifyTriangles(self._h, int(first), int(count), C.c_void_p(dev_mask_ptr)))
+
+    def geometryStream(self):
+        out = C.c_void_p()
+        self._ck(self._lib.iftrcuGetGeometryStream(self._h, C.byref(out)))
+        return out.value or 0
+
+    def setTriangleOwnerMask(self, dev_mask_ptr):
+        self._ck(self._lib.iftrcuSetTriangleOwnerMask(self._h, C.c_void_p(dev_mask_ptr) if dev_mask_ptr else None))
+
     def frameSignal(self, frame_id):
         self._ck(self._lib.iftrcuFrameSignal(self._h, C.c_uint32(frame_id)))
 

@@ -322,6 +322,14 @@ IFRIT_B200_API int iftrcuBindPeerFrameBuffer(iftrcuRenderer* h, const void* hand
  *                ... consume the frame ...; iftrcuFrameRelease(id)  "frame id may be overwritten"
  *   peers      : iftrcuFrameFence(id)                           the NEXT tile kernel first waits for the release of id
  * A wait gives up after 2 s (a later iftrcuSynchronize then returns IFRIT_ERR_STATE); the device never hangs. */
+/* Distributed triangle setup (2..8 ranks): each rank classifies 1 / worldSize of the draw's triangles — which ranks own a tile of
+ * the triangle's box, one mask byte per triangle into devMask[first ...] (caller-owned device array of one byte per triangle of
+ * the whole draw) — the ranks all-gather their slices (NCCL), and iftrcuSetTriangleOwnerMask gives the complete array to the
+ * following draws, whose setup pass then assembles only the triangles that name this rank.  Frames are unchanged. */
+IFRIT_B200_API int iftrcuClassifyTriangles(iftrcuRenderer* h, int firstTriangle, int count, void* devMask);
+IFRIT_B200_API int iftrcuSetTriangleOwnerMask(iftrcuRenderer* h, const void* devMask /* NULL = off */);
+/* the stream the geometry stage (and iftrcuClassifyTriangles) runs on: the caller's all-gather of the masks must be ordered on it */
+IFRIT_B200_API int iftrcuGetGeometryStream(iftrcuRenderer* h, void** cudaStreamOut);
 IFRIT_B200_API int iftrcuFrameSignal(iftrcuRenderer* h, uint32_t frameId);
 IFRIT_B200_API int iftrcuFrameWait(iftrcuRenderer* h, uint32_t frameId);
 IFRIT_B200_API int iftrcuFrameRelease(iftrcuRenderer* h, uint32_t frameId);

@@ -21,7 +21,7 @@ def main():
     u = scenes.uniform_block(scenes.default_mvp(W, H))
     tex = scenes.texture_checker(size=128, seed=7)
     ok = True
-    for mode in ("peer", "peer+preclear", "nccl"):
+    for mode in ("peer", "peer+preclear", "peer+preclear+dsetup", "nccl"):
         for msaa in (1, 8):
             r = R.TileRasterRendererCuda(local)
             r.Init()
@@ -31,7 +31,7 @@ def main():
             r.width, r.height = W, H
             if mode == "nccl":
                 r.bindFrameBuffer(None, None, W, H)
-            sf = MG.SortFirstRenderer(r, dist, dev, mode=mode.split("+")[0], clears_every_frame=mode.endswith("preclear"))
+            sf = MG.SortFirstRenderer(r, dist, dev, mode=mode.split("+")[0], clears_every_frame="preclear" in mode)
             R.setup_scene(r, vb, idx, R.VS_MVP, R.FS_TEXTURED, 2, u, texture=tex, mip_levels=7,
                           sampler=dict(filterMode=1, anisotropyEnable=True, maxAnisotropy=16.0))
             r.setMsaaSamples(msaa)
@@ -39,6 +39,8 @@ def main():
             r.setClearValues([(0.1, 0.2, 0.3, 1.0)], 255.0)
             for f in range(3):             # frames 2 and 3 of "peer+preclear" run with the empty tiles kept off NVLink
                 r.clear()
+                if mode.endswith("dsetup"):          # triangle setup split over the ranks, owner masks all-gathered
+                    sf.distribute_setup(len(idx) // 3)
                 r.drawElements()
                 sf.gather(hold=(f == 2))   # the last frame is held until it has been read (a release lets it be overwritten)
             torch.cuda.synchronize()

@@ -79,7 +79,7 @@ def test_peer_mode_frame_flag_protocol():
 
         def __getattr__(self, name):
             if name.startswith("frame"):
-                return lambda fid: self.calls.append((name, fid))
+                return lambda fid, cleared=False: self.calls.append((name, fid))
             raise AttributeError(name)
 
     class Dist:
