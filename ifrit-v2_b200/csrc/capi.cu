@@ -116,7 +116,7 @@ struct iftrcuRenderer {
     // scratch: two sets, so that the geometry stage of frame k + 1 (setup / scan / fill on the geometry stream) can run
     // while the tile kernel of frame k (draw stream) still reads the queues of frame k — iftrcuSetFramePipelining
     struct Scratch {
-        DevBuf scanPartial, pos, vary, rec, clipBary, tileBox, fan1List, heavyBits, tileCount, tileStart, tileCursor, tileOrder, queue, bigQueue, counters;
+        DevBuf scanPartial, pos, vary, rec, clipBary, planes, tileBox, fan1List, heavyBits, tileCount, tileStart, tileCursor, tileOrder, queue, bigQueue, counters;
         bool queueChecked = false;   // queue capacity verified for the current geometry / state
         uint32_t gridHint = 0;       // exact CTA count of the tile kernel for that geometry / state (DrawParams::gridHint)
         uint32_t avgBig = 0xffffffffu;   // big-queue entries per non-empty tile of that draw (unknown: treated as deep)
@@ -459,6 +459,11 @@ int rtc_launch(iftrcuRenderer* r, const DrawParams& p, cudaStream_t s) {
 }
 }   // namespace
 
+// the FAST textured shaders (opt-in sampler, plain tile kernel) read their varyings from per-triangle attribute planes
+// (kernels_geometry.cu: planes_kernel), written once per draw behind the fill pass
+static bool needs_planes(const iftrcuRenderer* r) {
+    return IFR_PLANES && r->hwFilter && (r->fsId == IFRIT_FS_TEXTURED || r->fsId == IFRIT_FS_TEXTURED_LOD0) && !r->blendEnable;
+}
 static void build_params(iftrcuRenderer* r, DrawParams& p) {
     memset(&p, 0, sizeof p);
     p.color = r->dColor; p.depth = r->dDepth; p.primIds = r->debugIds ? (int32_t*)r->primIds.p : nullptr;
@@ -514,6 +519,7 @@ static void build_params(iftrcuRenderer* r, DrawParams& p) {
         for (int k = 0; k < IFR_MAX_VARY; k++) p.varyOff[k] = 16 * k;
     }
     p.rec = (TriRec*)r->scr[r->set].rec.p; p.clipBary = (float*)r->scr[r->set].clipBary.p; p.tileBox = (uint2*)r->scr[r->set].tileBox.p;
+    p.planes = needs_planes(r) ? (const float4*)r->scr[r->set].planes.p : nullptr;
     p.fan1List = (uint32_t*)r->scr[r->set].fan1List.p; p.heavyBits = (uint32_t*)r->scr[r->set].heavyBits.p;
     p.tileCount = (uint32_t*)r->scr[r->set].tileCount.p; p.tileStart = (uint32_t*)r->scr[r->set].tileStart.p;
     p.tileCursor = (uint32_t*)r->scr[r->set].tileCursor.p; p.queue = (uint32_t*)r->scr[r->set].queue.p;
@@ -530,6 +536,7 @@ static void build_params(iftrcuRenderer* r, DrawParams& p) {
 
 static int ensure_scratch(iftrcuRenderer* r) {
     const size_t ntri = (size_t)r->icount / 3, ntiles = (size_t)((r->W + 15) / 16) * ((r->H + 15) / 16);
+    if (needs_planes(r)) CUDA_TRY(r->scr[r->set].planes.ensure(std::max<size_t>(1, 2 * ntri) * IFR_PLANE_QUADS * sizeof(float4)));
     if (!r->fusedVS) {
         CUDA_TRY(r->scr[r->set].pos.ensure(std::max<size_t>(1, r->nverts) * sizeof(float4)));
         CUDA_TRY(r->scr[r->set].vary.ensure(std::max<size_t>(1, (size_t)r->nverts * std::max(1, r->nvary)) * sizeof(float4)));
@@ -641,6 +648,7 @@ static int issue_draw(iftrcuRenderer* r, bool forceCheck, bool sameSet = false) 
     if (r->forceBigChunk == 32) p.bigChunk = 32;
     p.gridHint = (sc.queueChecked && r->useGridHint) ? sc.gridHint : 0;
     CUDA_TRY(ifr_launch_fill(p, g));
+    if (p.planes) { CUDA_TRY(ifr_launch_planes(p, g)); r->stats.kernel_launches += 1; }
     if (ev) CUDA_TRY(cudaEventRecord(ev[4], g));
     if (pipe) {
         CUDA_TRY(cudaEventRecord(r->evGeomDone[r->set], g));
@@ -814,7 +822,7 @@ int iftrcuDestroyInstance(iftrcuRenderer* h) {
                       &r->msCounts, &r->msStarts, &r->msVB, &r->msIB, &r->tsPayload, &r->tsSub, &r->tsNum, &r->tsParent, &r->tsList};
     for (int k = 0; k < 2; k++) {
         iftrcuRenderer::Scratch& c = r->scr[k];
-        DevBuf* sb[] = {&c.scanPartial, &c.pos, &c.vary, &c.rec, &c.clipBary, &c.tileBox, &c.fan1List, &c.heavyBits, &c.tileCount, &c.tileStart,
+        DevBuf* sb[] = {&c.scanPartial, &c.pos, &c.vary, &c.rec, &c.clipBary, &c.planes, &c.tileBox, &c.fan1List, &c.heavyBits, &c.tileCount, &c.tileStart,
                         &c.tileCursor, &c.tileOrder, &c.queue, &c.bigQueue, &c.counters};
         for (DevBuf* b : sb) b->release();
         if (r->evGeomDone[k]) cudaEventDestroy(r->evGeomDone[k]);

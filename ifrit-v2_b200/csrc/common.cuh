@@ -40,6 +40,12 @@ struct __align__(16) TriRec {
 #define IFR_FLAG_SMALL 8     // pixel bbox area <= IFR_SMALL_AREA: thread-per-triangle path of the tile kernel
 #define IFR_FLAG_WIDE 16     // an edge delta exceeds 2^20 sub-pixels (4096 px): int64 coverage path
 #define IFR_SMALL_AREA 16
+// FAST textured shaders: per-triangle screen-space planes of the perspective numerators instead of per-fragment barycentric
+// interpolation from the vertex data (-DIFR_PLANES=0: A/B switch, the FAST shaders interpolate like the exact ones)
+#ifndef IFR_PLANES
+#define IFR_PLANES 1
+#endif
+#define IFR_PLANE_QUADS 5
 
 // Per (triangle, tile) raster setup, written by the fill pass into the tile's big-triangle queue and
 // read with uniform 128-bit loads by every pixel thread of the tile: six 16-byte words.
@@ -101,6 +107,9 @@ struct DrawParams {
     const uint8_t* varyBase; int varyStride; int varyOff[IFR_MAX_VARY];
     // assembled triangles: rec[slot*3+v]; slot = prim (fan 0) or ntri + prim (fan 1)
     TriRec* rec; float* clipBary;    // clipBary[slot*6]
+    // attribute planes of the FAST textured shaders (kernels_geometry.cu: planes_kernel; tile_kernel.cuh: interp_planes):
+    // IFR_PLANE_QUADS float4 per slot, null when the draw's shader does not use them
+    const float4* planes;
     uint2* tileBox;                  // per slot: packed tile bbox, x = x0 | x1<<16, y = y0 | y1<<16 | small<<31; x0>x1 = none
     uint32_t* fan1List;              // slots of second fan triangles (clipped primitives only)
     uint32_t* heavyBits;             // one bit per first-fan slot: left to the heavy fill pass (multi-tile or big)
@@ -176,6 +185,7 @@ cudaError_t ifr_launch_pack(const DrawParams& p, float* dst, int rank, int world
 cudaError_t ifr_launch_flag_store(uint32_t* word, uint32_t value, cudaStream_t s);
 cudaError_t ifr_launch_flag_wait(const uint32_t* words, int n, uint32_t value, uint32_t* timedOut, cudaStream_t s);
 #define IFR_FLAG_WORDS 128    // frame-flag block at the tail of the depth allocation: [0..63] per-rank, [64] owner's release
+cudaError_t ifr_launch_planes(const DrawParams& p, cudaStream_t s);
 cudaError_t ifr_launch_classify(const DrawParams& p, int vsMode, int first, int count, uint8_t* mask, cudaStream_t s);
 cudaError_t ifr_launch_prims(const DrawParams& p, int mode, int vsId, int fsId, unsigned long long* keys, float4* seg, cudaStream_t s);
 cudaError_t ifr_launch_mesh_compact(const int* counts, int* starts, int nwg, const float4* pos, const float4* vary, const int* idx, int nvary,

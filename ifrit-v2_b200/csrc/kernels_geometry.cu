@@ -696,3 +696,108 @@ cudaError_t ifr_launch_fill(const DrawParams& p, cudaStream_t s) {
     fill_heavy_kernel<<<heavyBlocks, 128, 0, s>>>(p, wordsPerWarp, split);
     return cudaGetLastError();
 }
+
+// ---- attribute planes of the FAST textured shaders ------------------------------------------------------------------------------
+// The exact shaders interpolate every fragment from the triangle record, the three indices and the three vertices' varyings
+// (tile_kernel.cuh: interp — 13 dependent loads and ~170 instructions per fragment with derivatives).  The perspective numerators
+// N_i = beta_i * IW_i are AFFINE in the pixel position, and so are their sums with any per-vertex constant, so for the FAST
+// shaders (colour within 1/255, not bit-exact) one thread per assembled slot writes, once per draw,
+//     D = sum N_i,  U = sum N_i u_i,  V = sum N_i v_i,  Nrm = sum N_i n_i            (each as {value at the origin pixel, d/dx, d/dy})
+// relative to an origin pixel in the middle of the triangle's on-screen box; a fragment then needs five 16-byte loads and
+// (u, v) = (U, V) / D — the neighbours' values of ddx / ddy are one add away.  The normal is left undivided: `textured` only uses
+// its direction (SB:394-417).  Computed in double from the exact integer edge functions; the clip-space barycentric mapping of
+// clipped / swapped triangles (persp_weights) is folded into the per-vertex constants.
+__global__ void __launch_bounds__(256) planes_kernel(const __grid_constant__ DrawParams p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t slot;
+    if (i < p.ntri) {
+        const uint2 box = p.tileBox[i];
+        if ((box.x & 0xffffu) > (box.x >> 16)) return;          // nothing assembled in this slot
+        slot = (uint32_t)i;
+    } else {
+        const int k = i - p.ntri;
+        if (k >= p.ntri || (unsigned long long)k >= p.counters[4]) return;
+        slot = p.fan1List[k];
+    }
+    const int4* r = reinterpret_cast<const int4*>(p.rec + slot);
+    int X[3], Y[3];
+    float IW[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) { const int4 v = r[j]; X[j] = v.x; Y[j] = v.y; IW[j] = __int_as_float(v.w); }
+    const int4 w3 = r[3];
+    const double ar = (double)__int_as_float(w3.x);
+    const uint32_t flags = (uint32_t)w3.y;
+    const uint32_t prim = slot >= (uint32_t)p.ntri ? slot - (uint32_t)p.ntri : slot;
+    // clip-space barycentrics (u, v) of the record's three vertices: out = v0 u + v1 v + v2 (1 - u - v)
+    float bu[3], bv[3];
+    if (flags & IFR_FLAG_CLIPPED) {
+        const float* g = p.clipBary + (size_t)slot * 6;
+#pragma unroll
+        for (int j = 0; j < 3; j++) { bu[j] = g[2 * j]; bv[j] = g[2 * j + 1]; }
+    } else {
+        const bool sw = flags & IFR_FLAG_SWAPPED;
+        bu[0] = sw ? 1.0f : 0.0f; bv[0] = sw ? 0.0f : 1.0f;
+        bu[1] = 0.0f; bv[1] = 0.0f;
+        bu[2] = sw ? 0.0f : 1.0f; bv[2] = sw ? 1.0f : 0.0f;
+    }
+    // origin pixel: middle of the box clamped to the frame (keeps |fx|, |fy| of every shaded pixel small)
+    int x0 = min(X[0], min(X[1], X[2])) >> 8, x1 = max(X[0], max(X[1], X[2])) >> 8;
+    int y0 = min(Y[0], min(Y[1], Y[2])) >> 8, y1 = max(Y[0], max(Y[1], Y[2])) >> 8;
+    x0 = max(0, min(x0, p.W - 1)); x1 = max(0, min(x1, p.W - 1)); y0 = max(0, min(y0, p.H - 1)); y1 = max(0, min(y1, p.H - 1));
+    const int ox = (x0 + x1) >> 1, oy = (y0 + y1) >> 1;
+    const long long sx = (long long)ox * IFR_SUBPIX, sy = (long long)oy * IFR_SUBPIX;
+    double n0[3], nx[3], ny[3];
+#pragma unroll
+    for (int e = 0; e < 3; e++) {
+        const int a = (e + 1) % 3, b = (e + 2) % 3;
+        const long long dx = (long long)X[b] - X[a], dy = (long long)Y[b] - Y[a];
+        const long long E = dx * (sy - Y[a]) - dy * (sx - X[a]);
+        const double k = ar * (double)IW[e];
+        n0[e] = (double)E * k; nx[e] = -(double)(IFR_SUBPIX * dy) * k; ny[e] = (double)(IFR_SUBPIX * dx) * k;
+    }
+    // per-vertex constants of the record's vertices: normal (varying 0) and uv (varying 1)
+    int idx[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) idx[j] = p.ib[3 * (size_t)prim + j];
+    double c[3][5];
+#pragma unroll
+    for (int e = 0; e < 3; e++)
+#pragma unroll
+        for (int q = 0; q < 5; q++) c[e][q] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        if (k >= p.nvary) continue;
+        const uint8_t* vb = p.varyBase + p.varyOff[k];
+        const float4 v0 = *reinterpret_cast<const float4*>(vb + (size_t)idx[0] * p.varyStride),
+                     v1 = *reinterpret_cast<const float4*>(vb + (size_t)idx[1] * p.varyStride),
+                     v2 = *reinterpret_cast<const float4*>(vb + (size_t)idx[2] * p.varyStride);
+#pragma unroll
+        for (int e = 0; e < 3; e++) {
+            const double u = bu[e], v = bv[e], w = 1.0 - (u + v);
+            if (k == 0) {
+                c[e][2] = v0.x * u + v1.x * v + v2.x * w; c[e][3] = v0.y * u + v1.y * v + v2.y * w; c[e][4] = v0.z * u + v1.z * v + v2.z * w;
+            } else {
+                c[e][0] = v0.x * u + v1.x * v + v2.x * w; c[e][1] = v0.y * u + v1.y * v + v2.y * w;
+            }
+        }
+    }
+    float pl[18];        // D, U, V, Nx, Ny, Nz: {origin, d/dx, d/dy}
+    pl[0] = (float)(n0[0] + n0[1] + n0[2]); pl[1] = (float)(nx[0] + nx[1] + nx[2]); pl[2] = (float)(ny[0] + ny[1] + ny[2]);
+#pragma unroll
+    for (int q = 0; q < 5; q++) {
+        pl[3 + 3 * q] = (float)(n0[0] * c[0][q] + n0[1] * c[1][q] + n0[2] * c[2][q]);
+        pl[4 + 3 * q] = (float)(nx[0] * c[0][q] + nx[1] * c[1][q] + nx[2] * c[2][q]);
+        pl[5 + 3 * q] = (float)(ny[0] * c[0][q] + ny[1] * c[1][q] + ny[2] * c[2][q]);
+    }
+    float4* out = const_cast<float4*>(p.planes) + (size_t)slot * IFR_PLANE_QUADS;
+    out[0] = make_float4(pl[0], pl[1], pl[2], pl[3]);
+    out[1] = make_float4(pl[4], pl[5], pl[6], pl[7]);
+    out[2] = make_float4(pl[8], pl[9], pl[10], pl[11]);
+    out[3] = make_float4(pl[12], pl[13], pl[14], pl[15]);
+    out[4] = make_float4(pl[16], pl[17], (float)ox, (float)oy);
+}
+cudaError_t ifr_launch_planes(const DrawParams& p, cudaStream_t s) {
+    if (p.ntri <= 0 || !p.planes) return cudaSuccess;
+    planes_kernel<<<(2 * (long long)p.ntri + 255) / 256, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}

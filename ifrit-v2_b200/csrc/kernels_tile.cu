@@ -204,6 +204,8 @@ IFR_DECL_FS(100) IFR_DECL_FS(101) IFR_DECL_FS(102) IFR_DECL_FS(103)
 #undef IFR_DECL_FS
 
 cudaError_t ifr_launch_tiles(const DrawParams& p, int fsId, cudaStream_t s) {
+    // the FAST textured instantiations read attribute planes: the host must have run planes_kernel for this draw
+    if (IFR_PLANES && p.hwFilter && !p.planes && (fsId == IFRIT_FS_TEXTURED || fsId == IFRIT_FS_TEXTURED_LOD0)) return cudaErrorInvalidValue;
     switch (fsId) {
         case IFRIT_FS_VARYING0: return ifr_launch_fs_0(p, s);
         case IFRIT_FS_NORMAL_COLOR: return ifr_launch_fs_1(p, s);

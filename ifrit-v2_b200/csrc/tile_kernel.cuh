@@ -303,6 +303,43 @@ __device__ __forceinline__ void interp(const DrawParams& p, uint32_t slot, int p
     }
 }
 
+// ---- FAST textured shaders: varyings from the per-triangle attribute planes (kernels_geometry.cu: planes_kernel) --------------
+// v[0].xyz = the perspective numerator of the normal (direction only, `textured` normalises it), v[1].xy = uv; ddx / ddy of uv
+// from the planes evaluated one pixel towards the quad neighbour (same definition as interp: right - left, bottom - top of the
+// lane's 2x2 quad).  Five independent 16-byte loads, no triangle record, no indices, no vertex fetches.
+template <bool DERIV>
+__device__ __forceinline__ void interp_planes(const DrawParams& p, uint32_t slot, int px, int py, float4* out, float4* ddx, float4* ddy) {
+    const float4* q = p.planes + (size_t)slot * IFR_PLANE_QUADS;
+    const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3), q4 = __ldg(q + 4);
+    const float fx = (float)px - q4.z, fy = (float)py - q4.w;
+    const float D = fmaf(q0.z, fy, fmaf(q0.y, fx, q0.x));
+    const float U = fmaf(q1.y, fy, fmaf(q1.x, fx, q0.w));
+    const float V = fmaf(q2.x, fy, fmaf(q1.w, fx, q1.z));
+    out[0] = make_float4(fmaf(q2.w, fy, fmaf(q2.z, fx, q2.y)), fmaf(q3.z, fy, fmaf(q3.y, fx, q3.x)), fmaf(q4.y, fy, fmaf(q4.x, fx, q3.w)), 0.0f);
+    const float inv = rcp_fast(D);
+    const float u = U * inv, v = V * inv;
+    out[1] = make_float4(u, v, 0.0f, 0.0f);
+    if (DERIV) {
+        const float sh = (px & 1) ? -1.0f : 1.0f, sv = (py & 1) ? -1.0f : 1.0f;      // towards the quad neighbours
+        const float invH = rcp_fast(fmaf(sh, q0.y, D)), invV = rcp_fast(fmaf(sv, q0.z, D));
+        const float uH = fmaf(sh, q1.x, U) * invH, vH = fmaf(sh, q1.w, V) * invH;
+        const float uV = fmaf(sv, q1.y, U) * invV, vV = fmaf(sv, q2.x, V) * invV;
+        ddx[0] = make_float4(0, 0, 0, 0); ddy[0] = ddx[0];
+        ddx[1] = make_float4((uH - u) * sh, (vH - v) * sh, 0.0f, 0.0f);
+        ddy[1] = make_float4((uV - u) * sv, (vV - v) * sv, 0.0f, 0.0f);
+    }
+}
+// the depth a visibility key was made from (key_make): the shading pass of the plane shaders takes it from the winning key
+// instead of re-evaluating the depth plane from the triangle record — bit-identical, mono() is a bijection on canonical floats
+__device__ __forceinline__ float depth_from_word(const KeyMode& m, uint32_t w) {     // w = high word (ordered) / low word (others)
+    if (!m.ordered) return __uint_as_float(w);
+    const uint32_t t = w ^ m.xhi;
+    return __uint_as_float((t & 0x80000000u) ? (t ^ 0x80000000u) : ~t);
+}
+template <int FS> struct FsPlanes {
+    static constexpr bool value = IFR_PLANES && (FS == IFRIT_FS_TEXTURED_FAST || FS == IFRIT_FS_TEXTURED_LOD0_FAST || FS == IFRIT_FS_TEXTURED_FAST_RA);
+};
+
 // ------------------------------------------------------------------------------------------------
 #define IFR_CHUNK 256
 // Big-queue entries staged per bulk copy, double buffered: DrawParams::bigChunk = 32 or 64, chosen per draw by the host (capi.cu:
@@ -746,23 +783,32 @@ __global__ void __launch_bounds__(256, FsTraits<FS>::needsDerivs ? (S == 1 ? IFR
     // A pixel whose samples all hold the same key (S == 1, `uni`, or found equal below) needs no search: one FS
     // invocation with count S.  Otherwise the per-sample slots are re-read from the shared-memory keys by every search
     // (edge pixels only), so that nothing but the accumulators stays live across the fragment shader.
+    constexpr bool PLANES = FsPlanes<FS>::value;    // FAST textured shaders: varyings from attribute planes, depth from the key
     bool same = true;
     uint32_t slot0;
+    uint32_t dword0 = 0;      // PLANES: depth word of slot0's key
     int todo = 0;             // samples that still wait for their fragment
     if (S == 1 || uni) {
         const unsigned long long k = (S == 1 && nSmall != 0) ? keys[tid] : best;
         slot0 = key_slot(km, k);
+        if (PLANES) dword0 = km.ordered ? (uint32_t)(k >> 32) : (uint32_t)k;
         todo = slot0 != IFR_SLOT_NONE ? S : 0;
     } else {
         // the pixel's keys are final: replace each by its slot (low word, in place) so that the searches below are
-        // 32-bit loads and compares
+        // 32-bit loads and compares; PLANES: the other word keeps (ordered compare ops) or receives the key's depth word
         uint32_t* kw = reinterpret_cast<uint32_t*>(keys);
-        slot0 = key_slot(km, keys[tid]);
+        {
+            const unsigned long long k = keys[tid];
+            slot0 = key_slot(km, k);
+            if (PLANES) { dword0 = km.ordered ? (uint32_t)(k >> 32) : (uint32_t)k; if (!km.ordered) kw[2 * tid + 1] = dword0; }
+        }
         kw[2 * tid] = slot0;
         todo = slot0 != IFR_SLOT_NONE;
 #pragma unroll
         for (int s = 1; s < S; s++) {
-            const uint32_t v = key_slot(km, keys[s * IFR_TILE_PIX + tid]);
+            const unsigned long long k = keys[s * IFR_TILE_PIX + tid];
+            const uint32_t v = key_slot(km, k);
+            if (PLANES && !km.ordered) kw[2 * (s * IFR_TILE_PIX + tid) + 1] = (uint32_t)k;
             kw[2 * (s * IFR_TILE_PIX + tid)] = v;
             same = same && v == slot0;
             todo += v != IFR_SLOT_NONE;
@@ -788,6 +834,7 @@ __global__ void __launch_bounds__(256, FsTraits<FS>::needsDerivs ? (S == 1 ? IFR
     uint32_t lastp1 = 0;      // last shaded slot + 1
     while (todo > 0) {
         uint32_t cur = slot0;
+        uint32_t dword = dword0;
         int cnt = S;
         if (S > 1 && !same) {
             // smallest slot above `last` and its sample count: slots are compared as (slot - (last + 1)) mod 2^32, which
@@ -797,14 +844,22 @@ __global__ void __launch_bounds__(256, FsTraits<FS>::needsDerivs ? (S == 1 ? IFR
 #pragma unroll
             for (int s = 0; s < S; s++) { c[s] = kw[2 * (s * IFR_TILE_PIX + tid)] - lastp1; m = min(m, c[s]); }
             cnt = 0;
+            int first = 0;
 #pragma unroll
-            for (int s = 0; s < S; s++) cnt += c[s] == m;
+            for (int s = S - 1; s >= 0; s--) { cnt += c[s] == m; if (PLANES) first = c[s] == m ? s : first; }
             cur = m + lastp1;
+            if (PLANES) dword = kw[2 * (first * IFR_TILE_PIX + tid) + 1];     // all samples of one slot carry the pixel's depth
         }
         float4 v[NV > 0 ? NV : 1], ddx[NV > 0 ? NV : 1], ddy[NV > 0 ? NV : 1];
         float depth = 0.0f;
         int prim = 0, fan = 0;
-        interp<NV, FsTraits<FS>::needsDerivs, FS == IFRIT_FS_TEXTURED_FAST || FS == IFRIT_FS_TEXTURED_LOD0_FAST || FS == IFRIT_FS_TEXTURED_FAST_RA>(p, cur, px, py, v, ddx, ddy, depth, prim, fan);
+        if (PLANES) {
+            interp_planes<FsTraits<FS>::needsDerivs>(p, cur, px, py, v, ddx, ddy);
+            depth = depth_from_word(km, dword);
+            fan = cur >= (uint32_t)p.ntri;
+            prim = fan ? (int)(cur - (uint32_t)p.ntri) : (int)cur;
+        } else
+            interp<NV, FsTraits<FS>::needsDerivs, FS == IFRIT_FS_TEXTURED_FAST || FS == IFRIT_FS_TEXTURED_LOD0_FAST || FS == IFRIT_FS_TEXTURED_FAST_RA>(p, cur, px, py, v, ddx, ddy, depth, prim, fan);
         const float4 c = run_fs<FS>(p, v, ddx, ddy, prim, fan);
         const float fc = (float)cnt;
         acc.x = fmaf(fc, c.x, acc.x); acc.y = fmaf(fc, c.y, acc.y);

@@ -442,6 +442,34 @@ def test_textured_mesh(r, aniso, addr, hw):
         assert (o["color"].view(np.uint32) == g["color"].view(np.uint32)).mean() > 0.99
 
 
+@pytest.mark.parametrize("msaa", [1, 8])
+@pytest.mark.parametrize("depth_func", ["LESS", "GEQUAL", "ALWAYS", "EQUAL"])
+def test_fast_shader_attribute_planes(r, depth_func, msaa):
+    """The FAST textured shaders take their varyings from per-triangle attribute planes (kernels_geometry.cu: planes_kernel)
+    and the fragment depth from the winning visibility key: a camera INSIDE the sphere (near-plane clipped fans, second
+    fan slots, no cull / front cull = swapped winding), ordered and unordered compare ops, 1x and 8x — ids and depth
+    bit-exact, colour within 1/255 on >= 99.9 % like every FAST frame."""
+    W, H = 400, 232
+    vb, idx = scenes.mesh_sphere(n=40)
+    import math
+    proj = scenes.perspective(60.0 * math.pi / 180.0, W / H, 0.1, 100.0)
+    view = scenes.look_at((0.0, 0.0, 1.0), (0.5, 0.3, 0.9), (0, 1, 0))              # eye ON the surface: 5 clipped triangles, 2 second fans
+    u = scenes.uniform_block((proj.astype(np.float64) @ view.astype(np.float64)).astype(np.float32))
+    tex = scenes.texture_checker(size=256, seed=5)
+    chain = O.texture_chain(tex, 8)
+    samp = dict(filterMode=1, anisotropyEnable=True, maxAnisotropy=16.0)
+    func = getattr(O, "CMP_" + depth_func)
+    for cull in (0, 1):
+        kw = dict(cull=cull, msaa=msaa, depth_func=func, mip_levels=8, sampler=samp,
+                  clear_depth=0.0 if depth_func == "GEQUAL" else 1.0)
+        o = oracle_draw(W, H, vb, idx, 1, O.FS_TEXTURED, 2, u, texture_chain=chain, tex_dims=(256, 256), **kw)
+        g = gpu_draw(r, W, H, vb, idx, 1, O.FS_TEXTURED, 2, u, texture=tex, hw_filter=True, **kw)
+        compare(o, g)
+        if depth_func != "EQUAL":
+            assert (g["prim_id"] >= 0).mean() > 0.3
+        assert g["fragments_shaded"] == o["frags"]
+
+
 def test_textured_msaa8_nearest_and_lod0(r):
     W, H = 256, 144
     vb, idx, u = _mesh_case(W, H)
