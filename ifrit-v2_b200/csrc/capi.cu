@@ -125,6 +125,9 @@ struct iftrcuRenderer {
     uint32_t epoch = 0;
     bool pipelining = true;
     cudaStream_t geomStream = nullptr;
+    // pipelined draws read the statistics / overflow counters back on a side stream, so that the 16 KB copy does not sit between two
+    // tile kernels on the draw stream; evStat[set]: the copy of that scratch set's counters is done (its next memset waits for it)
+    cudaStream_t statStream = nullptr; cudaEvent_t evStat[2] = {nullptr, nullptr}; bool statPending[2] = {false, false};
     cudaEvent_t evGeomDone[2] = {nullptr, nullptr}, evTileDone[2] = {nullptr, nullptr}, evInputs = nullptr;
     bool tilePending[2] = {false, false}, inputsDirty = false;
     unsigned long long* hCounters = nullptr;   // pinned, 8 entries
@@ -568,6 +571,8 @@ static int ensure_pipeline(iftrcuRenderer* r) {
     int prLow = 0, prHigh = 0;
     CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prLow, &prHigh));
     CUDA_TRY(cudaStreamCreateWithPriority(&r->geomStream, cudaStreamNonBlocking, prHigh));
+    CUDA_TRY(cudaStreamCreateWithFlags(&r->statStream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) CUDA_TRY(cudaEventCreateWithFlags(&r->evStat[k], cudaEventDisableTiming));
     for (int k = 0; k < 2; k++) {
         CUDA_TRY(cudaEventCreateWithFlags(&r->evGeomDone[k], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&r->evTileDone[k], cudaEventDisableTiming));
@@ -610,6 +615,7 @@ static int issue_draw(iftrcuRenderer* r, bool forceCheck, bool sameSet = false) 
     iftrcuRenderer::Scratch& sc = r->scr[r->set];
     if (pipe) {
         if (r->tilePending[r->set]) { CUDA_TRY(cudaStreamWaitEvent(g, r->evTileDone[r->set], 0)); r->tilePending[r->set] = false; }
+        if (r->statPending[r->set]) { CUDA_TRY(cudaStreamWaitEvent(g, r->evStat[r->set], 0)); r->statPending[r->set] = false; }
         if (r->inputsDirty) { CUDA_TRY(cudaStreamWaitEvent(g, r->evInputs, 0)); r->inputsDirty = false; }
     }
     CUDA_TRY(cudaMemsetAsync(sc.tileCount.p, 0, 2 * ntiles * 4, g));
@@ -670,7 +676,13 @@ static int issue_draw(iftrcuRenderer* r, bool forceCheck, bool sameSet = false) 
     if (ev) { CUDA_TRY(cudaEventRecord(ev[6], s)); r->profDraws++; }
     if (pipe) { CUDA_TRY(cudaEventRecord(r->evTileDone[r->set], s)); r->tilePending[r->set] = true; }
     r->stats.kernel_launches += 3;
-    CUDA_TRY(cudaMemcpyAsync(r->hCounters, r->scr[r->set].counters.p, IFR_COUNTER_BYTES, cudaMemcpyDeviceToHost, s));
+    if (pipe && r->statStream) {
+        CUDA_TRY(cudaStreamWaitEvent(r->statStream, r->evTileDone[r->set], 0));
+        CUDA_TRY(cudaMemcpyAsync(r->hCounters, r->scr[r->set].counters.p, IFR_COUNTER_BYTES, cudaMemcpyDeviceToHost, r->statStream));
+        CUDA_TRY(cudaEventRecord(r->evStat[r->set], r->statStream));
+        r->statPending[r->set] = true;
+    } else
+        CUDA_TRY(cudaMemcpyAsync(r->hCounters, r->scr[r->set].counters.p, IFR_COUNTER_BYTES, cudaMemcpyDeviceToHost, s));
     r->lastDrawCleared = r->pendingClear;
     r->pendingClear = false;
     r->haveDraw = true;
@@ -711,6 +723,7 @@ static int issue_draw_prims(iftrcuRenderer* r) {
     int rc = flush_clear(r);
     if (rc) return rc;
     if (r->geomStream) CUDA_TRY(cudaStreamSynchronize(r->geomStream));
+    if (r->statStream) CUDA_TRY(cudaStreamSynchronize(r->statStream));   // an earlier draw's counters must not land after this draw's
     CUDA_TRY(r->primKeys.ensure((size_t)r->W * r->H * 8));
     CUDA_TRY(r->primSeg.ensure(std::max<size_t>(1, (size_t)r->icount) * 2 * sizeof(float4)));
     CUDA_TRY(r->scr[0].counters.ensure(IFR_COUNTER_BYTES));
@@ -746,6 +759,7 @@ static int flush_clear(iftrcuRenderer* r) {
 static int sync_and_check(iftrcuRenderer* r) {
     if (r->geomStream) CUDA_TRY(cudaStreamSynchronize(r->geomStream));
     CUDA_TRY(cudaStreamSynchronize(r->stream));
+    if (r->statStream) CUDA_TRY(cudaStreamSynchronize(r->statStream));
     if (r->doubleBuffer) CUDA_TRY(cudaStreamSynchronize(r->copyStream));
     if (r->haveDraw && (r->hCounters[3] || r->hCounters[12])) {
         // the queue sized from an earlier frame was too small: grow it and re-issue the draw
@@ -758,6 +772,7 @@ static int sync_and_check(iftrcuRenderer* r) {
         int rc = issue_draw(r, true, true);
         if (rc) return rc;
         CUDA_TRY(cudaStreamSynchronize(r->stream));
+        if (r->statStream) CUDA_TRY(cudaStreamSynchronize(r->statStream));
         if (r->doubleBuffer) CUDA_TRY(cudaStreamSynchronize(r->copyStream));
     }
     if (r->haveDraw && r->hCounters[6]) { r->hCounters[6] = 0; return r->fail(IFRIT_ERR_UNSUPPORTED, "drawElements", "alpha blending: a tile holds more than 4096 triangles"); }
@@ -830,6 +845,8 @@ int iftrcuDestroyInstance(iftrcuRenderer* h) {
     }
     if (r->evInputs) cudaEventDestroy(r->evInputs);
     if (r->geomStream) { cudaStreamSynchronize(r->geomStream); cudaStreamDestroy(r->geomStream); }
+    if (r->statStream) { cudaStreamSynchronize(r->statStream); cudaStreamDestroy(r->statStream); }
+    for (int k = 0; k < 2; k++) if (r->evStat[k]) cudaEventDestroy(r->evStat[k]);
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < IFR_MAX_TEX; i++) { destroy_tex_objects(r, i); r->texMem[i].release(); }
     for (int i = 0; i < IFR_MAX_BUF; i++) r->bufMem[i].release();
@@ -1370,6 +1387,7 @@ int iftrcuSetFramePipelining(iftrcuRenderer* h, int enable) {
     int rc = sync_and_check(r); if (rc) return rc;
     r->pipelining = enable != 0;
     r->tilePending[0] = r->tilePending[1] = false;
+    r->statPending[0] = r->statPending[1] = false;
     return IFRIT_OK;
 }
 int iftrcuSetVertexStageFused(iftrcuRenderer* h, int enable) { R_CHECK(h); r->fusedVS = enable != 0; return IFRIT_OK; }
