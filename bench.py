@@ -209,6 +209,11 @@ def run_ours(args, cfg_name, do_e2e=True, fast_sampler=True):
         rr.setSamplerHardwareFilter(fast_sampler)   # library default: the oracle's arithmetic (software fp32 lerps); the bench opts in to FAST (texture unit)
 
     configure(r)
+    if getattr(args, "emulate_rank", None) and world == 1:
+        # analysis aid (1 GPU): render only the tiles rank R of N would own — the per-rank kernel times of an N-GPU run without
+        # the exchange; the line is NOT a bench value (value / roofline refer to the whole frame)
+        er, en = (int(x) for x in args.emulate_rank.split("/"))
+        r.setTilePartition(er, en)
     sf = MG.SortFirstRenderer(r, dist, dev, mode=mg_mode, clears_every_frame=not getattr(args, 'no_preclear', False)) if world > 1 else None   # every bench frame is clear() + drawElements()
 
     # N >= 4: draws of a million triangles and more split the triangle setup over the ranks (one all-gather of owner masks per
@@ -219,8 +224,22 @@ def run_ours(args, cfg_name, do_e2e=True, fast_sampler=True):
     if getattr(args, "force_distributed_setup", False) and sf and world <= 8:
         dsetup = True
 
+    emu_mask = None
+    if getattr(args, "emulate_rank", None) and world == 1 and getattr(args, "force_distributed_setup", False):
+        # emulated distributed setup: the whole owner-mask array is classified once up front (stands for the all-gathered slices
+        # of the other ranks); every frame re-classifies this rank's 1 / N slice, as distribute_setup would
+        er, en = (int(x) for x in args.emulate_rank.split("/"))
+        chunk = ((ntri + en - 1) // en + 15) // 16 * 16
+        emu_mask = torch.zeros(chunk * en, dtype=torch.uint8, device=dev)
+        r.classifyTriangles(0, ntri, emu_mask.data_ptr())
+        r.synchronize()
+        r.setTriangleOwnerMask(emu_mask.data_ptr())
+        emu_first, emu_count = er * chunk, max(0, min(ntri, er * chunk + chunk) - er * chunk)
+
     def step():
         r.clear()
+        if emu_mask is not None:
+            r.classifyTriangles(emu_first, emu_count, emu_mask.data_ptr())
         if dsetup:
             sf.distribute_setup(ntri)
         r.drawElements()
@@ -491,6 +510,7 @@ def main():
     ap.add_argument("--no-exact-sampler", "--no-fast-sampler", dest="no_exact_sampler", action="store_true",
                     help="skip the extra run with the library's default (exact) sampler")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--emulate-rank", default=None, help="analysis aid, 1 GPU: 'R/N' renders only the tiles rank R of N owns (per-rank kernel times, no exchange)")
     ap.add_argument("--no-distributed-setup", action="store_true", help="A/B (N > 1): every rank assembles every triangle")
     ap.add_argument("--force-distributed-setup", action="store_true", help="A/B (N > 1): split the triangle setup whatever the rank / triangle count")
     ap.add_argument("--no-preclear", action="store_true", help="A/B (N > 1, peer mode): plain frame release, every rank sends all of its tiles")

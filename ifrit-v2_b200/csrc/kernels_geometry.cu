@@ -240,7 +240,9 @@ __device__ __forceinline__ bool tile_may_cover(const EdgeSet& e, int tx, int ty)
 // pass: small class -> append the slot; big class -> compute the per-tile raster setup once, here,
 // and append it, so that the tile kernel has no setup phase (and no barrier) for big triangles.
 __device__ __forceinline__ bool tile_owned(const DrawParams& p, int tx, int ty) {
-    return p.world <= 1 || ifr_tile_owner(tx, ty, p.world) == p.rank;
+    if (p.world <= 1) return true;
+    const int v = tx / (IFR_SUPER / IFR_TILE) + 3 * (ty / (IFR_SUPER / IFR_TILE));      // ifr_tile_owner without the runtime division
+    return ((p.world & (p.world - 1)) == 0 ? (v & (p.world - 1)) : v % p.world) == p.rank;
 }
 // bit r set <=> rank r owns a tile of the box (ownership interleaves 64-px super-tiles, common.cuh: ifr_tile_owner; boxes of more
 // than 16 super-tiles go to everyone) — a superset of the ranks finish_triangle keeps the triangle on
@@ -325,19 +327,26 @@ __device__ __forceinline__ void bin_triangle(const DrawParams& p, bool has, uint
             const unsigned peers = agg_group(act, q, lane, rank, leader);
             if (act && lane == leader) atomicAdd(&p.tileCount[q], (uint32_t)__popc(peers));
         }
-    } else if (nt >= 1 && nt <= IFR_BIG_TILES && sub < nt) {
+    } else if (nt >= 1 && nt <= IFR_BIG_TILES && sub < nt && (FILL || !(nx > 1 && ny > 1))) {
         RecRegs rr;
         if (FILL && big) load_rec(p, slot, rr);
         const bool test = nx > 1 && ny > 1;     // a one-tile-wide box is covered in every tile of it
+        int tx = tx0 + sub % nx, ty = ty0 + sub / nx;
         for (int i = sub; i < nt; i += G) {
-            const int tx = tx0 + i % nx, ty = ty0 + i / nx;
-            if (test && !tile_may_cover(e, tx, ty)) continue;
-            if (!tile_owned(p, tx, ty)) continue;
-            if (!FILL) atomicAdd(&p.tileCount[big * p.tilesX * p.tilesY + ty * p.tilesX + tx], 1u);
-            else emit_one(p, rr, slot, big, tx, ty, reserve_one(p, big, tx, ty));
+            // ownership first: under sort-first most tiles of a box belong to other ranks, and the exact test is the expensive part
+            if (tile_owned(p, tx, ty) && !(test && !tile_may_cover(e, tx, ty))) {
+                if (!FILL) atomicAdd(&p.tileCount[big * p.tilesX * p.tilesY + ty * p.tilesX + tx], 1u);
+                else emit_one(p, rr, slot, big, tx, ty, reserve_one(p, big, tx, ty));
+            }
+            tx += G;
+            while (tx > tx1) { tx -= nx; ty++; }
         }
     }
-    unsigned wideBox = __ballot_sync(0xffffffffu, nt > IFR_BIG_TILES && sub == 0);
+    // Warp-cooperative binning: one box at a time, a tile per lane.  Boxes of more than IFR_BIG_TILES tiles in both passes; in
+    // the COUNT pass also every box that needs the exact test (two or more tiles in both directions) — there each thread holds
+    // its own triangle, and a per-thread loop makes the whole warp wait for its largest box: on c5 (10 % of the triangles
+    // span 4 - 16 tiles, three of them in an average warp) that loop was most of the 3 ms of the setup pass.
+    unsigned wideBox = __ballot_sync(0xffffffffu, sub == 0 && (nt > IFR_BIG_TILES || (!FILL && nt >= 1 && nx > 1 && ny > 1)));
     const int lane = threadIdx.x & 31;
     while (wideBox) {
         const int src = __ffs(wideBox) - 1;
@@ -346,20 +355,22 @@ __device__ __forceinline__ void bin_triangle(const DrawParams& p, bool has, uint
         const int sbig = __shfl_sync(0xffffffffu, big, src);
         const int bx0 = __shfl_sync(0xffffffffu, tx0, src), bx1 = __shfl_sync(0xffffffffu, tx1, src);
         const int by0 = __shfl_sync(0xffffffffu, ty0, src), by1 = __shfl_sync(0xffffffffu, ty1, src);
-        EdgeSet be;
+        EdgeSet be;      // Xa / Ya are the vertices in rotated order: the deltas follow from them
 #pragma unroll
-        for (int i = 0; i < 3; i++) {
-            be.dX[i] = __shfl_sync(0xffffffffu, e.dX[i], src); be.dY[i] = __shfl_sync(0xffffffffu, e.dY[i], src);
-            be.Xa[i] = __shfl_sync(0xffffffffu, e.Xa[i], src); be.Ya[i] = __shfl_sync(0xffffffffu, e.Ya[i], src);
-        }
+        for (int i = 0; i < 3; i++) { be.Xa[i] = __shfl_sync(0xffffffffu, e.Xa[i], src); be.Ya[i] = __shfl_sync(0xffffffffu, e.Ya[i], src); }
+#pragma unroll
+        for (int i = 0; i < 3; i++) { be.dX[i] = be.Xa[(i + 1) % 3] - be.Xa[i]; be.dY[i] = be.Ya[(i + 1) % 3] - be.Ya[i]; }
         RecRegs wr;
         if (FILL && sbig) load_rec(p, s, wr);
         const int bnx = bx1 - bx0 + 1, total = bnx * (by1 - by0 + 1);
+        int tx = bx0 + lane % bnx, ty = by0 + lane / bnx;
         for (int i = lane; i < total; i += 32) {
-            const int tx = bx0 + i % bnx, ty = by0 + i / bnx;
-            if (!tile_may_cover(be, tx, ty) || !tile_owned(p, tx, ty)) continue;
-            if (!FILL) atomicAdd(&p.tileCount[sbig * p.tilesX * p.tilesY + ty * p.tilesX + tx], 1u);
-            else emit_one(p, wr, s, sbig, tx, ty, reserve_one(p, sbig, tx, ty));
+            if (tile_owned(p, tx, ty) && tile_may_cover(be, tx, ty)) {
+                if (!FILL) atomicAdd(&p.tileCount[sbig * p.tilesX * p.tilesY + ty * p.tilesX + tx], 1u);
+                else emit_one(p, wr, s, sbig, tx, ty, reserve_one(p, sbig, tx, ty));
+            }
+            tx += 32;
+            while (tx > bx1) { tx -= bnx; ty++; }
         }
     }
 }
