@@ -321,6 +321,7 @@ def run_ours(args, cfg_name, do_e2e=True, fast_sampler=True):
 
     # ---- N > 1: the gathered frame on rank 0 must equal the single-GPU frame bit for bit --------------------------
     frame_same = None
+    ref_frame = None
     if world > 1:
         r.clear()
         r.drawElements()
@@ -337,7 +338,8 @@ def run_ours(args, cfg_name, do_e2e=True, fast_sampler=True):
             one.clear()
             one.drawElements()
             one.synchronize()
-            frame_same = bool(np.array_equal(got.view(np.uint32), one.readColor().view(np.uint32)))
+            ref_frame = one.readColor()
+            frame_same = bool(np.array_equal(got.view(np.uint32), ref_frame.view(np.uint32)))
             one.close()
             del got
         dist.barrier()
@@ -390,6 +392,42 @@ def run_ours(args, cfg_name, do_e2e=True, fast_sampler=True):
             return max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
 
         e2e_ms = time_e2e()
+        # N > 1, distributed read-back (the e2e headline when it runs): every rank renders its tiles into a LOCAL framebuffer and stores
+        # them straight into ONE host image mapped by all ranks (multigpu.SharedHostImage, iftrcuCopyOwnedTilesToHost) — no NVLink
+        # gather, N PCIe links instead of rank 0's one.  The gathered variant above stays in the line as e2e_gather_rank0.
+        e2e_gather_ms = e2e_dist_same = None
+        if world > 1 and not getattr(args, "no_distributed_readback", False):
+            ok = torch.ones(1, dtype=torch.int32, device=dev)
+            shared = None
+            try:
+                shared = MG.SharedHostImage(W, H, dist)
+            except Exception as ex:      # collective inside: every rank fails or none does
+                print(f"[bench] rank {rank}: shared host image unavailable: {ex}", file=sys.stderr)
+            if shared is not None:
+                try:
+                    r.bindFrameBuffer(None, None, W, H)          # local device framebuffer on every rank; the tile partition stays
+                    r.clear(); r.drawElements(); r.copyOwnedTilesToHost(shared.ptr); r.synchronize()
+                except Exception as ex:
+                    print(f"[bench] rank {rank}: distributed read-back unavailable: {ex}", file=sys.stderr)
+                    ok.zero_()
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                if int(ok.item()):
+                    def e2e_step():      # noqa: F811 — the step time_e2e() runs from here on
+                        r.bindVertexBuffer(hvb, hvb.shape[0], hvb.shape[1] // 4)        # H2D (pinned, async), every rank
+                        r.bindIndexBuffer(hib, hib.shape[0])
+                        r.clear()
+                        r.drawElements()
+                        r.copyOwnedTilesToHost(shared.ptr)                             # D2H: this rank's tiles, its own PCIe link
+                        torch.cuda.current_stream().synchronize()
+                    e2e_gather_ms = e2e_ms
+                    if rank == 0:
+                        shared.array[...] = -7.0
+                    barrier()
+                    e2e_ms = time_e2e()
+                    if rank == 0 and ref_frame is not None:
+                        e2e_dist_same = bool(np.array_equal(shared.array.view(np.uint32), ref_frame.view(np.uint32)))
+                    readback = ("distributed: every rank stores the tiles it owns from its local framebuffer straight into one shared pinned "
+                                "host image (iftrcuCopyOwnedTilesToHost), N PCIe links, no NVLink gather; a step ends when every rank's stream has drained")
         # the same call sequence with the packed RGBA8 presentation image bound: the per-draw
         # copy-back carries 4 bytes per pixel instead of 16.  Reported next to `e2e`, never instead of it.
         e2e8_ms = None
@@ -399,9 +437,10 @@ def run_ours(args, cfg_name, do_e2e=True, fast_sampler=True):
             e2e8_ms = time_e2e() / e2e_steps
             r.bindPresentBuffer(None, 0)
         if world > 1:
-            t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+            t = torch.tensor([e2e_ms, e2e_gather_ms or 0.0], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_ms = float(t.item())
+            e2e_ms = float(t[0].item())
+            e2e_gather_ms = float(t[1].item()) / e2e_steps if e2e_gather_ms else None
         e2e_ms /= e2e_steps
         h2d_bytes = int(hvb.numel() * 4 + hib.numel() * 4)
         del hvb, hib, hcol
@@ -454,6 +493,10 @@ def run_ours(args, cfg_name, do_e2e=True, fast_sampler=True):
                           "readback": readback}
         if world > 1:
             out["frame_hash_equals_1gpu"] = frame_same
+            if e2e_ms and e2e_gather_ms:
+                out["e2e"]["frame_equals_1gpu"] = e2e_dist_same
+                out["e2e_gather_rank0"] = {"value": ntri / (e2e_gather_ms * 1e-3) / 1e6, "unit": "Mtris/s", "ms_per_step": e2e_gather_ms,
+                                           "note": "same steps with the frame gathered on rank 0 over NVLink and copied back over rank 0's PCIe link"}
         if e2e8_ms:
             out["e2e_rgba8"] = {"value": ntri / (e2e8_ms * 1e-3) / 1e6, "unit": "Mtris/s", "ms_per_step": e2e8_ms,
                                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(W * H * 4),
@@ -513,6 +556,7 @@ def main():
     ap.add_argument("--emulate-rank", default=None, help="analysis aid, 1 GPU: 'R/N' renders only the tiles rank R of N owns (per-rank kernel times, no exchange)")
     ap.add_argument("--no-distributed-setup", action="store_true", help="A/B (N > 1): every rank assembles every triangle")
     ap.add_argument("--force-distributed-setup", action="store_true", help="A/B (N > 1): split the triangle setup whatever the rank / triangle count")
+    ap.add_argument("--no-distributed-readback", action="store_true", help="A/B (N > 1): e2e reads the frame back through rank 0 only")
     ap.add_argument("--no-preclear", action="store_true", help="A/B (N > 1, peer mode): plain frame release, every rank sends all of its tiles")
     ap.add_argument("--tile-chunk", type=int, default=0, choices=[0, 32, 64], help="A/B: big-queue entries per staged chunk of the tile kernel (0 = automatic)")
     ap.add_argument("--no-grid-hint", action="store_true", help="A/B: tile kernel grid of one CTA per tile instead of the measured CTA count")

@@ -68,6 +68,7 @@ struct iftrcuRenderer {
     bool framePending[2] = {false, false}, copyPending[2] = {false, false};
     float* hColor = nullptr; float* hDepth = nullptr;
     void* registeredHost = nullptr;
+    void* registeredOwned = nullptr;      // host image pinned + mapped by iftrcuCopyOwnedTilesToHost
     void* peerColor = nullptr; void* peerDepth = nullptr;   // opened CUDA IPC mappings (peer framebuffer)
     bool debugIds = false;
     uint32_t* frameFlags = nullptr;       // frame-flag block of the bound framebuffer (own or peer), see kernels_image.cu
@@ -827,6 +828,7 @@ int iftrcuDestroyInstance(iftrcuRenderer* h) {
     cudaStreamSynchronize(r->stream);
     if (r->registeredHost) cudaHostUnregister(r->registeredHost);
     if (r->registeredPresent) cudaHostUnregister(r->registeredPresent);
+    if (r->registeredOwned) cudaHostUnregister(r->registeredOwned);
     for (auto& sh : r->rtc) for (int i = 0; i < 5; i++) if (sh.lib[i]) cudaLibraryUnload(sh.lib[i]);
     for (auto& st : r->meshShaders) if (st.lib) cudaLibraryUnload(st.lib);
     for (auto& st : r->taskShaders) if (st.lib) cudaLibraryUnload(st.lib);
@@ -1728,6 +1730,30 @@ int iftrcuFrameReleaseCleared(iftrcuRenderer* h, uint32_t frameId) {
 int iftrcuFrameFenceCleared(iftrcuRenderer* h, uint32_t frameId) {
     R_CHECK(h);
     r->fenceFrame = frameId; r->fencePending = true; r->skipArmed = true;
+    return IFRIT_OK;
+}
+
+/* Sort-first distributed read-back: the tiles this rank owns (iftrcuSetTilePartition) go from the bound DEVICE framebuffer straight into
+ * the full-frame host image (W*H RGBA32F, row-major — the layout iftrcuBindFrameBuffer's host image has), in stream order.  The image must
+ * be visible to every rank (one shared-memory mapping per process); a range that is not page-locked yet is registered (pinned + mapped)
+ * here, once.  The ranks' stores are disjoint, so no ordering between them is needed: the frame is complete when every rank's stream
+ * has passed this call.  With one rank it is a whole-frame copy. */
+int iftrcuCopyOwnedTilesToHost(iftrcuRenderer* h, void* hostImage) {
+    R_CHECK(h);
+    if (!hostImage || !r->dColor) return r->fail(IFRIT_ERR_INVALID, "CopyOwnedTilesToHost", "bad argument");
+    if (r->peerColor) return r->fail(IFRIT_ERR_STATE, "CopyOwnedTilesToHost", "the bound framebuffer lives on another GPU: bind a local one");
+    int rc = flush_clear(r); if (rc) return rc;
+    void* mapped = nullptr;
+    if (cudaHostGetDevicePointer(&mapped, hostImage, 0) != cudaSuccess) {
+        cudaGetLastError();
+        if (r->registeredOwned) { cudaHostUnregister(r->registeredOwned); r->registeredOwned = nullptr; }
+        CUDA_TRY(cudaHostRegister(hostImage, (size_t)r->W * r->H * 16, cudaHostRegisterMapped | cudaHostRegisterPortable));
+        r->registeredOwned = hostImage;
+        CUDA_TRY(cudaHostGetDevicePointer(&mapped, hostImage, 0));
+    }
+    const float4* src = (r->doubleBuffer && r->lastColor) ? r->lastColor : r->dColor;
+    CUDA_TRY(ifr_launch_owned_to_host(src, (float4*)mapped, r->W, r->H, r->rank, r->world, r->stream));
+    r->stats.kernel_launches += 1;
     return IFRIT_OK;
 }
 

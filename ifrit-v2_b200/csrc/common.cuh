@@ -182,6 +182,7 @@ cudaError_t ifr_launch_blit(const TexDesc& src, int srcLevel, int srcLayer, cons
                             int dstLayer, const uint32_t srcRect[4], const uint32_t dstRect[4], int filter,
                             cudaStream_t s);
 cudaError_t ifr_launch_pack(const DrawParams& p, float* dst, int rank, int world, int unpack, cudaStream_t s);
+cudaError_t ifr_launch_owned_to_host(const float4* src, float4* hostMapped, int W, int H, int rank, int world, cudaStream_t s);
 cudaError_t ifr_launch_flag_store(uint32_t* word, uint32_t value, cudaStream_t s);
 cudaError_t ifr_launch_flag_wait(const uint32_t* words, int n, uint32_t value, uint32_t* timedOut, cudaStream_t s);
 #define IFR_FLAG_WORDS 128    // frame-flag block at the tail of the depth allocation: [0..63] per-rank, [64] owner's release

@@ -120,6 +120,29 @@ cudaError_t ifr_launch_pack(const DrawParams& p, float* dst, int rank, int world
     return cudaGetLastError();
 }
 
+// Sort-first distributed read-back (no reference counterpart; the single-GPU reference copies the whole frame back over one PCIe
+// link, CU:3899-3909).  Every rank stores the super-tiles it owns from its LOCAL framebuffer straight into the full-frame, row-major
+// host image through mapped pinned memory: the frame never crosses NVLink, and N ranks drive N PCIe links at once.  A CTA takes one
+// owned super-tile; a warp writes 512 contiguous bytes per instruction (full PCIe write bursts).
+__global__ void __launch_bounds__(256) owned_to_host_kernel(const float4* __restrict__ src, float4* __restrict__ host, int W, int H,
+                                                            int rank, int world) {
+    const int sx = blockIdx.x, sy = blockIdx.y;
+    if ((sx + 3 * sy) % world != rank) return;
+    const int x = sx * IFR_SUPER + (threadIdx.x & 63);
+    if (x >= W) return;
+#pragma unroll 4
+    for (int r = threadIdx.x >> 6; r < IFR_SUPER; r += 4) {
+        const int y = sy * IFR_SUPER + r;
+        if (y >= H) break;
+        host[(size_t)y * W + x] = __ldcs(src + (size_t)y * W + x);
+    }
+}
+cudaError_t ifr_launch_owned_to_host(const float4* src, float4* hostMapped, int W, int H, int rank, int world, cudaStream_t s) {
+    const dim3 grid((W + IFR_SUPER - 1) / IFR_SUPER, (H + IFR_SUPER - 1) / IFR_SUPER);
+    owned_to_host_kernel<<<grid, 256, 0, s>>>(src, hostMapped, W, H, rank, world);
+    return cudaGetLastError();
+}
+
 // ---- sort-first frame flags (peer-memory mode) ---------------------------------------------------------
 // A block of 32-bit words at the tail of the framebuffer owner's depth allocation, mapped into every rank by
 // the same CUDA IPC handle as the framebuffer: word r = last frame whose tiles rank r has stored, word 64 = last

@@ -79,6 +79,44 @@ def gather_frame(packed_local, width, height, dist, dst=0):
     return outs
 
 
+def copy_owned_host(dst, color, rank, world):
+    """Host restatement of iftrcuCopyOwnedTilesToHost: the super-tiles `rank` owns of color [H, W, 4] -> the full-frame image dst."""
+    m = owned_mask(color.shape[1], color.shape[0], rank, world)
+    dst[m] = color[m]
+    return dst
+
+
+class SharedHostImage:
+    """One full-frame RGBA32F host image [H, W, 4] mapped by every rank of the box — the target of the distributed read-back
+    (iftrcuCopyOwnedTilesToHost): a file under /dev/shm created by rank 0, mapped by all, unlinked once everyone holds the mapping.
+    `array` is the numpy view, `ptr` its address (pinned + mapped by the renderer on first use)."""
+
+    def __init__(self, width, height, dist=None):
+        import mmap
+        import os
+        rank = dist.get_rank() if dist is not None else 0
+        world = dist.get_world_size() if dist is not None else 1
+        self.nbytes = width * height * 16
+        name = [None]
+        fd = -1
+        if rank == 0:
+            name = [f"/dev/shm/ifrit_b200_frame_{os.getpid()}_{id(self):x}"]
+            fd = os.open(name[0], os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
+            os.ftruncate(fd, self.nbytes)
+        if world > 1:
+            dist.broadcast_object_list(name, 0)
+        if rank != 0:
+            fd = os.open(name[0], os.O_RDWR)
+        self.mm = mmap.mmap(fd, self.nbytes)
+        os.close(fd)
+        if world > 1:
+            dist.barrier()
+        if rank == 0:
+            os.unlink(name[0])
+        self.array = np.frombuffer(self.mm, dtype=np.float32).reshape(height, width, 4)
+        self.ptr = self.array.ctypes.data
+
+
 def share_framebuffer(renderer, width, height, dist, device):
     """Peer-memory sort-first: rank 0 binds a renderer-owned device framebuffer and exports it (CUDA IPC);
     every other rank binds rank 0's memory as its render target, so its tile kernel writes the tiles it owns
@@ -172,6 +210,11 @@ class SortFirstRenderer:
             if not self.same_stream:
                 r.synchronize()
             self._keep = outs   # keep the receive buffers alive until the unpack kernels have run
+
+    def read_back_distributed(self, image):
+        """After drawElements() into a LOCAL framebuffer: this rank's tiles go straight to the shared host image (SharedHostImage) over
+        its own PCIe link — no NVLink gather, N links instead of one.  The frame is complete once every rank's stream has passed."""
+        self.r.copyOwnedTilesToHost(image.ptr)
 
     def release(self):
         """Peer mode, after gather(hold=True): rank 0 lets the other ranks overwrite the frame."""

@@ -139,6 +139,7 @@ def load_library():
         L.iftrcuSetTilePartition.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.iftrcuExportFrameBuffer.argtypes = [C.c_void_p, C.c_void_p]
         L.iftrcuCopyColorToHostAsync.argtypes = [C.c_void_p, C.c_void_p]
+        L.iftrcuCopyOwnedTilesToHost.argtypes = [C.c_void_p, C.c_void_p]
         L.iftrcuBindPeerFrameBuffer.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.iftrcuSetProfiling.argtypes = [C.c_void_p, C.c_int]
         L.iftrcuGetKernelTimes.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
@@ -482,6 +483,10 @@ class TileRasterRendererCuda:
     def frameFence(self, frame_id, cleared=False):
         fn = self._lib.iftrcuFrameFenceCleared if cleared else self._lib.iftrcuFrameFence
         self._ck(fn(self._h, C.c_uint32(frame_id)))
+
+    def copyOwnedTilesToHost(self, host_ptr):
+        """Sort-first distributed read-back: this rank's tiles -> the shared full-frame RGBA32F host image (stream order)."""
+        self._ck(self._lib.iftrcuCopyOwnedTilesToHost(self._h, C.c_void_p(host_ptr)))
 
     def packOwnedTiles(self, dev_ptr, nbytes):
         used = C.c_size_t()

@@ -339,6 +339,10 @@ IFRIT_B200_API int iftrcuFrameFence(iftrcuRenderer* h, uint32_t frameId);
  * variant then skips the NVLink stores of the colour of its empty tiles in that draw.  Frames stay bit-identical. */
 IFRIT_B200_API int iftrcuFrameReleaseCleared(iftrcuRenderer* h, uint32_t frameId);
 IFRIT_B200_API int iftrcuFrameFenceCleared(iftrcuRenderer* h, uint32_t frameId);
+/* Sort-first distributed read-back (no reference counterpart — the reference copies the frame back over one PCIe link, CU:3899-3909):
+ * stores the tiles this rank owns from its bound device framebuffer into the full-frame RGBA32F host image (row-major, W*H*16 bytes,
+ * shared by the ranks), in stream order, through mapped pinned memory.  Not page-locked yet -> registered here. */
+IFRIT_B200_API int iftrcuCopyOwnedTilesToHost(iftrcuRenderer* h, void* hostImage);
 IFRIT_B200_API int iftrcuPackOwnedTiles(iftrcuRenderer* h, void* devDst, size_t dstBytes, size_t* usedBytes);
 IFRIT_B200_API int iftrcuUnpackOwnedTiles(iftrcuRenderer* h, const void* devSrc, int rank, int worldSize);
 IFRIT_B200_API size_t iftrcuOwnedTileBytes(int width, int height, int rank, int worldSize);

@@ -47,6 +47,43 @@ def _worker(rank, world, port, W, H, q):
     dist.destroy_process_group()
 
 
+def _worker_shared(rank, world, port, W, H, q):
+    import sys
+    sys.path.insert(0, ROOT)
+    import ifrit_v2_b200  # noqa: F401
+    from ifrit_v2_b200 import multigpu as MG
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    full = np.random.default_rng(7).random((H, W, 4), dtype=np.float32)       # the same "frame" on every rank
+    img = MG.SharedHostImage(W, H, dist)
+    if rank == 0:
+        img.array[...] = -1.0
+    dist.barrier()
+    MG.copy_owned_host(img.array, full, rank, world)       # what iftrcuCopyOwnedTilesToHost does on the device side
+    dist.barrier()
+    if rank == 0:
+        q.put(bool(np.array_equal(img.array, full)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_distributed_read_back_shared_image_gloo():
+    """Sort-first distributed read-back: every rank stores the tiles it owns into ONE host image mapped by all ranks
+    (multigpu.SharedHostImage); the union is the full frame (world_size 2, odd frame size)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker_shared, args=(r, 2, port, 400, 230, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok
+
+
 @pytest.mark.parametrize("world", [2])
 def test_sort_first_gather_gloo(world):
     ctx = mp.get_context("spawn")
