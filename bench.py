@@ -214,7 +214,7 @@ def run_ours(args, cfg_name, do_e2e=True, fast_sampler=True):
         # the exchange; the line is NOT a bench value (value / roofline refer to the whole frame)
         er, en = (int(x) for x in args.emulate_rank.split("/"))
         r.setTilePartition(er, en)
-    sf = MG.SortFirstRenderer(r, dist, dev, mode=mg_mode, clears_every_frame=not getattr(args, 'no_preclear', False)) if world > 1 else None   # every bench frame is clear() + drawElements()
+    sf = MG.SortFirstRenderer(r, dist, dev, mode=mg_mode, clears_every_frame=not getattr(args, 'no_preclear', False), ring=getattr(args, "ring", 2)) if world > 1 else None   # every bench frame is clear() + drawElements()
 
     # N >= 4: draws of a million triangles and more split the triangle setup over the ranks (one all-gather of owner masks per
     # frame, multigpu.SortFirstRenderer.distribute_setup); below that the replicated setup is cheaper than the collective.  The
@@ -469,7 +469,7 @@ def run_ours(args, cfg_name, do_e2e=True, fast_sampler=True):
                        f"{W * H * 20 / 1e6:.0f} MB + texture) exceeds the 126 MB L2",
                        "sampler": ("FAST (opt-in): texture-unit bilinear blend, 8-bit weights, SFU lod math" if fast_sampler else
                                    "default: software fp32 lerps, the oracle's arithmetic op for op") if sc["tex"] is not None else "none",
-                       "parallelism": (f"sort-first x{world} ({mg_mode}" + (", pre-cleared release" if not getattr(args, "no_preclear", False) else "") +
+                       "parallelism": (f"sort-first x{world} ({mg_mode}" + (", two frames in flight" if (mg_mode == "peer" and getattr(args, "ring", 2) == 2) else "") + (", pre-cleared release" if not getattr(args, "no_preclear", False) else "") +
                                        (", triangle setup split over the ranks + NCCL all-gather of owner masks every frame" if dsetup else "") + ")") if world > 1 else "1 GPU"},
             "fps": 1e3 / ms_step, "gfrags_per_s": frags / (ms_step * 1e-3) / 1e9,
             "frame_latency_ms": lat_ms,
@@ -557,6 +557,7 @@ def main():
     ap.add_argument("--no-distributed-setup", action="store_true", help="A/B (N > 1): every rank assembles every triangle")
     ap.add_argument("--force-distributed-setup", action="store_true", help="A/B (N > 1): split the triangle setup whatever the rank / triangle count")
     ap.add_argument("--no-distributed-readback", action="store_true", help="A/B (N > 1): e2e reads the frame back through rank 0 only")
+    ap.add_argument("--ring", type=int, default=2, choices=[1, 2], help="A/B (N > 1, peer mode): frames in flight in the owner's framebuffer (2 = the peers render frame k + 1 while the owner releases frame k)")
     ap.add_argument("--no-preclear", action="store_true", help="A/B (N > 1, peer mode): plain frame release, every rank sends all of its tiles")
     ap.add_argument("--tile-chunk", type=int, default=0, choices=[0, 32, 64], help="A/B: big-queue entries per staged chunk of the tile kernel (0 = automatic)")
     ap.add_argument("--no-grid-hint", action="store_true", help="A/B: tile kernel grid of one CTA per tile instead of the measured CTA count")

@@ -75,6 +75,7 @@ struct iftrcuRenderer {
     uint32_t* hTimedOut = nullptr;        // pinned: set by a flag wait that gave up
     uint32_t fenceFrame = 0; bool fencePending = false;   // peer: next tile kernel waits for the owner's release
     const uint8_t* triMask = nullptr;                     // iftrcuSetTriangleOwnerMask (distributed triangle setup)
+    int ringCount = 1, ringIndex = 0; float4* ringBase = nullptr; uint32_t* flagsBase = nullptr;   // iftrcuSetFrameRing / iftrcuSelectFrame
     bool skipArmed = false; int lastSkip = 0;             // peer: the owner pre-cleared the frame (iftrcuFrameFenceCleared)
 
     // geometry
@@ -93,7 +94,7 @@ struct iftrcuRenderer {
     int polygonMode = IF_POLYGON_MODE_FILL;     // iftrcuSetRasterizerPolygonMode
     DevBuf primKeys, primSeg;                   // point / line modes: per-pixel winner keys, mapped segment ends (kernels_prim.cu)
     // TMA descriptors of the bound framebuffer (tma_maps), rebuilt when an image pointer or the size changes
-    struct TmaCache { void* c = nullptr; void* d = nullptr; void* pr = nullptr; int W = 0, H = 0, ok = 0; CUtensorMap m[6]; } tma;
+    struct TmaCache { void* c = nullptr; void* d = nullptr; void* pr = nullptr; int W = 0, H = 0, ok = 0; CUtensorMap m[6]; } tma[2];   // one per frame of the ring
     bool useTma = true;    // iftrcuSetTmaFramebuffer
     int forceBigChunk = 0;      // A/B: 32 / 64 pin the staged chunk size (iftrcuSetTileChunk)
     bool useGridHint = false;   // measured: no effect (profiles/r02_ab.txt), so the conservative grid stays the default
@@ -219,7 +220,7 @@ static bool tma_map_2d(CUtensorMap* m, CUtensorMapDataType dt, void* base, uint6
 static void tma_maps(iftrcuRenderer* r, DrawParams& p) {
     p.useTma = 0;
     if (!r->useTma || !p.color || !p.depth) return;
-    auto& t = r->tma;
+    auto& t = r->tma[r->ringIndex & 1];
     if (t.c != (void*)p.color || t.d != (void*)p.depth || t.pr != (void*)p.present || t.W != p.W || t.H != p.H) {
         t.c = p.color; t.d = p.depth; t.pr = p.present; t.W = p.W; t.H = p.H;
         const uint64_t W = (uint64_t)p.W, H = (uint64_t)p.H;
@@ -917,10 +918,11 @@ int iftrcuBindFrameBuffer(iftrcuRenderer* h, float* hostColor, float* hostDepth,
     close_peer(r);
     reset_double_buffer(r);
     CUDA_TRY(r->ownColor.ensure((size_t)width * height * 16));
-    CUDA_TRY(r->ownDepth.ensure(flag_offset(width, height) + IFR_FLAG_WORDS * 4));
+    CUDA_TRY(r->ownDepth.ensure(flag_offset(width, height) + 2 * IFR_FLAG_WORDS * 4));      // one flag block per frame of the ring
     r->frameFlags = (uint32_t*)((char*)r->ownDepth.p + flag_offset(width, height));
-    CUDA_TRY(cudaMemsetAsync(r->frameFlags, 0, IFR_FLAG_WORDS * 4, r->stream));
+    CUDA_TRY(cudaMemsetAsync(r->frameFlags, 0, 2 * IFR_FLAG_WORDS * 4, r->stream));
     r->fencePending = false;
+    r->ringCount = 1; r->ringIndex = 0; r->ringBase = nullptr; r->flagsBase = nullptr;
     r->wantDouble = useDoubleBuffer != 0;
     r->dColor = (float4*)r->ownColor.p; r->dDepth = (float*)r->ownDepth.p;
     r->externalFB = false;
@@ -981,7 +983,7 @@ int iftrcuExportFrameBuffer(iftrcuRenderer* h, void* handleOut128) {
     R_CHECK(h);
     if (!handleOut128) return IFRIT_ERR_INVALID;
     if (!r->dColor || r->externalFB || (void*)r->dColor != r->ownColor.p)
-        return r->fail(IFRIT_ERR_STATE, "exportFrameBuffer", "bind a renderer-owned framebuffer first (bindFrameBuffer)");
+        return r->fail(IFRIT_ERR_STATE, "exportFrameBuffer", "bind a renderer-owned framebuffer first (bindFrameBuffer), frame 0 of a ring selected");
     cudaIpcMemHandle_t hc, hd;
     CUDA_TRY(cudaIpcGetMemHandle(&hc, r->ownColor.p));
     CUDA_TRY(cudaIpcGetMemHandle(&hd, r->ownDepth.p));
@@ -1009,6 +1011,7 @@ int iftrcuBindPeerFrameBuffer(iftrcuRenderer* h, const void* handle128, int widt
     r->dColor = (float4*)r->peerColor; r->dDepth = (float*)r->ownDepth.p; r->externalFB = true; r->hColor = nullptr; r->hDepth = nullptr;
     r->frameFlags = (uint32_t*)((char*)r->peerDepth + flag_offset(width, height));
     r->fencePending = false;
+    r->ringCount = 1; r->ringIndex = 0; r->ringBase = nullptr; r->flagsBase = nullptr;
     if (r->W != width || r->H != height) r->scr[0].queueChecked = r->scr[1].queueChecked = false;
     r->W = width; r->H = height;
     return IFRIT_OK;
@@ -1025,6 +1028,7 @@ int iftrcuBindFrameBufferDevice(iftrcuRenderer* h, float* devColor, float* devDe
     if (r->registeredHost) { cudaHostUnregister(r->registeredHost); r->registeredHost = nullptr; }
     r->dColor = (float4*)devColor; r->dDepth = devDepth; r->externalFB = true; r->hColor = nullptr; r->hDepth = nullptr;
     r->frameFlags = nullptr; r->fencePending = false;
+    r->ringCount = 1; r->ringIndex = 0; r->ringBase = nullptr; r->flagsBase = nullptr;
     if (r->W != width || r->H != height) r->scr[0].queueChecked = r->scr[1].queueChecked = false;
     r->W = width; r->H = height;
     return IFRIT_OK;
@@ -1686,6 +1690,43 @@ int iftrcuGetGeometryStream(iftrcuRenderer* h, void** cudaStreamOut) {
 int iftrcuSetTriangleOwnerMask(iftrcuRenderer* h, const void* devMask) {
     R_CHECK(h);
     r->triMask = (const uint8_t*)devMask;      // read by the next setup pass, on the geometry stream, behind whatever the caller ordered there
+    return IFRIT_OK;
+}
+/* Sort-first peer mode with TWO frames in flight.  The owner's colour allocation holds `count` frames back to back (one CUDA IPC
+ * handle, mapped once by the peers) and there is one flag block per frame: while the owner consumes / pre-clears / releases frame k in
+ * one half, the peers already store the tiles of frame k + 1 into the other — their fence is on the release of frame k - 1, which is
+ * long past, so the release -> fence round trip leaves the critical path of every frame.  Owner: call after iftrcuBindFrameBuffer(NULL
+ * host image, no double buffering) and BEFORE iftrcuExportFrameBuffer; peers: after iftrcuBindPeerFrameBuffer.  count = 1 or 2. */
+int iftrcuSetFrameRing(iftrcuRenderer* h, int count) {
+    R_CHECK(h);
+    if (count != 1 && count != 2) return r->fail(IFRIT_ERR_INVALID, "SetFrameRing", "count must be 1 or 2");
+    if (!r->frameFlags || !r->dColor) return r->fail(IFRIT_ERR_STATE, "SetFrameRing", "no renderer-owned or peer framebuffer bound");
+    if (r->doubleBuffer || r->wantDouble || r->hColor || r->presentFormat) return r->fail(IFRIT_ERR_STATE, "SetFrameRing", "host images / double buffering do not combine with the frame ring");
+    int rc = flush_clear(r); if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(r->stream));
+    if (r->ringBase) { r->dColor = r->ringBase; r->frameFlags = r->flagsBase; }      // back to frame 0
+    if (!r->peerColor) {
+        const size_t frame = (size_t)r->W * r->H * 16;
+        if (r->ownColor.cap < count * frame) {
+            DevBuf bigger;
+            CUDA_TRY(bigger.ensure(count * frame));
+            CUDA_TRY(cudaMemcpy(bigger.p, r->ownColor.p, frame, cudaMemcpyDeviceToDevice));
+            r->ownColor.release();
+            r->ownColor = bigger;
+        }
+        r->dColor = (float4*)r->ownColor.p;
+    }
+    r->ringBase = r->dColor; r->flagsBase = r->frameFlags; r->ringCount = count; r->ringIndex = 0;
+    return IFRIT_OK;
+}
+/* the frame of the ring that the following clears / draws / read-backs / frame flags refer to (0 after iftrcuSetFrameRing) */
+int iftrcuSelectFrame(iftrcuRenderer* h, int index) {
+    R_CHECK(h);
+    if (!r->ringBase || index < 0 || index >= r->ringCount) return r->fail(IFRIT_ERR_INVALID, "SelectFrame", "no frame ring, or index out of range");
+    int rc = flush_clear(r); if (rc) return rc;      // a pending clear belongs to the frame that was selected when it was asked for
+    r->ringIndex = index;
+    r->dColor = r->ringBase + (size_t)index * r->W * r->H;
+    r->frameFlags = r->flagsBase + (size_t)index * IFR_FLAG_WORDS;
     return IFRIT_OK;
 }
 int iftrcuFrameSignal(iftrcuRenderer* h, uint32_t frameId) {

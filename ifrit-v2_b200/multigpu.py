@@ -117,20 +117,25 @@ class SharedHostImage:
         self.ptr = self.array.ctypes.data
 
 
-def share_framebuffer(renderer, width, height, dist, device):
+def share_framebuffer(renderer, width, height, dist, device, ring=1):
     """Peer-memory sort-first: rank 0 binds a renderer-owned device framebuffer and exports it (CUDA IPC);
     every other rank binds rank 0's memory as its render target, so its tile kernel writes the tiles it owns
-    straight into the final frame over NVLink.  Call on every rank before the first draw."""
+    straight into the final frame over NVLink.  Call on every rank before the first draw.  ring = 2: two frames
+    back to back in rank 0's allocation (iftrcuSetFrameRing), alternated by SortFirstRenderer.gather()."""
     import torch
     rank = dist.get_rank()
     blob = torch.zeros(128, dtype=torch.uint8, device=device)
     if rank == 0:
         renderer.bindFrameBuffer(None, None, width, height)
-        renderer.synchronize()      # the frame-flag block is zeroed before any peer can reach it
+        if ring > 1:
+            renderer.setFrameRing(ring)
+        renderer.synchronize()      # the frame-flag blocks are zeroed before any peer can reach them
         blob = torch.frombuffer(bytearray(renderer.exportFrameBuffer()), dtype=torch.uint8).to(device)
     dist.broadcast(blob, 0)
     if rank != 0:
         renderer.bindPeerFrameBuffer(bytes(blob.cpu().numpy().tobytes()), width, height)
+        if ring > 1:
+            renderer.setFrameRing(ring)
 
 
 class SortFirstRenderer:
@@ -139,7 +144,7 @@ class SortFirstRenderer:
     on the device through flag words in rank 0's memory (iftrcuFrameSignal / Wait / Release / Fence) — no NCCL
     call and no host round trip per frame.  mode "nccl": pack -> NCCL gather -> unpack."""
 
-    def __init__(self, renderer, dist, device, same_stream=True, mode="nccl", clears_every_frame=False):
+    def __init__(self, renderer, dist, device, same_stream=True, mode="nccl", clears_every_frame=False, ring=1):
         """same_stream: the renderer was given torch's current stream (setStream), so pack -> NCCL ->
         unpack are ordered on the device and need no host synchronisation."""
         import torch
@@ -149,8 +154,12 @@ class SortFirstRenderer:
         # peer mode: the caller promises that every frame starts with clear() -> rank 0 pre-clears the other ranks' tiles when
         # it releases a frame and the peers keep the colour of their empty tiles off NVLink (iftrcuFrameReleaseCleared)
         self.clears_every_frame = clears_every_frame
+        # peer mode, ring = 2: frame k lives in buffer (k - 1) & 1 of rank 0's allocation.  A peer fences frame k + 1 on the release of
+        # frame k - 1 (the last user of that buffer) instead of frame k: rank 0's wait / pre-clear / release of frame k overlap the peers'
+        # tile kernels of frame k + 1, and the flag round trip release -> fence leaves the critical path.
+        self.ring = ring if (mode == "peer" and self.world > 1) else 1
         if mode == "peer" and self.world > 1:
-            share_framebuffer(renderer, renderer.width, renderer.height, dist, device)
+            share_framebuffer(renderer, renderer.width, renderer.height, dist, device, ring=self.ring)
             self.frame = 0
         renderer.setTilePartition(self.rank, self.world)
         self.torch = torch
@@ -191,9 +200,13 @@ class SortFirstRenderer:
             if self.rank == 0:
                 r.frameWait(self.frame)           # polls until every rank has signalled
                 if not hold:
-                    r.frameRelease(self.frame, cleared=self.clears_every_frame)
-            else:
+                    self.release()
+            elif self.ring == 1:
                 r.frameFence(self.frame, cleared=self.clears_every_frame)   # my next tile kernel waits until rank 0 has released this frame
+            else:
+                r.selectFrame(self.frame & 1)     # buffer of frame k + 1, last used by frame k - 1
+                if self.frame >= 2:
+                    r.frameFence(self.frame - 1, cleared=self.clears_every_frame)
             return
         n = max_owned_floats(r.width, r.height, self.world)
         if self.packed is None or self.packed.numel() != n:
@@ -220,3 +233,5 @@ class SortFirstRenderer:
         """Peer mode, after gather(hold=True): rank 0 lets the other ranks overwrite the frame."""
         if self.world > 1 and self.mode == "peer" and self.rank == 0:
             self.r.frameRelease(self.frame, cleared=self.clears_every_frame)
+            if self.ring > 1:
+                self.r.selectFrame(self.frame & 1)

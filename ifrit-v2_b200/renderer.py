@@ -470,6 +470,12 @@ class TileRasterRendererCuda:
     def setTriangleOwnerMask(self, dev_mask_ptr):
         self._ck(self._lib.iftrcuSetTriangleOwnerMask(self._h, C.c_void_p(dev_mask_ptr) if dev_mask_ptr else None))
 
+    def setFrameRing(self, count):
+        self._ck(self._lib.iftrcuSetFrameRing(self._h, int(count)))
+
+    def selectFrame(self, index):
+        self._ck(self._lib.iftrcuSelectFrame(self._h, int(index)))
+
     def frameSignal(self, frame_id):
         self._ck(self._lib.iftrcuFrameSignal(self._h, C.c_uint32(frame_id)))
 

@@ -330,6 +330,13 @@ IFRIT_B200_API int iftrcuClassifyTriangles(iftrcuRenderer* h, int firstTriangle,
 IFRIT_B200_API int iftrcuSetTriangleOwnerMask(iftrcuRenderer* h, const void* devMask /* NULL = off */);
 /* the stream the geometry stage (and iftrcuClassifyTriangles) runs on: the caller's all-gather of the masks must be ordered on it */
 IFRIT_B200_API int iftrcuGetGeometryStream(iftrcuRenderer* h, void** cudaStreamOut);
+/* Peer mode with two frames in flight: the owner's colour allocation holds `count` (1 or 2) frames back to back behind the same CUDA
+ * IPC handle, with one flag block each; iftrcuSelectFrame picks the frame that the following clears / draws / read-backs and the
+ * iftrcuFrame* verbs refer to.  Owner: iftrcuBindFrameBuffer -> iftrcuSetFrameRing -> iftrcuExportFrameBuffer; peers:
+ * iftrcuBindPeerFrameBuffer -> iftrcuSetFrameRing.  With frame k in buffer (k - 1) & 1, a peer fences frame k + 1 on the release of frame
+ * k - 1, so that the owner's wait / pre-clear / release of frame k overlaps the peers' tile kernels of frame k + 1. */
+IFRIT_B200_API int iftrcuSetFrameRing(iftrcuRenderer* h, int count);
+IFRIT_B200_API int iftrcuSelectFrame(iftrcuRenderer* h, int index);
 IFRIT_B200_API int iftrcuFrameSignal(iftrcuRenderer* h, uint32_t frameId);
 IFRIT_B200_API int iftrcuFrameWait(iftrcuRenderer* h, uint32_t frameId);
 IFRIT_B200_API int iftrcuFrameRelease(iftrcuRenderer* h, uint32_t frameId);

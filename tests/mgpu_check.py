@@ -21,7 +21,7 @@ def main():
     u = scenes.uniform_block(scenes.default_mvp(W, H))
     tex = scenes.texture_checker(size=128, seed=7)
     ok = True
-    for mode in ("peer", "peer+preclear", "peer+preclear+dsetup", "nccl"):
+    for mode in ("peer", "peer+preclear", "peer+preclear+dsetup", "peer+ring", "peer+preclear+ring", "nccl"):
         for msaa in (1, 8):
             r = R.TileRasterRendererCuda(local)
             r.Init()
@@ -31,18 +31,21 @@ def main():
             r.width, r.height = W, H
             if mode == "nccl":
                 r.bindFrameBuffer(None, None, W, H)
-            sf = MG.SortFirstRenderer(r, dist, dev, mode=mode.split("+")[0], clears_every_frame="preclear" in mode)
+            sf = MG.SortFirstRenderer(r, dist, dev, mode=mode.split("+")[0], clears_every_frame="preclear" in mode, ring=2 if "ring" in mode else 1)
             R.setup_scene(r, vb, idx, R.VS_MVP, R.FS_TEXTURED, 2, u, texture=tex, mip_levels=7,
                           sampler=dict(filterMode=1, anisotropyEnable=True, maxAnisotropy=16.0))
             r.setMsaaSamples(msaa)
             r.SetCullMode(R.IF_CULL_MODE_BACK)
             r.setClearValues([(0.1, 0.2, 0.3, 1.0)], 255.0)
-            for f in range(3):             # frames 2 and 3 of "peer+preclear" run with the empty tiles kept off NVLink
+            nframes = 5 if "ring" in mode else 3       # ring: both buffers used twice, pre-cleared releases of both in effect
+            for f in range(nframes):             # frames 2 and 3 of "peer+preclear" run with the empty tiles kept off NVLink
                 r.clear()
+                if "ring" in mode:      # earlier frames differ from the last one (other faces culled): a stale or wrong buffer would show
+                    r.SetCullMode(R.IF_CULL_MODE_BACK if f == nframes - 1 else R.IF_CULL_MODE_FRONT)
                 if mode.endswith("dsetup"):          # triangle setup split over the ranks, owner masks all-gathered
                     sf.distribute_setup(len(idx) // 3)
                 r.drawElements()
-                sf.gather(hold=(f == 2))   # the last frame is held until it has been read (a release lets it be overwritten)
+                sf.gather(hold=(f == nframes - 1))   # the last frame is held until it has been read (a release lets it be overwritten)
             torch.cuda.synchronize()
             dist.barrier()
             if rank == 0:

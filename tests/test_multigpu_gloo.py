@@ -143,3 +143,60 @@ def test_peer_mode_frame_flag_protocol():
     assert r0.calls == [("partition", 0, 2), ("frameSignal", 1), ("frameWait", 1), ("frameRelease", 1),
                         ("frameSignal", 2), ("frameWait", 2), ("frameRelease", 2)]
     assert r1.calls == [("partition", 1, 2), ("frameSignal", 1), ("frameFence", 1), ("frameSignal", 2), ("frameFence", 2)]
+
+
+def test_peer_mode_frame_ring_protocol():
+    """Two frames in flight (iftrcuSetFrameRing / iftrcuSelectFrame): frame k lives in buffer (k - 1) & 1; rank 0 releases frame k and
+    moves on to the other buffer; a peer moves on first and fences its next tile kernel on the release of frame k - 1 — the last user of
+    that buffer — and on nothing at all before frame 2.  Host logic only, with a recording stand-in renderer."""
+    from ifrit_v2_b200 import multigpu as MG
+
+    class Rec:
+        width, height = 128, 64
+
+        def __init__(self):
+            self.calls = []
+
+        def setTilePartition(self, rank, world):
+            pass
+
+        def selectFrame(self, index):
+            self.calls.append(("select", index))
+
+        def __getattr__(self, name):
+            if name.startswith("frame"):
+                return lambda fid, cleared=False: self.calls.append((name, fid, cleared))
+            raise AttributeError(name)
+
+    class Dist:
+        def __init__(self, rank, world):
+            self.rank, self.world = rank, world
+
+        def get_rank(self):
+            return self.rank
+
+        def get_world_size(self):
+            return self.world
+
+    share = MG.share_framebuffer
+    seen = []
+    MG.share_framebuffer = lambda *a, **k: seen.append(k.get("ring"))
+    try:
+        r0, r1 = Rec(), Rec()
+        s0 = MG.SortFirstRenderer(r0, Dist(0, 2), None, mode="peer", clears_every_frame=True, ring=2)
+        s1 = MG.SortFirstRenderer(r1, Dist(1, 2), None, mode="peer", clears_every_frame=True, ring=2)
+        for _ in range(3):
+            s0.gather(); s1.gather()
+        s0.gather(hold=True); s1.gather(hold=True)
+        s0.release(); s1.release()
+    finally:
+        MG.share_framebuffer = share
+    assert seen == [2, 2]
+    assert r0.calls == [("frameSignal", 1, False), ("frameWait", 1, False), ("frameRelease", 1, True), ("select", 1),
+                        ("frameSignal", 2, False), ("frameWait", 2, False), ("frameRelease", 2, True), ("select", 0),
+                        ("frameSignal", 3, False), ("frameWait", 3, False), ("frameRelease", 3, True), ("select", 1),
+                        ("frameSignal", 4, False), ("frameWait", 4, False), ("frameRelease", 4, True), ("select", 0)]
+    assert r1.calls == [("frameSignal", 1, False), ("select", 1),
+                        ("frameSignal", 2, False), ("select", 0), ("frameFence", 1, True),
+                        ("frameSignal", 3, False), ("select", 1), ("frameFence", 2, True),
+                        ("frameSignal", 4, False), ("select", 0), ("frameFence", 3, True)]
