@@ -298,6 +298,12 @@ def run_ours(args, cfg_name, do_e2e=True, fast_sampler=True):
         frags = float(st1["fragments_shaded"])
     ms_step = ms / args.steps
     launches = st1["kernel_launches"] - st0["kernel_launches"]
+    tile_ms_ranks = None
+    if world > 1:       # the tile kernel of every rank (rank 0 stores locally, the others over NVLink)
+        tt = torch.zeros(world, dtype=torch.float64, device=dev)
+        tt[rank] = float(ktimes.get("tile", 0.0))
+        dist.all_reduce(tt)
+        tile_ms_ranks = [round(float(x), 4) for x in tt.tolist()]
 
     # single-frame latency: the same steps with frame pipelining off (geometry and tile stage of a frame back to back on
     # one stream, nothing of the next frame overlapping) — `value` is steady-state throughput with it on
@@ -493,6 +499,7 @@ def run_ours(args, cfg_name, do_e2e=True, fast_sampler=True):
                           "readback": readback}
         if world > 1:
             out["frame_hash_equals_1gpu"] = frame_same
+            out["tile_ms_per_rank"] = tile_ms_ranks
             if e2e_ms and e2e_gather_ms:
                 out["e2e"]["frame_equals_1gpu"] = e2e_dist_same
                 out["e2e_gather_rank0"] = {"value": ntri / (e2e_gather_ms * 1e-3) / 1e6, "unit": "Mtris/s", "ms_per_step": e2e_gather_ms,

@@ -76,6 +76,7 @@ struct iftrcuRenderer {
     uint32_t fenceFrame = 0; bool fencePending = false;   // peer: next tile kernel waits for the owner's release
     const uint8_t* triMask = nullptr;                     // iftrcuSetTriangleOwnerMask (distributed triangle setup)
     int ringCount = 1, ringIndex = 0; float4* ringBase = nullptr; uint32_t* flagsBase = nullptr;   // iftrcuSetFrameRing / iftrcuSelectFrame
+    cudaStream_t xStream = nullptr; cudaEvent_t evSignal = nullptr, evRetire[2] = {nullptr, nullptr}; bool retirePending[2] = {false, false};   // iftrcuFrameRetire
     bool skipArmed = false; int lastSkip = 0;             // peer: the owner pre-cleared the frame (iftrcuFrameFenceCleared)
 
     // geometry
@@ -662,6 +663,10 @@ static int issue_draw(iftrcuRenderer* r, bool forceCheck, bool sameSet = false) 
         CUDA_TRY(cudaEventRecord(r->evGeomDone[r->set], g));
         CUDA_TRY(cudaStreamWaitEvent(s, r->evGeomDone[r->set], 0));
     }
+    if (r->retirePending[r->ringIndex & 1]) {   // sort-first owner: this buffer's previous frame is being retired on the exchange stream
+        CUDA_TRY(cudaStreamWaitEvent(s, r->evRetire[r->ringIndex & 1], 0));
+        r->retirePending[r->ringIndex & 1] = false;
+    }
     if (r->fencePending && r->frameFlags) {   // sort-first peer: the owner must have released the frame these tiles overwrite
         CUDA_TRY(ifr_launch_flag_wait(r->frameFlags + 64, 1, r->fenceFrame, r->hTimedOut, s));
         r->fencePending = false;
@@ -749,6 +754,10 @@ static int issue_draw_prims(iftrcuRenderer* r) {
 
 static int flush_clear(iftrcuRenderer* r) {
     if (!r->pendingClear || !r->dColor) return IFRIT_OK;
+    if (r->retirePending[r->ringIndex & 1]) {
+        CUDA_TRY(cudaStreamWaitEvent(r->stream, r->evRetire[r->ringIndex & 1], 0));
+        r->retirePending[r->ringIndex & 1] = false;
+    }
     DrawParams p;
     build_params(r, p);
     CUDA_TRY(ifr_launch_clear(p, r->stream));
@@ -762,6 +771,7 @@ static int sync_and_check(iftrcuRenderer* r) {
     if (r->geomStream) CUDA_TRY(cudaStreamSynchronize(r->geomStream));
     CUDA_TRY(cudaStreamSynchronize(r->stream));
     if (r->statStream) CUDA_TRY(cudaStreamSynchronize(r->statStream));
+    if (r->xStream) CUDA_TRY(cudaStreamSynchronize(r->xStream));
     if (r->doubleBuffer) CUDA_TRY(cudaStreamSynchronize(r->copyStream));
     if (r->haveDraw && (r->hCounters[3] || r->hCounters[12])) {
         // the queue sized from an earlier frame was too small: grow it and re-issue the draw
@@ -830,6 +840,9 @@ int iftrcuDestroyInstance(iftrcuRenderer* h) {
     if (r->registeredHost) cudaHostUnregister(r->registeredHost);
     if (r->registeredPresent) cudaHostUnregister(r->registeredPresent);
     if (r->registeredOwned) cudaHostUnregister(r->registeredOwned);
+    if (r->xStream) { cudaStreamSynchronize(r->xStream); cudaStreamDestroy(r->xStream); }
+    if (r->evSignal) cudaEventDestroy(r->evSignal);
+    for (int i = 0; i < 2; i++) if (r->evRetire[i]) cudaEventDestroy(r->evRetire[i]);
     for (auto& sh : r->rtc) for (int i = 0; i < 5; i++) if (sh.lib[i]) cudaLibraryUnload(sh.lib[i]);
     for (auto& st : r->meshShaders) if (st.lib) cudaLibraryUnload(st.lib);
     for (auto& st : r->taskShaders) if (st.lib) cudaLibraryUnload(st.lib);
@@ -922,7 +935,7 @@ int iftrcuBindFrameBuffer(iftrcuRenderer* h, float* hostColor, float* hostDepth,
     r->frameFlags = (uint32_t*)((char*)r->ownDepth.p + flag_offset(width, height));
     CUDA_TRY(cudaMemsetAsync(r->frameFlags, 0, 2 * IFR_FLAG_WORDS * 4, r->stream));
     r->fencePending = false;
-    r->ringCount = 1; r->ringIndex = 0; r->ringBase = nullptr; r->flagsBase = nullptr;
+    r->ringCount = 1; r->ringIndex = 0; r->ringBase = nullptr; r->flagsBase = nullptr; r->retirePending[0] = r->retirePending[1] = false;
     r->wantDouble = useDoubleBuffer != 0;
     r->dColor = (float4*)r->ownColor.p; r->dDepth = (float*)r->ownDepth.p;
     r->externalFB = false;
@@ -1011,7 +1024,7 @@ int iftrcuBindPeerFrameBuffer(iftrcuRenderer* h, const void* handle128, int widt
     r->dColor = (float4*)r->peerColor; r->dDepth = (float*)r->ownDepth.p; r->externalFB = true; r->hColor = nullptr; r->hDepth = nullptr;
     r->frameFlags = (uint32_t*)((char*)r->peerDepth + flag_offset(width, height));
     r->fencePending = false;
-    r->ringCount = 1; r->ringIndex = 0; r->ringBase = nullptr; r->flagsBase = nullptr;
+    r->ringCount = 1; r->ringIndex = 0; r->ringBase = nullptr; r->flagsBase = nullptr; r->retirePending[0] = r->retirePending[1] = false;
     if (r->W != width || r->H != height) r->scr[0].queueChecked = r->scr[1].queueChecked = false;
     r->W = width; r->H = height;
     return IFRIT_OK;
@@ -1028,7 +1041,7 @@ int iftrcuBindFrameBufferDevice(iftrcuRenderer* h, float* devColor, float* devDe
     if (r->registeredHost) { cudaHostUnregister(r->registeredHost); r->registeredHost = nullptr; }
     r->dColor = (float4*)devColor; r->dDepth = devDepth; r->externalFB = true; r->hColor = nullptr; r->hDepth = nullptr;
     r->frameFlags = nullptr; r->fencePending = false;
-    r->ringCount = 1; r->ringIndex = 0; r->ringBase = nullptr; r->flagsBase = nullptr;
+    r->ringCount = 1; r->ringIndex = 0; r->ringBase = nullptr; r->flagsBase = nullptr; r->retirePending[0] = r->retirePending[1] = false;
     if (r->W != width || r->H != height) r->scr[0].queueChecked = r->scr[1].queueChecked = false;
     r->W = width; r->H = height;
     return IFRIT_OK;
@@ -1745,6 +1758,35 @@ int iftrcuFrameRelease(iftrcuRenderer* h, uint32_t frameId) {
     R_CHECK(h);
     if (!r->frameFlags) return r->fail(IFRIT_ERR_STATE, "FrameRelease", "no renderer-owned or peer framebuffer bound");
     CUDA_TRY(ifr_launch_flag_store(r->frameFlags + 64, frameId, r->stream));
+    return IFRIT_OK;
+}
+/* Owner, for frames that nothing on the draw stream consumes: wait for every rank's signal of frameId, pre-clear the other ranks' tiles
+ * (cleared != 0, the promise of iftrcuFrameReleaseCleared) and raise the release — all on the renderer's EXCHANGE stream, ordered behind
+ * what the draw stream holds now (the owner's own signal).  The draw stream goes straight on to the next frame; the next draw or clear
+ * into this buffer of the ring is ordered behind the retirement.  With a ring of two the owner's wait / pre-clear / release of frame k
+ * overlap its tile kernel of frame k + 1 just as they overlap the peers'. */
+int iftrcuFrameRetire(iftrcuRenderer* h, uint32_t frameId, int cleared) {
+    R_CHECK(h);
+    if (!r->frameFlags || !r->dColor || r->peerColor || r->world > 64) return r->fail(IFRIT_ERR_STATE, "FrameRetire", "no renderer-owned framebuffer bound");
+    int rc = flush_clear(r); if (rc) return rc;
+    if (!r->xStream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&r->xStream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&r->evSignal, cudaEventDisableTiming));
+        for (int i = 0; i < 2; i++) CUDA_TRY(cudaEventCreateWithFlags(&r->evRetire[i], cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventRecord(r->evSignal, r->stream));
+    CUDA_TRY(cudaStreamWaitEvent(r->xStream, r->evSignal, 0));
+    CUDA_TRY(ifr_launch_flag_wait(r->frameFlags, r->world, frameId, r->hTimedOut, r->xStream));
+    if (cleared && r->world > 1) {
+        DrawParams p;
+        build_params(r, p);
+        p.skipEmptyStores = 2; p.scissorEnable = 0; p.present = nullptr;
+        CUDA_TRY(ifr_launch_clear(p, r->xStream));
+        r->stats.kernel_launches += 1;
+    }
+    CUDA_TRY(ifr_launch_flag_store(r->frameFlags + 64, frameId, r->xStream));
+    CUDA_TRY(cudaEventRecord(r->evRetire[r->ringIndex & 1], r->xStream));
+    r->retirePending[r->ringIndex & 1] = true;
     return IFRIT_OK;
 }
 int iftrcuFrameFence(iftrcuRenderer* h, uint32_t frameId) {

@@ -198,9 +198,15 @@ class SortFirstRenderer:
             self.frame = (self.frame + 1) & 0xffffffff   # compared modulo 2^32 on the device
             r.frameSignal(self.frame)             # my tiles of this frame are stored (after my tile kernel)
             if self.rank == 0:
-                r.frameWait(self.frame)           # polls until every rank has signalled
-                if not hold:
-                    self.release()
+                if not hold and self.ring > 1:
+                    # nothing on the draw stream consumes the frame: wait / pre-clear / release run on the exchange stream and
+                    # overlap this rank's tile kernel of the next frame (other buffer of the ring)
+                    r.frameRetire(self.frame, cleared=self.clears_every_frame)
+                    r.selectFrame(self.frame & 1)
+                else:
+                    r.frameWait(self.frame)           # polls until every rank has signalled
+                    if not hold:
+                        self.release()
             elif self.ring == 1:
                 r.frameFence(self.frame, cleared=self.clears_every_frame)   # my next tile kernel waits until rank 0 has released this frame
             else:

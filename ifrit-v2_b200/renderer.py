@@ -486,6 +486,9 @@ class TileRasterRendererCuda:
         fn = self._lib.iftrcuFrameReleaseCleared if cleared else self._lib.iftrcuFrameRelease
         self._ck(fn(self._h, C.c_uint32(frame_id)))
 
+    def frameRetire(self, frame_id, cleared=False):
+        self._ck(self._lib.iftrcuFrameRetire(self._h, C.c_uint32(frame_id), int(bool(cleared))))
+
     def frameFence(self, frame_id, cleared=False):
         fn = self._lib.iftrcuFrameFenceCleared if cleared else self._lib.iftrcuFrameFence
         self._ck(fn(self._h, C.c_uint32(frame_id)))

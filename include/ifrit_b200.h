@@ -341,6 +341,10 @@ IFRIT_B200_API int iftrcuFrameSignal(iftrcuRenderer* h, uint32_t frameId);
 IFRIT_B200_API int iftrcuFrameWait(iftrcuRenderer* h, uint32_t frameId);
 IFRIT_B200_API int iftrcuFrameRelease(iftrcuRenderer* h, uint32_t frameId);
 IFRIT_B200_API int iftrcuFrameFence(iftrcuRenderer* h, uint32_t frameId);
+/* Owner: FrameWait + (cleared ? FrameReleaseCleared : FrameRelease) on the renderer's exchange stream, behind what the draw stream holds now,
+ * for frames nothing on the draw stream consumes; the next draw / clear into the same buffer of the ring is ordered behind it. */
+IFRIT_B200_API int iftrcuFrameRetire(iftrcuRenderer* h, uint32_t frameId, int cleared);
+
 /* The same pair with a promise: the NEXT draw into this framebuffer begins with iftrcuClear (same clear values on every
  * rank).  The owner clears the other ranks' tiles locally before raising the release; a peer that fences with the Cleared
  * variant then skips the NVLink stores of the colour of its empty tiles in that draw.  Frames stay bit-identical. */
