@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(256, IFR_SETUP_MINB) setup_count_kernel(const 
 // compacted list with full warps.
 #define IFR_MASKED_PER_CTA 2048
 #ifndef IFR_MASKED_MINB
-#define IFR_MASKED_MINB 3      // 80 registers, 604 B of spill stores; measured on c5 as rank 0 of 8: 1.20 ms against 1.51 ms with 2 (112 registers, no spills)
+#define IFR_MASKED_MINB 4      // 64 registers (spills on the clip path); measured on c5 as rank 0 of 8: 0.96 ms, against 1.20 ms with 3 (80 registers) and 1.51 ms with 2 (112, no spills): the pass is bound by the latency of its gathers, occupancy wins
 #endif
 template <int VSMODE>
 __global__ void __launch_bounds__(256, IFR_MASKED_MINB) setup_count_masked_kernel(const __grid_constant__ DrawParams p) {

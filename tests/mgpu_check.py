@@ -21,7 +21,8 @@ def main():
     u = scenes.uniform_block(scenes.default_mvp(W, H))
     tex = scenes.texture_checker(size=128, seed=7)
     ok = True
-    for mode in ("peer", "peer+preclear", "peer+preclear+dsetup", "peer+ring", "peer+preclear+ring", "nccl"):
+    modes = os.environ.get("MGPU_MODES", "peer,peer+preclear,peer+preclear+dsetup,peer+ring,peer+preclear+ring,nccl").split(",")
+    for mode in modes:
         for msaa in (1, 8):
             r = R.TileRasterRendererCuda(local)
             r.Init()

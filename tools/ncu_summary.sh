@@ -2,7 +2,7 @@
 # usage (here): tools/ncu_summary.sh <report.ncu-rep> <object file holding the kernel> <mangled kernel> <out.txt> [topN]
 # headline counters (--page raw) + per-source-line stall / instruction table (tools/ncu_lines.py) of one ncu --set full capture
 rep=$1; obj=$2; kern=$3; out=$4; top=${5:-30}
-d=$(mktemp -d); (cd $d && cuobjdump -xelf all $obj > /dev/null 2>&1); cub=$(ls $d/*.cubin | head -1)
+d=$(mktemp -d); (cd $d && cuobjdump -xelf all $obj > /dev/null 2>&1); cub=$(for c in $d/*.cubin; do if cuobjdump -elf $c 2>/dev/null | grep -q "$kern"; then echo $c; break; fi; done)
 {
 echo "# $(basename $rep): ncu --set full --clock-control none --import-source on, one launch; kernel $kern"
 ncu -i $rep --page raw --csv 2>/dev/null | python3 -c "
