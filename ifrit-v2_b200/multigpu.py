@@ -117,6 +117,28 @@ class SharedHostImage:
         self.ptr = self.array.ctypes.data
 
 
+def setup_slice(ntri, rank, world):
+    """Distributed triangle setup: (chunk, first, count) — rank `rank` classifies triangles [first, first + count); chunks are equal
+    and 16-aligned so that the all-gather of the owner masks is one contiguous, evenly split tensor."""
+    chunk = ((ntri + world - 1) // world + 15) // 16 * 16
+    first = rank * chunk
+    return chunk, first, max(0, min(ntri, first + chunk) - first)
+
+
+def box_owner_mask_host(world, tx0, tx1, ty0, ty1):
+    """Host restatement of box_owner_mask (csrc/kernels_geometry.cu): bit r set <=> rank r owns a 64-px super-tile that the box of
+    16-px tiles [tx0..tx1] x [ty0..ty1] touches; boxes of more than 16 super-tiles name every rank."""
+    st = SUPER // 16
+    sx0, sx1, sy0, sy1 = tx0 // st, tx1 // st, ty0 // st, ty1 // st
+    if (sx1 - sx0 + 1) * (sy1 - sy0 + 1) > 16:
+        return (1 << world) - 1
+    m = 0
+    for sy in range(sy0, sy1 + 1):
+        for sx in range(sx0, sx1 + 1):
+            m |= 1 << ((sx + 3 * sy) % world)
+    return m
+
+
 def share_framebuffer(renderer, width, height, dist, device, ring=1):
     """Peer-memory sort-first: rank 0 binds a renderer-owned device framebuffer and exports it (CUDA IPC);
     every other rank binds rank 0's memory as its render target, so its tile kernel writes the tiles it owns
@@ -174,12 +196,9 @@ class SortFirstRenderer:
         torch, r = self.torch, self.r
         if self.world < 2 or self.world > 8:
             return
-        chunk = (ntri + self.world - 1) // self.world
-        chunk = (chunk + 15) // 16 * 16
+        chunk, first, count = setup_slice(ntri, self.rank, self.world)
         if self._mask is None or self._mask.numel() != chunk * self.world:
             self._mask = torch.zeros(chunk * self.world, dtype=torch.uint8, device=self.device)
-        first = self.rank * chunk
-        count = max(0, min(ntri, first + chunk) - first)
         # everything on the renderer's GEOMETRY stream: classification -> all-gather -> (next draw's) setup pass, so that the whole
         # chain overlaps the previous frame's tile kernel on the draw stream
         r.classifyTriangles(first, count, self._mask.data_ptr())

@@ -202,3 +202,59 @@ def test_peer_mode_frame_ring_protocol():
                         ("frameSignal", 2, False), ("select", 0), ("frameFence", 1, True),
                         ("frameSignal", 3, False), ("select", 1), ("frameFence", 2, True),
                         ("frameSignal", 4, False), ("select", 0), ("frameFence", 3, True)]
+
+
+def _worker_masks(rank, world, port, ntri, q):
+    import sys
+    sys.path.insert(0, ROOT)
+    import ifrit_v2_b200  # noqa: F401
+    from ifrit_v2_b200 import multigpu as MG
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(11)                      # the same boxes on every rank (replicated geometry)
+    tx0 = rng.integers(0, 230, ntri); ty0 = rng.integers(0, 130, ntri)
+    tx1 = tx0 + rng.integers(0, 6, ntri) * (rng.random(ntri) < 0.3); ty1 = ty0 + rng.integers(0, 6, ntri) * (rng.random(ntri) < 0.3)
+    tx1[:3] = tx0[:3] + 40; ty1[:3] = ty0[:3] + 40      # a few boxes of more than 16 super-tiles
+    chunk, first, count = MG.setup_slice(ntri, rank, world)
+    mask = torch.zeros(chunk * world, dtype=torch.uint8)
+    for t in range(first, first + count):                # what iftrcuClassifyTriangles writes for this rank's slice
+        mask[t] = MG.box_owner_mask_host(world, int(tx0[t]), int(tx1[t]), int(ty0[t]), int(ty1[t]))
+    dist.all_gather_into_tensor(mask, mask[first:first + chunk].clone())
+    ok = True
+    if rank == 0:
+        m = mask.numpy()
+        # every slice arrived where it belongs, and the masks name (at least) every rank that owns a tile of the box
+        for t in range(ntri):
+            want = 0
+            for ty in range(int(ty0[t]), int(ty1[t]) + 1):
+                for tx in range(int(tx0[t]), int(tx1[t]) + 1):
+                    want |= 1 << (((tx // 4) + 3 * (ty // 4)) % world)
+            ok = ok and (int(m[t]) & want) == want and int(m[t]) == MG.box_owner_mask_host(world, int(tx0[t]), int(tx1[t]), int(ty0[t]), int(ty1[t]))
+        q.put(bool(ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_distributed_setup_slices_and_owner_masks_gloo():
+    """Distributed triangle setup, host side (world_size 2): the slices tile the draw (16-aligned, equal chunks, ragged tail), each rank
+    classifies its own, one all-gather gives everyone the whole mask array, and a mask names every rank that owns a tile of the box."""
+    from ifrit_v2_b200 import multigpu as MG
+    for ntri, world in ((1, 2), (31, 2), (1000, 3), (50_000_000, 8)):
+        seen = 0
+        for rank in range(world):
+            chunk, first, count = MG.setup_slice(ntri, rank, world)
+            assert chunk % 16 == 0 and chunk * world >= ntri and first == rank * chunk and first + count <= max(ntri, first)
+            seen += count
+        assert seen == ntri
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker_masks, args=(r, 2, port, 1003, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok
