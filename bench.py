@@ -488,7 +488,10 @@ def run_ours(args, cfg_name, do_e2e=True, fast_sampler=True):
                          "algorithmic_bytes_per_launch": ab["tile"] / world, "traffic": traffic,
                          "note": "duration from CUDA events around the kernel inside the timed (pipelined) region, where it shares the GPU "
                                  "with the next frame's geometry kernels; frac_unpipelined = the same kernel with the GPU to itself",
-                         "frac_unpipelined": (ab["tile"] / world / (ktimes_alone["tile"] * 1e-3) / 1e9 / peak) if ktimes_alone and ktimes_alone["tile"] > 0 else None},
+                         "frac_unpipelined": (ab["tile"] / world / (ktimes_alone["tile"] * 1e-3) / 1e9 / peak) if ktimes_alone and ktimes_alone["tile"] > 0 else None,
+                         # the same fraction from the DRAM bytes ncu measured for one launch (profiles/traffic.json) instead of the algorithmic
+                         # ones: SURVEY 8d's texel term saturates at the whole mip chain, the kernel actually touches less of it
+                         "frac_measured_traffic": (traffic / (tile_ms * 1e-3) / 1e9 / peak) if traffic and tile_ms > 0 else None},
             "frame_roofline": {"algorithmic_bytes": ab["frame"], "achieved": ab["frame"] / (ms_step * 1e-3) / 1e9,
                                "frac": ab["frame"] / (ms_step * 1e-3) / 1e9 / peak},
             "clocks": clocks,
